@@ -1,0 +1,279 @@
+"""gpuvoxels_b200 — B200-native Voxelyze step engine behind the gpuVoxels interfaces.
+
+Python here is only a binding over the C ABI in include/vx3b200.h (libvx3b200.so, built from
+gpuvoxels_b200/csrc by __graft_entry__.build()).  Names mirror the reference:
+
+  Model               ~ CVX_Sim::ReadVXA/Import + CVoxelyze builder calls   (Voxelyze3/src/VXA/VX_Sim.cpp, old/Voxelyze.cpp)
+  Context             ~ VX3_VoxelyzeKernel[] on one device + CUDA_Simulation (VX3/VX3_SimulationManager.cu:11-121, 384-458)
+  SimulationManager   ~ VX3_SimulationManager                              (VX3/VX3_SimulationManager.cuh:15-46)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import FP32, FP64, WorldDesc, WorldResult  # noqa: F401
+
+__all__ = ["Model", "Context", "SimulationManager", "FP32", "FP64", "VX3Error", "lib"]
+
+
+class VX3Error(RuntimeError):
+    pass
+
+
+def lib():
+    return _abi.load()
+
+
+def _check(rc, what):
+    if rc < 0:
+        raise VX3Error(f"{what}: {lib().vx3b_last_error().decode(errors='replace')} (status {rc})")
+    return rc
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+class Model:
+    """Host model of one world.  Build from VXA(+VXD) text or with CVoxelyze-style calls."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self._desc = None
+
+    # -- construction ---------------------------------------------------------------------
+    @classmethod
+    def from_vxa(cls, vxa_text, vxd_text=None):
+        h = C.c_void_p()
+        a = vxa_text.encode() if isinstance(vxa_text, str) else vxa_text
+        d = None if vxd_text is None else (vxd_text.encode() if isinstance(vxd_text, str) else vxd_text)
+        _check(lib().vx3b_model_from_vxa(a, d, C.byref(h)), "vx3b_model_from_vxa")
+        return cls(h)
+
+    @classmethod
+    def from_files(cls, vxa_path, vxd_path=None):
+        h = C.c_void_p()
+        _check(lib().vx3b_model_from_files(os.fsencode(vxa_path), None if vxd_path is None else os.fsencode(vxd_path), C.byref(h)),
+               "vx3b_model_from_files")
+        return cls(h)
+
+    @classmethod
+    def new(cls, vox_size):
+        h = C.c_void_p()
+        _check(lib().vx3b_model_new(float(vox_size), C.byref(h)), "vx3b_model_new")
+        return cls(h)
+
+    def add_material(self, youngs_modulus, density, **params):
+        self._desc = None
+        m = _check(lib().vx3b_model_add_material(self._h, float(youngs_modulus), float(density)), "vx3b_model_add_material")
+        for k, v in params.items():
+            self.set_material_param(m, k, v)
+        return m
+
+    def set_material_param(self, mat, name, value):
+        self._desc = None
+        _check(lib().vx3b_model_set_material_param(self._h, mat, name.encode(), float(value)), "vx3b_model_set_material_param")
+
+    def set_voxel(self, mat, ix, iy, iz):
+        self._desc = None
+        return _check(lib().vx3b_model_set_voxel(self._h, mat, ix, iy, iz), "vx3b_model_set_voxel")
+
+    def set_fixed(self, ix, iy, iz, dof_mask=_abi.DOF_ALL, translation=None, rotation=None):
+        self._desc = None
+        t = None if translation is None else np.ascontiguousarray(translation, dtype=np.float64)
+        r = None if rotation is None else np.ascontiguousarray(rotation, dtype=np.float64)
+        _check(lib().vx3b_model_set_fixed(self._h, ix, iy, iz, dof_mask, _dp(t), _dp(r)), "vx3b_model_set_fixed")
+
+    def set_force(self, ix, iy, iz, force=None, moment=None):
+        self._desc = None
+        f = None if force is None else np.ascontiguousarray(force, dtype=np.float64)
+        m = None if moment is None else np.ascontiguousarray(moment, dtype=np.float64)
+        _check(lib().vx3b_model_set_force(self._h, ix, iy, iz, _dp(f), _dp(m)), "vx3b_model_set_force")
+
+    def set_world_param(self, name, value):
+        self._desc = None
+        _check(lib().vx3b_model_set_world_param(self._h, name.encode(), float(value)), "vx3b_model_set_world_param")
+
+    def finalize(self):
+        _check(lib().vx3b_model_finalize(self._h), "vx3b_model_finalize")
+        self._desc = None
+        return self
+
+    # -- access ---------------------------------------------------------------------------
+    @property
+    def desc(self):
+        if self._desc is None:
+            d = WorldDesc()
+            rc = lib().vx3b_model_desc(self._h, C.byref(d))
+            if rc == _abi_err_state():
+                self.finalize()
+                rc = lib().vx3b_model_desc(self._h, C.byref(d))
+            _check(rc, "vx3b_model_desc")
+            self._desc = d
+        return self._desc
+
+    @property
+    def num_voxels(self):
+        return self.desc.num_voxels
+
+    @property
+    def num_links(self):
+        return self.desc.num_links
+
+    def array(self, name):
+        """numpy copy of one of the flat arrays of the world description."""
+        d = self.desc
+        nv, nl = d.num_voxels, d.num_links
+        shapes = {
+            "lattice": (nv, 3), "voxel_mat": (nv,), "phase_offset": (nv,), "base_cilia": (nv, 3), "shift_cilia": (nv, 3),
+            "dof_fixed": (nv,), "ext_force": (nv, 3), "ext_moment": (nv, 3), "ext_translation": (nv, 3), "ext_rotation": (nv, 3),
+            "link_neg": (nl,), "link_pos": (nl,), "link_axis": (nl,), "link_mat": (nl,),
+        }
+        ptr = getattr(d, name)
+        shape = shapes[name]
+        n = int(np.prod(shape))
+        if n == 0 or not ptr:
+            return np.zeros(shape, dtype=np.ctypeslib.as_array(ptr, (1,)).dtype if ptr else np.float64)
+        return np.ctypeslib.as_array(ptr, (n,)).reshape(shape).copy()
+
+    def voxel_materials(self):
+        d = self.desc
+        return [d.voxel_mats[i] for i in range(d.num_voxel_mats)]
+
+    def link_materials(self):
+        d = self.desc
+        return [d.link_mats[i] for i in range(d.num_link_mats)]
+
+    def merged_vxa(self):
+        need = C.c_int64()
+        lib().vx3b_model_merged_vxa(self._h, None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        lib().vx3b_model_merged_vxa(self._h, buf, need.value, None)
+        return buf.value.decode()
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().vx3b_model_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def _abi_err_state():
+    return -5
+
+
+class Context:
+    """One device context: a batch of worlds resident in HBM, stepped by the CUDA engine."""
+
+    def __init__(self, device=0, precision=FP32):
+        self._h = C.c_void_p()
+        self._n = 0
+        self._models = []
+        _check(lib().vx3b_ctx_create(int(device), int(precision), C.byref(self._h)), "vx3b_ctx_create")
+        self.precision = precision
+
+    def set_option(self, name, value):
+        _check(lib().vx3b_ctx_set_option(self._h, name.encode(), float(value)), "vx3b_ctx_set_option")
+
+    def set_stream(self, stream):
+        _check(lib().vx3b_ctx_set_stream(self._h, int(stream)), "vx3b_ctx_set_stream")
+
+    def upload(self, models):
+        models = list(models)
+        arr = (WorldDesc * len(models))(*[m.desc for m in models])
+        _check(lib().vx3b_batch_upload(self._h, arr, len(models)), "vx3b_batch_upload")
+        self._n = len(models)
+        self._models = models  # keep host arrays alive (the library copies, but descs point into them)
+        self._nv = [m.num_voxels for m in models]
+        self._nl = [m.num_links for m in models]
+
+    def run(self, max_steps, use_stop_formula=False):
+        _check(lib().vx3b_batch_run(self._h, int(max_steps), 1 if use_stop_formula else 0), "vx3b_batch_run")
+
+    def results(self):
+        out = (WorldResult * self._n)()
+        _check(lib().vx3b_batch_results(self._h, out), "vx3b_batch_results")
+        return list(out)
+
+    def read_state(self, world=0):
+        nv = self._nv[world]
+        pos, orient = np.empty((nv, 3)), np.empty((nv, 4))
+        lin, ang = np.empty((nv, 3)), np.empty((nv, 3))
+        _check(lib().vx3b_batch_read_state(self._h, world, _dp(pos), _dp(orient), _dp(lin), _dp(ang)), "vx3b_batch_read_state")
+        return {"pos": pos, "orient": orient, "linMom": lin, "angMom": ang}
+
+    def read_initial_pos(self, world=0):
+        pos = np.empty((self._nv[world], 3))
+        _check(lib().vx3b_batch_read_initial_pos(self._h, world, _dp(pos)), "vx3b_batch_read_initial_pos")
+        return pos
+
+    def read_links(self, world=0):
+        nl = self._nl[world]
+        p2, a1, a2 = np.empty((nl, 3)), np.empty((nl, 3)), np.empty((nl, 3))
+        fl = np.empty((nl,), dtype=np.int32)
+        _check(lib().vx3b_batch_read_links(self._h, world, _dp(p2), _dp(a1), _dp(a2), fl.ctypes.data_as(C.POINTER(C.c_int32))),
+               "vx3b_batch_read_links")
+        return {"pos2": p2, "angle1v": a1, "angle2v": a2, "flags": fl}
+
+    def collision_pairs(self, world=0, capacity=1 << 20):
+        buf = np.empty((capacity, 2), dtype=np.int32)
+        n = C.c_int32(capacity)
+        _check(lib().vx3b_batch_collision_pairs(self._h, world, buf.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)),
+               "vx3b_batch_collision_pairs")
+        if n.value > capacity:
+            return self.collision_pairs(world, n.value)
+        return buf[: n.value].copy()
+
+    def timing(self):
+        ms, k = C.c_float(), C.c_int64()
+        _check(lib().vx3b_ctx_timing(self._h, C.byref(ms), C.byref(k)), "vx3b_ctx_timing")
+        return ms.value, k.value
+
+    def total_voxel_steps(self):
+        return lib().vx3b_ctx_total_voxel_steps(self._h)
+
+    def close(self):
+        if self._h:
+            lib().vx3b_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SimulationManager:
+    """Mirror of VX3_SimulationManager(sub_batches, base, input_dir, num_devices): start() is blocking and
+    leaves h_results sorted by fitness descending, NaN last (VX3_SimulationResult.h:26-33)."""
+
+    def __init__(self, sub_batches, base, input_dir, num_of_devices, precision=FP32):
+        self.sub_batches = [list(b) for b in sub_batches]
+        self.base = base
+        self.input_dir = input_dir
+        self.num_of_devices = num_of_devices
+        self.precision = precision
+        self.h_results = []
+
+    def start(self):
+        import math
+        self.h_results = []
+        for device_index, files in enumerate(self.sub_batches):
+            if not files:
+                continue
+            models = [Model.from_files(self.base, os.path.join(self.input_dir, f)) for f in files]
+            ctx = Context(device_index, self.precision)
+            ctx.upload(models)
+            ctx.run(1000000, use_stop_formula=True)
+            for f, m, r in zip(files, models, ctx.results()):
+                self.h_results.append({"vxa_filename": os.path.basename(f), "result": r, "model": m,
+                                       "pos": ctx.read_state(len(self.h_results) % len(models))["pos"] if m.desc.save_position_of_all_voxels else None})
+            ctx.close()
+        self.h_results.sort(key=lambda e: (math.isnan(e["result"].fitness_score), -e["result"].fitness_score
+                                           if not math.isnan(e["result"].fitness_score) else 0.0))
+        return self.h_results

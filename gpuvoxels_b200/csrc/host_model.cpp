@@ -1,0 +1,999 @@
+#include "host_model.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <sstream>
+
+namespace vx3b {
+
+// ------------------------------------------------------------------------------------------
+// lattice / link construction
+// ------------------------------------------------------------------------------------------
+
+void HostModel::ensureExt() {
+    size_t nv = voxelMat.size();
+    dofFixed.resize(nv, 0);
+    extForce.resize(nv * 3, 0.0f);
+    extMoment.resize(nv * 3, 0.0f);
+    extTranslation.resize(nv * 3, 0.0);
+    extRotation.resize(nv * 3, 0.0);
+}
+
+int HostModel::setVoxel(int mat, int ix, int iy, int iz, std::string *err) {
+    if (mat < 0 || mat >= (int)mats.size()) {
+        if (err)
+            *err = "set_voxel: no such material index " + std::to_string(mat);
+        return -1;
+    }
+    if (ix < -32768 || ix > 32767 || iy < -32768 || iy > 32767 || iz < -32768 || iz > 32767) {
+        if (err)
+            *err = "set_voxel: lattice index out of the short range the reference uses (VX3_Voxel.h:272)";
+        return -1;
+    }
+    finalized = false;
+    int existing = voxelAt(ix, iy, iz);
+    if (existing >= 0) { // CVoxelyze::replaceVoxel: new material, links re-derived at finalize (link order kept)
+        voxelMat[existing] = mat;
+        return existing;
+    }
+    int v = numVoxels();
+    lattice.insert(lattice.end(), {(int16_t)ix, (int16_t)iy, (int16_t)iz});
+    voxelMat.push_back(mat);
+    phaseOffset.push_back(0.0);
+    baseCilia.insert(baseCilia.end(), 3, 0.0);
+    shiftCilia.insert(shiftCilia.end(), 3, 0.0);
+    occupied[std::make_tuple(ix, iy, iz)] = v;
+    ensureExt();
+    // links to already-present neighbours, directions X_POS,X_NEG,Y_POS,Y_NEG,Z_POS,Z_NEG
+    // (CVoxelyze::addVoxel, old/Voxelyze.cpp:439-461; end ordering CVX_Link ctor old/VX_Link.cpp:20-49)
+    static const int off[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    for (int dir = 0; dir < 6; dir++) {
+        int nx = ix + off[dir][0], ny = iy + off[dir][1], nz = iz + off[dir][2];
+        int o = voxelAt(nx, ny, nz);
+        if (o < 0)
+            continue;
+        int axis = dir / 2;
+        bool positive = (dir % 2) == 0; // neighbour lies on our positive side -> we are the negative end
+        int neg = positive ? v : o, pos = positive ? o : v;
+        auto key = std::make_tuple(axis, (int)lattice[neg * 3], (int)lattice[neg * 3 + 1], (int)lattice[neg * 3 + 2]);
+        if (linkAt.count(key))
+            continue;
+        linkAt[key] = (int)linkNeg.size();
+        linkNeg.push_back(neg);
+        linkPos.push_back(pos);
+        linkAxis.push_back((uint8_t)axis);
+        linkMat.push_back(-1); // resolved at finalize (materials may still change)
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// material derivation (float arithmetic mirrors the reference expression by expression)
+// ------------------------------------------------------------------------------------------
+
+static VX3B_VoxelMaterial derive_voxel_material(const MatInput &in, float nu, double nomSize, float gravMult) {
+    VX3B_VoxelMaterial o;
+    memset(&o, 0, sizeof(o));
+    o.E = in.E;
+    o.nu = nu;
+    o.rho = in.rho;
+    o.alphaCTE = in.alphaCTE;
+    o.muStatic = in.muStatic;
+    o.muKinetic = in.muKinetic;
+    o.zetaInternal = in.zetaInternal;
+    o.zetaGlobal = in.zetaGlobal;
+    o.zetaCollision = in.zetaCollision;
+    o.epsilonFail = in.epsilonFail;
+    o.gravMult = gravMult;
+    o.nomSize = nomSize;
+    o.Cilia = in.Cilia;
+    o.matid = in.matid;
+    o.fixed = in.fixed;
+    o.isTarget = in.isTarget;
+    o.isMeasured = in.isMeasured;
+    o.sticky = in.sticky;
+    o.linear = 1;
+    // CVX_MaterialVoxel::updateDerived (old/VX_MaterialVoxel.cpp:58-80)
+    double volume = nomSize * nomSize * nomSize;
+    o.mass = (float)(volume * in.rho);
+    o.momentInertia = (float)(o.mass * nomSize * nomSize / 6.0f);
+    if (volume == 0 || o.mass == 0 || o.momentInertia == 0) {
+        o.massInverse = o.sqrtMass = o.momentInertiaInverse = o._2xSqMxExS = o._2xSqIxExSxSxS = 0.0f;
+        return o;
+    }
+    o.massInverse = 1.0f / o.mass;
+    o.sqrtMass = sqrtf(o.mass);
+    o.momentInertiaInverse = 1.0f / o.momentInertia;
+    o._2xSqMxExS = (float)(2.0f * sqrt(o.mass * in.E * nomSize));
+    o._2xSqIxExSxSxS = (float)(2.0f * sqrt(o.momentInertia * in.E * nomSize * nomSize * nomSize));
+    return o;
+}
+
+static VX3B_LinkMaterial derive_link_material(const VX3B_VoxelMaterial &m1, const MatInput &i1, const VX3B_VoxelMaterial &m2,
+                                              const MatInput &i2, int a, int b) {
+    VX3B_LinkMaterial o;
+    memset(&o, 0, sizeof(o));
+    o.mat1 = a;
+    o.mat2 = b;
+    // CVX_MaterialLink::updateAll (old/VX_MaterialLink.cpp:53-117), linear ∘ linear branch
+    double nomSize = 0.5 * (m1.nomSize + m2.nomSize);
+    float f1 = i1.sigmaFail, f2 = i2.sigmaFail, stressFail;
+    if (f1 == -1.0f)
+        stressFail = f2;
+    else if (f2 == -1.0f)
+        stressFail = f1;
+    else
+        stressFail = f1 < f2 ? f1 : f2;
+    o.E = 2.0f * m1.E * m2.E / (m1.E + m2.E);
+    o.epsilonFail = (stressFail == -1.0f) ? -1.0f : stressFail / o.E; // setModelLinear, old/VX_Material.cpp:373-401
+    o.nu = 0.0f;                                                     // both ends have nu == 0 (checked in finalize)
+    o.eHat = o.E / ((1 - 2 * o.nu) * (1 + o.nu));
+    // CVX_MaterialLink::updateDerived (old/VX_MaterialLink.cpp:119-139)
+    float L = (float)nomSize;
+    o.a1 = o.E * L;
+    o.a2 = o.E * L * L * L / (12.0f * (1 + o.nu));
+    o.b1 = o.E * L;
+    o.b2 = o.E * L * L / 2.0f;
+    o.b3 = o.E * L * L * L / 6.0f;
+    o.sqA1 = sqrtf(o.a1);
+    o.sqA2xIp = sqrtf(o.a2 * L * L / 6.0f);
+    o.sqB1 = sqrtf(o.b1);
+    o.sqB2xFMp = sqrtf(o.b2 * L / 2.0f);
+    o.sqB3xIp = sqrtf(o.b3 * L * L / 6.0f);
+    return o;
+}
+
+bool HostModel::finalize(std::string *err) {
+    voxelMats.clear();
+    for (auto &m : mats) {
+        float nu = volumeEffects ? m.nuMemory : 0.0f; // CVX_Sim::EnableVolumeEffects, VX_Sim.cpp:445-458
+        if (nu != 0.0f) {
+            if (err)
+                *err = "Poisson/volume effects (VolumeEffectsEnabled with nu != 0) are not on the fused path yet (SURVEY.md §8f-4)";
+            return false;
+        }
+        voxelMats.push_back(derive_voxel_material(m, nu, voxSize, gravMult));
+    }
+    linkMatPairs.clear();
+    linkMats.clear();
+    for (size_t l = 0; l < linkNeg.size(); l++) {
+        // CVoxelyze::combinedMaterial (old/Voxelyze.cpp:614-628): first use creates, later uses find (either order)
+        int a = voxelMat[linkNeg[l]], b = voxelMat[linkPos[l]];
+        int found = -1;
+        for (size_t k = 0; k < linkMatPairs.size(); k++)
+            if ((linkMatPairs[k].first == a && linkMatPairs[k].second == b) || (linkMatPairs[k].first == b && linkMatPairs[k].second == a)) {
+                found = (int)k;
+                break;
+            }
+        if (found < 0) {
+            found = (int)linkMatPairs.size();
+            linkMatPairs.emplace_back(a, b);
+            linkMats.push_back(derive_link_material(voxelMats[a], mats[a], voxelMats[b], mats[b], a, b));
+        }
+        linkMat[l] = found;
+    }
+    auto pad = [](std::vector<VX3B_Token> &t) {
+        if (t.size() > VX3B_MAX_TOKENS)
+            return false;
+        VX3B_Token e;
+        memset(&e, 0, sizeof(e));
+        t.resize(VX3B_MAX_TOKENS, e);
+        return true;
+    };
+    if (!pad(stopCondition) || !pad(fitness) || !pad(forceField[0]) || !pad(forceField[1]) || !pad(forceField[2])) {
+        if (err)
+            *err = "formula longer than VX3B_MAX_TOKENS";
+        return false;
+    }
+    ensureExt();
+    finalized = true;
+    return true;
+}
+
+void HostModel::fillDesc(VX3B_WorldDesc *d) const {
+    memset(d, 0, sizeof(*d));
+    d->num_voxels = numVoxels();
+    d->num_links = (int)linkNeg.size();
+    d->num_voxel_mats = (int)voxelMats.size();
+    d->num_link_mats = (int)linkMats.size();
+    d->vox_size = voxSize;
+    d->lattice = lattice.data();
+    d->voxel_mat = voxelMat.data();
+    d->phase_offset = phaseOffset.data();
+    d->base_cilia = baseCilia.data();
+    d->shift_cilia = shiftCilia.data();
+    d->dof_fixed = dofFixed.data();
+    d->ext_force = extForce.data();
+    d->ext_moment = extMoment.data();
+    d->ext_translation = extTranslation.data();
+    d->ext_rotation = extRotation.data();
+    d->link_neg = linkNeg.data();
+    d->link_pos = linkPos.data();
+    d->link_axis = linkAxis.data();
+    d->link_mat = linkMat.data();
+    d->voxel_mats = voxelMats.data();
+    d->link_mats = linkMats.data();
+    d->dt_frac = dtFrac;
+    d->floor_enabled = floorEnabled;
+    d->vary_temp_enabled = varyTempEnabled;
+    d->temp_amplitude = tempAmplitude;
+    d->temp_period = tempPeriod;
+    d->initial_temp = initialTemp;
+    d->enable_collision = enableCollision;
+    d->enable_cilia = enableCilia;
+    d->enable_expansion = enableExpansion;
+    d->vx2_compat = vx2Compat;
+    d->max_dist_in_voxel_lengths_to_count_as_pair = maxDistPair;
+    d->save_position_of_all_voxels = savePositions;
+    memcpy(d->stop_condition, stopCondition.data(), sizeof(d->stop_condition));
+    memcpy(d->fitness, fitness.data(), sizeof(d->fitness));
+    for (int k = 0; k < 3; k++)
+        memcpy(d->force_field[k], forceField[k].data(), sizeof(d->force_field[k]));
+}
+
+// ------------------------------------------------------------------------------------------
+// formulas
+// ------------------------------------------------------------------------------------------
+
+bool parse_math_tree(const XmlNode *root, std::vector<VX3B_Token> &out, std::string *err) {
+    out.clear();
+    if (!root)
+        return true; // missing formula: empty program (the reference leaves token[0]=mtEND)
+    static const std::pair<const char *, int> ops[] = {
+        {"mtEND", VX3B_MT_END},       {"mtCONST", VX3B_MT_CONST},   {"mtE", VX3B_MT_E},
+        {"mtPI", VX3B_MT_PI},         {"mtVAR", VX3B_MT_VAR},       {"mtADD", VX3B_MT_ADD},
+        {"mtSUB", VX3B_MT_SUB},       {"mtMUL", VX3B_MT_MUL},       {"mtDIV", VX3B_MT_DIV},
+        {"mtPOW", VX3B_MT_POW},       {"mtSQRT", VX3B_MT_SQRT},     {"mtSIN", VX3B_MT_SIN},
+        {"mtCOS", VX3B_MT_COS},       {"mtTAN", VX3B_MT_TAN},       {"mtATAN", VX3B_MT_ATAN},
+        {"mtLOG", VX3B_MT_LOG},       {"mtINT", VX3B_MT_INT},       {"mtABS", VX3B_MT_ABS},
+        {"mtNOT", VX3B_MT_NOT},       {"mtGREATERTHAN", VX3B_MT_GREATERTHAN}, {"mtLESSTHAN", VX3B_MT_LESSTHAN},
+        {"mtAND", VX3B_MT_AND},       {"mtOR", VX3B_MT_OR},         {"mtNORMALCDF", VX3B_MT_NORMALCDF}};
+    static const char *vars[] = {"x", "y", "z", "hit", "t", "angle", "targetCloseness", "numClosePairs", "num_voxel"};
+    // level-order walk, tokens collected then reversed, END last (VX3_SimulationManager.cu:157-186)
+    std::vector<VX3B_Token> level;
+    std::deque<const XmlNode *> frontier;
+    frontier.push_back(root);
+    while (!frontier.empty()) {
+        const XmlNode *t = frontier.front();
+        frontier.pop_front();
+        for (auto &c : t->children) {
+            VX3B_Token tok;
+            memset(&tok, 0, sizeof(tok));
+            int op = -1;
+            for (auto &o : ops)
+                if (c->name == o.first)
+                    op = o.second;
+            if (op < 0) {
+                if (err)
+                    *err = "formula: token operation not implemented: " + c->name;
+                return false;
+            }
+            tok.op = op;
+            std::string val = xml_trim(c->text);
+            if (op == VX3B_MT_VAR) {
+                int id = -1;
+                for (int k = 0; k < 9; k++)
+                    if (val == vars[k])
+                        id = k;
+                if (id < 0) {
+                    if (err)
+                        *err = "formula: no such variable: " + val;
+                    return false;
+                }
+                tok.value = id;
+            } else if (op == VX3B_MT_CONST) {
+                char *end = nullptr;
+                tok.value = strtod(val.c_str(), &end);
+                if (end == val.c_str()) {
+                    if (err)
+                        *err = "formula: mtCONST with no number";
+                    return false;
+                }
+            }
+            level.push_back(tok);
+            frontier.push_back(c.get());
+        }
+    }
+    out.assign(level.rbegin(), level.rend());
+    VX3B_Token e;
+    memset(&e, 0, sizeof(e));
+    out.push_back(e);
+    if (out.size() > VX3B_MAX_TOKENS) {
+        if (err)
+            *err = "formula longer than VX3B_MAX_TOKENS tokens";
+        return false;
+    }
+    return true;
+}
+
+double eval_math_tree(const VX3B_Token *tok, double x, double y, double z, double hit, double t, double angle, double closeness,
+                      int numClosePairs, int numVoxel) {
+    double values[VX3B_MAX_TOKENS + 1];
+    values[0] = 0.0; // empty program evaluates to 0 (the reference reads an uninitialised slot here)
+    int vc = 0, pc = 0;
+    for (int i = 0; i < VX3B_MAX_TOKENS; i++) {
+        double v = 0;
+        switch (tok[i].op) {
+        case VX3B_MT_END:
+            return values[pc];
+        case VX3B_MT_CONST:
+            v = tok[i].value;
+            break;
+        case VX3B_MT_E:
+            v = 2.71828182845904523536;
+            break;
+        case VX3B_MT_PI:
+            v = 3.14159265358979323846;
+            break;
+        case VX3B_MT_VAR: {
+            double id = tok[i].value;
+            v = id < 0.5 ? x : id < 1.5 ? y : id < 2.5 ? z : id < 3.5 ? hit : id < 4.5 ? t : id < 5.5 ? angle : id < 6.5 ? closeness
+                : id < 7.5 ? (double)numClosePairs : (double)numVoxel;
+            break;
+        }
+        case VX3B_MT_SIN: v = sin(values[pc]); pc++; break;
+        case VX3B_MT_COS: v = cos(values[pc]); pc++; break;
+        case VX3B_MT_TAN: v = tan(values[pc]); pc++; break;
+        case VX3B_MT_ATAN: v = atan(values[pc]); pc++; break;
+        case VX3B_MT_LOG: v = log(values[pc]); pc++; break;
+        case VX3B_MT_INT: v = rint(values[pc]); pc++; break;
+        case VX3B_MT_NORMALCDF: v = 0.5 * erfc(-values[pc] * 0.70710678118654752440); pc++; break;
+        case VX3B_MT_SQRT: v = sqrt(values[pc]); pc++; break;
+        case VX3B_MT_ABS: v = fabs(values[pc]); pc++; break;
+        case VX3B_MT_NOT: v = !values[pc]; pc++; break;
+        case VX3B_MT_ADD: v = values[pc + 1] + values[pc]; pc += 2; break;
+        case VX3B_MT_SUB: v = values[pc + 1] - values[pc]; pc += 2; break;
+        case VX3B_MT_MUL: v = values[pc + 1] * values[pc]; pc += 2; break;
+        case VX3B_MT_DIV: v = values[pc + 1] / values[pc]; pc += 2; break;
+        case VX3B_MT_POW: v = pow(values[pc + 1], values[pc]); pc += 2; break;
+        case VX3B_MT_GREATERTHAN: v = values[pc + 1] > values[pc]; pc += 2; break;
+        case VX3B_MT_LESSTHAN: v = values[pc + 1] < values[pc]; pc += 2; break;
+        case VX3B_MT_AND: v = values[pc + 1] && values[pc]; pc += 2; break;
+        case VX3B_MT_OR: v = values[pc + 1] || values[pc]; pc += 2; break;
+        default:
+            return -1;
+        }
+        if (pc > vc)
+            return -1; // token sequence error
+        values[vc++] = v;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// VXA / VXD
+// ------------------------------------------------------------------------------------------
+
+bool merge_vxd(XmlNode &baseDoc, const XmlNode &vxdDoc, std::string *err) {
+    const XmlNode *vxd = vxdDoc.child("VXD");
+    if (!vxd)
+        vxd = &vxdDoc; // ptree_merge: source.get_child("VXD", source)
+    for (auto &c : vxd->children) {
+        const std::string *rep = c->attr("replace");
+        if (!rep || rep->empty())
+            continue;
+        xml_put_child(baseDoc, *rep, c->clone());
+    }
+    (void)err;
+    return true;
+}
+
+namespace {
+
+bool get_text(const XmlNode *parent, const char *tag, std::string *out) {
+    if (!parent)
+        return false;
+    const XmlNode *c = parent->child(tag);
+    if (!c)
+        return false;
+    std::string t = xml_trim(c->text);
+    if (t.empty())
+        return false; // CXML_Rip::FindLoadElement fails on an element without a text child
+    *out = t;
+    return true;
+}
+double get_double(const XmlNode *p, const char *tag, double dflt) {
+    std::string t;
+    return get_text(p, tag, &t) ? atof(t.c_str()) : dflt;
+}
+float get_float(const XmlNode *p, const char *tag, float dflt) {
+    std::string t;
+    return get_text(p, tag, &t) ? (float)atof(t.c_str()) : dflt;
+}
+int get_int(const XmlNode *p, const char *tag, int dflt) {
+    std::string t;
+    return get_text(p, tag, &t) ? atoi(t.c_str()) : dflt;
+}
+bool get_bool(const XmlNode *p, const char *tag, bool dflt) { return get_int(p, tag, dflt ? 1 : 0) != 0; }
+
+// boost ptree get<bool>/get<int> on the merged tree (VX3_SimulationManager.cu:323-375)
+int ptree_int(const XmlNode &vxa, const char *path, int dflt) {
+    const XmlNode *n = vxa.find(path);
+    if (!n)
+        return dflt;
+    std::string t = xml_trim(n->text);
+    if (t.empty())
+        return dflt;
+    if (t == "true")
+        return 1;
+    if (t == "false")
+        return 0;
+    return atoi(t.c_str());
+}
+double ptree_double(const XmlNode &vxa, const char *path, double dflt) {
+    const XmlNode *n = vxa.find(path);
+    if (!n)
+        return dflt;
+    std::string t = xml_trim(n->text);
+    return t.empty() ? dflt : atof(t.c_str());
+}
+
+std::vector<std::string> split_commas(const std::string &s) { // split(RawData, ',') as std::getline does
+    std::vector<std::string> out;
+    std::stringstream ss(s);
+    std::string item;
+    while (std::getline(ss, item, ','))
+        out.push_back(item);
+    return out;
+}
+
+std::vector<const XmlNode *> layers_of(const XmlNode *parent) {
+    std::vector<const XmlNode *> v;
+    if (parent)
+        for (auto &c : parent->children)
+            if (c->name == "Layer")
+                v.push_back(c.get());
+    return v;
+}
+
+} // namespace
+
+std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char *vxdText, std::string *err) {
+    std::string perr;
+    auto doc = xml_parse(vxaText, &perr);
+    if (!doc) {
+        if (err)
+            *err = "VXA: " + perr;
+        return nullptr;
+    }
+    if (vxdText && *vxdText) {
+        auto vxd = xml_parse(vxdText, &perr);
+        if (!vxd) {
+            if (err)
+                *err = "VXD: " + perr;
+            return nullptr;
+        }
+        merge_vxd(*doc, *vxd, err);
+    }
+    const XmlNode *vxa = doc->child("VXA");
+    if (!vxa) {
+        if (err)
+            *err = "no <VXA> root element";
+        return nullptr;
+    }
+    auto M = std::make_unique<HostModel>();
+    M->mergedVxa = xml_write(*vxa, true);
+
+    // ---- Simulator (CVX_Sim::ReadXML, VX_Sim.cpp:185-294) + VX3-only settings (VX3_SimulationManager.cu:323-375)
+    const XmlNode *sim = vxa->child("Simulator");
+    float bondZ = 0.1f, colZ = 1.0f, slowZ = 1.0f;
+    if (sim) {
+        if (const XmlNode *integ = sim->child("Integration"))
+            M->dtFrac = get_double(integ, "DtFrac", 0.9);
+        if (const XmlNode *damp = sim->child("Damping")) {
+            bondZ = get_float(damp, "BondDampingZ", 0.1f);
+            colZ = get_float(damp, "ColDampingZ", 1.0f);
+            slowZ = get_float(damp, "SlowDampingZ", 1.0f);
+        }
+        if (const XmlNode *feat = sim->child("Features"))
+            M->volumeEffects = get_bool(feat, "VolumeEffectsEnabled", false);
+    }
+    M->enableCollision = ptree_int(*vxa, "Simulator.AttachDetach.EnableCollision", 1) != 0;
+    if (ptree_int(*vxa, "Simulator.AttachDetach.EnableAttach", 0) || ptree_int(*vxa, "Simulator.AttachDetach.EnableDetach", 0) ||
+        ptree_int(*vxa, "Simulator.EnableSignals", 0) || ptree_int(*vxa, "Simulator.SecondaryExperiment", 0)) {
+        if (err)
+            *err = "EnableAttach / EnableDetach / EnableSignals / SecondaryExperiment change topology during the run; "
+                   "the static-topology fused path does not run them (SURVEY.md §8f-3)";
+        return nullptr;
+    }
+    M->enableCilia = ptree_int(*vxa, "Simulator.EnableCilia", 0) != 0;
+    M->enableExpansion = ptree_int(*vxa, "Simulator.EnableExpansion", 0) != 0;
+    M->savePositions = ptree_int(*vxa, "Simulator.SavePositionOfAllVoxels", 0) != 0;
+    M->maxDistPair = ptree_double(*vxa, "Simulator.MaxDistInVoxelLengthsToCountAsPair", 0.0);
+    if (!parse_math_tree(vxa->find("Simulator.StopCondition.StopConditionFormula"), M->stopCondition, err) ||
+        !parse_math_tree(vxa->find("Simulator.FitnessFunction"), M->fitness, err) ||
+        !parse_math_tree(vxa->find("Simulator.ForceField.x_forcefield"), M->forceField[0], err) ||
+        !parse_math_tree(vxa->find("Simulator.ForceField.y_forcefield"), M->forceField[1], err) ||
+        !parse_math_tree(vxa->find("Simulator.ForceField.z_forcefield"), M->forceField[2], err))
+        return nullptr;
+
+    // ---- Environment (CVX_Environment::ReadXML, old/VX_Environment.cpp:101-174; ctor defaults :26-35)
+    bool gravEnabled = true, floorEnabled = true;
+    double gravAcc = -9.81;
+    M->tempEnabled = true;
+    const XmlNode *env = vxa->child("Environment");
+    if (env) {
+        if (const XmlNode *bc = env->child("Boundary_Conditions")) {
+            if (get_int(bc, "NumBCs", 0) != 0) {
+                if (err)
+                    *err = "Boundary_Conditions/FRegion are not read by this host model yet; use vx3b_model_set_fixed / set_force";
+                return nullptr;
+            }
+        }
+        if (const XmlNode *g = env->child("Gravity")) {
+            gravEnabled = get_bool(g, "GravEnabled", false);
+            gravAcc = get_double(g, "GravAcc", -9.81);
+            floorEnabled = get_bool(g, "FloorEnabled", false);
+        }
+        if (const XmlNode *th = env->child("Thermal")) {
+            M->tempEnabled = get_bool(th, "TempEnabled", false);
+            M->tempBase = get_double(th, "TempBase", 25);
+            std::string t;
+            if (get_text(th, "TempAmplitude", &t))
+                M->tempAmplitude = atof(t.c_str());
+            else if (get_text(th, "TempAmp", &t))
+                M->tempAmplitude = atof(t.c_str()) - M->tempBase;
+            else
+                M->tempAmplitude = 0;
+            M->varyTempEnabled = get_bool(th, "VaryTempEnabled", false);
+            M->tempPeriod = get_double(th, "TempPeriod", 0.1);
+        }
+    }
+    (void)gravEnabled; // Import applies GravAcc whether or not GravEnabled is set (VX_Sim.cpp:67-68, :485)
+    M->gravMult = (float)(-(float)gravAcc / 9.80665);
+    M->floorEnabled = floorEnabled;
+    // initial temperature: CVX_Sim::UpdateMatTemps at Import (VX_Sim.cpp:146-147, 466-483)
+    if (M->tempEnabled) {
+        if (M->varyTempEnabled)
+            M->initialTemp = (M->tempPeriod == 0) ? (float)(0.0f - M->tempBase) : (float)((float)(M->tempBase + M->tempAmplitude * sin(0.0)) - M->tempBase);
+        else
+            M->initialTemp = (float)((float)(M->tempBase + M->tempAmplitude) - M->tempBase);
+    }
+
+    // ---- VXC (CVX_Object::ReadXML): lattice, palette, structure
+    const XmlNode *vxc = vxa->child("VXC");
+    if (!vxc)
+        vxc = vxa->child("DMF");
+    if (!vxc) {
+        if (err)
+            *err = "no <VXC> element";
+        return nullptr;
+    }
+    M->voxSize = get_double(vxc->child("Lattice"), "Lattice_Dim", 0.001);
+    if (M->voxSize <= 0)
+        M->voxSize = FLT_MIN; // CVX_MaterialVoxel::setNominalSize
+
+    std::vector<int> paletteToMat; // palette slot (1-based) -> model material
+    if (const XmlNode *pal = vxc->child("Palette")) {
+        for (auto &pm : pal->children) {
+            if (pm->name != "Material")
+                continue;
+            MatInput m;
+            m.matid = (int)paletteToMat.size() + 1; // CVX_Object::AddMat: matid = palette index (VX_Object.cpp:486)
+            int matType = get_int(pm.get(), "MatType", 0);
+            const XmlNode *mech = pm->child("Mechanical");
+            if (matType != 0) {
+                if (err)
+                    *err = "palette material with MatType != SINGLE is not supported";
+                return nullptr;
+            }
+            int matModel = get_int(mech, "MatModel", 0);
+            double E = get_double(mech, "Elastic_Mod", 0), failStress = get_double(mech, "Fail_Stress", 0);
+            if (matModel >= 2) {
+                if (err)
+                    *err = "bilinear / data material models are not on the fused path yet (SURVEY.md §8f-4)";
+                return nullptr;
+            }
+            // CVX_Sim::CopyMat (VX_Sim.cpp:368-420) -> CVX_Material::setModelLinear (old/VX_Material.cpp:373-401)
+            m.E = (float)E;
+            if (!(m.E > 0)) {
+                if (err)
+                    *err = "material " + std::to_string(m.matid) + ": Young's modulus must be positive";
+                return nullptr;
+            }
+            if (matModel == 1 && (float)failStress > 0) {
+                m.sigmaFail = (float)failStress;
+                m.epsilonFail = m.sigmaFail / m.E;
+            }
+            float nu = (float)get_double(mech, "Poissons_Ratio", 0);
+            if (nu < 0)
+                nu = 0;
+            if (nu >= 0.5)
+                nu = 0.5 - FLT_EPSILON * 2;
+            m.nuMemory = nu;
+            m.rho = (float)get_double(mech, "Density", 0);
+            if (m.rho <= 0)
+                m.rho = FLT_MIN;
+            m.alphaCTE = (float)get_double(mech, "CTE", 0);
+            m.muStatic = (float)get_double(mech, "uStatic", 0);
+            if (m.muStatic <= 0)
+                m.muStatic = 0;
+            m.muKinetic = (float)get_double(mech, "uDynamic", 0);
+            if (m.muKinetic <= 0)
+                m.muKinetic = 0;
+            m.zetaInternal = bondZ <= 0 ? 0 : bondZ;
+            m.zetaGlobal = slowZ <= 0 ? 0 : slowZ;
+            m.zetaCollision = colZ <= 0 ? 0 : colZ;
+            m.Cilia = get_double(mech, "Cilia", 0);
+            m.fixed = get_int(mech, "Fixed", 0) != 0;
+            m.isTarget = get_int(mech, "isTarget", 0) != 0;
+            m.isMeasured = get_int(mech, "isMeasured", 1);
+            m.sticky = get_int(mech, "Sticky", 0) != 0;
+            paletteToMat.push_back(M->addMaterial(m));
+        }
+    }
+
+    const XmlNode *st = vxc->child("Structure");
+    if (!st) {
+        if (err)
+            *err = "no <Structure> element";
+        return nullptr;
+    }
+    const std::string *comp = st->attr("Compression");
+    if (!comp || *comp != "ASCII_READABLE") {
+        if (err)
+            *err = "Structure Compression must be ASCII_READABLE (got " + (comp ? *comp : std::string("none")) + ")";
+        return nullptr;
+    }
+    int X = get_int(st, "X_Voxels", 1), Y = get_int(st, "Y_Voxels", 1), Z = get_int(st, "Z_Voxels", 1);
+    auto dataLayers = layers_of(st->child("Data"));
+    if ((int)dataLayers.size() < Z) {
+        if (err)
+            *err = "Structure/Data has fewer <Layer> elements than Z_Voxels";
+        return nullptr;
+    }
+    std::vector<int> cell((size_t)X * Y * Z, 0);
+    for (int z = 0; z < Z; z++) {
+        const std::string &raw = dataLayers[z]->text; // CDATA content, untrimmed like tinyxml's CDATA text
+        std::string t = raw.size() == (size_t)X * Y ? raw : xml_trim(raw);
+        if (t.size() != (size_t)X * Y) {
+            if (err)
+                *err = "Voxel layer data not present or does not match expected size (layer " + std::to_string(z) + ")";
+            return nullptr;
+        }
+        for (int k = 0; k < X * Y; k++)
+            cell[(size_t)X * Y * z + k] = (int)(signed char)(t[k] - 48);
+    }
+    // per-voxel CSV layers, indexed over present voxels only (VX_Object.cpp:1851-1959)
+    std::vector<double> phase, baseC, shiftC;
+    auto read_scalar_layers = [&](const char *tag, std::vector<double> &dst) {
+        const XmlNode *n = st->child(tag);
+        if (!n)
+            return;
+        auto ls = layers_of(n);
+        for (int z = 0; z < Z && z < (int)ls.size(); z++) {
+            auto arr = split_commas(ls[z]->text);
+            for (int k = 0; k < X * Y; k++)
+                if (cell[(size_t)X * Y * z + k] > 0)
+                    dst.push_back((int)arr.size() > k ? atof(arr[k].c_str()) : 0.0);
+        }
+    };
+    auto read_vec3_layers = [&](const char *tag, std::vector<double> &dst) {
+        const XmlNode *n = st->child(tag);
+        if (!n)
+            return;
+        auto ls = layers_of(n);
+        for (int z = 0; z < Z && z < (int)ls.size(); z++) {
+            auto arr = split_commas(ls[z]->text);
+            for (int k = 0; k < X * Y; k++)
+                if (cell[(size_t)X * Y * z + k] > 0) {
+                    if ((int)arr.size() <= k * 3)
+                        dst.insert(dst.end(), 3, 0.0);
+                    else
+                        for (int c = 0; c < 3; c++)
+                            dst.push_back((int)arr.size() > 3 * k + c ? atof(arr[3 * k + c].c_str()) : 0.0);
+                }
+        }
+    };
+    read_scalar_layers("PhaseOffset", phase);
+    read_vec3_layers("BaseCiliaForce", baseC);
+    read_vec3_layers("ShiftCiliaForce", shiftC);
+
+    // voxels in x-fastest, y, z order (VX_Sim.cpp:92-107)
+    int counter = 0;
+    for (int z = 0; z < Z; z++)
+        for (int y = 0; y < Y; y++)
+            for (int x = 0; x < X; x++) {
+                int c = cell[(size_t)X * Y * z + (size_t)X * y + x];
+                if (c <= 0)
+                    continue;
+                if (c > (int)paletteToMat.size()) {
+                    if (err)
+                        *err = "Structure refers to material " + std::to_string(c) + " which is not in the palette";
+                    return nullptr;
+                }
+                int v = M->setVoxel(paletteToMat[c - 1], x, y, z, err);
+                if (v < 0)
+                    return nullptr;
+                if ((int)phase.size() > counter)
+                    M->phaseOffset[v] = phase[counter];
+                if ((int)baseC.size() > counter * 3 + 2)
+                    for (int k = 0; k < 3; k++)
+                        M->baseCilia[v * 3 + k] = baseC[counter * 3 + k];
+                if ((int)shiftC.size() > counter * 3 + 2)
+                    for (int k = 0; k < 3; k++)
+                        M->shiftCilia[v * 3 + k] = shiftC[counter * 3 + k];
+                counter++;
+            }
+    if (!M->finalize(err))
+        return nullptr;
+    return M;
+}
+
+} // namespace vx3b
+
+// ------------------------------------------------------------------------------------------
+// C ABI: host model
+// ------------------------------------------------------------------------------------------
+
+namespace vx3b {
+thread_local std::string g_last_error;
+void set_error(const std::string &e) { g_last_error = e; }
+} // namespace vx3b
+
+struct vx3b_model {
+    std::unique_ptr<vx3b::HostModel> m;
+};
+
+extern "C" {
+
+const char *vx3b_last_error(void) { return vx3b::g_last_error.c_str(); }
+
+int vx3b_model_from_vxa(const char *vxa_xml, const char *vxd_xml, vx3b_model **out) {
+    if (!vxa_xml || !out) {
+        vx3b::set_error("vx3b_model_from_vxa: null argument");
+        return VX3B_ERR_ARG;
+    }
+    std::string err;
+    auto m = vx3b::model_from_vxa(vxa_xml, vxd_xml, &err);
+    if (!m) {
+        vx3b::set_error(err);
+        return VX3B_ERR_PARSE;
+    }
+    *out = new vx3b_model{std::move(m)};
+    return VX3B_OK;
+}
+
+static bool slurp(const char *path, std::string *out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f)
+        return false;
+    std::stringstream ss;
+    ss << f.rdbuf();
+    *out = ss.str();
+    return true;
+}
+
+int vx3b_model_from_files(const char *vxa_path, const char *vxd_path, vx3b_model **out) {
+    std::string a, d;
+    if (!vxa_path || !slurp(vxa_path, &a)) {
+        vx3b::set_error(std::string("cannot read ") + (vxa_path ? vxa_path : "(null)"));
+        return VX3B_ERR_IO;
+    }
+    if (vxd_path && *vxd_path && !slurp(vxd_path, &d)) {
+        vx3b::set_error(std::string("cannot read ") + vxd_path);
+        return VX3B_ERR_IO;
+    }
+    return vx3b_model_from_vxa(a.c_str(), vxd_path && *vxd_path ? d.c_str() : nullptr, out);
+}
+
+int vx3b_model_new(double vox_size, vx3b_model **out) {
+    if (!out || !(vox_size > 0)) {
+        vx3b::set_error("vx3b_model_new: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    auto m = std::make_unique<vx3b::HostModel>();
+    m->voxSize = vox_size;
+    m->enableCollision = false; // CVoxelyze default (collisions off, old/Voxelyze.cpp:347)
+    m->vx2Compat = true;        // programmatic models follow the Voxelyze2 library API
+    *out = new vx3b_model{std::move(m)};
+    return VX3B_OK;
+}
+
+int vx3b_model_add_material(vx3b_model *m, double youngs_modulus, double density) {
+    if (!m || !(youngs_modulus > 0)) {
+        vx3b::set_error("vx3b_model_add_material: Young's modulus must be positive");
+        return VX3B_ERR_ARG;
+    }
+    vx3b::MatInput in; // CVX_Material::clear defaults (old/VX_Material.cpp:71-90)
+    in.E = (float)youngs_modulus;
+    in.rho = (float)density;
+    if (in.rho <= 0)
+        in.rho = FLT_MIN;
+    in.matid = (int)m->m->mats.size() + 1;
+    m->m->finalized = false;
+    return m->m->addMaterial(in);
+}
+
+int vx3b_model_set_material_param(vx3b_model *m, int mat, const char *name, double value) {
+    if (!m || !name || mat < 0 || mat >= (int)m->m->mats.size()) {
+        vx3b::set_error("vx3b_model_set_material_param: bad material index");
+        return VX3B_ERR_ARG;
+    }
+    vx3b::MatInput &M = m->m->mats[mat];
+    std::string n = name;
+    float f = (float)value;
+    if (n == "youngs_modulus") {
+        if (!(f > 0)) {
+            vx3b::set_error("Young's modulus must be positive");
+            return VX3B_ERR_ARG;
+        }
+        M.E = f;
+        if (M.sigmaFail != -1.0f)
+            M.epsilonFail = M.sigmaFail / M.E;
+    } else if (n == "density")
+        M.rho = f <= 0 ? FLT_MIN : f;
+    else if (n == "poissons_ratio") {
+        if (f < 0)
+            f = 0;
+        if (f >= 0.5)
+            f = 0.5 - FLT_EPSILON * 2;
+        M.nuMemory = f;
+        m->m->volumeEffects = m->m->volumeEffects || f != 0;
+    } else if (n == "cte")
+        M.alphaCTE = f;
+    else if (n == "static_friction")
+        M.muStatic = f <= 0 ? 0 : f;
+    else if (n == "kinetic_friction")
+        M.muKinetic = f <= 0 ? 0 : f;
+    else if (n == "internal_damping")
+        M.zetaInternal = f <= 0 ? 0 : f;
+    else if (n == "global_damping")
+        M.zetaGlobal = f <= 0 ? 0 : f;
+    else if (n == "collision_damping")
+        M.zetaCollision = f <= 0 ? 0 : f;
+    else if (n == "fail_stress") {
+        if (f > 0) {
+            M.sigmaFail = f;
+            M.epsilonFail = f / M.E;
+        } else {
+            M.sigmaFail = M.epsilonFail = -1.0f;
+        }
+    } else if (n == "cilia")
+        M.Cilia = value;
+    else if (n == "fixed")
+        M.fixed = value != 0;
+    else if (n == "is_target")
+        M.isTarget = value != 0;
+    else if (n == "is_measured")
+        M.isMeasured = (int)value;
+    else if (n == "matid")
+        M.matid = (int)value;
+    else {
+        vx3b::set_error("unknown material parameter: " + n);
+        return VX3B_ERR_ARG;
+    }
+    m->m->finalized = false;
+    return VX3B_OK;
+}
+
+int vx3b_model_set_voxel(vx3b_model *m, int mat, int ix, int iy, int iz) {
+    if (!m)
+        return VX3B_ERR_ARG;
+    std::string err;
+    int v = m->m->setVoxel(mat, ix, iy, iz, &err);
+    if (v < 0) {
+        vx3b::set_error(err);
+        return VX3B_ERR_ARG;
+    }
+    return v;
+}
+
+int vx3b_model_set_fixed(vx3b_model *m, int ix, int iy, int iz, int dof_mask, const double *translation3, const double *rotation3) {
+    if (!m)
+        return VX3B_ERR_ARG;
+    int v = m->m->voxelAt(ix, iy, iz);
+    if (v < 0) {
+        vx3b::set_error("vx3b_model_set_fixed: no voxel at that lattice position");
+        return VX3B_ERR_ARG;
+    }
+    m->m->ensureExt();
+    m->m->dofFixed[v] = (uint8_t)(dof_mask & VX3B_DOF_ALL);
+    for (int k = 0; k < 3; k++) { // CVX_External::setDisplacement: only fixed dofs keep a displacement
+        m->m->extTranslation[v * 3 + k] = (translation3 && (dof_mask & (1 << k))) ? translation3[k] : 0.0;
+        m->m->extRotation[v * 3 + k] = (rotation3 && (dof_mask & (8 << k))) ? rotation3[k] : 0.0;
+    }
+    m->m->anyExt = true;
+    return VX3B_OK;
+}
+
+int vx3b_model_set_force(vx3b_model *m, int ix, int iy, int iz, const double *force3, const double *moment3) {
+    if (!m)
+        return VX3B_ERR_ARG;
+    int v = m->m->voxelAt(ix, iy, iz);
+    if (v < 0) {
+        vx3b::set_error("vx3b_model_set_force: no voxel at that lattice position");
+        return VX3B_ERR_ARG;
+    }
+    m->m->ensureExt();
+    for (int k = 0; k < 3; k++) {
+        if (force3)
+            m->m->extForce[v * 3 + k] = (float)force3[k];
+        if (moment3)
+            m->m->extMoment[v * 3 + k] = (float)moment3[k];
+    }
+    m->m->anyExt = true;
+    return VX3B_OK;
+}
+
+int vx3b_model_set_world_param(vx3b_model *m, const char *name, double value) {
+    if (!m || !name)
+        return VX3B_ERR_ARG;
+    vx3b::HostModel &M = *m->m;
+    std::string n = name;
+    if (n == "gravity") // CVoxelyze::setGravity: multiples of g
+        M.gravMult = (float)value;
+    else if (n == "grav_acc") // CVX_Sim::SetGravityAccel
+        M.gravMult = (float)(-(float)value / 9.80665);
+    else if (n == "floor")
+        M.floorEnabled = value != 0;
+    else if (n == "dt_frac")
+        M.dtFrac = value;
+    else if (n == "vary_temp")
+        M.varyTempEnabled = value != 0;
+    else if (n == "temp_amplitude")
+        M.tempAmplitude = value;
+    else if (n == "temp_period")
+        M.tempPeriod = value;
+    else if (n == "initial_temp") // CVoxelyze::setAmbientTemperature
+        M.initialTemp = (float)value;
+    else if (n == "enable_collision")
+        M.enableCollision = value != 0;
+    else if (n == "enable_cilia")
+        M.enableCilia = value != 0;
+    else if (n == "enable_expansion")
+        M.enableExpansion = value != 0;
+    else if (n == "vx2_compat")
+        M.vx2Compat = value != 0;
+    else {
+        vx3b::set_error("unknown world parameter: " + n);
+        return VX3B_ERR_ARG;
+    }
+    return VX3B_OK;
+}
+
+int vx3b_model_finalize(vx3b_model *m) {
+    if (!m)
+        return VX3B_ERR_ARG;
+    std::string err;
+    if (!m->m->finalize(&err)) {
+        vx3b::set_error(err);
+        return VX3B_ERR_PARSE;
+    }
+    return VX3B_OK;
+}
+
+int vx3b_model_desc(const vx3b_model *m, VX3B_WorldDesc *out) {
+    if (!m || !out)
+        return VX3B_ERR_ARG;
+    if (!m->m->finalized) {
+        vx3b::set_error("vx3b_model_desc: model not finalized");
+        return VX3B_ERR_STATE;
+    }
+    m->m->fillDesc(out);
+    return VX3B_OK;
+}
+
+int vx3b_model_merged_vxa(const vx3b_model *m, char *buf, int64_t cap, int64_t *needed) {
+    if (!m)
+        return VX3B_ERR_ARG;
+    const std::string &s = m->m->mergedVxa;
+    if (needed)
+        *needed = (int64_t)s.size() + 1;
+    if (buf && cap > 0) {
+        size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return VX3B_OK;
+}
+
+void vx3b_model_free(vx3b_model *m) { delete m; }
+
+} // extern "C"

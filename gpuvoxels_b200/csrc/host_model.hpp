@@ -1,0 +1,90 @@
+// Host model: VXA/VXD text or CVoxelyze-style calls -> flat VX3B_WorldDesc.
+// Own implementation of what CVX_Sim::ReadVXA + Import (Voxelyze3/src/VXA/VX_Sim.cpp:59-183),
+// CVoxelyze::addVoxel/addLink/combinedMaterial (Voxelyze3/src/old/Voxelyze.cpp:422-628) and the
+// material classes' updateDerived (old/VX_MaterialVoxel.cpp:58-80, old/VX_MaterialLink.cpp:119-139)
+// compute, without their pointer graph: voxels and links come out as index arrays in the
+// reference's creation order, materials as constant tables.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "vx3b200.h"
+#include "xml_min.hpp"
+
+namespace vx3b {
+
+struct MatInput { // CVX_Material state before derivation (floats, as the reference stores them)
+    float E = 1.0f, nu = 0.0f, rho = 1.0f, alphaCTE = 0.0f, muStatic = 0.0f, muKinetic = 0.0f;
+    float zetaInternal = 1.0f, zetaGlobal = 0.0f, zetaCollision = 0.0f;
+    float sigmaFail = -1.0f, epsilonFail = -1.0f;
+    float nuMemory = 0.0f; // Poisson's ratio as given (muMemory, VX_Sim.cpp:85)
+    double Cilia = 0;
+    int matid = 0, fixed = 0, isTarget = 0, isMeasured = 1, sticky = 0;
+};
+
+struct HostModel {
+    // --- inputs -------------------------------------------------------------------------
+    double voxSize = 0.001;
+    std::vector<MatInput> mats;
+    std::vector<int16_t> lattice;   // [nv][3]
+    std::vector<int32_t> voxelMat;  // [nv]
+    std::vector<double> phaseOffset, baseCilia, shiftCilia;
+    std::vector<uint8_t> dofFixed;
+    std::vector<float> extForce, extMoment;
+    std::vector<double> extTranslation, extRotation;
+    bool anyExt = false;
+    std::map<std::tuple<int, int, int>, int> occupied;
+
+    float gravMult = 0.0f;
+    bool floorEnabled = false;
+    double dtFrac = 0.9;
+    bool tempEnabled = false, varyTempEnabled = false;
+    double tempBase = 25, tempAmplitude = 0, tempPeriod = 0.1;
+    float initialTemp = 0.0f;
+    bool volumeEffects = false;
+    bool enableCollision = true, enableCilia = false, enableExpansion = false, vx2Compat = false;
+    bool savePositions = false;
+    double maxDistPair = 0;
+    std::vector<VX3B_Token> stopCondition, fitness, forceField[3];
+
+    // --- derived (finalize) ---------------------------------------------------------------
+    std::vector<int32_t> linkNeg, linkPos, linkMat;
+    std::vector<uint8_t> linkAxis;
+    std::vector<std::pair<int, int>> linkMatPairs; // combinedMaterial list, in creation order
+    std::map<std::tuple<int, int, int, int>, int> linkAt; // (axis, x, y, z of the negative end) -> link
+    std::vector<VX3B_VoxelMaterial> voxelMats;
+    std::vector<VX3B_LinkMaterial> linkMats;
+    bool finalized = false;
+    std::string mergedVxa;
+
+    int numVoxels() const { return (int)voxelMat.size(); }
+    int addMaterial(const MatInput &m) {
+        mats.push_back(m);
+        return (int)mats.size() - 1;
+    }
+    int setVoxel(int mat, int ix, int iy, int iz, std::string *err);
+    int voxelAt(int ix, int iy, int iz) const {
+        auto it = occupied.find(std::make_tuple(ix, iy, iz));
+        return it == occupied.end() ? -1 : it->second;
+    }
+    void ensureExt();
+    bool finalize(std::string *err);
+    void fillDesc(VX3B_WorldDesc *d) const;
+};
+
+// VXD ⊕ VXA merge (Utils/ctool.h:49-57): every child of <VXD> carrying replace="A.B.C" replaces that
+// subtree of the base document.
+bool merge_vxd(XmlNode &baseDoc, const XmlNode &vxdDoc, std::string *err);
+// Reads a (merged) VXA document into a finalized model.
+std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char *vxdText, std::string *err);
+// Formula XML -> token array in reversed level order (VX3_SimulationManager.cu:157-275).
+bool parse_math_tree(const XmlNode *formulaRoot, std::vector<VX3B_Token> &out, std::string *err);
+// Host evaluation of a token array (Utils/VX3_MathTree.h:50-193); empty program -> 0.
+double eval_math_tree(const VX3B_Token *tok, double x, double y, double z, double hit, double t, double angle, double closeness,
+                      int numClosePairs, int numVoxel);
+
+} // namespace vx3b

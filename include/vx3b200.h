@@ -1,0 +1,212 @@
+/* vx3b200.h — C ABI of the B200-native Voxelyze step engine (libvx3b200.so).
+ *
+ * This is the drop-in boundary for the hot path of liusida/gpuVoxels:
+ * everything the reference does between "host model built from VXA/VXD" and "results
+ * copied back" — i.e. what VX3_SimulationManager::readVXD/startKernel/collectResults
+ * (Voxelyze3/src/VX3/VX3_SimulationManager.cu:277-458) hand to and take from the
+ * CUDA_Simulation kernel (VX3_SimulationManager.cu:11-121).
+ *
+ * Conventions: extern "C", plain structs, int status (0 = ok, negative = error; text via
+ * vx3b_last_error()), caller owns host buffers, the library owns device memory, one
+ * context per device, one host thread per context.  No torch / C++ types cross this line.
+ * There is NO CPU fallback: every compute entry point fails with VX3B_ERR_CUDA when no
+ * sm_100 device is usable.
+ *
+ * Three layers are exported:
+ *   1. host model   (vx3b_model_*)  VXA/VXD text or CVoxelyze-style calls  -> VX3B_WorldDesc
+ *   2. step engine  (vx3b_ctx_*, vx3b_batch_*)  VX3B_WorldDesc[] -> stepped state/results
+ *   3. job          (vx3b_job_run)  directory of base.vxa + *.vxd -> report XML
+ */
+#ifndef VX3B200_H
+#define VX3B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VX3B_OK 0
+#define VX3B_ERR_ARG (-1)
+#define VX3B_ERR_CUDA (-2)
+#define VX3B_ERR_PARSE (-3)
+#define VX3B_ERR_IO (-4)
+#define VX3B_ERR_STATE (-5)
+
+/* precision of the device state and arithmetic */
+#define VX3B_FP32 32 /* production: float4 SoA, displacement-based positions          */
+#define VX3B_FP64 64 /* validation build: double state with the reference's float casts */
+
+/* link axis / direction enums: VoxCAD/src/VX2/include/types.h:6-56 */
+#define VX3B_AXIS_X 0
+#define VX3B_AXIS_Y 1
+#define VX3B_AXIS_Z 2
+/* dof bits (CVX_External::dofFixed, types.h): X_TRANSLATE=1<<0 .. Z_ROTATE=1<<5 */
+#define VX3B_DOF_TX 1
+#define VX3B_DOF_TY 2
+#define VX3B_DOF_TZ 4
+#define VX3B_DOF_RX 8
+#define VX3B_DOF_RY 16
+#define VX3B_DOF_RZ 32
+#define VX3B_DOF_ALL 63
+
+/* Formula VM opcodes — same numbering as VX3_MathTreeOperator (Utils/VX3_MathTree.h:4-29). */
+enum {
+    VX3B_MT_END = 0, VX3B_MT_CONST, VX3B_MT_E, VX3B_MT_PI, VX3B_MT_VAR, VX3B_MT_ADD, VX3B_MT_SUB, VX3B_MT_MUL,
+    VX3B_MT_DIV, VX3B_MT_POW, VX3B_MT_SQRT, VX3B_MT_SIN, VX3B_MT_COS, VX3B_MT_TAN, VX3B_MT_ATAN, VX3B_MT_LOG,
+    VX3B_MT_INT, VX3B_MT_ABS, VX3B_MT_NOT, VX3B_MT_GREATERTHAN, VX3B_MT_LESSTHAN, VX3B_MT_AND, VX3B_MT_OR,
+    VX3B_MT_NORMALCDF
+};
+#define VX3B_MAX_TOKENS 64 /* the reference allows 1024 (VX3_VoxelyzeKernel.cuh:113-119); no shipped formula exceeds 40 */
+
+typedef struct VX3B_Token {
+    int32_t op;   /* VX3B_MT_* */
+    int32_t pad;
+    double value; /* constant, or variable id 0..8 = x,y,z,hit,t,angle,targetCloseness,numClosePairs,num_voxel */
+} VX3B_Token;
+
+/* One palette material with the derived constants exactly as the reference caches them
+ * (float storage!): CVX_Material (Voxelyze3/src/old/VX_Material.h), CVX_MaterialVoxel::updateDerived
+ * (VX3_MaterialVoxel.cu:49-71). */
+typedef struct VX3B_VoxelMaterial {
+    float E, nu, rho, alphaCTE, muStatic, muKinetic, zetaInternal, zetaGlobal, zetaCollision;
+    float epsilonFail;           /* -1 = never fails */
+    float gravMult;              /* multiples of g; gravity force = -mass*9.80665f*gravMult */
+    float mass, massInverse, sqrtMass, momentInertia, momentInertiaInverse;
+    float _2xSqMxExS, _2xSqIxExSxSxS;
+    double nomSize;
+    double Cilia;                /* scale of the cilia force */
+    int32_t matid;               /* palette ID reported in <mats> */
+    int32_t fixed, isTarget, isMeasured, sticky, linear;
+    int32_t pad;
+} VX3B_VoxelMaterial;
+
+/* Combined material of a voxel pair: CVX_MaterialLink::updateAll/updateDerived
+ * (VX3_MaterialLink.cu:53-148). */
+typedef struct VX3B_LinkMaterial {
+    float E, nu, eHat;
+    float a1, a2, b1, b2, b3;
+    float sqA1, sqA2xIp, sqB1, sqB2xFMp, sqB3xIp;
+    float epsilonFail;           /* -1 = never fails */
+    int32_t mat1, mat2;          /* indices into voxel_mats */
+} VX3B_LinkMaterial;
+
+/* One world (= one VXA⊕VXD), flattened.  Voxels are in the reference's creation order
+ * (x fastest, then y, then z over occupied lattice cells — VX_Sim.cpp:92-107), links in the
+ * order CVoxelyze::addVoxel creates them (Voxelyze.cpp:439-461): that order defines the
+ * surface list and therefore the collision pair enumeration. */
+typedef struct VX3B_WorldDesc {
+    int32_t num_voxels, num_links, num_voxel_mats, num_link_mats;
+    double vox_size;
+
+    const int16_t *lattice;      /* [nv][3] ix,iy,iz */
+    const int32_t *voxel_mat;    /* [nv] index into voxel_mats */
+    const double *phase_offset;  /* [nv] or NULL */
+    const double *base_cilia;    /* [nv][3] or NULL */
+    const double *shift_cilia;   /* [nv][3] or NULL (needs signals; accepted, unused while EnableSignals=0) */
+    const uint8_t *dof_fixed;    /* [nv] VX3B_DOF_* mask or NULL */
+    const float *ext_force;      /* [nv][3] or NULL (float, as CVX_External stores it) */
+    const float *ext_moment;     /* [nv][3] or NULL */
+    const double *ext_translation; /* [nv][3] or NULL prescribed displacement of fixed dofs */
+    const double *ext_rotation;  /* [nv][3] or NULL rotation vector of fixed rotational dofs */
+
+    const int32_t *link_neg;     /* [nl] voxel index of the negative end */
+    const int32_t *link_pos;     /* [nl] voxel index of the positive end */
+    const uint8_t *link_axis;    /* [nl] VX3B_AXIS_* */
+    const int32_t *link_mat;     /* [nl] index into link_mats */
+
+    const VX3B_VoxelMaterial *voxel_mats;
+    const VX3B_LinkMaterial *link_mats;
+
+    /* world scalars (VX3_VoxelyzeKernel.cuh:50-161, VX3_SimulationManager.cu:323-375) */
+    double dt_frac;
+    int32_t floor_enabled;
+    int32_t vary_temp_enabled;
+    double temp_amplitude, temp_period;
+    int32_t enable_collision, enable_cilia, enable_expansion;
+    int32_t vx2_compat;          /* 1: Voxelyze2 semantics (float dt, no angMom zeroing, no Fixed-material skip) */
+    double max_dist_in_voxel_lengths_to_count_as_pair;
+    int32_t save_position_of_all_voxels;
+    float initial_temp;          /* temperature offset every voxel starts with (CVX_Sim::UpdateMatTemps at Import) */
+
+    VX3B_Token stop_condition[VX3B_MAX_TOKENS]; /* empty (op[0]==END) = never stops by formula */
+    VX3B_Token fitness[VX3B_MAX_TOKENS];
+    VX3B_Token force_field[3][VX3B_MAX_TOKENS]; /* x,y,z; empty = no field */
+} VX3B_WorldDesc;
+
+/* Numeric fields of VX3_SimulationResult (VX3_SimulationResult.h:4-24). */
+typedef struct VX3B_WorldResult {
+    double current_time;
+    double fitness_score;
+    double initial_com[3];
+    double current_com[3];
+    double total_distance_of_all_voxels;
+    double vox_size;
+    double recent_angle, target_closeness;
+    double dt;                   /* the (float-truncated) step actually used */
+    int64_t steps;               /* steps taken (CurStepCount) */
+    int32_t num_voxel, num_measured_voxel, num_close_pairs, collision_count;
+    int32_t diverged, stopped;   /* diverged: some link strain > 100; stopped: stop formula > 0 */
+} VX3B_WorldResult;
+
+typedef struct vx3b_ctx vx3b_ctx;
+typedef struct vx3b_model vx3b_model;
+
+const char *vx3b_last_error(void);
+const char *vx3b_version(void);
+
+/* ---------------------------------------------------------------- 1. host model ------
+ * Replaces CVX_Sim::ReadVXA + Import (Voxelyze3/src/VXA/VX_Sim.cpp:155-183, 59-153) and the
+ * VXD⊕VXA merge (Voxelyze3/src/Utils/ctool.h:49-57, VX3_SimulationManager.cu:277-380). */
+int vx3b_model_from_vxa(const char *vxa_xml, const char *vxd_xml /* may be NULL */, vx3b_model **out);
+int vx3b_model_from_files(const char *vxa_path, const char *vxd_path /* may be NULL */, vx3b_model **out);
+/* CVoxelyze-style programmatic construction (VoxCAD/src/VX2/include/Voxelyze.h:43-134) */
+int vx3b_model_new(double vox_size, vx3b_model **out);
+int vx3b_model_add_material(vx3b_model *m, double youngs_modulus, double density); /* returns material index >= 0 */
+int vx3b_model_set_material_param(vx3b_model *m, int mat, const char *name, double value);
+int vx3b_model_set_voxel(vx3b_model *m, int mat, int ix, int iy, int iz);
+int vx3b_model_set_fixed(vx3b_model *m, int ix, int iy, int iz, int dof_mask, const double *translation3, const double *rotation3);
+int vx3b_model_set_force(vx3b_model *m, int ix, int iy, int iz, const double *force3, const double *moment3);
+int vx3b_model_set_world_param(vx3b_model *m, const char *name, double value); /* gravity, floor, dt_frac, ... */
+int vx3b_model_finalize(vx3b_model *m); /* builds links + combined materials + derived constants */
+int vx3b_model_desc(const vx3b_model *m, VX3B_WorldDesc *out); /* pointers stay owned by the model */
+int vx3b_model_merged_vxa(const vx3b_model *m, char *buf, int64_t cap, int64_t *needed); /* merged VXA text (for the reference harness) */
+void vx3b_model_free(vx3b_model *m);
+
+/* ---------------------------------------------------------------- 2. step engine -----
+ * Replaces VX3_VoxelyzeKernel (host ctor, VX3_VoxelyzeKernel.cu:27-105) + CUDA_Simulation
+ * + doTimeStep and all gpu_update_* kernels (VX3_VoxelyzeKernel.cu:237-359, 566-650, 833-859). */
+int vx3b_ctx_create(int device, int precision, vx3b_ctx **out);
+void vx3b_ctx_destroy(vx3b_ctx *ctx);
+/* 0 = automatic; 1 = generic streaming kernels (link pass + voxel pass); 2 = resident kernel
+ * (one CTA per world, state in shared memory); 3 = fused tile kernel (big bodies). */
+int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value);
+int vx3b_batch_upload(vx3b_ctx *ctx, const VX3B_WorldDesc *worlds, int n);
+/* Advance every world by up to max_steps more steps.  use_stop_formula: test the world's stop
+ * condition before every step as CUDA_Simulation does (VX3_SimulationManager.cu:62-69).
+ * Worlds that diverge (any link strain > 100) stop, as VX3_VoxelyzeKernel.cu:271-280. */
+int vx3b_batch_run(vx3b_ctx *ctx, int64_t max_steps, int use_stop_formula);
+int vx3b_batch_results(vx3b_ctx *ctx, VX3B_WorldResult *out /* [n] */);
+/* state of one world in creation order, always as double; any pointer may be NULL */
+int vx3b_batch_read_state(vx3b_ctx *ctx, int world, double *pos3, double *orient4 /* w,x,y,z */, double *lin_mom3, double *ang_mom3);
+int vx3b_batch_read_initial_pos(vx3b_ctx *ctx, int world, double *pos3);
+int vx3b_batch_read_links(vx3b_ctx *ctx, int world, double *pos2_3, double *angle1v3, double *angle2v3, int32_t *flags /* bit0 smallAngle bit1 localVelocityValid */);
+/* collision pair set found in the LAST executed step of `world`: pairs (i,j), i>j, voxel indices in
+ * creation order, sorted ascending by (i,j).  *n in: capacity (pairs), out: count. */
+int vx3b_batch_collision_pairs(vx3b_ctx *ctx, int world, int32_t *pairs2, int32_t *n);
+/* device time (CUDA events) of the last vx3b_batch_run, and how many kernels it launched */
+int vx3b_ctx_timing(vx3b_ctx *ctx, float *device_ms, int64_t *kernel_launches);
+int64_t vx3b_ctx_total_voxel_steps(vx3b_ctx *ctx); /* sum over worlds of nv*steps in the last run */
+/* torch interop: run on an existing stream (cudaStream_t as integer); 0 = own stream */
+int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t cuda_stream);
+
+/* ---------------------------------------------------------------- 3. job -------------
+ * Replaces vx3_node_worker main + VX3_SimulationManager::start (vx3_node_worker.cu:32-142,
+ * VX3_SimulationManager.cu:138-155): every *.vxd in input_dir over base.vxa, worlds sharded over
+ * `num_devices` GPUs, report XML in the reference's layout written to report_path. */
+int vx3b_job_run(const char *input_dir, const char *report_path, int num_devices, int precision);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VX3B200_H */
