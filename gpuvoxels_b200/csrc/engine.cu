@@ -1,0 +1,914 @@
+// Step engine: device memory, upload, run loop, read-back and the engine part of the C ABI.
+// Replaces VX3_VoxelyzeKernel's host constructor (VX3/VX3_VoxelyzeKernel.cu:27-105),
+// VX3_SimulationManager::startKernel / collectResults (VX3/VX3_SimulationManager.cu:384-458) and, through the
+// kernels it launches, CUDA_Simulation + doTimeStep.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+#include "kernels_resident.cuh"
+#include "kernels_stream.cuh"
+
+namespace vx3b {
+
+#define CUDA_TRY(expr)                                                                                                          \
+    do {                                                                                                                        \
+        cudaError_t _e = (expr);                                                                                                \
+        if (_e != cudaSuccess) {                                                                                                \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                                                      \
+            return VX3B_ERR_CUDA;                                                                                               \
+        }                                                                                                                       \
+    } while (0)
+
+struct DeviceBuf { // owns one cudaMalloc allocation
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DeviceBuf() { release(); }
+    void release() {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t alloc(size_t n) {
+        release();
+        bytes = n;
+        if (n == 0)
+            return cudaSuccess;
+        return cudaMalloc(&p, n);
+    }
+};
+
+struct WorldHost {
+    int nv, nl, ns, voff, loff, soff;
+    double recommendedDt;
+    float dt;
+};
+
+// recommended time step exactly as the reference computes it (VX3: double, VX2: float)
+static double recommended_dt(const VX3B_WorldDesc &d) {
+    const bool vx3 = !d.vx2_compat;
+    if (vx3) { // VX3/VX3_VoxelyzeKernel.cu:184-217
+        double maxF2 = 0.0f;
+        for (int l = 0; l < d.num_links; l++) {
+            double m1 = d.voxel_mats[d.voxel_mat[d.link_neg[l]]].mass, m2 = d.voxel_mats[d.voxel_mat[d.link_pos[l]]].mass;
+            double f2 = d.link_mats[d.link_mat[l]].a1 / (m1 < m2 ? m1 : m2);
+            if (f2 > maxF2)
+                maxF2 = f2;
+        }
+        if (maxF2 <= 0.0f)
+            for (int v = 0; v < d.num_voxels; v++) {
+                const VX3B_VoxelMaterial &m = d.voxel_mats[d.voxel_mat[v]];
+                double f2 = m.E * m.nomSize / m.mass;
+                if (f2 > maxF2)
+                    maxF2 = f2;
+            }
+        if (maxF2 <= 0.0f)
+            return 0.0f;
+        return 1.0f / (6.283185f * sqrt(maxF2));
+    }
+    float maxF2 = 0.0f; // old/Voxelyze.cpp:286-311
+    for (int l = 0; l < d.num_links; l++) {
+        float m1 = d.voxel_mats[d.voxel_mat[d.link_neg[l]]].mass, m2 = d.voxel_mats[d.voxel_mat[d.link_pos[l]]].mass;
+        float f2 = d.link_mats[d.link_mat[l]].a1 / (m1 < m2 ? m1 : m2);
+        if (f2 > maxF2)
+            maxF2 = f2;
+    }
+    if (maxF2 <= 0.0f)
+        for (int v = 0; v < d.num_voxels; v++) {
+            const VX3B_VoxelMaterial &m = d.voxel_mats[d.voxel_mat[v]];
+            float f2 = (float)(m.E * m.nomSize / m.mass);
+            if (f2 > maxF2)
+                maxF2 = f2;
+        }
+    if (maxF2 <= 0.0f)
+        return 0.0f;
+    return (float)(1.0f / (6.283185f * sqrtf(maxF2)));
+}
+
+static bool formula_empty(const VX3B_Token *t) { return t[0].op == VX3B_MT_END; }
+
+class EngineBase {
+  public:
+    virtual ~EngineBase() {}
+    virtual int upload(const VX3B_WorldDesc *worlds, int n) = 0;
+    virtual int run(int64_t maxSteps, int useStop) = 0;
+    virtual int results(VX3B_WorldResult *out) = 0;
+    virtual int read_state(int world, double *pos, double *orient, double *lin, double *ang) = 0;
+    virtual int read_initial_pos(int world, double *pos) = 0;
+    virtual int read_links(int world, double *pos2, double *a1, double *a2, int32_t *flags) = 0;
+    virtual int collision_pairs(int world, int32_t *pairs, int32_t *n) = 0;
+    int device = 0, precision = 32;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    float lastMs = 0;
+    int64_t lastLaunches = 0, lastVoxelSteps = 0;
+    // options
+    int path = 0;         // 0 auto, 1 streaming, 2 resident
+    int recordPairs = 0;  // keep the collision pair list of the last step (parity tests)
+    int chunk = 64;       // steps per CUDA-graph replay on the streaming path
+    double dtOverride = 0;
+    int residentThreads = 256;
+};
+
+template <class R> class Engine : public EngineBase {
+    using T4 = typename Store<R>::T4;
+    using T2 = typename Store<R>::T2;
+
+  public:
+    Arrays<R> A;
+    std::vector<WorldHost> H;
+    std::vector<std::unique_ptr<DeviceBuf>> bufs;
+    std::vector<ContactTile> hTiles;
+    ContactTile *dTiles = nullptr;
+    int *dActive = nullptr;
+    int *hActive = nullptr; // pinned
+    cudaGraphExec_t graphExec = nullptr;
+    int graphChunk = 0, graphUseStop = -1, graphRecord = -1;
+    bool anyCollision = false;
+    int maxNv = 0, maxNl = 0, maxNs = 0;
+    ResidentCfg rcfg;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    ~Engine() override {
+        if (graphExec)
+            cudaGraphExecDestroy(graphExec);
+        if (hActive)
+            cudaFreeHost(hActive);
+        if (ev0)
+            cudaEventDestroy(ev0);
+        if (ev1)
+            cudaEventDestroy(ev1);
+        bufs.clear();
+        if (ownStream && stream)
+            cudaStreamDestroy(stream);
+    }
+
+    template <class T> int dalloc(T **out, size_t count, const T *src = nullptr) {
+        auto b = std::make_unique<DeviceBuf>();
+        CUDA_TRY(b->alloc(std::max<size_t>(count, 1) * sizeof(T)));
+        *out = (T *)b->p;
+        if (src && count)
+            CUDA_TRY(cudaMemcpyAsync(b->p, src, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+        else
+            CUDA_TRY(cudaMemsetAsync(b->p, 0, std::max<size_t>(count, 1) * sizeof(T), stream));
+        bufs.push_back(std::move(b));
+        return VX3B_OK;
+    }
+
+    int upload(const VX3B_WorldDesc *worlds, int n) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (graphExec) {
+            cudaGraphExecDestroy(graphExec);
+            graphExec = nullptr;
+        }
+        bufs.clear();
+        H.clear();
+        hTiles.clear();
+        memset(&A, 0, sizeof(A));
+        if (n <= 0 || !worlds) {
+            set_error("vx3b_batch_upload: no worlds");
+            return VX3B_ERR_ARG;
+        }
+        // ---- sizes
+        size_t nvTot = 0, nlTot = 0, nvm = 0, nlm = 0;
+        for (int w = 0; w < n; w++) {
+            const VX3B_WorldDesc &d = worlds[w];
+            if (d.num_voxels < 0 || d.num_links < 0 || (d.num_voxels > 0 && (!d.lattice || !d.voxel_mat || !d.voxel_mats)) ||
+                (d.num_links > 0 && (!d.link_neg || !d.link_pos || !d.link_axis || !d.link_mat || !d.link_mats))) {
+                set_error("vx3b_batch_upload: world " + std::to_string(w) + " has null arrays");
+                return VX3B_ERR_ARG;
+            }
+            nvTot += d.num_voxels;
+            nlTot += d.num_links;
+            nvm += d.num_voxel_mats;
+            nlm += d.num_link_mats;
+        }
+        if (nvTot > 0x7fffffffull || nlTot > 0x3fffffffull) {
+            set_error("vx3b_batch_upload: batch too large for 32-bit indices");
+            return VX3B_ERR_ARG;
+        }
+        // ---- host staging
+        std::vector<WorldD> hW(n);
+        std::vector<D2> pxy(nvTot), pzt(nvTot), ipxy(nvTot);
+        std::vector<double> ipz(nvTot), phase(nvTot, 0.0);
+        std::vector<T4> orient(nvTot), lm(nvTot);
+        std::vector<T2> am(nvTot);
+        std::vector<int32_t> vmat(nvTot), vworld(nvTot), vlinks(6 * nvTot, -1), vsurf(nvTot, -1), vext(nvTot, -1), surf;
+        std::vector<short4> lat(nvTot);
+        std::vector<D4> baseCilia(nvTot);
+        std::vector<DExt> ext;
+        std::vector<T4> lpos2(nlTot), lzero(nlTot);
+        std::vector<int2> lends(nlTot);
+        std::vector<uint32_t> lmeta(nlTot);
+        std::vector<int32_t> lworld(nlTot);
+        std::vector<DVoxMat> vmats(nvm);
+        std::vector<DLinkMat> lmats(nlm);
+        bool anyPhase = false, anyCilia = false;
+        anyCollision = false;
+        maxNv = maxNl = maxNs = 0;
+        size_t voff = 0, loff = 0, vmo = 0, lmo = 0;
+        memset(lzero.data(), 0, lzero.size() * sizeof(T4));
+        for (int w = 0; w < n; w++) {
+            const VX3B_WorldDesc &d = worlds[w];
+            WorldD &W = hW[w];
+            memset(&W, 0, sizeof(W));
+            WorldHost h;
+            h.nv = d.num_voxels;
+            h.nl = d.num_links;
+            h.voff = (int)voff;
+            h.loff = (int)loff;
+            h.soff = (int)surf.size();
+            const bool vx3 = !d.vx2_compat;
+            // dt: VX3_VoxelyzeKernel.cu:244-254 / caller-side DtFrac*recommendedTimeStep for Voxelyze2
+            double opt = recommended_dt(d);
+            if (vx3 && opt < 1e-10)
+                opt = 1e-10;
+            h.recommendedDt = opt;
+            h.dt = (float)(d.dt_frac * opt);
+            if (dtOverride > 0)
+                h.dt = (float)dtOverride;
+            W.voff = h.voff;
+            W.nv = h.nv;
+            W.loff = h.loff;
+            W.nl = h.nl;
+            W.soff = h.soff;
+            W.vmatOff = (int)vmo;
+            W.lmatOff = (int)lmo;
+            W.dt = h.dt;
+            W.tempAmp = d.temp_amplitude;
+            W.tempPeriod = d.temp_period;
+            W.voxSize = d.vox_size;
+            W.maxDistPair = d.max_dist_in_voxel_lengths_to_count_as_pair;
+            W.cycle = (h.dt > 0 && vx3) ? (int)(d.temp_period / h.dt) : 0;
+            const bool hasFF = !formula_empty(d.force_field[0]) || !formula_empty(d.force_field[1]) || !formula_empty(d.force_field[2]);
+            W.flags = (d.floor_enabled ? WF_FLOOR : 0) | ((d.vary_temp_enabled && d.temp_period > 0) ? WF_VARY_TEMP : 0) |
+                      (d.enable_collision ? WF_COLLISION : 0) | (d.enable_cilia ? WF_CILIA : 0) | (d.enable_expansion ? WF_EXPANSION : 0) |
+                      (vx3 ? WF_VX3 : 0) | (hasFF ? WF_FORCE_FIELD : 0) | (!formula_empty(d.stop_condition) ? WF_STOP_FORMULA : 0);
+            memcpy(W.stop, d.stop_condition, sizeof(W.stop));
+            memcpy(W.fitnessF, d.fitness, sizeof(W.fitnessF));
+            memcpy(W.ff, d.force_field, sizeof(W.ff));
+            if (d.enable_collision)
+                anyCollision = true;
+            // materials
+            for (int k = 0; k < d.num_voxel_mats; k++) {
+                const VX3B_VoxelMaterial &m = d.voxel_mats[k];
+                DVoxMat &o = vmats[vmo + k];
+                memset(&o, 0, sizeof(o));
+                o.E = m.E;
+                o.alphaCTE = m.alphaCTE;
+                o.muStatic = m.muStatic;
+                o.muKinetic = m.muKinetic;
+                o.mass = m.mass;
+                o.massInverse = m.massInverse;
+                o.momentInertiaInverse = m.momentInertiaInverse;
+                o.sqrtMassZetaInt2 = 2 * m.sqrtMass * m.zetaInternal;
+                o.globalDampTranslateC = m.zetaGlobal * m._2xSqMxExS;
+                o.globalDampRotateC = m.zetaGlobal * m._2xSqIxExSxSxS;
+                o.collisionDampTranslateC = m.zetaCollision * m._2xSqMxExS;
+                o.penetrationStiffness = (float)(2 * m.E * m.nomSize);
+                o.gravityForce = -m.mass * 9.80665f * m.gravMult;
+                o.nomSizeF = (float)m.nomSize;
+                o.nomSize = m.nomSize;
+                o.cilia = m.Cilia;
+                o.fixed = m.fixed;
+                o.isTarget = m.isTarget;
+                o.isMeasured = m.isMeasured;
+            }
+            for (int k = 0; k < d.num_link_mats; k++) {
+                const VX3B_LinkMaterial &m = d.link_mats[k];
+                DLinkMat &o = lmats[lmo + k];
+                o.E = m.E;
+                o.a2 = m.a2;
+                o.b1 = m.b1;
+                o.b2 = m.b2;
+                o.b3 = m.b3;
+                o.sqA1 = m.sqA1;
+                o.sqA2xIp = m.sqA2xIp;
+                o.sqB1 = m.sqB1;
+                o.sqB2xFMp = m.sqB2xFMp;
+                o.sqB3xIp = m.sqB3xIp;
+                o.epsilonFail = m.epsilonFail;
+                float s1 = (float)d.voxel_mats[m.mat1].nomSize, s2 = (float)d.voxel_mats[m.mat2].nomSize;
+                o.area = 0.5f * (s1 * s1 + s2 * s2); // currentTransverseArea for nu == 0 (VX3_Link.cu:85-88, VX3_Voxel.cu:496-499)
+            }
+            // voxels
+            const bool vary = (W.flags & WF_VARY_TEMP) != 0;
+            for (int v = 0; v < d.num_voxels; v++) {
+                size_t g = voff + v;
+                const VX3B_VoxelMaterial &m = d.voxel_mats[d.voxel_mat[v]];
+                short ix = d.lattice[v * 3], iy = d.lattice[v * 3 + 1], iz = d.lattice[v * 3 + 2];
+                double px = ix * m.nomSize, py = iy * m.nomSize, pz = iz * m.nomSize;
+                float temp = d.initial_temp;
+                double ph = d.phase_offset ? d.phase_offset[v] : 0.0;
+                if (ph != 0)
+                    anyPhase = true;
+                if (vary && !(vx3 && m.fixed)) { // first step's gpu_update_temperature at t = 0
+                    double T = d.temp_amplitude * sin(2 * 3.1415926f * (0.0 / d.temp_period + ph));
+                    if (!d.enable_expansion && T > 0)
+                        T = 0;
+                    temp = (float)T;
+                }
+                phase[g] = ph;
+                pxy[g] = D2{px, py};
+                uint32_t tb;
+                memcpy(&tb, &temp, 4);
+                unsigned long long bits = ((unsigned long long)VF_STATIC_FRICTION << 32) | tb; // voxels start in static friction
+                double packed;
+                memcpy(&packed, &bits, 8);
+                pzt[g] = D2{pz, packed};
+                ipxy[g] = D2{px, py};
+                ipz[g] = pz;
+                orient[g].x = R(1);
+                orient[g].y = orient[g].z = orient[g].w = R(0);
+                lm[g].x = lm[g].y = lm[g].z = lm[g].w = R(0);
+                am[g].x = am[g].y = R(0);
+                vmat[g] = (int)vmo + d.voxel_mat[v];
+                vworld[g] = w;
+                lat[g] = make_short4(ix, iy, iz, 0);
+                D4 bc{0, 0, 0, 0};
+                if (d.base_cilia) {
+                    bc.x = d.base_cilia[v * 3];
+                    bc.y = d.base_cilia[v * 3 + 1];
+                    bc.z = d.base_cilia[v * 3 + 2];
+                    if (d.enable_cilia && (bc.x != 0 || bc.y != 0 || bc.z != 0))
+                        anyCilia = true;
+                }
+                baseCilia[g] = bc;
+                uint8_t dof = d.dof_fixed ? d.dof_fixed[v] : 0;
+                bool hasF = false;
+                for (int k = 0; k < 3; k++)
+                    hasF = hasF || (d.ext_force && d.ext_force[v * 3 + k] != 0) || (d.ext_moment && d.ext_moment[v * 3 + k] != 0);
+                if (dof || hasF) {
+                    DExt e;
+                    memset(&e, 0, sizeof(e));
+                    e.dof = dof;
+                    for (int k = 0; k < 3; k++) {
+                        e.force[k] = d.ext_force ? d.ext_force[v * 3 + k] : 0.0f;
+                        e.moment[k] = d.ext_moment ? d.ext_moment[v * 3 + k] : 0.0f;
+                        e.translation[k] = d.ext_translation ? d.ext_translation[v * 3 + k] : 0.0;
+                    }
+                    double rx = d.ext_rotation ? d.ext_rotation[v * 3] : 0, ry = d.ext_rotation ? d.ext_rotation[v * 3 + 1] : 0,
+                           rz = d.ext_rotation ? d.ext_rotation[v * 3 + 2] : 0;
+                    e.rotQ[0] = 1;
+                    if (rx != 0 || ry != 0 || rz != 0) { // CVX_External::rotationChanged -> Quat3D(rotation vector)
+                        double hx = rx / 2, hy = ry / 2, hz = rz / 2, m2 = hx * hx + hy * hy + hz * hz, qw, s;
+                        if (m2 * m2 < 5.328e-15) {
+                            qw = 1.0 - 0.5 * m2;
+                            s = 1.0 - m2 / 6.0;
+                        } else {
+                            double mm = sqrt(m2);
+                            qw = cos(mm);
+                            s = sin(mm) / mm;
+                        }
+                        e.rotQ[0] = qw;
+                        e.rotQ[1] = hx * s;
+                        e.rotQ[2] = hy * s;
+                        e.rotQ[3] = hz * s;
+                    }
+                    vext[g] = (int)ext.size();
+                    ext.push_back(e);
+                }
+            }
+            // links
+            for (int l = 0; l < d.num_links; l++) {
+                size_t g = loff + l;
+                int a = d.link_neg[l], b = d.link_pos[l], ax = d.link_axis[l];
+                if (a < 0 || a >= d.num_voxels || b < 0 || b >= d.num_voxels || ax > 2) {
+                    set_error("vx3b_batch_upload: link " + std::to_string(l) + " of world " + std::to_string(w) + " is malformed");
+                    return VX3B_ERR_ARG;
+                }
+                lends[g] = make_int2((int)voff + a, (int)voff + b);
+                lmeta[g] = (uint32_t)ax | ((uint32_t)(lmo + d.link_mat[l]) << 2);
+                lworld[g] = w;
+                vlinks[(size_t)(2 * ax) * nvTot + voff + a] = (int)g;     // positive-side slot of the negative end
+                vlinks[(size_t)(2 * ax + 1) * nvTot + voff + b] = (int)g; // negative-side slot of the positive end
+                T4 p2;
+                p2.x = p2.y = p2.z = R(0);
+                uint32_t fl = LF_SMALL_ANGLE; // CVX_Link::reset: smallAngle = true, LOCAL_VELOCITY_VALID = false
+                if constexpr (sizeof(R) == 4) {
+                    float f;
+                    memcpy(&f, &fl, 4);
+                    p2.w = f;
+                } else {
+                    long long b64 = fl;
+                    double dd;
+                    memcpy(&dd, &b64, 8);
+                    p2.w = dd;
+                }
+                lpos2[g] = p2;
+            }
+            // surface list: voxels with an empty link slot, creation order (VX3_VoxelyzeKernel.cu:495-513)
+            for (int v = 0; v < d.num_voxels; v++) {
+                bool interior = true;
+                for (int k = 0; k < 6; k++)
+                    if (vlinks[(size_t)k * nvTot + voff + v] < 0)
+                        interior = false;
+                if (!interior) {
+                    vsurf[voff + v] = (int)surf.size();
+                    surf.push_back((int)(voff + v));
+                }
+            }
+            h.ns = (int)surf.size() - h.soff;
+            W.ns = h.ns;
+            if (d.enable_collision)
+                for (int f = 0; f < h.ns; f += 128)
+                    hTiles.push_back(ContactTile{w, f});
+            maxNv = std::max(maxNv, h.nv);
+            maxNl = std::max(maxNl, h.nl);
+            maxNs = std::max(maxNs, h.ns);
+            H.push_back(h);
+            voff += d.num_voxels;
+            loff += d.num_links;
+            vmo += d.num_voxel_mats;
+            lmo += d.num_link_mats;
+        }
+        // ---- device
+        if (!stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            ownStream = true;
+        }
+        if (!ev0) {
+            CUDA_TRY(cudaEventCreate(&ev0));
+            CUDA_TRY(cudaEventCreate(&ev1));
+        }
+        A.nvTot = (int)nvTot;
+        A.nlTot = (int)nlTot;
+        A.nsTot = (int)surf.size();
+        A.nWorlds = n;
+        int rc;
+#define UP(field, vec)                                                                                                          \
+    if ((rc = dalloc(&A.field, (vec).size(), (vec).data())) != VX3B_OK)                                                         \
+        return rc;
+        UP(worlds, hW);
+        UP(pxy, pxy);
+        UP(pzt, pzt);
+        UP(orient, orient);
+        UP(lm, lm);
+        UP(am, am);
+        UP(vmat, vmat);
+        UP(vworld, vworld);
+        UP(vlinks, vlinks);
+        UP(vsurf, vsurf);
+        UP(vext, vext);
+        UP(lat, lat);
+        UP(ipxy, ipxy);
+        UP(ipz, ipz);
+        UP(ext, ext);
+        UP(surf, surf);
+        UP(lpos2, lpos2);
+        UP(la1, lzero);
+        UP(la2, lzero);
+        UP(lends, lends);
+        UP(lmeta, lmeta);
+        UP(lworld, lworld);
+        UP(lfN, lzero);
+        UP(lfP, lzero);
+        UP(lmN, lzero);
+        UP(lmP, lzero);
+        UP(vmats, vmats);
+        UP(lmats, lmats);
+        if (anyPhase) {
+            UP(phase, phase);
+        }
+        if (anyCilia) {
+            UP(baseCilia, baseCilia);
+        }
+#undef UP
+        if ((rc = dalloc(&A.contactF, surf.size())) != VX3B_OK)
+            return rc;
+        if ((rc = dalloc(&dTiles, hTiles.size(), hTiles.data())) != VX3B_OK)
+            return rc;
+        if ((rc = dalloc(&dActive, 1)) != VX3B_OK)
+            return rc;
+        A.pairCap = 1 << 20;
+        if ((rc = dalloc(&A.pairBuf, recordPairs ? (size_t)A.pairCap : 1)) != VX3B_OK)
+            return rc;
+        if ((rc = dalloc(&A.pairCount, 1)) != VX3B_OK)
+            return rc;
+        if (!hActive)
+            CUDA_TRY(cudaMallocHost(&hActive, sizeof(int)));
+        // initial centre of mass (CUDA_Simulation: updateCurrentCenterOfMass + InitializeCenterOfMass)
+        if (nvTot) {
+            k_reduce_com<R><<<(unsigned)((nvTot + 255) / 256), 256, 0, stream>>>(A, 0);
+            k_world_finish<R><<<(n + 127) / 128, 128, 0, stream>>>(A, 0);
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(stream)); // host staging vectors die here
+        rcfg = resident_configure<R>(maxNv, maxNl, maxNs, residentThreads);
+        return VX3B_OK;
+    }
+
+    // ---- streaming path: CUDA graph of `chunk` steps -----------------------------------------------------
+    int launches_per_step() const { return 3 + (anyCollision ? 1 : 0) + ((anyCollision && recordPairs) ? 1 : 0); }
+    void enqueue_step(int useStop) {
+        const unsigned lb = (A.nlTot + 255) / 256, vb = (A.nvTot + 255) / 256, wb = (A.nWorlds + 127) / 128;
+        if (A.nlTot)
+            k_links<R><<<lb, 256, 0, stream>>>(A);
+        if (anyCollision && !hTiles.empty()) {
+            if (recordPairs)
+                k_zero_int<<<1, 1, 0, stream>>>(A.pairCount);
+            k_contact<R><<<(unsigned)hTiles.size(), 128, 0, stream>>>(A, dTiles, recordPairs);
+        }
+        k_voxels<R><<<vb, 256, 0, stream>>>(A);
+        k_world_step<R><<<wb, 128, 0, stream>>>(A, useStop, dActive);
+    }
+    int build_graph(int steps, int useStop) {
+        if (graphExec && graphChunk == steps && graphUseStop == useStop && graphRecord == recordPairs)
+            return VX3B_OK;
+        if (graphExec) {
+            cudaGraphExecDestroy(graphExec);
+            graphExec = nullptr;
+        }
+        cudaGraph_t g;
+        CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        for (int s = 0; s < steps; s++) {
+            if (s == steps - 1)
+                k_zero_int<<<1, 1, 0, stream>>>(dActive);
+            enqueue_step(useStop);
+        }
+        CUDA_TRY(cudaStreamEndCapture(stream, &g));
+        CUDA_TRY(cudaGraphInstantiate(&graphExec, g, 0));
+        cudaGraphDestroy(g);
+        graphChunk = steps;
+        graphUseStop = useStop;
+        graphRecord = recordPairs;
+        return VX3B_OK;
+    }
+
+    int run_streaming(int64_t maxSteps, int useStop) {
+        int64_t done = 0;
+        while (done < maxSteps) {
+            int steps = (int)std::min<int64_t>(chunk, maxSteps - done);
+            int rc = build_graph(steps, useStop);
+            if (rc != VX3B_OK)
+                return rc;
+            CUDA_TRY(cudaGraphLaunch(graphExec, stream));
+            lastLaunches += (int64_t)steps * launches_per_step() + 1;
+            done += steps;
+            CUDA_TRY(cudaMemcpyAsync(hActive, dActive, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (*hActive == 0)
+                break;
+        }
+        return VX3B_OK;
+    }
+
+    int run_resident(int64_t maxSteps, int useStop) {
+        int rc = resident_launch<R>(A, rcfg, maxSteps, useStop, recordPairs, stream);
+        if (rc != VX3B_OK)
+            return rc;
+        lastLaunches += 1;
+        return VX3B_OK;
+    }
+
+    int run(int64_t maxSteps, int useStop) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (H.empty()) {
+            set_error("vx3b_batch_run: nothing uploaded");
+            return VX3B_ERR_STATE;
+        }
+        lastLaunches = 0;
+        std::vector<int64_t> before(H.size());
+        int rc = read_steps(before);
+        if (rc != VX3B_OK)
+            return rc;
+        const unsigned wb = (A.nWorlds + 127) / 128;
+        CUDA_TRY(cudaEventRecord(ev0, stream));
+        k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)maxSteps, useStop);
+        lastLaunches++;
+        int use = path;
+        if (use == 0)
+            use = rcfg.ok ? 2 : 1;
+        if (use == 2 && !rcfg.ok) {
+            set_error("vx3b_batch_run: resident path requested but the largest world does not fit in shared memory");
+            return VX3B_ERR_ARG;
+        }
+        rc = (use == 2) ? run_resident(maxSteps, useStop) : run_streaming(maxSteps, useStop);
+        if (rc != VX3B_OK)
+            return rc;
+        if (A.nvTot) {
+            k_reduce_com<R><<<(unsigned)((A.nvTot + 255) / 256), 256, 0, stream>>>(A, 1);
+            k_world_finish<R><<<wb, 128, 0, stream>>>(A, 1);
+            lastLaunches += 2;
+        }
+        CUDA_TRY(cudaEventRecord(ev1, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventElapsedTime(&lastMs, ev0, ev1));
+        std::vector<int64_t> after(H.size());
+        rc = read_steps(after);
+        if (rc != VX3B_OK)
+            return rc;
+        lastVoxelSteps = 0;
+        for (size_t w = 0; w < H.size(); w++)
+            lastVoxelSteps += (after[w] - before[w]) * (int64_t)H[w].nv;
+        return VX3B_OK;
+    }
+
+    int read_steps(std::vector<int64_t> &out) {
+        std::vector<WorldD> hW(H.size());
+        CUDA_TRY(cudaMemcpyAsync(hW.data(), A.worlds, hW.size() * sizeof(WorldD), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (size_t w = 0; w < H.size(); w++)
+            out[w] = hW[w].step;
+        return VX3B_OK;
+    }
+
+    int results(VX3B_WorldResult *out) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (!out || H.empty()) {
+            set_error("vx3b_batch_results: nothing uploaded");
+            return VX3B_ERR_STATE;
+        }
+        std::vector<WorldD> hW(H.size());
+        CUDA_TRY(cudaMemcpyAsync(hW.data(), A.worlds, hW.size() * sizeof(WorldD), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        std::vector<int32_t> vmat(A.nvTot);
+        std::vector<DVoxMat> vm(bufsize_of(A.vmats) / sizeof(DVoxMat));
+        CUDA_TRY(cudaMemcpy(vmat.data(), A.vmat, vmat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(vm.data(), A.vmats, vm.size() * sizeof(DVoxMat), cudaMemcpyDeviceToHost));
+        for (size_t w = 0; w < H.size(); w++) {
+            const WorldD &W = hW[w];
+            VX3B_WorldResult &r = out[w];
+            memset(&r, 0, sizeof(r));
+            r.current_time = W.t;
+            r.fitness_score = W.fitness;
+            for (int k = 0; k < 3; k++) {
+                r.initial_com[k] = W.initialCom[k];
+                r.current_com[k] = W.com[k];
+            }
+            r.total_distance_of_all_voxels = W.totalDistance;
+            r.vox_size = W.voxSize;
+            r.recent_angle = W.recentAngle;
+            r.target_closeness = W.closeness;
+            r.dt = W.dt;
+            r.steps = W.step;
+            r.num_voxel = W.nv;
+            r.num_close_pairs = W.numClosePairs;
+            r.collision_count = W.collisionCount;
+            r.diverged = W.diverged;
+            r.stopped = W.stopped;
+            int measured = 0;
+            for (int v = 0; v < W.nv; v++)
+                if (vm[vmat[W.voff + v]].isMeasured)
+                    measured++;
+            r.num_measured_voxel = measured;
+        }
+        return VX3B_OK;
+    }
+
+    size_t bufsize_of(const void *p) const {
+        for (auto &b : bufs)
+            if (b->p == p)
+                return b->bytes;
+        return 0;
+    }
+
+    bool check_world(int world) {
+        if (world < 0 || world >= (int)H.size()) {
+            set_error("world index out of range");
+            return false;
+        }
+        return true;
+    }
+
+    int read_state(int world, double *pos, double *orient, double *lin, double *ang) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (!check_world(world))
+            return VX3B_ERR_ARG;
+        const WorldHost &h = H[world];
+        std::vector<D2> pxy(h.nv), pzt(h.nv);
+        std::vector<T4> o(h.nv), lm(h.nv);
+        std::vector<T2> am(h.nv);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemcpy(pxy.data(), A.pxy + h.voff, h.nv * sizeof(D2), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(pzt.data(), A.pzt + h.voff, h.nv * sizeof(D2), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(o.data(), A.orient + h.voff, h.nv * sizeof(T4), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(lm.data(), A.lm + h.voff, h.nv * sizeof(T4), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(am.data(), A.am + h.voff, h.nv * sizeof(T2), cudaMemcpyDeviceToHost));
+        for (int v = 0; v < h.nv; v++) {
+            if (pos) {
+                pos[v * 3] = pxy[v].x;
+                pos[v * 3 + 1] = pxy[v].y;
+                pos[v * 3 + 2] = pzt[v].x;
+            }
+            if (orient) {
+                orient[v * 4] = o[v].x;
+                orient[v * 4 + 1] = o[v].y;
+                orient[v * 4 + 2] = o[v].z;
+                orient[v * 4 + 3] = o[v].w;
+            }
+            if (lin) {
+                lin[v * 3] = lm[v].x;
+                lin[v * 3 + 1] = lm[v].y;
+                lin[v * 3 + 2] = lm[v].z;
+            }
+            if (ang) {
+                ang[v * 3] = lm[v].w;
+                ang[v * 3 + 1] = am[v].x;
+                ang[v * 3 + 2] = am[v].y;
+            }
+        }
+        return VX3B_OK;
+    }
+
+    int read_initial_pos(int world, double *pos) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (!check_world(world) || !pos)
+            return VX3B_ERR_ARG;
+        const WorldHost &h = H[world];
+        std::vector<D2> pxy(h.nv);
+        std::vector<double> pz(h.nv);
+        CUDA_TRY(cudaMemcpy(pxy.data(), A.ipxy + h.voff, h.nv * sizeof(D2), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(pz.data(), A.ipz + h.voff, h.nv * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int v = 0; v < h.nv; v++) {
+            pos[v * 3] = pxy[v].x;
+            pos[v * 3 + 1] = pxy[v].y;
+            pos[v * 3 + 2] = pz[v];
+        }
+        return VX3B_OK;
+    }
+
+    int read_links(int world, double *pos2, double *a1, double *a2, int32_t *flags) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (!check_world(world))
+            return VX3B_ERR_ARG;
+        const WorldHost &h = H[world];
+        std::vector<T4> p(h.nl), x1(h.nl), x2(h.nl);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemcpy(p.data(), A.lpos2 + h.loff, h.nl * sizeof(T4), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(x1.data(), A.la1 + h.loff, h.nl * sizeof(T4), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(x2.data(), A.la2 + h.loff, h.nl * sizeof(T4), cudaMemcpyDeviceToHost));
+        for (int l = 0; l < h.nl; l++) {
+            if (pos2) {
+                pos2[l * 3] = p[l].x;
+                pos2[l * 3 + 1] = p[l].y;
+                pos2[l * 3 + 2] = p[l].z;
+            }
+            if (a1) {
+                a1[l * 3] = x1[l].x;
+                a1[l * 3 + 1] = x1[l].y;
+                a1[l * 3 + 2] = x1[l].z;
+            }
+            if (a2) {
+                a2[l * 3] = x2[l].x;
+                a2[l * 3 + 1] = x2[l].y;
+                a2[l * 3 + 2] = x2[l].z;
+            }
+            if (flags) {
+                uint32_t f;
+                if constexpr (sizeof(R) == 4)
+                    memcpy(&f, &p[l].w, 4);
+                else {
+                    long long b;
+                    memcpy(&b, &p[l].w, 8);
+                    f = (uint32_t)b;
+                }
+                flags[l] = (int32_t)f;
+            }
+        }
+        return VX3B_OK;
+    }
+
+    int collision_pairs(int world, int32_t *pairs, int32_t *n) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (!check_world(world) || !n)
+            return VX3B_ERR_ARG;
+        if (!recordPairs) {
+            set_error("vx3b_batch_collision_pairs: set option record_pairs=1 before vx3b_batch_upload");
+            return VX3B_ERR_STATE;
+        }
+        int count = 0;
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemcpy(&count, A.pairCount, sizeof(int), cudaMemcpyDeviceToHost));
+        if (count > A.pairCap) {
+            set_error("vx3b_batch_collision_pairs: pair buffer overflow");
+            return VX3B_ERR_STATE;
+        }
+        std::vector<int4> buf(count);
+        if (count)
+            CUDA_TRY(cudaMemcpy(buf.data(), A.pairBuf, count * sizeof(int4), cudaMemcpyDeviceToHost));
+        std::vector<std::pair<int, int>> mine;
+        for (auto &p : buf)
+            if (p.x == world)
+                mine.emplace_back(p.y, p.z);
+        std::sort(mine.begin(), mine.end());
+        int cap = *n;
+        *n = (int)mine.size();
+        if (pairs)
+            for (int i = 0; i < (int)mine.size() && i < cap; i++) {
+                pairs[i * 2] = mine[i].first;
+                pairs[i * 2 + 1] = mine[i].second;
+            }
+        return VX3B_OK;
+    }
+};
+
+} // namespace vx3b
+
+struct vx3b_ctx {
+    std::unique_ptr<vx3b::EngineBase> e;
+};
+
+extern "C" {
+
+const char *vx3b_version(void) { return "vx3b200 0.1 (sm_100a)"; }
+
+int vx3b_ctx_create(int device, int precision, vx3b_ctx **out) {
+    using namespace vx3b;
+    if (!out || (precision != VX3B_FP32 && precision != VX3B_FP64)) {
+        set_error("vx3b_ctx_create: precision must be VX3B_FP32 or VX3B_FP64");
+        return VX3B_ERR_ARG;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("vx3b_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU fallback");
+        return VX3B_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        set_error("vx3b_ctx_create: device index out of range");
+        return VX3B_ERR_ARG;
+    }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("vx3b_ctx_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+        return VX3B_ERR_CUDA;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    auto *c = new vx3b_ctx();
+    if (precision == VX3B_FP32)
+        c->e = std::make_unique<Engine<float>>();
+    else
+        c->e = std::make_unique<Engine<double>>();
+    c->e->device = device;
+    c->e->precision = precision;
+    *out = c;
+    return VX3B_OK;
+}
+
+void vx3b_ctx_destroy(vx3b_ctx *ctx) { delete ctx; }
+
+int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value) {
+    if (!ctx || !name)
+        return VX3B_ERR_ARG;
+    std::string n = name;
+    if (n == "path")
+        ctx->e->path = (int)value;
+    else if (n == "record_pairs")
+        ctx->e->recordPairs = value != 0;
+    else if (n == "chunk")
+        ctx->e->chunk = std::max(1, (int)value);
+    else if (n == "dt_override")
+        ctx->e->dtOverride = value;
+    else if (n == "resident_threads")
+        ctx->e->residentThreads = (int)value;
+    else {
+        vx3b::set_error("unknown option: " + n);
+        return VX3B_ERR_ARG;
+    }
+    return VX3B_OK;
+}
+
+int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t s) {
+    if (!ctx)
+        return VX3B_ERR_ARG;
+    if (ctx->e->ownStream && ctx->e->stream)
+        cudaStreamDestroy(ctx->e->stream);
+    ctx->e->stream = (cudaStream_t)s;
+    ctx->e->ownStream = false;
+    return VX3B_OK;
+}
+
+int vx3b_batch_upload(vx3b_ctx *ctx, const VX3B_WorldDesc *worlds, int n) { return ctx ? ctx->e->upload(worlds, n) : VX3B_ERR_ARG; }
+int vx3b_batch_run(vx3b_ctx *ctx, int64_t max_steps, int use_stop) { return ctx ? ctx->e->run(max_steps, use_stop) : VX3B_ERR_ARG; }
+int vx3b_batch_results(vx3b_ctx *ctx, VX3B_WorldResult *out) { return ctx ? ctx->e->results(out) : VX3B_ERR_ARG; }
+int vx3b_batch_read_state(vx3b_ctx *ctx, int world, double *p, double *o, double *l, double *a) {
+    return ctx ? ctx->e->read_state(world, p, o, l, a) : VX3B_ERR_ARG;
+}
+int vx3b_batch_read_initial_pos(vx3b_ctx *ctx, int world, double *p) { return ctx ? ctx->e->read_initial_pos(world, p) : VX3B_ERR_ARG; }
+int vx3b_batch_read_links(vx3b_ctx *ctx, int world, double *p2, double *a1, double *a2, int32_t *f) {
+    return ctx ? ctx->e->read_links(world, p2, a1, a2, f) : VX3B_ERR_ARG;
+}
+int vx3b_batch_collision_pairs(vx3b_ctx *ctx, int world, int32_t *pairs, int32_t *n) {
+    return ctx ? ctx->e->collision_pairs(world, pairs, n) : VX3B_ERR_ARG;
+}
+int vx3b_ctx_timing(vx3b_ctx *ctx, float *ms, int64_t *launches) {
+    if (!ctx)
+        return VX3B_ERR_ARG;
+    if (ms)
+        *ms = ctx->e->lastMs;
+    if (launches)
+        *launches = ctx->e->lastLaunches;
+    return VX3B_OK;
+}
+int64_t vx3b_ctx_total_voxel_steps(vx3b_ctx *ctx) { return ctx ? ctx->e->lastVoxelSteps : 0; }
+
+} // extern "C"

@@ -1,0 +1,127 @@
+// Engine-internal declarations shared by engine.cu and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "physics.cuh"
+#include "vx3b200.h"
+
+namespace vx3b {
+
+void set_error(const std::string &e);
+
+// ---- 4-wide / 2-wide storage vectors per arithmetic type ---------------------------------------
+struct alignas(16) D2 {
+    double x, y;
+};
+struct alignas(32) D4 {
+    double x, y, z, w;
+};
+template <class R> struct Store;
+template <> struct Store<float> {
+    using T4 = float4;
+    using T2 = float2;
+};
+template <> struct Store<double> {
+    using T4 = D4;
+    using T2 = D2;
+};
+template <class R> VXD typename Store<R>::T4 mk4(R x, R y, R z, R w) {
+    typename Store<R>::T4 v;
+    v.x = x;
+    v.y = y;
+    v.z = z;
+    v.w = w;
+    return v;
+}
+template <class R> VXD typename Store<R>::T2 mk2(R x, R y) {
+    typename Store<R>::T2 v;
+    v.x = x;
+    v.y = y;
+    return v;
+}
+VXD uint32_t f2u(float f) { return __float_as_uint(f); }
+VXD float u2f(uint32_t u) { return __uint_as_float(u); }
+
+// ---- per-world device record ---------------------------------------------------------------------
+enum {
+    WF_FLOOR = 1, WF_VARY_TEMP = 2, WF_COLLISION = 4, WF_CILIA = 8, WF_EXPANSION = 16, WF_VX3 = 32, WF_FORCE_FIELD = 64,
+    WF_STOP_FORMULA = 128
+};
+struct WorldD {
+    // static
+    int32_t voff, nv, loff, nl, soff, ns, vmatOff, lmatOff;
+    uint32_t flags;
+    int32_t cycle; // int(TempPeriod/dt): COM/angle sampling period in steps (0 = never)
+    float dt;
+    float pad0;
+    double tempAmp, tempPeriod, voxSize, maxDistPair;
+    // dynamic
+    double t;
+    int64_t step;     // CurStepCount
+    int64_t runSteps; // steps left in the current vx3b_batch_run
+    int32_t active, diverged, stopped, divergedNow;
+    int32_t angleSamples, numClosePairs, collisionCount, pad1;
+    double recentAngle, closeness, fitness, totalDistance;
+    double comAcc[4]; // Σ m·x, Σ m·y, Σ m·z, Σ m  (measured voxels)
+    double distAcc;
+    double com[3], initialCom[3], comHist[2][3];
+    int32_t numMeasured, pad2;
+    VX3B_Token stop[VX3B_MAX_TOKENS], fitnessF[VX3B_MAX_TOKENS], ff[3 * VX3B_MAX_TOKENS];
+};
+
+struct DExt { // compact table of voxels that carry boundary conditions
+    uint32_t dof;
+    float force[3], moment[3];
+    double translation[3];
+    double rotQ[4];
+};
+
+// ---- all device arrays of a batch (struct of arrays; worlds concatenated) ------------------------------
+template <class R> struct Arrays {
+    using T4 = typename Store<R>::T4;
+    using T2 = typename Store<R>::T2;
+    int nvTot, nlTot, nsTot, nWorlds;
+    WorldD *worlds;
+    // voxel state (read+write every step)
+    D2 *pxy;  // pos.x, pos.y
+    D2 *pzt;  // pos.z, {float temp | uint32 flags} packed in the second double's bits
+    T4 *orient; // w,x,y,z
+    T4 *lm;     // linMom.xyz, angMom.x
+    T2 *am;     // angMom.y, angMom.z
+    // voxel static
+    int32_t *vmat;   // global index into vmats
+    int32_t *vworld; // world of each voxel
+    int32_t *vlinks; // [6][nvTot] global link index or -1 (direction-major)
+    int32_t *vsurf;  // surface slot (global) or -1
+    int32_t *vext;   // index into ext or -1
+    short4 *lat;     // lattice ix,iy,iz (w unused)
+    double *phase;   // or nullptr
+    D4 *baseCilia;   // xyz (w unused) or nullptr
+    D2 *ipxy;        // initial positions (results: total_distance_of_all_voxels)
+    double *ipz;
+    DExt *ext;
+    // surface
+    int32_t *surf;   // [nsTot] global voxel index, creation order inside each world
+    T4 *contactF;    // [nsTot] contact force accumulated for the voxel pass
+    // links
+    T4 *lpos2; // pos2.xyz, flags (bit pattern)
+    T4 *la1;   // angle1v.xyz, maxStrain
+    T4 *la2;   // angle2v.xyz, strain
+    int2 *lends;     // global voxel index of (neg, pos)
+    uint32_t *lmeta; // axis (bits 0-1) | global link-material index << 2
+    int32_t *lworld;
+    T4 *lfN, *lfP, *lmN, *lmP; // link forces/moments for the voxel pass (streaming path only)
+    // materials
+    DVoxMat *vmats;
+    DLinkMat *lmats;
+    // pair recording (parity tests)
+    int4 *pairBuf;
+    int32_t *pairCount;
+    int32_t pairCap;
+};
+
+} // namespace vx3b

@@ -1,0 +1,230 @@
+// Job level of the C ABI: a directory of base.vxa + *.vxd -> report XML.
+// Replaces vx3_node_worker's main (Voxelyze3/src/Executables/vx3_node_worker.cu:32-142) and
+// VX3_SimulationManager::start / readVXD / collectResults / sortResults
+// (Voxelyze3/src/VX3/VX3_SimulationManager.cu:138-155, 277-380, 416-460), with one host thread per device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dirent.h>
+#include <fstream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <thread>
+#include <vector>
+
+#include "host_model.hpp"
+#include "vx3b200.h"
+
+namespace vx3b {
+void set_error(const std::string &e);
+
+struct JobWorld {
+    std::string file;
+    vx3b_model *model = nullptr;
+    VX3B_WorldDesc desc;
+    VX3B_WorldResult res;
+    std::vector<double> pos, initPos;
+};
+
+static bool read_file(const std::string &p, std::string *out) {
+    std::ifstream f(p, std::ios::binary);
+    if (!f)
+        return false;
+    std::stringstream ss;
+    ss << f.rdbuf();
+    *out = ss.str();
+    return true;
+}
+
+static std::string fmt_double(double v) { // boost ptree's stream translator: max_digits10 significant digits
+    char b[64];
+    snprintf(b, sizeof(b), "%.17g", v);
+    return b;
+}
+
+static bool ends_with_ci(const std::string &s, const std::string &ext) { // ctool::u_with_ext: case-insensitive extension match
+    if (s.size() < ext.size())
+        return false;
+    for (size_t i = 0; i < ext.size(); i++)
+        if (tolower((unsigned char)s[s.size() - ext.size() + i]) != tolower((unsigned char)ext[i]))
+            return false;
+    return true;
+}
+
+// fitness descending, NaN last (VX3_SimulationResult.h:26-33)
+static bool better(const JobWorld *a, const JobWorld *b) {
+    if (std::isnan(b->res.fitness_score))
+        return !std::isnan(a->res.fitness_score);
+    if (std::isnan(a->res.fitness_score))
+        return false;
+    return a->res.fitness_score > b->res.fitness_score;
+}
+
+} // namespace vx3b
+
+extern "C" int vx3b_job_run(const char *input_dir, const char *report_path, int num_devices, int precision) {
+    using namespace vx3b;
+    if (!input_dir || !report_path || num_devices < 1) {
+        set_error("vx3b_job_run: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    std::string dir = input_dir, base;
+    if (!read_file(dir + "/base.vxa", &base)) {
+        set_error("vx3b_job_run: no base.vxa in " + dir);
+        return VX3B_ERR_IO;
+    }
+    std::vector<std::string> files;
+    if (DIR *d = opendir(dir.c_str())) {
+        while (dirent *e = readdir(d))
+            if (ends_with_ci(e->d_name, ".vxd"))
+                files.push_back(e->d_name);
+        closedir(d);
+    }
+    std::sort(files.begin(), files.end());
+    if (files.empty()) {
+        set_error("vx3b_job_run: no .vxd files in " + dir);
+        return VX3B_ERR_IO;
+    }
+    std::vector<JobWorld> worlds(files.size());
+    for (size_t i = 0; i < files.size(); i++) {
+        std::string vxd;
+        if (!read_file(dir + "/" + files[i], &vxd)) {
+            set_error("vx3b_job_run: cannot read " + files[i]);
+            return VX3B_ERR_IO;
+        }
+        worlds[i].file = files[i];
+        int rc = vx3b_model_from_vxa(base.c_str(), vxd.c_str(), &worlds[i].model);
+        if (rc != VX3B_OK) {
+            std::string msg = std::string(files[i]) + ": " + vx3b_last_error();
+            for (auto &w : worlds)
+                if (w.model)
+                    vx3b_model_free(w.model);
+            set_error(msg);
+            return rc;
+        }
+        vx3b_model_desc(worlds[i].model, &worlds[i].desc);
+    }
+    // round-robin split over devices (vx3_node_worker.cu:88-93), one host thread and one context per device
+    std::vector<std::vector<int>> sub(num_devices);
+    for (size_t i = 0; i < worlds.size(); i++)
+        sub[i % num_devices].push_back((int)i);
+    std::vector<int> status(num_devices, VX3B_OK);
+    std::vector<std::string> errors(num_devices);
+    std::vector<std::thread> threads;
+    for (int dev = 0; dev < num_devices; dev++) {
+        if (sub[dev].empty())
+            continue;
+        threads.emplace_back([&, dev]() {
+            vx3b_ctx *ctx = nullptr;
+            auto fail = [&](int rc) {
+                status[dev] = rc;
+                errors[dev] = vx3b_last_error();
+                if (ctx)
+                    vx3b_ctx_destroy(ctx);
+            };
+            int rc = vx3b_ctx_create(dev, precision, &ctx);
+            if (rc != VX3B_OK)
+                return fail(rc);
+            std::vector<VX3B_WorldDesc> descs;
+            for (int i : sub[dev])
+                descs.push_back(worlds[i].desc);
+            if ((rc = vx3b_batch_upload(ctx, descs.data(), (int)descs.size())) != VX3B_OK)
+                return fail(rc);
+            if ((rc = vx3b_batch_run(ctx, 1000000, 1)) != VX3B_OK) // "Maximum Steps 1000000" (VX3_SimulationManager.cu:62)
+                return fail(rc);
+            std::vector<VX3B_WorldResult> res(descs.size());
+            if ((rc = vx3b_batch_results(ctx, res.data())) != VX3B_OK)
+                return fail(rc);
+            for (size_t k = 0; k < sub[dev].size(); k++) {
+                JobWorld &w = worlds[sub[dev][k]];
+                w.res = res[k];
+                if (w.desc.save_position_of_all_voxels) {
+                    w.pos.resize((size_t)w.desc.num_voxels * 3);
+                    w.initPos.resize((size_t)w.desc.num_voxels * 3);
+                    vx3b_batch_read_state(ctx, (int)k, w.pos.data(), nullptr, nullptr, nullptr);
+                    vx3b_batch_read_initial_pos(ctx, (int)k, w.initPos.data());
+                }
+            }
+            vx3b_ctx_destroy(ctx);
+        });
+    }
+    for (auto &t : threads)
+        t.join();
+    int rcAll = VX3B_OK;
+    for (int dev = 0; dev < num_devices; dev++)
+        if (status[dev] != VX3B_OK) {
+            rcAll = status[dev];
+            set_error("device " + std::to_string(dev) + ": " + errors[dev]);
+        }
+    if (rcAll == VX3B_OK) {
+        std::vector<JobWorld *> order;
+        for (auto &w : worlds)
+            order.push_back(&w);
+        std::stable_sort(order.begin(), order.end(), better);
+        // report layout: vx3_node_worker.cu:98-141
+        std::string inputName = dir;
+        while (inputName.size() > 1 && inputName.back() == '/')
+            inputName.pop_back();
+        size_t slash = inputName.find_last_of('/');
+        if (slash != std::string::npos)
+            inputName = inputName.substr(slash + 1);
+        XmlNode report;
+        report.name = "report";
+        auto add = [](XmlNode &p, const std::string &name, const std::string &text) -> XmlNode & {
+            auto n = std::make_unique<XmlNode>();
+            n->name = name;
+            n->text = text;
+            p.children.push_back(std::move(n));
+            return *p.children.back();
+        };
+        add(report, "inputdir", inputName);
+        XmlNode &best = add(report, "bestfit", "");
+        add(best, "filename", order[0]->file);
+        add(best, "fitness_score", fmt_double(order[0]->res.fitness_score));
+        XmlNode &detail = add(report, "detail", "");
+        for (JobWorld *w : order) {
+            std::string name = w->file.substr(0, w->file.find('.'));
+            XmlNode &n = add(detail, name, "");
+            const VX3B_WorldResult &r = w->res;
+            add(n, "currentTime", fmt_double(r.current_time));
+            add(n, "fitness_score", fmt_double(r.fitness_score));
+            add(n, "num_voxel", std::to_string(r.num_voxel));
+            add(n, "num_measured_voxel", std::to_string(r.num_measured_voxel));
+            add(n, "voxSize", fmt_double(r.vox_size));
+            add(n, "numClosePairs", std::to_string(r.num_close_pairs));
+            XmlNode &ic = add(n, "initialCenterOfMass", "");
+            add(ic, "x", fmt_double(r.initial_com[0]));
+            add(ic, "y", fmt_double(r.initial_com[1]));
+            add(ic, "z", fmt_double(r.initial_com[2]));
+            XmlNode &cc = add(n, "currentCenterOfMass", "");
+            add(cc, "x", fmt_double(r.current_com[0]));
+            add(cc, "y", fmt_double(r.current_com[1]));
+            add(cc, "z", fmt_double(r.current_com[2]));
+            add(n, "total_distance_of_all_voxels", fmt_double(r.total_distance_of_all_voxels));
+            if (w->desc.save_position_of_all_voxels) {
+                std::string ip, p, mats;
+                for (int v = 0; v < w->desc.num_voxels; v++) { // std::to_string(double): "%f"
+                    ip += std::to_string(w->initPos[v * 3]) + "," + std::to_string(w->initPos[v * 3 + 1]) + "," + std::to_string(w->initPos[v * 3 + 2]) + ";";
+                    p += std::to_string(w->pos[v * 3]) + "," + std::to_string(w->pos[v * 3 + 1]) + "," + std::to_string(w->pos[v * 3 + 2]) + ";";
+                    mats += std::to_string(w->desc.voxel_mats[w->desc.voxel_mat[v]].matid) + ";";
+                }
+                add(n, "init_pos", ip);
+                add(n, "pos", p);
+                add(n, "mats", mats);
+            }
+        }
+        std::ofstream out(report_path, std::ios::binary);
+        if (!out) {
+            set_error(std::string("vx3b_job_run: cannot write ") + report_path);
+            rcAll = VX3B_ERR_IO;
+        } else
+            out << xml_write(report, true);
+    }
+    for (auto &w : worlds)
+        if (w.model)
+            vx3b_model_free(w.model);
+    return rcAll;
+}

@@ -1,0 +1,486 @@
+// Resident path: one CTA per world, the whole world state lives in shared memory for the entire run
+// (all steps in ONE launch), so a generation of small xenobot-scale worlds touches HBM only at the
+// start and at the end.  Worlds are independent, so there is no inter-CTA communication at all.
+//
+// Replaces, for worlds that fit, the reference's one-thread-per-world CUDA_Simulation driver with its
+// 3-6 child launches + device-wide syncs per step (VX3/VX3_SimulationManager.cu:11-121,
+// VX3/VX3_VoxelyzeKernel.cu:237-359).
+#pragma once
+#include "engine.cuh"
+#include "kernels_stream.cuh"
+
+namespace vx3b {
+
+template <class R> struct R3 {
+    R x, y, z;
+};
+
+// shared-memory layout for capacities (capV, capL, capS); every array is 16-byte aligned
+template <class R> struct ResidentLayout {
+    size_t pos, orient, linMom, angMom, temp, vflags, vmat, vlinks, lat, phase, cilia, vext, vsurfslot;
+    size_t lpos2, la1, la2, lflags, lmaxs, lends, lmeta, lfN, lfP, lmN, lmP;
+    size_t surf, contactF;
+    size_t total;
+    __host__ __device__ static size_t up(size_t x) { return (x + 15) & ~(size_t)15; }
+    __host__ __device__ ResidentLayout(int capV, int capL, int capS) {
+        size_t o = 0;
+        auto take = [&](size_t bytes) {
+            size_t at = o;
+            o = up(o + bytes);
+            return at;
+        };
+        pos = take(sizeof(double) * 3 * capV);
+        orient = take(sizeof(R) * 4 * capV);
+        linMom = take(sizeof(R) * 3 * capV);
+        angMom = take(sizeof(R) * 3 * capV);
+        temp = take(sizeof(float) * capV);
+        vflags = take(capV);
+        vmat = take(sizeof(uint16_t) * capV);
+        vlinks = take(sizeof(uint16_t) * 6 * capV);
+        lat = take(sizeof(short4) * capV);
+        phase = take(sizeof(double) * capV);
+        cilia = take(sizeof(float) * 3 * capV);
+        vext = take(sizeof(int32_t) * capV);
+        vsurfslot = take(sizeof(uint16_t) * capV);
+        lpos2 = take(sizeof(R) * 3 * capL);
+        la1 = take(sizeof(R) * 3 * capL);
+        la2 = take(sizeof(R) * 3 * capL);
+        lflags = take(capL);
+        lmaxs = take(sizeof(float) * capL);
+        lends = take(sizeof(uint16_t) * 2 * capL);
+        lmeta = take(sizeof(uint16_t) * capL);
+        lfN = take(sizeof(R) * 3 * capL);
+        lfP = take(sizeof(R) * 3 * capL);
+        lmN = take(sizeof(R) * 3 * capL);
+        lmP = take(sizeof(R) * 3 * capL);
+        surf = take(sizeof(uint16_t) * capS);
+        contactF = take(sizeof(R) * 3 * capS);
+        total = o;
+    }
+};
+
+struct ResidentShared { // block-wide scalars
+    int32_t diverged, hits, comFlag, pad;
+    double com[4];
+};
+
+template <class R>
+__global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long maxSteps, int useStop, int recordPairs) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ ResidentShared sh;
+    const int w = blockIdx.x;
+    WorldD &W = A.worlds[w];
+    if (!W.active)
+        return;
+    const ResidentLayout<R> L(capV, capL, capS);
+    double *sPos = (double *)(smem + L.pos);
+    R *sOri = (R *)(smem + L.orient);
+    R *sLin = (R *)(smem + L.linMom);
+    R *sAng = (R *)(smem + L.angMom);
+    float *sTemp = (float *)(smem + L.temp);
+    uint8_t *sVflags = smem + L.vflags;
+    uint16_t *sVmat = (uint16_t *)(smem + L.vmat);
+    uint16_t *sVlinks = (uint16_t *)(smem + L.vlinks);
+    short4 *sLat = (short4 *)(smem + L.lat);
+    double *sPhase = (double *)(smem + L.phase);
+    float *sCilia = (float *)(smem + L.cilia);
+    int32_t *sVext = (int32_t *)(smem + L.vext);
+    uint16_t *sVsurf = (uint16_t *)(smem + L.vsurfslot);
+    R *sP2 = (R *)(smem + L.lpos2);
+    R *sA1 = (R *)(smem + L.la1);
+    R *sA2 = (R *)(smem + L.la2);
+    uint8_t *sLflags = smem + L.lflags;
+    float *sLmax = (float *)(smem + L.lmaxs);
+    uint16_t *sLends = (uint16_t *)(smem + L.lends);
+    uint16_t *sLmeta = (uint16_t *)(smem + L.lmeta);
+    R *sFN = (R *)(smem + L.lfN);
+    R *sFP = (R *)(smem + L.lfP);
+    R *sMN = (R *)(smem + L.lmN);
+    R *sMP = (R *)(smem + L.lmP);
+    uint16_t *sSurf = (uint16_t *)(smem + L.surf);
+    R *sCF = (R *)(smem + L.contactF);
+
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int nv = W.nv, nl = W.nl, ns = W.ns, voff = W.voff, loff = W.loff, soff = W.soff;
+    const uint32_t wflags = W.flags;
+    const bool vx3 = wflags & WF_VX3, floorOn = wflags & WF_FLOOR, collide = (wflags & WF_COLLISION) && ns > 1;
+    const bool ciliaOn = (wflags & WF_CILIA) && A.baseCilia, varyTemp = (wflags & WF_VARY_TEMP) && W.tempPeriod > 0;
+    const float dt = W.dt;
+    const double voxSize = W.voxSize, tempAmp = W.tempAmp, tempPeriod = W.tempPeriod;
+    const int cycle = W.cycle;
+    const DVoxMat *vmats = A.vmats + W.vmatOff;
+    const DLinkMat *lmats = A.lmats + W.lmatOff;
+
+    // ---- load the world into shared memory --------------------------------------------------------------
+    for (int v = tid; v < nv; v += nt) {
+        const int g = voff + v;
+        float temp;
+        uint32_t fl;
+        V3<double> p = load_pos(A, g, &temp, &fl);
+        sPos[3 * v] = p.x;
+        sPos[3 * v + 1] = p.y;
+        sPos[3 * v + 2] = p.z;
+        auto o = A.orient[g];
+        auto lm = A.lm[g];
+        auto am = A.am[g];
+        sOri[4 * v] = o.x;
+        sOri[4 * v + 1] = o.y;
+        sOri[4 * v + 2] = o.z;
+        sOri[4 * v + 3] = o.w;
+        sLin[3 * v] = lm.x;
+        sLin[3 * v + 1] = lm.y;
+        sLin[3 * v + 2] = lm.z;
+        sAng[3 * v] = lm.w;
+        sAng[3 * v + 1] = am.x;
+        sAng[3 * v + 2] = am.y;
+        sTemp[v] = temp;
+        sVflags[v] = (uint8_t)fl;
+        sVmat[v] = (uint16_t)(A.vmat[g] - W.vmatOff);
+        for (int k = 0; k < 6; k++) {
+            int l = A.vlinks[(size_t)k * A.nvTot + g];
+            sVlinks[6 * v + k] = l < 0 ? (uint16_t)0xffff : (uint16_t)(l - loff);
+        }
+        sLat[v] = A.lat[g];
+        sPhase[v] = A.phase ? A.phase[g] : 0.0;
+        if (A.baseCilia) {
+            D4 b = A.baseCilia[g];
+            sCilia[3 * v] = (float)b.x;
+            sCilia[3 * v + 1] = (float)b.y;
+            sCilia[3 * v + 2] = (float)b.z;
+        }
+        sVext[v] = A.vext[g];
+        int slot = A.vsurf[g];
+        sVsurf[v] = slot < 0 ? (uint16_t)0xffff : (uint16_t)(slot - soff);
+    }
+    for (int l = tid; l < nl; l += nt) {
+        const int g = loff + l;
+        auto s0 = A.lpos2[g], s1 = A.la1[g], s2 = A.la2[g];
+        sP2[3 * l] = s0.x;
+        sP2[3 * l + 1] = s0.y;
+        sP2[3 * l + 2] = s0.z;
+        sA1[3 * l] = s1.x;
+        sA1[3 * l + 1] = s1.y;
+        sA1[3 * l + 2] = s1.z;
+        sA2[3 * l] = s2.x;
+        sA2[3 * l + 1] = s2.y;
+        sA2[3 * l + 2] = s2.z;
+        uint32_t fl;
+        if constexpr (sizeof(R) == 4)
+            fl = f2u(s0.w);
+        else
+            fl = (uint32_t)__double_as_longlong(s0.w);
+        sLflags[l] = (uint8_t)fl;
+        sLmax[l] = (float)s1.w;
+        int2 e = A.lends[g];
+        sLends[2 * l] = (uint16_t)(e.x - voff);
+        sLends[2 * l + 1] = (uint16_t)(e.y - voff);
+        uint32_t meta = A.lmeta[g];
+        sLmeta[l] = (uint16_t)((meta & 3) | (((meta >> 2) - W.lmatOff) << 2));
+        for (int k = 0; k < 3; k++)
+            sFN[3 * l + k] = sFP[3 * l + k] = sMN[3 * l + k] = sMP[3 * l + k] = R(0);
+    }
+    for (int s = tid; s < ns; s += nt) {
+        sSurf[s] = (uint16_t)(A.surf[soff + s] - voff);
+        sCF[3 * s] = sCF[3 * s + 1] = sCF[3 * s + 2] = R(0);
+    }
+    if (tid == 0) {
+        sh.diverged = 0;
+        sh.hits = 0;
+        sh.com[0] = sh.com[1] = sh.com[2] = sh.com[3] = 0;
+    }
+    __syncthreads();
+
+    // world scalars that change during the run live in registers of every thread (all threads compute them identically)
+    double t = W.t;
+    long long step = W.step;
+    long long left = maxSteps;
+    int collisionCount = W.collisionCount;
+    bool running = true;
+
+    while (running) {
+        // ---- link pass ----------------------------------------------------------------------------------------
+        for (int l = tid; l < nl; l += nt) {
+            const int a = sLends[2 * l], b = sLends[2 * l + 1];
+            const uint32_t meta = sLmeta[l];
+            const int axis = meta & 3;
+            const DVoxMat &mn = vmats[sVmat[a]], &mp = vmats[sVmat[b]];
+            if (vx3 && mn.fixed && mp.fixed)
+                continue;
+            const DLinkMat lmat = lmats[meta >> 2];
+            V3<double> dpos{sPos[3 * b] - sPos[3 * a], sPos[3 * b + 1] - sPos[3 * a + 1], sPos[3 * b + 2] - sPos[3 * a + 2]};
+            Qt<R> qn{sOri[4 * a], sOri[4 * a + 1], sOri[4 * a + 2], sOri[4 * a + 3]};
+            Qt<R> qp{sOri[4 * b], sOri[4 * b + 1], sOri[4 * b + 2], sOri[4 * b + 3]};
+            double restLen = 0.5 * (base_size(mn, sTemp[a]) + base_size(mp, sTemp[b]));
+            LinkHist<R> h;
+            h.pos2 = {sP2[3 * l], sP2[3 * l + 1], sP2[3 * l + 2]};
+            h.a1v = {sA1[3 * l], sA1[3 * l + 1], sA1[3 * l + 2]};
+            h.a2v = {sA2[3 * l], sA2[3 * l + 1], sA2[3 * l + 2]};
+            h.flags = sLflags[l];
+            h.maxStrain = sLmax[l];
+            float dmN = mn.sqrtMassZetaInt2 / ((vx3 && mn.fixed) ? 0.0f : dt);
+            float dmP = mp.sqrtMassZetaInt2 / ((vx3 && mp.fixed) ? 0.0f : dt);
+            LinkForces<R> f;
+            link_update<R>(lmat, axis, dpos, voxSize, qn, qp, restLen, dmN, dmP, h, f);
+            sP2[3 * l] = h.pos2.x;
+            sP2[3 * l + 1] = h.pos2.y;
+            sP2[3 * l + 2] = h.pos2.z;
+            sA1[3 * l] = h.a1v.x;
+            sA1[3 * l + 1] = h.a1v.y;
+            sA1[3 * l + 2] = h.a1v.z;
+            sA2[3 * l] = h.a2v.x;
+            sA2[3 * l + 1] = h.a2v.y;
+            sA2[3 * l + 2] = h.a2v.z;
+            sLflags[l] = (uint8_t)h.flags;
+            sLmax[l] = h.maxStrain;
+            sFN[3 * l] = f.fNeg.x;
+            sFN[3 * l + 1] = f.fNeg.y;
+            sFN[3 * l + 2] = f.fNeg.z;
+            sFP[3 * l] = f.fPos.x;
+            sFP[3 * l + 1] = f.fPos.y;
+            sFP[3 * l + 2] = f.fPos.z;
+            sMN[3 * l] = f.mNeg.x;
+            sMN[3 * l + 1] = f.mNeg.y;
+            sMN[3 * l + 2] = f.mNeg.z;
+            sMP[3 * l] = f.mPos.x;
+            sMP[3 * l + 1] = f.mPos.y;
+            sMP[3 * l + 2] = f.mPos.z;
+            if (f.strain > 100.0f)
+                sh.diverged = 1;
+        }
+        // ---- contact: all pairs of surface voxels (positions of the step start) -------------------------------------
+        if (collide) {
+            const bool rec = recordPairs && left == 1; // parity tests read the pair set of the run's last step
+            int hits = 0;
+            for (int i = tid; i < ns; i += nt) {
+                const int v1 = sSurf[i];
+                const DVoxMat &m1 = vmats[sVmat[v1]];
+                const V3<double> p1{sPos[3 * v1], sPos[3 * v1 + 1], sPos[3 * v1 + 2]};
+                const V3<R> l1{sLin[3 * v1], sLin[3 * v1 + 1], sLin[3 * v1 + 2]};
+                const short4 c1 = sLat[v1];
+                const float t1 = sTemp[v1];
+                V3<R> acc{R(0), R(0), R(0)};
+                for (int j = 0; j < ns; j++) {
+                    if (j == i)
+                        continue;
+                    const int v2 = sSurf[j];
+                    const short4 c2 = sLat[v2];
+                    if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1)
+                        continue;
+                    const DVoxMat &m2 = vmats[sVmat[v2]];
+                    if (m1.fixed && m2.fixed)
+                        continue;
+                    const V3<double> p2{sPos[3 * v2], sPos[3 * v2 + 1], sPos[3 * v2 + 2]};
+                    const V3<R> l2{sLin[3 * v2], sLin[3 * v2 + 1], sLin[3 * v2 + 2]};
+                    V3<R> f;
+                    if (i > j) {
+                        if (contact_pair<R>(m1, t1, p1, l1, m2, sTemp[v2], p2, l2, f)) {
+                            acc = acc + f;
+                            if ((m1.isTarget != 0) != (m2.isTarget != 0))
+                                hits++;
+                            if (rec) {
+                                int slot = atomicAdd(A.pairCount, 1);
+                                if (slot < A.pairCap)
+                                    A.pairBuf[slot] = make_int4(w, v1, v2, 0);
+                            }
+                        }
+                    } else if (contact_pair<R>(m2, sTemp[v2], p2, l2, m1, t1, p1, l1, f))
+                        acc = acc - f;
+                }
+                sCF[3 * i] = acc.x;
+                sCF[3 * i + 1] = acc.y;
+                sCF[3 * i + 2] = acc.z;
+            }
+            if (hits)
+                atomicAdd(&sh.hits, hits);
+        }
+        __syncthreads();
+        const bool divergedNow = sh.diverged != 0;
+        collisionCount += sh.hits;
+        const bool sampling = vx3 && cycle > 0 && ((step + 1) % cycle == 0);
+        __syncthreads(); // everyone has read sh.hits / sh.diverged
+        if (tid == 0)
+            sh.hits = 0;
+        // ---- voxel pass ---------------------------------------------------------------------------------------
+        if (!divergedNow) {
+            double cx = 0, cy = 0, cz = 0, cm = 0;
+            for (int v = tid; v < nv; v += nt) {
+                const DVoxMat &m = vmats[sVmat[v]];
+                VoxState<R> s;
+                s.pos = {sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]};
+                if (!(vx3 && m.fixed)) {
+                    s.orient = {sOri[4 * v], sOri[4 * v + 1], sOri[4 * v + 2], sOri[4 * v + 3]};
+                    s.linMom = {sLin[3 * v], sLin[3 * v + 1], sLin[3 * v + 2]};
+                    s.angMom = {sAng[3 * v], sAng[3 * v + 1], sAng[3 * v + 2]};
+                    s.temp = sTemp[v];
+                    s.flags = sVflags[v];
+                    V3<R> F{R(0), R(0), R(0)}, M{R(0), R(0), R(0)};
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const int l = sVlinks[6 * v + k];
+                        if (l == 0xffff)
+                            continue;
+                        const R *f = (k & 1) ? sFP : sFN, *mo = (k & 1) ? sMP : sMN;
+                        F = F + V3<R>{f[3 * l], f[3 * l + 1], f[3 * l + 2]};
+                        M = M + V3<R>{mo[3 * l], mo[3 * l + 1], mo[3 * l + 2]};
+                    }
+                    V3<R> contact{R(0), R(0), R(0)}, cilia{R(0), R(0), R(0)};
+                    const int slot = sVsurf[v];
+                    if (slot != 0xffff) {
+                        if (collide)
+                            contact = {sCF[3 * slot], sCF[3 * slot + 1], sCF[3 * slot + 2]};
+                        if (ciliaOn && m.cilia != 0)
+                            cilia = qrot(s.orient, V3<R>{(R)sCilia[3 * v], (R)sCilia[3 * v + 1], (R)sCilia[3 * v + 2]});
+                    }
+                    WorldStepParams wp;
+                    wp.dt = dt;
+                    wp.floorEnabled = floorOn;
+                    wp.vx3 = vx3;
+                    wp.forceField = (wflags & WF_FORCE_FIELD) ? W.ff : nullptr;
+                    wp.fv = FormulaVars{0, 0, 0, (double)collisionCount, t, W.recentAngle, W.closeness, W.numClosePairs, nv};
+                    VoxExt ext;
+                    const VoxExt *pe = nullptr;
+                    const int ei = sVext[v];
+                    const short4 lat = sLat[v];
+                    V3<double> nominal{lat.x * m.nomSize, lat.y * m.nomSize, lat.z * m.nomSize};
+                    if (ei >= 0) {
+                        const DExt &x = A.ext[ei];
+                        ext.dof = x.dof;
+                        ext.force = {x.force[0], x.force[1], x.force[2]};
+                        ext.moment = {x.moment[0], x.moment[1], x.moment[2]};
+                        ext.translation = {x.translation[0], x.translation[1], x.translation[2]};
+                        ext.rotationQ = {x.rotQ[0], x.rotQ[1], x.rotQ[2], x.rotQ[3]};
+                        pe = &ext;
+                    }
+                    voxel_update<R>(m, wp, pe, nominal, s, F, M, contact, cilia);
+                    if (varyTemp && m.alphaCTE != 0.0f) // temperature is only observable through alphaCTE
+                        s.temp = voxel_temperature(tempAmp, tempPeriod, sPhase[v], t + (double)dt, (wflags & WF_EXPANSION) != 0);
+                    sPos[3 * v] = s.pos.x;
+                    sPos[3 * v + 1] = s.pos.y;
+                    sPos[3 * v + 2] = s.pos.z;
+                    sOri[4 * v] = s.orient.w;
+                    sOri[4 * v + 1] = s.orient.x;
+                    sOri[4 * v + 2] = s.orient.y;
+                    sOri[4 * v + 3] = s.orient.z;
+                    sLin[3 * v] = s.linMom.x;
+                    sLin[3 * v + 1] = s.linMom.y;
+                    sLin[3 * v + 2] = s.linMom.z;
+                    sAng[3 * v] = s.angMom.x;
+                    sAng[3 * v + 1] = s.angMom.y;
+                    sAng[3 * v + 2] = s.angMom.z;
+                    sTemp[v] = s.temp;
+                    sVflags[v] = (uint8_t)s.flags;
+                }
+                if (sampling && m.isMeasured) {
+                    double mass = m.mass;
+                    cx += s.pos.x * mass;
+                    cy += s.pos.y * mass;
+                    cz += s.pos.z * mass;
+                    cm += mass;
+                }
+            }
+            if (sampling) { // warp-shuffle reduction, one shared atomic per warp
+                for (int o = 16; o > 0; o >>= 1) {
+                    cx += __shfl_xor_sync(0xffffffffu, cx, o);
+                    cy += __shfl_xor_sync(0xffffffffu, cy, o);
+                    cz += __shfl_xor_sync(0xffffffffu, cz, o);
+                    cm += __shfl_xor_sync(0xffffffffu, cm, o);
+                }
+                if ((tid & 31) == 0) {
+                    atomicAdd(&sh.com[0], cx);
+                    atomicAdd(&sh.com[1], cy);
+                    atomicAdd(&sh.com[2], cz);
+                    atomicAdd(&sh.com[3], cm);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- end-of-step bookkeeping: thread 0 owns the world record, everyone mirrors the scalars ---------------------
+        if (tid == 0) {
+            W.collisionCount = collisionCount;
+            W.divergedNow = divergedNow;
+            if (sampling && !divergedNow)
+                for (int k = 0; k < 4; k++) {
+                    W.comAcc[k] = sh.com[k];
+                    sh.com[k] = 0;
+                }
+            if (sampling && !divergedNow && W.maxDistPair != 0) { // closeness needs current positions in HBM
+                for (int v = 0; v < nv; v++)
+                    store_pos(A, voff + v, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, sTemp[v], sVflags[v]);
+            }
+            world_end_of_step(A, W, useStop);
+            sh.comFlag = W.active;
+        }
+        __syncthreads();
+        running = sh.comFlag != 0;
+        step++;
+        left--;
+        if (!divergedNow)
+            t += dt;
+    }
+
+    // ---- write the world back ------------------------------------------------------------------------------------
+    for (int v = tid; v < nv; v += nt) {
+        const int g = voff + v;
+        store_pos(A, g, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, sTemp[v], sVflags[v]);
+        A.orient[g] = mk4<R>(sOri[4 * v], sOri[4 * v + 1], sOri[4 * v + 2], sOri[4 * v + 3]);
+        A.lm[g] = mk4<R>(sLin[3 * v], sLin[3 * v + 1], sLin[3 * v + 2], sAng[3 * v]);
+        A.am[g] = mk2<R>(sAng[3 * v + 1], sAng[3 * v + 2]);
+    }
+    for (int l = tid; l < nl; l += nt) {
+        const int g = loff + l;
+        R fl;
+        if constexpr (sizeof(R) == 4)
+            fl = u2f((uint32_t)sLflags[l]);
+        else
+            fl = __longlong_as_double((long long)sLflags[l]);
+        A.lpos2[g] = mk4<R>(sP2[3 * l], sP2[3 * l + 1], sP2[3 * l + 2], fl);
+        A.la1[g] = mk4<R>(sA1[3 * l], sA1[3 * l + 1], sA1[3 * l + 2], (R)sLmax[l]);
+        A.la2[g] = mk4<R>(sA2[3 * l], sA2[3 * l + 1], sA2[3 * l + 2], R(0));
+        A.lfN[g] = mk4<R>(sFN[3 * l], sFN[3 * l + 1], sFN[3 * l + 2], R(0));
+        A.lfP[g] = mk4<R>(sFP[3 * l], sFP[3 * l + 1], sFP[3 * l + 2], R(0));
+        A.lmN[g] = mk4<R>(sMN[3 * l], sMN[3 * l + 1], sMN[3 * l + 2], R(0));
+        A.lmP[g] = mk4<R>(sMP[3 * l], sMP[3 * l + 1], sMP[3 * l + 2], R(0));
+    }
+}
+
+struct ResidentCfg {
+    int capV = 0, capL = 0, capS = 0, threads = 256;
+    size_t smem = 0;
+    bool ok = false;
+};
+
+// Can the largest world of the batch live in one CTA's shared memory?
+template <class R> ResidentCfg resident_configure(int maxNv, int maxNl, int maxNs, int threads) {
+    ResidentCfg c;
+    c.threads = std::max(32, std::min(1024, (threads + 31) / 32 * 32));
+    if (maxNv <= 0 || maxNv >= 0xffff || maxNl >= 0xffff)
+        return c;
+    c.capV = maxNv;
+    c.capL = std::max(maxNl, 1);
+    c.capS = std::max(maxNs, 1);
+    ResidentLayout<R> L(c.capV, c.capL, c.capS);
+    c.smem = L.total;
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return c;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (L.total + 1024 > (size_t)optin)
+        return c;
+    c.ok = cudaFuncSetAttribute(k_resident<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess;
+    return c;
+}
+
+template <class R>
+int resident_launch(const Arrays<R> &A, const ResidentCfg &c, int64_t maxSteps, int useStop, int recordPairs, cudaStream_t stream) {
+    if (recordPairs)
+        cudaMemsetAsync(A.pairCount, 0, sizeof(int), stream);
+    k_resident<R><<<A.nWorlds, c.threads, c.smem, stream>>>(A, c.capV, c.capL, c.capS, (long long)maxSteps, useStop, recordPairs);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error(std::string("k_resident launch: ") + cudaGetErrorString(e));
+        return VX3B_ERR_CUDA;
+    }
+    return VX3B_OK;
+}
+
+} // namespace vx3b

@@ -1,0 +1,552 @@
+// Device-side physics of the Voxelyze step, storage-agnostic: every function works on values in
+// registers so the streaming kernels (HBM-resident state), the resident kernel (state in shared
+// memory) and the fused tile kernel all share one implementation.
+//
+// R = float  : production arithmetic.  Positions stay double in storage; the link pass subtracts
+//              the two end positions and the nominal lattice offset in double and only then drops
+//              to float, so strain resolution does not degrade as a body travels.
+// R = double : validation arithmetic; reproduces the reference's float casts at the same places
+//              (SURVEY.md §7 "mixed precision in the reference").
+//
+// Equations follow SURVEY.md Appendix A; reference locations are cited per function
+// (paths under /root/reference/Voxelyze3/src).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vx3b200.h"
+
+namespace vx3b {
+
+#define VXD __device__ __forceinline__
+
+template <class R> struct V3 {
+    R x, y, z;
+};
+template <class R> struct Qt {
+    R w, x, y, z;
+};
+
+template <class R> VXD V3<R> mk3(R x, R y, R z) { return V3<R>{x, y, z}; }
+template <class R> VXD V3<R> operator+(V3<R> a, V3<R> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <class R> VXD V3<R> operator-(V3<R> a, V3<R> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <class R> VXD V3<R> operator-(V3<R> a) { return {-a.x, -a.y, -a.z}; }
+template <class R> VXD V3<R> operator*(V3<R> a, R f) { return {f * a.x, f * a.y, f * a.z}; }
+template <class R> VXD V3<R> operator*(R f, V3<R> a) { return {f * a.x, f * a.y, f * a.z}; }
+template <class R> VXD R dot(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <class R> VXD R len2(V3<R> a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+
+VXD float vsqrt(float x) { return sqrtf(x); }
+VXD double vsqrt(double x) { return sqrt(x); }
+VXD float vabs(float x) { return fabsf(x); }
+VXD double vabs(double x) { return fabs(x); }
+VXD float vacos(float x) { return acosf(x); }
+VXD double vacos(double x) { return acos(x); }
+VXD float vasin(float x) { return asinf(x); }
+VXD double vasin(double x) { return asin(x); }
+VXD void vsincos(float a, float *s, float *c) { sincosf(a, s, c); }
+VXD void vsincos(double a, double *s, double *c) { sincos(a, s, c); }
+
+template <class R> VXD Qt<R> qmul(Qt<R> a, Qt<R> f) { // Utils/VX3_Quat3D.h:217-222
+    return {a.w * f.w - a.x * f.x - a.y * f.y - a.z * f.z, a.w * f.x + a.x * f.w + a.y * f.z - a.z * f.y,
+            a.w * f.y - a.x * f.z + a.y * f.w + a.z * f.x, a.w * f.z + a.x * f.y - a.y * f.x + a.z * f.w};
+}
+template <class R> VXD Qt<R> qconj(Qt<R> a) { return {a.w, -a.x, -a.y, -a.z}; }
+template <class R> VXD V3<R> qrot(Qt<R> q, V3<R> f) { // RotateVec3D, Utils/VX3_Quat3D.h:439-448
+    R tw = f.x * q.x + f.y * q.y + f.z * q.z;
+    R tx = f.x * q.w - f.y * q.z + f.z * q.y;
+    R ty = f.x * q.z + f.y * q.w - f.z * q.x;
+    R tz = -f.x * q.y + f.y * q.x + f.z * q.w;
+    return {q.w * tx + q.x * tw + q.y * tz - q.z * ty, q.w * ty - q.x * tz + q.y * tw + q.z * tx, q.w * tz + q.x * ty - q.y * tx + q.z * tw};
+}
+template <class R> VXD V3<R> qrot_inv(Qt<R> q, V3<R> f) { // RotateVec3DInv, Utils/VX3_Quat3D.h:465-474
+    R tw = q.x * f.x + q.y * f.y + q.z * f.z;
+    R tx = q.w * f.x - q.y * f.z + q.z * f.y;
+    R ty = q.w * f.y + q.x * f.z - q.z * f.x;
+    R tz = q.w * f.z - q.x * f.y + q.y * f.x;
+    return {tw * q.x + tx * q.w + ty * q.z - tz * q.y, tw * q.y - tx * q.z + ty * q.w + tz * q.x, tw * q.z + tx * q.y - ty * q.x + tz * q.w};
+}
+
+// Quaternion -> rotation vector (Utils/VX3_Quat3D.h:347-359).
+VXD V3<double> rotvec(Qt<double> q) {
+    if (q.w >= 1.0 || q.w <= -1.0)
+        return {0, 0, 0};
+    double sl = 1.0 - q.w * q.w;
+    V3<double> v2{2.0 * q.x, 2.0 * q.y, 2.0 * q.z};
+    if (sl < 2.4e-3)
+        return v2 * sqrt((2 - 2 * q.w) / sl);
+    double inv = 1.0 / sqrt(sl);
+    return (v2 * acos(q.w)) * inv;
+}
+// float: 1 - w*w cancels catastrophically near identity, so use |v| directly (equal for unit q):
+// rotvec = 2 * v * asin(|v|)/|v|, series near zero.
+VXD V3<float> rotvec(Qt<float> q) {
+    float s2 = q.x * q.x + q.y * q.y + q.z * q.z;
+    float k;
+    if (s2 < 2.4e-3f)
+        k = 2.0f + s2 * (0.33333334f + s2 * 0.15f); // 2*asin(s)/s = 2 + s^2/3 + 3 s^4/20 + ...
+    else {
+        float s = sqrtf(s2);
+        float half = (q.w > 0.70710678f) ? asinf(s) : acosf(fminf(fmaxf(q.w, -1.0f), 1.0f));
+        if (q.w < -0.70710678f) // stay on the reference's branch of acos
+            half = acosf(fmaxf(q.w, -1.0f));
+        k = 2.0f * half / s;
+    }
+    return {k * q.x, k * q.y, k * q.z};
+}
+
+// Rotation vector -> quaternion (Utils/VX3_Quat3D.h:363-382).
+VXD Qt<double> quat_from_rotvec(V3<double> in) {
+    V3<double> th{0.5 * in.x, 0.5 * in.y, 0.5 * in.z};
+    double m2 = len2(th), w, s;
+    if (m2 * m2 < 5.328e-15) {
+        w = 1.0 - 0.5 * m2;
+        s = 1.0 - m2 / 6.0;
+    } else {
+        double m = sqrt(m2), sn, cs;
+        sincos(m, &sn, &cs);
+        w = cs;
+        s = sn / m;
+    }
+    return {w, th.x * s, th.y * s, th.z * s};
+}
+VXD Qt<float> quat_from_rotvec(V3<float> in) {
+    V3<float> th{0.5f * in.x, 0.5f * in.y, 0.5f * in.z};
+    float m2 = len2(th), w, s;
+    if (m2 < 1.0e-3f) { // two more series terms than the reference's double branch: exact to float precision here
+        w = 1.0f - m2 * (0.5f - m2 * 0.041666668f);
+        s = 1.0f - m2 * (0.16666667f - m2 * 0.0083333338f);
+    } else {
+        float m = sqrtf(m2), sn, cs;
+        sincosf(m, &sn, &cs);
+        w = cs;
+        s = sn / m;
+    }
+    return {w, th.x * s, th.y * s, th.z * s};
+}
+
+// Quaternion that rotates `from` onto +X (Utils/VX3_Quat3D.h:384-437); q is left untouched for a zero vector.
+template <class R> VXD void quat_to_pos_x(Qt<R> &q, V3<R> from) {
+    if (from.x == R(0) && from.y == R(0) && from.z == R(0))
+        return;
+    const R SMALL = R(1.732e-2);
+    R yox = from.y / from.x, zox = from.z / from.x;
+    if (yox < SMALL && yox > -SMALL && zox < SMALL && zox > -SMALL) {
+        q.x = R(0);
+        q.y = R(0.5) * zox;
+        q.z = R(-0.5) * yox;
+        q.w = R(1) + R(0.5) * (-q.y * q.y - q.z * q.z);
+        return;
+    }
+    R l = vsqrt(len2(from));
+    V3<R> n = from;
+    if (l > R(0)) {
+        R inv = R(1) / l;
+        n = {inv * from.x, inv * from.y, inv * from.z};
+    }
+    R theta = vacos(n.x);
+    if (theta > R(3.14159265358979) - R(1e-7)) {
+        q = {R(0), R(0), R(1), R(0)};
+        return;
+    }
+    R axisMagInv = R(1) / vsqrt(n.z * n.z + n.y * n.y);
+    R sn, cs;
+    vsincos(R(0.5) * theta, &sn, &cs);
+    q.w = cs;
+    q.x = R(0);
+    q.y = n.z * axisMagInv * sn;
+    q.z = -n.y * axisMagInv * sn;
+}
+
+// axis swizzles (VX3/VX3_Link.h:97-191)
+template <class R> VXD V3<R> to_axis_x(V3<R> v, int axis) {
+    return axis == 1 ? V3<R>{v.y, -v.x, v.z} : axis == 2 ? V3<R>{v.z, v.y, -v.x} : v;
+}
+template <class R> VXD Qt<R> to_axis_x(Qt<R> q, int axis) {
+    return axis == 1 ? Qt<R>{q.w, q.y, -q.x, q.z} : axis == 2 ? Qt<R>{q.w, q.z, q.y, -q.x} : q;
+}
+template <class R> VXD V3<R> to_axis_original(V3<R> v, int axis) {
+    return axis == 1 ? V3<R>{-v.y, v.x, v.z} : axis == 2 ? V3<R>{-v.z, v.y, v.x} : v;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-side constant tables
+// ------------------------------------------------------------------------------------------
+struct DVoxMat { // per voxel material, pre-multiplied where the reference multiplies two floats every step
+    float E, alphaCTE, muStatic, muKinetic;
+    float mass, massInverse, momentInertiaInverse, sqrtMassZetaInt2; // 2*sqrtMass*zetaInternal (numerator of dampingMultiplier)
+    float globalDampTranslateC, globalDampRotateC, collisionDampTranslateC, penetrationStiffness;
+    float gravityForce; // -mass*9.80665f*gravMult
+    float nomSizeF;     // (float)nomSize
+    double nomSize;
+    double cilia;
+    int32_t fixed, isTarget, isMeasured, pad;
+};
+struct DLinkMat {
+    float E, a2, b1, b2, b3, sqA1, sqA2xIp, sqB1, sqB2xFMp, sqB3xIp, epsilonFail, area; // area: currentTransverseArea (nu == 0)
+};
+
+// link history flags
+enum { LF_SMALL_ANGLE = 1, LF_VEL_VALID = 2 };
+// voxel flags
+enum { VF_STATIC_FRICTION = 1 };
+
+template <class R> struct LinkHist {
+    V3<R> pos2, a1v, a2v;
+    uint32_t flags;
+    float maxStrain;
+};
+template <class R> struct LinkForces {
+    V3<R> fNeg, fPos, mNeg, mPos;
+    float strain;
+};
+
+// base size along one axis = nomSize * (1 + temp*alphaCTE), the bracket being a float expression (VX3/VX3_Voxel.h:96-99)
+VXD double base_size(const DVoxMat &m, float temp) { return m.nomSize * (double)(1 + temp * m.alphaCTE); }
+VXD double base_size_average(const DVoxMat &m, float temp) { // VX3/VX3_Voxel.h:102-105
+    double b = base_size(m, temp);
+    return (b + b + b) / 3.0f;
+}
+
+// One link: orientLink + updateForces (VX3/VX3_Link.cu:90-218, updateStrain :220-231 linear / nu == 0 branch).
+//   dpos    = p₊ − p₋ (double, global frame); qn/qp = end orientations; restLen from both ends' temperatures
+//   dmN/dmP = dampingMultiplier of the negative/positive end voxel (2*sqrtMass*zetaInternal/previousDt)
+template <class R>
+VXD void link_update(const DLinkMat &m, int axis, V3<double> dpos, double nomLen, Qt<R> qn, Qt<R> qp, double restLen, float dmN, float dmP,
+                     LinkHist<R> &h, LinkForces<R> &out) {
+    const V3<R> oldPos2 = h.pos2, oldA1 = h.a1v, oldA2 = h.a2v;
+    Qt<R> q1 = to_axis_x(qn, axis), q2 = to_axis_x(qp, axis);
+    Qt<R> total = qconj(q1);
+    q2 = qmul(total, q2);
+    V3<R> d; // end-to-end vector in the negative end's frame, link axis on +X
+    R rest = (R)restLen;
+    R dxMinusRest; // d.x - restLen, formed without cancellation in float
+    if constexpr (sizeof(R) == 8) {
+        d = qrot(total, to_axis_x(V3<R>{dpos.x, dpos.y, dpos.z}, axis));
+        dxMinusRest = d.x - rest;
+    } else {
+        // d = Rᵀ(e + L·x̂) with e = dpos − L·x̂ small: rotate e in float, add L·Rᵀx̂ analytically
+        V3<double> dd = to_axis_x(dpos, axis);
+        V3<R> e{(R)(dd.x - nomLen), (R)dd.y, (R)dd.z};
+        V3<R> er = qrot(total, e);
+        R L = (R)nomLen;
+        // Rᵀx̂ for unit q1=(w,x,y,z): (1-2(y²+z²), 2(xy - wz), 2(xz + wy))
+        R cx = R(-2) * (q1.y * q1.y + q1.z * q1.z); // = Rᵀx̂.x - 1
+        R cy = R(2) * (q1.x * q1.y - q1.w * q1.z);
+        R cz = R(2) * (q1.x * q1.z + q1.w * q1.y);
+        d = {er.x + L * cx + L, er.y + L * cy, er.z + L * cz};
+        dxMinusRest = er.x + L * cx + (R)(nomLen - restLen);
+    }
+    q1 = {R(1), R(0), R(0), R(0)};
+    float smallTurn = (float)((vabs(d.z) + vabs(d.y)) / d.x);
+    float extendPerc = (float)vabs(dxMinusRest / rest); // |1 - d.x/restLen|
+    if constexpr (sizeof(R) == 8)
+        extendPerc = (float)vabs(R(1) - d.x / rest);
+    const float HYST = 1.2f, BEND = 0.05f, EXT = 0.50f; // VoxCAD/src/VX2/include/types.h:57-59
+    bool small = h.flags & LF_SMALL_ANGLE;
+    bool valid = h.flags & LF_VEL_VALID;
+    if (!small && smallTurn < BEND && extendPerc < EXT) {
+        small = true;
+        valid = false;
+    } else if (small && (smallTurn > HYST * BEND || extendPerc > HYST * EXT)) {
+        small = false;
+        valid = false;
+    }
+    V3<R> th1{R(0), R(0), R(0)};
+    if (small) {
+        d.x = dxMinusRest;
+    } else {
+        quat_to_pos_x(q1, d);
+        total = qmul(q1, total);
+        q2 = qmul(q1, q2);
+        d = {vsqrt(len2(d)) - rest, R(0), R(0)};
+        th1 = rotvec(q1);
+    }
+    V3<R> th2 = rotvec(q2);
+    h.pos2 = d;
+    h.a1v = th1;
+    h.a2v = th2;
+
+    float eps = (float)(d.x / rest);
+    out.strain = eps;
+    if (eps > h.maxStrain)
+        h.maxStrain = eps;
+    const bool canFail = m.epsilonFail != -1.0f;
+    float stress = (canFail && eps > m.epsilonFail) ? 0.0f : m.E * eps;
+    if (canFail && h.maxStrain > m.epsilonFail) { // isFailed(): outputs zero, flags keep their pre-damping value
+        out.fNeg = out.fPos = out.mNeg = out.mPos = V3<R>{R(0), R(0), R(0)};
+        h.flags = (small ? LF_SMALL_ANGLE : 0) | (valid ? LF_VEL_VALID : 0);
+        return;
+    }
+    const R b1 = m.b1, b2 = m.b2, b3 = m.b3, a2 = m.a2;
+    V3<R> FN{(R)(stress * m.area), b1 * d.y - b2 * (th1.z + th2.z), b1 * d.z + b2 * (th1.y + th2.y)};
+    V3<R> FP = -FN;
+    V3<R> MN{a2 * (th2.x - th1.x), -b2 * d.z - b3 * (R(2) * th1.y + th2.y), b2 * d.y - b3 * (R(2) * th1.z + th2.z)};
+    V3<R> MP{a2 * (th1.x - th2.x), -b2 * d.z - b3 * (th1.y + R(2) * th2.y), b2 * d.y - b3 * (th1.z + R(2) * th2.z)};
+    if (valid) { // local damping from half-deltas of the link's own history (VX3/VX3_Link.cu:172-188)
+        V3<R> dP = R(0.5) * (d - oldPos2), dA1 = R(0.5) * (th1 - oldA1), dA2 = R(0.5) * (th2 - oldA2);
+        const R sqA1 = m.sqA1, sqA2xIp = m.sqA2xIp, sqB1 = m.sqB1, sqB2xFMp = m.sqB2xFMp, sqB3xIp = m.sqB3xIp;
+        V3<R> pc{sqA1 * dP.x, sqB1 * dP.y - sqB2xFMp * (dA1.z + dA2.z), sqB1 * dP.z + sqB2xFMp * (dA1.y + dA2.y)};
+        FN = FN + (R)dmN * pc;
+        FP = FP - (R)dmP * pc;
+        R tw = sqA2xIp * (dA2.x - dA1.x);
+        MN = MN - (R(0.5) * (R)dmN) * V3<R>{-tw, sqB2xFMp * dP.z + sqB3xIp * (R(2) * dA1.y + dA2.y), -sqB2xFMp * dP.y + sqB3xIp * (R(2) * dA1.z + dA2.z)};
+        MP = MP - (R(0.5) * (R)dmP) * V3<R>{tw, sqB2xFMp * dP.z + sqB3xIp * (dA1.y + R(2) * dA2.y), -sqB2xFMp * dP.y + sqB3xIp * (dA1.z + R(2) * dA2.z)};
+    } else
+        valid = true;
+    if (!small) {
+        FN = qrot_inv(q1, FN);
+        MN = qrot_inv(q1, MN);
+    }
+    FP = qrot_inv(q2, FP);
+    MP = qrot_inv(q2, MP);
+    out.fNeg = to_axis_original(FN, axis);
+    out.fPos = to_axis_original(FP, axis);
+    out.mNeg = to_axis_original(MN, axis);
+    out.mPos = to_axis_original(MP, axis);
+    h.flags = (small ? LF_SMALL_ANGLE : 0) | (valid ? LF_VEL_VALID : 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// formula VM (Utils/VX3_MathTree.h:50-193): FIFO queue machine over a reversed level-order program
+// ------------------------------------------------------------------------------------------
+struct FormulaVars {
+    double x, y, z, hit, t, angle, closeness;
+    int numClosePairs, numVoxel;
+};
+__device__ inline double eval_formula(const VX3B_Token *tok, const FormulaVars &v) {
+    double values[VX3B_MAX_TOKENS + 1];
+    values[0] = 0.0;
+    int vc = 0, pc = 0;
+    for (int i = 0; i < VX3B_MAX_TOKENS; i++) {
+        const int op = tok[i].op;
+        double r = 0;
+        if (op == VX3B_MT_END)
+            return values[pc];
+        if (op == VX3B_MT_CONST)
+            r = tok[i].value;
+        else if (op == VX3B_MT_E)
+            r = 2.71828182845904523536;
+        else if (op == VX3B_MT_PI)
+            r = 3.14159265358979323846;
+        else if (op == VX3B_MT_VAR) {
+            double id = tok[i].value;
+            r = id < 0.5 ? v.x : id < 1.5 ? v.y : id < 2.5 ? v.z : id < 3.5 ? v.hit : id < 4.5 ? v.t : id < 5.5 ? v.angle
+                : id < 6.5 ? v.closeness : id < 7.5 ? (double)v.numClosePairs : (double)v.numVoxel;
+        } else if (op == VX3B_MT_ADD || op == VX3B_MT_SUB || op == VX3B_MT_MUL || op == VX3B_MT_DIV || op == VX3B_MT_POW ||
+                   op == VX3B_MT_GREATERTHAN || op == VX3B_MT_LESSTHAN || op == VX3B_MT_AND || op == VX3B_MT_OR) {
+            double a = values[pc + 1], b = values[pc];
+            pc += 2;
+            r = op == VX3B_MT_ADD ? a + b : op == VX3B_MT_SUB ? a - b : op == VX3B_MT_MUL ? a * b : op == VX3B_MT_DIV ? a / b
+                : op == VX3B_MT_POW ? pow(a, b) : op == VX3B_MT_GREATERTHAN ? (double)(a > b) : op == VX3B_MT_LESSTHAN ? (double)(a < b)
+                : op == VX3B_MT_AND ? (double)(a != 0 && b != 0) : (double)(a != 0 || b != 0);
+        } else {
+            double a = values[pc];
+            pc += 1;
+            switch (op) {
+            case VX3B_MT_SQRT: r = sqrt(a); break;
+            case VX3B_MT_SIN: r = sin(a); break;
+            case VX3B_MT_COS: r = cos(a); break;
+            case VX3B_MT_TAN: r = tan(a); break;
+            case VX3B_MT_ATAN: r = atan(a); break;
+            case VX3B_MT_LOG: r = log(a); break;
+            case VX3B_MT_INT: r = rint(a); break;
+            case VX3B_MT_ABS: r = fabs(a); break;
+            case VX3B_MT_NOT: r = (double)(a == 0); break;
+            case VX3B_MT_NORMALCDF: r = normcdf(a); break;
+            default: return -1;
+            }
+        }
+        if (pc > vc)
+            return -1;
+        values[vc++] = r;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// voxel integration (VX3/VX3_Voxel.cu:162-277, force :350-380, moment :382-397, floorForce :399-426)
+// ------------------------------------------------------------------------------------------
+struct WorldStepParams { // what one voxel needs to know about its world for one step
+    float dt;
+    int floorEnabled, vx3;
+    const VX3B_Token *forceField; // [3][VX3B_MAX_TOKENS] or nullptr
+    FormulaVars fv;               // hit/t/angle/closeness/pairs/nv for the force field
+};
+template <class R> struct VoxState {
+    V3<double> pos;
+    Qt<R> orient;
+    V3<R> linMom, angMom;
+    uint32_t flags;
+    float temp;
+};
+struct VoxExt { // boundary conditions of one voxel (CVX_External)
+    uint32_t dof;
+    V3<float> force, moment;
+    V3<double> translation;
+    Qt<double> rotationQ;
+};
+
+VXD float floor_penetration(const DVoxMat &m, float temp, double z) { // VX3/VX3_Voxel.h:185-187
+    return (float)(base_size_average(m, temp) / 2 - m.nomSize / 2 - z);
+}
+
+// Fsum/Msum: sums of the ≤6 link forces/moments in the voxel's local frame; contact/cilia in the global frame.
+template <class R>
+VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt *ext, V3<double> nominalPos, VoxState<R> &s, V3<R> Fsum, V3<R> Msum,
+                      V3<R> contact, V3<R> cilia) {
+    const R dt = (R)wp.dt;
+    if (ext && ext->dof == VX3B_DOF_ALL) {
+        s.pos = nominalPos + ext->translation;
+        s.orient = {(R)ext->rotationQ.w, (R)ext->rotationQ.x, (R)ext->rotationQ.y, (R)ext->rotationQ.z};
+        s.linMom = s.angMom = V3<R>{R(0), R(0), R(0)};
+        return;
+    }
+    V3<R> F = qrot(s.orient, Fsum);
+    if (ext)
+        F = F + V3<R>{(R)ext->force.x, (R)ext->force.y, (R)ext->force.z};
+    F = F - (s.linMom * (R)m.massInverse) * (R)m.globalDampTranslateC;
+    F.z += (R)m.gravityForce;
+    F = F - contact;
+    F = F + cilia * (R)m.cilia;
+    if (wp.forceField) {
+        FormulaVars fv = wp.fv;
+        fv.x = s.pos.x;
+        fv.y = s.pos.y;
+        fv.z = s.pos.z;
+        if (wp.forceField[0].op != VX3B_MT_END)
+            F.x += (R)eval_formula(wp.forceField, fv);
+        if (wp.forceField[VX3B_MAX_TOKENS].op != VX3B_MT_END)
+            F.y += (R)eval_formula(wp.forceField + VX3B_MAX_TOKENS, fv);
+        if (wp.forceField[2 * VX3B_MAX_TOKENS].op != VX3B_MT_END)
+            F.z += (R)eval_formula(wp.forceField + 2 * VX3B_MAX_TOKENS, fv);
+    }
+    V3<R> fric = F;
+    bool staticFric = s.flags & VF_STATIC_FRICTION;
+    if (wp.floorEnabled) {
+        float pen = floor_penetration(m, s.temp, s.pos.z);
+        if (pen >= 0) {
+            V3<R> vel = s.linMom * (R)m.massInverse;
+            float normalForce = m.penetrationStiffness * pen;
+            F.z += (R)normalForce - (R)m.collisionDampTranslateC * vel.z;
+            if (staticFric) {
+                float surfaceSq = (float)(F.x * F.x + F.y * F.y);
+                float frictionSq = (m.muStatic * normalForce) * (m.muStatic * normalForce);
+                if (surfaceSq > frictionSq)
+                    staticFric = false;
+            } else {
+                R hl = vsqrt(vel.x * vel.x + vel.y * vel.y);
+                if (hl > R(0)) {
+                    R k = (R)(m.muKinetic * normalForce) * (R(1) / hl);
+                    F.x -= k * vel.x;
+                    F.y -= k * vel.y;
+                }
+            }
+        } else
+            staticFric = false;
+    }
+    fric = F - fric;
+    s.linMom = s.linMom + F * dt;
+    V3<R> tr = s.linMom * (dt * (R)m.massInverse);
+    if (wp.floorEnabled && floor_penetration(m, s.temp, s.pos.z) >= 0) {
+        R work = fric.x * tr.x + fric.y * tr.y;
+        R hKe = (R(0.5) * (R)m.massInverse) * (s.linMom.x * s.linMom.x + s.linMom.y * s.linMom.y);
+        if (hKe + work <= R(0))
+            staticFric = true;
+        if (staticFric) {
+            s.linMom.x = s.linMom.y = R(0);
+            tr.x = tr.y = R(0);
+        }
+    } else
+        staticFric = false;
+    s.pos = {s.pos.x + (double)tr.x, s.pos.y + (double)tr.y, s.pos.z + (double)tr.z};
+
+    V3<R> Mo = qrot(s.orient, Msum);
+    if (ext)
+        Mo = Mo + V3<R>{(R)ext->moment.x, (R)ext->moment.y, (R)ext->moment.z};
+    Mo = Mo - (s.angMom * (R)m.momentInertiaInverse) * (R)m.globalDampRotateC;
+    s.angMom = s.angMom + Mo * dt;
+    s.orient = qmul(quat_from_rotvec(s.angMom * (dt * (R)m.momentInertiaInverse)), s.orient);
+    if constexpr (sizeof(R) == 4) { // float build keeps the quaternion unit length; the reference (double) never renormalises
+        R n2 = s.orient.w * s.orient.w + s.orient.x * s.orient.x + s.orient.y * s.orient.y + s.orient.z * s.orient.z;
+        R inv = rsqrtf(n2);
+        s.orient = {s.orient.w * inv, s.orient.x * inv, s.orient.y * inv, s.orient.z * inv};
+    }
+    if (ext && ext->dof) { // partial dof fixes (VX3/VX3_Voxel.cu:222-257)
+        const uint32_t f = ext->dof;
+        if (f & VX3B_DOF_TX) {
+            s.pos.x = nominalPos.x + ext->translation.x;
+            s.linMom.x = R(0);
+        }
+        if (f & VX3B_DOF_TY) {
+            s.pos.y = nominalPos.y + ext->translation.y;
+            s.linMom.y = R(0);
+        }
+        if (f & VX3B_DOF_TZ) {
+            s.pos.z = nominalPos.z + ext->translation.z;
+            s.linMom.z = R(0);
+        }
+        const uint32_t rotAll = VX3B_DOF_RX | VX3B_DOF_RY | VX3B_DOF_RZ;
+        if (f & rotAll) {
+            if ((f & rotAll) == rotAll) {
+                s.orient = {(R)ext->rotationQ.w, (R)ext->rotationQ.x, (R)ext->rotationQ.y, (R)ext->rotationQ.z};
+                s.angMom = V3<R>{R(0), R(0), R(0)};
+            } else {
+                V3<R> rv = rotvec(s.orient);
+                if (f & VX3B_DOF_RX) {
+                    rv.x = R(0);
+                    s.angMom.x = R(0);
+                }
+                if (f & VX3B_DOF_RY) {
+                    rv.y = R(0);
+                    s.angMom.y = R(0);
+                }
+                if (f & VX3B_DOF_RZ) {
+                    rv.z = R(0);
+                    s.angMom.z = R(0);
+                }
+                s.orient = quat_from_rotvec(rv);
+            }
+        }
+    }
+    if (wp.vx3 && wp.floorEnabled && staticFric && floor_penetration(m, s.temp, s.pos.z) >= 0) // VX3/VX3_Voxel.cu:258-264
+        s.angMom = V3<R>{R(0), R(0), R(0)};
+    s.flags = staticFric ? VF_STATIC_FRICTION : 0;
+}
+
+// Temperature of a voxel at time t (VX3/VX3_VoxelyzeKernel.cu:638-647); the sine is taken in double as the reference does.
+VXD float voxel_temperature(double amplitude, double period, double phase, double t, int enableExpansion) {
+    double T = amplitude * sin(2 * 3.1415926f * (t / period + phase));
+    if (!enableExpansion && T > 0)
+        T = 0;
+    return (float)T;
+}
+
+// Contact between two surface voxels (VX3/VX3_VoxelyzeKernel.cu:682-727, VX3/VX3_Collision.cu:3-31).
+// Returns true when (1,2) is a watched pair (inside the envelope on every axis and in distance); `force` is the force
+// the reference adds to voxel 1's contactForce (voxel 2 gets the negative).  The caller has already excluded linked
+// voxels and pairs whose materials are both `fixed`.
+template <class R>
+VXD bool contact_pair(const DVoxMat &m1, float temp1, V3<double> p1, V3<R> linMom1, const DVoxMat &m2, float temp2, V3<double> p2,
+                      V3<R> linMom2, V3<R> &force) {
+    double Rw = (base_size_average(m1, temp1) + base_size_average(m2, temp2)) * 0.625;
+    double dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
+    force = V3<R>{R(0), R(0), R(0)};
+    if (dx > Rw || dx < -Rw || dy > Rw || dy < -Rw || dz > Rw || dz < -Rw)
+        return false;
+    double dist = sqrt(dx * dx + dy * dy + dz * dz);
+    if (dist > Rw)
+        return false;
+    double relDist = Rw - dist;
+    if (relDist > 0) {
+        float stiff = 2.0f / (1.0f / m1.penetrationStiffness + 1.0f / m2.penetrationStiffness);
+        float damp = 0.5f * (m1.collisionDampTranslateC + m2.collisionDampTranslateC);
+        double inv = dist > 0 ? 1.0 / dist : 0.0;
+        V3<R> unit{(R)(-dx * inv), (R)(-dy * inv), (R)(-dz * inv)}; // from voxel 1 towards voxel 2
+        R relVel = dot(linMom1 * (R)m1.massInverse, unit) - dot(linMom2 * (R)m2.massInverse, unit);
+        force = unit * ((R)stiff * (R)relDist + (R)damp * relVel);
+    }
+    return true;
+}
+
+} // namespace vx3b

@@ -1,0 +1,205 @@
+"""Synthetic VXA / VXD text generators for the BASELINE.json configurations.
+
+Everything is emitted as real VXA/VXD XML so the same text feeds our host model and the reference's own
+parser (oracle/_ref).  Fixed seeds; numpy only.
+"""
+import numpy as np
+
+_MAT_DEFAULTS = dict(name="mat", E=5e6, density=1e6, nu=0.35, cte=0.0, u_static=1.0, u_dynamic=0.5, cilia=0.0,
+                     is_target=0, fixed=0, is_measured=1, mat_model=0, fail_stress=0.0)
+
+
+def material(**kw):
+    m = dict(_MAT_DEFAULTS)
+    m.update(kw)
+    return m
+
+
+def _mat_xml(i, m):
+    extra = ""
+    if m["cilia"]:
+        extra += f"<Cilia>{m['cilia']:g}</Cilia>"
+    if m["is_target"]:
+        extra += "<isTarget>1</isTarget>"
+    if m["fixed"]:
+        extra += "<Fixed>1</Fixed>"
+    if not m["is_measured"]:
+        extra += "<isMeasured>0</isMeasured>"
+    return (f'<Material ID="{i}"><MatType>0</MatType><Name>{m["name"]}</Name>'
+            f"<Display><Red>0.5</Red><Green>0.5</Green><Blue>0.5</Blue><Alpha>1</Alpha></Display>"
+            f"<Mechanical>{extra}<MatModel>{m['mat_model']}</MatModel><Elastic_Mod>{m['E']!r}</Elastic_Mod>"
+            f"<Plastic_Mod>0</Plastic_Mod><Yield_Stress>0</Yield_Stress><FailModel>0</FailModel>"
+            f"<Fail_Stress>{m['fail_stress']!r}</Fail_Stress><Fail_Strain>0</Fail_Strain><Density>{m['density']!r}</Density>"
+            f"<Poissons_Ratio>{m['nu']!r}</Poissons_Ratio><CTE>{m['cte']!r}</CTE><MaterialTempPhase>0</MaterialTempPhase>"
+            f"<uStatic>{m['u_static']!r}</uStatic><uDynamic>{m['u_dynamic']!r}</uDynamic></Mechanical></Material>")
+
+
+def structure_xml(data, phase=None, base_cilia=None, replace=None):
+    """data: int array [Z][Y][X] of palette ids (0 = empty).  phase: float [Z][Y][X].  base_cilia: float [Z][Y][X][3]."""
+    data = np.asarray(data)
+    Z, Y, X = data.shape
+    assert data.max() <= 74, "ASCII_READABLE stores id+48 in one char"
+    attr = f' replace="{replace}"' if replace else ""
+    out = [f'<Structure{attr} Compression="ASCII_READABLE"><X_Voxels>{X}</X_Voxels><Y_Voxels>{Y}</Y_Voxels><Z_Voxels>{Z}</Z_Voxels><Data>']
+    for z in range(Z):
+        out.append("<Layer><![CDATA[" + "".join(chr(48 + int(c)) for c in data[z].reshape(-1)) + "]]></Layer>")
+    out.append("</Data>")
+    if phase is not None:
+        out.append("<PhaseOffset>")
+        for z in range(Z):
+            out.append("<Layer><![CDATA[" + ", ".join(repr(float(p)) for p in np.asarray(phase)[z].reshape(-1)) + "]]></Layer>")
+        out.append("</PhaseOffset>")
+    if base_cilia is not None:
+        out.append("<BaseCiliaForce>")
+        for z in range(Z):
+            out.append("<Layer><![CDATA[" + ", ".join(repr(float(p)) for p in np.asarray(base_cilia)[z].reshape(-1)) + "]]></Layer>")
+        out.append("</BaseCiliaForce>")
+    out.append("</Structure>")
+    return "".join(out)
+
+
+def formula_xml(tag, body):
+    return f"<{tag}>{body}</{tag}>"
+
+
+STOP_AT = lambda seconds: f"<mtSUB><mtVAR>t</mtVAR><mtCONST>{seconds!r}</mtCONST></mtSUB>"  # noqa: E731
+FITNESS_XY_DISTANCE = ("<mtSQRT><mtADD><mtMUL><mtVAR>x</mtVAR><mtVAR>x</mtVAR></mtMUL>"
+                       "<mtMUL><mtVAR>y</mtVAR><mtVAR>y</mtVAR></mtMUL></mtADD></mtSQRT>")
+
+
+def vxa_document(materials, structure, lattice_dim=0.01, dt_frac=0.9, bond_damping=1.0, col_damping=0.8, slow_damping=0.01,
+                 grav_acc=-9.81, floor=True, temp_enabled=True, temp_amplitude=0.0, temp_base=25.0, vary_temp=False,
+                 temp_period=0.1, enable_collision=None, enable_cilia=False, enable_expansion=False, stop_formula=None,
+                 fitness_formula=None, force_field=None, save_positions=False, volume_effects=False):
+    sim = []
+    if enable_cilia:
+        sim.append("<EnableCilia>1</EnableCilia>")
+    if enable_expansion:
+        sim.append("<EnableExpansion>1</EnableExpansion>")
+    if save_positions:
+        sim.append("<SavePositionOfAllVoxels>1</SavePositionOfAllVoxels>")
+    if enable_collision is not None:
+        sim.append(f"<AttachDetach><EnableCollision>{int(enable_collision)}</EnableCollision></AttachDetach>")
+    if fitness_formula:
+        sim.append(formula_xml("FitnessFunction", fitness_formula))
+    if force_field:
+        sim.append("<ForceField>" + "".join(formula_xml(f"{ax}_forcefield", f) for ax, f in zip("xyz", force_field) if f) + "</ForceField>")
+    sim.append(f"<Integration><Integrator>0</Integrator><DtFrac>{dt_frac!r}</DtFrac></Integration>")
+    sim.append(f"<Damping><BondDampingZ>{bond_damping!r}</BondDampingZ><ColDampingZ>{col_damping!r}</ColDampingZ>"
+               f"<SlowDampingZ>{slow_damping!r}</SlowDampingZ></Damping>")
+    sim.append("<Collisions><SelfColEnabled>1</SelfColEnabled><ColSystem>3</ColSystem><CollisionHorizon>3</CollisionHorizon></Collisions>")
+    sim.append(f"<Features><VolumeEffectsEnabled>{int(volume_effects)}</VolumeEffectsEnabled></Features>")
+    stop = formula_xml("StopConditionFormula", stop_formula) if stop_formula else ""
+    sim.append(f"<StopCondition><StopConditionType>0</StopConditionType><StopConditionValue>99</StopConditionValue>{stop}</StopCondition>")
+    env = (f"<Environment><Boundary_Conditions><NumBCs>0</NumBCs></Boundary_Conditions>"
+           f"<Gravity><GravEnabled>1</GravEnabled><GravAcc>{grav_acc!r}</GravAcc><FloorEnabled>{int(floor)}</FloorEnabled></Gravity>"
+           f"<Thermal><TempEnabled>{int(temp_enabled)}</TempEnabled><TempAmplitude>{temp_amplitude!r}</TempAmplitude>"
+           f"<TempBase>{temp_base!r}</TempBase><VaryTempEnabled>{int(vary_temp)}</VaryTempEnabled><TempPeriod>{temp_period!r}</TempPeriod>"
+           f"</Thermal></Environment>")
+    palette = "".join(_mat_xml(i + 1, m) for i, m in enumerate(materials))
+    vxc = (f'<VXC Version="0.94"><Lattice><Lattice_Dim>{lattice_dim!r}</Lattice_Dim></Lattice>'
+           f"<Voxel><Vox_Name>BOX</Vox_Name></Voxel><Palette>{palette}</Palette>{structure}</VXC>")
+    return ('<?xml version="1.0" encoding="ISO-8859-1"?>\n<VXA Version="1.1"><Simulator>' + "".join(sim) + "</Simulator>" + env + vxc + "</VXA>\n")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def small_block_vxa(enable_collision=False, seed=3):
+    """4x4x3 block, two materials (one thermally actuated with phase offsets), floor + gravity.  The smoke-test world."""
+    rng = np.random.default_rng(seed)
+    data = np.ones((3, 4, 4), dtype=int)
+    data[:, 1:3, 1:3] = 2
+    data[0, 0, 0] = 0
+    data[2, 3, :2] = 0
+    phase = rng.uniform(0, 1, size=data.shape)
+    mats = [material(name="soft", E=5e6, cte=0.0), material(name="active", E=1e7, cte=0.01)]
+    return vxa_document(mats, structure_xml(data, phase=phase), dt_frac=0.5, temp_amplitude=14.4714, vary_temp=True, temp_period=0.2,
+                        enable_collision=enable_collision)
+
+
+def cube_vxa(n, steps_hint=None, enable_collision=False):
+    """C3: n^3 single-material soft body under gravity on the floor (doc/misc/example.vxa's damping), no self-collision."""
+    data = np.ones((n, n, n), dtype=int)
+    return vxa_document([material(name="body", E=5e6, density=1e6)], structure_xml(data), dt_frac=0.9, bond_damping=1.0, col_damping=0.8,
+                        slow_damping=0.01, grav_acc=-9.81, floor=True, enable_collision=enable_collision)
+
+
+XENOBOT_DIMS = (7, 14, 14)  # Z, Y, X — e.circle_push uses 12x12x7; two more rows/columns keep the pebbles clear of the body
+
+
+def xenobot_base_vxa(stop_seconds=5.0, enable_collision=True):
+    """C2 base.vxa modelled on Experiments/xenobot/e.circle_push/base.vxa: cilia-driven body (material 1, Cilia=8) and
+    target pebbles (material 2), GravAcc=-1, DtFrac=1, TempPeriod 0.1, stop at t = stop_seconds."""
+    mats = [material(name="Cilia", E=5e6, density=5e5, cilia=8.0), material(name="TargetPebble", E=5e6, density=5e5, is_target=1)]
+    fitness = ("<mtADD><mtADD><mtABS><mtVAR>angle</mtVAR></mtABS><mtLOG><mtADD><mtVAR>hit</mtVAR><mtCONST>1</mtCONST></mtADD></mtLOG></mtADD>"
+               "<mtLOG><mtADD><mtMUL><mtVAR>x</mtVAR><mtVAR>x</mtVAR></mtMUL><mtMUL><mtVAR>y</mtVAR><mtVAR>y</mtVAR></mtMUL></mtADD></mtLOG></mtADD>")
+    placeholder = structure_xml(np.array([[[1, 1], [1, 1]], [[0, 0], [0, 0]]]))
+    return vxa_document(mats, placeholder, dt_frac=1.0, grav_acc=-1.0, floor=True, temp_amplitude=7.72173, vary_temp=True, temp_period=0.1,
+                        enable_collision=enable_collision, enable_cilia=True, stop_formula=STOP_AT(stop_seconds), fitness_formula=fitness)
+
+
+def _largest_component(mask):
+    Z, Y, X = mask.shape
+    seen = np.zeros_like(mask, dtype=bool)
+    best = None
+    for start in zip(*np.nonzero(mask)):
+        if seen[start]:
+            continue
+        comp, stack = [], [start]
+        seen[start] = True
+        while stack:
+            z, y, x = stack.pop()
+            comp.append((z, y, x))
+            for dz, dy, dx in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+                q = (z + dz, y + dy, x + dx)
+                if 0 <= q[0] < Z and 0 <= q[1] < Y and 0 <= q[2] < X and mask[q] and not seen[q]:
+                    seen[q] = True
+                    stack.append(q)
+        if best is None or len(comp) > len(best):
+            best = comp
+    out = np.zeros_like(mask, dtype=bool)
+    for c in best or []:
+        out[c] = True
+    return out
+
+
+def xenobot_vxd(index, pebbles=True):
+    """C2 robot: largest 6-connected component of rand < p on the 12x12x7 body region of the lattice, p ~ U(0.35, 0.75),
+    numpy default_rng(1000 + index); BaseCiliaForce ~ U(-1,1)^3 (z component 0, as evolved bots push in-plane); optionally
+    two target pebbles in the far corner as in data1/bot_0017.vxd."""
+    rng = np.random.default_rng(1000 + index)
+    Z, Y, X = XENOBOT_DIMS
+    p = rng.uniform(0.35, 0.75)
+    mask = np.zeros((Z, Y, X), dtype=bool)
+    mask[:, :12, :12] = rng.uniform(size=(Z, 12, 12)) < p
+    body = _largest_component(mask)
+    # drop the body onto the floor: shift down so its lowest layer is z = 0
+    zs = np.nonzero(body.any(axis=(1, 2)))[0]
+    body = np.roll(body, -int(zs.min()), axis=0) if len(zs) else body
+    data = body.astype(int)
+    if pebbles:
+        data[0, Y - 1, X - 2:] = 2
+        data[1, Y - 1, X - 2:] = 2
+    cilia = np.zeros((Z, Y, X, 3))
+    cilia[..., :2] = rng.uniform(-1, 1, size=(Z, Y, X, 2))
+    cilia[data != 1] = 0
+    return "<VXD>" + structure_xml(data, base_cilia=cilia, replace="VXA.VXC.Structure") + "</VXD>"
+
+
+def contact_pile_vxa(k=3, cube=4, seed=7):
+    """C4 synthetic: k x k grid of cube^3 bodies dropped from staggered heights so they pile up and collide."""
+    rng = np.random.default_rng(seed)
+    gap = cube + 1
+    heights = rng.integers(0, 3, size=(k, k))
+    Z = cube * 2 + 3 + cube
+    data = np.zeros((Z, k * gap, k * gap), dtype=int)
+    for a in range(k):
+        for b in range(k):
+            z0 = int(heights[a, b])
+            data[z0:z0 + cube, a * gap:a * gap + cube, b * gap:b * gap + cube] = 1
+    # a second layer of bodies above, offset by half a cube so they land on the gaps
+    for a in range(k - 1):
+        for b in range(k - 1):
+            z0 = cube + 3
+            data[z0:z0 + cube, a * gap + cube // 2 + 1:a * gap + cube // 2 + 1 + cube, b * gap + cube // 2 + 1:b * gap + cube // 2 + 1 + cube] = 2
+    mats = [material(name="lower", E=5e6, density=1e6), material(name="upper", E=1e7, density=1e6)]
+    return vxa_document(mats, structure_xml(data), dt_frac=0.9, grav_acc=-9.81, floor=True, enable_collision=True)
