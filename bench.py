@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: voxel-steps/sec (device-timed) on the xenobot-generation workload.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+  python bench.py --impl reference ...        # the reference's own CPU path (oracle/_ref) on the same worlds
+
+Workload (config.workload): BASELINE.json configs[1] — a generation of 1024 xenobot-scale VXA worlds per GPU (cilia forces,
+floor, voxel-voxel contact), each bench "step" = one vx3b_batch_run advancing every world by --sim-steps time steps.
+Weak scaling: every rank gets its own 1024 worlds; the only cross-rank traffic is the report gather (fitness per world).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "voxel-steps/sec"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--worlds", type=int, default=1024, help="worlds per GPU")
+    ap.add_argument("--sim-steps", type=int, default=1000, help="time steps every world advances per bench step")
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 streaming, 2 resident")
+    ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube"])
+    ap.add_argument("--cube", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-worlds", type=int, default=8)
+    return ap.parse_args()
+
+
+def workload_config(args):
+    if args.workload == "cube":
+        return {"workload": f"BASELINE configs[2]: single {args.cube}^3-voxel soft body under gravity with floor contact, no self-collision",
+                "worlds_per_gpu": 1, "sim_steps_per_step": args.sim_steps, "parallelism": "replicas", "l2": "state larger than L2 + explicit L2 flush between steps"}
+    return {"workload": "BASELINE configs[1]: xenobot generation, 1024 small VXA worlds (~500 voxels, cilia forces, floor, contact) batched per B200",
+            "worlds_per_gpu": args.worlds, "sim_steps_per_step": args.sim_steps, "parallelism": f"worlds sharded over {args.gpus} GPU(s), no data-path collective",
+            "l2": "explicit L2 flush (256 MiB write) between timed steps"}
+
+
+def build_worlds(args, rank):
+    import gpuvoxels_b200 as gv
+    from gpuvoxels_b200 import worlds as W
+    if args.workload == "cube":
+        return [gv.Model.from_vxa(W.cube_vxa(args.cube))], [(W.cube_vxa(args.cube), None)]
+    base = W.xenobot_base_vxa()
+    texts = [(base, W.xenobot_vxd(rank * args.worlds + i)) for i in range(args.worlds)]
+    return [gv.Model.from_vxa(a, d) for a, d in texts], texts
+
+
+def algorithmic_bytes_per_sim_step(models, precision):
+    # fp32 112*Nv + 88*Nl, fp64 216*Nv + 160*Nl bytes per time step
+    nv = sum(m.num_voxels for m in models)
+    nl = sum(m.num_links for m in models)
+    return (112 * nv + 88 * nl) if precision == 32 else (216 * nv + 160 * nl)
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- reference (CPU) arm
+def reference_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "vx2_ref")
+    return p if os.path.exists(p) and os.access(p, os.X_OK) else None
+
+
+def run_reference_sample(texts, sim_steps, procs, collisions=True):
+    """Runs the UNMODIFIED reference CPU library on a sample of the same worlds, `procs` single-threaded processes at a time
+    (the reference has no CPU batch mode; one process per core is how a generation uses a whole host).  Returns
+    (voxel_steps_per_sec, total_voxel_steps, wall_seconds)."""
+    import gpuvoxels_b200 as gv
+    ref = reference_binary()
+    with tempfile.TemporaryDirectory() as td:
+        jobs = []
+        for i, (vxa, vxd) in enumerate(texts):
+            p = os.path.join(td, f"w{i}.vxa")
+            with open(p, "w") as f:
+                f.write(gv.Model.from_vxa(vxa, vxd).merged_vxa())
+            cmd = [ref, "--vxa", p, "--steps", str(sim_steps), "--vx3", "--enable-cilia", "1", "--threads", "1", "--time"]
+            if collisions:
+                cmd += ["--vx2-collisions", "1"]
+            jobs.append(cmd)
+        t0 = time.perf_counter()
+        running, outs, it = [], [], iter(jobs)
+        pending = True
+        while pending or running:
+            while pending and len(running) < procs:
+                try:
+                    running.append(subprocess.Popen(next(it), stdout=subprocess.PIPE, text=True))
+                except StopIteration:
+                    pending = False
+            for p in list(running):
+                if p.poll() is not None:
+                    outs.append(p.stdout.read())
+                    running.remove(p)
+            time.sleep(0.002)
+        wall = time.perf_counter() - t0
+    vs, rates = 0, []
+    for o in outs:
+        j = json.loads(o.strip().splitlines()[-1])
+        vs += j["voxels"] * j["steps"]
+        rates.append(j["voxel_steps_per_s"])  # steady_clock around the step loop only (parse/Import excluded)
+    return min(procs, len(jobs)) * float(np.mean(rates)), vs, wall
+
+
+def oracle_port_sample(models, sim_steps):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    t0 = time.perf_counter()
+    vs = 0
+    for m in models:
+        w = O.OracleWorld(m)
+        w.run(sim_steps)
+        vs += m.num_voxels * sim_steps
+    wall = time.perf_counter() - t0
+    return vs / wall, vs, wall
+
+
+def cpu_baseline(args, models, texts):
+    n = min(args.cpu_sample_worlds, len(texts))
+    cores = os.cpu_count() or 1
+    steps = min(args.sim_steps, 500 if args.workload == "xenobot" else 5)
+    if reference_binary():
+        procs = min(cores, n)
+        v, vs, wall = run_reference_sample(texts[:n], steps, procs, collisions=args.workload == "xenobot")
+        return {"value": v, "unit": METRIC, "cores": procs, "kind": "reference",
+                "sample": f"{n} of the {len(texts)} worlds x {steps} time steps, oracle/_ref/vx2_ref (unmodified CVoxelyze + VX3 stepping deltas, its own "
+                          f"collision system), {procs} single-threaded processes in parallel; {vs} voxel-steps in {wall:.1f} s"}
+    v, vs, wall = oracle_port_sample(models[:n], steps)
+    return {"value": v, "unit": METRIC, "cores": 1, "kind": "port",
+            "sample": f"{n} of the {len(texts)} worlds x {steps} time steps, scalar CPU restatement (oracle/vx3_oracle.cpp), 1 thread; {vs} voxel-steps in {wall:.1f} s"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import gpuvoxels_b200 as gv  # host model only (parsing); no CUDA needed for this arm
+    models, texts = build_worlds(args, 0)
+    cores = os.cpu_count() or 1
+    n = min(len(texts), max(cores, args.cpu_sample_worlds))
+    steps = min(args.sim_steps, 300 if args.workload == "xenobot" else 3)
+    times, vs_total, rates = [], 0, []
+    kind = "reference" if reference_binary() else "port"
+    for it in range(args.warmup + args.steps):
+        if kind == "reference":
+            v, vs, wall = run_reference_sample(texts[:n], steps, min(cores, n), collisions=args.workload == "xenobot")
+        else:
+            v, vs, wall = oracle_port_sample(models[:n], steps)
+        if it >= args.warmup:
+            times.append(wall)
+            vs_total += vs
+            rates.append(v)
+    value = float(np.mean(rates))
+    used = min(cores, n) if kind == "reference" else 1
+    sample = (f"each step = {n} of the {len(texts)} worlds x {steps} time steps on the host CPU "
+              f"({'oracle/_ref/vx2_ref, unmodified reference CPU library' if kind == 'reference' else 'oracle port'}, {used} core(s))")
+    cfg = workload_config(args)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": cfg, "cpu_baseline": {"value": value, "unit": METRIC, "cores": used, "kind": kind, "sample": sample},
+                      "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def upload_bytes(models):
+    import ctypes as C
+    from gpuvoxels_b200 import _abi
+    total = 0
+    for m in models:
+        d = m.desc
+        nv, nl = d.num_voxels, d.num_links
+        total += C.sizeof(_abi.WorldDesc) + nv * (6 + 4 + 8 + 24 + 24 + 1 + 12 + 12 + 24 + 24) + nl * (4 + 4 + 1 + 4)
+        total += d.num_voxel_mats * C.sizeof(_abi.VoxelMaterial) + d.num_link_mats * C.sizeof(_abi.LinkMaterial)
+    return total
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import gpuvoxels_b200 as gv
+    from gpuvoxels_b200 import _abi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    models, texts = build_worlds(args, rank)
+    ctx = gv.Context(local, args.precision)
+    ctx.set_option("path", args.path)
+    ctx.upload(models)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    bytes_per_sim_step = algorithmic_bytes_per_sim_step(models, args.precision)
+
+    # ---- device-timed throughput: state resident in HBM, K steps -------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.run(args.sim_steps)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    dev_ms, vsteps, launches = 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.run(args.sim_steps)
+        ms, k = ctx.timing()
+        dev_ms += ms
+        launches += k
+        vsteps += ctx.total_voxel_steps()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    results = ctx.results()
+    diverged = sum(r.diverged for r in results)
+
+    # ---- end to end through the C ABI with host buffers: upload + run + results (+ report gather) ----------------------
+    h2d = upload_bytes(models)
+    d2h = len(models) * C.sizeof(_abi.WorldResult)
+    ctx2 = gv.Context(local, args.precision)
+    ctx2.set_option("path", args.path)
+    e2e_steps = max(1, min(args.steps, 3))
+    ctx2.upload(models)
+    ctx2.run(args.sim_steps)
+    barrier()
+    t1 = time.perf_counter()
+    e2e_vs = 0
+    for _ in range(e2e_steps):
+        ctx2.upload(models)
+        ctx2.run(args.sim_steps)
+        res = ctx2.results()
+        fit = torch.tensor([r.fitness_score for r in res], dtype=torch.float64, device="cuda")
+        if world > 1:
+            gathered = [torch.empty_like(fit) for _ in range(world)]
+            dist.all_gather(gathered, fit)
+        _ = fit.cpu()
+        e2e_vs += ctx2.total_voxel_steps()
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    ctx2.close()
+
+    # ---- reduce over ranks: time = max, work = sum -----------------------------------------------------------------------
+    stats = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device="cuda")
+    work = torch.tensor([float(vsteps), float(e2e_vs), float(launches), float(diverged)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_max, e2e_wall_max = stats.tolist()
+    vs_all, e2e_vs_all, launches_all, diverged_all = work.tolist()
+
+    if rank == 0:
+        value = vs_all / (dev_ms_max * 1e-3)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md)"
+        # dominant kernel: the resident (or streaming link+voxel) step kernel; algorithmic bytes per launch = per-step bytes x steps
+        achieved = bytes_per_sim_step * args.sim_steps / ((dev_ms / args.steps) * 1e-3) / 1e9
+        kernel = "k_resident" if (args.path == 2 or (args.path == 0 and args.workload == "xenobot")) else "k_links+k_voxels"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(kernel)
+        out = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 arithmetic, f64 positions" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args),
+            "voxels_per_gpu": sum(m.num_voxels for m in models), "links_per_gpu": sum(m.num_links for m in models),
+            "wall_s_timed_region": wall_max, "diverged_worlds": int(diverged_all),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": kernel, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_sim_step * args.sim_steps,
+                         "note": "algorithmic bytes = (112*Nv + 88*Nl) per time step (SURVEY.md 8d) x time steps per launch, rank 0's worlds"},
+            "e2e": {"value": e2e_vs_all / e2e_wall_max, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "vx3b_batch_upload (host arrays -> HBM) + vx3b_batch_run + vx3b_batch_results (+ NCCL gather of fitness for N>1), wall clock"},
+            "gpu_launches": int(launches_all), "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, models, texts)
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

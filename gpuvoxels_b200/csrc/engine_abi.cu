@@ -1,0 +1,116 @@
+// Engine part of the C ABI (include/vx3b200.h, section 2).
+#include <algorithm>
+#include <memory>
+#include <string>
+
+#include "engine_base.hpp"
+
+namespace vx3b {
+void set_error(const std::string &e);
+#define CUDA_TRY(expr)                                                                                                          \
+    do {                                                                                                                        \
+        cudaError_t _e = (expr);                                                                                                \
+        if (_e != cudaSuccess) {                                                                                                \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                                                      \
+            return VX3B_ERR_CUDA;                                                                                               \
+        }                                                                                                                       \
+    } while (0)
+} // namespace vx3b
+
+struct vx3b_ctx {
+    std::unique_ptr<vx3b::EngineBase> e;
+};
+
+extern "C" {
+
+const char *vx3b_version(void) { return "vx3b200 0.1 (sm_100a)"; }
+
+int vx3b_ctx_create(int device, int precision, vx3b_ctx **out) {
+    using namespace vx3b;
+    if (!out || (precision != VX3B_FP32 && precision != VX3B_FP64)) {
+        set_error("vx3b_ctx_create: precision must be VX3B_FP32 or VX3B_FP64");
+        return VX3B_ERR_ARG;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("vx3b_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU fallback");
+        return VX3B_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        set_error("vx3b_ctx_create: device index out of range");
+        return VX3B_ERR_ARG;
+    }
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("vx3b_ctx_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+        return VX3B_ERR_CUDA;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    auto *c = new vx3b_ctx();
+    c->e.reset(precision == VX3B_FP32 ? make_engine_f32() : make_engine_f64());
+    c->e->device = device;
+    c->e->precision = precision;
+    *out = c;
+    return VX3B_OK;
+}
+
+void vx3b_ctx_destroy(vx3b_ctx *ctx) { delete ctx; }
+
+int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value) {
+    if (!ctx || !name)
+        return VX3B_ERR_ARG;
+    std::string n = name;
+    if (n == "path")
+        ctx->e->path = (int)value;
+    else if (n == "record_pairs")
+        ctx->e->recordPairs = value != 0;
+    else if (n == "chunk")
+        ctx->e->chunk = std::max(1, (int)value);
+    else if (n == "dt_override")
+        ctx->e->dtOverride = value;
+    else if (n == "resident_threads")
+        ctx->e->residentThreads = (int)value;
+    else {
+        vx3b::set_error("unknown option: " + n);
+        return VX3B_ERR_ARG;
+    }
+    return VX3B_OK;
+}
+
+int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t s) {
+    if (!ctx)
+        return VX3B_ERR_ARG;
+    if (ctx->e->ownStream && ctx->e->stream)
+        cudaStreamDestroy(ctx->e->stream);
+    ctx->e->stream = (cudaStream_t)s;
+    ctx->e->ownStream = false;
+    return VX3B_OK;
+}
+
+int vx3b_batch_upload(vx3b_ctx *ctx, const VX3B_WorldDesc *worlds, int n) { return ctx ? ctx->e->upload(worlds, n) : VX3B_ERR_ARG; }
+int vx3b_batch_run(vx3b_ctx *ctx, int64_t max_steps, int use_stop) { return ctx ? ctx->e->run(max_steps, use_stop) : VX3B_ERR_ARG; }
+int vx3b_batch_results(vx3b_ctx *ctx, VX3B_WorldResult *out) { return ctx ? ctx->e->results(out) : VX3B_ERR_ARG; }
+int vx3b_batch_read_state(vx3b_ctx *ctx, int world, double *p, double *o, double *l, double *a) {
+    return ctx ? ctx->e->read_state(world, p, o, l, a) : VX3B_ERR_ARG;
+}
+int vx3b_batch_read_initial_pos(vx3b_ctx *ctx, int world, double *p) { return ctx ? ctx->e->read_initial_pos(world, p) : VX3B_ERR_ARG; }
+int vx3b_batch_read_links(vx3b_ctx *ctx, int world, double *p2, double *a1, double *a2, int32_t *f) {
+    return ctx ? ctx->e->read_links(world, p2, a1, a2, f) : VX3B_ERR_ARG;
+}
+int vx3b_batch_collision_pairs(vx3b_ctx *ctx, int world, int32_t *pairs, int32_t *n) {
+    return ctx ? ctx->e->collision_pairs(world, pairs, n) : VX3B_ERR_ARG;
+}
+int vx3b_ctx_timing(vx3b_ctx *ctx, float *ms, int64_t *launches) {
+    if (!ctx)
+        return VX3B_ERR_ARG;
+    if (ms)
+        *ms = ctx->e->lastMs;
+    if (launches)
+        *launches = ctx->e->lastLaunches;
+    return VX3B_OK;
+}
+int64_t vx3b_ctx_total_voxel_steps(vx3b_ctx *ctx) { return ctx ? ctx->e->lastVoxelSteps : 0; }
+
+} // extern "C"

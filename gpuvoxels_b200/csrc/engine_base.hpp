@@ -1,0 +1,39 @@
+// Precision-independent interface of the step engine; Engine<float> and Engine<double> live in separate
+// translation units so the fp64 validation build can be compiled without FMA contraction (-fmad=false),
+// matching the reference CPU library's (and the oracle's) unfused double arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vx3b200.h"
+
+namespace vx3b {
+
+class EngineBase {
+  public:
+    virtual ~EngineBase() {}
+    virtual int upload(const VX3B_WorldDesc *worlds, int n) = 0;
+    virtual int run(int64_t maxSteps, int useStop) = 0;
+    virtual int results(VX3B_WorldResult *out) = 0;
+    virtual int read_state(int world, double *pos, double *orient, double *lin, double *ang) = 0;
+    virtual int read_initial_pos(int world, double *pos) = 0;
+    virtual int read_links(int world, double *pos2, double *a1, double *a2, int32_t *flags) = 0;
+    virtual int collision_pairs(int world, int32_t *pairs, int32_t *n) = 0;
+    int device = 0, precision = 32;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    float lastMs = 0;
+    int64_t lastLaunches = 0, lastVoxelSteps = 0;
+    // options
+    int path = 0;         // 0 auto, 1 streaming, 2 resident
+    int recordPairs = 0;  // keep the collision pair list of the last step (parity tests)
+    int chunk = 64;       // steps per CUDA-graph replay on the streaming path
+    double dtOverride = 0;
+    int residentThreads = 256;
+};
+
+
+EngineBase *make_engine_f32();
+EngineBase *make_engine_f64();
+
+} // namespace vx3b

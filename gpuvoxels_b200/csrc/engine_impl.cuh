@@ -1,3 +1,4 @@
+#pragma once
 // Step engine: device memory, upload, run loop, read-back and the engine part of the C ABI.
 // Replaces VX3_VoxelyzeKernel's host constructor (VX3/VX3_VoxelyzeKernel.cu:27-105),
 // VX3_SimulationManager::startKernel / collectResults (VX3/VX3_SimulationManager.cu:384-458) and, through the
@@ -11,6 +12,7 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "engine_base.hpp"
 #include "kernels_resident.cuh"
 #include "kernels_stream.cuh"
 
@@ -92,29 +94,6 @@ static double recommended_dt(const VX3B_WorldDesc &d) {
 }
 
 static bool formula_empty(const VX3B_Token *t) { return t[0].op == VX3B_MT_END; }
-
-class EngineBase {
-  public:
-    virtual ~EngineBase() {}
-    virtual int upload(const VX3B_WorldDesc *worlds, int n) = 0;
-    virtual int run(int64_t maxSteps, int useStop) = 0;
-    virtual int results(VX3B_WorldResult *out) = 0;
-    virtual int read_state(int world, double *pos, double *orient, double *lin, double *ang) = 0;
-    virtual int read_initial_pos(int world, double *pos) = 0;
-    virtual int read_links(int world, double *pos2, double *a1, double *a2, int32_t *flags) = 0;
-    virtual int collision_pairs(int world, int32_t *pairs, int32_t *n) = 0;
-    int device = 0, precision = 32;
-    cudaStream_t stream = nullptr;
-    bool ownStream = false;
-    float lastMs = 0;
-    int64_t lastLaunches = 0, lastVoxelSteps = 0;
-    // options
-    int path = 0;         // 0 auto, 1 streaming, 2 resident
-    int recordPairs = 0;  // keep the collision pair list of the last step (parity tests)
-    int chunk = 64;       // steps per CUDA-graph replay on the streaming path
-    double dtOverride = 0;
-    int residentThreads = 256;
-};
 
 template <class R> class Engine : public EngineBase {
     using T4 = typename Store<R>::T4;
@@ -810,105 +789,5 @@ template <class R> class Engine : public EngineBase {
     }
 };
 
+
 } // namespace vx3b
-
-struct vx3b_ctx {
-    std::unique_ptr<vx3b::EngineBase> e;
-};
-
-extern "C" {
-
-const char *vx3b_version(void) { return "vx3b200 0.1 (sm_100a)"; }
-
-int vx3b_ctx_create(int device, int precision, vx3b_ctx **out) {
-    using namespace vx3b;
-    if (!out || (precision != VX3B_FP32 && precision != VX3B_FP64)) {
-        set_error("vx3b_ctx_create: precision must be VX3B_FP32 or VX3B_FP64");
-        return VX3B_ERR_ARG;
-    }
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        set_error(std::string("vx3b_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU fallback");
-        return VX3B_ERR_CUDA;
-    }
-    if (device < 0 || device >= count) {
-        set_error("vx3b_ctx_create: device index out of range");
-        return VX3B_ERR_ARG;
-    }
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        set_error("vx3b_ctx_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
-        return VX3B_ERR_CUDA;
-    }
-    CUDA_TRY(cudaSetDevice(device));
-    auto *c = new vx3b_ctx();
-    if (precision == VX3B_FP32)
-        c->e = std::make_unique<Engine<float>>();
-    else
-        c->e = std::make_unique<Engine<double>>();
-    c->e->device = device;
-    c->e->precision = precision;
-    *out = c;
-    return VX3B_OK;
-}
-
-void vx3b_ctx_destroy(vx3b_ctx *ctx) { delete ctx; }
-
-int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value) {
-    if (!ctx || !name)
-        return VX3B_ERR_ARG;
-    std::string n = name;
-    if (n == "path")
-        ctx->e->path = (int)value;
-    else if (n == "record_pairs")
-        ctx->e->recordPairs = value != 0;
-    else if (n == "chunk")
-        ctx->e->chunk = std::max(1, (int)value);
-    else if (n == "dt_override")
-        ctx->e->dtOverride = value;
-    else if (n == "resident_threads")
-        ctx->e->residentThreads = (int)value;
-    else {
-        vx3b::set_error("unknown option: " + n);
-        return VX3B_ERR_ARG;
-    }
-    return VX3B_OK;
-}
-
-int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t s) {
-    if (!ctx)
-        return VX3B_ERR_ARG;
-    if (ctx->e->ownStream && ctx->e->stream)
-        cudaStreamDestroy(ctx->e->stream);
-    ctx->e->stream = (cudaStream_t)s;
-    ctx->e->ownStream = false;
-    return VX3B_OK;
-}
-
-int vx3b_batch_upload(vx3b_ctx *ctx, const VX3B_WorldDesc *worlds, int n) { return ctx ? ctx->e->upload(worlds, n) : VX3B_ERR_ARG; }
-int vx3b_batch_run(vx3b_ctx *ctx, int64_t max_steps, int use_stop) { return ctx ? ctx->e->run(max_steps, use_stop) : VX3B_ERR_ARG; }
-int vx3b_batch_results(vx3b_ctx *ctx, VX3B_WorldResult *out) { return ctx ? ctx->e->results(out) : VX3B_ERR_ARG; }
-int vx3b_batch_read_state(vx3b_ctx *ctx, int world, double *p, double *o, double *l, double *a) {
-    return ctx ? ctx->e->read_state(world, p, o, l, a) : VX3B_ERR_ARG;
-}
-int vx3b_batch_read_initial_pos(vx3b_ctx *ctx, int world, double *p) { return ctx ? ctx->e->read_initial_pos(world, p) : VX3B_ERR_ARG; }
-int vx3b_batch_read_links(vx3b_ctx *ctx, int world, double *p2, double *a1, double *a2, int32_t *f) {
-    return ctx ? ctx->e->read_links(world, p2, a1, a2, f) : VX3B_ERR_ARG;
-}
-int vx3b_batch_collision_pairs(vx3b_ctx *ctx, int world, int32_t *pairs, int32_t *n) {
-    return ctx ? ctx->e->collision_pairs(world, pairs, n) : VX3B_ERR_ARG;
-}
-int vx3b_ctx_timing(vx3b_ctx *ctx, float *ms, int64_t *launches) {
-    if (!ctx)
-        return VX3B_ERR_ARG;
-    if (ms)
-        *ms = ctx->e->lastMs;
-    if (launches)
-        *launches = ctx->e->lastLaunches;
-    return VX3B_OK;
-}
-int64_t vx3b_ctx_total_voxel_steps(vx3b_ctx *ctx) { return ctx ? ctx->e->lastVoxelSteps : 0; }
-
-} // extern "C"

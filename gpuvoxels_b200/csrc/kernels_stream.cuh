@@ -419,6 +419,6 @@ template <class R> __global__ void k_world_step(Arrays<R> A, int useStop, int *a
         atomicAdd(activeCount, 1);
 }
 
-__global__ void k_zero_int(int *p) { *p = 0; }
+static __global__ void k_zero_int(int *p) { *p = 0; }
 
 } // namespace vx3b

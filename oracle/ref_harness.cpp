@@ -75,7 +75,7 @@ struct Dump {
 struct Args {
     std::string vxa, dump, dump_model;
     long steps = 0;
-    bool vx3 = false, enable_expansion = false, enable_cilia = false, no_temp = false, timing = false;
+    bool vx3 = false, enable_expansion = false, enable_cilia = false, no_temp = false, timing = false, vx2_collisions = false;
     int threads = 1;
     double dt_override = 0;
     int repeat = 1;
@@ -237,6 +237,8 @@ int main(int argc, char **argv) {
             a.enable_expansion = atoi(next()) != 0;
         else if (k == "--enable-cilia")
             a.enable_cilia = atoi(next()) != 0;
+        else if (k == "--vx2-collisions")
+            a.vx2_collisions = atoi(next()) != 0;
         else if (k == "--no-temp")
             a.no_temp = true;
         else if (k == "--time")
@@ -280,6 +282,8 @@ int main(int argc, char **argv) {
         Sim.ReadVXA(&XML, &msg);
         Sim.Import(NULL, NULL, &msg);
         CVoxelyze &Vx = Sim.Vx;
+        if (a.vx2_collisions) // Voxelyze2's own watch-list contact (Voxelyze.cpp:670-750); Import() switched it off (Voxelyze.cpp:347)
+            Vx.enableCollisions(true);
         nv = (int)Vx.voxelsList.size();
         nl = (int)Vx.linksList.size();
 

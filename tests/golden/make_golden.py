@@ -1,0 +1,48 @@
+"""Regenerates tests/golden/*.vxbin by running the UNMODIFIED reference CPU library (oracle/_ref/vx2_ref, built from
+/root/reference by oracle/Makefile) on VXA text.  Run in the build container (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Each fixture holds the reference's model dump (voxels, links, material constants) and its state after N steps.
+`mode` vx2 = plain CVoxelyze::doTimeStep; vx3 = with the Voxelyze3 stepping deltas applied by the harness
+(oracle/ref_harness.cpp --vx3: double dt, phase-offset temperature, cilia, angMom zeroing)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import gpuvoxels_b200 as gv  # noqa: E402
+import oracle_lib as O  # noqa: E402
+from gpuvoxels_b200 import worlds as W  # noqa: E402
+
+CASES = {
+    # name: (vxa text, vxd text, steps, mode, cilia)
+    "example_vx2_1000": (open(os.path.join(ROOT, "tests", "data", "example.vxa")).read(), None, 1000, "vx2", False),
+    "example_vx3_1000": (open(os.path.join(ROOT, "tests", "data", "example.vxa")).read(), None, 1000, "vx3", False),
+    "small_vx3_2000": (W.small_block_vxa(), None, 2000, "vx3", False),
+    "xeno3_vx3_cilia_800": (W.xenobot_base_vxa(), W.xenobot_vxd(3), 800, "vx3", True),
+    "cube8_vx2_400": (W.cube_vxa(8), None, 400, "vx2", False),
+}
+
+
+def main():
+    assert O.have_reference(), "build oracle/_ref first: make -C oracle ref"
+    for name, (vxa, vxd, steps, mode, cilia) in CASES.items():
+        m = gv.Model.from_vxa(vxa, vxd)
+        state, model, _ = O.run_reference(m.merged_vxa(), steps, vx3=(mode == "vx3"), enable_cilia=cilia, want_model=True)
+        out = {}
+        for k in ("scalars", "pos", "orient", "linMom", "angMom", "link_pos2", "link_angle1v", "link_angle2v", "link_flags"):
+            out["state_" + k] = state[k]
+        for k, v in model.items():
+            out["model_" + k] = v
+        O.write_vxbin(os.path.join(HERE, name + ".vxbin"), out)
+        print(name, "voxels", len(state["pos"]), "links", len(state["link_pos2"]), "dt", state["scalars"][0, 1])
+
+
+if __name__ == "__main__":
+    main()

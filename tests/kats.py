@@ -1,0 +1,208 @@
+"""Known-answer scenarios replayed from the reference's own Voxelyze2 unit tests
+(/root/reference/VoxCAD/src/VX2/test/tVoxelyze.h), expressed with our CVoxelyze-style builder.
+Each scenario returns (model, steps, check) where check(state_dict) asserts the reference's expected value.
+The same scenarios run on the CPU oracle (-m "not gpu") and through the C ABI on the GPU (-m gpu)."""
+import numpy as np
+
+import gpuvoxels_b200 as gv
+
+TX, TY, TZ, RX, RY, RZ = 1, 2, 4, 8, 16, 32
+OFF = {"X_POS": (1, 0, 0), "X_NEG": (-1, 0, 0), "Y_POS": (0, 1, 0), "Y_NEG": (0, -1, 0), "Z_POS": (0, 0, 1), "Z_NEG": (0, 0, -1)}
+
+
+def rotvec(q):
+    """Quat3D::ToRotationVector (VoxCAD/src/VX2/include/Quat3D.h)"""
+    w, v = q[0], np.array(q[1:])
+    if w >= 1.0 or w <= -1.0:
+        return np.zeros(3)
+    sl = 1.0 - w * w
+    if sl < 2.4e-3:
+        return v * 2.0 * np.sqrt((2 - 2 * w) / sl)
+    return v * 2.0 * np.arccos(w) / np.sqrt(sl)
+
+
+def _base(sz=0.001, E=1e6, rho=1e3, internal=1.0, glob=0.2):
+    m = gv.Model.new(sz)
+    mat = m.add_material(E, rho, internal_damping=internal, global_damping=glob)
+    m.set_world_param("dt_frac", 1.0)  # tests step with ts = recommendedTimeStep()
+    return m, mat
+
+
+def two_vox(direction, force, moment, free_dof, expected, what, steps=1000):
+    """test2Vox (tVoxelyze.h:66-113): voxel 1 fixed, voxel 2 loaded; all dofs of voxel 2 fixed except free_dof."""
+    m, mat = _base()
+    off = OFF[direction]
+    m.set_voxel(mat, 0, 0, 0)
+    m.set_fixed(0, 0, 0, 63)
+    m.set_voxel(mat, *off)
+    m.set_fixed(*off, 63 & ~free_dof)
+    m.set_force(*off, force=force, moment=moment)
+    m.finalize()
+    idx = 1
+
+    def check(state, tol=1e-5):
+        if what in (TX, TY, TZ):
+            k = {TX: 0, TY: 1, TZ: 2}[what]
+            data = state["pos"][idx][k] - off[k] * 0.001
+        else:
+            k = {RX: 0, RY: 1, RZ: 2}[what]
+            data = rotvec(state["orient"][idx])[k]
+        if expected == 0:
+            assert abs(data) < 1e-12, data
+        else:
+            assert abs(data - expected) < abs(expected) * max(tol, 1e-5), (data, expected)
+    return m, steps, check
+
+
+def single_bond_cases():
+    """subset of TEST(CVoxelyze, singleBondFixedFree), tVoxelyze.h:142-199"""
+    F, M = 1e-3, 1e-9
+    c = []
+    for d in ("X_POS", "X_NEG"):
+        c.append((f"{d}-FPX", two_vox(d, (F, 0, 0), None, TX, 1e-6, TX)))
+        c.append((f"{d}-FPY", two_vox(d, (0, F, 0), None, TY, 1e-6, TY)))
+    c.append(("X_POS-FNZ", two_vox("X_POS", (0, 0, -F), None, TZ, -1e-6, TZ)))
+    c.append(("Y_POS-FPX", two_vox("Y_POS", (F, 0, 0), None, TX, 1e-6, TX)))
+    c.append(("Z_NEG-FPZ", two_vox("Z_NEG", (0, 0, F), None, TZ, 1e-6, TZ)))
+    c.append(("X_POS-MPX", two_vox("X_POS", None, (M, 0, 0), RX, 1.2e-5, RX)))
+    c.append(("X_POS-MNY", two_vox("X_POS", None, (0, -M, 0), RY, -3e-6, RY)))
+    c.append(("Y_POS-MPY", two_vox("Y_POS", None, (0, M, 0), RY, 1.2e-5, RY)))
+    c.append(("Z_POS-MPX", two_vox("Z_POS", None, (M, 0, 0), RX, 3e-6, RX)))
+    c.append(("X_POS-MPY-TZ", two_vox("X_POS", None, (0, M, 0), TZ | RY, -6e-9, TZ)))
+    c.append(("X_POS-FPY-RZ", two_vox("X_POS", (0, F, 0), None, TY | RZ, 6e-3, RZ)))
+    return c
+
+
+def internal_damping():
+    """TEST(CVoxelyze, internalDamping), tVoxelyze.h:261-285: expects 1e-9/6 (EXPECT_FLOAT_EQ)"""
+    m, mat = _base(internal=1.0, glob=0.0)
+    m.set_voxel(mat, 0, 0, 0)
+    m.set_force(0, 0, 0, force=(1e-6, 1e-6, 1e-6))
+    for off in OFF.values():
+        m.set_voxel(mat, *off)
+        m.set_fixed(*off, 63)
+    m.finalize()
+
+    def check(state, tol=4e-7):
+        assert abs(state["pos"][0][1] - 1e-9 / 6) < max(tol, 4e-7) * 1e-9 / 6, state["pos"][0]
+    return m, 100, check
+
+
+def global_damping_cantilever():
+    """second half of TEST(CVoxelyze, globalDamping), tVoxelyze.h:316-334: expects 4e-9 (EXPECT_FLOAT_EQ)"""
+    m, mat = _base(internal=0.0, glob=0.25)
+    m.set_voxel(mat, 0, 0, 0)
+    m.set_fixed(0, 0, 0, 63)
+    m.set_voxel(mat, 1, 0, 0)
+    m.set_force(1, 0, 0, force=(1e-6, 1e-6, 1e-6))
+    m.finalize()
+
+    def check(state, tol=4e-7):
+        assert abs(state["pos"][1][1] - 4e-9) < max(tol, 4e-7) * 4e-9, state["pos"][1]
+    return m, 300, check
+
+
+def combined_damping():
+    """TEST(CVoxelyze, combinedDamping) first pass, tVoxelyze.h:336-363: voxel(3,0,0).z == 1.742e-8 +- 1e-10"""
+    m, mat = _base(internal=1.0, glob=0.05)
+    idx = None
+    for i in range(4):
+        for j in range(3):
+            for k in range(3):
+                v = m.set_voxel(mat, i, j, k)
+                if i == 0:
+                    m.set_fixed(i, j, k, 63)
+                elif i == 3:
+                    m.set_force(i, j, k, force=(0, 0, 1e-6))
+                if (i, j, k) == (3, 0, 0):
+                    idx = v
+    m.finalize()
+
+    def check(state, tol=0):
+        assert abs(state["pos"][idx][2] - 1.742e-8) < 1e-10 + tol * 1.742e-8, state["pos"][idx]
+    return m, 1000, check
+
+
+def large_deformation_damping():
+    """TEST(CVoxelyze, largeDeformationDamping), tVoxelyze.h:442-469: z == 9.5587e-4 +- 1e-7 after 200 steps"""
+    m, mat = _base(internal=1.0, glob=0.2)
+    m.set_voxel(mat, 0, 0, 0)
+    m.set_fixed(0, 0, 0, 63)
+    m.set_voxel(mat, 1, 0, 0)
+    m.set_force(1, 0, 0, force=(-0.2, 0.0, 0.2))
+    m.finalize()
+
+    def check(state, tol=0):
+        assert abs(state["pos"][1][2] - 9.5587e-4) < 1e-7 + tol * 9.5587e-4, state["pos"][1]
+    return m, 200, check
+
+
+def multi_simple2():
+    """TEST(CVoxelyze, multiSimple2), tVoxelyze.h:642-680: x(7) - 0.007 == 3.5035e-6 +- 1e-10 after 10000 steps"""
+    m = gv.Model.new(0.001)
+    m1 = m.add_material(1e6, 1e3, internal_damping=1.0, global_damping=0.01)
+    m2 = m.add_material(1e9, 1e3, internal_damping=1.0, global_damping=0.01)
+    m.set_world_param("dt_frac", 1.0)
+    for i in range(8):
+        m.set_voxel(m1 if (i // 2) % 2 == 0 else m2, i, 0, 0)
+    m.set_fixed(0, 0, 0, 63)
+    m.set_force(7, 0, 0, force=(1e-3, 0, 0))
+    m.finalize()
+
+    def check(state, tol=0):
+        assert abs((state["pos"][7][0] - 0.007) - 3.5035e-6) < 1e-10 + tol * 3.5035e-6, state["pos"][7]
+    return m, 10000, check
+
+
+def double_bond_cantilever(axis, sign):
+    """TEST(CVoxelyze, doubleBondCantilever), tVoxelyze.h:520-566: tip deflection 1e-8 (axial) / 1.6e-7 (FL^3/3EI) within 1e-4"""
+    m, mat = _base(internal=1.0, glob=0.1)
+    for i in range(3):
+        m.set_voxel(mat, i, 0, 0)
+    m.set_fixed(0, 0, 0, 63)
+    i = axis
+    fixed = (TX if i != 0 else 0) | (TY if i != 1 else 0) | (TZ if i != 2 else 0) | RX | (RY if i != 2 else 0) | (RZ if i != 1 else 0)
+    m.set_fixed(2, 0, 0, fixed)
+    f = [0.0, 0.0, 0.0]
+    f[i] = sign * 5e-6
+    m.set_force(2, 0, 0, force=f)
+    m.finalize()
+    expected = sign * (1e-8 if i == 0 else 1.6e-7)
+
+    def check(state, tol=0):
+        data = (state["pos"][2] - np.array([0.002, 0, 0]))[i]
+        assert abs(data - expected) < abs(expected) * (1e-4 + tol), (data, expected)
+    return m, 3000, check
+
+
+def temperature(delta, expected):
+    """TEST(CVoxelyze, temperature), tVoxelyze.h:990-1032: bimorph tip z = 2.55e-5 (+5 K) / -2.591e-5 (-5 K), +-1e-8"""
+    m = gv.Model.new(0.001)
+    m1 = m.add_material(1e6, 1e3, internal_damping=1.0, global_damping=0.15, cte=0.01)
+    m2 = m.add_material(1e7, 1e3, internal_damping=1.0, global_damping=0.15)
+    m.set_world_param("dt_frac", 1.0)
+    idx = None
+    for i in range(3):
+        v = m.set_voxel(m1, i, 0, 0)
+        if i == 2:
+            idx = v
+        m.set_voxel(m2, i, 0, 1)
+    m.set_fixed(0, 0, 0, 63)
+    m.set_fixed(0, 0, 1, 63)
+    m.set_world_param("initial_temp", delta)
+    m.finalize()
+
+    def check(state, tol=0):
+        assert abs(state["pos"][idx][2] - expected) < 1e-8 + tol * abs(expected), state["pos"][idx]
+    return m, 500, check
+
+
+def all_kats():
+    k = [("singleBond-" + n, c) for n, c in single_bond_cases()]
+    k += [("internalDamping", internal_damping()), ("globalDampingCantilever", global_damping_cantilever()),
+          ("combinedDamping", combined_damping()), ("largeDeformationDamping", large_deformation_damping()),
+          ("multiSimple2", multi_simple2()), ("temperature+5", temperature(5.0, 2.55e-5)), ("temperature-5", temperature(-5.0, -2.591e-5))]
+    for axis in range(3):
+        for sign in (1.0, -1.0):
+            k.append((f"doubleBondCantilever-{axis}{'+' if sign > 0 else '-'}", double_bond_cantilever(axis, sign)))
+    return k

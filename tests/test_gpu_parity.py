@@ -1,0 +1,224 @@
+"""Parity tests proper: the CUDA engine, called through the C ABI, against the CPU oracle and the reference's golden
+vectors on the same inputs.  Tolerances are the north star's (BASELINE.json): fp64 validation build 1e-5 relative over
+1,000 steps; fp32 1e-3 relative on collision-free cases; fitness within 1 % on contact-heavy runs; collision pair sets
+bit-exact at a fixed step.  'relative' here = max |Δ| over voxels divided by the largest displacement from the lattice
+(stricter than dividing by the position magnitude)."""
+import os
+import tempfile
+import xml.etree.ElementTree as ET
+
+import numpy as np
+import pytest
+
+import gpuvoxels_b200 as gv
+import kats
+import oracle_lib as O
+from gpuvoxels_b200 import worlds as W
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+STREAM, RESIDENT = 1, 2
+
+
+def gpu_run(models, steps, precision, path, use_stop=False, **opts):
+    ctx = gv.Context(0, precision)
+    ctx.set_option("path", path)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    ctx.upload(models)
+    ctx.run(steps, use_stop)
+    return ctx
+
+
+def disp_scale(model, pos):
+    return max(np.abs(pos - model.array("lattice") * model.desc.vox_size).max(), 1e-30)
+
+
+def pos_err(model, got, ref):
+    return np.abs(got["pos"] - ref["pos"]).max() / disp_scale(model, ref["pos"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+KATS = kats.all_kats()
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT])
+@pytest.mark.parametrize("precision,tol", [(gv.FP64, 0.0), (gv.FP32, 2e-3)])
+@pytest.mark.parametrize("name,case", KATS, ids=[n for n, _ in KATS])
+def test_reference_kats_through_the_c_abi(name, case, precision, tol, path):
+    model, steps, check = case
+    ctx = gpu_run([model], steps, precision, path)
+    check(ctx.read_state(0), tol)
+    ctx.close()
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT])
+def test_fp64_matches_oracle_over_1000_steps(example_vxa, path):
+    model = gv.Model.from_vxa(example_vxa)  # verbatim: VX3 semantics, collisions on (no pairs form in 1000 steps), actuation on
+    want = O.OracleWorld(model)
+    want.run(1000)
+    ctx = gpu_run([model], 1000, gv.FP64, path)
+    got, ref = ctx.read_state(0), want.state()
+    assert pos_err(model, got, ref) < 1e-5
+    assert np.abs(got["orient"] - ref["orient"]).max() < 1e-5 * max(np.abs(ref["orient"][:, 1:]).max(), 1e-30)
+    gl, rl = ctx.read_links(0), want.links()
+    assert np.array_equal(gl["flags"], rl["flags"])
+    assert O.rel_err(gl["pos2"], rl["pos2"]) < 1e-4
+    ctx.close()
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT])
+@pytest.mark.parametrize("maker,steps", [(lambda: (W.small_block_vxa(), None), 2000), (lambda: (W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(4)), 1000),
+                                         (lambda: (open(os.path.join(ROOT, "tests", "data", "example.vxa")).read(), None), 1000)])
+def test_fp32_matches_oracle_collision_free(maker, steps, path):
+    vxa, vxd = maker()
+    model = gv.Model.from_vxa(vxa, vxd)
+    model.set_world_param("enable_collision", 0)
+    want = O.OracleWorld(model)
+    want.run(steps)
+    ctx = gpu_run([model], steps, gv.FP32, path)
+    got, ref = ctx.read_state(0), want.state()
+    assert pos_err(model, got, ref) < 1e-3
+    assert np.abs(got["orient"] - ref["orient"]).max() < 1e-3
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["example_vx2_1000", "example_vx3_1000", "small_vx3_2000"])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT])
+def test_fp64_matches_reference_golden_vectors(name, path):
+    """CUDA fp64 directly against outputs of the unmodified reference CPU library (tests/golden/make_golden.py)."""
+    from golden.make_golden import CASES
+    vxa, vxd, steps, mode, cilia = CASES[name]
+    g = O.read_vxbin(os.path.join(GOLD, name + ".vxbin"))
+    model = gv.Model.from_vxa(vxa, vxd)
+    model.set_world_param("enable_collision", 0)
+    if mode == "vx2":
+        model.set_world_param("vx2_compat", 1)
+        model.set_world_param("vary_temp", 0)
+    ctx = gpu_run([model], steps, gv.FP64, path)
+    got = ctx.read_state(0)
+    assert ctx.results()[0].dt == g["state_scalars"][0, 1]
+    assert np.abs(got["pos"] - g["state_pos"]).max() / disp_scale(model, g["state_pos"]) < 1e-5
+    assert np.abs(got["orient"] - g["state_orient"]).max() < 1e-5 * max(np.abs(g["state_orient"][:, 1:]).max(), 1e-30)
+    ctx.close()
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT])
+@pytest.mark.parametrize("maker,steps,precision", [
+    (lambda: (W.contact_pile_vxa(k=2, cube=3), None), 300, gv.FP64),
+    (lambda: (W.xenobot_base_vxa(), W.xenobot_vxd(7)), 500, gv.FP64),
+    (lambda: (W.contact_pile_vxa(k=2, cube=3), None), 60, gv.FP32),
+])
+def test_collision_pair_set_is_bit_exact(maker, steps, precision, path):
+    vxa, vxd = maker()
+    model = gv.Model.from_vxa(vxa, vxd)
+    want = O.OracleWorld(model)
+    want.run(steps)
+    ctx = gpu_run([model], steps, precision, path, record_pairs=1)
+    got, ref = ctx.collision_pairs(0), want.collision_pairs()
+    assert len(ref) > 0
+    assert np.array_equal(got, ref)
+    assert ctx.results()[0].collision_count == want.result().collision_count
+    ctx.close()
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT])
+@pytest.mark.parametrize("precision,tol", [(gv.FP64, 1e-5), (gv.FP32, 1e-3)])
+def test_batch_of_ragged_worlds(path, precision, tol):
+    """Worlds of different sizes, materials and features in one launch; each must equal its own oracle run."""
+    models = [gv.Model.from_vxa(W.small_block_vxa()), gv.Model.from_vxa(W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(9)),
+              gv.Model.from_vxa(W.cube_vxa(5)), gv.Model.from_vxa(W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(10)),
+              kats.temperature(5.0, 2.55e-5)[0], gv.Model.from_vxa(W.cube_vxa(1))]
+    steps = 400
+    ctx = gpu_run(models, steps, precision, path)
+    for i, m in enumerate(models):
+        want = O.OracleWorld(m)
+        want.run(steps)
+        got, ref = ctx.read_state(i), want.state()
+        scale = max(disp_scale(m, ref["pos"]), 1e-9)
+        assert np.abs(got["pos"] - ref["pos"]).max() / scale < (tol if m.num_voxels > 1 else 1.0), i
+        r, rr = ctx.results()[i], want.result()
+        assert r.steps == rr.steps == steps and abs(r.current_time - rr.current_time) < 1e-12
+        assert np.abs(np.array(r.current_com) - np.array(rr.current_com)).max() < 1e-4 * max(scale, 1e-6) + 1e-12
+    assert ctx.total_voxel_steps() == steps * sum(m.num_voxels for m in models)
+    ctx.close()
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT])
+def test_stop_condition_fitness_and_results(path):
+    models = [gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=0.2), W.xenobot_vxd(i)) for i in (12, 13, 14)]
+    ctx = gpu_run(models, 1000000, gv.FP64, path, use_stop=True)
+    for i, m in enumerate(models):
+        want = O.OracleWorld(m)
+        want.run(1000000, use_stop_formula=True)
+        r, rr = ctx.results()[i], want.result()
+        assert r.stopped == 1 and r.steps == rr.steps and r.current_time == rr.current_time
+        assert r.num_voxel == rr.num_voxel and r.num_measured_voxel == rr.num_measured_voxel
+        assert abs(r.fitness_score - rr.fitness_score) < 1e-6 * abs(rr.fitness_score)
+        assert abs(r.total_distance_of_all_voxels - rr.total_distance_of_all_voxels) < 1e-5 * rr.total_distance_of_all_voxels
+        assert np.allclose(r.initial_com, rr.initial_com, rtol=0, atol=1e-15)
+        assert abs(r.recent_angle - rr.recent_angle) < 1e-5
+    ctx.close()
+
+
+def test_fitness_within_one_percent_on_contact_heavy_run():
+    model = gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=1.0), W.xenobot_vxd(15))
+    want = O.OracleWorld(model)
+    want.run(1000000, use_stop_formula=True)
+    for path in (STREAM, RESIDENT):
+        ctx = gpu_run([model], 1000000, gv.FP32, path, use_stop=True)
+        r, rr = ctx.results()[0], want.result()
+        assert r.steps == rr.steps
+        assert abs(r.fitness_score - rr.fitness_score) < 0.01 * abs(rr.fitness_score)
+        ctx.close()
+
+
+def test_million_voxel_body_properties():
+    """BASELINE config 3 at full size (100^3): too big for the oracle, so check what the physics guarantees —
+    x<->y mirror symmetry of a cube dropped flat, centre of mass stays on the axis, run-to-run determinism."""
+    n, steps = 100, 30
+    model = gv.Model.from_vxa(W.cube_vxa(n))
+    states = []
+    for _ in range(2):
+        ctx = gpu_run([model], steps, gv.FP32, STREAM)
+        states.append(ctx.read_state(0))
+        r = ctx.results()[0]
+        ctx.close()
+    assert np.array_equal(states[0]["pos"], states[1]["pos"])  # deterministic
+    pos = states[0]["pos"].reshape(n, n, n, 3)  # [z][y][x]
+    assert np.isfinite(pos).all()
+    mirrored = pos.transpose(0, 2, 1, 3)[..., [1, 0, 2]]  # swap x<->y indices and components
+    assert np.abs(pos - mirrored).max() < 1e-9
+    c = (n - 1) * 0.01 / 2
+    assert abs(r.current_com[0] - c) < 1e-9 and abs(r.current_com[1] - c) < 1e-9
+    assert r.current_com[2] < r.initial_com[2]  # it fell
+    assert r.steps == steps and r.diverged == 0
+
+
+def test_job_run_writes_the_reference_report_layout():
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "base.vxa"), "w").write(W.xenobot_base_vxa(stop_seconds=0.1).replace("<Simulator>", "<Simulator><SavePositionOfAllVoxels>1</SavePositionOfAllVoxels>", 1))
+        for i in (30, 31, 32):
+            open(os.path.join(td, f"bot_{i:04d}.vxd"), "w").write(W.xenobot_vxd(i))
+        out = os.path.join(td, "report.xml")
+        rc = gv.lib().vx3b_job_run(td.encode(), out.encode(), 1, gv.FP64)
+        assert rc == 0, gv.lib().vx3b_last_error()
+        root = ET.parse(out).getroot()
+        assert root.tag == "report" and root.find("inputdir").text == os.path.basename(td)
+        detail = list(root.find("detail"))
+        assert sorted(d.tag for d in detail) == ["bot_0030", "bot_0031", "bot_0032"]
+        fits = [float(d.find("fitness_score").text) for d in detail]
+        assert fits == sorted(fits, reverse=True)
+        assert root.find("bestfit/filename").text == detail[0].tag + ".vxd"
+        for d in detail:
+            i = int(d.tag[-4:])
+            m = gv.Model.from_vxa(open(os.path.join(td, "base.vxa")).read(), W.xenobot_vxd(i))
+            want = O.OracleWorld(m)
+            want.run(1000000, use_stop_formula=True)
+            rr = want.result()
+            assert abs(float(d.find("fitness_score").text) - rr.fitness_score) < 1e-6 * abs(rr.fitness_score)
+            assert float(d.find("currentTime").text) == rr.current_time
+            assert int(d.find("num_voxel").text) == m.num_voxels
+            assert len(d.find("pos").text.strip(";").split(";")) == m.num_voxels
+            assert abs(float(d.find("currentCenterOfMass/x").text) - rr.current_com[0]) < 1e-9
