@@ -49,16 +49,21 @@ VXD float u2f(uint32_t u) { return __uint_as_float(u); }
 // ---- per-world device record ---------------------------------------------------------------------
 enum {
     WF_FLOOR = 1, WF_VARY_TEMP = 2, WF_COLLISION = 4, WF_CILIA = 8, WF_EXPANSION = 16, WF_VX3 = 32, WF_FORCE_FIELD = 64,
-    WF_STOP_FORMULA = 128
+    WF_STOP_FORMULA = 128, WF_RESIDENT = 256, // WF_RESIDENT: stepped by k_resident in this run; the streaming kernels skip it
+    WF_THERMAL = 512,  // temperature varies AND some material has alphaCTE != 0 (otherwise temperature is unobservable)
+    WF_CAN_FAIL = 1024 // some link material has a failure strain
 };
 struct WorldD {
     // static
     int32_t voff, nv, loff, nl, soff, ns, vmatOff, lmatOff;
+    int32_t nvm, nlm; // materials of this world
+    int32_t residentClass, padc; // CTAs per SM of the world's k_resident size class; 0 = does not fit in shared memory
     uint32_t flags;
     int32_t cycle; // int(TempPeriod/dt): COM/angle sampling period in steps (0 = never)
     float dt;
     float pad0;
     double tempAmp, tempPeriod, voxSize, maxDistPair;
+    double invCell; // 1 / edge of the contact broad-phase cell (edge >= the largest watch distance of this world)
     // dynamic
     double t;
     int64_t step;     // CurStepCount

@@ -110,8 +110,11 @@ template <class R> class Engine : public EngineBase {
     cudaGraphExec_t graphExec = nullptr;
     int graphChunk = 0, graphUseStop = -1, graphRecord = -1;
     bool anyCollision = false;
-    int maxNv = 0, maxNl = 0, maxNs = 0;
-    ResidentCfg rcfg;
+    std::vector<ResidentClass> classes; // k_resident size classes (kernels_resident.cuh)
+    int numResident = 0;                // worlds that fit in shared memory (laid out first; streaming-only worlds follow)
+    int vStream0 = 0, lStream0 = 0, tileStream0 = 0; // first voxel / link / contact tile of the streaming-only worlds
+    int graphMixed = -1;
+    cudaEvent_t evBegin = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     ~Engine() override {
@@ -123,9 +126,22 @@ template <class R> class Engine : public EngineBase {
             cudaEventDestroy(ev0);
         if (ev1)
             cudaEventDestroy(ev1);
+        if (evBegin)
+            cudaEventDestroy(evBegin);
+        release_classes();
         bufs.clear();
         if (ownStream && stream)
             cudaStreamDestroy(stream);
+    }
+
+    void release_classes() {
+        for (auto &c : classes) {
+            if (c.stream)
+                cudaStreamDestroy(c.stream);
+            if (c.done)
+                cudaEventDestroy(c.done);
+        }
+        classes.clear();
     }
 
     template <class T> int dalloc(T **out, size_t count, const T *src = nullptr) {
@@ -149,6 +165,7 @@ template <class R> class Engine : public EngineBase {
         bufs.clear();
         H.clear();
         hTiles.clear();
+        release_classes();
         memset(&A, 0, sizeof(A));
         if (n <= 0 || !worlds) {
             set_error("vx3b_batch_upload: no worlds");
@@ -172,6 +189,73 @@ template <class R> class Engine : public EngineBase {
             set_error("vx3b_batch_upload: batch too large for 32-bit indices");
             return VX3B_ERR_ARG;
         }
+        // ---- per-world summary: surface count, feature flags, shared-memory need -> k_resident size class ------------------
+        struct Pre {
+            int ns = 0, cls = 0;
+            uint32_t flags = 0;
+            size_t bytes = 0;
+            double invCell = 0;
+        };
+        std::vector<Pre> pre(n);
+        int dev = 0, smemPerSm = 0, smemOptin = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&smemPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        {
+            std::vector<uint8_t> deg;
+            for (int w = 0; w < n; w++) {
+                const VX3B_WorldDesc &d = worlds[w];
+                Pre &p = pre[w];
+                deg.assign(d.num_voxels, 0);
+                for (int l = 0; l < d.num_links; l++) {
+                    int a = d.link_neg[l], b = d.link_pos[l];
+                    if (a < 0 || a >= d.num_voxels || b < 0 || b >= d.num_voxels || d.link_axis[l] > 2) {
+                        set_error("vx3b_batch_upload: link " + std::to_string(l) + " of world " + std::to_string(w) + " is malformed");
+                        return VX3B_ERR_ARG;
+                    }
+                    deg[a]++;
+                    deg[b]++;
+                }
+                for (int v = 0; v < d.num_voxels; v++)
+                    p.ns += deg[v] < 6;
+                const bool vx3 = !d.vx2_compat;
+                const bool hasFF = !formula_empty(d.force_field[0]) || !formula_empty(d.force_field[1]) || !formula_empty(d.force_field[2]);
+                double maxAlpha = 0, maxSize = d.vox_size;
+                bool canFail = false;
+                for (int k = 0; k < d.num_voxel_mats; k++) {
+                    maxAlpha = std::max(maxAlpha, (double)fabsf(d.voxel_mats[k].alphaCTE));
+                    maxSize = std::max(maxSize, d.voxel_mats[k].nomSize);
+                }
+                for (int k = 0; k < d.num_link_mats; k++)
+                    canFail = canFail || d.link_mats[k].epsilonFail != -1.0f;
+                const bool vary = d.vary_temp_enabled && d.temp_period > 0;
+                p.flags = (d.floor_enabled ? WF_FLOOR : 0) | (vary ? WF_VARY_TEMP : 0) | (d.enable_collision ? WF_COLLISION : 0) |
+                          (d.enable_cilia ? WF_CILIA : 0) | (d.enable_expansion ? WF_EXPANSION : 0) | (vx3 ? WF_VX3 : 0) |
+                          (hasFF ? WF_FORCE_FIELD : 0) | (!formula_empty(d.stop_condition) ? WF_STOP_FORMULA : 0) |
+                          ((vary && maxAlpha != 0) ? WF_THERMAL : 0) | (canFail ? WF_CAN_FAIL : 0);
+                // contact broad-phase cell: >= the largest watch distance 0.625*(size1+size2), sizes at their largest temperature
+                double cell = 1.25 * maxSize * (1.0 + (fabs(d.temp_amplitude) + fabs((double)d.initial_temp)) * maxAlpha) * (1.0 + 1e-6);
+                p.invCell = cell > 0 ? 1.0 / cell : 0.0;
+                p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags);
+                p.cls = p.bytes == (size_t)-1 ? 0 : resident_class_of(p.bytes, (size_t)smemPerSm, (size_t)smemOptin);
+            }
+        }
+        // internal layout order: resident-capable worlds first (largest class = smallest worlds first does not matter; inside a
+        // class the most expensive worlds are launched first), streaming-only worlds last so the streaming kernels cover a suffix
+        std::vector<int> perm(n);
+        for (int w = 0; w < n; w++)
+            perm[w] = w;
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+            const bool ra = pre[a].cls > 0, rb = pre[b].cls > 0;
+            if (ra != rb)
+                return ra;
+            if (pre[a].cls != pre[b].cls)
+                return pre[a].cls < pre[b].cls;
+            return worlds[a].num_links + worlds[a].num_voxels > worlds[b].num_links + worlds[b].num_voxels;
+        });
+        numResident = 0;
+        vStream0 = lStream0 = tileStream0 = -1;
+        H.resize(n);
         // ---- host staging
         std::vector<WorldD> hW(n);
         std::vector<D2> pxy(nvTot), pzt(nvTot), ipxy(nvTot);
@@ -190,13 +274,20 @@ template <class R> class Engine : public EngineBase {
         std::vector<DLinkMat> lmats(nlm);
         bool anyPhase = false, anyCilia = false;
         anyCollision = false;
-        maxNv = maxNl = maxNs = 0;
         size_t voff = 0, loff = 0, vmo = 0, lmo = 0;
         memset(lzero.data(), 0, lzero.size() * sizeof(T4));
-        for (int w = 0; w < n; w++) {
+        for (int oi = 0; oi < n; oi++) {
+            const int w = perm[oi];
             const VX3B_WorldDesc &d = worlds[w];
             WorldD &W = hW[w];
             memset(&W, 0, sizeof(W));
+            if (pre[w].cls > 0)
+                numResident++;
+            else if (vStream0 < 0) {
+                vStream0 = (int)voff;
+                lStream0 = (int)loff;
+                tileStream0 = (int)hTiles.size();
+            }
             WorldHost h;
             h.nv = d.num_voxels;
             h.nl = d.num_links;
@@ -225,10 +316,11 @@ template <class R> class Engine : public EngineBase {
             W.voxSize = d.vox_size;
             W.maxDistPair = d.max_dist_in_voxel_lengths_to_count_as_pair;
             W.cycle = (h.dt > 0 && vx3) ? (int)(d.temp_period / h.dt) : 0;
-            const bool hasFF = !formula_empty(d.force_field[0]) || !formula_empty(d.force_field[1]) || !formula_empty(d.force_field[2]);
-            W.flags = (d.floor_enabled ? WF_FLOOR : 0) | ((d.vary_temp_enabled && d.temp_period > 0) ? WF_VARY_TEMP : 0) |
-                      (d.enable_collision ? WF_COLLISION : 0) | (d.enable_cilia ? WF_CILIA : 0) | (d.enable_expansion ? WF_EXPANSION : 0) |
-                      (vx3 ? WF_VX3 : 0) | (hasFF ? WF_FORCE_FIELD : 0) | (!formula_empty(d.stop_condition) ? WF_STOP_FORMULA : 0);
+            W.flags = pre[w].flags;
+            W.nvm = d.num_voxel_mats;
+            W.nlm = d.num_link_mats;
+            W.invCell = pre[w].invCell;
+            W.residentClass = pre[w].cls;
             memcpy(W.stop, d.stop_condition, sizeof(W.stop));
             memcpy(W.fitnessF, d.fitness, sizeof(W.fitnessF));
             memcpy(W.ff, d.force_field, sizeof(W.ff));
@@ -358,10 +450,6 @@ template <class R> class Engine : public EngineBase {
             for (int l = 0; l < d.num_links; l++) {
                 size_t g = loff + l;
                 int a = d.link_neg[l], b = d.link_pos[l], ax = d.link_axis[l];
-                if (a < 0 || a >= d.num_voxels || b < 0 || b >= d.num_voxels || ax > 2) {
-                    set_error("vx3b_batch_upload: link " + std::to_string(l) + " of world " + std::to_string(w) + " is malformed");
-                    return VX3B_ERR_ARG;
-                }
                 lends[g] = make_int2((int)voff + a, (int)voff + b);
                 lmeta[g] = (uint32_t)ax | ((uint32_t)(lmo + d.link_mat[l]) << 2);
                 lworld[g] = w;
@@ -398,10 +486,7 @@ template <class R> class Engine : public EngineBase {
             if (d.enable_collision)
                 for (int f = 0; f < h.ns; f += 128)
                     hTiles.push_back(ContactTile{w, f});
-            maxNv = std::max(maxNv, h.nv);
-            maxNl = std::max(maxNl, h.nl);
-            maxNs = std::max(maxNs, h.ns);
-            H.push_back(h);
+            H[w] = h;
             voff += d.num_voxels;
             loff += d.num_links;
             vmo += d.num_voxel_mats;
@@ -478,27 +563,54 @@ template <class R> class Engine : public EngineBase {
             k_world_finish<R><<<(n + 127) / 128, 128, 0, stream>>>(A, 0);
         }
         CUDA_TRY(cudaGetLastError());
+        // ---- k_resident size classes: one launch + stream per class
+        if (vStream0 < 0) {
+            vStream0 = (int)nvTot;
+            lStream0 = (int)nlTot;
+            tileStream0 = (int)hTiles.size();
+        }
+        static const int ks[] = {6, 4, 3, 2, 1};
+        for (int k : ks) {
+            ResidentClass c;
+            c.ctasPerSm = k;
+            for (int oi = 0; oi < n; oi++)
+                if (pre[perm[oi]].cls == k) {
+                    c.worlds.push_back(perm[oi]);
+                    c.smem = std::max(c.smem, pre[perm[oi]].bytes);
+                }
+            if (c.worlds.empty())
+                continue;
+            // registers cap the SM at 512 threads of this kernel (__launch_bounds__(512, 1) -> 128 registers/thread)
+            c.threads = residentThreads > 0 ? std::max(32, std::min(512, (residentThreads + 31) / 32 * 32)) : std::max(64, (512 / k) / 32 * 32);
+            if ((rc = dalloc(&c.dList, c.worlds.size(), c.worlds.data())) != VX3B_OK)
+                return rc;
+            CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+            classes.push_back(std::move(c));
+        }
+        if (!evBegin)
+            CUDA_TRY(cudaEventCreateWithFlags(&evBegin, cudaEventDisableTiming));
         CUDA_TRY(cudaStreamSynchronize(stream)); // host staging vectors die here
-        rcfg = resident_configure<R>(maxNv, maxNl, maxNs, residentThreads);
         return VX3B_OK;
     }
 
     // ---- streaming path: CUDA graph of `chunk` steps -----------------------------------------------------
-    int launches_per_step() const { return 3 + (anyCollision ? 1 : 0) + ((anyCollision && recordPairs) ? 1 : 0); }
-    void enqueue_step(int useStop) {
-        const unsigned lb = (A.nlTot + 255) / 256, vb = (A.nvTot + 255) / 256, wb = (A.nWorlds + 127) / 128;
-        if (A.nlTot)
-            k_links<R><<<lb, 256, 0, stream>>>(A);
-        if (anyCollision && !hTiles.empty()) {
-            if (recordPairs)
-                k_zero_int<<<1, 1, 0, stream>>>(A.pairCount);
-            k_contact<R><<<(unsigned)hTiles.size(), 128, 0, stream>>>(A, dTiles, recordPairs);
+    int launches_per_step() const { return 3 + (anyCollision ? 1 : 0); }
+    // mixed: only the streaming-only worlds (a suffix of every array) are stepped here; the others run in k_resident
+    void enqueue_step(int useStop, bool mixed) {
+        const int l0 = mixed ? lStream0 : 0, v0 = mixed ? vStream0 : 0, t0 = mixed ? tileStream0 : 0;
+        const unsigned lb = (A.nlTot - l0 + 255) / 256, vb = (A.nvTot - v0 + 255) / 256, wb = (A.nWorlds + 127) / 128;
+        if (A.nlTot > l0)
+            k_links<R><<<lb, 256, 0, stream>>>(A, l0);
+        if (anyCollision && (int)hTiles.size() > t0) {
+            k_contact<R><<<(unsigned)hTiles.size() - t0, 128, 0, stream>>>(A, dTiles + t0, recordPairs);
         }
-        k_voxels<R><<<vb, 256, 0, stream>>>(A);
+        if (A.nvTot > v0)
+            k_voxels<R><<<vb, 256, 0, stream>>>(A, v0);
         k_world_step<R><<<wb, 128, 0, stream>>>(A, useStop, dActive);
     }
-    int build_graph(int steps, int useStop) {
-        if (graphExec && graphChunk == steps && graphUseStop == useStop && graphRecord == recordPairs)
+    int build_graph(int steps, int useStop, bool mixed) {
+        if (graphExec && graphChunk == steps && graphUseStop == useStop && graphRecord == recordPairs && graphMixed == (int)mixed)
             return VX3B_OK;
         if (graphExec) {
             cudaGraphExecDestroy(graphExec);
@@ -509,7 +621,7 @@ template <class R> class Engine : public EngineBase {
         for (int s = 0; s < steps; s++) {
             if (s == steps - 1)
                 k_zero_int<<<1, 1, 0, stream>>>(dActive);
-            enqueue_step(useStop);
+            enqueue_step(useStop, mixed);
         }
         CUDA_TRY(cudaStreamEndCapture(stream, &g));
         CUDA_TRY(cudaGraphInstantiate(&graphExec, g, 0));
@@ -517,14 +629,15 @@ template <class R> class Engine : public EngineBase {
         graphChunk = steps;
         graphUseStop = useStop;
         graphRecord = recordPairs;
+        graphMixed = (int)mixed;
         return VX3B_OK;
     }
 
-    int run_streaming(int64_t maxSteps, int useStop) {
+    int run_streaming(int64_t maxSteps, int useStop, bool mixed) {
         int64_t done = 0;
         while (done < maxSteps) {
             int steps = (int)std::min<int64_t>(chunk, maxSteps - done);
-            int rc = build_graph(steps, useStop);
+            int rc = build_graph(steps, useStop, mixed);
             if (rc != VX3B_OK)
                 return rc;
             CUDA_TRY(cudaGraphLaunch(graphExec, stream));
@@ -538,11 +651,22 @@ template <class R> class Engine : public EngineBase {
         return VX3B_OK;
     }
 
+    // every size class on its own stream, all of them ordered after k_world_begin and before the final reductions
     int run_resident(int64_t maxSteps, int useStop) {
-        int rc = resident_launch<R>(A, rcfg, maxSteps, useStop, recordPairs, stream);
-        if (rc != VX3B_OK)
-            return rc;
-        lastLaunches += 1;
+        CUDA_TRY(cudaEventRecord(evBegin, stream));
+        for (auto &c : classes) {
+            CUDA_TRY(cudaStreamWaitEvent(c.stream, evBegin, 0));
+            int rc = resident_launch<R>(A, c, maxSteps, useStop, recordPairs);
+            if (rc != VX3B_OK)
+                return rc;
+            CUDA_TRY(cudaEventRecord(c.done, c.stream));
+            lastLaunches += 1;
+        }
+        return VX3B_OK;
+    }
+    int join_resident() {
+        for (auto &c : classes)
+            CUDA_TRY(cudaStreamWaitEvent(stream, c.done, 0));
         return VX3B_OK;
     }
 
@@ -559,17 +683,23 @@ template <class R> class Engine : public EngineBase {
             return rc;
         const unsigned wb = (A.nWorlds + 127) / 128;
         CUDA_TRY(cudaEventRecord(ev0, stream));
-        k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)maxSteps, useStop);
-        lastLaunches++;
-        int use = path;
-        if (use == 0)
-            use = rcfg.ok ? 2 : 1;
-        if (use == 2 && !rcfg.ok) {
-            set_error("vx3b_batch_run: resident path requested but the largest world does not fit in shared memory");
+        // path 1: streaming kernels for every world; path 2: k_resident for every world (error if one does not fit);
+        // path 0: k_resident for the worlds that fit, streaming kernels (concurrently, on the main stream) for the rest
+        if (path == 2 && numResident != (int)H.size()) {
+            set_error("vx3b_batch_run: resident path requested but " + std::to_string(H.size() - numResident) + " world(s) do not fit in shared memory");
             return VX3B_ERR_ARG;
         }
-        rc = (use == 2) ? run_resident(maxSteps, useStop) : run_streaming(maxSteps, useStop);
-        if (rc != VX3B_OK)
+        if (recordPairs) // the pair list is that of the last step of a fixed-length run (W.runSteps == 1)
+            CUDA_TRY(cudaMemsetAsync(A.pairCount, 0, sizeof(int), stream));
+        const bool resident = path != 1 && numResident > 0;
+        const bool streaming = path == 1 || numResident != (int)H.size();
+        k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)maxSteps, useStop, resident ? 1 : 0);
+        lastLaunches++;
+        if (resident && (rc = run_resident(maxSteps, useStop)) != VX3B_OK)
+            return rc;
+        if (streaming && (rc = run_streaming(maxSteps, useStop, resident)) != VX3B_OK)
+            return rc;
+        if (resident && (rc = join_resident()) != VX3B_OK)
             return rc;
         if (A.nvTot) {
             k_reduce_com<R><<<(unsigned)((A.nvTot + 255) / 256), 256, 0, stream>>>(A, 1);

@@ -5,48 +5,56 @@
 // Replaces, for worlds that fit, the reference's one-thread-per-world CUDA_Simulation driver with its
 // 3-6 child launches + device-wide syncs per step (VX3/VX3_SimulationManager.cu:11-121,
 // VX3/VX3_VoxelyzeKernel.cu:237-359).
+//
+// Contact (reference: all Ns^2/2 surface pairs every step, VX3_VoxelyzeKernel.cu:833-843) is a uniform-grid
+// broad phase kept in shared memory: surface voxels are counting-sorted by hashed cell every step, then each
+// surface voxel scans the 27 cells around its own.  The cell edge is >= the largest watch distance of the world,
+// so the watched-pair SET is exactly the reference's; candidates are visited in (cell, index) order, which makes
+// the force sums deterministic.
 #pragma once
 #include "engine.cuh"
 #include "kernels_stream.cuh"
 
 namespace vx3b {
 
-template <class R> struct R3 {
-    R x, y, z;
-};
-
 // shared-memory layout for capacities (capV, capL, capS); every array is 16-byte aligned
 template <class R> struct ResidentLayout {
+    size_t world, vmats, lmats;
     size_t pos, orient, linMom, angMom, temp, vflags, vmat, vlinks, lat, phase, cilia, vext, vsurfslot;
     size_t lpos2, la1, la2, lflags, lmaxs, lends, lmeta, lfN, lfP, lmN, lmP;
-    size_t surf, contactF;
+    size_t surf, contactF, skey, sorted, cnt;
     size_t total;
+    int H; // hash buckets (power of two)
     __host__ __device__ static size_t up(size_t x) { return (x + 15) & ~(size_t)15; }
-    __host__ __device__ ResidentLayout(int capV, int capL, int capS) {
+    __host__ __device__ ResidentLayout(int capV, int capL, int capS, int capVM, int capLM, uint32_t wflags) {
+        const bool collide = (wflags & WF_COLLISION) && capS > 1;
         size_t o = 0;
         auto take = [&](size_t bytes) {
             size_t at = o;
             o = up(o + bytes);
             return at;
         };
+        world = take(sizeof(WorldD));
+        vmats = take(sizeof(DVoxMat) * capVM);
+        lmats = take(sizeof(DLinkMat) * capLM);
         pos = take(sizeof(double) * 3 * capV);
         orient = take(sizeof(R) * 4 * capV);
         linMom = take(sizeof(R) * 3 * capV);
         angMom = take(sizeof(R) * 3 * capV);
         temp = take(sizeof(float) * capV);
         vflags = take(capV);
-        vmat = take(sizeof(uint16_t) * capV);
+        vmat = take(capV);
         vlinks = take(sizeof(uint16_t) * 6 * capV);
         lat = take(sizeof(short4) * capV);
-        phase = take(sizeof(double) * capV);
-        cilia = take(sizeof(float) * 3 * capV);
+        phase = take((wflags & WF_THERMAL) ? sizeof(double) * capV : 0);
+        cilia = take((wflags & WF_CILIA) ? sizeof(float) * 3 * capV : 0);
         vext = take(sizeof(int32_t) * capV);
         vsurfslot = take(sizeof(uint16_t) * capV);
         lpos2 = take(sizeof(R) * 3 * capL);
         la1 = take(sizeof(R) * 3 * capL);
         la2 = take(sizeof(R) * 3 * capL);
         lflags = take(capL);
-        lmaxs = take(sizeof(float) * capL);
+        lmaxs = take((wflags & WF_CAN_FAIL) ? sizeof(float) * capL : 0);
         lends = take(sizeof(uint16_t) * 2 * capL);
         lmeta = take(sizeof(uint16_t) * capL);
         lfN = take(sizeof(R) * 3 * capL);
@@ -54,32 +62,49 @@ template <class R> struct ResidentLayout {
         lmN = take(sizeof(R) * 3 * capL);
         lmP = take(sizeof(R) * 3 * capL);
         surf = take(sizeof(uint16_t) * capS);
-        contactF = take(sizeof(R) * 3 * capS);
+        H = 64;
+        while (H < 2 * capS && H < 8192)
+            H *= 2;
+        if (collide) {
+            contactF = take(sizeof(R) * 3 * capS);
+            skey = take(sizeof(uint32_t) * capS);
+            sorted = take(sizeof(uint16_t) * capS);
+            cnt = take(sizeof(int32_t) * H);
+        } else
+            contactF = skey = sorted = cnt = o;
         total = o;
     }
 };
 
 struct ResidentShared { // block-wide scalars
-    int32_t diverged, hits, comFlag, pad;
+    int32_t diverged, hits, running, pad;
+    int32_t warpSums[32];
     double com[4];
 };
 
+VXD uint32_t cell_hash(uint32_t key, int log2H) { return (key * 2654435761u) >> (32 - log2H); }
+
+// worldList: the worlds of one size class (every CTA lays its shared memory out for its own world's counts; the class only
+// fixes the dynamic shared-memory size, i.e. how many CTAs share an SM).
 template <class R>
-__global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long maxSteps, int useStop, int recordPairs) {
+__global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t *worldList, long long maxSteps, int useStop, int recordPairs) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ ResidentShared sh;
-    const int w = blockIdx.x;
-    WorldD &W = A.worlds[w];
-    if (!W.active)
+    const int w = worldList[blockIdx.x];
+    WorldD &Wg = A.worlds[w];
+    if (!Wg.active)
         return;
-    const ResidentLayout<R> L(capV, capL, capS);
+    const ResidentLayout<R> L(Wg.nv, max(Wg.nl, 1), max(Wg.ns, 1), max(Wg.nvm, 1), max(Wg.nlm, 1), Wg.flags);
+    WorldD &W = *(WorldD *)(smem + L.world);
+    DVoxMat *vmats = (DVoxMat *)(smem + L.vmats);
+    DLinkMat *lmats = (DLinkMat *)(smem + L.lmats);
     double *sPos = (double *)(smem + L.pos);
     R *sOri = (R *)(smem + L.orient);
     R *sLin = (R *)(smem + L.linMom);
     R *sAng = (R *)(smem + L.angMom);
     float *sTemp = (float *)(smem + L.temp);
     uint8_t *sVflags = smem + L.vflags;
-    uint16_t *sVmat = (uint16_t *)(smem + L.vmat);
+    uint8_t *sVmat = smem + L.vmat;
     uint16_t *sVlinks = (uint16_t *)(smem + L.vlinks);
     short4 *sLat = (short4 *)(smem + L.lat);
     double *sPhase = (double *)(smem + L.phase);
@@ -99,19 +124,32 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
     R *sMP = (R *)(smem + L.lmP);
     uint16_t *sSurf = (uint16_t *)(smem + L.surf);
     R *sCF = (R *)(smem + L.contactF);
+    uint32_t *sKey = (uint32_t *)(smem + L.skey);
+    uint16_t *sSorted = (uint16_t *)(smem + L.sorted);
+    int32_t *sCnt = (int32_t *)(smem + L.cnt);
 
     const int tid = threadIdx.x, nt = blockDim.x;
+    // ---- load the world into shared memory --------------------------------------------------------------
+    {
+        const uint32_t *src = (const uint32_t *)&Wg;
+        uint32_t *dst = (uint32_t *)&W;
+        for (int i = tid; i < (int)(sizeof(WorldD) / 4); i += nt)
+            dst[i] = src[i];
+    }
+    __syncthreads();
     const int nv = W.nv, nl = W.nl, ns = W.ns, voff = W.voff, loff = W.loff, soff = W.soff;
     const uint32_t wflags = W.flags;
     const bool vx3 = wflags & WF_VX3, floorOn = wflags & WF_FLOOR, collide = (wflags & WF_COLLISION) && ns > 1;
-    const bool ciliaOn = (wflags & WF_CILIA) && A.baseCilia, varyTemp = (wflags & WF_VARY_TEMP) && W.tempPeriod > 0;
+    const bool ciliaOn = (wflags & WF_CILIA) && A.baseCilia, varyTemp = (wflags & WF_THERMAL) && W.tempPeriod > 0;
+    const bool canFail = wflags & WF_CAN_FAIL;
     const float dt = W.dt;
-    const double voxSize = W.voxSize, tempAmp = W.tempAmp, tempPeriod = W.tempPeriod;
+    const double voxSize = W.voxSize, tempAmp = W.tempAmp, tempPeriod = W.tempPeriod, invCell = W.invCell;
     const int cycle = W.cycle;
-    const DVoxMat *vmats = A.vmats + W.vmatOff;
-    const DLinkMat *lmats = A.lmats + W.lmatOff;
-
-    // ---- load the world into shared memory --------------------------------------------------------------
+    const int H = L.H, log2H = 31 - __clz(H);
+    for (int i = tid; i < W.nvm * (int)(sizeof(DVoxMat) / 4); i += nt)
+        ((uint32_t *)vmats)[i] = ((const uint32_t *)(A.vmats + W.vmatOff))[i];
+    for (int i = tid; i < W.nlm * (int)(sizeof(DLinkMat) / 4); i += nt)
+        ((uint32_t *)lmats)[i] = ((const uint32_t *)(A.lmats + W.lmatOff))[i];
     for (int v = tid; v < nv; v += nt) {
         const int g = voff + v;
         float temp;
@@ -135,14 +173,15 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
         sAng[3 * v + 2] = am.y;
         sTemp[v] = temp;
         sVflags[v] = (uint8_t)fl;
-        sVmat[v] = (uint16_t)(A.vmat[g] - W.vmatOff);
+        sVmat[v] = (uint8_t)(A.vmat[g] - W.vmatOff);
         for (int k = 0; k < 6; k++) {
             int l = A.vlinks[(size_t)k * A.nvTot + g];
             sVlinks[6 * v + k] = l < 0 ? (uint16_t)0xffff : (uint16_t)(l - loff);
         }
         sLat[v] = A.lat[g];
-        sPhase[v] = A.phase ? A.phase[g] : 0.0;
-        if (A.baseCilia) {
+        if (varyTemp)
+            sPhase[v] = A.phase ? A.phase[g] : 0.0;
+        if (ciliaOn) {
             D4 b = A.baseCilia[g];
             sCilia[3 * v] = (float)b.x;
             sCilia[3 * v + 1] = (float)b.y;
@@ -170,7 +209,8 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
         else
             fl = (uint32_t)__double_as_longlong(s0.w);
         sLflags[l] = (uint8_t)fl;
-        sLmax[l] = (float)s1.w;
+        if (canFail)
+            sLmax[l] = (float)s1.w;
         int2 e = A.lends[g];
         sLends[2 * l] = (uint16_t)(e.x - voff);
         sLends[2 * l + 1] = (uint16_t)(e.y - voff);
@@ -179,13 +219,18 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
         for (int k = 0; k < 3; k++)
             sFN[3 * l + k] = sFP[3 * l + k] = sMN[3 * l + k] = sMP[3 * l + k] = R(0);
     }
-    for (int s = tid; s < ns; s += nt) {
+    for (int s = tid; s < ns; s += nt)
         sSurf[s] = (uint16_t)(A.surf[soff + s] - voff);
-        sCF[3 * s] = sCF[3 * s + 1] = sCF[3 * s + 2] = R(0);
+    if (collide) {
+        for (int s = tid; s < ns; s += nt)
+            sCF[3 * s] = sCF[3 * s + 1] = sCF[3 * s + 2] = R(0);
+        for (int h = tid; h < H; h += nt)
+            sCnt[h] = 0;
     }
     if (tid == 0) {
         sh.diverged = 0;
         sh.hits = 0;
+        sh.running = 1;
         sh.com[0] = sh.com[1] = sh.com[2] = sh.com[3] = 0;
     }
     __syncthreads();
@@ -198,7 +243,7 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
     bool running = true;
 
     while (running) {
-        // ---- link pass ----------------------------------------------------------------------------------------
+        // ---- phase A: link pass + cell keys / bucket counts of the surface voxels (positions of the step start) ------
         for (int l = tid; l < nl; l += nt) {
             const int a = sLends[2 * l], b = sLends[2 * l + 1];
             const uint32_t meta = sLmeta[l];
@@ -206,7 +251,7 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
             const DVoxMat &mn = vmats[sVmat[a]], &mp = vmats[sVmat[b]];
             if (vx3 && mn.fixed && mp.fixed)
                 continue;
-            const DLinkMat lmat = lmats[meta >> 2];
+            const DLinkMat &lmat = lmats[meta >> 2];
             V3<double> dpos{sPos[3 * b] - sPos[3 * a], sPos[3 * b + 1] - sPos[3 * a + 1], sPos[3 * b + 2] - sPos[3 * a + 2]};
             Qt<R> qn{sOri[4 * a], sOri[4 * a + 1], sOri[4 * a + 2], sOri[4 * a + 3]};
             Qt<R> qp{sOri[4 * b], sOri[4 * b + 1], sOri[4 * b + 2], sOri[4 * b + 3]};
@@ -216,7 +261,7 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
             h.a1v = {sA1[3 * l], sA1[3 * l + 1], sA1[3 * l + 2]};
             h.a2v = {sA2[3 * l], sA2[3 * l + 1], sA2[3 * l + 2]};
             h.flags = sLflags[l];
-            h.maxStrain = sLmax[l];
+            h.maxStrain = canFail ? sLmax[l] : -1e30f;
             float dmN = mn.sqrtMassZetaInt2 / ((vx3 && mn.fixed) ? 0.0f : dt);
             float dmP = mp.sqrtMassZetaInt2 / ((vx3 && mp.fixed) ? 0.0f : dt);
             LinkForces<R> f;
@@ -231,7 +276,8 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
             sA2[3 * l + 1] = h.a2v.y;
             sA2[3 * l + 2] = h.a2v.z;
             sLflags[l] = (uint8_t)h.flags;
-            sLmax[l] = h.maxStrain;
+            if (canFail)
+                sLmax[l] = h.maxStrain;
             sFN[3 * l] = f.fNeg.x;
             sFN[3 * l + 1] = f.fNeg.y;
             sFN[3 * l + 2] = f.fNeg.z;
@@ -247,8 +293,70 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
             if (f.strain > 100.0f)
                 sh.diverged = 1;
         }
-        // ---- contact: all pairs of surface voxels (positions of the step start) -------------------------------------
         if (collide) {
+            for (int i = tid; i < ns; i += nt) {
+                const int v = sSurf[i];
+                const int cx = (int)floor(sPos[3 * v] * invCell), cy = (int)floor(sPos[3 * v + 1] * invCell), cz = (int)floor(sPos[3 * v + 2] * invCell);
+                const uint32_t key = (uint32_t)(cx & 1023) | ((uint32_t)(cy & 1023) << 10) | ((uint32_t)(cz & 1023) << 20);
+                sKey[i] = key;
+                atomicAdd(&sCnt[cell_hash(key, log2H)], 1);
+            }
+        }
+        __syncthreads();
+        const bool divergedNow = sh.diverged != 0;
+        if (collide) {
+            // ---- phase B: exclusive scan of the bucket counts -------------------------------------------------------------
+            const int per = (H + nt - 1) / nt, b0 = tid * per;
+            int sum = 0;
+            for (int k = 0; k < per; k++)
+                if (b0 + k < H)
+                    sum += sCnt[b0 + k];
+            int inc = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((tid & 31) >= o)
+                    inc += n;
+            }
+            if ((tid & 31) == 31)
+                sh.warpSums[tid >> 5] = inc;
+            __syncthreads();
+            if (tid < 32) {
+                int ws = tid < (nt >> 5) ? sh.warpSums[tid] : 0, wi = ws;
+                for (int o = 1; o < 32; o <<= 1) {
+                    int n = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (tid >= o)
+                        wi += n;
+                }
+                sh.warpSums[tid] = wi - ws; // exclusive
+            }
+            __syncthreads();
+            int offset = sh.warpSums[tid >> 5] + inc - sum;
+            for (int k = 0; k < per; k++)
+                if (b0 + k < H) {
+                    int c = sCnt[b0 + k];
+                    sCnt[b0 + k] = offset;
+                    offset += c;
+                }
+            __syncthreads();
+            // ---- phase C: scatter (after it sCnt[h] = END of bucket h; its start is sCnt[h-1]) --------------------------------
+            for (int i = tid; i < ns; i += nt)
+                sSorted[atomicAdd(&sCnt[cell_hash(sKey[i], log2H)], 1)] = (uint16_t)i;
+            __syncthreads();
+            // ---- phase D: order every bucket by surface index (the atomics above are not ordered) ---------------------------------
+            for (int h = tid; h < H; h += nt) {
+                const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
+                for (int p = beg + 1; p < end; p++) {
+                    uint16_t x = sSorted[p];
+                    int q = p - 1;
+                    while (q >= beg && sSorted[q] > x) {
+                        sSorted[q + 1] = sSorted[q];
+                        q--;
+                    }
+                    sSorted[q + 1] = x;
+                }
+            }
+            __syncthreads();
+            // ---- phase E: narrow phase over the 27 cells around each surface voxel ----------------------------------------------
             const bool rec = recordPairs && left == 1; // parity tests read the pair set of the run's last step
             int hits = 0;
             for (int i = tid; i < ns; i += nt) {
@@ -258,33 +366,42 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
                 const V3<R> l1{sLin[3 * v1], sLin[3 * v1 + 1], sLin[3 * v1 + 2]};
                 const short4 c1 = sLat[v1];
                 const float t1 = sTemp[v1];
+                const uint32_t key = sKey[i];
+                const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
                 V3<R> acc{R(0), R(0), R(0)};
-                for (int j = 0; j < ns; j++) {
-                    if (j == i)
-                        continue;
-                    const int v2 = sSurf[j];
-                    const short4 c2 = sLat[v2];
-                    if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1)
-                        continue;
-                    const DVoxMat &m2 = vmats[sVmat[v2]];
-                    if (m1.fixed && m2.fixed)
-                        continue;
-                    const V3<double> p2{sPos[3 * v2], sPos[3 * v2 + 1], sPos[3 * v2 + 2]};
-                    const V3<R> l2{sLin[3 * v2], sLin[3 * v2 + 1], sLin[3 * v2 + 2]};
-                    V3<R> f;
-                    if (i > j) {
-                        if (contact_pair<R>(m1, t1, p1, l1, m2, sTemp[v2], p2, l2, f)) {
-                            acc = acc + f;
-                            if ((m1.isTarget != 0) != (m2.isTarget != 0))
-                                hits++;
-                            if (rec) {
-                                int slot = atomicAdd(A.pairCount, 1);
-                                if (slot < A.pairCap)
-                                    A.pairBuf[slot] = make_int4(w, v1, v2, 0);
+                for (int n = 0; n < 27; n++) {
+                    const int dx = n % 3 - 1, dy = (n / 3) % 3 - 1, dz = n / 9 - 1;
+                    const uint32_t k2 = (uint32_t)((cx + dx) & 1023) | ((uint32_t)((cy + dy) & 1023) << 10) | ((uint32_t)((cz + dz) & 1023) << 20);
+                    const uint32_t h = cell_hash(k2, log2H);
+                    const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
+                    for (int p = beg; p < end; p++) {
+                        const int j = sSorted[p];
+                        if (j == i || sKey[j] != k2)
+                            continue;
+                        const int v2 = sSurf[j];
+                        const V3<double> p2{sPos[3 * v2], sPos[3 * v2 + 1], sPos[3 * v2 + 2]};
+                        const short4 c2 = sLat[v2];
+                        if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1)
+                            continue; // directly linked (lattice neighbours; static topology): is_neighbor(depth 1)
+                        const DVoxMat &m2 = vmats[sVmat[v2]];
+                        if (m1.fixed && m2.fixed)
+                            continue;
+                        const V3<R> l2{sLin[3 * v2], sLin[3 * v2 + 1], sLin[3 * v2 + 2]};
+                        V3<R> f;
+                        if (i > j) {
+                            if (contact_pair<R>(m1, t1, p1, l1, m2, sTemp[v2], p2, l2, f)) {
+                                acc = acc + f;
+                                if ((m1.isTarget != 0) != (m2.isTarget != 0))
+                                    hits++;
+                                if (rec) {
+                                    int slot = atomicAdd(A.pairCount, 1);
+                                    if (slot < A.pairCap)
+                                        A.pairBuf[slot] = make_int4(w, v1, v2, 0);
+                                }
                             }
-                        }
-                    } else if (contact_pair<R>(m2, sTemp[v2], p2, l2, m1, t1, p1, l1, f))
-                        acc = acc - f;
+                        } else if (contact_pair<R>(m2, sTemp[v2], p2, l2, m1, t1, p1, l1, f))
+                            acc = acc - f;
+                    }
                 }
                 sCF[3 * i] = acc.x;
                 sCF[3 * i + 1] = acc.y;
@@ -292,15 +409,14 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
             }
             if (hits)
                 atomicAdd(&sh.hits, hits);
+            __syncthreads();
+            collisionCount += sh.hits;
         }
-        __syncthreads();
-        const bool divergedNow = sh.diverged != 0;
-        collisionCount += sh.hits;
         const bool sampling = vx3 && cycle > 0 && ((step + 1) % cycle == 0);
-        __syncthreads(); // everyone has read sh.hits / sh.diverged
-        if (tid == 0)
-            sh.hits = 0;
-        // ---- voxel pass ---------------------------------------------------------------------------------------
+        // ---- phase F: voxel pass (+ reset of the grid counters and, on ordinary steps, the world bookkeeping) ---------------
+        if (collide)
+            for (int h = tid; h < H; h += nt)
+                sCnt[h] = 0;
         if (!divergedNow) {
             double cx = 0, cy = 0, cz = 0, cm = 0;
             for (int v = tid; v < nv; v += nt) {
@@ -393,25 +509,38 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
                 }
             }
         }
-        __syncthreads();
-        // ---- end-of-step bookkeeping: thread 0 owns the world record, everyone mirrors the scalars ---------------------
-        if (tid == 0) {
+        // ---- end-of-step bookkeeping on the shared-memory copy of the world record.  On ordinary steps the last thread does
+        // it right after its own voxels (nothing it needs depends on the other threads); on COM-sampling steps and on
+        // divergence it waits for the voxel pass.
+        const bool late = sampling || divergedNow;
+        if (!late && tid == nt - 1) {
             W.collisionCount = collisionCount;
-            W.divergedNow = divergedNow;
-            if (sampling && !divergedNow)
-                for (int k = 0; k < 4; k++) {
-                    W.comAcc[k] = sh.com[k];
-                    sh.com[k] = 0;
-                }
-            if (sampling && !divergedNow && W.maxDistPair != 0) { // closeness needs current positions in HBM
-                for (int v = 0; v < nv; v++)
-                    store_pos(A, voff + v, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, sTemp[v], sVflags[v]);
-            }
+            W.divergedNow = 0;
             world_end_of_step(A, W, useStop);
-            sh.comFlag = W.active;
+            sh.running = W.active;
+            sh.hits = 0;
         }
         __syncthreads();
-        running = sh.comFlag != 0;
+        if (late) {
+            if (tid == 0) {
+                W.collisionCount = collisionCount;
+                W.divergedNow = divergedNow;
+                if (sampling && !divergedNow)
+                    for (int k = 0; k < 4; k++) {
+                        W.comAcc[k] = sh.com[k];
+                        sh.com[k] = 0;
+                    }
+                if (sampling && !divergedNow && W.maxDistPair != 0) { // closeness needs current positions in HBM
+                    for (int v = 0; v < nv; v++)
+                        store_pos(A, voff + v, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, sTemp[v], sVflags[v]);
+                }
+                world_end_of_step(A, W, useStop);
+                sh.running = W.active;
+                sh.hits = 0;
+            }
+            __syncthreads();
+        }
+        running = sh.running != 0;
         step++;
         left--;
         if (!divergedNow)
@@ -419,6 +548,15 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
     }
 
     // ---- write the world back ------------------------------------------------------------------------------------
+    __syncthreads();
+    {
+        // dynamic part of the world record (everything from `t` up to the formula programs)
+        const size_t from = offsetof(WorldD, t) / 4, to = offsetof(WorldD, stop) / 4;
+        const uint32_t *src = (const uint32_t *)&W;
+        uint32_t *dst = (uint32_t *)&Wg;
+        for (int i = (int)from + tid; i < (int)to; i += nt)
+            dst[i] = src[i];
+    }
     for (int v = tid; v < nv; v += nt) {
         const int g = voff + v;
         store_pos(A, g, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, sTemp[v], sVflags[v]);
@@ -434,7 +572,7 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
         else
             fl = __longlong_as_double((long long)sLflags[l]);
         A.lpos2[g] = mk4<R>(sP2[3 * l], sP2[3 * l + 1], sP2[3 * l + 2], fl);
-        A.la1[g] = mk4<R>(sA1[3 * l], sA1[3 * l + 1], sA1[3 * l + 2], (R)sLmax[l]);
+        A.la1[g] = mk4<R>(sA1[3 * l], sA1[3 * l + 1], sA1[3 * l + 2], canFail ? (R)sLmax[l] : R(0));
         A.la2[g] = mk4<R>(sA2[3 * l], sA2[3 * l + 1], sA2[3 * l + 2], R(0));
         A.lfN[g] = mk4<R>(sFN[3 * l], sFN[3 * l + 1], sFN[3 * l + 2], R(0));
         A.lfP[g] = mk4<R>(sFP[3 * l], sFP[3 * l + 1], sFP[3 * l + 2], R(0));
@@ -443,39 +581,47 @@ __global__ void k_resident(Arrays<R> A, int capV, int capL, int capS, long long 
     }
 }
 
-struct ResidentCfg {
-    int capV = 0, capL = 0, capS = 0, threads = 256;
-    size_t smem = 0;
-    bool ok = false;
+// ---- host side: size classes ---------------------------------------------------------------------------------------
+// A world needs resident_bytes() of dynamic shared memory.  Worlds are binned by how many of them fit on one SM at the
+// same time (6, 4, 3, 2 or 1 CTAs per SM); each class is one k_resident launch on its own stream so the block scheduler
+// packs small and large worlds onto the same SMs.  Worlds that do not fit even alone are stepped by the streaming kernels.
+struct ResidentClass {
+    int ctasPerSm = 1, threads = 512;
+    size_t smem = 0; // dynamic shared memory of the launch = largest member
+    std::vector<int32_t> worlds;
+    int32_t *dList = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
 };
 
-// Can the largest world of the batch live in one CTA's shared memory?
-template <class R> ResidentCfg resident_configure(int maxNv, int maxNl, int maxNs, int threads) {
-    ResidentCfg c;
-    c.threads = std::max(32, std::min(1024, (threads + 31) / 32 * 32));
-    if (maxNv <= 0 || maxNv >= 0xffff || maxNl >= 0xffff)
-        return c;
-    c.capV = maxNv;
-    c.capL = std::max(maxNl, 1);
-    c.capS = std::max(maxNs, 1);
-    ResidentLayout<R> L(c.capV, c.capL, c.capS);
-    c.smem = L.total;
-    int dev = 0, optin = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess)
-        return c;
-    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (L.total + 1024 > (size_t)optin)
-        return c;
-    c.ok = cudaFuncSetAttribute(k_resident<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) == cudaSuccess;
-    return c;
+template <class R> size_t resident_bytes(int nv, int nl, int ns, int nvm, int nlm, uint32_t wflags) {
+    if (nv <= 0 || nv >= 0xffff || nl >= 0xffff || ns >= 0xffff || nvm > 255 || nlm >= (1 << 14))
+        return (size_t)-1;
+    return ResidentLayout<R>(nv, std::max(nl, 1), std::max(ns, 1), std::max(nvm, 1), std::max(nlm, 1), wflags).total;
+}
+
+// per-SM shared memory budget: 228 KB per SM, 1 KB reserved per resident CTA, plus this kernel's static shared memory
+inline int resident_class_of(size_t bytes, size_t smemPerSm, size_t maxOptin) {
+    static const int ks[] = {6, 4, 3, 2, 1};
+    for (int k : ks) {
+        size_t lim = smemPerSm / k - 1024 - sizeof(ResidentShared) - 64;
+        if (k == 1)
+            lim = std::min(lim, maxOptin - sizeof(ResidentShared) - 64);
+        if (bytes <= lim)
+            return k;
+    }
+    return 0;
 }
 
 template <class R>
-int resident_launch(const Arrays<R> &A, const ResidentCfg &c, int64_t maxSteps, int useStop, int recordPairs, cudaStream_t stream) {
-    if (recordPairs)
-        cudaMemsetAsync(A.pairCount, 0, sizeof(int), stream);
-    k_resident<R><<<A.nWorlds, c.threads, c.smem, stream>>>(A, c.capV, c.capL, c.capS, (long long)maxSteps, useStop, recordPairs);
-    cudaError_t e = cudaGetLastError();
+int resident_launch(const Arrays<R> &A, const ResidentClass &c, int64_t maxSteps, int useStop, int recordPairs) {
+    if (c.worlds.empty())
+        return VX3B_OK;
+    cudaError_t e = cudaFuncSetAttribute(k_resident<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    if (e == cudaSuccess) {
+        k_resident<R><<<(unsigned)c.worlds.size(), c.threads, c.smem, c.stream>>>(A, c.dList, (long long)maxSteps, useStop, recordPairs);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) {
         set_error(std::string("k_resident launch: ") + cudaGetErrorString(e));
         return VX3B_ERR_CUDA;

@@ -53,13 +53,13 @@ VXD void world_accumulate(double *acc4, int world, bool contributes, double x, d
 }
 
 // ---- link pass --------------------------------------------------------------------------------------
-template <class R> __global__ void __launch_bounds__(256) k_links(Arrays<R> A) {
-    int l = blockIdx.x * blockDim.x + threadIdx.x;
+template <class R> __global__ void __launch_bounds__(256) k_links(Arrays<R> A, int first) {
+    int l = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= A.nlTot)
         return;
     const int w = A.lworld[l];
     WorldD &W = A.worlds[w];
-    if (!W.active)
+    if (!W.active || (W.flags & WF_RESIDENT))
         return;
     const uint32_t meta = A.lmeta[l];
     const int axis = meta & 3;
@@ -121,9 +121,10 @@ template <class R> __global__ void __launch_bounds__(128) k_contact(Arrays<R> A,
     __shared__ SurfRec<R> tile[128];
     const ContactTile ct = tiles[blockIdx.x];
     WorldD &W = A.worlds[ct.world];
-    if (!W.active || !(W.flags & WF_COLLISION))
+    if (!W.active || !(W.flags & WF_COLLISION) || (W.flags & WF_RESIDENT))
         return;
     const int ns = W.ns, soff = W.soff;
+    recordPairs = recordPairs && W.runSteps == 1; // parity tests read the pair set of the run's last step
     const int i = ct.first + threadIdx.x; // local surface index
     SurfRec<R> me;
     const bool have = i < ns;
@@ -203,13 +204,13 @@ template <class R> __global__ void __launch_bounds__(128) k_contact(Arrays<R> A,
 }
 
 // ---- voxel pass -------------------------------------------------------------------------------------
-template <class R> __global__ void __launch_bounds__(256) k_voxels(Arrays<R> A) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
+template <class R> __global__ void __launch_bounds__(256) k_voxels(Arrays<R> A, int first) {
+    int v = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= A.nvTot)
         return;
     const int w = A.vworld[v];
     WorldD &W = A.worlds[w];
-    if (!W.active || W.divergedNow)
+    if (!W.active || W.divergedNow || (W.flags & WF_RESIDENT))
         return;
     const DVoxMat &m = A.vmats[A.vmat[v]];
     const bool vx3 = W.flags & WF_VX3;
@@ -332,11 +333,12 @@ template <class R> __global__ void k_world_finish(Arrays<R> A, int mode) {
 }
 
 // Before the first step of a run: arm the run counter and test the stop condition (CUDA_Simulation checks it before every step).
-template <class R> __global__ void k_world_begin(Arrays<R> A, long long maxSteps, int useStop) {
+template <class R> __global__ void k_world_begin(Arrays<R> A, long long maxSteps, int useStop, int residentMode) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= A.nWorlds)
         return;
     WorldD &W = A.worlds[w];
+    W.flags = (residentMode && W.residentClass > 0) ? (W.flags | WF_RESIDENT) : (W.flags & ~(uint32_t)WF_RESIDENT);
     W.runSteps = maxSteps;
     W.active = (!W.diverged && !W.stopped && maxSteps > 0 && W.nv > 0) ? 1 : 0;
     if (W.active && useStop && (W.flags & WF_STOP_FORMULA) && eval_formula(W.stop, world_vars(W, W.com[0], W.com[1], W.com[2])) > 0) {
@@ -412,7 +414,7 @@ template <class R> __global__ void k_world_step(Arrays<R> A, int useStop, int *a
     if (w >= A.nWorlds)
         return;
     WorldD &W = A.worlds[w];
-    if (!W.active)
+    if (!W.active || (W.flags & WF_RESIDENT))
         return;
     world_end_of_step(A, W, useStop);
     if (W.active && activeCount)

@@ -51,7 +51,31 @@ def compare(name, model, steps, precisions=(gv.FP64, gv.FP32), paths=(1, 2)):
                 print(f"{name} fp{prec} path{path}: FAILED {e}", flush=True)
 
 
+def growth(name, model, checkpoints=(1, 2, 3, 5, 10, 20, 50, 100, 200, 400), prec=None, path=1):
+    """Error against the oracle as a function of the step count: separates a bug (wrong from step 1) from amplified rounding."""
+    prec = prec or gv.FP64
+    ow = O.OracleWorld(model)
+    ctx = gv.Context(0, prec)
+    ctx.set_option("path", path)
+    ctx.upload([model])
+    done = 0
+    lat = model.array("lattice") * model.desc.vox_size
+    for c in checkpoints:
+        ow.run(c - done)
+        ctx.run(c - done)
+        done = c
+        got, ref = ctx.read_state(0), ow.state()
+        disp = max(np.abs(ref["pos"] - lat).max(), 1e-30)
+        e = np.abs(got["pos"] - ref["pos"])
+        print(f"growth {name} fp{prec} step {c:4d}: rel pos err xyz {e[:, 0].max() / disp:.2e} {e[:, 1].max() / disp:.2e} {e[:, 2].max() / disp:.2e} (disp {disp:.2e})", flush=True)
+    ctx.close()
+
+
 def main():
+    if "--growth" in sys.argv:
+        growth("cube5", gv.Model.from_vxa(W.cube_vxa(5)))
+        growth("cube5", gv.Model.from_vxa(W.cube_vxa(5)), prec=gv.FP32)
+        return
     compare("small", gv.Model.from_vxa(W.small_block_vxa()), 200)
     compare("small", gv.Model.from_vxa(W.small_block_vxa()), 2000)
     compare("small+col", gv.Model.from_vxa(W.small_block_vxa(enable_collision=True)), 500)

@@ -10,9 +10,13 @@ TX, TY, TZ, RX, RY, RZ = 1, 2, 4, 8, 16, 32
 OFF = {"X_POS": (1, 0, 0), "X_NEG": (-1, 0, 0), "Y_POS": (0, 1, 0), "Y_NEG": (0, -1, 0), "Z_POS": (0, 0, 1), "Z_NEG": (0, 0, -1)}
 
 
-def rotvec(q):
-    """Quat3D::ToRotationVector (VoxCAD/src/VX2/include/Quat3D.h)"""
+def rotvec(q, robust=False):
+    """Quat3D::ToRotationVector (VoxCAD/src/VX2/include/Quat3D.h).  robust=True: the same rotation vector formed from the
+    vector part (2*atan2(|v|, w)), for states that were stored in float, where w rounds to exactly 1 for tiny angles."""
     w, v = q[0], np.array(q[1:])
+    if robust:
+        n = np.linalg.norm(v)
+        return v * (2.0 * np.arctan2(n, w) / n) if n > 0 else np.zeros(3)
     if w >= 1.0 or w <= -1.0:
         return np.zeros(3)
     sl = 1.0 - w * w
@@ -46,7 +50,7 @@ def two_vox(direction, force, moment, free_dof, expected, what, steps=1000):
             data = state["pos"][idx][k] - off[k] * 0.001
         else:
             k = {RX: 0, RY: 1, RZ: 2}[what]
-            data = rotvec(state["orient"][idx])[k]
+            data = rotvec(state["orient"][idx], robust=tol > 1e-5)[k]
         if expected == 0:
             assert abs(data) < 1e-12, data
         else:
