@@ -57,13 +57,15 @@ struct WorldD {
     // static
     int32_t voff, nv, loff, nl, soff, ns, vmatOff, lmatOff;
     int32_t nvm, nlm; // materials of this world
-    int32_t residentClass, padc; // CTAs per SM of the world's k_resident size class; 0 = does not fit in shared memory
+    int32_t residentClass, padc; // CTAs per SM of the world's k_resident size class (+16: spill variant); 0 = does not fit
     uint32_t flags;
     int32_t cycle; // int(TempPeriod/dt): COM/angle sampling period in steps (0 = never)
     float dt;
     float pad0;
     double tempAmp, tempPeriod, voxSize, maxDistPair;
-    double invCell; // 1 / edge of the contact broad-phase cell (edge >= the largest watch distance of this world)
+    // contact broad phase (k_resident): cell edge = largest watch distance of this world + skin
+    double invCell, listR2; // 1/edge; edge^2 (a voxel's candidate list holds everything within the edge)
+    float skinHalf2, padf;  // (skin/2)^2: a surface voxel that moved further since the last rebuild forces a new one
     // dynamic
     double t;
     int64_t step;     // CurStepCount

@@ -29,7 +29,8 @@ class EngineBase {
     int recordPairs = 0;  // keep the collision pair list of the last step (parity tests)
     int chunk = 64;       // steps per CUDA-graph replay on the streaming path
     double dtOverride = 0;
-    int residentThreads = 256;
+    int residentThreads = 0;    // threads per k_resident CTA; 0 = by size class (512 / CTAs per SM)
+    double contactSkin = 0.15;  // skin of the contact candidate lists, in voxel sizes
 };
 
 

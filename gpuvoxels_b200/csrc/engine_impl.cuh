@@ -194,7 +194,9 @@ template <class R> class Engine : public EngineBase {
             int ns = 0, cls = 0;
             uint32_t flags = 0;
             size_t bytes = 0;
-            double invCell = 0;
+            double invCell = 0, listR2 = 0;
+            float skinHalf2 = 0;
+            bool spill = false;
         };
         std::vector<Pre> pre(n);
         int dev = 0, smemPerSm = 0, smemOptin = 0;
@@ -234,10 +236,20 @@ template <class R> class Engine : public EngineBase {
                           (hasFF ? WF_FORCE_FIELD : 0) | (!formula_empty(d.stop_condition) ? WF_STOP_FORMULA : 0) |
                           ((vary && maxAlpha != 0) ? WF_THERMAL : 0) | (canFail ? WF_CAN_FAIL : 0);
                 // contact broad-phase cell: >= the largest watch distance 0.625*(size1+size2), sizes at their largest temperature
-                double cell = 1.25 * maxSize * (1.0 + (fabs(d.temp_amplitude) + fabs((double)d.initial_temp)) * maxAlpha) * (1.0 + 1e-6);
+                const double skin = contactSkin * d.vox_size;
+                double cell = 1.25 * maxSize * (1.0 + (fabs(d.temp_amplitude) + fabs((double)d.initial_temp)) * maxAlpha) * (1.0 + 1e-6) + skin;
                 p.invCell = cell > 0 ? 1.0 / cell : 0.0;
-                p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags);
+                p.listR2 = cell * cell;
+                p.skinHalf2 = (float)(0.25 * skin * skin * (1.0 - 1e-3)); // a little early rather than late (float compare)
+                p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags, false);
                 p.cls = p.bytes == (size_t)-1 ? 0 : resident_class_of(p.bytes, (size_t)smemPerSm, (size_t)smemOptin);
+                if (p.cls == 0 && p.bytes != (size_t)-1) { // too big: keep the per-link force arrays in global memory instead
+                    p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags, true);
+                    p.cls = resident_class_of(p.bytes, (size_t)smemPerSm, (size_t)smemOptin);
+                    p.spill = p.cls > 0;
+                    if (p.spill)
+                        p.cls += 16;
+                }
             }
         }
         // internal layout order: resident-capable worlds first (largest class = smallest worlds first does not matter; inside a
@@ -320,6 +332,8 @@ template <class R> class Engine : public EngineBase {
             W.nvm = d.num_voxel_mats;
             W.nlm = d.num_link_mats;
             W.invCell = pre[w].invCell;
+            W.listR2 = pre[w].listR2;
+            W.skinHalf2 = pre[w].skinHalf2;
             W.residentClass = pre[w].cls;
             memcpy(W.stop, d.stop_condition, sizeof(W.stop));
             memcpy(W.fitnessF, d.fitness, sizeof(W.fitnessF));
@@ -569,12 +583,14 @@ template <class R> class Engine : public EngineBase {
             lStream0 = (int)nlTot;
             tileStream0 = (int)hTiles.size();
         }
-        static const int ks[] = {6, 4, 3, 2, 1};
-        for (int k : ks) {
+        static const int ks[] = {1 + 16, 2 + 16, 3 + 16, 1, 2, 3, 4, 6}; // most expensive worlds are launched first
+        for (int kc : ks) {
             ResidentClass c;
+            const int k = kc & 15;
             c.ctasPerSm = k;
+            c.spill = kc >= 16;
             for (int oi = 0; oi < n; oi++)
-                if (pre[perm[oi]].cls == k) {
+                if (pre[perm[oi]].cls == kc) {
                     c.worlds.push_back(perm[oi]);
                     c.smem = std::max(c.smem, pre[perm[oi]].bytes);
                 }

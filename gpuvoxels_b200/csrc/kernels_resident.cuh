@@ -7,26 +7,33 @@
 // VX3/VX3_VoxelyzeKernel.cu:237-359).
 //
 // Contact (reference: all Ns^2/2 surface pairs every step, VX3_VoxelyzeKernel.cu:833-843) is a uniform-grid
-// broad phase kept in shared memory: surface voxels are counting-sorted by hashed cell every step, then each
-// surface voxel scans the 27 cells around its own.  The cell edge is >= the largest watch distance of the world,
-// so the watched-pair SET is exactly the reference's; candidates are visited in (cell, index) order, which makes
-// the force sums deterministic.
+// broad phase kept in shared memory plus per-voxel candidate lists with a skin (Verlet lists):
+//   rebuild (only when some surface voxel has moved more than skin/2 since the last rebuild): surface voxels are
+//     counting-sorted by hashed cell (edge = largest watch distance + skin); one warp per surface voxel scans the 27 cells
+//     around it, one cell per lane, and keeps every non-linked voxel within (watch distance + skin) in the voxel's list;
+//   every step: each surface voxel tests only its list with the reference's exact double-precision predicate.
+// Any pair the reference would watch at the current step is in the lists (triangle inequality), so the watched-pair SET
+// is exactly the reference's; lists are filled in (cell, index) order, which keeps the force sums deterministic.
 #pragma once
 #include "engine.cuh"
 #include "kernels_stream.cuh"
 
 namespace vx3b {
 
+constexpr int RES_K = 16; // capacity of one surface voxel's candidate list (overflow -> that step scans the grid directly)
+
 // shared-memory layout for capacities (capV, capL, capS); every array is 16-byte aligned
 template <class R> struct ResidentLayout {
     size_t world, vmats, lmats;
     size_t pos, orient, linMom, angMom, temp, vflags, vmat, vlinks, lat, phase, cilia, vext, vsurfslot;
     size_t lpos2, la1, la2, lflags, lmaxs, lends, lmeta, lfN, lfP, lmN, lmP;
-    size_t surf, contactF, skey, sorted, cnt;
+    size_t surf, contactF, skey, sorted, cnt, nbr, nbrCnt, ref;
     size_t total;
     int H; // hash buckets (power of two)
     __host__ __device__ static size_t up(size_t x) { return (x + 15) & ~(size_t)15; }
-    __host__ __device__ ResidentLayout(int capV, int capL, int capS, int capVM, int capLM, uint32_t wflags) {
+    // spill: the four per-link force/moment arrays stay in global memory (A.lfN ...; L2-resident) so that worlds whose
+    // full state exceeds one SM's shared memory can still run in k_resident
+    __host__ __device__ ResidentLayout(int capV, int capL, int capS, int capVM, int capLM, uint32_t wflags, bool spill) {
         const bool collide = (wflags & WF_COLLISION) && capS > 1;
         size_t o = 0;
         auto take = [&](size_t bytes) {
@@ -57,10 +64,10 @@ template <class R> struct ResidentLayout {
         lmaxs = take((wflags & WF_CAN_FAIL) ? sizeof(float) * capL : 0);
         lends = take(sizeof(uint16_t) * 2 * capL);
         lmeta = take(sizeof(uint16_t) * capL);
-        lfN = take(sizeof(R) * 3 * capL);
-        lfP = take(sizeof(R) * 3 * capL);
-        lmN = take(sizeof(R) * 3 * capL);
-        lmP = take(sizeof(R) * 3 * capL);
+        lfN = take(spill ? 0 : sizeof(R) * 3 * capL);
+        lfP = take(spill ? 0 : sizeof(R) * 3 * capL);
+        lmN = take(spill ? 0 : sizeof(R) * 3 * capL);
+        lmP = take(spill ? 0 : sizeof(R) * 3 * capL);
         surf = take(sizeof(uint16_t) * capS);
         H = 64;
         while (H < 2 * capS && H < 8192)
@@ -70,14 +77,17 @@ template <class R> struct ResidentLayout {
             skey = take(sizeof(uint32_t) * capS);
             sorted = take(sizeof(uint16_t) * capS);
             cnt = take(sizeof(int32_t) * H);
+            nbr = take(sizeof(uint16_t) * RES_K * capS);
+            nbrCnt = take(capS);
+            ref = take(sizeof(float) * 3 * capS);
         } else
-            contactF = skey = sorted = cnt = o;
+            contactF = skey = sorted = cnt = nbr = nbrCnt = ref = o;
         total = o;
     }
 };
 
 struct ResidentShared { // block-wide scalars
-    int32_t diverged, hits, running, pad;
+    int32_t diverged, hits, running, rebuild, overflow, pad[3];
     int32_t warpSums[32];
     double com[4];
 };
@@ -86,7 +96,7 @@ VXD uint32_t cell_hash(uint32_t key, int log2H) { return (key * 2654435761u) >> 
 
 // worldList: the worlds of one size class (every CTA lays its shared memory out for its own world's counts; the class only
 // fixes the dynamic shared-memory size, i.e. how many CTAs share an SM).
-template <class R>
+template <class R, bool SPILL>
 __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t *worldList, long long maxSteps, int useStop, int recordPairs) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ ResidentShared sh;
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     WorldD &Wg = A.worlds[w];
     if (!Wg.active)
         return;
-    const ResidentLayout<R> L(Wg.nv, max(Wg.nl, 1), max(Wg.ns, 1), max(Wg.nvm, 1), max(Wg.nlm, 1), Wg.flags);
+    const ResidentLayout<R> L(Wg.nv, max(Wg.nl, 1), max(Wg.ns, 1), max(Wg.nvm, 1), max(Wg.nlm, 1), Wg.flags, SPILL);
     WorldD &W = *(WorldD *)(smem + L.world);
     DVoxMat *vmats = (DVoxMat *)(smem + L.vmats);
     DLinkMat *lmats = (DLinkMat *)(smem + L.lmats);
@@ -118,15 +128,20 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     float *sLmax = (float *)(smem + L.lmaxs);
     uint16_t *sLends = (uint16_t *)(smem + L.lends);
     uint16_t *sLmeta = (uint16_t *)(smem + L.lmeta);
-    R *sFN = (R *)(smem + L.lfN);
-    R *sFP = (R *)(smem + L.lfP);
-    R *sMN = (R *)(smem + L.lmN);
-    R *sMP = (R *)(smem + L.lmP);
+    // per-link forces/moments for the voxel pass: shared memory (stride 3) or, spilled, the global arrays (stride 4)
+    constexpr int FS = SPILL ? 4 : 3;
+    R *sFN = SPILL ? (R *)(A.lfN + Wg.loff) : (R *)(smem + L.lfN);
+    R *sFP = SPILL ? (R *)(A.lfP + Wg.loff) : (R *)(smem + L.lfP);
+    R *sMN = SPILL ? (R *)(A.lmN + Wg.loff) : (R *)(smem + L.lmN);
+    R *sMP = SPILL ? (R *)(A.lmP + Wg.loff) : (R *)(smem + L.lmP);
     uint16_t *sSurf = (uint16_t *)(smem + L.surf);
     R *sCF = (R *)(smem + L.contactF);
     uint32_t *sKey = (uint32_t *)(smem + L.skey);
     uint16_t *sSorted = (uint16_t *)(smem + L.sorted);
     int32_t *sCnt = (int32_t *)(smem + L.cnt);
+    uint16_t *sNbr = (uint16_t *)(smem + L.nbr);
+    uint8_t *sNbrCnt = smem + L.nbrCnt;
+    float *sRef = (float *)(smem + L.ref);
 
     const int tid = threadIdx.x, nt = blockDim.x;
     // ---- load the world into shared memory --------------------------------------------------------------
@@ -143,7 +158,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     const bool ciliaOn = (wflags & WF_CILIA) && A.baseCilia, varyTemp = (wflags & WF_THERMAL) && W.tempPeriod > 0;
     const bool canFail = wflags & WF_CAN_FAIL;
     const float dt = W.dt;
-    const double voxSize = W.voxSize, tempAmp = W.tempAmp, tempPeriod = W.tempPeriod, invCell = W.invCell;
+    const double voxSize = W.voxSize, tempAmp = W.tempAmp, tempPeriod = W.tempPeriod, invCell = W.invCell, listR2 = W.listR2;
+    const float skinHalf2 = W.skinHalf2;
     const int cycle = W.cycle;
     const int H = L.H, log2H = 31 - __clz(H);
     for (int i = tid; i < W.nvm * (int)(sizeof(DVoxMat) / 4); i += nt)
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
         uint32_t meta = A.lmeta[g];
         sLmeta[l] = (uint16_t)((meta & 3) | (((meta >> 2) - W.lmatOff) << 2));
         for (int k = 0; k < 3; k++)
-            sFN[3 * l + k] = sFP[3 * l + k] = sMN[3 * l + k] = sMP[3 * l + k] = R(0);
+            sFN[FS * l + k] = sFP[FS * l + k] = sMN[FS * l + k] = sMP[FS * l + k] = R(0);
     }
     for (int s = tid; s < ns; s += nt)
         sSurf[s] = (uint16_t)(A.surf[soff + s] - voff);
@@ -231,6 +247,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
         sh.diverged = 0;
         sh.hits = 0;
         sh.running = 1;
+        sh.rebuild = 1;
+        sh.overflow = 0;
         sh.com[0] = sh.com[1] = sh.com[2] = sh.com[3] = 0;
     }
     __syncthreads();
@@ -241,6 +259,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     long long left = maxSteps;
     int collisionCount = W.collisionCount;
     bool running = true;
+    bool rebuild = true; // contact candidate lists must be rebuilt this step (uniform over the block)
+    const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
 
     while (running) {
         // ---- phase A: link pass + cell keys / bucket counts of the surface voxels (positions of the step start) ------
@@ -278,22 +298,22 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
             sLflags[l] = (uint8_t)h.flags;
             if (canFail)
                 sLmax[l] = h.maxStrain;
-            sFN[3 * l] = f.fNeg.x;
-            sFN[3 * l + 1] = f.fNeg.y;
-            sFN[3 * l + 2] = f.fNeg.z;
-            sFP[3 * l] = f.fPos.x;
-            sFP[3 * l + 1] = f.fPos.y;
-            sFP[3 * l + 2] = f.fPos.z;
-            sMN[3 * l] = f.mNeg.x;
-            sMN[3 * l + 1] = f.mNeg.y;
-            sMN[3 * l + 2] = f.mNeg.z;
-            sMP[3 * l] = f.mPos.x;
-            sMP[3 * l + 1] = f.mPos.y;
-            sMP[3 * l + 2] = f.mPos.z;
+            sFN[FS * l] = f.fNeg.x;
+            sFN[FS * l + 1] = f.fNeg.y;
+            sFN[FS * l + 2] = f.fNeg.z;
+            sFP[FS * l] = f.fPos.x;
+            sFP[FS * l + 1] = f.fPos.y;
+            sFP[FS * l + 2] = f.fPos.z;
+            sMN[FS * l] = f.mNeg.x;
+            sMN[FS * l + 1] = f.mNeg.y;
+            sMN[FS * l + 2] = f.mNeg.z;
+            sMP[FS * l] = f.mPos.x;
+            sMP[FS * l + 1] = f.mPos.y;
+            sMP[FS * l + 2] = f.mPos.z;
             if (f.strain > 100.0f)
                 sh.diverged = 1;
         }
-        if (collide) {
+        if (collide && rebuild) {
             for (int i = tid; i < ns; i += nt) {
                 const int v = sSurf[i];
                 const int cx = (int)floor(sPos[3 * v] * invCell), cy = (int)floor(sPos[3 * v + 1] * invCell), cz = (int)floor(sPos[3 * v + 2] * invCell);
@@ -305,58 +325,116 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
         __syncthreads();
         const bool divergedNow = sh.diverged != 0;
         if (collide) {
-            // ---- phase B: exclusive scan of the bucket counts -------------------------------------------------------------
-            const int per = (H + nt - 1) / nt, b0 = tid * per;
-            int sum = 0;
-            for (int k = 0; k < per; k++)
-                if (b0 + k < H)
-                    sum += sCnt[b0 + k];
-            int inc = sum;
-            for (int o = 1; o < 32; o <<= 1) {
-                int n = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((tid & 31) >= o)
-                    inc += n;
-            }
-            if ((tid & 31) == 31)
-                sh.warpSums[tid >> 5] = inc;
-            __syncthreads();
-            if (tid < 32) {
-                int ws = tid < (nt >> 5) ? sh.warpSums[tid] : 0, wi = ws;
+            bool overflow = false;
+            if (rebuild) {
+                // ---- B1: exclusive scan of the bucket counts -------------------------------------------------------------
+                const int per = (H + nt - 1) / nt, b0 = tid * per;
+                int sum = 0;
+                for (int k = 0; k < per; k++)
+                    if (b0 + k < H)
+                        sum += sCnt[b0 + k];
+                int inc = sum;
                 for (int o = 1; o < 32; o <<= 1) {
-                    int n = __shfl_up_sync(0xffffffffu, wi, o);
-                    if (tid >= o)
-                        wi += n;
+                    int n = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o)
+                        inc += n;
                 }
-                sh.warpSums[tid] = wi - ws; // exclusive
-            }
-            __syncthreads();
-            int offset = sh.warpSums[tid >> 5] + inc - sum;
-            for (int k = 0; k < per; k++)
-                if (b0 + k < H) {
-                    int c = sCnt[b0 + k];
-                    sCnt[b0 + k] = offset;
-                    offset += c;
+                if (lane == 31)
+                    sh.warpSums[wid] = inc;
+                if (tid == 0) {
+                    sh.rebuild = 0; // everyone has read it (barrier above); the voxel pass below may set it again
+                    sh.overflow = 0;
                 }
-            __syncthreads();
-            // ---- phase C: scatter (after it sCnt[h] = END of bucket h; its start is sCnt[h-1]) --------------------------------
-            for (int i = tid; i < ns; i += nt)
-                sSorted[atomicAdd(&sCnt[cell_hash(sKey[i], log2H)], 1)] = (uint16_t)i;
-            __syncthreads();
-            // ---- phase D: order every bucket by surface index (the atomics above are not ordered) ---------------------------------
-            for (int h = tid; h < H; h += nt) {
-                const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
-                for (int p = beg + 1; p < end; p++) {
-                    uint16_t x = sSorted[p];
-                    int q = p - 1;
-                    while (q >= beg && sSorted[q] > x) {
-                        sSorted[q + 1] = sSorted[q];
-                        q--;
+                __syncthreads();
+                if (tid < 32) {
+                    int ws = tid < nw ? sh.warpSums[tid] : 0, wi = ws;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int n = __shfl_up_sync(0xffffffffu, wi, o);
+                        if (tid >= o)
+                            wi += n;
                     }
-                    sSorted[q + 1] = x;
+                    sh.warpSums[tid] = wi - ws; // exclusive
                 }
+                __syncthreads();
+                int offset = sh.warpSums[wid] + inc - sum;
+                for (int k = 0; k < per; k++)
+                    if (b0 + k < H) {
+                        int c = sCnt[b0 + k];
+                        sCnt[b0 + k] = offset;
+                        offset += c;
+                    }
+                __syncthreads();
+                // ---- B2: scatter (after it sCnt[h] = END of bucket h; its start is sCnt[h-1]) --------------------------------
+                for (int i = tid; i < ns; i += nt)
+                    sSorted[atomicAdd(&sCnt[cell_hash(sKey[i], log2H)], 1)] = (uint16_t)i;
+                __syncthreads();
+                // ---- B3: order every bucket by surface index (the atomics above are not ordered) ---------------------------------
+                for (int h = tid; h < H; h += nt) {
+                    const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
+                    for (int p = beg + 1; p < end; p++) {
+                        uint16_t x = sSorted[p];
+                        int q = p - 1;
+                        while (q >= beg && sSorted[q] > x) {
+                            sSorted[q + 1] = sSorted[q];
+                            q--;
+                        }
+                        sSorted[q + 1] = x;
+                    }
+                }
+                __syncthreads();
+                // ---- B4: candidate lists, one warp per surface voxel, one of the 27 neighbouring cells per lane --------------------
+                for (int i = wid; i < ns; i += nw) {
+                    const int v1 = sSurf[i];
+                    const double x1 = sPos[3 * v1], y1 = sPos[3 * v1 + 1], z1 = sPos[3 * v1 + 2];
+                    const short4 c1 = sLat[v1];
+                    const bool fixed1 = vmats[sVmat[v1]].fixed != 0;
+                    const uint32_t key = sKey[i];
+                    int beg = 0, end = 0;
+                    uint32_t k2 = 0;
+                    if (lane < 27) {
+                        const int cx = (key & 1023) + lane % 3 - 1, cy = ((key >> 10) & 1023) + (lane / 3) % 3 - 1, cz = (key >> 20) + lane / 9 - 1;
+                        k2 = (uint32_t)(cx & 1023) | ((uint32_t)(cy & 1023) << 10) | ((uint32_t)(cz & 1023) << 20);
+                        const uint32_t h = cell_hash(k2, log2H);
+                        beg = h ? sCnt[h - 1] : 0;
+                        end = sCnt[h];
+                    }
+                    int count = 0;
+                    while (__any_sync(0xffffffffu, beg < end)) {
+                        bool ok = false;
+                        int j = 0;
+                        if (beg < end) {
+                            j = sSorted[beg++];
+                            if (j != i && sKey[j] == k2) {
+                                const int v2 = sSurf[j];
+                                const short4 c2 = sLat[v2];
+                                const double dx = sPos[3 * v2] - x1, dy = sPos[3 * v2 + 1] - y1, dz = sPos[3 * v2 + 2] - z1;
+                                // directly linked voxels (lattice neighbours; static topology) never collide: is_neighbor(depth 1);
+                                // nor do two voxels of `fixed` materials
+                                ok = dx * dx + dy * dy + dz * dz <= listR2 && abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) != 1 &&
+                                     !(fixed1 && vmats[sVmat[v2]].fixed != 0);
+                            }
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, ok);
+                        if (ok) {
+                            const int slot = count + __popc(m & ((1u << lane) - 1));
+                            if (slot < RES_K)
+                                sNbr[i * RES_K + slot] = (uint16_t)j;
+                        }
+                        count += __popc(m);
+                    }
+                    if (lane == 0) {
+                        sNbrCnt[i] = (uint8_t)min(count, RES_K);
+                        if (count > RES_K)
+                            sh.overflow = 1;
+                        sRef[3 * i] = (float)x1;
+                        sRef[3 * i + 1] = (float)y1;
+                        sRef[3 * i + 2] = (float)z1;
+                    }
+                }
+                __syncthreads();
+                overflow = sh.overflow != 0;
             }
-            __syncthreads();
-            // ---- phase E: narrow phase over the 27 cells around each surface voxel ----------------------------------------------
+            // ---- C: narrow phase with the reference's exact predicate -------------------------------------------------------------
             const bool rec = recordPairs && left == 1; // parity tests read the pair set of the run's last step
             int hits = 0;
             for (int i = tid; i < ns; i += nt) {
@@ -364,43 +442,51 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                 const DVoxMat &m1 = vmats[sVmat[v1]];
                 const V3<double> p1{sPos[3 * v1], sPos[3 * v1 + 1], sPos[3 * v1 + 2]};
                 const V3<R> l1{sLin[3 * v1], sLin[3 * v1 + 1], sLin[3 * v1 + 2]};
-                const short4 c1 = sLat[v1];
                 const float t1 = sTemp[v1];
-                const uint32_t key = sKey[i];
-                const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
                 V3<R> acc{R(0), R(0), R(0)};
-                for (int n = 0; n < 27; n++) {
-                    const int dx = n % 3 - 1, dy = (n / 3) % 3 - 1, dz = n / 9 - 1;
-                    const uint32_t k2 = (uint32_t)((cx + dx) & 1023) | ((uint32_t)((cy + dy) & 1023) << 10) | ((uint32_t)((cz + dz) & 1023) << 20);
-                    const uint32_t h = cell_hash(k2, log2H);
-                    const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
-                    for (int p = beg; p < end; p++) {
-                        const int j = sSorted[p];
-                        if (j == i || sKey[j] != k2)
-                            continue;
-                        const int v2 = sSurf[j];
-                        const V3<double> p2{sPos[3 * v2], sPos[3 * v2 + 1], sPos[3 * v2 + 2]};
-                        const short4 c2 = sLat[v2];
-                        if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1)
-                            continue; // directly linked (lattice neighbours; static topology): is_neighbor(depth 1)
-                        const DVoxMat &m2 = vmats[sVmat[v2]];
-                        if (m1.fixed && m2.fixed)
-                            continue;
-                        const V3<R> l2{sLin[3 * v2], sLin[3 * v2 + 1], sLin[3 * v2 + 2]};
-                        V3<R> f;
-                        if (i > j) {
-                            if (contact_pair<R>(m1, t1, p1, l1, m2, sTemp[v2], p2, l2, f)) {
-                                acc = acc + f;
-                                if ((m1.isTarget != 0) != (m2.isTarget != 0))
-                                    hits++;
-                                if (rec) {
-                                    int slot = atomicAdd(A.pairCount, 1);
-                                    if (slot < A.pairCap)
-                                        A.pairBuf[slot] = make_int4(w, v1, v2, 0);
-                                }
+                auto pair = [&](int j) {
+                    const int v2 = sSurf[j];
+                    const DVoxMat &m2 = vmats[sVmat[v2]];
+                    const V3<double> p2{sPos[3 * v2], sPos[3 * v2 + 1], sPos[3 * v2 + 2]};
+                    const V3<R> l2{sLin[3 * v2], sLin[3 * v2 + 1], sLin[3 * v2 + 2]};
+                    V3<R> f;
+                    if (i > j) {
+                        if (contact_pair<R>(m1, t1, p1, l1, m2, sTemp[v2], p2, l2, f)) {
+                            acc = acc + f;
+                            if ((m1.isTarget != 0) != (m2.isTarget != 0))
+                                hits++;
+                            if (rec) {
+                                int slot = atomicAdd(A.pairCount, 1);
+                                if (slot < A.pairCap)
+                                    A.pairBuf[slot] = make_int4(w, v1, v2, 0);
                             }
-                        } else if (contact_pair<R>(m2, sTemp[v2], p2, l2, m1, t1, p1, l1, f))
-                            acc = acc - f;
+                        }
+                    } else if (contact_pair<R>(m2, sTemp[v2], p2, l2, m1, t1, p1, l1, f))
+                        acc = acc - f;
+                };
+                if (!overflow) {
+                    const int cnt = sNbrCnt[i];
+                    for (int k = 0; k < cnt; k++)
+                        pair(sNbr[i * RES_K + k]);
+                } else { // some list overflowed at this rebuild: scan the grid directly (and rebuild again next step)
+                    const short4 c1 = sLat[v1];
+                    const uint32_t key = sKey[i];
+                    const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
+                    for (int n = 0; n < 27; n++) {
+                        const int dx = n % 3 - 1, dy = (n / 3) % 3 - 1, dz = n / 9 - 1;
+                        const uint32_t k2 = (uint32_t)((cx + dx) & 1023) | ((uint32_t)((cy + dy) & 1023) << 10) | ((uint32_t)((cz + dz) & 1023) << 20);
+                        const uint32_t h = cell_hash(k2, log2H);
+                        const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
+                        for (int p = beg; p < end; p++) {
+                            const int j = sSorted[p];
+                            if (j == i || sKey[j] != k2)
+                                continue;
+                            const int v2 = sSurf[j];
+                            const short4 c2 = sLat[v2];
+                            if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1 || (m1.fixed && vmats[sVmat[v2]].fixed))
+                                continue;
+                            pair(j);
+                        }
                     }
                 }
                 sCF[3 * i] = acc.x;
@@ -409,12 +495,14 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
             }
             if (hits)
                 atomicAdd(&sh.hits, hits);
+            if (overflow && tid == 0)
+                sh.rebuild = 1;
             __syncthreads();
             collisionCount += sh.hits;
         }
         const bool sampling = vx3 && cycle > 0 && ((step + 1) % cycle == 0);
         // ---- phase F: voxel pass (+ reset of the grid counters and, on ordinary steps, the world bookkeeping) ---------------
-        if (collide)
+        if (collide && rebuild)
             for (int h = tid; h < H; h += nt)
                 sCnt[h] = 0;
         if (!divergedNow) {
@@ -436,8 +524,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                         if (l == 0xffff)
                             continue;
                         const R *f = (k & 1) ? sFP : sFN, *mo = (k & 1) ? sMP : sMN;
-                        F = F + V3<R>{f[3 * l], f[3 * l + 1], f[3 * l + 2]};
-                        M = M + V3<R>{mo[3 * l], mo[3 * l + 1], mo[3 * l + 2]};
+                        F = F + V3<R>{f[FS * l], f[FS * l + 1], f[FS * l + 2]};
+                        M = M + V3<R>{mo[FS * l], mo[FS * l + 1], mo[FS * l + 2]};
                     }
                     V3<R> contact{R(0), R(0), R(0)}, cilia{R(0), R(0), R(0)};
                     const int slot = sVsurf[v];
@@ -485,6 +573,11 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                     sAng[3 * v + 2] = s.angMom.z;
                     sTemp[v] = s.temp;
                     sVflags[v] = (uint8_t)s.flags;
+                    if (collide && slot != 0xffff) { // moved more than skin/2 since the candidate lists were built?
+                        const float ddx = (float)s.pos.x - sRef[3 * slot], ddy = (float)s.pos.y - sRef[3 * slot + 1], ddz = (float)s.pos.z - sRef[3 * slot + 2];
+                        if (ddx * ddx + ddy * ddy + ddz * ddz > skinHalf2)
+                            sh.rebuild = 1;
+                    }
                 }
                 if (sampling && m.isMeasured) {
                     double mass = m.mass;
@@ -541,6 +634,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
             __syncthreads();
         }
         running = sh.running != 0;
+        rebuild = sh.rebuild != 0;
         step++;
         left--;
         if (!divergedNow)
@@ -574,10 +668,12 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
         A.lpos2[g] = mk4<R>(sP2[3 * l], sP2[3 * l + 1], sP2[3 * l + 2], fl);
         A.la1[g] = mk4<R>(sA1[3 * l], sA1[3 * l + 1], sA1[3 * l + 2], canFail ? (R)sLmax[l] : R(0));
         A.la2[g] = mk4<R>(sA2[3 * l], sA2[3 * l + 1], sA2[3 * l + 2], R(0));
-        A.lfN[g] = mk4<R>(sFN[3 * l], sFN[3 * l + 1], sFN[3 * l + 2], R(0));
-        A.lfP[g] = mk4<R>(sFP[3 * l], sFP[3 * l + 1], sFP[3 * l + 2], R(0));
-        A.lmN[g] = mk4<R>(sMN[3 * l], sMN[3 * l + 1], sMN[3 * l + 2], R(0));
-        A.lmP[g] = mk4<R>(sMP[3 * l], sMP[3 * l + 1], sMP[3 * l + 2], R(0));
+        if constexpr (!SPILL) {
+            A.lfN[g] = mk4<R>(sFN[3 * l], sFN[3 * l + 1], sFN[3 * l + 2], R(0));
+            A.lfP[g] = mk4<R>(sFP[3 * l], sFP[3 * l + 1], sFP[3 * l + 2], R(0));
+            A.lmN[g] = mk4<R>(sMN[3 * l], sMN[3 * l + 1], sMN[3 * l + 2], R(0));
+            A.lmP[g] = mk4<R>(sMP[3 * l], sMP[3 * l + 1], sMP[3 * l + 2], R(0));
+        }
     }
 }
 
@@ -587,6 +683,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
 // packs small and large worlds onto the same SMs.  Worlds that do not fit even alone are stepped by the streaming kernels.
 struct ResidentClass {
     int ctasPerSm = 1, threads = 512;
+    bool spill = false; // per-link force arrays in global memory (worlds too big for shared memory otherwise)
     size_t smem = 0; // dynamic shared memory of the launch = largest member
     std::vector<int32_t> worlds;
     int32_t *dList = nullptr;
@@ -594,10 +691,10 @@ struct ResidentClass {
     cudaEvent_t done = nullptr;
 };
 
-template <class R> size_t resident_bytes(int nv, int nl, int ns, int nvm, int nlm, uint32_t wflags) {
+template <class R> size_t resident_bytes(int nv, int nl, int ns, int nvm, int nlm, uint32_t wflags, bool spill) {
     if (nv <= 0 || nv >= 0xffff || nl >= 0xffff || ns >= 0xffff || nvm > 255 || nlm >= (1 << 14))
         return (size_t)-1;
-    return ResidentLayout<R>(nv, std::max(nl, 1), std::max(ns, 1), std::max(nvm, 1), std::max(nlm, 1), wflags).total;
+    return ResidentLayout<R>(nv, std::max(nl, 1), std::max(ns, 1), std::max(nvm, 1), std::max(nlm, 1), wflags, spill).total;
 }
 
 // per-SM shared memory budget: 228 KB per SM, 1 KB reserved per resident CTA, plus this kernel's static shared memory
@@ -617,9 +714,10 @@ template <class R>
 int resident_launch(const Arrays<R> &A, const ResidentClass &c, int64_t maxSteps, int useStop, int recordPairs) {
     if (c.worlds.empty())
         return VX3B_OK;
-    cudaError_t e = cudaFuncSetAttribute(k_resident<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    auto kernel = c.spill ? k_resident<R, true> : k_resident<R, false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e == cudaSuccess) {
-        k_resident<R><<<(unsigned)c.worlds.size(), c.threads, c.smem, c.stream>>>(A, c.dList, (long long)maxSteps, useStop, recordPairs);
+        kernel<<<(unsigned)c.worlds.size(), c.threads, c.smem, c.stream>>>(A, c.dList, (long long)maxSteps, useStop, recordPairs);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {
