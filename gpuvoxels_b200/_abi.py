@@ -59,7 +59,7 @@ class WorldResult(C.Structure):
         ("total_distance_of_all_voxels", C.c_double), ("vox_size", C.c_double), ("recent_angle", C.c_double),
         ("target_closeness", C.c_double), ("dt", C.c_double), ("steps", C.c_int64),
         ("num_voxel", C.c_int32), ("num_measured_voxel", C.c_int32), ("num_close_pairs", C.c_int32), ("collision_count", C.c_int32),
-        ("diverged", C.c_int32), ("stopped", C.c_int32),
+        ("diverged", C.c_int32), ("stopped", C.c_int32), ("contact_rebuilds", C.c_int32), ("contact_overflows", C.c_int32),
     ]
 
 

@@ -65,13 +65,16 @@ struct WorldD {
     double tempAmp, tempPeriod, voxSize, maxDistPair;
     // contact broad phase (k_resident): cell edge = largest watch distance of this world + skin
     double invCell, listR2; // 1/edge; edge^2 (a voxel's candidate list holds everything within the edge)
-    float skinHalf2, padf;  // (skin/2)^2: a surface voxel that moved further since the last rebuild forces a new one
+    double watchR2;         // (largest watch distance)^2 * (1 + 1e-12) when voxel sizes cannot change, else 0
+    float skinHalf2;        // (skin/2)^2: a surface voxel that moved further (relative to the common drift) since the last rebuild forces a new one
+    int32_t listCap;        // entries per surface voxel's candidate list
     // dynamic
     double t;
     int64_t step;     // CurStepCount
     int64_t runSteps; // steps left in the current vx3b_batch_run
     int32_t active, diverged, stopped, divergedNow;
     int32_t angleSamples, numClosePairs, collisionCount, pad1;
+    int32_t contactRebuilds, contactOverflows; // k_resident diagnostics: candidate-list rebuilds / rebuilds whose lists overflowed
     double recentAngle, closeness, fitness, totalDistance;
     double comAcc[4]; // Σ m·x, Σ m·y, Σ m·z, Σ m  (measured voxels)
     double distAcc;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -199,6 +200,7 @@ template <class R> class Engine : public EngineBase {
             bool spill = false;
         };
         std::vector<Pre> pre(n);
+        std::vector<int> listCaps(n, 16);
         int dev = 0, smemPerSm = 0, smemOptin = 0;
         CUDA_TRY(cudaGetDevice(&dev));
         CUDA_TRY(cudaDeviceGetAttribute(&smemPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
@@ -237,14 +239,17 @@ template <class R> class Engine : public EngineBase {
                           ((vary && maxAlpha != 0) ? WF_THERMAL : 0) | (canFail ? WF_CAN_FAIL : 0);
                 // contact broad-phase cell: >= the largest watch distance 0.625*(size1+size2), sizes at their largest temperature
                 const double skin = contactSkin * d.vox_size;
+                // list capacity: at rest the 12 face diagonals (1.414) enter once skin > 0.16, the 8 body diagonals (1.732) once skin > 0.48
+                const int listCap = contactListCap > 0 ? contactListCap : contactSkin < 0.16 ? 16 : contactSkin < 0.48 ? 24 : 36;
+                listCaps[w] = listCap;
                 double cell = 1.25 * maxSize * (1.0 + (fabs(d.temp_amplitude) + fabs((double)d.initial_temp)) * maxAlpha) * (1.0 + 1e-6) + skin;
                 p.invCell = cell > 0 ? 1.0 / cell : 0.0;
                 p.listR2 = cell * cell;
-                p.skinHalf2 = (float)(0.25 * skin * skin * (1.0 - 1e-3)); // a little early rather than late (float compare)
-                p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags, false);
+                p.skinHalf2 = (float)(0.25 * skin * skin * (1.0 - 1e-2)); // a little early rather than late (float compare)
+                p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags, false, listCap);
                 p.cls = p.bytes == (size_t)-1 ? 0 : resident_class_of(p.bytes, (size_t)smemPerSm, (size_t)smemOptin);
                 if (p.cls == 0 && p.bytes != (size_t)-1) { // too big: keep the per-link force arrays in global memory instead
-                    p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags, true);
+                    p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags, true, listCap);
                     p.cls = resident_class_of(p.bytes, (size_t)smemPerSm, (size_t)smemOptin);
                     p.spill = p.cls > 0;
                     if (p.spill)
@@ -334,6 +339,8 @@ template <class R> class Engine : public EngineBase {
             W.invCell = pre[w].invCell;
             W.listR2 = pre[w].listR2;
             W.skinHalf2 = pre[w].skinHalf2;
+            W.listCap = listCaps[w];
+            W.watchR2 = 0; // set below once the materials' constant sizes are known
             W.residentClass = pre[w].cls;
             memcpy(W.stop, d.stop_condition, sizeof(W.stop));
             memcpy(W.fitnessF, d.fitness, sizeof(W.fitnessF));
@@ -361,9 +368,22 @@ template <class R> class Engine : public EngineBase {
                 o.nomSizeF = (float)m.nomSize;
                 o.nomSize = m.nomSize;
                 o.cilia = m.Cilia;
+                // sizes are constant unless the world is thermally actuated (then the kernels evaluate the expressions every step)
+                o.sizeIsConst = (pre[w].flags & WF_THERMAL) ? 0 : 1;
+                const float T0 = (pre[w].flags & WF_VARY_TEMP) ? 0.0f : d.initial_temp; // varying but not thermal => every alphaCTE == 0
+                o.baseSize0 = base_size_expr(m.nomSize, m.alphaCTE, T0);
+                o.avgSize0 = base_size_average_expr(o.baseSize0);
+                o.floorOffset0 = o.avgSize0 / 2 - m.nomSize / 2;
                 o.fixed = m.fixed;
                 o.isTarget = m.isTarget;
                 o.isMeasured = m.isMeasured;
+            }
+            if (!(pre[w].flags & WF_THERMAL)) { // quick reject of contact candidates: nothing beyond the largest watch distance matters
+                double maxAvg = 0;
+                for (int k = 0; k < d.num_voxel_mats; k++)
+                    maxAvg = std::max(maxAvg, vmats[vmo + k].avgSize0);
+                const double Rw = (maxAvg + maxAvg) * 0.625;
+                W.watchR2 = Rw * Rw * (1.0 + 1e-12);
             }
             for (int k = 0; k < d.num_link_mats; k++) {
                 const VX3B_LinkMaterial &m = d.link_mats[k];
@@ -597,13 +617,18 @@ template <class R> class Engine : public EngineBase {
             if (c.worlds.empty())
                 continue;
             // registers cap the SM at 512 threads of this kernel (__launch_bounds__(512, 1) -> 128 registers/thread)
-            c.threads = residentThreads > 0 ? std::max(32, std::min(512, (residentThreads + 31) / 32 * 32)) : std::max(64, (512 / k) / 32 * 32);
+            c.threads = residentThreads > 0 ? std::max(32, std::min(512, (residentThreads + 31) / 32 * 32)) : std::max(128, (512 / k) / 32 * 32);
             if ((rc = dalloc(&c.dList, c.worlds.size(), c.worlds.data())) != VX3B_OK)
                 return rc;
             CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+            if (getenv("VX3B_DEBUG"))
+                fprintf(stderr, "[vx3b] resident class: %d CTA/SM%s, %zu worlds, %d threads, %zu B shared memory\n", k, c.spill ? " (spill)" : "",
+                        c.worlds.size(), c.threads, c.smem);
             classes.push_back(std::move(c));
         }
+        if (getenv("VX3B_DEBUG"))
+            fprintf(stderr, "[vx3b] %d worlds, %d resident, %d streaming-only\n", n, numResident, n - numResident);
         if (!evBegin)
             CUDA_TRY(cudaEventCreateWithFlags(&evBegin, cudaEventDisableTiming));
         CUDA_TRY(cudaStreamSynchronize(stream)); // host staging vectors die here
@@ -779,6 +804,8 @@ template <class R> class Engine : public EngineBase {
             r.collision_count = W.collisionCount;
             r.diverged = W.diverged;
             r.stopped = W.stopped;
+            r.contact_rebuilds = W.contactRebuilds;
+            r.contact_overflows = W.contactOverflows;
             int measured = 0;
             for (int v = 0; v < W.nv; v++)
                 if (vm[vmat[W.voff + v]].isMeasured)

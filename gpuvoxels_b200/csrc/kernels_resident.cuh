@@ -8,9 +8,9 @@
 //
 // Contact (reference: all Ns^2/2 surface pairs every step, VX3_VoxelyzeKernel.cu:833-843) is a uniform-grid
 // broad phase kept in shared memory plus per-voxel candidate lists with a skin (Verlet lists):
-//   rebuild (only when some surface voxel has moved more than skin/2 since the last rebuild): surface voxels are
-//     counting-sorted by hashed cell (edge = largest watch distance + skin); one warp per surface voxel scans the 27 cells
-//     around it, one cell per lane, and keeps every non-linked voxel within (watch distance + skin) in the voxel's list;
+//   rebuild (only when some surface voxel has moved more than skin/2, relative to the world's common drift, since the last
+//     rebuild): surface voxels are counting-sorted by hashed cell (edge = largest watch distance + skin); each surface voxel
+//     scans the 27 cells around it and keeps every non-linked voxel within (watch distance + skin) in its list;
 //   every step: each surface voxel tests only its list with the reference's exact double-precision predicate.
 // Any pair the reference would watch at the current step is in the lists (triangle inequality), so the watched-pair SET
 // is exactly the reference's; lists are filled in (cell, index) order, which keeps the force sums deterministic.
@@ -20,7 +20,6 @@
 
 namespace vx3b {
 
-constexpr int RES_K = 16; // capacity of one surface voxel's candidate list (overflow -> that step scans the grid directly)
 
 // shared-memory layout for capacities (capV, capL, capS); every array is 16-byte aligned
 template <class R> struct ResidentLayout {
@@ -33,7 +32,7 @@ template <class R> struct ResidentLayout {
     __host__ __device__ static size_t up(size_t x) { return (x + 15) & ~(size_t)15; }
     // spill: the four per-link force/moment arrays stay in global memory (A.lfN ...; L2-resident) so that worlds whose
     // full state exceeds one SM's shared memory can still run in k_resident
-    __host__ __device__ ResidentLayout(int capV, int capL, int capS, int capVM, int capLM, uint32_t wflags, bool spill) {
+    __host__ __device__ ResidentLayout(int capV, int capL, int capS, int capVM, int capLM, uint32_t wflags, bool spill, int listCap) {
         const bool collide = (wflags & WF_COLLISION) && capS > 1;
         size_t o = 0;
         auto take = [&](size_t bytes) {
@@ -41,14 +40,14 @@ template <class R> struct ResidentLayout {
             o = up(o + bytes);
             return at;
         };
-        world = take(sizeof(WorldD));
+        world = take(offsetof(WorldD, fitnessF)); // the kernel needs the record up to and including the stop-condition program
         vmats = take(sizeof(DVoxMat) * capVM);
         lmats = take(sizeof(DLinkMat) * capLM);
         pos = take(sizeof(double) * 3 * capV);
         orient = take(sizeof(R) * 4 * capV);
         linMom = take(sizeof(R) * 3 * capV);
         angMom = take(sizeof(R) * 3 * capV);
-        temp = take(sizeof(float) * capV);
+        temp = take((wflags & WF_THERMAL) ? sizeof(float) * capV : 0); // temperature is unobservable otherwise
         vflags = take(capV);
         vmat = take(capV);
         vlinks = take(sizeof(uint16_t) * 6 * capV);
@@ -64,24 +63,29 @@ template <class R> struct ResidentLayout {
         lmaxs = take((wflags & WF_CAN_FAIL) ? sizeof(float) * capL : 0);
         lends = take(sizeof(uint16_t) * 2 * capL);
         lmeta = take(sizeof(uint16_t) * capL);
-        lfN = take(spill ? 0 : sizeof(R) * 3 * capL);
-        lfP = take(spill ? 0 : sizeof(R) * 3 * capL);
-        lmN = take(spill ? 0 : sizeof(R) * 3 * capL);
-        lmP = take(spill ? 0 : sizeof(R) * 3 * capL);
         surf = take(sizeof(uint16_t) * capS);
         H = 64;
         while (H < 2 * capS && H < 8192)
             H *= 2;
+        // the four per-link force arrays and the grid scratch of the contact rebuild share one region: the scratch is only
+        // alive between the start of a step and its link pass, when the forces of the previous step are dead
+        const size_t forceBytes = spill ? 0 : 4 * up(sizeof(R) * 3 * capL);
+        const size_t scratchBytes = collide ? up(sizeof(uint32_t) * capS) + up(sizeof(uint16_t) * capS) + up(sizeof(int32_t) * H) : 0;
+        const size_t shared = take(forceBytes > scratchBytes ? forceBytes : scratchBytes);
+        lfN = shared;
+        lfP = lfN + up(sizeof(R) * 3 * capL);
+        lmN = lfP + up(sizeof(R) * 3 * capL);
+        lmP = lmN + up(sizeof(R) * 3 * capL);
+        skey = shared;
+        sorted = skey + up(sizeof(uint32_t) * capS);
+        cnt = sorted + up(sizeof(uint16_t) * capS);
         if (collide) {
             contactF = take(sizeof(R) * 3 * capS);
-            skey = take(sizeof(uint32_t) * capS);
-            sorted = take(sizeof(uint16_t) * capS);
-            cnt = take(sizeof(int32_t) * H);
-            nbr = take(sizeof(uint16_t) * RES_K * capS);
+            nbr = take(sizeof(uint16_t) * listCap * capS);
             nbrCnt = take(capS);
             ref = take(sizeof(float) * 3 * capS);
         } else
-            contactF = skey = sorted = cnt = nbr = nbrCnt = ref = o;
+            contactF = nbr = nbrCnt = ref = o;
         total = o;
     }
 };
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     WorldD &Wg = A.worlds[w];
     if (!Wg.active)
         return;
-    const ResidentLayout<R> L(Wg.nv, max(Wg.nl, 1), max(Wg.ns, 1), max(Wg.nvm, 1), max(Wg.nlm, 1), Wg.flags, SPILL);
+    const ResidentLayout<R> L(Wg.nv, max(Wg.nl, 1), max(Wg.ns, 1), max(Wg.nvm, 1), max(Wg.nlm, 1), Wg.flags, SPILL, Wg.listCap);
     WorldD &W = *(WorldD *)(smem + L.world);
     DVoxMat *vmats = (DVoxMat *)(smem + L.vmats);
     DLinkMat *lmats = (DLinkMat *)(smem + L.lmats);
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     {
         const uint32_t *src = (const uint32_t *)&Wg;
         uint32_t *dst = (uint32_t *)&W;
-        for (int i = tid; i < (int)(sizeof(WorldD) / 4); i += nt)
+        for (int i = tid; i < (int)(offsetof(WorldD, fitnessF) / 4); i += nt)
             dst[i] = src[i];
     }
     __syncthreads();
@@ -156,10 +160,12 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     const uint32_t wflags = W.flags;
     const bool vx3 = wflags & WF_VX3, floorOn = wflags & WF_FLOOR, collide = (wflags & WF_COLLISION) && ns > 1;
     const bool ciliaOn = (wflags & WF_CILIA) && A.baseCilia, varyTemp = (wflags & WF_THERMAL) && W.tempPeriod > 0;
-    const bool canFail = wflags & WF_CAN_FAIL;
+    const bool canFail = wflags & WF_CAN_FAIL, thermal = wflags & WF_THERMAL;
     const float dt = W.dt;
     const double voxSize = W.voxSize, tempAmp = W.tempAmp, tempPeriod = W.tempPeriod, invCell = W.invCell, listR2 = W.listR2;
     const float skinHalf2 = W.skinHalf2;
+    const double watchR2 = W.watchR2; // > 0: upper bound of every pair's squared watch distance (uniform constant sizes)
+    const int RES_K = W.listCap; // capacity of one surface voxel's candidate list (overflow -> that step scans the grid directly)
     const int cycle = W.cycle;
     const int H = L.H, log2H = 31 - __clz(H);
     for (int i = tid; i < W.nvm * (int)(sizeof(DVoxMat) / 4); i += nt)
@@ -187,7 +193,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
         sAng[3 * v] = lm.w;
         sAng[3 * v + 1] = am.x;
         sAng[3 * v + 2] = am.y;
-        sTemp[v] = temp;
+        if (thermal)
+            sTemp[v] = temp;
         sVflags[v] = (uint8_t)fl;
         sVmat[v] = (uint8_t)(A.vmat[g] - W.vmatOff);
         for (int k = 0; k < 6; k++) {
@@ -263,19 +270,219 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
 
     while (running) {
-        // ---- phase A: link pass + cell keys / bucket counts of the surface voxels (positions of the step start) ------
+        // ---- contact step 1 (only when the candidate lists are stale): grid + lists from the positions of the step start.
+        // The grid scratch (keys, sorted order, bucket counters) aliases the per-link force arrays, which are dead here.
+        bool overflow = false;
+        int hits = 0;
+        float driftX = 0, driftY = 0, driftZ = 0;
+        // one surface voxel against one candidate with the reference's exact predicate (both members of a pair evaluate it in
+        // the same orientation, voxel1 = the later surface voxel, so the two forces are bit-identical and no atomics are needed)
+        auto narrow = [&](bool direct) {
+            const bool rec = recordPairs && left == 1; // parity tests read the pair set of the run's last step
+            for (int i = tid; i < ns; i += nt) {
+                const int v1 = sSurf[i];
+                const DVoxMat &m1 = vmats[sVmat[v1]];
+                const V3<double> p1{sPos[3 * v1], sPos[3 * v1 + 1], sPos[3 * v1 + 2]};
+                const V3<R> l1{sLin[3 * v1], sLin[3 * v1 + 1], sLin[3 * v1 + 2]};
+                const float t1 = thermal ? sTemp[v1] : 0.0f;
+                V3<R> acc{R(0), R(0), R(0)};
+                auto pair = [&](int j) {
+                    const int v2 = sSurf[j];
+                    const V3<double> p2{sPos[3 * v2], sPos[3 * v2 + 1], sPos[3 * v2 + 2]};
+                    if (watchR2 > 0) { // all voxel sizes of this world are constant: reject on the squared distance alone
+                        const double ex = p1.x - p2.x, ey = p1.y - p2.y, ez = p1.z - p2.z;
+                        if (ex * ex + ey * ey + ez * ez > watchR2)
+                            return;
+                    }
+                    const DVoxMat &m2 = vmats[sVmat[v2]];
+                    const V3<R> l2{sLin[3 * v2], sLin[3 * v2 + 1], sLin[3 * v2 + 2]};
+                    const float t2 = thermal ? sTemp[v2] : 0.0f;
+                    V3<R> f;
+                    if (i > j) {
+                        if (contact_pair<R>(m1, t1, p1, l1, m2, t2, p2, l2, f)) {
+                            acc = acc + f;
+                            if ((m1.isTarget != 0) != (m2.isTarget != 0))
+                                hits++;
+                            if (rec) {
+                                int slot = atomicAdd(A.pairCount, 1);
+                                if (slot < A.pairCap)
+                                    A.pairBuf[slot] = make_int4(w, v1, v2, 0);
+                            }
+                        }
+                    } else if (contact_pair<R>(m2, t2, p2, l2, m1, t1, p1, l1, f))
+                        acc = acc - f;
+                };
+                if (!direct) {
+                    const int cnt = sNbrCnt[i];
+                    for (int k = 0; k < cnt; k++)
+                        pair(sNbr[i * RES_K + k]);
+                } else { // some list overflowed at this rebuild: scan the grid directly (and rebuild again next step)
+                    const short4 c1 = sLat[v1];
+                    const uint32_t key = sKey[i];
+                    const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
+                    for (int n = 0; n < 27; n++) {
+                        const int dx = n % 3 - 1, dy = (n / 3) % 3 - 1, dz = n / 9 - 1;
+                        const uint32_t k2 = (uint32_t)((cx + dx) & 1023) | ((uint32_t)((cy + dy) & 1023) << 10) | ((uint32_t)((cz + dz) & 1023) << 20);
+                        const uint32_t h = cell_hash(k2, log2H);
+                        const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
+                        for (int p = beg; p < end; p++) {
+                            const int j = sSorted[p];
+                            if (j == i || sKey[j] != k2)
+                                continue;
+                            const int v2 = sSurf[j];
+                            const short4 c2 = sLat[v2];
+                            if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1 || (m1.fixed && vmats[sVmat[v2]].fixed))
+                                continue;
+                            pair(j);
+                        }
+                    }
+                }
+                sCF[3 * i] = acc.x;
+                sCF[3 * i + 1] = acc.y;
+                sCF[3 * i + 2] = acc.z;
+            }
+        };
+        if (collide && rebuild) {
+            for (int h = tid; h < H; h += nt)
+                sCnt[h] = 0;
+            if (tid == 0) {
+                sh.rebuild = 0; // everyone has read it (barrier at the end of the previous step); the voxel pass may set it again
+                sh.overflow = 0;
+            }
+            __syncthreads();
+            for (int i = tid; i < ns; i += nt) {
+                const int v = sSurf[i];
+                const int cx = (int)floor(sPos[3 * v] * invCell), cy = (int)floor(sPos[3 * v + 1] * invCell), cz = (int)floor(sPos[3 * v + 2] * invCell);
+                const uint32_t key = (uint32_t)(cx & 1023) | ((uint32_t)(cy & 1023) << 10) | ((uint32_t)(cz & 1023) << 20);
+                sKey[i] = key;
+                atomicAdd(&sCnt[cell_hash(key, log2H)], 1);
+            }
+            __syncthreads();
+            // ---- B1: exclusive scan of the bucket counts -------------------------------------------------------------
+            const int per = (H + nt - 1) / nt, b0 = tid * per;
+            int sum = 0;
+            for (int k = 0; k < per; k++)
+                if (b0 + k < H)
+                    sum += sCnt[b0 + k];
+            int inc = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                int n = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                    inc += n;
+            }
+            if (lane == 31)
+                sh.warpSums[wid] = inc;
+            __syncthreads();
+            if (tid < 32) {
+                int ws = tid < nw ? sh.warpSums[tid] : 0, wi = ws;
+                for (int o = 1; o < 32; o <<= 1) {
+                    int n = __shfl_up_sync(0xffffffffu, wi, o);
+                    if (tid >= o)
+                        wi += n;
+                }
+                sh.warpSums[tid] = wi - ws; // exclusive
+            }
+            __syncthreads();
+            int offset = sh.warpSums[wid] + inc - sum;
+            for (int k = 0; k < per; k++)
+                if (b0 + k < H) {
+                    int c = sCnt[b0 + k];
+                    sCnt[b0 + k] = offset;
+                    offset += c;
+                }
+            __syncthreads();
+            // ---- B2: scatter (after it sCnt[h] = END of bucket h; its start is sCnt[h-1]) --------------------------------
+            for (int i = tid; i < ns; i += nt)
+                sSorted[atomicAdd(&sCnt[cell_hash(sKey[i], log2H)], 1)] = (uint16_t)i;
+            __syncthreads();
+            // ---- B3: order every bucket by surface index (the atomics above are not ordered) ---------------------------------
+            for (int h = tid; h < H; h += nt) {
+                const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
+                for (int p = beg + 1; p < end; p++) {
+                    uint16_t x = sSorted[p];
+                    int q = p - 1;
+                    while (q >= beg && sSorted[q] > x) {
+                        sSorted[q + 1] = sSorted[q];
+                        q--;
+                    }
+                    sSorted[q + 1] = x;
+                }
+            }
+            __syncthreads();
+            // ---- B4: candidate lists, one thread per surface voxel.  A flat loop that either tests the next voxel of the current
+            // cell or moves on to the next of the 27 cells, so the lanes of a warp stay busy although their cells hold different
+            // numbers of voxels (a nested cell/voxel loop costs the warp the SUM over cells of the longest bucket).
+            for (int i = tid; i < ns; i += nt) {
+                const int v1 = sSurf[i];
+                const double x1 = sPos[3 * v1], y1 = sPos[3 * v1 + 1], z1 = sPos[3 * v1 + 2];
+                const short4 c1 = sLat[v1];
+                const bool fixed1 = vmats[sVmat[v1]].fixed != 0;
+                const uint32_t key = sKey[i];
+                const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
+                int n = -1, p = 0, end = 0, count = 0;
+                uint32_t k2 = 0;
+                while (true) {
+                    if (p < end) {
+                        const int j = sSorted[p++];
+                        if (j != i && sKey[j] == k2) {
+                            const int v2 = sSurf[j];
+                            const short4 c2 = sLat[v2];
+                            const double dx = sPos[3 * v2] - x1, dy = sPos[3 * v2 + 1] - y1, dz = sPos[3 * v2 + 2] - z1;
+                            // directly linked voxels (lattice neighbours; static topology) never collide: is_neighbor(depth 1);
+                            // nor do two voxels of `fixed` materials
+                            if (dx * dx + dy * dy + dz * dz <= listR2 && abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) != 1 &&
+                                !(fixed1 && vmats[sVmat[v2]].fixed != 0)) {
+                                if (count < RES_K)
+                                    sNbr[i * RES_K + count] = (uint16_t)j;
+                                count++;
+                            }
+                        }
+                    } else {
+                        if (++n == 27)
+                            break;
+                        k2 = (uint32_t)((cx + n % 3 - 1) & 1023) | ((uint32_t)((cy + (n / 3) % 3 - 1) & 1023) << 10) |
+                             ((uint32_t)((cz + n / 9 - 1) & 1023) << 20);
+                        const uint32_t h = cell_hash(k2, log2H);
+                        p = h ? sCnt[h - 1] : 0;
+                        end = sCnt[h];
+                    }
+                }
+                sNbrCnt[i] = (uint8_t)min(count, RES_K);
+                if (count > RES_K)
+                    sh.overflow = 1;
+                sRef[3 * i] = (float)x1;
+                sRef[3 * i + 1] = (float)y1;
+                sRef[3 * i + 2] = (float)z1;
+            }
+            __syncthreads();
+            overflow = sh.overflow != 0;
+            if (tid == 0) {
+                W.contactRebuilds++;
+                W.contactOverflows += overflow;
+                if (overflow)
+                    sh.rebuild = 1;
+            }
+            if (overflow) { // the grid scratch dies with the link pass below, so the direct scan has to come first
+                narrow(true);
+                __syncthreads();
+            }
+        }
+        // ---- phase A: link pass, and the contact narrow phase over the candidate lists (independent of each other) ------------
         for (int l = tid; l < nl; l += nt) {
             const int a = sLends[2 * l], b = sLends[2 * l + 1];
             const uint32_t meta = sLmeta[l];
             const int axis = meta & 3;
             const DVoxMat &mn = vmats[sVmat[a]], &mp = vmats[sVmat[b]];
-            if (vx3 && mn.fixed && mp.fixed)
+            if (vx3 && mn.fixed && mp.fixed) { // gpu_update_links skips these; their force slots must still be defined
+                for (int k = 0; k < 3; k++)
+                    sFN[FS * l + k] = sFP[FS * l + k] = sMN[FS * l + k] = sMP[FS * l + k] = R(0);
                 continue;
+            }
             const DLinkMat &lmat = lmats[meta >> 2];
             V3<double> dpos{sPos[3 * b] - sPos[3 * a], sPos[3 * b + 1] - sPos[3 * a + 1], sPos[3 * b + 2] - sPos[3 * a + 2]};
             Qt<R> qn{sOri[4 * a], sOri[4 * a + 1], sOri[4 * a + 2], sOri[4 * a + 3]};
             Qt<R> qp{sOri[4 * b], sOri[4 * b + 1], sOri[4 * b + 2], sOri[4 * b + 3]};
-            double restLen = 0.5 * (base_size(mn, sTemp[a]) + base_size(mp, sTemp[b]));
+            double restLen = 0.5 * (base_size(mn, thermal ? sTemp[a] : 0.0f) + base_size(mp, thermal ? sTemp[b] : 0.0f));
             LinkHist<R> h;
             h.pos2 = {sP2[3 * l], sP2[3 * l + 1], sP2[3 * l + 2]};
             h.a1v = {sA1[3 * l], sA1[3 * l + 1], sA1[3 * l + 2]};
@@ -313,198 +520,22 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
             if (f.strain > 100.0f)
                 sh.diverged = 1;
         }
-        if (collide && rebuild) {
-            for (int i = tid; i < ns; i += nt) {
-                const int v = sSurf[i];
-                const int cx = (int)floor(sPos[3 * v] * invCell), cy = (int)floor(sPos[3 * v + 1] * invCell), cz = (int)floor(sPos[3 * v + 2] * invCell);
-                const uint32_t key = (uint32_t)(cx & 1023) | ((uint32_t)(cy & 1023) << 10) | ((uint32_t)(cz & 1023) << 20);
-                sKey[i] = key;
-                atomicAdd(&sCnt[cell_hash(key, log2H)], 1);
-            }
+        if (collide && !overflow) {
+            // common displacement since the rebuild (that of one reference voxel): the rebuild test in the voxel pass removes it,
+            // because only RELATIVE motion of two voxels can bring an unlisted pair inside the watch distance
+            const int s0 = ns >> 1, v0 = sSurf[s0];
+            driftX = (float)sPos[3 * v0] - sRef[3 * s0];
+            driftY = (float)sPos[3 * v0 + 1] - sRef[3 * s0 + 1];
+            driftZ = (float)sPos[3 * v0 + 2] - sRef[3 * s0 + 2];
+            narrow(false);
         }
+        if (hits)
+            atomicAdd(&sh.hits, hits);
         __syncthreads();
         const bool divergedNow = sh.diverged != 0;
-        if (collide) {
-            bool overflow = false;
-            if (rebuild) {
-                // ---- B1: exclusive scan of the bucket counts -------------------------------------------------------------
-                const int per = (H + nt - 1) / nt, b0 = tid * per;
-                int sum = 0;
-                for (int k = 0; k < per; k++)
-                    if (b0 + k < H)
-                        sum += sCnt[b0 + k];
-                int inc = sum;
-                for (int o = 1; o < 32; o <<= 1) {
-                    int n = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o)
-                        inc += n;
-                }
-                if (lane == 31)
-                    sh.warpSums[wid] = inc;
-                if (tid == 0) {
-                    sh.rebuild = 0; // everyone has read it (barrier above); the voxel pass below may set it again
-                    sh.overflow = 0;
-                }
-                __syncthreads();
-                if (tid < 32) {
-                    int ws = tid < nw ? sh.warpSums[tid] : 0, wi = ws;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        int n = __shfl_up_sync(0xffffffffu, wi, o);
-                        if (tid >= o)
-                            wi += n;
-                    }
-                    sh.warpSums[tid] = wi - ws; // exclusive
-                }
-                __syncthreads();
-                int offset = sh.warpSums[wid] + inc - sum;
-                for (int k = 0; k < per; k++)
-                    if (b0 + k < H) {
-                        int c = sCnt[b0 + k];
-                        sCnt[b0 + k] = offset;
-                        offset += c;
-                    }
-                __syncthreads();
-                // ---- B2: scatter (after it sCnt[h] = END of bucket h; its start is sCnt[h-1]) --------------------------------
-                for (int i = tid; i < ns; i += nt)
-                    sSorted[atomicAdd(&sCnt[cell_hash(sKey[i], log2H)], 1)] = (uint16_t)i;
-                __syncthreads();
-                // ---- B3: order every bucket by surface index (the atomics above are not ordered) ---------------------------------
-                for (int h = tid; h < H; h += nt) {
-                    const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
-                    for (int p = beg + 1; p < end; p++) {
-                        uint16_t x = sSorted[p];
-                        int q = p - 1;
-                        while (q >= beg && sSorted[q] > x) {
-                            sSorted[q + 1] = sSorted[q];
-                            q--;
-                        }
-                        sSorted[q + 1] = x;
-                    }
-                }
-                __syncthreads();
-                // ---- B4: candidate lists, one warp per surface voxel, one of the 27 neighbouring cells per lane --------------------
-                for (int i = wid; i < ns; i += nw) {
-                    const int v1 = sSurf[i];
-                    const double x1 = sPos[3 * v1], y1 = sPos[3 * v1 + 1], z1 = sPos[3 * v1 + 2];
-                    const short4 c1 = sLat[v1];
-                    const bool fixed1 = vmats[sVmat[v1]].fixed != 0;
-                    const uint32_t key = sKey[i];
-                    int beg = 0, end = 0;
-                    uint32_t k2 = 0;
-                    if (lane < 27) {
-                        const int cx = (key & 1023) + lane % 3 - 1, cy = ((key >> 10) & 1023) + (lane / 3) % 3 - 1, cz = (key >> 20) + lane / 9 - 1;
-                        k2 = (uint32_t)(cx & 1023) | ((uint32_t)(cy & 1023) << 10) | ((uint32_t)(cz & 1023) << 20);
-                        const uint32_t h = cell_hash(k2, log2H);
-                        beg = h ? sCnt[h - 1] : 0;
-                        end = sCnt[h];
-                    }
-                    int count = 0;
-                    while (__any_sync(0xffffffffu, beg < end)) {
-                        bool ok = false;
-                        int j = 0;
-                        if (beg < end) {
-                            j = sSorted[beg++];
-                            if (j != i && sKey[j] == k2) {
-                                const int v2 = sSurf[j];
-                                const short4 c2 = sLat[v2];
-                                const double dx = sPos[3 * v2] - x1, dy = sPos[3 * v2 + 1] - y1, dz = sPos[3 * v2 + 2] - z1;
-                                // directly linked voxels (lattice neighbours; static topology) never collide: is_neighbor(depth 1);
-                                // nor do two voxels of `fixed` materials
-                                ok = dx * dx + dy * dy + dz * dz <= listR2 && abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) != 1 &&
-                                     !(fixed1 && vmats[sVmat[v2]].fixed != 0);
-                            }
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, ok);
-                        if (ok) {
-                            const int slot = count + __popc(m & ((1u << lane) - 1));
-                            if (slot < RES_K)
-                                sNbr[i * RES_K + slot] = (uint16_t)j;
-                        }
-                        count += __popc(m);
-                    }
-                    if (lane == 0) {
-                        sNbrCnt[i] = (uint8_t)min(count, RES_K);
-                        if (count > RES_K)
-                            sh.overflow = 1;
-                        sRef[3 * i] = (float)x1;
-                        sRef[3 * i + 1] = (float)y1;
-                        sRef[3 * i + 2] = (float)z1;
-                    }
-                }
-                __syncthreads();
-                overflow = sh.overflow != 0;
-            }
-            // ---- C: narrow phase with the reference's exact predicate -------------------------------------------------------------
-            const bool rec = recordPairs && left == 1; // parity tests read the pair set of the run's last step
-            int hits = 0;
-            for (int i = tid; i < ns; i += nt) {
-                const int v1 = sSurf[i];
-                const DVoxMat &m1 = vmats[sVmat[v1]];
-                const V3<double> p1{sPos[3 * v1], sPos[3 * v1 + 1], sPos[3 * v1 + 2]};
-                const V3<R> l1{sLin[3 * v1], sLin[3 * v1 + 1], sLin[3 * v1 + 2]};
-                const float t1 = sTemp[v1];
-                V3<R> acc{R(0), R(0), R(0)};
-                auto pair = [&](int j) {
-                    const int v2 = sSurf[j];
-                    const DVoxMat &m2 = vmats[sVmat[v2]];
-                    const V3<double> p2{sPos[3 * v2], sPos[3 * v2 + 1], sPos[3 * v2 + 2]};
-                    const V3<R> l2{sLin[3 * v2], sLin[3 * v2 + 1], sLin[3 * v2 + 2]};
-                    V3<R> f;
-                    if (i > j) {
-                        if (contact_pair<R>(m1, t1, p1, l1, m2, sTemp[v2], p2, l2, f)) {
-                            acc = acc + f;
-                            if ((m1.isTarget != 0) != (m2.isTarget != 0))
-                                hits++;
-                            if (rec) {
-                                int slot = atomicAdd(A.pairCount, 1);
-                                if (slot < A.pairCap)
-                                    A.pairBuf[slot] = make_int4(w, v1, v2, 0);
-                            }
-                        }
-                    } else if (contact_pair<R>(m2, sTemp[v2], p2, l2, m1, t1, p1, l1, f))
-                        acc = acc - f;
-                };
-                if (!overflow) {
-                    const int cnt = sNbrCnt[i];
-                    for (int k = 0; k < cnt; k++)
-                        pair(sNbr[i * RES_K + k]);
-                } else { // some list overflowed at this rebuild: scan the grid directly (and rebuild again next step)
-                    const short4 c1 = sLat[v1];
-                    const uint32_t key = sKey[i];
-                    const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
-                    for (int n = 0; n < 27; n++) {
-                        const int dx = n % 3 - 1, dy = (n / 3) % 3 - 1, dz = n / 9 - 1;
-                        const uint32_t k2 = (uint32_t)((cx + dx) & 1023) | ((uint32_t)((cy + dy) & 1023) << 10) | ((uint32_t)((cz + dz) & 1023) << 20);
-                        const uint32_t h = cell_hash(k2, log2H);
-                        const int beg = h ? sCnt[h - 1] : 0, end = sCnt[h];
-                        for (int p = beg; p < end; p++) {
-                            const int j = sSorted[p];
-                            if (j == i || sKey[j] != k2)
-                                continue;
-                            const int v2 = sSurf[j];
-                            const short4 c2 = sLat[v2];
-                            if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1 || (m1.fixed && vmats[sVmat[v2]].fixed))
-                                continue;
-                            pair(j);
-                        }
-                    }
-                }
-                sCF[3 * i] = acc.x;
-                sCF[3 * i + 1] = acc.y;
-                sCF[3 * i + 2] = acc.z;
-            }
-            if (hits)
-                atomicAdd(&sh.hits, hits);
-            if (overflow && tid == 0)
-                sh.rebuild = 1;
-            __syncthreads();
-            collisionCount += sh.hits;
-        }
+        collisionCount += sh.hits;
         const bool sampling = vx3 && cycle > 0 && ((step + 1) % cycle == 0);
         // ---- phase F: voxel pass (+ reset of the grid counters and, on ordinary steps, the world bookkeeping) ---------------
-        if (collide && rebuild)
-            for (int h = tid; h < H; h += nt)
-                sCnt[h] = 0;
         if (!divergedNow) {
             double cx = 0, cy = 0, cz = 0, cm = 0;
             for (int v = tid; v < nv; v += nt) {
@@ -515,7 +546,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                     s.orient = {sOri[4 * v], sOri[4 * v + 1], sOri[4 * v + 2], sOri[4 * v + 3]};
                     s.linMom = {sLin[3 * v], sLin[3 * v + 1], sLin[3 * v + 2]};
                     s.angMom = {sAng[3 * v], sAng[3 * v + 1], sAng[3 * v + 2]};
-                    s.temp = sTemp[v];
+                    s.temp = thermal ? sTemp[v] : 0.0f;
                     s.flags = sVflags[v];
                     V3<R> F{R(0), R(0), R(0)}, M{R(0), R(0), R(0)};
 #pragma unroll
@@ -539,7 +570,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                     wp.dt = dt;
                     wp.floorEnabled = floorOn;
                     wp.vx3 = vx3;
-                    wp.forceField = (wflags & WF_FORCE_FIELD) ? W.ff : nullptr;
+                    wp.forceField = (wflags & WF_FORCE_FIELD) ? Wg.ff : nullptr; // (not part of the shared-memory copy)
                     wp.fv = FormulaVars{0, 0, 0, (double)collisionCount, t, W.recentAngle, W.closeness, W.numClosePairs, nv};
                     VoxExt ext;
                     const VoxExt *pe = nullptr;
@@ -571,10 +602,12 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                     sAng[3 * v] = s.angMom.x;
                     sAng[3 * v + 1] = s.angMom.y;
                     sAng[3 * v + 2] = s.angMom.z;
-                    sTemp[v] = s.temp;
+                    if (thermal)
+                        sTemp[v] = s.temp;
                     sVflags[v] = (uint8_t)s.flags;
                     if (collide && slot != 0xffff) { // moved more than skin/2 since the candidate lists were built?
-                        const float ddx = (float)s.pos.x - sRef[3 * slot], ddy = (float)s.pos.y - sRef[3 * slot + 1], ddz = (float)s.pos.z - sRef[3 * slot + 2];
+                        const float ddx = (float)s.pos.x - sRef[3 * slot] - driftX, ddy = (float)s.pos.y - sRef[3 * slot + 1] - driftY,
+                                    ddz = (float)s.pos.z - sRef[3 * slot + 2] - driftZ;
                         if (ddx * ddx + ddy * ddy + ddz * ddz > skinHalf2)
                             sh.rebuild = 1;
                     }
@@ -624,8 +657,11 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                         sh.com[k] = 0;
                     }
                 if (sampling && !divergedNow && W.maxDistPair != 0) { // closeness needs current positions in HBM
-                    for (int v = 0; v < nv; v++)
-                        store_pos(A, voff + v, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, sTemp[v], sVflags[v]);
+                    for (int v = 0; v < nv; v++) {
+                        float tv;
+                        load_pos(A, voff + v, &tv, nullptr);
+                        store_pos(A, voff + v, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, thermal ? sTemp[v] : tv, sVflags[v]);
+                    }
                 }
                 world_end_of_step(A, W, useStop);
                 sh.running = W.active;
@@ -653,7 +689,9 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     }
     for (int v = tid; v < nv; v += nt) {
         const int g = voff + v;
-        store_pos(A, g, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, sTemp[v], sVflags[v]);
+        float tv;
+        load_pos(A, g, &tv, nullptr); // a world without thermal actuation never changes (or stages) its temperatures
+        store_pos(A, g, V3<double>{sPos[3 * v], sPos[3 * v + 1], sPos[3 * v + 2]}, thermal ? sTemp[v] : tv, sVflags[v]);
         A.orient[g] = mk4<R>(sOri[4 * v], sOri[4 * v + 1], sOri[4 * v + 2], sOri[4 * v + 3]);
         A.lm[g] = mk4<R>(sLin[3 * v], sLin[3 * v + 1], sLin[3 * v + 2], sAng[3 * v]);
         A.am[g] = mk2<R>(sAng[3 * v + 1], sAng[3 * v + 2]);
@@ -691,10 +729,10 @@ struct ResidentClass {
     cudaEvent_t done = nullptr;
 };
 
-template <class R> size_t resident_bytes(int nv, int nl, int ns, int nvm, int nlm, uint32_t wflags, bool spill) {
+template <class R> size_t resident_bytes(int nv, int nl, int ns, int nvm, int nlm, uint32_t wflags, bool spill, int listCap) {
     if (nv <= 0 || nv >= 0xffff || nl >= 0xffff || ns >= 0xffff || nvm > 255 || nlm >= (1 << 14))
         return (size_t)-1;
-    return ResidentLayout<R>(nv, std::max(nl, 1), std::max(ns, 1), std::max(nvm, 1), std::max(nlm, 1), wflags, spill).total;
+    return ResidentLayout<R>(nv, std::max(nl, 1), std::max(ns, 1), std::max(nvm, 1), std::max(nlm, 1), wflags, spill, listCap).total;
 }
 
 // per-SM shared memory budget: 228 KB per SM, 1 KB reserved per resident CTA, plus this kernel's static shared memory

@@ -180,7 +180,10 @@ struct DVoxMat { // per voxel material, pre-multiplied where the reference multi
     float nomSizeF;     // (float)nomSize
     double nomSize;
     double cilia;
-    int32_t fixed, isTarget, isMeasured, pad;
+    // sizes when the voxel temperature cannot change them (world without thermal actuation, or alphaCTE == 0): the values the
+    // expressions below produce, evaluated once on the host (they contain a double division the step would otherwise repeat)
+    double baseSize0, avgSize0, floorOffset0; // base_size, base_size_average, avg/2 - nomSize/2
+    int32_t fixed, isTarget, isMeasured, sizeIsConst;
 };
 struct DLinkMat {
     float E, a2, b1, b2, b3, sqA1, sqA2xIp, sqB1, sqB2xFMp, sqB3xIp, epsilonFail, area; // area: currentTransverseArea (nu == 0)
@@ -202,10 +205,11 @@ template <class R> struct LinkForces {
 };
 
 // base size along one axis = nomSize * (1 + temp*alphaCTE), the bracket being a float expression (VX3/VX3_Voxel.h:96-99)
-VXD double base_size(const DVoxMat &m, float temp) { return m.nomSize * (double)(1 + temp * m.alphaCTE); }
-VXD double base_size_average(const DVoxMat &m, float temp) { // VX3/VX3_Voxel.h:102-105
-    double b = base_size(m, temp);
-    return (b + b + b) / 3.0f;
+__host__ __device__ inline double base_size_expr(double nomSize, float alphaCTE, float temp) { return nomSize * (double)(1 + temp * alphaCTE); }
+__host__ __device__ inline double base_size_average_expr(double b) { return (b + b + b) / 3.0f; } // VX3/VX3_Voxel.h:102-105
+VXD double base_size(const DVoxMat &m, float temp) { return m.sizeIsConst ? m.baseSize0 : base_size_expr(m.nomSize, m.alphaCTE, temp); }
+VXD double base_size_average(const DVoxMat &m, float temp) {
+    return m.sizeIsConst ? m.avgSize0 : base_size_average_expr(base_size_expr(m.nomSize, m.alphaCTE, temp));
 }
 
 // One link: orientLink + updateForces (VX3/VX3_Link.cu:90-218, updateStrain :220-231 linear / nu == 0 branch).
@@ -388,6 +392,8 @@ struct VoxExt { // boundary conditions of one voxel (CVX_External)
 };
 
 VXD float floor_penetration(const DVoxMat &m, float temp, double z) { // VX3/VX3_Voxel.h:185-187
+    if (m.sizeIsConst)
+        return (float)(m.floorOffset0 - z);
     return (float)(base_size_average(m, temp) / 2 - m.nomSize / 2 - z);
 }
 
@@ -532,9 +538,12 @@ VXD bool contact_pair(const DVoxMat &m1, float temp1, V3<double> p1, V3<R> linMo
     double Rw = (base_size_average(m1, temp1) + base_size_average(m2, temp2)) * 0.625;
     double dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
     force = V3<R>{R(0), R(0), R(0)};
+    double d2 = dx * dx + dy * dy + dz * dz;
+    if (d2 > Rw * Rw * (1.0 + 1e-12)) // certainly outside: the reference's box test and Length() > watchDistance both reject it
+        return false;
     if (dx > Rw || dx < -Rw || dy > Rw || dy < -Rw || dz > Rw || dz < -Rw)
         return false;
-    double dist = sqrt(dx * dx + dy * dy + dz * dz);
+    double dist = sqrt(d2);
     if (dist > Rw)
         return false;
     double relDist = Rw - dist;

@@ -147,6 +147,7 @@ typedef struct VX3B_WorldResult {
     int64_t steps;               /* steps taken (CurStepCount) */
     int32_t num_voxel, num_measured_voxel, num_close_pairs, collision_count;
     int32_t diverged, stopped;   /* diverged: some link strain > 100; stopped: stop formula > 0 */
+    int32_t contact_rebuilds, contact_overflows; /* diagnostics of the resident contact broad phase (0 on the streaming path) */
 } VX3B_WorldResult;
 
 typedef struct vx3b_ctx vx3b_ctx;

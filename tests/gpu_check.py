@@ -102,7 +102,11 @@ def main():
                 ctx.run(steps)
                 ms, launches = ctx.timing()
                 vs = ctx.total_voxel_steps()
-                print(f"batch n={n} path{path} fp{prec}: {steps} steps {ms:.1f} ms -> {vs / ms * 1e3:.3e} voxel-steps/s ({launches} launches)", flush=True)
+                res = ctx.results()
+                rb = np.array([r.contact_rebuilds for r in res]) / steps
+                ov = np.array([r.contact_overflows for r in res]) / steps
+                print(f"batch n={n} path{path} fp{prec}: {steps} steps {ms:.1f} ms -> {vs / ms * 1e3:.3e} voxel-steps/s ({launches} launches); "
+                      f"contact rebuilds/step mean {rb.mean():.3f} max {rb.max():.3f}, overflows/step mean {ov.mean():.4f} max {ov.max():.3f}", flush=True)
                 ctx.close()
     # big body streaming throughput
     for n in (50, 100):
