@@ -96,6 +96,7 @@ SYMBOLS = {
     "vx3b_ctx_total_voxel_steps": (C.c_int64, [_P]),
     "vx3b_ctx_set_stream": (C.c_int, [_P, C.c_uint64]),
     "vx3b_job_run": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
+    "vx3b_shard_worlds": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int32)]),
 }
 
 _lib = None

@@ -65,6 +65,30 @@ static bool better(const JobWorld *a, const JobWorld *b) {
 
 } // namespace vx3b
 
+// Longest-processing-time-first: worlds in descending cost, each to the currently lightest shard (ties: lowest shard index,
+// then lowest world index, so every rank of a multi-process job computes the same assignment).
+extern "C" int vx3b_shard_worlds(const int64_t *cost, int n, int num_shards, int32_t *shard_of) {
+    using namespace vx3b;
+    if (n < 0 || num_shards < 1 || (n > 0 && (!cost || !shard_of))) {
+        set_error("vx3b_shard_worlds: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++)
+        order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<int64_t> load(num_shards, 0);
+    for (int i : order) {
+        int best = 0;
+        for (int s = 1; s < num_shards; s++)
+            if (load[s] < load[best])
+                best = s;
+        shard_of[i] = best;
+        load[best] += cost[i] > 0 ? cost[i] : 1;
+    }
+    return VX3B_OK;
+}
+
 extern "C" int vx3b_job_run(const char *input_dir, const char *report_path, int num_devices, int precision) {
     using namespace vx3b;
     if (!input_dir || !report_path || num_devices < 1) {
@@ -107,10 +131,18 @@ extern "C" int vx3b_job_run(const char *input_dir, const char *report_path, int 
         }
         vx3b_model_desc(worlds[i].model, &worlds[i].desc);
     }
-    // round-robin split over devices (vx3_node_worker.cu:88-93), one host thread and one context per device
+    // split over devices, one host thread and one context per device.  The reference deals files round-robin
+    // (vx3_node_worker.cu:88-93); worlds differ 10x in cost, so we deal them longest-processing-time-first instead.
     std::vector<std::vector<int>> sub(num_devices);
-    for (size_t i = 0; i < worlds.size(); i++)
-        sub[i % num_devices].push_back((int)i);
+    {
+        std::vector<int64_t> cost(worlds.size());
+        std::vector<int32_t> shard(worlds.size());
+        for (size_t i = 0; i < worlds.size(); i++)
+            cost[i] = (int64_t)worlds[i].desc.num_voxels + 2 * (int64_t)worlds[i].desc.num_links;
+        vx3b_shard_worlds(cost.data(), (int)worlds.size(), num_devices, shard.data());
+        for (size_t i = 0; i < worlds.size(); i++)
+            sub[shard[i]].push_back((int)i);
+    }
     std::vector<int> status(num_devices, VX3B_OK);
     std::vector<std::string> errors(num_devices);
     std::vector<std::thread> threads;

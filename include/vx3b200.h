@@ -206,6 +206,9 @@ int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t cuda_stream);
  * VX3_SimulationManager.cu:138-155): every *.vxd in input_dir over base.vxa, worlds sharded over
  * `num_devices` GPUs, report XML in the reference's layout written to report_path. */
 int vx3b_job_run(const char *input_dir, const char *report_path, int num_devices, int precision);
+/* Host-only: assign n worlds of the given cost to num_shards devices / ranks, longest-processing-time-first (the reference
+ * deals files round-robin, vx3_node_worker.cu:88-93).  Deterministic, so every rank of a multi-process job agrees. */
+int vx3b_shard_worlds(const int64_t *cost, int n, int num_shards, int32_t *shard_of);
 
 #ifdef __cplusplus
 }
