@@ -51,13 +51,15 @@ enum {
     WF_FLOOR = 1, WF_VARY_TEMP = 2, WF_COLLISION = 4, WF_CILIA = 8, WF_EXPANSION = 16, WF_VX3 = 32, WF_FORCE_FIELD = 64,
     WF_STOP_FORMULA = 128, WF_RESIDENT = 256, // WF_RESIDENT: stepped by k_resident in this run; the streaming kernels skip it
     WF_THERMAL = 512,  // temperature varies AND some material has alphaCTE != 0 (otherwise temperature is unobservable)
-    WF_CAN_FAIL = 1024 // some link material has a failure strain
+    WF_CAN_FAIL = 1024, // some link material has a failure strain
+    WF_FUSED = 2048     // stepped by k_fused in this run (state ping-pongs between the main and the alternate buffers)
 };
 struct WorldD {
     // static
     int32_t voff, nv, loff, nl, soff, ns, vmatOff, lmatOff;
     int32_t nvm, nlm; // materials of this world
-    int32_t residentClass, padc; // CTAs per SM of the world's k_resident size class (+16: spill variant); 0 = does not fit
+    int32_t residentClass;       // CTAs per SM of the world's k_resident size class (+16: spill variant); 0 = does not fit
+    int32_t parity;              // dynamic: which buffer set holds the world's current state (k_fused ping-pong; 0 outside a run)
     uint32_t flags;
     int32_t cycle; // int(TempPeriod/dt): COM/angle sampling period in steps (0 = never)
     float dt;
@@ -90,10 +92,21 @@ struct DExt { // compact table of voxels that carry boundary conditions
     double rotQ[4];
 };
 
+// the per-step read+write state: voxel state and link history (one set = one buffer of the k_fused ping-pong)
+template <class R> struct StateSet {
+    using T4 = typename Store<R>::T4;
+    using T2 = typename Store<R>::T2;
+    D2 *pxy, *pzt;
+    T4 *orient, *lm;
+    T2 *am;
+    T4 *lpos2, *la1, *la2;
+};
+
 // ---- all device arrays of a batch (struct of arrays; worlds concatenated) ------------------------------
 template <class R> struct Arrays {
     using T4 = typename Store<R>::T4;
     using T2 = typename Store<R>::T2;
+    StateSet<R> alt; // second buffer set (allocated only when some world runs on the fused path)
     int nvTot, nlTot, nsTot, nWorlds;
     WorldD *worlds;
     // voxel state (read+write every step)
@@ -133,5 +146,9 @@ template <class R> struct Arrays {
     int32_t *pairCount;
     int32_t pairCap;
 };
+
+template <class R> VXD StateSet<R> main_set(const Arrays<R> &A) { return StateSet<R>{A.pxy, A.pzt, A.orient, A.lm, A.am, A.lpos2, A.la1, A.la2}; }
+// buffer set holding a world's current state
+template <class R> VXD StateSet<R> cur_set(const Arrays<R> &A, int parity) { return parity ? A.alt : main_set(A); }
 
 } // namespace vx3b

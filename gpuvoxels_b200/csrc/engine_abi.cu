@@ -72,6 +72,8 @@ int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value) {
         ctx->e->dtOverride = value;
     else if (n == "resident_threads")
         ctx->e->residentThreads = (int)value;
+    else if (n == "brick_x" || n == "brick_y" || n == "brick_z")
+        ctx->e->brickDim[n[6] - 'x'] = std::max(1, std::min(64, (int)value));
     else if (n == "contact_list_cap")
         ctx->e->contactListCap = std::max(0, std::min(255, (int)value));
     else if (n == "contact_skin")

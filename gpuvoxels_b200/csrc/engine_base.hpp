@@ -25,7 +25,8 @@ class EngineBase {
     float lastMs = 0;
     int64_t lastLaunches = 0, lastVoxelSteps = 0;
     // options
-    int path = 0;         // 0 auto, 1 streaming, 2 resident
+    int path = 0;         // 0 auto (resident + fused), 1 two-kernel streaming, 2 resident, 3 fused for all, 4 resident + two-kernel streaming
+    int brickDim[3] = {8, 8, 4}; // lattice cells per brick of the fused path
     int recordPairs = 0;  // keep the collision pair list of the last step (parity tests)
     int chunk = 64;       // steps per CUDA-graph replay on the streaming path
     double dtOverride = 0;

@@ -14,6 +14,7 @@
 
 #include "engine.cuh"
 #include "engine_base.hpp"
+#include "kernels_fused.cuh"
 #include "kernels_resident.cuh"
 #include "kernels_stream.cuh"
 
@@ -114,7 +115,12 @@ template <class R> class Engine : public EngineBase {
     std::vector<ResidentClass> classes; // k_resident size classes (kernels_resident.cuh)
     int numResident = 0;                // worlds that fit in shared memory (laid out first; streaming-only worlds follow)
     int vStream0 = 0, lStream0 = 0, tileStream0 = 0; // first voxel / link / contact tile of the streaming-only worlds
-    int graphMixed = -1;
+    int graphMixed = -1, graphFused = -1;
+    // fused tile path (kernels_fused.cuh): bricks of the streaming-only worlds (of every world when path 3 was chosen before upload)
+    FusedArrays FA{};
+    int fusedCapTab = 0, fusedCapOwn = 0, fusedBrick0 = 0; // fusedBrick0: first brick of the streaming-only worlds
+    bool fusedAllWorlds = false;
+    size_t fusedSmem = 0;
     cudaEvent_t evBegin = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -597,6 +603,138 @@ template <class R> class Engine : public EngineBase {
             k_world_finish<R><<<(n + 127) / 128, 128, 0, stream>>>(A, 0);
         }
         CUDA_TRY(cudaGetLastError());
+        // ---- fused tile path: cut the streaming-only worlds (all worlds for path 3) into bricks --------------------------------
+        FA = FusedArrays{};
+        fusedAllWorlds = path == 3;
+        {
+            std::vector<BrickD> bricks;
+            std::vector<int32_t> bvox;
+            std::vector<uint8_t> mask;
+            std::vector<BrickLink> blinks;
+            std::vector<int32_t> local(nvTot, -1);
+            fusedCapTab = fusedCapOwn = 0;
+            fusedBrick0 = -1;
+            const int BX = brickDim[0], BY = brickDim[1], BZ = brickDim[2];
+            for (int oi = 0; oi < n; oi++) {
+                const int w = perm[oi];
+                const bool streamingOnly = pre[w].cls == 0;
+                if (!streamingOnly && !fusedAllWorlds)
+                    continue;
+                if (streamingOnly && fusedBrick0 < 0)
+                    fusedBrick0 = (int)bricks.size();
+                const WorldHost &h = H[w];
+                if (h.nv == 0)
+                    continue;
+                // brick key of every voxel; voxels of a brick stay in creation order (x runs are contiguous in memory)
+                int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+                for (int v = 0; v < h.nv; v++)
+                    for (int k = 0; k < 3; k++) {
+                        int c = (&lat[h.voff + v].x)[k];
+                        mn[k] = std::min(mn[k], c);
+                        mx[k] = std::max(mx[k], c);
+                    }
+                const int64_t nbx = (mx[0] - mn[0]) / BX + 1, nby = (mx[1] - mn[1]) / BY + 1;
+                std::vector<std::pair<int64_t, int>> keyed(h.nv);
+                for (int v = 0; v < h.nv; v++) {
+                    const short4 c = lat[h.voff + v];
+                    int64_t key = (((int64_t)(c.z - mn[2]) / BZ) * nby + (c.y - mn[1]) / BY) * nbx + (c.x - mn[0]) / BX;
+                    keyed[v] = {key, v};
+                }
+                std::sort(keyed.begin(), keyed.end());
+                std::vector<int64_t> brickOf(h.nv);
+                for (auto &kv : keyed)
+                    brickOf[kv.second] = kv.first;
+                for (size_t a = 0; a < keyed.size();) {
+                    size_t b = a;
+                    while (b < keyed.size() && keyed[b].first == keyed[a].first)
+                        b++;
+                    BrickD B;
+                    memset(&B, 0, sizeof(B));
+                    B.world = w;
+                    B.voxBeg = (int)bvox.size();
+                    B.nOwn = (int)(b - a);
+                    B.linkBeg = (int)blinks.size();
+                    for (size_t q = a; q < b; q++) {
+                        local[h.voff + keyed[q].second] = (int)(q - a);
+                        bvox.push_back(h.voff + keyed[q].second);
+                    }
+                    mask.resize(bvox.size(), 0);
+                    std::vector<int> halo;
+                    auto local_of = [&](int g) { // brick-local table index of global voxel g (own or halo)
+                        if (local[g] < 0) {
+                            local[g] = B.nOwn + (int)halo.size();
+                            halo.push_back(g);
+                        }
+                        return local[g];
+                    };
+                    for (size_t q = a; q < b; q++) {
+                        const int g = h.voff + keyed[q].second;
+                        uint8_t mk = 0;
+                        for (int dir = 0; dir < 6; dir++) {
+                            const int l = vlinks[(size_t)dir * nvTot + g];
+                            if (l < 0)
+                                continue;
+                            mk |= (uint8_t)(1u << dir);
+                            const int neg = lends[l].x, pos = lends[l].y;
+                            const bool negOwn = brickOf[neg - h.voff] == keyed[a].first, posOwn = brickOf[pos - h.voff] == keyed[a].first;
+                            // a link is listed once per brick: by its positive end when that end is here (owned), else by its negative end
+                            if ((dir & 1) == 0 && posOwn)
+                                continue;
+                            BrickLink k;
+                            memset(&k, 0, sizeof(k));
+                            k.link = l;
+                            k.a = (uint16_t)local_of(neg);
+                            k.b = (uint16_t)local_of(pos);
+                            k.flags = (uint16_t)((lmeta[l] & 3) | (posOwn ? BL_OWNED | BL_POS_OWN : 0) | (negOwn ? BL_NEG_OWN : 0));
+                            k.lmat = lmeta[l] >> 2;
+                            blinks.push_back(k);
+                        }
+                        mask[B.voxBeg + (q - a)] = mk;
+                    }
+                    for (int g : halo)
+                        bvox.push_back(g);
+                    mask.resize(bvox.size(), 0);
+                    B.nHalo = (int)halo.size();
+                    B.nLinks = (int)blinks.size() - B.linkBeg;
+                    for (int q = 0; q < B.nOwn + B.nHalo; q++)
+                        local[bvox[B.voxBeg + q]] = -1;
+                    fusedCapTab = std::max(fusedCapTab, B.nOwn + B.nHalo);
+                    fusedCapOwn = std::max(fusedCapOwn, B.nOwn);
+                    bricks.push_back(B);
+                    a = b;
+                }
+            }
+            if (fusedBrick0 < 0)
+                fusedBrick0 = (int)bricks.size();
+            if (!bricks.empty()) {
+                if (fusedCapTab > 0xffff) {
+                    set_error("vx3b_batch_upload: brick too large for 16-bit local indices");
+                    return VX3B_ERR_ARG;
+                }
+                BrickD *dB = nullptr;
+                int32_t *dV = nullptr;
+                BrickLink *dL = nullptr;
+                uint8_t *dM = nullptr;
+                if ((rc = dalloc(&dB, bricks.size(), bricks.data())) != VX3B_OK || (rc = dalloc(&dV, bvox.size(), bvox.data())) != VX3B_OK ||
+                    (rc = dalloc(&dL, blinks.size(), blinks.data())) != VX3B_OK || (rc = dalloc(&dM, mask.size(), mask.data())) != VX3B_OK)
+                    return rc;
+                FA.nBricks = (int)bricks.size();
+                FA.bricks = dB;
+                FA.bvox = dV;
+                FA.blinks = dL;
+                FA.linkMask = dM;
+                // second buffer set for the ping-pong (contents are produced by the first fused step)
+                if ((rc = dalloc(&A.alt.pxy, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.pzt, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.orient, nvTot)) != VX3B_OK ||
+                    (rc = dalloc(&A.alt.lm, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.am, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.lpos2, nlTot)) != VX3B_OK ||
+                    (rc = dalloc(&A.alt.la1, nlTot)) != VX3B_OK || (rc = dalloc(&A.alt.la2, nlTot)) != VX3B_OK)
+                    return rc;
+                fusedSmem = FusedLayout<R>(fusedCapTab, fusedCapOwn).total;
+                CUDA_TRY(cudaFuncSetAttribute(k_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fusedSmem));
+                if (getenv("VX3B_DEBUG"))
+                    fprintf(stderr, "[vx3b] fused path: %zu bricks (%dx%dx%d), table <= %d voxels, own <= %d, %zu links incl. %.1f%% recomputed, %zu B shared memory\n",
+                            bricks.size(), BX, BY, BZ, fusedCapTab, fusedCapOwn, blinks.size(), 100.0 * (blinks.size() - (double)nlTot) / std::max<size_t>(nlTot, 1), fusedSmem);
+            }
+        }
         // ---- k_resident size classes: one launch + stream per class
         if (vStream0 < 0) {
             vStream0 = (int)nvTot;
@@ -638,20 +776,27 @@ template <class R> class Engine : public EngineBase {
     // ---- streaming path: CUDA graph of `chunk` steps -----------------------------------------------------
     int launches_per_step() const { return 3 + (anyCollision ? 1 : 0); }
     // mixed: only the streaming-only worlds (a suffix of every array) are stepped here; the others run in k_resident
-    void enqueue_step(int useStop, bool mixed) {
+    // fused: one k_fused launch per step instead of k_links + k_voxels
+    void enqueue_step(int useStop, bool mixed, bool fused) {
         const int l0 = mixed ? lStream0 : 0, v0 = mixed ? vStream0 : 0, t0 = mixed ? tileStream0 : 0;
         const unsigned lb = (A.nlTot - l0 + 255) / 256, vb = (A.nvTot - v0 + 255) / 256, wb = (A.nWorlds + 127) / 128;
-        if (A.nlTot > l0)
+        if (!fused && A.nlTot > l0)
             k_links<R><<<lb, 256, 0, stream>>>(A, l0);
         if (anyCollision && (int)hTiles.size() > t0) {
             k_contact<R><<<(unsigned)hTiles.size() - t0, 128, 0, stream>>>(A, dTiles + t0, recordPairs);
         }
-        if (A.nvTot > v0)
+        if (fused) {
+            const int b0 = mixed ? fusedBrick0 : 0;
+            FusedArrays F = FA;
+            F.bricks += b0;
+            if (FA.nBricks > b0)
+                k_fused<R><<<(unsigned)(FA.nBricks - b0), 256, fusedSmem, stream>>>(A, F, fusedCapTab, fusedCapOwn);
+        } else if (A.nvTot > v0)
             k_voxels<R><<<vb, 256, 0, stream>>>(A, v0);
         k_world_step<R><<<wb, 128, 0, stream>>>(A, useStop, dActive);
     }
-    int build_graph(int steps, int useStop, bool mixed) {
-        if (graphExec && graphChunk == steps && graphUseStop == useStop && graphRecord == recordPairs && graphMixed == (int)mixed)
+    int build_graph(int steps, int useStop, bool mixed, bool fused) {
+        if (graphExec && graphChunk == steps && graphUseStop == useStop && graphRecord == recordPairs && graphMixed == (int)mixed && graphFused == (int)fused)
             return VX3B_OK;
         if (graphExec) {
             cudaGraphExecDestroy(graphExec);
@@ -662,7 +807,7 @@ template <class R> class Engine : public EngineBase {
         for (int s = 0; s < steps; s++) {
             if (s == steps - 1)
                 k_zero_int<<<1, 1, 0, stream>>>(dActive);
-            enqueue_step(useStop, mixed);
+            enqueue_step(useStop, mixed, fused);
         }
         CUDA_TRY(cudaStreamEndCapture(stream, &g));
         CUDA_TRY(cudaGraphInstantiate(&graphExec, g, 0));
@@ -671,18 +816,19 @@ template <class R> class Engine : public EngineBase {
         graphUseStop = useStop;
         graphRecord = recordPairs;
         graphMixed = (int)mixed;
+        graphFused = (int)fused;
         return VX3B_OK;
     }
 
-    int run_streaming(int64_t maxSteps, int useStop, bool mixed) {
+    int run_streaming(int64_t maxSteps, int useStop, bool mixed, bool fused) {
         int64_t done = 0;
         while (done < maxSteps) {
             int steps = (int)std::min<int64_t>(chunk, maxSteps - done);
-            int rc = build_graph(steps, useStop, mixed);
+            int rc = build_graph(steps, useStop, mixed, fused);
             if (rc != VX3B_OK)
                 return rc;
             CUDA_TRY(cudaGraphLaunch(graphExec, stream));
-            lastLaunches += (int64_t)steps * launches_per_step() + 1;
+            lastLaunches += (int64_t)steps * (launches_per_step() - (fused ? 1 : 0)) + 1;
             done += steps;
             CUDA_TRY(cudaMemcpyAsync(hActive, dActive, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
@@ -724,24 +870,37 @@ template <class R> class Engine : public EngineBase {
             return rc;
         const unsigned wb = (A.nWorlds + 127) / 128;
         CUDA_TRY(cudaEventRecord(ev0, stream));
-        // path 1: streaming kernels for every world; path 2: k_resident for every world (error if one does not fit);
-        // path 0: k_resident for the worlds that fit, streaming kernels (concurrently, on the main stream) for the rest
+        // path 0: k_resident for the worlds that fit in shared memory, k_fused (concurrently, on the main stream) for the rest;
+        // path 1: the two-kernel streaming path (k_links + k_voxels) for every world; path 2: k_resident for every world (error
+        // if one does not fit); path 3: k_fused for every world (must be chosen before upload); path 4: as 0 but with the
+        // two-kernel streaming path instead of k_fused
         if (path == 2 && numResident != (int)H.size()) {
             set_error("vx3b_batch_run: resident path requested but " + std::to_string(H.size() - numResident) + " world(s) do not fit in shared memory");
             return VX3B_ERR_ARG;
         }
+        if (path == 3 && !fusedAllWorlds) {
+            set_error("vx3b_batch_run: the fused path for every world must be selected (option path = 3) before vx3b_batch_upload");
+            return VX3B_ERR_ARG;
+        }
         if (recordPairs) // the pair list is that of the last step of a fixed-length run (W.runSteps == 1)
             CUDA_TRY(cudaMemsetAsync(A.pairCount, 0, sizeof(int), stream));
-        const bool resident = path != 1 && numResident > 0;
-        const bool streaming = path == 1 || numResident != (int)H.size();
-        k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)maxSteps, useStop, resident ? 1 : 0);
+        const bool resident = (path == 0 || path == 2 || path == 4) && numResident > 0;
+        const bool streaming = path == 1 || path == 3 || numResident != (int)H.size();
+        const bool fused = streaming && (path == 0 || path == 3) && FA.nBricks > 0;
+        k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)maxSteps, useStop, resident ? 1 : 0, fused ? 1 : 0);
         lastLaunches++;
         if (resident && (rc = run_resident(maxSteps, useStop)) != VX3B_OK)
             return rc;
-        if (streaming && (rc = run_streaming(maxSteps, useStop, resident)) != VX3B_OK)
+        if (streaming && (rc = run_streaming(maxSteps, useStop, resident, fused)) != VX3B_OK)
             return rc;
         if (resident && (rc = join_resident()) != VX3B_OK)
             return rc;
+        if (fused) { // bring every world's state back to the main buffers
+            const unsigned nb = (unsigned)((std::max(A.nvTot, A.nlTot) + 255) / 256);
+            k_unparity<R><<<nb, 256, 0, stream>>>(A, 0, 0);
+            k_clear_parity<R><<<wb, 128, 0, stream>>>(A);
+            lastLaunches += 2;
+        }
         if (A.nvTot) {
             k_reduce_com<R><<<(unsigned)((A.nvTot + 255) / 256), 256, 0, stream>>>(A, 1);
             k_world_finish<R><<<wb, 128, 0, stream>>>(A, 1);

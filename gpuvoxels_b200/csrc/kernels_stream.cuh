@@ -128,12 +128,14 @@ template <class R> __global__ void __launch_bounds__(128) k_contact(Arrays<R> A,
     const int i = ct.first + threadIdx.x; // local surface index
     SurfRec<R> me;
     const bool have = i < ns;
+    const StateSet<R> cur = cur_set(A, W.parity);
     auto load = [&](int slot) {
         SurfRec<R> r;
         int v = A.surf[soff + slot];
-        float temp;
-        V3<double> p = load_pos(A, v, &temp, nullptr);
-        auto lm = A.lm[v];
+        const D2 pa = cur.pxy[v], pb = cur.pzt[v];
+        const float temp = u2f((uint32_t)((unsigned long long)__double_as_longlong(pb.y) & 0xffffffffu));
+        const V3<double> p{pa.x, pa.y, pb.x};
+        auto lm = cur.lm[v];
         r.x = p.x;
         r.y = p.y;
         r.z = p.z;
@@ -333,12 +335,18 @@ template <class R> __global__ void k_world_finish(Arrays<R> A, int mode) {
 }
 
 // Before the first step of a run: arm the run counter and test the stop condition (CUDA_Simulation checks it before every step).
-template <class R> __global__ void k_world_begin(Arrays<R> A, long long maxSteps, int useStop, int residentMode) {
+template <class R> __global__ void k_world_begin(Arrays<R> A, long long maxSteps, int useStop, int residentMode, int fusedMode) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= A.nWorlds)
         return;
     WorldD &W = A.worlds[w];
-    W.flags = (residentMode && W.residentClass > 0) ? (W.flags | WF_RESIDENT) : (W.flags & ~(uint32_t)WF_RESIDENT);
+    // residentMode 1: worlds that fit run in k_resident; fusedMode 1: the others run in k_fused (else in k_links + k_voxels)
+    uint32_t fl = W.flags & ~(uint32_t)(WF_RESIDENT | WF_FUSED);
+    if (residentMode && W.residentClass > 0)
+        fl |= WF_RESIDENT;
+    else if (fusedMode)
+        fl |= WF_FUSED;
+    W.flags = fl;
     W.runSteps = maxSteps;
     W.active = (!W.diverged && !W.stopped && maxSteps > 0 && W.nv > 0) ? 1 : 0;
     if (W.active && useStop && (W.flags & WF_STOP_FORMULA) && eval_formula(W.stop, world_vars(W, W.com[0], W.com[1], W.com[2])) > 0) {
@@ -353,6 +361,11 @@ template <class R> __device__ void compute_target_closeness(const Arrays<R> &A, 
         return;
     double Rr = W.maxDistPair * W.voxSize, ret = 0;
     int pairs = 0;
+    const StateSet<R> cur = cur_set(A, W.parity);
+    auto load_pos = [&](const Arrays<R> &, int v, float *, uint32_t *) {
+        const D2 a = cur.pxy[v], b = cur.pzt[v];
+        return V3<double>{a.x, a.y, b.x};
+    };
     for (int i = 0; i < W.nv; i++) {
         if (!A.vmats[A.vmat[W.voff + i]].isTarget)
             continue;
@@ -416,6 +429,8 @@ template <class R> __global__ void k_world_step(Arrays<R> A, int useStop, int *a
     WorldD &W = A.worlds[w];
     if (!W.active || (W.flags & WF_RESIDENT))
         return;
+    if (W.flags & WF_FUSED)
+        W.parity ^= 1; // k_fused has just written the other buffer set
     world_end_of_step(A, W, useStop);
     if (W.active && activeCount)
         atomicAdd(activeCount, 1);

@@ -15,7 +15,7 @@ import oracle_lib as O  # noqa: E402
 from gpuvoxels_b200 import worlds as W  # noqa: E402
 
 
-def compare(name, model, steps, precisions=(gv.FP64, gv.FP32), paths=(1, 2)):
+def compare(name, model, steps, precisions=(gv.FP64, gv.FP32), paths=(1, 2, 3)):
     ow = O.OracleWorld(model)
     t0 = time.time()
     ow.run(steps)
@@ -86,7 +86,7 @@ def main():
     compare("xeno1", gv.Model.from_vxa(W.xenobot_base_vxa(), W.xenobot_vxd(1)), 3000, precisions=(gv.FP32,))
     compare("pile", gv.Model.from_vxa(W.contact_pile_vxa()), 600)
     compare("cube12", gv.Model.from_vxa(W.cube_vxa(12)), 300)
-    compare("cube30", gv.Model.from_vxa(W.cube_vxa(30)), 100, paths=(1,))
+    compare("cube30", gv.Model.from_vxa(W.cube_vxa(30)), 100, paths=(1, 3))
 
     # batch throughput: many xenobot worlds
     for n in (64, 1024):
@@ -111,14 +111,15 @@ def main():
     # big body streaming throughput
     for n in (50, 100):
         m = gv.Model.from_vxa(W.cube_vxa(n))
-        ctx = gv.Context(0, gv.FP32)
-        ctx.set_option("path", 1)
-        ctx.upload([m])
-        ctx.run(20)
-        ctx.run(100)
-        ms, launches = ctx.timing()
-        print(f"cube{n} path1 fp32: 100 steps {ms:.1f} ms -> {ctx.total_voxel_steps() / ms * 1e3:.3e} voxel-steps/s", flush=True)
-        ctx.close()
+        for path in (1, 3):
+            ctx = gv.Context(0, gv.FP32)
+            ctx.set_option("path", path)
+            ctx.upload([m])
+            ctx.run(20)
+            ctx.run(100)
+            ms, launches = ctx.timing()
+            print(f"cube{n} path{path} fp32: 100 steps {ms:.1f} ms -> {ctx.total_voxel_steps() / ms * 1e3:.3e} voxel-steps/s", flush=True)
+            ctx.close()
 
 
 if __name__ == "__main__":
