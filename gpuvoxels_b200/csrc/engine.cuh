@@ -52,7 +52,8 @@ enum {
     WF_STOP_FORMULA = 128, WF_RESIDENT = 256, // WF_RESIDENT: stepped by k_resident in this run; the streaming kernels skip it
     WF_THERMAL = 512,  // temperature varies AND some material has alphaCTE != 0 (otherwise temperature is unobservable)
     WF_CAN_FAIL = 1024, // some link material has a failure strain
-    WF_FUSED = 2048     // stepped by k_fused in this run (state ping-pongs between the main and the alternate buffers)
+    WF_FUSED = 2048,    // stepped by k_fused in this run (state ping-pongs between the main and the alternate buffers)
+    WF_BRICK = 4096     // stepped by k_brick in this run (state lives in the brick-ordered buffer sets, kernels_brick.cuh)
 };
 struct WorldD {
     // static
@@ -63,7 +64,7 @@ struct WorldD {
     uint32_t flags;
     int32_t cycle; // int(TempPeriod/dt): COM/angle sampling period in steps (0 = never)
     float dt;
-    float pad0;
+    int32_t brickOk; // static: the world has brick tables (eligible for k_brick)
     double tempAmp, tempPeriod, voxSize, maxDistPair;
     // contact broad phase (k_resident): cell edge = largest watch distance of this world + skin
     double invCell, listR2; // 1/edge; edge^2 (a voxel's candidate list holds everything within the edge)

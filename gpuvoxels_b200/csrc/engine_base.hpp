@@ -25,8 +25,9 @@ class EngineBase {
     float lastMs = 0;
     int64_t lastLaunches = 0, lastVoxelSteps = 0;
     // options
-    int path = 0;         // 0 auto (resident + fused), 1 two-kernel streaming, 2 resident, 3 fused for all, 4 resident + two-kernel streaming
-    int brickDim[3] = {8, 8, 4}; // lattice cells per brick of the fused path
+    int path = 0;         // 0 auto (resident + brick/fused), 1 two-kernel streaming, 2 resident, 3 fused for all, 4 resident + two-kernel streaming,
+                          // 5 brick for every eligible world, fused for the rest (3 and 5 must be set before upload)
+    int brickDim[3] = {8, 8, 4}; // lattice cells per brick of the fused and brick paths (the brick path halves them until a brick fits)
     int recordPairs = 0;  // keep the collision pair list of the last step (parity tests)
     int chunk = 64;       // steps per CUDA-graph replay on the streaming path
     double dtOverride = 0;

@@ -8,12 +8,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "engine.cuh"
 #include "engine_base.hpp"
+#include "kernels_brick.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_resident.cuh"
 #include "kernels_stream.cuh"
@@ -109,8 +111,9 @@ template <class R> class Engine : public EngineBase {
     ContactTile *dTiles = nullptr;
     int *dActive = nullptr;
     int *hActive = nullptr; // pinned
-    cudaGraphExec_t graphExec = nullptr;
-    int graphChunk = 0, graphUseStop = -1, graphRecord = -1;
+    cudaGraphExec_t graphExec = nullptr; // the graph build_graph selected (owned by `graphs`)
+    std::map<int, cudaGraphExec_t> graphs;
+    int graphUseStop = -1, graphRecord = -1;
     bool anyCollision = false;
     std::vector<ResidentClass> classes; // k_resident size classes (kernels_resident.cuh)
     int numResident = 0;                // worlds that fit in shared memory (laid out first; streaming-only worlds follow)
@@ -121,12 +124,24 @@ template <class R> class Engine : public EngineBase {
     int fusedCapTab = 0, fusedCapOwn = 0, fusedBrick0 = 0; // fusedBrick0: first brick of the streaming-only worlds
     bool fusedAllWorlds = false;
     size_t fusedSmem = 0;
+    // brick path (kernels_brick.cuh): brick-ordered copy of the eligible streaming-only worlds (of every eligible world for path 5)
+    BrickArrays<R> BA{};
+    BrickCaps brickCaps{};
+    BrickLayout<R> brickLayout;
+    size_t brickSmem = 0;
+    bool brickLean = true;
+    int brickDimsUsed[3] = {0, 0, 0};
+    struct BrickHost {
+        std::vector<BrickB> bricks;
+        std::vector<int32_t> haloVox, haloLink, borig, lorig;
+        std::vector<LinkDesc> ldesc;
+        std::vector<uint32_t> bstat;
+    };
     cudaEvent_t evBegin = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     ~Engine() override {
-        if (graphExec)
-            cudaGraphExecDestroy(graphExec);
+        release_graphs();
         if (hActive)
             cudaFreeHost(hActive);
         if (ev0)
@@ -165,10 +180,7 @@ template <class R> class Engine : public EngineBase {
 
     int upload(const VX3B_WorldDesc *worlds, int n) override {
         CUDA_TRY(cudaSetDevice(device));
-        if (graphExec) {
-            cudaGraphExecDestroy(graphExec);
-            graphExec = nullptr;
-        }
+        release_graphs();
         bufs.clear();
         H.clear();
         hTiles.clear();
@@ -407,6 +419,7 @@ template <class R> class Engine : public EngineBase {
                 o.epsilonFail = m.epsilonFail;
                 float s1 = (float)d.voxel_mats[m.mat1].nomSize, s2 = (float)d.voxel_mats[m.mat2].nomSize;
                 o.area = 0.5f * (s1 * s1 + s2 * s2); // currentTransverseArea for nu == 0 (VX3_Link.cu:85-88, VX3_Voxel.cu:496-499)
+                o.matPair = (uint32_t)m.mat1 | ((uint32_t)m.mat2 << 16);
             }
             // voxels
             const bool vary = (W.flags & WF_VARY_TEMP) != 0;
@@ -532,6 +545,196 @@ template <class R> class Engine : public EngineBase {
             vmo += d.num_voxel_mats;
             lmo += d.num_link_mats;
         }
+
+        // ---- brick path plan (host only; kernels_brick.cuh): which worlds, brick tables, shared-memory fit -----------------------
+        BrickHost bh;
+        BA = BrickArrays<R>{};
+        brickLean = true;
+        {
+            std::vector<int> bw; // brick worlds in layout order
+            for (int oi = 0; oi < n; oi++) {
+                const int w = perm[oi];
+                const VX3B_WorldDesc &d = worlds[w];
+                const bool wanted = path == 5 || (path == 0 && pre[w].cls == 0);
+                if (!wanted || d.num_voxels == 0 || (pre[w].flags & (WF_COLLISION | WF_FORCE_FIELD)) || d.max_dist_in_voxel_lengths_to_count_as_pair != 0 ||
+                    d.num_voxel_mats > BRICK_MAX_VMATS || d.num_link_mats > BRICK_MAX_LMATS)
+                    continue;
+                bw.push_back(w);
+            }
+            int dims[3] = {brickDim[0], brickDim[1], brickDim[2]};
+            const size_t limit = std::min<size_t>((size_t)smemOptin, ((size_t)smemPerSm - 2048) / 2); // two CTAs per SM
+            while (!bw.empty()) {
+                bh = BrickHost{};
+                BrickCaps caps{0, 0, 0, 0, 1, 1};
+                bool ok = true;
+                std::vector<int32_t> slotOf, lslotOf, brickOf, local;
+                for (int w : bw) {
+                    const WorldHost &h = H[w];
+                    const WorldD &W = hW[w];
+                    caps.nvm = std::max(caps.nvm, W.nvm);
+                    caps.nlm = std::max(caps.nlm, W.nlm);
+                    int mn[3] = {1 << 30, 1 << 30, 1 << 30};
+                    for (int v = 0; v < h.nv; v++)
+                        for (int k = 0; k < 3; k++)
+                            mn[k] = std::min(mn[k], (int)(&lat[h.voff + v].x)[k]);
+                    int mx[2] = {-(1 << 30), -(1 << 30)};
+                    for (int v = 0; v < h.nv; v++)
+                        for (int k = 0; k < 2; k++)
+                            mx[k] = std::max(mx[k], (int)(&lat[h.voff + v].x)[k]);
+                    const int64_t nbx = (mx[0] - mn[0]) / dims[0] + 1, nby = (mx[1] - mn[1]) / dims[1] + 1;
+                    std::vector<std::pair<int64_t, int>> keyed(h.nv); // (brick key, voxel): creation order inside a brick = x fastest
+                    for (int v = 0; v < h.nv; v++) {
+                        const short4 c = lat[h.voff + v];
+                        keyed[v] = {(((int64_t)(c.z - mn[2]) / dims[2]) * nby + (c.y - mn[1]) / dims[1]) * nbx + (c.x - mn[0]) / dims[0], v};
+                    }
+                    std::sort(keyed.begin(), keyed.end());
+                    slotOf.assign(h.nv, -1);
+                    lslotOf.assign(h.nl, -1);
+                    brickOf.assign(h.nv, -1);
+                    local.assign(h.nv, -1);
+                    const size_t firstBrick = bh.bricks.size();
+                    // pass 1: brick-order slots of voxels and owned links
+                    for (size_t a = 0; a < keyed.size();) {
+                        size_t b = a;
+                        while (b < keyed.size() && keyed[b].first == keyed[a].first)
+                            b++;
+                        if (bh.borig.size() & 1) { // own runs start on an even slot (16-byte alignment of the 8-byte arrays)
+                            bh.borig.push_back(-1);
+                            bh.bstat.push_back(0);
+                        }
+                        BrickB B;
+                        memset(&B, 0, sizeof(B));
+                        B.world = w;
+                        B.v0 = (int)bh.borig.size();
+                        B.nOwn = (int)(b - a);
+                        for (size_t q = a; q < b; q++) {
+                            const int v = keyed[q].second, g = h.voff + v;
+                            slotOf[v] = (int)bh.borig.size();
+                            brickOf[v] = (int)bh.bricks.size();
+                            uint32_t mk = 0;
+                            for (int dir = 0; dir < 6; dir++)
+                                if (vlinks[(size_t)dir * nvTot + g] >= 0)
+                                    mk |= 1u << dir;
+                            bh.borig.push_back(g);
+                            bh.bstat.push_back((uint32_t)(vmat[g] - W.vmatOff) | (mk << 8) | (vext[g] >= 0 ? 1u << 14 : 0u));
+                            if (vext[g] >= 0)
+                                brickLean = false;
+                        }
+                        B.l0 = (int)bh.lorig.size();
+                        for (int axis = 0; axis < 3; axis++)
+                            for (size_t q = a; q < b; q++) {
+                                const int l = vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + keyed[q].second];
+                                if (l >= 0) {
+                                    lslotOf[l - h.loff] = (int)bh.lorig.size();
+                                    bh.lorig.push_back(l);
+                                }
+                            }
+                        B.nOwned = (int)bh.lorig.size() - B.l0;
+                        bh.bricks.push_back(B);
+                        a = b;
+                    }
+                    // pass 2: link descriptors (recomputed links first, then the owned run in slot order) and halo tables
+                    size_t a = 0;
+                    for (size_t bi = firstBrick; bi < bh.bricks.size(); bi++) {
+                        BrickB &B = bh.bricks[bi];
+                        const int nOwnPad = (B.nOwn + 1) & ~1;
+                        std::vector<int> halo; // world-local voxel index
+                        for (int i = 0; i < B.nOwn; i++)
+                            local[keyed[a + i].second] = i;
+                        auto local_of = [&](int v) {
+                            if (local[v] < 0) {
+                                local[v] = nOwnPad + (int)halo.size();
+                                halo.push_back(v);
+                            }
+                            return local[v];
+                        };
+                        auto mat_of = [&](int v) { return (uint32_t)(vmat[h.voff + v] - W.vmatOff); };
+                        if (bh.ldesc.size() & 1)
+                            bh.ldesc.push_back(LinkDesc{0, 0, 0, 0});
+                        B.descBeg = (int)bh.ldesc.size();
+                        B.haloLinkBeg = (int)bh.haloLink.size();
+                        for (int axis = 0; axis < 3; axis++)
+                            for (int i = 0; i < B.nOwn; i++) {
+                                const int v = keyed[a + i].second;
+                                const int l = vlinks[(size_t)(2 * axis) * nvTot + h.voff + v]; // v is the negative end
+                                if (l < 0)
+                                    continue;
+                                const int pos = lends[l].y - h.voff;
+                                if (brickOf[pos] == (int)bi)
+                                    continue; // owned by this brick
+                                LinkDesc k;
+                                k.a = (uint16_t)i;
+                                k.b = (uint16_t)local_of(pos);
+                                k.lmat = (uint16_t)((lmeta[l] >> 2) - (uint32_t)W.lmatOff);
+                                k.flags = (uint16_t)(axis | BD_NEG_OWN | (mat_of(v) << 4) | (mat_of(pos) << 8));
+                                bh.ldesc.push_back(k);
+                                bh.haloLink.push_back(lslotOf[l - h.loff]);
+                            }
+                        B.nHaloL = (int)bh.haloLink.size() - B.haloLinkBeg;
+                        for (int axis = 0; axis < 3; axis++)
+                            for (int i = 0; i < B.nOwn; i++) {
+                                const int v = keyed[a + i].second;
+                                const int l = vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + v]; // v is the positive end: owned
+                                if (l < 0)
+                                    continue;
+                                const int neg = lends[l].x - h.voff;
+                                LinkDesc k;
+                                k.a = (uint16_t)local_of(neg);
+                                k.b = (uint16_t)i;
+                                k.lmat = (uint16_t)((lmeta[l] >> 2) - (uint32_t)W.lmatOff);
+                                k.flags = (uint16_t)(axis | BD_POS_OWN | (brickOf[neg] == (int)bi ? BD_NEG_OWN : 0) | (mat_of(neg) << 4) | (mat_of(v) << 8));
+                                bh.ldesc.push_back(k);
+                            }
+                        B.haloBeg = (int)bh.haloVox.size();
+                        B.nHalo = (int)halo.size();
+                        for (int v : halo) {
+                            bh.haloVox.push_back(slotOf[v]);
+                            local[v] = -1;
+                        }
+                        for (int i = 0; i < B.nOwn; i++)
+                            local[keyed[a + i].second] = -1;
+                        a += B.nOwn;
+                        const int nl = B.nHaloL + B.nOwned;
+                        caps.own = std::max(caps.own, nOwnPad);
+                        caps.halo = std::max(caps.halo, B.nHalo);
+                        caps.owned = std::max(caps.owned, B.nOwned);
+                        caps.links = std::max(caps.links, (nl + 1) & ~1);
+                        if (nOwnPad + B.nHalo > 0xffff)
+                            ok = false;
+                    }
+                }
+                if (bh.borig.size() & 1) {
+                    bh.borig.push_back(-1);
+                    bh.bstat.push_back(0);
+                }
+                if (bh.ldesc.size() & 1)
+                    bh.ldesc.push_back(LinkDesc{0, 0, 0, 0});
+                brickLayout = BrickLayout<R>(caps);
+                brickSmem = brickLayout.total;
+                if (ok && brickSmem <= limit) {
+                    brickCaps = caps;
+                    for (int k = 0; k < 3; k++)
+                        brickDimsUsed[k] = dims[k];
+                    break;
+                }
+                int big = dims[0] >= dims[1] && dims[0] >= dims[2] ? 0 : dims[1] >= dims[2] ? 1 : 2;
+                if (dims[big] <= 1) { // cannot happen for lattice worlds; leave every world to k_fused
+                    bw.clear();
+                    bh = BrickHost{};
+                    break;
+                }
+                dims[big] = (dims[big] + 1) / 2;
+                brickLean = true;
+            }
+            for (int w : bw) {
+                hW[w].brickOk = 1;
+                if (pre[w].flags & (WF_VARY_TEMP | WF_THERMAL | WF_CILIA))
+                    brickLean = false;
+                for (int k = 0; k < hW[w].nvm; k++)
+                    if (vmats[hW[w].vmatOff + k].fixed)
+                        brickLean = false;
+            }
+        }
         // ---- device
         if (!stream) {
             CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -605,7 +808,7 @@ template <class R> class Engine : public EngineBase {
         CUDA_TRY(cudaGetLastError());
         // ---- fused tile path: cut the streaming-only worlds (all worlds for path 3) into bricks --------------------------------
         FA = FusedArrays{};
-        fusedAllWorlds = path == 3;
+        fusedAllWorlds = path == 3 || path == 5;
         {
             std::vector<BrickD> bricks;
             std::vector<int32_t> bvox;
@@ -620,6 +823,8 @@ template <class R> class Engine : public EngineBase {
                 const bool streamingOnly = pre[w].cls == 0;
                 if (!streamingOnly && !fusedAllWorlds)
                     continue;
+                if (hW[w].brickOk)
+                    continue; // stepped by k_brick
                 if (streamingOnly && fusedBrick0 < 0)
                     fusedBrick0 = (int)bricks.size();
                 const WorldHost &h = H[w];
@@ -735,6 +940,41 @@ template <class R> class Engine : public EngineBase {
                             bricks.size(), BX, BY, BZ, fusedCapTab, fusedCapOwn, blinks.size(), 100.0 * (blinks.size() - (double)nlTot) / std::max<size_t>(nlTot, 1), fusedSmem);
             }
         }
+        // ---- brick path: tables and the two brick-ordered buffer sets
+        if (!bh.bricks.empty()) {
+            BrickB *dB = nullptr;
+            int32_t *dHV = nullptr, *dHL = nullptr, *dVO = nullptr, *dLO = nullptr;
+            LinkDesc *dD = nullptr;
+            uint32_t *dS = nullptr;
+            if ((rc = dalloc(&dB, bh.bricks.size(), bh.bricks.data())) != VX3B_OK || (rc = dalloc(&dHV, bh.haloVox.size(), bh.haloVox.data())) != VX3B_OK ||
+                (rc = dalloc(&dHL, bh.haloLink.size(), bh.haloLink.data())) != VX3B_OK || (rc = dalloc(&dVO, bh.borig.size(), bh.borig.data())) != VX3B_OK ||
+                (rc = dalloc(&dLO, bh.lorig.size(), bh.lorig.data())) != VX3B_OK || (rc = dalloc(&dD, bh.ldesc.size(), bh.ldesc.data())) != VX3B_OK ||
+                (rc = dalloc(&dS, bh.bstat.size(), bh.bstat.data())) != VX3B_OK)
+                return rc;
+            BA.nBricks = (int)bh.bricks.size();
+            BA.bricks = dB;
+            BA.haloVox = dHV;
+            BA.haloLink = dHL;
+            BA.borig = dVO;
+            BA.lorig = dLO;
+            BA.ldesc = dD;
+            BA.bstat = dS;
+            BA.nvSlots = (int)bh.borig.size();
+            BA.nlSlots = (int)bh.lorig.size();
+            for (int k = 0; k < 2; k++) {
+                StateSet<R> &S = BA.set[k];
+                if ((rc = dalloc(&S.pxy, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.pzt, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.orient, BA.nvSlots)) != VX3B_OK ||
+                    (rc = dalloc(&S.lm, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.am, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.lpos2, BA.nlSlots)) != VX3B_OK ||
+                    (rc = dalloc(&S.la1, BA.nlSlots)) != VX3B_OK || (rc = dalloc(&S.la2, BA.nlSlots)) != VX3B_OK)
+                    return rc;
+            }
+            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brickSmem));
+            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brickSmem));
+            if (getenv("VX3B_DEBUG"))
+                fprintf(stderr, "[vx3b] brick path: %zu bricks (%dx%dx%d), own <= %d, halo <= %d, owned links <= %d, links <= %d (%.1f%% recomputed), %zu B shared memory, %s\n",
+                        bh.bricks.size(), brickDimsUsed[0], brickDimsUsed[1], brickDimsUsed[2], brickCaps.own, brickCaps.halo, brickCaps.owned, brickCaps.links,
+                        100.0 * (double)bh.haloLink.size() / std::max<size_t>(bh.lorig.size(), 1), brickSmem, brickLean ? "lean" : "full");
+        }
         // ---- k_resident size classes: one launch + stream per class
         if (vStream0 < 0) {
             vStream0 = (int)nvTot;
@@ -791,16 +1031,25 @@ template <class R> class Engine : public EngineBase {
             F.bricks += b0;
             if (FA.nBricks > b0)
                 k_fused<R><<<(unsigned)(FA.nBricks - b0), 256, fusedSmem, stream>>>(A, F, fusedCapTab, fusedCapOwn);
+            if (BA.nBricks > 0) {
+                if (brickLean)
+                    k_brick<R, true><<<(unsigned)BA.nBricks, 256, brickSmem, stream>>>(A, BA, brickLayout);
+                else
+                    k_brick<R, false><<<(unsigned)BA.nBricks, 256, brickSmem, stream>>>(A, BA, brickLayout);
+            }
         } else if (A.nvTot > v0)
             k_voxels<R><<<vb, 256, 0, stream>>>(A, v0);
         k_world_step<R><<<wb, 128, 0, stream>>>(A, useStop, dActive);
     }
+    // one instantiated graph per chunk length (a run of 200 steps replays the 64-step graph three times and an 8-step one once;
+    // re-capturing on every change of length costs milliseconds)
     int build_graph(int steps, int useStop, bool mixed, bool fused) {
-        if (graphExec && graphChunk == steps && graphUseStop == useStop && graphRecord == recordPairs && graphMixed == (int)mixed && graphFused == (int)fused)
+        if (graphUseStop != useStop || graphRecord != recordPairs || graphMixed != (int)mixed || graphFused != (int)fused)
+            release_graphs();
+        auto it = graphs.find(steps);
+        if (it != graphs.end()) {
+            graphExec = it->second;
             return VX3B_OK;
-        if (graphExec) {
-            cudaGraphExecDestroy(graphExec);
-            graphExec = nullptr;
         }
         cudaGraph_t g;
         CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
@@ -812,12 +1061,18 @@ template <class R> class Engine : public EngineBase {
         CUDA_TRY(cudaStreamEndCapture(stream, &g));
         CUDA_TRY(cudaGraphInstantiate(&graphExec, g, 0));
         cudaGraphDestroy(g);
-        graphChunk = steps;
+        graphs[steps] = graphExec;
         graphUseStop = useStop;
         graphRecord = recordPairs;
         graphMixed = (int)mixed;
         graphFused = (int)fused;
         return VX3B_OK;
+    }
+    void release_graphs() {
+        for (auto &kv : graphs)
+            cudaGraphExecDestroy(kv.second);
+        graphs.clear();
+        graphExec = nullptr;
     }
 
     int run_streaming(int64_t maxSteps, int useStop, bool mixed, bool fused) {
@@ -828,7 +1083,8 @@ template <class R> class Engine : public EngineBase {
             if (rc != VX3B_OK)
                 return rc;
             CUDA_TRY(cudaGraphLaunch(graphExec, stream));
-            lastLaunches += (int64_t)steps * (launches_per_step() - (fused ? 1 : 0)) + 1;
+            const int fusedLaunches = (FA.nBricks > (mixed ? fusedBrick0 : 0) ? 1 : 0) + (BA.nBricks > 0 ? 1 : 0);
+            lastLaunches += (int64_t)steps * (fused ? launches_per_step() - 2 + fusedLaunches : launches_per_step()) + 1;
             done += steps;
             CUDA_TRY(cudaMemcpyAsync(hActive, dActive, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
@@ -878,17 +1134,22 @@ template <class R> class Engine : public EngineBase {
             set_error("vx3b_batch_run: resident path requested but " + std::to_string(H.size() - numResident) + " world(s) do not fit in shared memory");
             return VX3B_ERR_ARG;
         }
-        if (path == 3 && !fusedAllWorlds) {
-            set_error("vx3b_batch_run: the fused path for every world must be selected (option path = 3) before vx3b_batch_upload");
+        if ((path == 3 || path == 5) && !fusedAllWorlds) {
+            set_error("vx3b_batch_run: the fused / brick path for every world must be selected (option path = 3 or 5) before vx3b_batch_upload");
             return VX3B_ERR_ARG;
         }
         if (recordPairs) // the pair list is that of the last step of a fixed-length run (W.runSteps == 1)
             CUDA_TRY(cudaMemsetAsync(A.pairCount, 0, sizeof(int), stream));
         const bool resident = (path == 0 || path == 2 || path == 4) && numResident > 0;
-        const bool streaming = path == 1 || path == 3 || numResident != (int)H.size();
-        const bool fused = streaming && (path == 0 || path == 3) && FA.nBricks > 0;
+        const bool streaming = path == 1 || path == 3 || path == 5 || numResident != (int)H.size();
+        const bool fused = streaming && (path == 0 || path == 3 || path == 5) && (FA.nBricks > 0 || BA.nBricks > 0);
         k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)maxSteps, useStop, resident ? 1 : 0, fused ? 1 : 0);
         lastLaunches++;
+        const unsigned nbb = (unsigned)((std::max(BA.nvSlots, BA.nlSlots) + 255) / 256);
+        if (fused && BA.nBricks > 0) { // API-order state -> brick order
+            k_brick_pack<R><<<nbb, 256, 0, stream>>>(A, BA);
+            lastLaunches++;
+        }
         if (resident && (rc = run_resident(maxSteps, useStop)) != VX3B_OK)
             return rc;
         if (streaming && (rc = run_streaming(maxSteps, useStop, resident, fused)) != VX3B_OK)
@@ -897,9 +1158,16 @@ template <class R> class Engine : public EngineBase {
             return rc;
         if (fused) { // bring every world's state back to the main buffers
             const unsigned nb = (unsigned)((std::max(A.nvTot, A.nlTot) + 255) / 256);
-            k_unparity<R><<<nb, 256, 0, stream>>>(A, 0, 0);
+            if (FA.nBricks > 0) {
+                k_unparity<R><<<nb, 256, 0, stream>>>(A, 0, 0);
+                lastLaunches++;
+            }
+            if (BA.nBricks > 0) {
+                k_brick_unpack<R><<<nbb, 256, 0, stream>>>(A, BA);
+                lastLaunches++;
+            }
             k_clear_parity<R><<<wb, 128, 0, stream>>>(A);
-            lastLaunches += 2;
+            lastLaunches++;
         }
         if (A.nvTot) {
             k_reduce_com<R><<<(unsigned)((A.nvTot + 255) / 256), 256, 0, stream>>>(A, 1);

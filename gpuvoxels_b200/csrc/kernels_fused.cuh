@@ -69,7 +69,7 @@ template <class R> __global__ void __launch_bounds__(256, 2) k_fused(Arrays<R> A
     extern __shared__ __align__(16) unsigned char smem[];
     const BrickD B = FA.bricks[blockIdx.x];
     WorldD &W = A.worlds[B.world];
-    if (!W.active || (W.flags & WF_RESIDENT))
+    if (!W.active || !(W.flags & WF_FUSED))
         return;
     const StateSet<R> src = cur_set(A, W.parity), dst = cur_set(A, W.parity ^ 1);
     const FusedLayout<R> L(capTab, capOwn);
@@ -252,14 +252,14 @@ template <class R> __global__ void __launch_bounds__(256, 2) k_fused(Arrays<R> A
 template <class R> __global__ void k_unparity(Arrays<R> A, int v0, int l0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = v0 + i, l = l0 + i;
-    if (v < A.nvTot && A.worlds[A.vworld[v]].parity) {
+    if (v < A.nvTot && A.worlds[A.vworld[v]].parity && (A.worlds[A.vworld[v]].flags & WF_FUSED)) {
         A.pxy[v] = A.alt.pxy[v];
         A.pzt[v] = A.alt.pzt[v];
         A.orient[v] = A.alt.orient[v];
         A.lm[v] = A.alt.lm[v];
         A.am[v] = A.alt.am[v];
     }
-    if (l < A.nlTot && A.worlds[A.lworld[l]].parity) {
+    if (l < A.nlTot && A.worlds[A.lworld[l]].parity && (A.worlds[A.lworld[l]].flags & WF_FUSED)) {
         A.lpos2[l] = A.alt.lpos2[l];
         A.la1[l] = A.alt.la1[l];
         A.la2[l] = A.alt.la2[l];

@@ -285,20 +285,57 @@ template <class R> __global__ void __launch_bounds__(256) k_voxels(Arrays<R> A, 
 
 // ---- centre of mass / distance reduction (initialisation and end of run) ------------------------------------
 template <class R> __global__ void __launch_bounds__(256) k_reduce_com(Arrays<R> A, int withDistance) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= A.nvTot)
-        return;
-    const int w = A.vworld[v];
+    __shared__ double part[8][5];
+    const int first = blockIdx.x * blockDim.x, v = first + threadIdx.x;
+    const bool in = v < A.nvTot;
+    const int w = A.vworld[in ? v : A.nvTot - 1];
     WorldD &W = A.worlds[w];
-    const DVoxMat &m = A.vmats[A.vmat[v]];
-    V3<double> p = load_pos(A, v, nullptr, nullptr);
-    double mass = m.mass;
-    world_accumulate(W.comAcc, w, m.isMeasured != 0, p.x * mass, p.y * mass, p.z * mass, mass);
-    if (withDistance && m.isMeasured) {
-        D2 a = A.ipxy[v];
-        double dz = p.z - A.ipz[v], dx = p.x - a.x, dy = p.y - a.y;
-        atomicAdd(&W.distAcc, sqrt(dx * dx + dy * dy + dz * dz));
+    double x = 0, y = 0, z = 0, mass = 0, dist = 0;
+    bool measured = false;
+    if (in) {
+        const DVoxMat &m = A.vmats[A.vmat[v]];
+        measured = m.isMeasured != 0;
+        V3<double> p = load_pos(A, v, nullptr, nullptr);
+        mass = m.mass;
+        x = p.x * mass, y = p.y * mass, z = p.z * mass;
+        if (withDistance && measured) {
+            D2 a = A.ipxy[v];
+            double dz = p.z - A.ipz[v], dx = p.x - a.x, dy = p.y - a.y;
+            dist = sqrt(dx * dx + dy * dy + dz * dz);
+        }
     }
+    // a block inside one world (worlds are contiguous): shuffle + shared-memory reduction, five atomics per block
+    if (A.vworld[first] == A.vworld[min(first + (int)blockDim.x, A.nvTot) - 1]) {
+        if (!measured)
+            x = y = z = mass = 0;
+        for (int o = 16; o > 0; o >>= 1) {
+            x += __shfl_xor_sync(0xffffffffu, x, o);
+            y += __shfl_xor_sync(0xffffffffu, y, o);
+            z += __shfl_xor_sync(0xffffffffu, z, o);
+            mass += __shfl_xor_sync(0xffffffffu, mass, o);
+            dist += __shfl_xor_sync(0xffffffffu, dist, o);
+        }
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) {
+            part[warp][0] = x, part[warp][1] = y, part[warp][2] = z, part[warp][3] = mass, part[warp][4] = dist;
+        }
+        __syncthreads();
+        if (threadIdx.x < 5) {
+            double s = 0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++)
+                s += part[k][threadIdx.x];
+            if (threadIdx.x < 4)
+                atomicAdd(W.comAcc + threadIdx.x, s);
+            else if (withDistance)
+                atomicAdd(&W.distAcc, s);
+        }
+        return;
+    }
+    if (!in)
+        return;
+    world_accumulate(W.comAcc, w, measured, x, y, z, mass);
+    if (withDistance && measured)
+        atomicAdd(&W.distAcc, dist);
 }
 
 VXD void finish_com(WorldD &W) {
@@ -340,12 +377,13 @@ template <class R> __global__ void k_world_begin(Arrays<R> A, long long maxSteps
     if (w >= A.nWorlds)
         return;
     WorldD &W = A.worlds[w];
-    // residentMode 1: worlds that fit run in k_resident; fusedMode 1: the others run in k_fused (else in k_links + k_voxels)
-    uint32_t fl = W.flags & ~(uint32_t)(WF_RESIDENT | WF_FUSED);
+    // residentMode 1: worlds that fit run in k_resident; fusedMode 1: the others run in k_brick when they have brick tables,
+    // else in k_fused (fusedMode 0: in k_links + k_voxels)
+    uint32_t fl = W.flags & ~(uint32_t)(WF_RESIDENT | WF_FUSED | WF_BRICK);
     if (residentMode && W.residentClass > 0)
         fl |= WF_RESIDENT;
     else if (fusedMode)
-        fl |= WF_FUSED;
+        fl |= W.brickOk ? WF_BRICK : WF_FUSED;
     W.flags = fl;
     W.runSteps = maxSteps;
     W.active = (!W.diverged && !W.stopped && maxSteps > 0 && W.nv > 0) ? 1 : 0;
@@ -429,8 +467,8 @@ template <class R> __global__ void k_world_step(Arrays<R> A, int useStop, int *a
     WorldD &W = A.worlds[w];
     if (!W.active || (W.flags & WF_RESIDENT))
         return;
-    if (W.flags & WF_FUSED)
-        W.parity ^= 1; // k_fused has just written the other buffer set
+    if (W.flags & (WF_FUSED | WF_BRICK))
+        W.parity ^= 1; // k_fused / k_brick has just written the other buffer set
     world_end_of_step(A, W, useStop);
     if (W.active && activeCount)
         atomicAdd(activeCount, 1);

@@ -36,8 +36,22 @@ template <class R> VXD V3<R> operator*(R f, V3<R> a) { return {f * a.x, f * a.y,
 template <class R> VXD R dot(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 template <class R> VXD R len2(V3<R> a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
 
-VXD float vsqrt(float x) { return sqrtf(x); }
+// float build: approximate sqrt / division / reciprocal (MUFU + one multiply, <= 2 ulp).  The IEEE forms cost a range check and,
+// whenever an operand is zero or tiny - exactly what a body at rest feeds them - a ~100-instruction slow path (profiles/r01g).
+VXD float vsqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 VXD double vsqrt(double x) { return sqrt(x); }
+VXD float vdiv(float a, float b) { return __fdividef(a, b); }
+VXD double vdiv(double a, double b) { return a / b; }
+VXD float vrcp(float a) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+VXD double vrcp(double a) { return 1.0 / a; }
 VXD float vabs(float x) { return fabsf(x); }
 VXD double vabs(double x) { return fabs(x); }
 VXD float vacos(float x) { return acosf(x); }
@@ -86,11 +100,11 @@ VXD V3<float> rotvec(Qt<float> q) {
     if (s2 < 2.4e-3f)
         k = 2.0f + s2 * (0.33333334f + s2 * 0.15f); // 2*asin(s)/s = 2 + s^2/3 + 3 s^4/20 + ...
     else {
-        float s = sqrtf(s2);
+        float s = vsqrt(s2);
         float half = (q.w > 0.70710678f) ? asinf(s) : acosf(fminf(fmaxf(q.w, -1.0f), 1.0f));
         if (q.w < -0.70710678f) // stay on the reference's branch of acos
             half = acosf(fmaxf(q.w, -1.0f));
-        k = 2.0f * half / s;
+        k = vdiv(2.0f * half, s);
     }
     return {k * q.x, k * q.y, k * q.z};
 }
@@ -117,10 +131,10 @@ VXD Qt<float> quat_from_rotvec(V3<float> in) {
         w = 1.0f - m2 * (0.5f - m2 * 0.041666668f);
         s = 1.0f - m2 * (0.16666667f - m2 * 0.0083333338f);
     } else {
-        float m = sqrtf(m2), sn, cs;
+        float m = vsqrt(m2), sn, cs;
         sincosf(m, &sn, &cs);
         w = cs;
-        s = sn / m;
+        s = vdiv(sn, m);
     }
     return {w, th.x * s, th.y * s, th.z * s};
 }
@@ -130,7 +144,7 @@ template <class R> VXD void quat_to_pos_x(Qt<R> &q, V3<R> from) {
     if (from.x == R(0) && from.y == R(0) && from.z == R(0))
         return;
     const R SMALL = R(1.732e-2);
-    R yox = from.y / from.x, zox = from.z / from.x;
+    R yox = vdiv(from.y, from.x), zox = vdiv(from.z, from.x);
     if (yox < SMALL && yox > -SMALL && zox < SMALL && zox > -SMALL) {
         q.x = R(0);
         q.y = R(0.5) * zox;
@@ -141,7 +155,7 @@ template <class R> VXD void quat_to_pos_x(Qt<R> &q, V3<R> from) {
     R l = vsqrt(len2(from));
     V3<R> n = from;
     if (l > R(0)) {
-        R inv = R(1) / l;
+        R inv = vrcp(l);
         n = {inv * from.x, inv * from.y, inv * from.z};
     }
     R theta = vacos(n.x);
@@ -149,7 +163,7 @@ template <class R> VXD void quat_to_pos_x(Qt<R> &q, V3<R> from) {
         q = {R(0), R(0), R(1), R(0)};
         return;
     }
-    R axisMagInv = R(1) / vsqrt(n.z * n.z + n.y * n.y);
+    R axisMagInv = vrcp(vsqrt(n.z * n.z + n.y * n.y));
     R sn, cs;
     vsincos(R(0.5) * theta, &sn, &cs);
     q.w = cs;
@@ -187,6 +201,7 @@ struct DVoxMat { // per voxel material, pre-multiplied where the reference multi
 };
 struct DLinkMat {
     float E, a2, b1, b2, b3, sqA1, sqA2xIp, sqB1, sqB2xFMp, sqB3xIp, epsilonFail, area; // area: currentTransverseArea (nu == 0)
+    uint32_t matPair; // world-local voxel materials the link material combines: mat1 | mat2 << 16
 };
 
 // link history flags
@@ -215,15 +230,33 @@ VXD double base_size_average(const DVoxMat &m, float temp) {
 // One link: orientLink + updateForces (VX3/VX3_Link.cu:90-218, updateStrain :220-231 linear / nu == 0 branch).
 //   dpos    = p₊ − p₋ (double, global frame); qn/qp = end orientations; restLen from both ends' temperatures
 //   dmN/dmP = dampingMultiplier of the negative/positive end voxel (2*sqrtMass*zetaInternal/previousDt)
-template <class R>
-VXD void link_update(const DLinkMat &m, int axis, V3<double> dpos, double nomLen, Qt<R> qn, Qt<R> qp, double restLen, float dmN, float dmP,
-                     LinkHist<R> &h, LinkForces<R> &out) {
+// lengths of one link in the arithmetic type: the nominal lattice spacing stays double (it is subtracted from a double position
+// difference), the rest are what the float formulation needs; constant per link material while sizes do not change
+template <class R> struct LinkLen {
+    double nomLen;
+    R rest, nomMinusRest, invRest; // (R)restLen, (R)(nomLen - restLen), 1/rest (float build only)
+};
+template <class R> VXD LinkLen<R> link_len(double nomLen, double restLen) {
+    LinkLen<R> l;
+    l.nomLen = nomLen;
+    l.rest = (R)restLen;
+    l.nomMinusRest = (R)(nomLen - restLen);
+    l.invRest = vrcp(l.rest);
+    return l;
+}
+// AXIS >= 0: the link axis is a compile-time constant (the caller dispatches once per link; the seven swizzles fold away);
+// AXIS == -1: run-time axis
+template <class R, int AXIS = -1>
+VXD void link_update(const DLinkMat &m, int axisRt, V3<double> dpos, const LinkLen<R> len, Qt<R> qn, Qt<R> qp, float dmN, float dmP, LinkHist<R> &h,
+                     LinkForces<R> &out) {
+    const int axis = AXIS >= 0 ? AXIS : axisRt;
+    const double nomLen = len.nomLen;
     const V3<R> oldPos2 = h.pos2, oldA1 = h.a1v, oldA2 = h.a2v;
     Qt<R> q1 = to_axis_x(qn, axis), q2 = to_axis_x(qp, axis);
     Qt<R> total = qconj(q1);
     q2 = qmul(total, q2);
     V3<R> d; // end-to-end vector in the negative end's frame, link axis on +X
-    R rest = (R)restLen;
+    const R rest = len.rest;
     R dxMinusRest; // d.x - restLen, formed without cancellation in float
     if constexpr (sizeof(R) == 8) {
         d = qrot(total, to_axis_x(V3<R>{dpos.x, dpos.y, dpos.z}, axis));
@@ -239,13 +272,15 @@ VXD void link_update(const DLinkMat &m, int axis, V3<double> dpos, double nomLen
         R cy = R(2) * (q1.x * q1.y - q1.w * q1.z);
         R cz = R(2) * (q1.x * q1.z + q1.w * q1.y);
         d = {er.x + L * cx + L, er.y + L * cy, er.z + L * cz};
-        dxMinusRest = er.x + L * cx + (R)(nomLen - restLen);
+        dxMinusRest = er.x + L * cx + len.nomMinusRest;
     }
     q1 = {R(1), R(0), R(0), R(0)};
-    float smallTurn = (float)((vabs(d.z) + vabs(d.y)) / d.x);
-    float extendPerc = (float)vabs(dxMinusRest / rest); // |1 - d.x/restLen|
+    float smallTurn = (float)vdiv(vabs(d.z) + vabs(d.y), d.x);
+    float extendPerc; // |1 - d.x/restLen|
     if constexpr (sizeof(R) == 8)
         extendPerc = (float)vabs(R(1) - d.x / rest);
+    else
+        extendPerc = vabs(dxMinusRest * len.invRest);
     const float HYST = 1.2f, BEND = 0.05f, EXT = 0.50f; // VoxCAD/src/VX2/include/types.h:57-59
     bool small = h.flags & LF_SMALL_ANGLE;
     bool valid = h.flags & LF_VEL_VALID;
@@ -271,7 +306,11 @@ VXD void link_update(const DLinkMat &m, int axis, V3<double> dpos, double nomLen
     h.a1v = th1;
     h.a2v = th2;
 
-    float eps = (float)(d.x / rest);
+    float eps;
+    if constexpr (sizeof(R) == 8)
+        eps = (float)(d.x / rest);
+    else
+        eps = d.x * len.invRest;
     out.strain = eps;
     if (eps > h.maxStrain)
         h.maxStrain = eps;
@@ -309,6 +348,11 @@ VXD void link_update(const DLinkMat &m, int axis, V3<double> dpos, double nomLen
     out.mNeg = to_axis_original(MN, axis);
     out.mPos = to_axis_original(MP, axis);
     h.flags = (small ? LF_SMALL_ANGLE : 0) | (valid ? LF_VEL_VALID : 0);
+}
+template <class R>
+VXD void link_update(const DLinkMat &m, int axis, V3<double> dpos, double nomLen, Qt<R> qn, Qt<R> qp, double restLen, float dmN, float dmP,
+                     LinkHist<R> &h, LinkForces<R> &out) {
+    link_update<R, -1>(m, axis, dpos, link_len<R>(nomLen, restLen), qn, qp, dmN, dmP, h, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -443,7 +487,7 @@ VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt 
             } else {
                 R hl = vsqrt(vel.x * vel.x + vel.y * vel.y);
                 if (hl > R(0)) {
-                    R k = (R)(m.muKinetic * normalForce) * (R(1) / hl);
+                    R k = (R)(m.muKinetic * normalForce) * vrcp(hl);
                     F.x -= k * vel.x;
                     F.y -= k * vel.y;
                 }

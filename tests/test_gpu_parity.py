@@ -18,7 +18,7 @@ from gpuvoxels_b200 import worlds as W
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
-STREAM, RESIDENT, FUSED = 1, 2, 3
+STREAM, RESIDENT, FUSED, BRICK = 1, 2, 3, 5
 
 
 def gpu_run(models, steps, precision, path, use_stop=False, **opts):
@@ -43,7 +43,7 @@ def pos_err(model, got, ref):
 KATS = kats.all_kats()
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 @pytest.mark.parametrize("precision,tol", [(gv.FP64, 0.0), (gv.FP32, 2e-3)])
 @pytest.mark.parametrize("name,case", KATS, ids=[n for n, _ in KATS])
 def test_reference_kats_through_the_c_abi(name, case, precision, tol, path):
@@ -53,7 +53,7 @@ def test_reference_kats_through_the_c_abi(name, case, precision, tol, path):
     ctx.close()
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 def test_fp64_matches_oracle_over_1000_steps(example_vxa, path):
     model = gv.Model.from_vxa(example_vxa)  # verbatim: VX3 semantics, collisions on (no pairs form in 1000 steps), actuation on
     want = O.OracleWorld(model)
@@ -68,7 +68,7 @@ def test_fp64_matches_oracle_over_1000_steps(example_vxa, path):
     ctx.close()
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 @pytest.mark.parametrize("maker,steps", [(lambda: (W.small_block_vxa(), None), 2000), (lambda: (W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(4)), 1000),
                                          (lambda: (open(os.path.join(ROOT, "tests", "data", "example.vxa")).read(), None), 1000)])
 def test_fp32_matches_oracle_collision_free(maker, steps, path):
@@ -85,7 +85,7 @@ def test_fp32_matches_oracle_collision_free(maker, steps, path):
 
 
 @pytest.mark.parametrize("name", ["example_vx2_1000", "example_vx3_1000", "small_vx3_2000"])
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 def test_fp64_matches_reference_golden_vectors(name, path):
     """CUDA fp64 directly against outputs of the unmodified reference CPU library (tests/golden/make_golden.py)."""
     from golden.make_golden import CASES
@@ -104,7 +104,7 @@ def test_fp64_matches_reference_golden_vectors(name, path):
     ctx.close()
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 @pytest.mark.parametrize("maker,steps,precision", [
     (lambda: (W.contact_pile_vxa(k=2, cube=3), None), 300, gv.FP64),
     (lambda: (W.xenobot_base_vxa(), W.xenobot_vxd(7)), 500, gv.FP64),
@@ -123,7 +123,7 @@ def test_collision_pair_set_is_bit_exact(maker, steps, precision, path):
     ctx.close()
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 @pytest.mark.parametrize("precision,tol", [(gv.FP64, 1e-5), (gv.FP32, 1e-3)])
 def test_batch_of_ragged_worlds(path, precision, tol):
     """Worlds of different sizes, materials and features in one launch; each must equal its own oracle run."""
@@ -173,7 +173,7 @@ def test_mixed_batch_resident_and_streaming_worlds():
     ctx.close()
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 def test_stop_condition_fitness_and_results(path):
     models = [gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=0.2), W.xenobot_vxd(i)) for i in (12, 7, 15)]
     ctx = gpu_run(models, 1000000, gv.FP64, path, use_stop=True)
@@ -194,7 +194,7 @@ def test_fitness_within_one_percent_on_contact_heavy_run():
     model = gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=1.0), W.xenobot_vxd(15))
     want = O.OracleWorld(model)
     want.run(1000000, use_stop_formula=True)
-    for path in (STREAM, RESIDENT, FUSED):
+    for path in (STREAM, RESIDENT, FUSED, BRICK):
         ctx = gpu_run([model], 1000000, gv.FP32, path, use_stop=True)
         r, rr = ctx.results()[0], want.result()
         assert r.steps == rr.steps
@@ -217,7 +217,7 @@ def test_million_voxel_body_properties():
     model = gv.Model.from_vxa(W.cube_vxa(n))
     states = []
     for prec in (gv.FP32, gv.FP32, gv.FP64):
-        ctx = gpu_run([model], steps, prec, FUSED)
+        ctx = gpu_run([model], steps, prec, 0)  # automatic: a body this size goes to the brick path
         states.append(ctx.read_state(0))
         r = ctx.results()[0]
         assert r.steps == steps and r.diverged == 0
@@ -237,6 +237,31 @@ def test_million_voxel_body_properties():
     c = (n - 1) * 0.01 / 2
     assert abs(r.current_com[0] - c) < 1e-6 and abs(r.current_com[1] - c) < 1e-6
     assert abs((r.current_com[2] - r.initial_com[2]) - dz64.mean()) < 1e-9
+
+
+@pytest.mark.parametrize("brick", [(8, 8, 4), (3, 2, 5), (16, 1, 1)])
+def test_brick_path_equals_fused_path_bit_for_bit_in_fp64(brick):
+    """Same arithmetic, different data layout (brick-ordered state + bulk copies vs gathered tables): the fp64 build is
+    compiled without FMA contraction, so the two paths must agree to the last bit — on ragged worlds cut into several
+    bricks (table construction, halo recompute, alignment padding), over several runs (pack / unpack round trips)."""
+    models = [gv.Model.from_vxa(W.cube_vxa(11)), gv.Model.from_vxa(W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(9)),
+              gv.Model.from_vxa(W.small_block_vxa()), kats.temperature(5.0, 2.55e-5)[0], gv.Model.from_vxa(W.cube_vxa(1))]
+    opts = dict(brick_x=brick[0], brick_y=brick[1], brick_z=brick[2])
+    a, b = gpu_run(models, 150, gv.FP64, FUSED, **opts), gpu_run(models, 150, gv.FP64, BRICK, **opts)
+    for rounds in range(2):
+        for i in range(len(models)):
+            sa, sb = a.read_state(i), b.read_state(i)
+            for k in ("pos", "orient", "linMom", "angMom"):
+                assert np.array_equal(sa[k], sb[k]), (i, k, rounds)
+            la, lb = a.read_links(i), b.read_links(i)
+            for k in ("pos2", "angle1v", "angle2v", "flags"):
+                assert np.array_equal(la[k], lb[k]), (i, k, rounds)
+            ra, rb = a.results()[i], b.results()[i]
+            assert ra.steps == rb.steps and np.allclose(ra.current_com, rb.current_com, rtol=1e-12, atol=0)  # sampled COM: atomics, order varies
+        a.run(37)
+        b.run(37)
+    a.close()
+    b.close()
 
 
 def test_job_run_writes_the_reference_report_layout():
