@@ -131,9 +131,11 @@ template <class R> class Engine : public EngineBase {
     size_t brickSmem = 0;
     bool brickLean = true;
     int brickDimsUsed[3] = {0, 0, 0};
+    int brickGrid = 0, brickThreads = 256;
     struct BrickHost {
         std::vector<BrickB> bricks;
-        std::vector<int32_t> haloVox, haloLink, borig, lorig;
+        std::vector<int32_t> glist, borig, lorig;
+        size_t recomputed = 0;
         std::vector<LinkDesc> ldesc;
         std::vector<uint32_t> bstat;
     };
@@ -562,7 +564,8 @@ template <class R> class Engine : public EngineBase {
                 bw.push_back(w);
             }
             int dims[3] = {brickDim[0], brickDim[1], brickDim[2]};
-            const size_t limit = std::min<size_t>((size_t)smemOptin, ((size_t)smemPerSm - 2048) / 2); // two CTAs per SM
+            // one persistent CTA (512 threads, two-stage ring) may take the whole SM; small bricks leave room for two (256 threads each)
+            const size_t limit = (size_t)smemOptin;
             while (!bw.empty()) {
                 bh = BrickHost{};
                 BrickCaps caps{0, 0, 0, 0, 1, 1};
@@ -652,7 +655,7 @@ template <class R> class Engine : public EngineBase {
                         if (bh.ldesc.size() & 1)
                             bh.ldesc.push_back(LinkDesc{0, 0, 0, 0});
                         B.descBeg = (int)bh.ldesc.size();
-                        B.haloLinkBeg = (int)bh.haloLink.size();
+                        std::vector<int32_t> haloLinks;
                         for (int axis = 0; axis < 3; axis++)
                             for (int i = 0; i < B.nOwn; i++) {
                                 const int v = keyed[a + i].second;
@@ -668,9 +671,10 @@ template <class R> class Engine : public EngineBase {
                                 k.lmat = (uint16_t)((lmeta[l] >> 2) - (uint32_t)W.lmatOff);
                                 k.flags = (uint16_t)(axis | BD_NEG_OWN | (mat_of(v) << 4) | (mat_of(pos) << 8));
                                 bh.ldesc.push_back(k);
-                                bh.haloLink.push_back(lslotOf[l - h.loff]);
+                                haloLinks.push_back(lslotOf[l - h.loff]);
                             }
-                        B.nHaloL = (int)bh.haloLink.size() - B.haloLinkBeg;
+                        B.nHaloL = (int)haloLinks.size();
+                        bh.recomputed += haloLinks.size();
                         for (int axis = 0; axis < 3; axis++)
                             for (int i = 0; i < B.nOwn; i++) {
                                 const int v = keyed[a + i].second;
@@ -685,20 +689,23 @@ template <class R> class Engine : public EngineBase {
                                 k.flags = (uint16_t)(axis | BD_POS_OWN | (brickOf[neg] == (int)bi ? BD_NEG_OWN : 0) | (mat_of(neg) << 4) | (mat_of(v) << 8));
                                 bh.ldesc.push_back(k);
                             }
-                        B.haloBeg = (int)bh.haloVox.size();
+                        B.gBeg = (int)bh.glist.size(); // a multiple of 4 (bulk copies move 16-byte units)
                         B.nHalo = (int)halo.size();
                         for (int v : halo) {
-                            bh.haloVox.push_back(slotOf[v]);
+                            bh.glist.push_back(slotOf[v]);
                             local[v] = -1;
                         }
+                        for (int ls : haloLinks)
+                            bh.glist.push_back(ls);
+                        while (bh.glist.size() & 3)
+                            bh.glist.push_back(0);
                         for (int i = 0; i < B.nOwn; i++)
                             local[keyed[a + i].second] = -1;
                         a += B.nOwn;
-                        const int nl = B.nHaloL + B.nOwned;
                         caps.own = std::max(caps.own, nOwnPad);
                         caps.halo = std::max(caps.halo, B.nHalo);
                         caps.owned = std::max(caps.owned, B.nOwned);
-                        caps.links = std::max(caps.links, (nl + 1) & ~1);
+                        caps.haloL = std::max(caps.haloL, B.nHaloL);
                         if (nOwnPad + B.nHalo > 0xffff)
                             ok = false;
                     }
@@ -717,7 +724,7 @@ template <class R> class Engine : public EngineBase {
                         brickDimsUsed[k] = dims[k];
                     break;
                 }
-                int big = dims[0] >= dims[1] && dims[0] >= dims[2] ? 0 : dims[1] >= dims[2] ? 1 : 2;
+                int big = dims[1] >= dims[0] && dims[1] >= dims[2] ? 1 : dims[2] >= dims[0] ? 2 : 0; // ties: keep the x runs long
                 if (dims[big] <= 1) { // cannot happen for lattice worlds; leave every world to k_fused
                     bw.clear();
                     bh = BrickHost{};
@@ -943,18 +950,17 @@ template <class R> class Engine : public EngineBase {
         // ---- brick path: tables and the two brick-ordered buffer sets
         if (!bh.bricks.empty()) {
             BrickB *dB = nullptr;
-            int32_t *dHV = nullptr, *dHL = nullptr, *dVO = nullptr, *dLO = nullptr;
+            int32_t *dG = nullptr, *dVO = nullptr, *dLO = nullptr;
             LinkDesc *dD = nullptr;
             uint32_t *dS = nullptr;
-            if ((rc = dalloc(&dB, bh.bricks.size(), bh.bricks.data())) != VX3B_OK || (rc = dalloc(&dHV, bh.haloVox.size(), bh.haloVox.data())) != VX3B_OK ||
-                (rc = dalloc(&dHL, bh.haloLink.size(), bh.haloLink.data())) != VX3B_OK || (rc = dalloc(&dVO, bh.borig.size(), bh.borig.data())) != VX3B_OK ||
+            if ((rc = dalloc(&dB, bh.bricks.size(), bh.bricks.data())) != VX3B_OK || (rc = dalloc(&dG, bh.glist.size(), bh.glist.data())) != VX3B_OK ||
+                (rc = dalloc(&dVO, bh.borig.size(), bh.borig.data())) != VX3B_OK ||
                 (rc = dalloc(&dLO, bh.lorig.size(), bh.lorig.data())) != VX3B_OK || (rc = dalloc(&dD, bh.ldesc.size(), bh.ldesc.data())) != VX3B_OK ||
                 (rc = dalloc(&dS, bh.bstat.size(), bh.bstat.data())) != VX3B_OK)
                 return rc;
             BA.nBricks = (int)bh.bricks.size();
             BA.bricks = dB;
-            BA.haloVox = dHV;
-            BA.haloLink = dHL;
+            BA.glist = dG;
             BA.borig = dVO;
             BA.lorig = dLO;
             BA.ldesc = dD;
@@ -962,7 +968,7 @@ template <class R> class Engine : public EngineBase {
             BA.nvSlots = (int)bh.borig.size();
             BA.nlSlots = (int)bh.lorig.size();
             for (int k = 0; k < 2; k++) {
-                StateSet<R> &S = BA.set[k];
+                BrickSet<R> &S = BA.set[k];
                 if ((rc = dalloc(&S.pxy, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.pzt, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.orient, BA.nvSlots)) != VX3B_OK ||
                     (rc = dalloc(&S.lm, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.am, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.lpos2, BA.nlSlots)) != VX3B_OK ||
                     (rc = dalloc(&S.la1, BA.nlSlots)) != VX3B_OK || (rc = dalloc(&S.la2, BA.nlSlots)) != VX3B_OK)
@@ -970,10 +976,17 @@ template <class R> class Engine : public EngineBase {
             }
             CUDA_TRY(cudaFuncSetAttribute(k_brick<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brickSmem));
             CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brickSmem));
+            // persistent grid: as many CTAs as fit at once, each stepping consecutive bricks in chunks
+            int numSm = 0;
+            CUDA_TRY(cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev));
+            const int perSm = std::max(1, std::min(2, (int)((size_t)smemPerSm / (brickSmem + 1024))));
+            brickGrid = std::min(BA.nBricks, perSm * numSm);
+            BA.chunk = std::max(1, std::min((int)BRICK_CHUNK, (BA.nBricks + brickGrid - 1) / brickGrid));
+            brickThreads = perSm == 1 ? 512 : 256;
             if (getenv("VX3B_DEBUG"))
-                fprintf(stderr, "[vx3b] brick path: %zu bricks (%dx%dx%d), own <= %d, halo <= %d, owned links <= %d, links <= %d (%.1f%% recomputed), %zu B shared memory, %s\n",
-                        bh.bricks.size(), brickDimsUsed[0], brickDimsUsed[1], brickDimsUsed[2], brickCaps.own, brickCaps.halo, brickCaps.owned, brickCaps.links,
-                        100.0 * (double)bh.haloLink.size() / std::max<size_t>(bh.lorig.size(), 1), brickSmem, brickLean ? "lean" : "full");
+                fprintf(stderr, "[vx3b] brick path: %zu bricks (%dx%dx%d), own <= %d, halo <= %d, owned links <= %d, recomputed links <= %d (%.1f%%), %zu B shared memory, grid %d x %d threads x chunk %d, %s\n",
+                        bh.bricks.size(), brickDimsUsed[0], brickDimsUsed[1], brickDimsUsed[2], brickCaps.own, brickCaps.halo, brickCaps.owned, brickCaps.haloL,
+                        100.0 * (double)bh.recomputed / std::max<size_t>(bh.lorig.size(), 1), brickSmem, brickGrid, brickThreads, BA.chunk, brickLean ? "lean" : "full");
         }
         // ---- k_resident size classes: one launch + stream per class
         if (vStream0 < 0) {
@@ -1033,9 +1046,9 @@ template <class R> class Engine : public EngineBase {
                 k_fused<R><<<(unsigned)(FA.nBricks - b0), 256, fusedSmem, stream>>>(A, F, fusedCapTab, fusedCapOwn);
             if (BA.nBricks > 0) {
                 if (brickLean)
-                    k_brick<R, true><<<(unsigned)BA.nBricks, 256, brickSmem, stream>>>(A, BA, brickLayout);
+                    k_brick<R, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout);
                 else
-                    k_brick<R, false><<<(unsigned)BA.nBricks, 256, brickSmem, stream>>>(A, BA, brickLayout);
+                    k_brick<R, false><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout);
             }
         } else if (A.nvTot > v0)
             k_voxels<R><<<vb, 256, 0, stream>>>(A, v0);

@@ -2,21 +2,23 @@
 //
 // k_fused (kernels_fused.cuh) showed where the time goes on a 1e6-voxel body: not HBM (25 % of peak) but instruction issue and
 // exposed load latency - per-link index tables, gathered 16-byte loads with two dependent global loads per link, generic
-// per-voxel feature tests, 3-way bank conflicts.  This path changes the data layout instead of the arithmetic:
+// per-voxel feature tests, 3-way bank conflicts.  This path changes the data layout and the schedule instead of the arithmetic:
 //   * at the start of a run the voxels and links of every eligible world are copied ("packed") into brick order: the own
 //     voxels of a brick (BX x BY x BZ lattice cells, x fastest) and the links a brick owns (those whose POSITIVE end is an own
 //     voxel; x-, y-, z-links in that order) are contiguous, 16-byte aligned runs of the state arrays;
-//   * one CTA steps one brick.  One thread arms an mbarrier and issues eight 1-D bulk copies (cp.async.bulk, the TMA engine's
-//     linear mode: UBLKCP in SASS) that bring the brick's voxel state, link history and link descriptors into shared memory
-//     while the other threads gather the halo (voxels of neighbouring bricks that share a link with this one) and prefetch
-//     the history of the recomputed halo links; nothing in the two compute phases waits on a global load;
-//   * link forces travel from the link threads to the voxel threads through shared memory in a [slot][component][voxel]
-//     layout (conflict-free on both sides); new state goes straight from registers to HBM, coalesced, into the other buffer
-//     set (ping-pong by W.parity, as k_fused);
-//   * the world's material tables are staged in shared memory once per CTA with the per-material damping multiplier
-//     2*sqrt(m)*zeta/dt already divided;
-//   * LEAN instantiation (no boundary conditions, no cilia, no thermal actuation in any brick world of the launch) compiles
-//     the feature tests away.
+//   * PERSISTENT CTAs, each stepping a contiguous chunk of bricks through a TWO-STAGE shared-memory ring: while the CTA
+//     computes brick k out of one stage, the other stage fills with brick k+1 - its own runs, link history and link
+//     descriptors by 1-D bulk copies (cp.async.bulk, the TMA engine's linear mode: UBLKCP in SASS) that complete on the
+//     stage's mbarrier, its halo (voxels of neighbouring bricks that share a link with it, and the history of the links it
+//     recomputes) by 16-byte cp.async gathers whose index list was itself bulk-copied one brick earlier.  Nothing in the two
+//     compute phases waits on a global load;
+//   * link forces travel from the link threads to the voxel threads through shared memory in a [voxel][37] layout (odd
+//     stride: conflict-free on both sides, every access an immediate offset from one address); new state goes straight from
+//     registers to HBM, coalesced, into the other buffer set (ping-pong by W.parity, as k_fused);
+//   * the world's material tables are staged in shared memory (once per CTA while the world does not change) with the
+//     per-material damping multiplier 2*sqrt(m)*zeta/dt and the per-link-material rest lengths already formed;
+//   * the link axis is a template parameter (one switch per link instead of seven swizzle selects); the LEAN instantiation
+//     (no boundary conditions, cilia, thermal actuation or Fixed materials in any brick world) compiles the feature tests away.
 // Links cut by a brick face are recomputed by the brick that does not own them, from the same inputs, so no force crosses
 // CTAs (same rule as k_fused).  Worlds with voxel-voxel contact, a force field or target materials stay on k_fused: their
 // per-step helpers read the API-order arrays.
@@ -31,39 +33,52 @@ namespace vx3b {
 
 struct BrickB {
     int32_t world;
-    int32_t v0, nOwn, nHalo;    // own voxels: brick-order slots [v0, v0+nOwn), v0 even; halo: haloVox[haloBeg .. +nHalo)
-    int32_t l0, nOwned, nHaloL; // owned links: brick-order slots [l0, l0+nOwned); recomputed links: haloLink[haloLinkBeg .. +nHaloL)
-    int32_t haloBeg, descBeg, haloLinkBeg; // descBeg even: descriptors of the halo links, then of the owned links
-    int32_t pad0, pad1;
+    int32_t v0, nOwn, nHalo;    // own voxels: brick-order slots [v0, v0+nOwn), v0 even
+    int32_t l0, nOwned, nHaloL; // owned links: brick-order slots [l0, l0+nOwned); nHaloL recomputed links
+    int32_t descBeg;            // even: descriptors of the recomputed links, then of the owned links
+    int32_t gBeg;               // multiple of 4: gather list = nHalo voxel slots, then nHaloL link slots (padded to a multiple of 4)
+    int32_t pad0, pad1, pad2;
 };
 // One link as seen from one brick.  a/b: table index of the negative / positive end (own voxel i -> i, halo voxel j -> nOwnPad + j)
 struct alignas(8) LinkDesc {
     uint16_t a, b, lmat, flags; // lmat: world-local link material; flags: bits 0-1 axis, BD_NEG_OWN, BD_POS_OWN, bits 4-7 / 8-11 world-local voxel material of a / b
 };
 enum { BD_NEG_OWN = 4, BD_POS_OWN = 8 };
-enum { BRICK_MAX_VMATS = 16, BRICK_MAX_LMATS = 48 };
+enum { BRICK_MAX_VMATS = 16, BRICK_MAX_LMATS = 48, BRICK_CHUNK = 64, BRICK_FSTRIDE = 37 };
 
+// One brick-ordered buffer set.  Unlike the API-order StateSet the angular momentum has its own 16-byte array (am = angMom.xyz, 0;
+// lm = linMom.xyz, 0), so the translation half and the rotation half of a voxel update write disjoint arrays, and the VX3 "static
+// friction zeroes angMom" rule travels as a flag bit (VF_ZERO_ANGMOM in pzt) applied by whoever loads angMom next.
+template <class R> struct BrickSet {
+    using T4 = typename Store<R>::T4;
+    D2 *pxy, *pzt;
+    T4 *orient, *lm, *am;
+    T4 *lpos2, *la1, *la2;
+};
 template <class R> struct BrickArrays {
-    int nBricks;
+    int nBricks, chunk;      // chunk: consecutive bricks per CTA and round (<= BRICK_CHUNK)
     const BrickB *bricks;
-    const int32_t *haloVox;  // brick-order voxel slot of each halo voxel
     const LinkDesc *ldesc;
-    const int32_t *haloLink; // brick-order link slot of each recomputed link
+    const int32_t *glist;    // gather lists (brick-order voxel slots, then link slots)
     const uint32_t *bstat;   // per brick-order voxel slot: world-local material | link mask << 8 | has boundary conditions << 14
     const int32_t *borig;    // brick-order voxel slot -> global (API-order) voxel index, -1 for alignment padding
     const int32_t *lorig;    // brick-order link slot -> global link index
-    StateSet<R> set[2];
+    BrickSet<R> set[2];
     int nvSlots, nlSlots;
 };
 struct BrickCaps {
-    int own, halo, owned, links, nvm, nlm; // own and links are even
+    int own, halo, owned, haloL, nvm, nlm; // own even
+    int tab() const { return own + halo; }
+    int links() const { return (owned + haloL + 1) & ~1; }
+    int glist() const { return (halo + haloL + 3) & ~3; }
 };
 
 template <class R> struct BrickLayout { // byte offsets into the CTA's dynamic shared memory; computed once on the host
     using T4 = typename Store<R>::T4;
     using T2 = typename Store<R>::T2;
-    uint32_t bar, pxy, pzt, ori, lm, am, h0, h1, h2, desc, F, vmat, lmat, damp, len, total;
-    int capOwn;
+    uint32_t bar, hdr, glist[2], F, vmat, lmat, damp, len, stage[2];
+    uint32_t pxy, pzt, ori, lm, am, h0, h1, h2, desc; // relative to a stage
+    uint32_t total;
     static uint32_t up(size_t x) { return (uint32_t)((x + 127) & ~(size_t)127); }
     BrickLayout() {}
     explicit BrickLayout(const BrickCaps &c) {
@@ -73,28 +88,34 @@ template <class R> struct BrickLayout { // byte offsets into the CTA's dynamic s
             o = up(o + bytes);
             return at;
         };
-        const size_t tab = (size_t)c.own + c.halo;
-        capOwn = c.own;
-        bar = take(8);
-        pxy = take(sizeof(D2) * tab);
-        pzt = take(sizeof(D2) * tab);
-        ori = take(sizeof(T4) * tab);
-        lm = take(sizeof(T4) * c.own);
-        am = take(sizeof(T2) * c.own);
-        h0 = take(sizeof(T4) * c.owned);
-        h1 = take(sizeof(T4) * c.owned);
-        h2 = take(sizeof(T4) * c.owned);
-        desc = take(sizeof(LinkDesc) * c.links);
-        F = take(sizeof(R) * 36 * c.own);
+        bar = take(16);
+        hdr = take(sizeof(BrickB) * BRICK_CHUNK);
+        glist[0] = take(sizeof(int32_t) * c.glist());
+        glist[1] = take(sizeof(int32_t) * c.glist());
+        F = take(sizeof(R) * BRICK_FSTRIDE * c.own);
         vmat = take(sizeof(DVoxMat) * c.nvm);
         lmat = take(sizeof(DLinkMat) * c.nlm);
         damp = take(sizeof(float) * c.nvm);
         len = take(sizeof(LinkLen<R>) * c.nlm);
-        total = o;
+        const uint32_t base = o;
+        o = 0;
+        pxy = take(sizeof(D2) * c.tab());
+        pzt = take(sizeof(D2) * c.tab());
+        ori = take(sizeof(T4) * c.tab());
+        lm = take(sizeof(T4) * c.own);
+        am = take(sizeof(T4) * c.own);
+        h0 = take(sizeof(T4) * (c.owned + c.haloL));
+        h1 = take(sizeof(T4) * (c.owned + c.haloL));
+        h2 = take(sizeof(T4) * (c.owned + c.haloL));
+        desc = take(sizeof(LinkDesc) * c.links());
+        const uint32_t stageBytes = o;
+        stage[0] = base;
+        stage[1] = base + stageBytes;
+        total = base + 2 * stageBytes;
     }
 };
 
-// ---- mbarrier / bulk-copy PTX (sm_90+; the guide's TMA + mbarrier pattern in its 1-D form) --------------------------------
+// ---- mbarrier / bulk-copy / cp.async PTX (the guide's TMA + mbarrier producer/consumer pattern in its 1-D form) ------------
 VXD uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 VXD void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 VXD void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -118,6 +139,12 @@ VXD void mbar_wait(uint32_t bar, uint32_t phase) {
                      : "memory");
     } while (!done);
 }
+template <int BYTES> VXD void gather16(uint32_t dst, const void *src) { // BYTES = 16 or 32
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    if constexpr (BYTES == 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16), "l"((const char *)src + 16) : "memory");
+}
+VXD void gather_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <class R> VXD uint32_t hist_flags(typename Store<R>::T4 s0) {
     if constexpr (sizeof(R) == 4)
@@ -147,240 +174,346 @@ VXD void brick_link(const DLinkMat &lmat, const LinkLen<R> &len0, const DVoxMat 
     link_update<R, AXIS>(lmat, AXIS, dpos, len, qn, qp, sDamp[ma], sDamp[mb], h, f);
 }
 
-template <class R, bool LEAN> __global__ void __launch_bounds__(256, 2) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L) {
+template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L) {
     using T4 = typename Store<R>::T4;
     using T2 = typename Store<R>::T2;
     extern __shared__ __align__(128) unsigned char smem_brick[];
     unsigned char *smem = smem_brick;
-    const BrickB B = BA.bricks[blockIdx.x];
-    WorldD &W = A.worlds[B.world];
-    if (!W.active || !(W.flags & WF_BRICK))
-        return;
-    const int par = W.parity;
-    const StateSet<R> src = BA.set[par], dst = BA.set[par ^ 1];
-    D2 *sPxy = (D2 *)(smem + L.pxy), *sPzt = (D2 *)(smem + L.pzt);
-    T4 *sOri = (T4 *)(smem + L.ori), *sLm = (T4 *)(smem + L.lm);
-    T2 *sAm = (T2 *)(smem + L.am);
-    T4 *sH0 = (T4 *)(smem + L.h0), *sH1 = (T4 *)(smem + L.h1), *sH2 = (T4 *)(smem + L.h2);
-    const LinkDesc *sDesc = (const LinkDesc *)(smem + L.desc);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const BrickB *sHdr = (const BrickB *)(smem + L.hdr);
     R *sF = (R *)(smem + L.F);
     DVoxMat *sVm = (DVoxMat *)(smem + L.vmat);
     DLinkMat *sLmat = (DLinkMat *)(smem + L.lmat);
     float *sDamp = (float *)(smem + L.damp);
     LinkLen<R> *sLen = (LinkLen<R> *)(smem + L.len);
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int nOwn = B.nOwn, nOwnPad = (nOwn + 1) & ~1, nLinks = B.nHaloL + B.nOwned, nLinksPad = (nLinks + 1) & ~1;
-    const int capOwn = L.capOwn;
-    const uint32_t wflags = W.flags;
-    const bool vx3 = wflags & WF_VX3;
-    const float dt = W.dt;
-
-    // ---- phase 0: bulk copies of the brick's own runs (one thread), halo gather + material staging (everybody) -------------
-    const uint32_t bar = smem_u32(smem + L.bar);
+    const uint32_t bar0 = smem_u32(smem + L.bar);
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
         mbar_fence_init();
-        const uint32_t bV16 = (uint32_t)nOwnPad * 16u, bV4 = (uint32_t)nOwnPad * (uint32_t)sizeof(T4), bV2 = (uint32_t)nOwnPad * (uint32_t)sizeof(T2);
-        const uint32_t bL = (uint32_t)B.nOwned * (uint32_t)sizeof(T4), bD = (uint32_t)nLinksPad * (uint32_t)sizeof(LinkDesc);
-        mbar_expect_tx(bar, 2 * bV16 + 2 * bV4 + bV2 + 3 * bL + bD);
-        if (nOwnPad) {
-            bulk_g2s(smem_u32(sPxy), src.pxy + B.v0, bV16, bar);
-            bulk_g2s(smem_u32(sPzt), src.pzt + B.v0, bV16, bar);
-            bulk_g2s(smem_u32(sOri), src.orient + B.v0, bV4, bar);
-            bulk_g2s(smem_u32(sLm), src.lm + B.v0, bV4, bar);
-            bulk_g2s(smem_u32(sAm), src.am + B.v0, bV2, bar);
-        }
-        if (B.nOwned) {
-            bulk_g2s(smem_u32(sH0), src.lpos2 + B.l0, bL, bar);
-            bulk_g2s(smem_u32(sH1), src.la1 + B.l0, bL, bar);
-            bulk_g2s(smem_u32(sH2), src.la2 + B.l0, bL, bar);
-        }
-        if (nLinksPad)
-            bulk_g2s(smem_u32(sDesc), BA.ldesc + B.descBeg, bD, bar);
     }
-    // history of this thread's first recomputed link and the static word of its first voxel: in flight across the barrier
-    T4 pre0, pre1, pre2;
-    pre0 = pre1 = pre2 = mk4<R>(R(0), R(0), R(0), R(0));
-    if (tid < B.nHaloL) {
-        const int hl = BA.haloLink[B.haloLinkBeg + tid];
-        pre0 = src.lpos2[hl];
-        pre1 = src.la1[hl];
-        pre2 = src.la2[hl];
-    }
-    uint32_t stat0 = tid < nOwn ? BA.bstat[B.v0 + tid] : 0u;
-    for (int i = tid; i < B.nHalo; i += nt) {
-        const int g = BA.haloVox[B.haloBeg + i];
-        sPxy[nOwnPad + i] = src.pxy[g];
-        sPzt[nOwnPad + i] = src.pzt[g];
-        sOri[nOwnPad + i] = src.orient[g];
-    }
-    {
-        const uint32_t *gv = (const uint32_t *)(A.vmats + W.vmatOff), *gl = (const uint32_t *)(A.lmats + W.lmatOff);
-        uint32_t *sv = (uint32_t *)sVm, *sl = (uint32_t *)sLmat;
-        const int nwv = W.nvm * (int)(sizeof(DVoxMat) / 4), nwl = W.nlm * (int)(sizeof(DLinkMat) / 4);
-        for (int i = tid; i < nwv; i += nt)
-            sv[i] = gv[i];
-        for (int i = tid; i < nwl; i += nt)
-            sl[i] = gl[i];
-        if (tid < W.nvm) { // dampingMultiplier numerator / previousDt (VX3/VX3_Voxel.h:206-208); Fixed voxels never set previousDt
-            const DVoxMat &m = A.vmats[W.vmatOff + tid];
-            sDamp[tid] = m.sqrtMassZetaInt2 / ((vx3 && m.fixed) ? 0.0f : dt);
-        }
-        if (tid >= 32 && tid - 32 < W.nlm) { // rest lengths per link material at the sizes of a world whose temperature cannot change them
-            const uint32_t mp = A.lmats[W.lmatOff + tid - 32].matPair;
-            sLen[tid - 32] = link_len<R>(W.voxSize, 0.5 * (A.vmats[W.vmatOff + (mp & 0xffff)].baseSize0 + A.vmats[W.vmatOff + (mp >> 16)].baseSize0));
-        }
-    }
-    __syncthreads();
-    mbar_wait(bar, 0);
+    uint32_t phaseBits = 0; // bit s: parity the next wait on stage s's mbarrier expects
+    int curWorld = -1;
+    // per-world scalars (valid while curWorld is)
+    uint32_t wflags = 0;
+    bool vx3 = false, active = false, sampling = false;
+    float dt = 0;
+    double voxSize = 0;
+    BrickSet<R> src = BA.set[0], dst = BA.set[1];
+    WorldD *Wp = nullptr;
 
-    // ---- phase 1: links (recomputed halo links first, then the owned run) -----------------------------------------------------
-    bool diverged = false;
-    for (int r = tid; r < nLinks; r += nt) {
-        const LinkDesc k = sDesc[r];
-        const int axis = k.flags & 3, ia = k.a, ib = k.b;
-        const int o = r - B.nHaloL; // >= 0: owned link, slot l0 + o
-        T4 s0, s1, s2;
-        if (o >= 0) {
-            s0 = sH0[o];
-            s1 = sH1[o];
-            s2 = sH2[o];
-        } else if (r == tid) {
-            s0 = pre0;
-            s1 = pre1;
-            s2 = pre2;
-        } else {
-            const int hl = BA.haloLink[B.haloLinkBeg + r];
-            s0 = src.lpos2[hl];
-            s1 = src.la1[hl];
-            s2 = src.la2[hl];
-        }
-        const int ma = (k.flags >> 4) & 15, mb = (k.flags >> 8) & 15;
-        LinkForces<R> f;
-        f.fNeg = f.fPos = f.mNeg = f.mPos = V3<R>{R(0), R(0), R(0)};
-        f.strain = 0;
-        bool skip = false;
-        if constexpr (!LEAN)
-            skip = vx3 && sVm[ma].fixed && sVm[mb].fixed; // gpu_update_links skips these
-        if (!skip) {
-            const D2 axy = sPxy[ia], azt = sPzt[ia], bxy = sPxy[ib], bzt = sPzt[ib];
-            const T4 oa = sOri[ia], ob = sOri[ib];
-            LinkHist<R> h;
-            h.pos2 = {s0.x, s0.y, s0.z};
-            h.a1v = {s1.x, s1.y, s1.z};
-            h.a2v = {s2.x, s2.y, s2.z};
-            h.flags = hist_flags<R>(s0);
-            h.maxStrain = (float)s1.w;
-            const DLinkMat &lmat = sLmat[k.lmat];
-            const LinkLen<R> &len = sLen[k.lmat];
-            if (axis == 0)
-                brick_link<R, LEAN, 0>(lmat, len, sVm, sDamp, ma, mb, W.voxSize, axy, azt, bxy, bzt, oa, ob, h, f);
-            else if (axis == 1)
-                brick_link<R, LEAN, 1>(lmat, len, sVm, sDamp, ma, mb, W.voxSize, axy, azt, bxy, bzt, oa, ob, h, f);
-            else
-                brick_link<R, LEAN, 2>(lmat, len, sVm, sDamp, ma, mb, W.voxSize, axy, azt, bxy, bzt, oa, ob, h, f);
-            if (o >= 0) {
-                dst.lpos2[B.l0 + o] = mk4<R>(h.pos2.x, h.pos2.y, h.pos2.z, hist_flags_pack<R>(h.flags));
-                dst.la1[B.l0 + o] = mk4<R>(h.a1v.x, h.a1v.y, h.a1v.z, (R)h.maxStrain);
-                dst.la2[B.l0 + o] = mk4<R>(h.a2v.x, h.a2v.y, h.a2v.z, (R)f.strain);
-                if (f.strain > 100.0f)
-                    diverged = true;
+    // Fill stage `s` with brick B: bulk copies of its runs (+ the gather list of the brick after it, `next`, into its list slot)
+    // on the stage's mbarrier by thread 0, halo gathers by everybody.  idx: the brick's gather list (shared or global memory).
+    // ft / fnt: this thread's rank among, and the number of, the threads that take part.
+    auto fill = [&](const BrickB &B, int s, const int32_t *idx, const BrickB *next, int nextSlot, int ft, int fnt) {
+        unsigned char *st = smem + L.stage[s];
+        const int nOwnPad = (B.nOwn + 1) & ~1;
+        if (ft == 0) {
+            const uint32_t bar = bar0 + 8 * s;
+            const uint32_t bV16 = (uint32_t)nOwnPad * 16u, bV4 = (uint32_t)nOwnPad * (uint32_t)sizeof(T4);
+            const uint32_t bL = (uint32_t)B.nOwned * (uint32_t)sizeof(T4), bD = (uint32_t)((B.nHaloL + B.nOwned + 1) & ~1) * (uint32_t)sizeof(LinkDesc);
+            const uint32_t bG = next ? (uint32_t)((next->nHalo + next->nHaloL + 3) & ~3) * 4u : 0u;
+            mbar_expect_tx(bar, 2 * bV16 + 3 * bV4 + 3 * bL + bD + bG);
+            if (nOwnPad) {
+                bulk_g2s(smem_u32(st + L.pxy), src.pxy + B.v0, bV16, bar);
+                bulk_g2s(smem_u32(st + L.pzt), src.pzt + B.v0, bV16, bar);
+                bulk_g2s(smem_u32(st + L.ori), src.orient + B.v0, bV4, bar);
+                bulk_g2s(smem_u32(st + L.lm), src.lm + B.v0, bV4, bar);
+                bulk_g2s(smem_u32(st + L.am), src.am + B.v0, bV4, bar);
             }
-        } else if (o >= 0) { // carry the untouched history over to the other buffer
-            dst.lpos2[B.l0 + o] = s0;
-            dst.la1[B.l0 + o] = s1;
-            dst.la2[B.l0 + o] = s2;
+            if (B.nOwned) { // owned history lands behind the recomputed links' (gathered) history: one array indexed by link number
+                const uint32_t off = (uint32_t)B.nHaloL * (uint32_t)sizeof(T4);
+                bulk_g2s(smem_u32(st + L.h0) + off, src.lpos2 + B.l0, bL, bar);
+                bulk_g2s(smem_u32(st + L.h1) + off, src.la1 + B.l0, bL, bar);
+                bulk_g2s(smem_u32(st + L.h2) + off, src.la2 + B.l0, bL, bar);
+            }
+            if (bD)
+                bulk_g2s(smem_u32(st + L.desc), BA.ldesc + B.descBeg, bD, bar);
+            if (bG)
+                bulk_g2s(smem_u32(smem + L.glist[nextSlot]), BA.glist + next->gBeg, bG, bar);
         }
-        if (k.flags & BD_NEG_OWN) { // the negative end takes the link in its positive-direction slot 2*axis
-            R *p = sF + (12 * axis) * capOwn + ia;
-            p[0] = f.fNeg.x, p[capOwn] = f.fNeg.y, p[2 * capOwn] = f.fNeg.z;
-            p[3 * capOwn] = f.mNeg.x, p[4 * capOwn] = f.mNeg.y, p[5 * capOwn] = f.mNeg.z;
+        const uint32_t dPxy = smem_u32(st + L.pxy) + (uint32_t)nOwnPad * 16u, dPzt = smem_u32(st + L.pzt) + (uint32_t)nOwnPad * 16u;
+        const uint32_t dOri = smem_u32(st + L.ori) + (uint32_t)nOwnPad * (uint32_t)sizeof(T4);
+#pragma unroll 1
+        for (int i = ft; i < B.nHalo; i += fnt) {
+            const int g = idx[i];
+            gather16<16>(dPxy + 16u * i, src.pxy + g);
+            gather16<16>(dPzt + 16u * i, src.pzt + g);
+            gather16<sizeof(T4)>(dOri + (uint32_t)sizeof(T4) * i, src.orient + g);
         }
-        if (k.flags & BD_POS_OWN) { // the positive end in its negative-direction slot 2*axis+1
-            R *p = sF + (12 * axis + 6) * capOwn + ib;
-            p[0] = f.fPos.x, p[capOwn] = f.fPos.y, p[2 * capOwn] = f.fPos.z;
-            p[3 * capOwn] = f.mPos.x, p[4 * capOwn] = f.mPos.y, p[5 * capOwn] = f.mPos.z;
+        const uint32_t dH0 = smem_u32(st + L.h0), dH1 = smem_u32(st + L.h1), dH2 = smem_u32(st + L.h2);
+#pragma unroll 1
+        for (int i = ft; i < B.nHaloL; i += fnt) {
+            const int g = idx[B.nHalo + i];
+            gather16<sizeof(T4)>(dH0 + (uint32_t)sizeof(T4) * i, src.lpos2 + g);
+            gather16<sizeof(T4)>(dH1 + (uint32_t)sizeof(T4) * i, src.la1 + g);
+            gather16<sizeof(T4)>(dH2 + (uint32_t)sizeof(T4) * i, src.la2 + g);
         }
-    }
-    if (diverged)
-        W.divergedNow = 1;
-    __syncthreads();
+    };
 
-    // ---- phase 2: own voxels ---------------------------------------------------------------------------------------------------------
-    const bool sampling = vx3 && W.cycle > 0 && ((W.step + 1) % W.cycle == 0);
-    for (int i = tid; i < nOwn; i += nt) {
-        const uint32_t st = (i == tid) ? stat0 : BA.bstat[B.v0 + i];
-        const DVoxMat &m = sVm[st & 255];
-        const D2 pxy = sPxy[i], pzt = sPzt[i];
-        const T4 ori = sOri[i], lm = sLm[i];
-        const T2 am = sAm[i];
-        const unsigned long long packed = (unsigned long long)__double_as_longlong(pzt.y);
-        VoxState<R> s;
-        s.pos = {pxy.x, pxy.y, pzt.x};
-        s.temp = u2f((uint32_t)(packed & 0xffffffffu));
-        s.flags = (uint32_t)(packed >> 32);
-        s.orient = {ori.x, ori.y, ori.z, ori.w};
-        s.linMom = {lm.x, lm.y, lm.z};
-        s.angMom = {lm.w, am.x, am.y};
-        bool fixedMat = false;
-        if constexpr (!LEAN)
-            fixedMat = vx3 && m.fixed;
-        if (!fixedMat) {
-            V3<R> F{R(0), R(0), R(0)}, M{R(0), R(0), R(0)};
-            const uint32_t mk = st >> 8;
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                if (!(mk & (1u << k)))
-                    continue;
-                const R *p = sF + (6 * k) * capOwn + i;
-                F = F + V3<R>{p[0], p[capOwn], p[2 * capOwn]};
-                M = M + V3<R>{p[3 * capOwn], p[4 * capOwn], p[5 * capOwn]};
+    for (int base = blockIdx.x * BA.chunk; base < BA.nBricks; base += gridDim.x * BA.chunk) {
+        const int cnt = min(BA.chunk, BA.nBricks - base);
+        __syncthreads(); // previous round's readers of the header array are done (also orders the mbarrier init)
+        {
+            const uint32_t *g = (const uint32_t *)(BA.bricks + base);
+            uint32_t *d = (uint32_t *)(smem + L.hdr);
+#pragma unroll 1
+            for (int i = tid; i < cnt * (int)(sizeof(BrickB) / 4); i += nt)
+                d[i] = g[i];
+        }
+        __syncthreads();
+        bool filled = false; // brick k's stage is already in flight (prefetched during brick k-1)
+        int s = 0;           // stage of brick k
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            const BrickB B = sHdr[k];
+            if (B.world != curWorld) { // (re)stage the world: scalars in registers, material tables in shared memory
+                curWorld = B.world;
+                Wp = A.worlds + B.world;
+                const WorldD &W = *Wp;
+                wflags = W.flags;
+                vx3 = wflags & WF_VX3;
+                active = W.active && (wflags & WF_BRICK);
+                dt = W.dt;
+                voxSize = W.voxSize;
+                sampling = vx3 && W.cycle > 0 && ((W.step + 1) % W.cycle == 0);
+                const int par = W.parity;
+                src = BA.set[par];
+                dst = BA.set[par ^ 1];
+                if (active) {
+                    __syncthreads(); // nobody still reads the previous world's tables
+                    const uint32_t *gv = (const uint32_t *)(A.vmats + W.vmatOff), *gl = (const uint32_t *)(A.lmats + W.lmatOff);
+                    uint32_t *sv = (uint32_t *)sVm, *sl = (uint32_t *)sLmat;
+                    const int nwv = W.nvm * (int)(sizeof(DVoxMat) / 4), nwl = W.nlm * (int)(sizeof(DLinkMat) / 4);
+#pragma unroll 1
+                    for (int i = tid; i < nwv; i += nt)
+                        sv[i] = gv[i];
+#pragma unroll 1
+                    for (int i = tid; i < nwl; i += nt)
+                        sl[i] = gl[i];
+                    if (tid < W.nvm) { // dampingMultiplier numerator / previousDt (VX3/VX3_Voxel.h:206-208); Fixed voxels never set previousDt
+                        const DVoxMat &m = A.vmats[W.vmatOff + tid];
+                        sDamp[tid] = m.sqrtMassZetaInt2 / ((vx3 && m.fixed) ? 0.0f : dt);
+                    }
+                    if (tid >= 32 && tid - 32 < W.nlm) { // rest lengths per link material at sizes the temperature cannot change
+                        const uint32_t mp = A.lmats[W.lmatOff + tid - 32].matPair;
+                        sLen[tid - 32] = link_len<R>(W.voxSize, 0.5 * (A.vmats[W.vmatOff + (mp & 0xffff)].baseSize0 + A.vmats[W.vmatOff + (mp >> 16)].baseSize0));
+                    }
+                    __syncthreads();
+                }
             }
-            V3<R> contact{R(0), R(0), R(0)}, cilia{R(0), R(0), R(0)};
+            if (!active) {
+                filled = false;
+                continue;
+            }
+            const bool haveNext = k + 1 < cnt && sHdr[k + 1].world == curWorld;
+            if (!filled) { // first brick of a round / of a world: nothing was prefetched, indices come from global memory
+                fill(B, s, BA.glist + B.gBeg, haveNext ? &sHdr[k + 1] : nullptr, (k + 1) & 1, tid, nt);
+                gather_wait_all();
+                __syncthreads();
+            }
+            mbar_wait(bar0 + 8 * s, (phaseBits >> s) & 1);
+            phaseBits ^= 1u << s;
+            filled = haveNext; // brick k+1 is prefetched below, by the warps that run out of links first
+
+            unsigned char *st = smem + L.stage[s];
+            const D2 *sPxy = (const D2 *)(st + L.pxy), *sPzt = (const D2 *)(st + L.pzt);
+            const T4 *sOri = (const T4 *)(st + L.ori), *sLm = (const T4 *)(st + L.lm);
+            const T4 *sAm = (const T4 *)(st + L.am);
+            const T4 *sH0 = (const T4 *)(st + L.h0), *sH1 = (const T4 *)(st + L.h1), *sH2 = (const T4 *)(st + L.h2);
+            const LinkDesc *sDesc = (const LinkDesc *)(st + L.desc);
+            const int nOwn = B.nOwn, nLinks = B.nHaloL + B.nOwned;
+            // phase 2 roles: with at least two threads per own voxel (and no per-voxel extras: LEAN) the lower half of the CTA
+            // integrates translations, the upper half rotations; otherwise one thread does both halves of its voxel
+            const int half = nt >> 1;
+            const bool split = LEAN && nOwn <= half;
+            const bool rotRole = split && tid >= half;
+            const int myVox = rotRole ? tid - half : tid;
+            const uint32_t stat0 = myVox < nOwn ? BA.bstat[B.v0 + myVox] : 0u; // consumed in phase 2: in flight during phase 1
+
+            // ---- phase 1: links (recomputed ones first, then the owned run) ---------------------------------------------------
+            bool diverged = false;
+#pragma unroll 1
+            for (int r = tid; r < nLinks; r += nt) {
+                const LinkDesc kd = sDesc[r];
+                const int axis = kd.flags & 3, ia = kd.a, ib = kd.b;
+                const int o = r - B.nHaloL; // >= 0: owned link, slot l0 + o
+                const T4 s0 = sH0[r], s1 = sH1[r], s2 = sH2[r];
+                const int ma = (kd.flags >> 4) & 15, mb = (kd.flags >> 8) & 15;
+                LinkForces<R> f;
+                f.fNeg = f.fPos = f.mNeg = f.mPos = V3<R>{R(0), R(0), R(0)};
+                f.strain = 0;
+                bool skip = false;
+                if constexpr (!LEAN)
+                    skip = vx3 && sVm[ma].fixed && sVm[mb].fixed; // gpu_update_links skips these
+                if (!skip) {
+                    const D2 axy = sPxy[ia], azt = sPzt[ia], bxy = sPxy[ib], bzt = sPzt[ib];
+                    const T4 oa = sOri[ia], ob = sOri[ib];
+                    LinkHist<R> h;
+                    h.pos2 = {s0.x, s0.y, s0.z};
+                    h.a1v = {s1.x, s1.y, s1.z};
+                    h.a2v = {s2.x, s2.y, s2.z};
+                    h.flags = hist_flags<R>(s0);
+                    h.maxStrain = (float)s1.w;
+                    const DLinkMat &lmat = sLmat[kd.lmat];
+                    const LinkLen<R> &len = sLen[kd.lmat];
+                    if (axis == 0)
+                        brick_link<R, LEAN, 0>(lmat, len, sVm, sDamp, ma, mb, voxSize, axy, azt, bxy, bzt, oa, ob, h, f);
+                    else if (axis == 1)
+                        brick_link<R, LEAN, 1>(lmat, len, sVm, sDamp, ma, mb, voxSize, axy, azt, bxy, bzt, oa, ob, h, f);
+                    else
+                        brick_link<R, LEAN, 2>(lmat, len, sVm, sDamp, ma, mb, voxSize, axy, azt, bxy, bzt, oa, ob, h, f);
+                    if (o >= 0) {
+                        dst.lpos2[B.l0 + o] = mk4<R>(h.pos2.x, h.pos2.y, h.pos2.z, hist_flags_pack<R>(h.flags));
+                        dst.la1[B.l0 + o] = mk4<R>(h.a1v.x, h.a1v.y, h.a1v.z, (R)h.maxStrain);
+                        dst.la2[B.l0 + o] = mk4<R>(h.a2v.x, h.a2v.y, h.a2v.z, (R)f.strain);
+                        if (f.strain > 100.0f)
+                            diverged = true;
+                    }
+                } else if (o >= 0) { // carry the untouched history over to the other buffer
+                    dst.lpos2[B.l0 + o] = s0;
+                    dst.la1[B.l0 + o] = s1;
+                    dst.la2[B.l0 + o] = s2;
+                }
+                if (kd.flags & BD_NEG_OWN) { // the negative end takes the link in its positive-direction slot 2*axis
+                    R *p = sF + ia * BRICK_FSTRIDE + 12 * axis;
+                    p[0] = f.fNeg.x, p[1] = f.fNeg.y, p[2] = f.fNeg.z;
+                    p[3] = f.mNeg.x, p[4] = f.mNeg.y, p[5] = f.mNeg.z;
+                }
+                if (kd.flags & BD_POS_OWN) { // the positive end in its negative-direction slot 2*axis+1
+                    R *p = sF + ib * BRICK_FSTRIDE + 12 * axis + 6;
+                    p[0] = f.fPos.x, p[1] = f.fPos.y, p[2] = f.fPos.z;
+                    p[3] = f.mPos.x, p[4] = f.mPos.y, p[5] = f.mPos.z;
+                }
+            }
+            if (diverged)
+                Wp->divergedNow = 1;
+            // prefetch brick k+1 into the other stage (its last readers passed the barrier that ended brick k-1).  The last four
+            // warps do it: they hold the highest link numbers, so they are the ones with an iteration to spare
+            if (haveNext && tid >= nt - 128) {
+                const bool haveNext2 = k + 2 < cnt && sHdr[k + 2].world == curWorld;
+                fill(sHdr[k + 1], s ^ 1, (const int32_t *)(smem + L.glist[(k + 1) & 1]), haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, tid - (nt - 128), 128);
+            }
+            __syncthreads();
+
+            // ---- phase 2: own voxels -----------------------------------------------------------------------------------------------
             WorldStepParams wp;
             wp.dt = dt;
             wp.floorEnabled = (wflags & WF_FLOOR) != 0;
             wp.vx3 = vx3;
             wp.forceField = nullptr;
-            VoxExt ext;
-            const VoxExt *pe = nullptr;
-            V3<double> nominal{0, 0, 0};
-            if constexpr (!LEAN) {
-                const int g = BA.borig[B.v0 + i];
-                if ((wflags & WF_CILIA) && m.cilia != 0 && A.baseCilia && A.vsurf[g] >= 0) {
-                    D4 b = A.baseCilia[g];
-                    cilia = qrot(s.orient, V3<R>{(R)b.x, (R)b.y, (R)b.z});
+#pragma unroll 1
+            for (int i = myVox; i < nOwn; i += (split ? nOwn : nt)) {
+                const uint32_t stw = (i == myVox) ? stat0 : BA.bstat[B.v0 + i];
+                const DVoxMat &m = sVm[stw & 255];
+                const D2 pzt = sPzt[i];
+                const T4 ori = sOri[i];
+                const unsigned long long packed = (unsigned long long)__double_as_longlong(pzt.y);
+                VoxState<R> v;
+                v.temp = u2f((uint32_t)(packed & 0xffffffffu));
+                v.flags = (uint32_t)(packed >> 32);
+                v.orient = {ori.x, ori.y, ori.z, ori.w};
+                const uint32_t mk = (stw >> 8) & 63u;
+                const bool allSix = __all_sync(__activemask(), mk == 63u); // interior warp: sum in the reference's direction order, no tests
+                const R *p = sF + i * BRICK_FSTRIDE;
+                const int vs = B.v0 + i;
+                auto sum_slots = [&](int off) {
+                    V3<R> a{R(0), R(0), R(0)};
+                    if (allSix) {
+                        a = V3<R>{p[off], p[off + 1], p[off + 2]};
+#pragma unroll
+                        for (int q = 1; q < 6; q++)
+                            a = a + V3<R>{p[6 * q + off], p[6 * q + off + 1], p[6 * q + off + 2]};
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 6; q++)
+                            if (mk & (1u << q))
+                                a = a + V3<R>{p[6 * q + off], p[6 * q + off + 1], p[6 * q + off + 2]};
+                    }
+                    return a;
+                };
+                if (split) { // LEAN only
+                    if (!rotRole) {
+                        const D2 pxy = sPxy[i];
+                        const T4 lm = sLm[i];
+                        v.pos = {pxy.x, pxy.y, pzt.x};
+                        v.linMom = {lm.x, lm.y, lm.z};
+                        const V3<R> zero{R(0), R(0), R(0)};
+                        const bool sf = voxel_translate<R, true>(m, wp, nullptr, v, sum_slots(0), zero, zero);
+                        const uint32_t fl = (sf ? VF_STATIC_FRICTION : 0u) | (voxel_zero_angmom(m, wp, sf, v.temp, v.pos.z) ? VF_ZERO_ANGMOM : 0u);
+                        dst.pxy[vs] = D2{v.pos.x, v.pos.y};
+                        const unsigned long long b2 = ((unsigned long long)fl << 32) | (unsigned long long)f2u(v.temp);
+                        dst.pzt[vs] = D2{v.pos.z, __longlong_as_double((long long)b2)};
+                        dst.lm[vs] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
+                        if (sampling) {
+                            const double mass = m.mass;
+                            world_accumulate(Wp->comAcc, B.world, m.isMeasured != 0, v.pos.x * mass, v.pos.y * mass, v.pos.z * mass, mass);
+                        }
+                    } else {
+                        const T4 am = sAm[i];
+                        v.angMom = (v.flags & VF_ZERO_ANGMOM) ? V3<R>{R(0), R(0), R(0)} : V3<R>{am.x, am.y, am.z};
+                        voxel_rotate<R, true>(m, wp, nullptr, v, sum_slots(3));
+                        dst.orient[vs] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
+                        dst.am[vs] = mk4<R>(v.angMom.x, v.angMom.y, v.angMom.z, R(0));
+                    }
+                    continue;
                 }
-                if (st & (1u << 14)) {
-                    const DExt &x = A.ext[A.vext[g]];
-                    const short4 lat = A.lat[g];
-                    nominal = {lat.x * m.nomSize, lat.y * m.nomSize, lat.z * m.nomSize};
-                    ext.dof = x.dof;
-                    ext.force = {x.force[0], x.force[1], x.force[2]};
-                    ext.moment = {x.moment[0], x.moment[1], x.moment[2]};
-                    ext.translation = {x.translation[0], x.translation[1], x.translation[2]};
-                    ext.rotationQ = {x.rotQ[0], x.rotQ[1], x.rotQ[2], x.rotQ[3]};
-                    pe = &ext;
+                const D2 pxy = sPxy[i];
+                const T4 lm = sLm[i], am = sAm[i];
+                v.pos = {pxy.x, pxy.y, pzt.x};
+                v.linMom = {lm.x, lm.y, lm.z};
+                v.angMom = (v.flags & VF_ZERO_ANGMOM) ? V3<R>{R(0), R(0), R(0)} : V3<R>{am.x, am.y, am.z};
+                v.flags &= VF_STATIC_FRICTION;
+                bool fixedMat = false;
+                if constexpr (!LEAN)
+                    fixedMat = vx3 && m.fixed;
+                if (!fixedMat) {
+                    const V3<R> F = sum_slots(0), M = sum_slots(3);
+                    V3<R> contact{R(0), R(0), R(0)}, cilia{R(0), R(0), R(0)};
+                    VoxExt ext;
+                    const VoxExt *pe = nullptr;
+                    V3<double> nominal{0, 0, 0};
+                    if constexpr (!LEAN) {
+                        const int g = BA.borig[B.v0 + i];
+                        if ((wflags & WF_CILIA) && m.cilia != 0 && A.baseCilia && A.vsurf[g] >= 0) {
+                            D4 b = A.baseCilia[g];
+                            cilia = qrot(v.orient, V3<R>{(R)b.x, (R)b.y, (R)b.z});
+                        }
+                        if (stw & (1u << 14)) {
+                            const DExt &x = A.ext[A.vext[g]];
+                            const short4 lat = A.lat[g];
+                            nominal = {lat.x * m.nomSize, lat.y * m.nomSize, lat.z * m.nomSize};
+                            ext.dof = x.dof;
+                            ext.force = {x.force[0], x.force[1], x.force[2]};
+                            ext.moment = {x.moment[0], x.moment[1], x.moment[2]};
+                            ext.translation = {x.translation[0], x.translation[1], x.translation[2]};
+                            ext.rotationQ = {x.rotQ[0], x.rotQ[1], x.rotQ[2], x.rotQ[3]};
+                            pe = &ext;
+                        }
+                    }
+                    voxel_update<R, LEAN>(m, wp, pe, nominal, v, F, M, contact, cilia);
+                    if constexpr (!LEAN) {
+                        const WorldD &W = *Wp;
+                        if ((wflags & WF_VARY_TEMP) && W.tempPeriod > 0) { // temperature the next step will see (start-of-step time t+dt)
+                            const int g = BA.borig[B.v0 + i];
+                            v.temp = voxel_temperature(W.tempAmp, W.tempPeriod, A.phase ? A.phase[g] : 0.0, W.t + (double)dt, (wflags & WF_EXPANSION) != 0);
+                        }
+                    }
+                }
+                dst.pxy[vs] = D2{v.pos.x, v.pos.y};
+                const unsigned long long b2 = ((unsigned long long)v.flags << 32) | (unsigned long long)f2u(v.temp);
+                dst.pzt[vs] = D2{v.pos.z, __longlong_as_double((long long)b2)};
+                dst.orient[vs] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
+                dst.lm[vs] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
+                dst.am[vs] = mk4<R>(v.angMom.x, v.angMom.y, v.angMom.z, R(0));
+                if (sampling) {
+                    const double mass = m.mass;
+                    world_accumulate(Wp->comAcc, B.world, m.isMeasured != 0, v.pos.x * mass, v.pos.y * mass, v.pos.z * mass, mass);
                 }
             }
-            voxel_update<R>(m, wp, pe, nominal, s, F, M, contact, cilia);
-            if constexpr (!LEAN) {
-                if ((wflags & WF_VARY_TEMP) && W.tempPeriod > 0) { // temperature the next step will see (start-of-step time t+dt)
-                    const int g = BA.borig[B.v0 + i];
-                    s.temp = voxel_temperature(W.tempAmp, W.tempPeriod, A.phase ? A.phase[g] : 0.0, W.t + (double)dt, (wflags & WF_EXPANSION) != 0);
-                }
-            }
-        }
-        const int v = B.v0 + i;
-        dst.pxy[v] = D2{s.pos.x, s.pos.y};
-        const unsigned long long b2 = ((unsigned long long)s.flags << 32) | (unsigned long long)f2u(s.temp);
-        dst.pzt[v] = D2{s.pos.z, __longlong_as_double((long long)b2)};
-        dst.orient[v] = mk4<R>(s.orient.w, s.orient.x, s.orient.y, s.orient.z);
-        dst.lm[v] = mk4<R>(s.linMom.x, s.linMom.y, s.linMom.z, s.angMom.x);
-        dst.am[v] = mk2<R>(s.angMom.y, s.angMom.z);
-        if (sampling) {
-            const double mass = m.mass;
-            world_accumulate(W.comAcc, B.world, m.isMeasured != 0, s.pos.x * mass, s.pos.y * mass, s.pos.z * mass, mass);
+            gather_wait_all(); // this thread's gathers for brick k+1 have landed ...
+            __syncthreads();   // ... and everybody's have; stage s and the force slots are free again
+            s ^= 1;
         }
     }
 }
@@ -391,11 +524,13 @@ template <class R> __global__ void k_brick_pack(Arrays<R> A, BrickArrays<R> BA) 
     if (i < BA.nvSlots) {
         const int g = BA.borig[i];
         if (g >= 0 && (A.worlds[A.vworld[g]].flags & WF_BRICK)) {
+            const auto lm = A.lm[g];
+            const auto am = A.am[g];
             BA.set[0].pxy[i] = A.pxy[g];
             BA.set[0].pzt[i] = A.pzt[g];
             BA.set[0].orient[i] = A.orient[g];
-            BA.set[0].lm[i] = A.lm[g];
-            BA.set[0].am[i] = A.am[g];
+            BA.set[0].lm[i] = mk4<R>(lm.x, lm.y, lm.z, R(0));
+            BA.set[0].am[i] = mk4<R>(lm.w, am.x, am.y, R(0));
         }
     }
     if (i < BA.nlSlots) {
@@ -415,12 +550,21 @@ template <class R> __global__ void k_brick_unpack(Arrays<R> A, BrickArrays<R> BA
         if (g >= 0) {
             const WorldD &W = A.worlds[A.vworld[g]];
             if (W.flags & WF_BRICK) {
-                const StateSet<R> &s = BA.set[W.parity];
+                const BrickSet<R> &s = BA.set[W.parity];
+                D2 pzt = s.pzt[i];
+                unsigned long long packed = (unsigned long long)__double_as_longlong(pzt.y);
+                auto lm = s.lm[i];
+                auto am = s.am[i];
+                if ((packed >> 32) & VF_ZERO_ANGMOM) { // the pending VX3 zeroing (see BrickSet)
+                    am.x = am.y = am.z = R(0);
+                    packed &= ~((unsigned long long)VF_ZERO_ANGMOM << 32);
+                    pzt.y = __longlong_as_double((long long)packed);
+                }
                 A.pxy[g] = s.pxy[i];
-                A.pzt[g] = s.pzt[i];
+                A.pzt[g] = pzt;
                 A.orient[g] = s.orient[i];
-                A.lm[g] = s.lm[i];
-                A.am[g] = s.am[i];
+                A.lm[g] = mk4<R>(lm.x, lm.y, lm.z, am.x);
+                A.am[g] = mk2<R>(am.y, am.z);
             }
         }
     }
@@ -429,7 +573,7 @@ template <class R> __global__ void k_brick_unpack(Arrays<R> A, BrickArrays<R> BA
         if (g >= 0) {
             const WorldD &W = A.worlds[A.lworld[g]];
             if (W.flags & WF_BRICK) {
-                const StateSet<R> &s = BA.set[W.parity];
+                const BrickSet<R> &s = BA.set[W.parity];
                 A.lpos2[g] = s.lpos2[i];
                 A.la1[g] = s.la1[i];
                 A.la2[g] = s.la2[i];

@@ -52,6 +52,27 @@ VXD float vrcp(float a) {
     return r;
 }
 VXD double vrcp(double a) { return 1.0 / a; }
+// float build: asin / acos without the libm slow paths (Cephes asinf core polynomial, |error| < 1e-7 on |x| <= 0.5, plus the
+// half-angle reductions).  A crushed region of a big body keeps its links in the large-angle branch, where every warp that holds
+// one such link pays for these (profiles/r01k: +30 M warp instructions per step on the 100^3 body once it has hit the floor).
+VXD float asin_poly(float x) { // |x| <= 0.5
+    const float z = x * x;
+    const float p = (((4.2163199048e-2f * z + 2.4181311049e-2f) * z + 4.5470025998e-2f) * z + 7.4953002686e-2f) * z + 1.6666752422e-1f;
+    return x + x * z * p;
+}
+VXD float asin_fast(float x) { // 0 <= x <= 1
+    const bool big = x > 0.5f;
+    const float y = big ? vsqrt(0.5f * (1.0f - x)) : x;
+    const float a = asin_poly(y);
+    return big ? 1.5707963268f - 2.0f * a : a;
+}
+VXD float acos_fast(float x) { // -1 <= x <= 1
+    const float ax = fabsf(x);
+    const bool big = ax > 0.5f;
+    const float y = big ? vsqrt(0.5f * (1.0f - ax)) : x;
+    const float a = asin_poly(y);
+    return big ? (x > 0.0f ? 2.0f * a : 3.14159265359f - 2.0f * a) : 1.5707963268f - a;
+}
 VXD float vabs(float x) { return fabsf(x); }
 VXD double vabs(double x) { return fabs(x); }
 VXD float vacos(float x) { return acosf(x); }
@@ -101,9 +122,8 @@ VXD V3<float> rotvec(Qt<float> q) {
         k = 2.0f + s2 * (0.33333334f + s2 * 0.15f); // 2*asin(s)/s = 2 + s^2/3 + 3 s^4/20 + ...
     else {
         float s = vsqrt(s2);
-        float half = (q.w > 0.70710678f) ? asinf(s) : acosf(fminf(fmaxf(q.w, -1.0f), 1.0f));
-        if (q.w < -0.70710678f) // stay on the reference's branch of acos
-            half = acosf(fmaxf(q.w, -1.0f));
+        // asin of the vector part where it is well conditioned, acos(w) (the reference's branch) elsewhere
+        const float half = (q.w > 0.70710678f) ? asin_fast(fminf(s, 1.0f)) : acos_fast(fminf(fmaxf(q.w, -1.0f), 1.0f));
         k = vdiv(2.0f * half, s);
     }
     return {k * q.x, k * q.y, k * q.z};
@@ -132,7 +152,7 @@ VXD Qt<float> quat_from_rotvec(V3<float> in) {
         s = 1.0f - m2 * (0.16666667f - m2 * 0.0083333338f);
     } else {
         float m = vsqrt(m2), sn, cs;
-        sincosf(m, &sn, &cs);
+        __sincosf(m, &sn, &cs); // |m| is a fraction of a radian here: the fast path's absolute error (2^-21) is below float resolution of w
         w = cs;
         s = vdiv(sn, m);
     }
@@ -152,24 +172,38 @@ template <class R> VXD void quat_to_pos_x(Qt<R> &q, V3<R> from) {
         q.w = R(1) + R(0.5) * (-q.y * q.y - q.z * q.z);
         return;
     }
-    R l = vsqrt(len2(from));
-    V3<R> n = from;
-    if (l > R(0)) {
-        R inv = vrcp(l);
-        n = {inv * from.x, inv * from.y, inv * from.z};
+    if constexpr (sizeof(R) == 4) {
+        // float build, without trigonometry: the unit quaternion taking n to +X is (1 + n.x, n x X) normalised
+        // = (cos(t/2), sin(t/2) * (0, n.z, -n.y) / |(n.y, n.z)|), the same rotation the reference builds from acos / sincos
+        const R inv = rsqrtf(len2(from));
+        const V3<R> n{inv * from.x, inv * from.y, inv * from.z};
+        const R c1 = R(1) + n.x;
+        if (c1 < R(1e-7)) { // pointing along -X: the reference's 180 degree case
+            q = {R(0), R(0), R(1), R(0)};
+            return;
+        }
+        const R k = rsqrtf(R(2) * c1);
+        q = {c1 * k, R(0), n.z * k, -n.y * k};
+    } else {
+        R l = vsqrt(len2(from));
+        V3<R> n = from;
+        if (l > R(0)) {
+            R inv = vrcp(l);
+            n = {inv * from.x, inv * from.y, inv * from.z};
+        }
+        R theta = vacos(n.x);
+        if (theta > R(3.14159265358979) - R(1e-7)) {
+            q = {R(0), R(0), R(1), R(0)};
+            return;
+        }
+        R axisMagInv = vrcp(vsqrt(n.z * n.z + n.y * n.y));
+        R sn, cs;
+        vsincos(R(0.5) * theta, &sn, &cs);
+        q.w = cs;
+        q.x = R(0);
+        q.y = n.z * axisMagInv * sn;
+        q.z = -n.y * axisMagInv * sn;
     }
-    R theta = vacos(n.x);
-    if (theta > R(3.14159265358979) - R(1e-7)) {
-        q = {R(0), R(0), R(1), R(0)};
-        return;
-    }
-    R axisMagInv = vrcp(vsqrt(n.z * n.z + n.y * n.y));
-    R sn, cs;
-    vsincos(R(0.5) * theta, &sn, &cs);
-    q.w = cs;
-    q.x = R(0);
-    q.y = n.z * axisMagInv * sn;
-    q.z = -n.y * axisMagInv * sn;
 }
 
 // axis swizzles (VX3/VX3_Link.h:97-191)
@@ -207,7 +241,7 @@ struct DLinkMat {
 // link history flags
 enum { LF_SMALL_ANGLE = 1, LF_VEL_VALID = 2 };
 // voxel flags
-enum { VF_STATIC_FRICTION = 1 };
+enum { VF_STATIC_FRICTION = 1, VF_ZERO_ANGMOM = 2 }; // VF_ZERO_ANGMOM: brick-ordered sets only (k_brick applies the VX3 zeroing lazily)
 
 template <class R> struct LinkHist {
     V3<R> pos2, a1v, a2v;
@@ -442,24 +476,25 @@ VXD float floor_penetration(const DVoxMat &m, float temp, double z) { // VX3/VX3
 }
 
 // Fsum/Msum: sums of the ≤6 link forces/moments in the voxel's local frame; contact/cilia in the global frame.
-template <class R>
-VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt *ext, V3<double> nominalPos, VoxState<R> &s, V3<R> Fsum, V3<R> Msum,
-                      V3<R> contact, V3<R> cilia) {
+// PLAIN: the caller guarantees no boundary conditions, force field, contact or cilia force (compiled away).
+// The update is the composition of a translation half (reads orient; writes pos, linMom; returns the friction mode) and a
+// rotation half (writes angMom, orient) that depend on each other only through VX3's "static friction zeroes angMom" rule, which
+// the caller applies afterwards - so a kernel may give the two halves of one voxel to two threads (k_brick).
+template <class R, bool PLAIN = false>
+VXD bool voxel_translate(const DVoxMat &m, const WorldStepParams &wp, const VoxExt *ext, VoxState<R> &s, V3<R> Fsum, V3<R> contact, V3<R> cilia) {
     const R dt = (R)wp.dt;
-    if (ext && ext->dof == VX3B_DOF_ALL) {
-        s.pos = nominalPos + ext->translation;
-        s.orient = {(R)ext->rotationQ.w, (R)ext->rotationQ.x, (R)ext->rotationQ.y, (R)ext->rotationQ.z};
-        s.linMom = s.angMom = V3<R>{R(0), R(0), R(0)};
-        return;
-    }
+    if constexpr (PLAIN)
+        ext = nullptr;
     V3<R> F = qrot(s.orient, Fsum);
     if (ext)
         F = F + V3<R>{(R)ext->force.x, (R)ext->force.y, (R)ext->force.z};
     F = F - (s.linMom * (R)m.massInverse) * (R)m.globalDampTranslateC;
     F.z += (R)m.gravityForce;
-    F = F - contact;
-    F = F + cilia * (R)m.cilia;
-    if (wp.forceField) {
+    if constexpr (!PLAIN) {
+        F = F - contact;
+        F = F + cilia * (R)m.cilia;
+    }
+    if (!PLAIN && wp.forceField) {
         FormulaVars fv = wp.fv;
         fv.x = s.pos.x;
         fv.y = s.pos.y;
@@ -473,8 +508,10 @@ VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt 
     }
     V3<R> fric = F;
     bool staticFric = s.flags & VF_STATIC_FRICTION;
+    bool onFloor = false; // floor enabled and penetrating at the start of the step
     if (wp.floorEnabled) {
         float pen = floor_penetration(m, s.temp, s.pos.z);
+        onFloor = pen >= 0;
         if (pen >= 0) {
             V3<R> vel = s.linMom * (R)m.massInverse;
             float normalForce = m.penetrationStiffness * pen;
@@ -498,7 +535,7 @@ VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt 
     fric = F - fric;
     s.linMom = s.linMom + F * dt;
     V3<R> tr = s.linMom * (dt * (R)m.massInverse);
-    if (wp.floorEnabled && floor_penetration(m, s.temp, s.pos.z) >= 0) {
+    if (onFloor) {
         R work = fric.x * tr.x + fric.y * tr.y;
         R hKe = (R(0.5) * (R)m.massInverse) * (s.linMom.x * s.linMom.x + s.linMom.y * s.linMom.y);
         if (hKe + work <= R(0))
@@ -510,7 +547,12 @@ VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt 
     } else
         staticFric = false;
     s.pos = {s.pos.x + (double)tr.x, s.pos.y + (double)tr.y, s.pos.z + (double)tr.z};
-
+    return staticFric;
+}
+template <class R, bool PLAIN = false> VXD void voxel_rotate(const DVoxMat &m, const WorldStepParams &wp, const VoxExt *ext, VoxState<R> &s, V3<R> Msum) {
+    const R dt = (R)wp.dt;
+    if constexpr (PLAIN)
+        ext = nullptr;
     V3<R> Mo = qrot(s.orient, Msum);
     if (ext)
         Mo = Mo + V3<R>{(R)ext->moment.x, (R)ext->moment.y, (R)ext->moment.z};
@@ -522,6 +564,24 @@ VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt 
         R inv = rsqrtf(n2);
         s.orient = {s.orient.w * inv, s.orient.x * inv, s.orient.y * inv, s.orient.z * inv};
     }
+}
+// VX3 only: a voxel resting on the floor in static friction has its angular momentum cleared (VX3/VX3_Voxel.cu:258-264)
+VXD bool voxel_zero_angmom(const DVoxMat &m, const WorldStepParams &wp, bool staticFric, float temp, double newZ) {
+    return wp.vx3 && wp.floorEnabled && staticFric && floor_penetration(m, temp, newZ) >= 0;
+}
+template <class R, bool PLAIN = false>
+VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt *ext, V3<double> nominalPos, VoxState<R> &s, V3<R> Fsum, V3<R> Msum,
+                      V3<R> contact, V3<R> cilia) {
+    if constexpr (PLAIN)
+        ext = nullptr;
+    if (ext && ext->dof == VX3B_DOF_ALL) {
+        s.pos = nominalPos + ext->translation;
+        s.orient = {(R)ext->rotationQ.w, (R)ext->rotationQ.x, (R)ext->rotationQ.y, (R)ext->rotationQ.z};
+        s.linMom = s.angMom = V3<R>{R(0), R(0), R(0)};
+        return;
+    }
+    const bool staticFric = voxel_translate<R, PLAIN>(m, wp, ext, s, Fsum, contact, cilia);
+    voxel_rotate<R, PLAIN>(m, wp, ext, s, Msum);
     if (ext && ext->dof) { // partial dof fixes (VX3/VX3_Voxel.cu:222-257)
         const uint32_t f = ext->dof;
         if (f & VX3B_DOF_TX) {
@@ -559,7 +619,7 @@ VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt 
             }
         }
     }
-    if (wp.vx3 && wp.floorEnabled && staticFric && floor_penetration(m, s.temp, s.pos.z) >= 0) // VX3/VX3_Voxel.cu:258-264
+    if (voxel_zero_angmom(m, wp, staticFric, s.temp, s.pos.z))
         s.angMom = V3<R>{R(0), R(0), R(0)};
     s.flags = staticFric ? VF_STATIC_FRICTION : 0;
 }
