@@ -131,7 +131,9 @@ template <class R> class Engine : public EngineBase {
     size_t brickSmem = 0;
     bool brickLean = true;
     int brickDimsUsed[3] = {0, 0, 0};
-    int brickGrid = 0, brickThreads = 256;
+    int brickGrid = 0, brickThreads = 256, nBrickWorlds = 0;
+    bool brickDoesWorldStep = false;
+    std::vector<int> brickWorldList;
     struct BrickHost {
         std::vector<BrickB> bricks;
         std::vector<int32_t> glist, borig, lorig;
@@ -733,6 +735,8 @@ template <class R> class Engine : public EngineBase {
                 dims[big] = (dims[big] + 1) / 2;
                 brickLean = true;
             }
+            nBrickWorlds = (int)bw.size();
+            brickWorldList = bw;
             for (int w : bw) {
                 hW[w].brickOk = 1;
                 if (pre[w].flags & (WF_VARY_TEMP | WF_THERMAL | WF_CILIA))
@@ -965,6 +969,13 @@ template <class R> class Engine : public EngineBase {
             BA.lorig = dLO;
             BA.ldesc = dD;
             BA.bstat = dS;
+            int32_t *dWL = nullptr;
+            int *dTicket = nullptr;
+            if ((rc = dalloc(&dWL, brickWorldList.size(), brickWorldList.data())) != VX3B_OK || (rc = dalloc(&dTicket, 1)) != VX3B_OK)
+                return rc;
+            BA.worldList = dWL;
+            BA.nWorlds = (int)brickWorldList.size();
+            BA.ticket = dTicket;
             BA.nvSlots = (int)bh.borig.size();
             BA.nlSlots = (int)bh.lorig.size();
             for (int k = 0; k < 2; k++) {
@@ -1044,12 +1055,17 @@ template <class R> class Engine : public EngineBase {
             F.bricks += b0;
             if (FA.nBricks > b0)
                 k_fused<R><<<(unsigned)(FA.nBricks - b0), 256, fusedSmem, stream>>>(A, F, fusedCapTab, fusedCapOwn);
+            // every world this step touches is a brick world: k_brick's last CTA does the end-of-step bookkeeping itself
+            brickDoesWorldStep = BA.nBricks > 0 && FA.nBricks <= b0 && !anyCollision && nBrickWorlds == (mixed ? (int)H.size() - numResident : (int)H.size());
             if (BA.nBricks > 0) {
+                const int ws = brickDoesWorldStep ? 1 : 0;
                 if (brickLean)
-                    k_brick<R, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout);
+                    k_brick<R, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive);
                 else
-                    k_brick<R, false><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout);
+                    k_brick<R, false><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive);
             }
+            if (brickDoesWorldStep)
+                return;
         } else if (A.nvTot > v0)
             k_voxels<R><<<vb, 256, 0, stream>>>(A, v0);
         k_world_step<R><<<wb, 128, 0, stream>>>(A, useStop, dActive);
@@ -1097,7 +1113,7 @@ template <class R> class Engine : public EngineBase {
                 return rc;
             CUDA_TRY(cudaGraphLaunch(graphExec, stream));
             const int fusedLaunches = (FA.nBricks > (mixed ? fusedBrick0 : 0) ? 1 : 0) + (BA.nBricks > 0 ? 1 : 0);
-            lastLaunches += (int64_t)steps * (fused ? launches_per_step() - 2 + fusedLaunches : launches_per_step()) + 1;
+            lastLaunches += (int64_t)steps * (fused ? (brickDoesWorldStep ? 1 : launches_per_step() - 2 + fusedLaunches) : launches_per_step()) + 1;
             done += steps;
             CUDA_TRY(cudaMemcpyAsync(hActive, dActive, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));

@@ -65,6 +65,9 @@ template <class R> struct BrickArrays {
     const int32_t *lorig;    // brick-order link slot -> global link index
     BrickSet<R> set[2];
     int nvSlots, nlSlots;
+    const int32_t *worldList; // the brick worlds (for the end-of-step bookkeeping folded into k_brick)
+    int nWorlds;
+    int *ticket;              // CTAs that have finished the current launch
 };
 struct BrickCaps {
     int own, halo, owned, haloL, nvm, nlm; // own even
@@ -174,7 +177,22 @@ VXD void brick_link(const DLinkMat &lmat, const LinkLen<R> &len0, const DVoxMat 
     link_update<R, AXIS>(lmat, AXIS, dpos, len, qn, qp, sDamp[ma], sDamp[mb], h, f);
 }
 
-template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L) {
+// k_world_step's job for the brick worlds, by one thread; kept out of line so that the formula evaluator's stack frame and
+// registers stay out of the step kernel proper
+template <class R> __device__ __noinline__ void brick_world_step(WorldD *worlds, const int32_t *worldList, int nWorlds, int useStop, int *activeCount) {
+    const Arrays<R> *none = nullptr; // brick worlds count no target pairs: the arrays are never looked at
+    for (int i = 0; i < nWorlds; i++) {
+        WorldD &W = worlds[worldList[i]];
+        if (!W.active || !(W.flags & WF_BRICK))
+            continue;
+        W.parity ^= 1;
+        world_end_of_step<R, false>(*none, W, useStop);
+        if (W.active && activeCount)
+            atomicAdd(activeCount, 1);
+    }
+}
+
+template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L, int worldStep, int useStop, int *activeCount) {
     using T4 = typename Store<R>::T4;
     using T2 = typename Store<R>::T2;
     extern __shared__ __align__(128) unsigned char smem_brick[];
@@ -205,7 +223,16 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
     // Fill stage `s` with brick B: bulk copies of its runs (+ the gather list of the brick after it, `next`, into its list slot)
     // on the stage's mbarrier by thread 0, halo gathers by everybody.  idx: the brick's gather list (shared or global memory).
     // ft / fnt: this thread's rank among, and the number of, the threads that take part.
-    auto fill = [&](const BrickB &B, int s, const int32_t *idx, const BrickB *next, int nextSlot, int ft, int fnt) {
+    auto fill = [&](const BrickB &B, int s, const int32_t *idx, bool idxShared, const BrickB *next, int nextSlot, int ft, int fnt) {
+        const uint32_t idxS = idxShared ? smem_u32(idx) : 0u;
+        auto index = [&](int i) -> int {
+            if (idxShared) {
+                int g;
+                asm volatile("ld.shared.s32 %0, [%1];" : "=r"(g) : "r"(idxS + 4u * (uint32_t)i));
+                return g;
+            }
+            return __ldg(idx + i);
+        };
         unsigned char *st = smem + L.stage[s];
         const int nOwnPad = (B.nOwn + 1) & ~1;
         if (ft == 0) {
@@ -236,7 +263,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
         const uint32_t dOri = smem_u32(st + L.ori) + (uint32_t)nOwnPad * (uint32_t)sizeof(T4);
 #pragma unroll 1
         for (int i = ft; i < B.nHalo; i += fnt) {
-            const int g = idx[i];
+            const int g = index(i);
             gather16<16>(dPxy + 16u * i, src.pxy + g);
             gather16<16>(dPzt + 16u * i, src.pzt + g);
             gather16<sizeof(T4)>(dOri + (uint32_t)sizeof(T4) * i, src.orient + g);
@@ -244,7 +271,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
         const uint32_t dH0 = smem_u32(st + L.h0), dH1 = smem_u32(st + L.h1), dH2 = smem_u32(st + L.h2);
 #pragma unroll 1
         for (int i = ft; i < B.nHaloL; i += fnt) {
-            const int g = idx[B.nHalo + i];
+            const int g = index(B.nHalo + i);
             gather16<sizeof(T4)>(dH0 + (uint32_t)sizeof(T4) * i, src.lpos2 + g);
             gather16<sizeof(T4)>(dH1 + (uint32_t)sizeof(T4) * i, src.la1 + g);
             gather16<sizeof(T4)>(dH2 + (uint32_t)sizeof(T4) * i, src.la2 + g);
@@ -308,13 +335,13 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             }
             const bool haveNext = k + 1 < cnt && sHdr[k + 1].world == curWorld;
             if (!filled) { // first brick of a round / of a world: nothing was prefetched, indices come from global memory
-                fill(B, s, BA.glist + B.gBeg, haveNext ? &sHdr[k + 1] : nullptr, (k + 1) & 1, tid, nt);
+                fill(B, s, BA.glist + B.gBeg, false, haveNext ? &sHdr[k + 1] : nullptr, (k + 1) & 1, tid, nt);
                 gather_wait_all();
                 __syncthreads();
             }
             mbar_wait(bar0 + 8 * s, (phaseBits >> s) & 1);
             phaseBits ^= 1u << s;
-            filled = haveNext; // brick k+1 is prefetched below, by the warps that run out of links first
+            filled = haveNext; // brick k+1 is prefetched at the end of phase 1
 
             unsigned char *st = smem + L.stage[s];
             const D2 *sPxy = (const D2 *)(st + L.pxy), *sPzt = (const D2 *)(st + L.pzt);
@@ -388,11 +415,13 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             }
             if (diverged)
                 Wp->divergedNow = 1;
-            // prefetch brick k+1 into the other stage (its last readers passed the barrier that ended brick k-1).  The last four
-            // warps do it: they hold the highest link numbers, so they are the ones with an iteration to spare
+            // Prefetch brick k+1 into the other stage (its last readers passed the barrier that ended brick k-1).  The last four warps
+            // do it, after their links: they hold the highest link numbers, so they are the ones with an iteration to spare.
+            // (Issuing it before the links instead costs 20 % - measured, profiles/r01m: it takes issue slots while all 16 warps
+            // still have link work.)
             if (haveNext && tid >= nt - 128) {
                 const bool haveNext2 = k + 2 < cnt && sHdr[k + 2].world == curWorld;
-                fill(sHdr[k + 1], s ^ 1, (const int32_t *)(smem + L.glist[(k + 1) & 1]), haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, tid - (nt - 128), 128);
+                fill(sHdr[k + 1], s ^ 1, (const int32_t *)(smem + L.glist[(k + 1) & 1]), true, haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, tid - (nt - 128), 128);
             }
             __syncthreads();
 
@@ -514,6 +543,19 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             gather_wait_all(); // this thread's gathers for brick k+1 have landed ...
             __syncthreads();   // ... and everybody's have; stage s and the force slots are free again
             s ^= 1;
+        }
+    }
+    // End-of-step bookkeeping of the brick worlds (k_world_step's job) by the last CTA to finish, when the host asked for it:
+    // one launch per time step instead of two.
+    if (worldStep) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(BA.ticket, 1) == (int)gridDim.x - 1) {
+                *BA.ticket = 0;
+                __threadfence();
+                brick_world_step<R>(A.worlds, BA.worldList, BA.nWorlds, useStop, activeCount);
+            }
         }
     }
 }

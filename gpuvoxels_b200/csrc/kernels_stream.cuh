@@ -424,7 +424,8 @@ template <class R> __device__ void compute_target_closeness(const Arrays<R> &A, 
 }
 
 // End-of-step bookkeeping of one world (the serial tail of doTimeStep + the loop head of CUDA_Simulation).
-template <class R> __device__ void world_end_of_step(const Arrays<R> &A, WorldD &W, int useStop) {
+// TARGETS = false: the caller knows the world counts no target pairs (maxDistPair == 0) and passes no arrays
+template <class R, bool TARGETS = true> __device__ void world_end_of_step(const Arrays<R> &A, WorldD &W, int useStop) {
     W.step++;
     if (W.divergedNow) { // doTimeStep returned false: links were updated, voxels were not, time does not advance
         W.diverged = 1;
@@ -448,7 +449,8 @@ template <class R> __device__ void world_end_of_step(const Arrays<R> &A, WorldD 
             double ux = Bx - Ax, uy = By - Ay, uz = Bz - Az, vx = Cx - Bx, vy = Cy - By, vz = Cz - Bz;
             W.recentAngle = acos((ux * vx + uy * vy + uz * vz) / (sqrt(ux * ux + uy * uy + uz * uz) * sqrt(vx * vx + vy * vy + vz * vz)));
         }
-        compute_target_closeness(A, W);
+        if constexpr (TARGETS)
+            compute_target_closeness(A, W);
     }
     W.t += W.dt;
     W.runSteps--;

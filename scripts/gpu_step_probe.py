@@ -1,19 +1,22 @@
-"""Per-step time of the cube workload as a function of run length and graph chunk (where does the time between kernels go?)."""
+"""Per-step device time of the cube workload for a list of brick shapes (engine options brick_x/y/z), early and late in the run.
+usage: gpu_step_probe.py <cube edge> [bx,by,bz ...]"""
 import sys, time
 import gpuvoxels_b200 as gv
 from gpuvoxels_b200 import worlds as W
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [(8, 8, 4)]
 model = gv.Model.from_vxa(W.cube_vxa(n))
-for chunk in (64, 512):
+for shape in shapes:
     ctx = gv.Context(0, gv.FP32)
-    ctx.set_option("chunk", chunk)
+    for k, v in zip("xyz", shape):
+        ctx.set_option("brick_" + k, v)
     ctx.upload([model])
     ctx.run(64)
-    for steps in (64, 512, 512, 2048):
-        t0 = time.perf_counter()
+    out = []
+    for steps in (64, 512, 1024):
         ctx.run(steps)
-        wall = time.perf_counter() - t0
         ms, k = ctx.timing()
-        print(f"chunk {chunk:4d} steps {steps:5d}: device {1e3 * ms / steps:7.1f} us/step, wall {1e6 * wall / steps:7.1f} us/step, launches {k}, total steps so far {ctx.results()[0].steps}")
+        out.append(f"{1e3 * ms / steps:6.1f}")
+    print(f"brick {shape}: us/step after 64 / 128 / 640 steps: {' '.join(out)}   ({k} launches in the last run)", flush=True)
     ctx.close()
