@@ -35,7 +35,7 @@ def parse_args():
     ap.add_argument("--worlds", type=int, default=1024, help="worlds per GPU")
     ap.add_argument("--sim-steps", type=int, default=1000, help="time steps every world advances per bench step")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
-    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 streaming, 2 resident")
+    ap.add_argument("--path", type=int, default=0, help="0 auto (resident + brick/fused), 1 two-kernel streaming, 2 resident, 3 fused, 5 brick")
     ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube"])
     ap.add_argument("--cube", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -75,7 +75,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -311,11 +311,25 @@ def main_ours(args):
             peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md)"
         # dominant kernel: the resident (or streaming link+voxel) step kernel; algorithmic bytes per launch = per-step bytes x steps
         achieved = bytes_per_sim_step * args.sim_steps / ((dev_ms / args.steps) * 1e-3) / 1e9
-        kernel = "k_resident" if (args.path == 2 or (args.path == 0 and args.workload == "xenobot")) else "k_links+k_voxels"
-        traffic = None
+        if args.path == 2 or (args.path == 0 and args.workload == "xenobot"):
+            kernel = "k_resident"  # one launch per size class steps every world through all sim_steps
+        elif args.path in (0, 5):
+            kernel = "k_brick"     # one launch per time step
+        else:
+            kernel = "k_fused" if args.path == 3 else "k_links+k_voxels"
+        # DRAM bytes of the dominant kernel from the newest committed `ncu --set full` capture (profiles/traffic.json, written by
+        # scripts/summarize_profiles.py): for k_brick per launch = per time step; for k_resident summed over the size-class
+        # launches of the captured run (state is loaded and stored once per launch, so it does not scale with sim_steps)
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(kernel)
+            tj = json.load(open(tpath))
+            for tag in sorted(tj):
+                rows = [r for k, v in tj[tag].items() if k.startswith(kernel) for r in v]
+                if rows:
+                    per_launch = [r["dram_bytes"] for r in rows]
+                    traffic = sum(per_launch) / len(per_launch) if kernel == "k_brick" else sum(per_launch)
+                    traffic_src = f"profiles/traffic.json[{tag}]"
         out = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -323,7 +337,7 @@ def main_ours(args):
             "voxels_per_gpu": sum(m.num_voxels for m in models), "links_per_gpu": sum(m.num_links for m in models),
             "wall_s_timed_region": wall_max, "diverged_worlds": int(diverged_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": kernel, "peak_source": peak_src,
+                         "kernel": kernel, "peak_source": peak_src, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_per_sim_step * args.sim_steps,
                          "note": "algorithmic bytes = (112*Nv + 88*Nl) per time step (SURVEY.md 8d) x time steps per launch, rank 0's worlds"},
             "e2e": {"value": e2e_vs_all / e2e_wall_max, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -50,6 +50,7 @@ class WorldDesc(C.Structure):
         ("max_dist_in_voxel_lengths_to_count_as_pair", C.c_double),
         ("save_position_of_all_voxels", C.c_int32), ("initial_temp", C.c_float),
         ("stop_condition", Token * MAX_TOKENS), ("fitness", Token * MAX_TOKENS), ("force_field", (Token * MAX_TOKENS) * 3),
+        ("ghost", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -87,6 +88,11 @@ SYMBOLS = {
     "vx3b_ctx_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "vx3b_batch_upload": (C.c_int, [_P, C.POINTER(WorldDesc), C.c_int]),
     "vx3b_batch_run": (C.c_int, [_P, C.c_int64, C.c_int]),
+    "vx3b_batch_run_async": (C.c_int, [_P, C.c_int64]),
+    "vx3b_batch_halo_set": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int]),
+    "vx3b_batch_halo_record_bytes": (C.c_int, [_P]),
+    "vx3b_batch_halo_export": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
+    "vx3b_batch_halo_import": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
     "vx3b_batch_results": (C.c_int, [_P, C.POINTER(WorldResult)]),
     "vx3b_batch_read_state": (C.c_int, [_P, C.c_int, _DP, _DP, _DP, _DP]),
     "vx3b_batch_read_initial_pos": (C.c_int, [_P, C.c_int, _DP]),

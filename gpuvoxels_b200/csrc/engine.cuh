@@ -123,6 +123,7 @@ template <class R> struct Arrays {
     int32_t *vsurf;  // surface slot (global) or -1
     int32_t *vext;   // index into ext or -1
     short4 *lat;     // lattice ix,iy,iz (w unused)
+    uint8_t *vghost; // 1 = ghost voxel of a slab (include/vx3b200.h section 2b), or nullptr
     double *phase;   // or nullptr
     D4 *baseCilia;   // xyz (w unused) or nullptr
     D2 *ipxy;        // initial positions (results: total_distance_of_all_voxels)

@@ -97,6 +97,13 @@ int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t s) {
 
 int vx3b_batch_upload(vx3b_ctx *ctx, const VX3B_WorldDesc *worlds, int n) { return ctx ? ctx->e->upload(worlds, n) : VX3B_ERR_ARG; }
 int vx3b_batch_run(vx3b_ctx *ctx, int64_t max_steps, int use_stop) { return ctx ? ctx->e->run(max_steps, use_stop) : VX3B_ERR_ARG; }
+int vx3b_batch_run_async(vx3b_ctx *ctx, int64_t steps) { return ctx ? ctx->e->run_async(steps) : VX3B_ERR_ARG; }
+int vx3b_batch_halo_set(vx3b_ctx *ctx, int world, int list_id, const int32_t *voxels, int n) {
+    return ctx ? ctx->e->halo_set(world, list_id, voxels, n) : VX3B_ERR_ARG;
+}
+int vx3b_batch_halo_record_bytes(vx3b_ctx *ctx) { return ctx ? ctx->e->halo_record_bytes() : VX3B_ERR_ARG; }
+int vx3b_batch_halo_export(vx3b_ctx *ctx, int world, int list_id, void *buf) { return ctx ? ctx->e->halo_export(world, list_id, buf) : VX3B_ERR_ARG; }
+int vx3b_batch_halo_import(vx3b_ctx *ctx, int world, int list_id, const void *buf) { return ctx ? ctx->e->halo_import(world, list_id, buf) : VX3B_ERR_ARG; }
 int vx3b_batch_results(vx3b_ctx *ctx, VX3B_WorldResult *out) { return ctx ? ctx->e->results(out) : VX3B_ERR_ARG; }
 int vx3b_batch_read_state(vx3b_ctx *ctx, int world, double *p, double *o, double *l, double *a) {
     return ctx ? ctx->e->read_state(world, p, o, l, a) : VX3B_ERR_ARG;

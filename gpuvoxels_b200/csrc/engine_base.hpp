@@ -19,6 +19,11 @@ class EngineBase {
     virtual int read_initial_pos(int world, double *pos) = 0;
     virtual int read_links(int world, double *pos2, double *a1, double *a2, int32_t *flags) = 0;
     virtual int collision_pairs(int world, int32_t *pairs, int32_t *n) = 0;
+    virtual int run_async(int64_t steps) = 0;
+    virtual int halo_set(int world, int listId, const int32_t *voxels, int n) = 0;
+    virtual int halo_record_bytes() = 0;
+    virtual int halo_export(int world, int listId, void *deviceBuffer) = 0;
+    virtual int halo_import(int world, int listId, const void *deviceBuffer) = 0;
     int device = 0, precision = 32;
     cudaStream_t stream = nullptr;
     bool ownStream = false;

@@ -60,7 +60,7 @@ template <class R> struct BrickArrays {
     const BrickB *bricks;
     const LinkDesc *ldesc;
     const int32_t *glist;    // gather lists (brick-order voxel slots, then link slots)
-    const uint32_t *bstat;   // per brick-order voxel slot: world-local material | link mask << 8 | has boundary conditions << 14
+    const uint32_t *bstat;   // per brick-order voxel slot: world-local material | link mask << 8 | has boundary conditions << 14 | ghost << 15
     const int32_t *borig;    // brick-order voxel slot -> global (API-order) voxel index, -1 for alignment padding
     const int32_t *lorig;    // brick-order link slot -> global link index
     BrickSet<R> set[2];
@@ -461,7 +461,19 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                     }
                     return a;
                 };
+                const bool ghost = stw & (1u << 15); // a voxel another GPU's slab owns: carried through, refreshed by the halo import
                 if (split) { // LEAN only
+                    if (ghost) {
+                        if (!rotRole) {
+                            dst.pxy[vs] = sPxy[i];
+                            dst.pzt[vs] = pzt;
+                            dst.lm[vs] = sLm[i];
+                        } else {
+                            dst.orient[vs] = ori;
+                            dst.am[vs] = sAm[i];
+                        }
+                        continue;
+                    }
                     if (!rotRole) {
                         const D2 pxy = sPxy[i];
                         const T4 lm = sLm[i];
@@ -476,7 +488,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                         dst.lm[vs] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
                         if (sampling) {
                             const double mass = m.mass;
-                            world_accumulate(Wp->comAcc, B.world, m.isMeasured != 0, v.pos.x * mass, v.pos.y * mass, v.pos.z * mass, mass);
+                            world_accumulate(Wp->comAcc, B.world, m.isMeasured != 0 && !ghost, v.pos.x * mass, v.pos.y * mass, v.pos.z * mass, mass);
                         }
                     } else {
                         const T4 am = sAm[i];
@@ -493,9 +505,9 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                 v.linMom = {lm.x, lm.y, lm.z};
                 v.angMom = (v.flags & VF_ZERO_ANGMOM) ? V3<R>{R(0), R(0), R(0)} : V3<R>{am.x, am.y, am.z};
                 v.flags &= VF_STATIC_FRICTION;
-                bool fixedMat = false;
+                bool fixedMat = ghost;
                 if constexpr (!LEAN)
-                    fixedMat = vx3 && m.fixed;
+                    fixedMat = ghost || (vx3 && m.fixed);
                 if (!fixedMat) {
                     const V3<R> F = sum_slots(0), M = sum_slots(3);
                     V3<R> contact{R(0), R(0), R(0)}, cilia{R(0), R(0), R(0)};
@@ -537,7 +549,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                 dst.am[vs] = mk4<R>(v.angMom.x, v.angMom.y, v.angMom.z, R(0));
                 if (sampling) {
                     const double mass = m.mass;
-                    world_accumulate(Wp->comAcc, B.world, m.isMeasured != 0, v.pos.x * mass, v.pos.y * mass, v.pos.z * mass, mass);
+                    world_accumulate(Wp->comAcc, B.world, m.isMeasured != 0 && !ghost, v.pos.x * mass, v.pos.y * mass, v.pos.z * mass, mass);
                 }
             }
             gather_wait_all(); // this thread's gathers for brick k+1 have landed ...
@@ -622,6 +634,44 @@ template <class R> __global__ void k_brick_unpack(Arrays<R> A, BrickArrays<R> BA
             }
         }
     }
+}
+
+// ---- halo exchange of a body cut into slabs (include/vx3b200.h section 2b) -------------------------------------------------
+// One record per listed voxel: what the link pass of the neighbouring slab reads from it.
+template <class R> struct HaloRec {
+    double x, y, z;
+    unsigned long long packed; // temperature | flags, as stored in pzt
+    typename Store<R>::T4 orient;
+};
+// resident: the state lives in the brick-ordered sets (between asynchronous runs), else in the API-order arrays
+template <class R> __global__ void k_halo_export(Arrays<R> A, BrickArrays<R> BA, int world, const int32_t *vox, const int32_t *slots, int n, int resident, HaloRec<R> *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    D2 a, b;
+    typename Store<R>::T4 o;
+    if (resident) {
+        const BrickSet<R> &s = BA.set[A.worlds[world].parity];
+        a = s.pxy[slots[i]], b = s.pzt[slots[i]], o = s.orient[slots[i]];
+    } else
+        a = A.pxy[vox[i]], b = A.pzt[vox[i]], o = A.orient[vox[i]];
+    HaloRec<R> r;
+    r.x = a.x, r.y = a.y, r.z = b.x;
+    r.packed = (unsigned long long)__double_as_longlong(b.y);
+    r.orient = o;
+    out[i] = r;
+}
+template <class R> __global__ void k_halo_import(Arrays<R> A, BrickArrays<R> BA, int world, const int32_t *vox, const int32_t *slots, int n, int resident, const HaloRec<R> *in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const HaloRec<R> r = in[i];
+    const D2 a{r.x, r.y}, b{r.z, __longlong_as_double((long long)r.packed)};
+    if (resident) {
+        const BrickSet<R> &s = BA.set[A.worlds[world].parity];
+        s.pxy[slots[i]] = a, s.pzt[slots[i]] = b, s.orient[slots[i]] = r.orient;
+    } else
+        A.pxy[vox[i]] = a, A.pzt[vox[i]] = b, A.orient[vox[i]] = r.orient;
 }
 
 } // namespace vx3b

@@ -294,7 +294,7 @@ template <class R> __global__ void __launch_bounds__(256) k_reduce_com(Arrays<R>
     bool measured = false;
     if (in) {
         const DVoxMat &m = A.vmats[A.vmat[v]];
-        measured = m.isMeasured != 0;
+        measured = m.isMeasured != 0 && !(A.vghost && A.vghost[v]); // a ghost is measured by the slab that owns it
         V3<double> p = load_pos(A, v, nullptr, nullptr);
         mass = m.mass;
         x = p.x * mass, y = p.y * mass, z = p.z * mass;

@@ -132,6 +132,10 @@ typedef struct VX3B_WorldDesc {
     VX3B_Token stop_condition[VX3B_MAX_TOKENS]; /* empty (op[0]==END) = never stops by formula */
     VX3B_Token fitness[VX3B_MAX_TOKENS];
     VX3B_Token force_field[3][VX3B_MAX_TOKENS]; /* x,y,z; empty = no field */
+
+    /* One body over several GPUs (section 2b): [nv] or NULL; 1 = ghost, a copy of a voxel another GPU's slab owns.  Ghosts are
+     * never integrated; their state arrives through vx3b_batch_halo_import.  Links between two ghosts must not be listed. */
+    const uint8_t *ghost;
 } VX3B_WorldDesc;
 
 /* Numeric fields of VX3_SimulationResult (VX3_SimulationResult.h:4-24). */
@@ -200,6 +204,21 @@ int vx3b_ctx_timing(vx3b_ctx *ctx, float *device_ms, int64_t *kernel_launches);
 int64_t vx3b_ctx_total_voxel_steps(vx3b_ctx *ctx); /* sum over worlds of nv*steps in the last run */
 /* torch interop: run on an existing stream (cudaStream_t as integer); 0 = own stream */
 int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t cuda_stream);
+
+/* ---------------------------------------------------------------- 2b. one body over several GPUs ----
+ * No reference counterpart: a reference world never spans devices.  The body is cut into slabs; each
+ * slab is uploaded as one world holding its own voxels plus one ghost layer per cut face (VX3B_WorldDesc.ghost) and every link
+ * with at least one own end - a cut link is stepped on both sides from identical inputs, so its history stays identical without
+ * a force return trip.  Per time step: vx3b_batch_run_async(ctx, 1), export the boundary voxels the neighbours hold as ghosts,
+ * exchange the buffers (NCCL send/recv on the same stream), import into the own ghosts.
+ * State stays in the engine's internal order between asynchronous runs; every read-back call synchronises it first. */
+int vx3b_batch_run_async(vx3b_ctx *ctx, int64_t steps); /* enqueue `steps` steps on the context's stream: no host sync, no stop formula */
+/* register voxel list `list_id` (0..7) of `world`: creation-order voxel indices, copied */
+int vx3b_batch_halo_set(vx3b_ctx *ctx, int world, int list_id, const int32_t *voxels, int n);
+int vx3b_batch_halo_record_bytes(vx3b_ctx *ctx); /* bytes per voxel record: pos 3 x f64, temperature | flags, orientation 4 x f32/f64 */
+/* pack / unpack the current records of a registered list into / from a DEVICE buffer of n * record_bytes, on the context's stream */
+int vx3b_batch_halo_export(vx3b_ctx *ctx, int world, int list_id, void *device_buffer);
+int vx3b_batch_halo_import(vx3b_ctx *ctx, int world, int list_id, const void *device_buffer);
 
 /* ---------------------------------------------------------------- 3. job -------------
  * Replaces vx3_node_worker main + VX3_SimulationManager::start (vx3_node_worker.cu:32-142,

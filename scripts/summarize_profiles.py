@@ -21,10 +21,12 @@ os.makedirs(OUT, exist_ok=True)
 
 
 def launches():
-    src = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
-    if not os.path.exists(src):
-        return
-    shutil.copy(src, os.path.join(OUT, f"{tag}_launches.csv"))
+    for src in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"launches*_{tag}.csv"))):
+        launches_one(src, os.path.basename(src)[len("launches"):-len(f"_{tag}.csv")])
+
+
+def launches_one(src, name):
+    shutil.copy(src, os.path.join(OUT, f"{tag}{name}_launches.csv"))
     lines = [l for l in open(src) if not l.startswith("==")]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
@@ -38,7 +40,7 @@ def launches():
         a[0] += 1
         a[1] += v
     tot = sum(t for _, t in agg.values()) or 1
-    with open(os.path.join(OUT, f"{tag}_launches_summary.txt"), "w") as f:
+    with open(os.path.join(OUT, f"{tag}{name}_launches_summary.txt"), "w") as f:
         f.write("ncu --metrics gpu__time_duration.sum --clock-control none (command: see scripts/gpu_round.sh)\n")
         f.write("per-launch times are serialised and cold-cache: compare SHARES of the step, not absolutes\n\n")
         for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
