@@ -15,7 +15,7 @@ import numpy as np
 from . import _abi
 from ._abi import FP32, FP64, WorldDesc, WorldResult  # noqa: F401
 
-__all__ = ["Model", "Context", "SimulationManager", "FP32", "FP64", "VX3Error", "lib"]
+__all__ = ["Model", "ArrayModel", "Context", "SimulationManager", "FP32", "FP64", "VX3Error", "lib"]
 
 
 class VX3Error(RuntimeError):
@@ -166,6 +166,47 @@ def _abi_err_state():
     return -5
 
 
+class ArrayModel:
+    """A world description assembled from numpy arrays (a slab of a bigger Model, gpuvoxels_b200.slab): same `.desc`,
+    `.num_voxels`, `.num_links`, `.array()` surface as Model.  Material tables and world scalars are shared with `parent`."""
+
+    _PTR = {"lattice": C.c_int16, "voxel_mat": C.c_int32, "phase_offset": C.c_double, "base_cilia": C.c_double, "shift_cilia": C.c_double,
+            "dof_fixed": C.c_uint8, "ext_force": C.c_float, "ext_moment": C.c_float, "ext_translation": C.c_double, "ext_rotation": C.c_double,
+            "link_neg": C.c_int32, "link_pos": C.c_int32, "link_axis": C.c_uint8, "link_mat": C.c_int32, "ghost": C.c_uint8}
+
+    def __init__(self, parent, arrays):
+        self.parent = parent
+        d = WorldDesc()
+        C.memmove(C.byref(d), C.byref(parent.desc), C.sizeof(WorldDesc))  # scalars, formulas, material tables
+        self._arrays = {}
+        for name, ctype in self._PTR.items():
+            a = arrays.get(name)
+            if a is None:
+                setattr(d, name, C.POINTER(ctype)())
+                continue
+            a = np.ascontiguousarray(a, dtype=np.dtype(ctype))
+            self._arrays[name] = a
+            setattr(d, name, a.ctypes.data_as(C.POINTER(ctype)))
+        d.num_voxels = len(self._arrays["voxel_mat"])
+        d.num_links = len(self._arrays["link_neg"])
+        self._desc = d
+
+    @property
+    def desc(self):
+        return self._desc
+
+    @property
+    def num_voxels(self):
+        return self._desc.num_voxels
+
+    @property
+    def num_links(self):
+        return self._desc.num_links
+
+    def array(self, name):
+        return self._arrays[name].copy()
+
+
 class Context:
     """One device context: a batch of worlds resident in HBM, stepped by the CUDA engine."""
 
@@ -193,6 +234,23 @@ class Context:
 
     def run(self, max_steps, use_stop_formula=False):
         _check(lib().vx3b_batch_run(self._h, int(max_steps), 1 if use_stop_formula else 0), "vx3b_batch_run")
+
+    # -- one body over several GPUs (include/vx3b200.h section 2b) ---------------------------------
+    def run_async(self, steps):
+        _check(lib().vx3b_batch_run_async(self._h, int(steps)), "vx3b_batch_run_async")
+
+    def halo_set(self, world, list_id, voxels):
+        v = np.ascontiguousarray(voxels, dtype=np.int32)
+        _check(lib().vx3b_batch_halo_set(self._h, int(world), int(list_id), v.ctypes.data_as(C.POINTER(C.c_int32)), len(v)), "vx3b_batch_halo_set")
+
+    def halo_record_bytes(self):
+        return _check(lib().vx3b_batch_halo_record_bytes(self._h), "vx3b_batch_halo_record_bytes")
+
+    def halo_export(self, world, list_id, device_ptr):
+        _check(lib().vx3b_batch_halo_export(self._h, int(world), int(list_id), C.c_void_p(int(device_ptr))), "vx3b_batch_halo_export")
+
+    def halo_import(self, world, list_id, device_ptr):
+        _check(lib().vx3b_batch_halo_import(self._h, int(world), int(list_id), C.c_void_p(int(device_ptr))), "vx3b_batch_halo_import")
 
     def results(self):
         out = (WorldResult * self._n)()

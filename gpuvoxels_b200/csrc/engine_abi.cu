@@ -4,6 +4,7 @@
 #include <string>
 
 #include "engine_base.hpp"
+#include "host_dt.hpp"
 
 namespace vx3b {
 void set_error(const std::string &e);
@@ -97,6 +98,12 @@ int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t s) {
 
 int vx3b_batch_upload(vx3b_ctx *ctx, const VX3B_WorldDesc *worlds, int n) { return ctx ? ctx->e->upload(worlds, n) : VX3B_ERR_ARG; }
 int vx3b_batch_run(vx3b_ctx *ctx, int64_t max_steps, int use_stop) { return ctx ? ctx->e->run(max_steps, use_stop) : VX3B_ERR_ARG; }
+int vx3b_world_time_step(const VX3B_WorldDesc *world, double *dt) {
+    if (!world || !dt)
+        return VX3B_ERR_ARG;
+    *dt = (double)vx3b::world_time_step(*world);
+    return VX3B_OK;
+}
 int vx3b_batch_run_async(vx3b_ctx *ctx, int64_t steps) { return ctx ? ctx->e->run_async(steps) : VX3B_ERR_ARG; }
 int vx3b_batch_halo_set(vx3b_ctx *ctx, int world, int list_id, const int32_t *voxels, int n) {
     return ctx ? ctx->e->halo_set(world, list_id, voxels, n) : VX3B_ERR_ARG;

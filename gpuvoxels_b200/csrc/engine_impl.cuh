@@ -15,6 +15,7 @@
 
 #include "engine.cuh"
 #include "engine_base.hpp"
+#include "host_dt.hpp"
 #include "kernels_brick.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_resident.cuh"
@@ -56,47 +57,6 @@ struct WorldHost {
     float dt;
 };
 
-// recommended time step exactly as the reference computes it (VX3: double, VX2: float)
-static double recommended_dt(const VX3B_WorldDesc &d) {
-    const bool vx3 = !d.vx2_compat;
-    if (vx3) { // VX3/VX3_VoxelyzeKernel.cu:184-217
-        double maxF2 = 0.0f;
-        for (int l = 0; l < d.num_links; l++) {
-            double m1 = d.voxel_mats[d.voxel_mat[d.link_neg[l]]].mass, m2 = d.voxel_mats[d.voxel_mat[d.link_pos[l]]].mass;
-            double f2 = d.link_mats[d.link_mat[l]].a1 / (m1 < m2 ? m1 : m2);
-            if (f2 > maxF2)
-                maxF2 = f2;
-        }
-        if (maxF2 <= 0.0f)
-            for (int v = 0; v < d.num_voxels; v++) {
-                const VX3B_VoxelMaterial &m = d.voxel_mats[d.voxel_mat[v]];
-                double f2 = m.E * m.nomSize / m.mass;
-                if (f2 > maxF2)
-                    maxF2 = f2;
-            }
-        if (maxF2 <= 0.0f)
-            return 0.0f;
-        return 1.0f / (6.283185f * sqrt(maxF2));
-    }
-    float maxF2 = 0.0f; // old/Voxelyze.cpp:286-311
-    for (int l = 0; l < d.num_links; l++) {
-        float m1 = d.voxel_mats[d.voxel_mat[d.link_neg[l]]].mass, m2 = d.voxel_mats[d.voxel_mat[d.link_pos[l]]].mass;
-        float f2 = d.link_mats[d.link_mat[l]].a1 / (m1 < m2 ? m1 : m2);
-        if (f2 > maxF2)
-            maxF2 = f2;
-    }
-    if (maxF2 <= 0.0f)
-        for (int v = 0; v < d.num_voxels; v++) {
-            const VX3B_VoxelMaterial &m = d.voxel_mats[d.voxel_mat[v]];
-            float f2 = (float)(m.E * m.nomSize / m.mass);
-            if (f2 > maxF2)
-                maxF2 = f2;
-        }
-    if (maxF2 <= 0.0f)
-        return 0.0f;
-    return (float)(1.0f / (6.283185f * sqrtf(maxF2)));
-}
-
 static bool formula_empty(const VX3B_Token *t) { return t[0].op == VX3B_MT_END; }
 
 template <class R> class Engine : public EngineBase {
@@ -133,6 +93,13 @@ template <class R> class Engine : public EngineBase {
     int brickDimsUsed[3] = {0, 0, 0};
     int brickGrid = 0, brickThreads = 256, nBrickWorlds = 0;
     bool brickDoesWorldStep = false;
+    bool brickResident = false; // the truth lives in the brick-ordered sets (after vx3b_batch_run_async); API-order arrays are stale
+    std::vector<int32_t> hVoxSlot; // global voxel -> brick-order slot (-1: not a brick world's voxel)
+    struct HaloList {
+        int world = -1, n = 0;
+        int32_t *dVox = nullptr, *dSlots = nullptr;
+    };
+    HaloList halo[8];
     std::vector<int> brickWorldList;
     struct BrickHost {
         std::vector<BrickB> bricks;
@@ -185,6 +152,9 @@ template <class R> class Engine : public EngineBase {
     int upload(const VX3B_WorldDesc *worlds, int n) override {
         CUDA_TRY(cudaSetDevice(device));
         release_graphs();
+        brickResident = false;
+        for (auto &hl : halo)
+            hl = HaloList{};
         bufs.clear();
         H.clear();
         hTiles.clear();
@@ -303,6 +273,8 @@ template <class R> class Engine : public EngineBase {
         std::vector<T2> am(nvTot);
         std::vector<int32_t> vmat(nvTot), vworld(nvTot), vlinks(6 * nvTot, -1), vsurf(nvTot, -1), vext(nvTot, -1), surf;
         std::vector<short4> lat(nvTot);
+        std::vector<uint8_t> vghost(nvTot, 0);
+        bool anyGhost = false;
         std::vector<D4> baseCilia(nvTot);
         std::vector<DExt> ext;
         std::vector<T4> lpos2(nlTot), lzero(nlTot);
@@ -459,6 +431,10 @@ template <class R> class Engine : public EngineBase {
                 vmat[g] = (int)vmo + d.voxel_mat[v];
                 vworld[g] = w;
                 lat[g] = make_short4(ix, iy, iz, 0);
+                if (d.ghost && d.ghost[v]) {
+                    vghost[g] = 1;
+                    anyGhost = true;
+                }
                 D4 bc{0, 0, 0, 0};
                 if (d.base_cilia) {
                     bc.x = d.base_cilia[v * 3];
@@ -621,7 +597,7 @@ template <class R> class Engine : public EngineBase {
                                 if (vlinks[(size_t)dir * nvTot + g] >= 0)
                                     mk |= 1u << dir;
                             bh.borig.push_back(g);
-                            bh.bstat.push_back((uint32_t)(vmat[g] - W.vmatOff) | (mk << 8) | (vext[g] >= 0 ? 1u << 14 : 0u));
+                            bh.bstat.push_back((uint32_t)(vmat[g] - W.vmatOff) | (mk << 8) | (vext[g] >= 0 ? 1u << 14 : 0u) | (vghost[g] ? 1u << 15 : 0u));
                             if (vext[g] >= 0)
                                 brickLean = false;
                         }
@@ -737,6 +713,20 @@ template <class R> class Engine : public EngineBase {
             }
             nBrickWorlds = (int)bw.size();
             brickWorldList = bw;
+            hVoxSlot.assign(anyGhost ? nvTot : 0, -1);
+            if (anyGhost) {
+                for (size_t sl = 0; sl < bh.borig.size(); sl++)
+                    if (bh.borig[sl] >= 0)
+                        hVoxSlot[bh.borig[sl]] = (int32_t)sl;
+                std::vector<char> isBrick(n, 0);
+                for (int w : bw)
+                    isBrick[w] = 1;
+                for (int w = 0; w < n; w++)
+                    if (worlds[w].ghost && !isBrick[w]) {
+                        set_error("vx3b_batch_upload: world " + std::to_string(w) + " has ghost voxels but is not stepped by the brick path (select option path = 5; no collision / force field / targets)");
+                        return VX3B_ERR_ARG;
+                    }
+            }
             for (int w : bw) {
                 hW[w].brickOk = 1;
                 if (pre[w].flags & (WF_VARY_TEMP | WF_THERMAL | WF_CILIA))
@@ -775,6 +765,9 @@ template <class R> class Engine : public EngineBase {
         UP(vsurf, vsurf);
         UP(vext, vext);
         UP(lat, lat);
+        if (anyGhost) {
+            UP(vghost, vghost);
+        }
         UP(ipxy, ipxy);
         UP(ipz, ipz);
         UP(ext, ext);
@@ -945,7 +938,7 @@ template <class R> class Engine : public EngineBase {
                     (rc = dalloc(&A.alt.la1, nlTot)) != VX3B_OK || (rc = dalloc(&A.alt.la2, nlTot)) != VX3B_OK)
                     return rc;
                 fusedSmem = FusedLayout<R>(fusedCapTab, fusedCapOwn).total;
-                CUDA_TRY(cudaFuncSetAttribute(k_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fusedSmem));
+                CUDA_TRY(cudaFuncSetAttribute(k_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin)); // the limit is per function, not per context: never lower it
                 if (getenv("VX3B_DEBUG"))
                     fprintf(stderr, "[vx3b] fused path: %zu bricks (%dx%dx%d), table <= %d voxels, own <= %d, %zu links incl. %.1f%% recomputed, %zu B shared memory\n",
                             bricks.size(), BX, BY, BZ, fusedCapTab, fusedCapOwn, blinks.size(), 100.0 * (blinks.size() - (double)nlTot) / std::max<size_t>(nlTot, 1), fusedSmem);
@@ -985,8 +978,8 @@ template <class R> class Engine : public EngineBase {
                     (rc = dalloc(&S.la1, BA.nlSlots)) != VX3B_OK || (rc = dalloc(&S.la2, BA.nlSlots)) != VX3B_OK)
                     return rc;
             }
-            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brickSmem));
-            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)brickSmem));
+            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin)); // per function, shared by every context
+            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
             // persistent grid: as many CTAs as fit at once, each stepping consecutive bricks in chunks
             int numSm = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev));
@@ -1175,7 +1168,9 @@ template <class R> class Engine : public EngineBase {
         k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)maxSteps, useStop, resident ? 1 : 0, fused ? 1 : 0);
         lastLaunches++;
         const unsigned nbb = (unsigned)((std::max(BA.nvSlots, BA.nlSlots) + 255) / 256);
-        if (fused && BA.nBricks > 0) { // API-order state -> brick order
+        if (brickResident && !(fused && BA.nBricks > 0) && (rc = ensure_api_state()) != VX3B_OK)
+            return rc;
+        if (fused && BA.nBricks > 0 && !brickResident) { // API-order state -> brick order
             k_brick_pack<R><<<nbb, 256, 0, stream>>>(A, BA);
             lastLaunches++;
         }
@@ -1197,6 +1192,7 @@ template <class R> class Engine : public EngineBase {
             }
             k_clear_parity<R><<<wb, 128, 0, stream>>>(A);
             lastLaunches++;
+            brickResident = false;
         }
         if (A.nvTot) {
             k_reduce_com<R><<<(unsigned)((A.nvTot + 255) / 256), 256, 0, stream>>>(A, 1);
@@ -1217,6 +1213,104 @@ template <class R> class Engine : public EngineBase {
         return VX3B_OK;
     }
 
+    // ---- one body over several GPUs: asynchronous stepping with the state kept in brick order, halo lists ----------------------
+    // Brings the API-order arrays (and the end-of-run reductions) up to date after asynchronous runs; a no-op otherwise.
+    int ensure_api_state() {
+        if (!brickResident)
+            return VX3B_OK;
+        CUDA_TRY(cudaSetDevice(device));
+        const unsigned wb = (A.nWorlds + 127) / 128, nbb = (unsigned)((std::max(BA.nvSlots, BA.nlSlots) + 255) / 256);
+        k_brick_unpack<R><<<nbb, 256, 0, stream>>>(A, BA);
+        k_clear_parity<R><<<wb, 128, 0, stream>>>(A);
+        k_reduce_com<R><<<(unsigned)((A.nvTot + 255) / 256), 256, 0, stream>>>(A, 1);
+        k_world_finish<R><<<wb, 128, 0, stream>>>(A, 1);
+        CUDA_TRY(cudaGetLastError());
+        brickResident = false;
+        return VX3B_OK;
+    }
+    int run_async(int64_t steps) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (H.empty() || BA.nBricks == 0 || nBrickWorlds != (int)H.size() || !fusedAllWorlds || FA.nBricks > 0) {
+            set_error("vx3b_batch_run_async: every world must be on the brick path (option path = 5 before upload; no collision, force field or targets)");
+            return VX3B_ERR_STATE;
+        }
+        const unsigned wb = (A.nWorlds + 127) / 128, nbb = (unsigned)((std::max(BA.nvSlots, BA.nlSlots) + 255) / 256);
+        k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)steps, 0, 0, 1);
+        if (!brickResident) {
+            k_brick_pack<R><<<nbb, 256, 0, stream>>>(A, BA);
+            brickResident = true;
+        }
+        int64_t done = 0;
+        while (done < steps) {
+            const int c = (int)std::min<int64_t>(chunk, steps - done);
+            int rc = build_graph(c, 0, false, true);
+            if (rc != VX3B_OK)
+                return rc;
+            CUDA_TRY(cudaGraphLaunch(graphExec, stream));
+            done += c;
+        }
+        return VX3B_OK;
+    }
+    int halo_record_bytes() override { return (int)sizeof(HaloRec<R>); }
+    int halo_set(int world, int listId, const int32_t *voxels, int n) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (!check_world(world) || listId < 0 || listId >= 8 || n < 0 || (n > 0 && !voxels)) {
+            set_error("vx3b_batch_halo_set: bad world, list id or list");
+            return VX3B_ERR_ARG;
+        }
+        const WorldHost &h = H[world];
+        std::vector<int32_t> vox(n), slots(n);
+        for (int i = 0; i < n; i++) {
+            if (voxels[i] < 0 || voxels[i] >= h.nv) {
+                set_error("vx3b_batch_halo_set: voxel index out of range");
+                return VX3B_ERR_ARG;
+            }
+            vox[i] = h.voff + voxels[i];
+            slots[i] = hVoxSlot.empty() ? -1 : hVoxSlot[vox[i]];
+            if (slots[i] < 0 && BA.nBricks > 0 && !hVoxSlot.empty()) {
+                set_error("vx3b_batch_halo_set: voxel is not on the brick path");
+                return VX3B_ERR_ARG;
+            }
+        }
+        if (hVoxSlot.empty() && BA.nBricks > 0) { // no ghost anywhere in the batch: build the slot map now
+            std::vector<int32_t> borig(BA.nvSlots);
+            CUDA_TRY(cudaMemcpy(borig.data(), BA.borig, borig.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            hVoxSlot.assign(A.nvTot, -1);
+            for (size_t sl = 0; sl < borig.size(); sl++)
+                if (borig[sl] >= 0)
+                    hVoxSlot[borig[sl]] = (int32_t)sl;
+            for (int i = 0; i < n; i++)
+                slots[i] = hVoxSlot[vox[i]];
+        }
+        HaloList &L = halo[listId];
+        L.world = world;
+        L.n = n;
+        int rc;
+        if ((rc = dalloc(&L.dVox, n, vox.data())) != VX3B_OK || (rc = dalloc(&L.dSlots, n, slots.data())) != VX3B_OK)
+            return rc;
+        CUDA_TRY(cudaStreamSynchronize(stream)); // the staging vectors die here
+        return VX3B_OK;
+    }
+    int halo_transfer(int world, int listId, void *buf, bool exporting) {
+        CUDA_TRY(cudaSetDevice(device));
+        if (listId < 0 || listId >= 8 || halo[listId].world != world || !buf) {
+            set_error("vx3b_batch_halo_export/import: list not registered for this world");
+            return VX3B_ERR_ARG;
+        }
+        const HaloList &L = halo[listId];
+        if (L.n == 0)
+            return VX3B_OK;
+        const unsigned nb = (unsigned)((L.n + 127) / 128);
+        if (exporting)
+            k_halo_export<R><<<nb, 128, 0, stream>>>(A, BA, world, L.dVox, L.dSlots, L.n, brickResident ? 1 : 0, (HaloRec<R> *)buf);
+        else
+            k_halo_import<R><<<nb, 128, 0, stream>>>(A, BA, world, L.dVox, L.dSlots, L.n, brickResident ? 1 : 0, (const HaloRec<R> *)buf);
+        CUDA_TRY(cudaGetLastError());
+        return VX3B_OK;
+    }
+    int halo_export(int world, int listId, void *buf) override { return halo_transfer(world, listId, buf, true); }
+    int halo_import(int world, int listId, const void *buf) override { return halo_transfer(world, listId, const_cast<void *>(buf), false); }
+
     int read_steps(std::vector<int64_t> &out) {
         std::vector<WorldD> hW(H.size());
         CUDA_TRY(cudaMemcpyAsync(hW.data(), A.worlds, hW.size() * sizeof(WorldD), cudaMemcpyDeviceToHost, stream));
@@ -1228,6 +1322,11 @@ template <class R> class Engine : public EngineBase {
 
     int results(VX3B_WorldResult *out) override {
         CUDA_TRY(cudaSetDevice(device));
+        {
+            int rcs = ensure_api_state();
+            if (rcs != VX3B_OK)
+                return rcs;
+        }
         if (!out || H.empty()) {
             set_error("vx3b_batch_results: nothing uploaded");
             return VX3B_ERR_STATE;
@@ -1288,6 +1387,11 @@ template <class R> class Engine : public EngineBase {
 
     int read_state(int world, double *pos, double *orient, double *lin, double *ang) override {
         CUDA_TRY(cudaSetDevice(device));
+        {
+            int rcs = ensure_api_state();
+            if (rcs != VX3B_OK)
+                return rcs;
+        }
         if (!check_world(world))
             return VX3B_ERR_ARG;
         const WorldHost &h = H[world];
@@ -1345,6 +1449,11 @@ template <class R> class Engine : public EngineBase {
 
     int read_links(int world, double *pos2, double *a1, double *a2, int32_t *flags) override {
         CUDA_TRY(cudaSetDevice(device));
+        {
+            int rcs = ensure_api_state();
+            if (rcs != VX3B_OK)
+                return rcs;
+        }
         if (!check_world(world))
             return VX3B_ERR_ARG;
         const WorldHost &h = H[world];
@@ -1386,6 +1495,11 @@ template <class R> class Engine : public EngineBase {
 
     int collision_pairs(int world, int32_t *pairs, int32_t *n) override {
         CUDA_TRY(cudaSetDevice(device));
+        {
+            int rcs = ensure_api_state();
+            if (rcs != VX3B_OK)
+                return rcs;
+        }
         if (!check_world(world) || !n)
             return VX3B_ERR_ARG;
         if (!recordPairs) {

@@ -212,6 +212,9 @@ int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t cuda_stream);
  * a force return trip.  Per time step: vx3b_batch_run_async(ctx, 1), export the boundary voxels the neighbours hold as ghosts,
  * exchange the buffers (NCCL send/recv on the same stream), import into the own ghosts.
  * State stays in the engine's internal order between asynchronous runs; every read-back call synchronises it first. */
+/* host-only: the time step a world takes when uploaded (VX3: (float)(DtFrac * recommendedTimeStep), VX3_VoxelyzeKernel.cu:184-254).
+ * Slabs of one body must all step with the WHOLE body's value: pass it to each slab context as option "dt_override". */
+int vx3b_world_time_step(const VX3B_WorldDesc *world, double *dt);
 int vx3b_batch_run_async(vx3b_ctx *ctx, int64_t steps); /* enqueue `steps` steps on the context's stream: no host sync, no stop formula */
 /* register voxel list `list_id` (0..7) of `world`: creation-order voxel indices, copied */
 int vx3b_batch_halo_set(vx3b_ctx *ctx, int world, int list_id, const int32_t *voxels, int n);

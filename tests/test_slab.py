@@ -1,0 +1,180 @@
+"""One body over several GPUs (gpuvoxels_b200/slab.py): the slab decomposition and its exchange plan on the
+CPU - invariants of split_body, and two gloo ranks that really exchange their boundary lists - and, on the GPU, slabs stepped as
+separate contexts with halo exchange against the same body stepped whole."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import gpuvoxels_b200 as gv
+from gpuvoxels_b200 import slab
+from gpuvoxels_b200 import worlds as W
+
+
+def bodies():
+    return {"cube7": gv.Model.from_vxa(W.cube_vxa(7)), "xenobot": gv.Model.from_vxa(W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(9)),
+            "block": gv.Model.from_vxa(W.small_block_vxa())}
+
+
+@pytest.mark.parametrize("name", ["cube7", "xenobot", "block"])
+@pytest.mark.parametrize("n_parts,axis", [(2, 2), (3, 2), (2, 0)])
+def test_split_body_invariants(name, n_parts, axis):
+    model = bodies()[name]
+    lat = model.array("lattice")
+    if lat[:, axis].max() - lat[:, axis].min() + 1 < n_parts:
+        pytest.skip("fewer layers than slabs")
+    parts = slab.split_body(model, n_parts, axis)
+    nv, nl = model.num_voxels, model.num_links
+    owner = np.full(nv, -1)
+    link_seen = np.zeros(nl, dtype=int)
+    full_links = {(a, b): i for i, (a, b) in enumerate(zip(model.array("link_neg"), model.array("link_pos")))}
+    for p in parts:
+        g = p.global_index
+        assert np.all(np.diff(g) > 0)  # creation order kept
+        assert np.all(owner[g[p.own]] == -1)
+        owner[g[p.own]] = p.rank
+        assert np.array_equal(p.model.array("ghost").astype(bool), ~p.own)
+        assert np.array_equal(p.model.array("lattice"), lat[g]) and np.array_equal(p.model.array("voxel_mat"), model.array("voxel_mat")[g])
+        sn, sp = p.model.array("link_neg"), p.model.array("link_pos")
+        assert np.all(p.own[sn] | p.own[sp])  # no ghost-ghost link
+        for a, b, ax, lm in zip(g[sn], g[sp], p.model.array("link_axis"), p.model.array("link_mat")):
+            i = full_links[(a, b)]
+            link_seen[i] += 1
+            assert model.array("link_axis")[i] == ax and model.array("link_mat")[i] == lm
+        # every link of an own voxel is present: its degree in the slab equals its degree in the body
+        deg_full = np.bincount(np.concatenate([model.array("link_neg"), model.array("link_pos")]), minlength=nv)
+        deg_sub = np.bincount(np.concatenate([sn, sp]), minlength=len(g))
+        assert np.array_equal(deg_sub[p.own], deg_full[g[p.own]])
+        assert set(p.ghost_lo) | set(p.ghost_hi) == set(np.nonzero(~p.own)[0]) and not set(p.ghost_lo) & set(p.ghost_hi)
+    assert np.all(owner >= 0)
+    cut = owner[model.array("link_neg")] != owner[model.array("link_pos")]
+    assert np.array_equal(link_seen, 1 + cut.astype(int))  # a cut link lives on both sides, every other link once
+    assert parts[0].ghost_lo.size == 0 and parts[-1].ghost_hi.size == 0
+    dt = slab.body_time_step(model)
+    assert dt > 0 and dt == np.float32(dt)
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = gv.Model.from_vxa(W.cube_vxa(6))
+    part = slab.split_body(model, world)[rank]
+    lat = model.array("lattice")
+    # the record a rank would pack for a boundary voxel: here its global number and lattice cell
+    rec = lambda idx: torch.from_numpy(np.concatenate([part.global_index[idx][:, None], lat[part.global_index[idx]]], axis=1).astype(np.int64))
+    got = {}
+    ops = []
+    if rank > 0:
+        got["lo"] = torch.empty((len(part.ghost_lo), 4), dtype=torch.int64)
+        ops += [dist.P2POp(dist.isend, rec(part.send_lo), rank - 1), dist.P2POp(dist.irecv, got["lo"], rank - 1)]
+    if rank < world - 1:
+        got["hi"] = torch.empty((len(part.ghost_hi), 4), dtype=torch.int64)
+        ops += [dist.P2POp(dist.isend, rec(part.send_hi), rank + 1), dist.P2POp(dist.irecv, got["hi"], rank + 1)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    ok = True
+    for side, idx in (("lo", part.ghost_lo), ("hi", part.ghost_hi)):
+        if side in got:
+            ok = ok and torch.equal(got[side], rec(idx)) and len(idx) == 36
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok), part.num_own, int((~part.own).sum())))
+
+
+def test_two_gloo_ranks_exchange_their_boundary_layers():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert outs == [(0, True, 108, 36), (1, True, 108, 36)]
+
+
+def run_slabs(model, n_parts, steps, precision, options=None):
+    import torch
+    parts = slab.split_body(model, n_parts)
+    dt = slab.body_time_step(model)
+    stream = torch.cuda.Stream(0)
+    runners = [slab.SlabRunner(p, 0, precision, dt, options, stream=stream) for p in parts]
+    with torch.cuda.stream(stream):
+        for _ in range(steps):
+            for r in runners:
+                r.step_begin()
+            for lo, hi in zip(runners[:-1], runners[1:]):  # same device, same stream: the exchange is two device copies per cut
+                hi.buf[slab.GHOST_LO].copy_(lo.buf[slab.SEND_HI])
+                lo.buf[slab.GHOST_HI].copy_(hi.buf[slab.SEND_LO])
+            for r in runners:
+                r.step_end()
+    torch.cuda.synchronize()
+    nv = model.num_voxels
+    out = {"pos": np.zeros((nv, 3)), "orient": np.zeros((nv, 4)), "linMom": np.zeros((nv, 3)), "angMom": np.zeros((nv, 3))}
+    for r in runners:
+        st, g = r.own_state()
+        for k in out:
+            out[k][g] = st[k]
+        assert r.ctx.results()[0].steps == steps
+        r.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [gv.FP64, gv.FP32])
+@pytest.mark.parametrize("n_parts", [2, 3])
+def test_slabs_with_halo_exchange_equal_the_whole_body_bit_for_bit(precision, n_parts):
+    """Every voxel and every link is stepped by the same code from the same inputs whichever slab it lands in, so the sliced
+    run must reproduce the whole-body run exactly - in both precisions - including the cut links' history on both sides."""
+    steps = 150
+    for model, opts in ((gv.Model.from_vxa(W.cube_vxa(9)), dict(brick_x=4, brick_y=3, brick_z=2)),
+                        (gv.Model.from_vxa(W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(9)), None)):
+        whole = gv.Context(0, precision)
+        whole.set_option("path", 5)
+        for k, v in (opts or {}).items():
+            whole.set_option(k, v)
+        whole.upload([model])
+        whole.run(steps)
+        ref = whole.read_state(0)
+        whole.close()
+        got = run_slabs(model, n_parts, steps, precision, opts)
+        for k in ("pos", "orient", "linMom", "angMom"):
+            assert np.array_equal(got[k], ref[k]), (k, np.abs(got[k] - ref[k]).max())
+
+
+@pytest.mark.gpu
+def test_asynchronous_runs_keep_state_in_brick_order_until_read_back():
+    """vx3b_batch_run_async leaves the state in the engine's internal order; any read-back must synchronise it, and mixing
+    asynchronous and synchronous runs must give what one synchronous run gives."""
+    model = gv.Model.from_vxa(W.cube_vxa(6))
+    a, b = gv.Context(0, gv.FP64), gv.Context(0, gv.FP64)
+    for c in (a, b):
+        c.set_option("path", 5)
+        c.upload([model])
+    a.run(90)
+    b.run_async(20)
+    b.run_async(30)
+    assert b.results()[0].steps == 50
+    b.run(25)
+    b.run_async(15)
+    sa, sb = a.read_state(0), b.read_state(0)
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    ra, rb = a.results()[0], b.results()[0]
+    assert ra.steps == rb.steps == 90 and ra.current_time == rb.current_time
+    assert np.allclose(ra.current_com, rb.current_com, rtol=1e-12, atol=0)
+    with pytest.raises(gv.VX3Error):
+        c = gv.Context(0, gv.FP64)
+        c.upload([model])  # automatic path: a body this small is stepped by k_resident, which run_async does not drive
+        c.run_async(5)
+    a.close()
+    b.close()
