@@ -36,7 +36,8 @@ def parse_args():
     ap.add_argument("--sim-steps", type=int, default=1000, help="time steps every world advances per bench step")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--path", type=int, default=0, help="0 auto (resident + brick/fused), 1 two-kernel streaming, 2 resident, 3 fused, 5 brick")
-    ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube"])
+    ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube", "slab"],
+                    help="xenobot: BASELINE configs[1] (worlds sharded over the GPUs); cube: configs[2] on one GPU; slab: one --cube^3 body cut into --gpus slabs with NCCL halo exchange (configs[4], second part)")
     ap.add_argument("--cube", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-worlds", type=int, default=8)
@@ -44,6 +45,11 @@ def parse_args():
 
 
 def workload_config(args):
+    if args.workload == "slab":
+        return {"workload": f"BASELINE configs[4] (second part): ONE {args.cube}^3-voxel soft body under gravity with floor contact, split into {args.gpus} z-slab(s)",
+                "worlds_per_gpu": 1, "sim_steps_per_step": args.sim_steps,
+                "parallelism": f"{args.gpus} slab(s), one per GPU; per time step one NCCL send/recv of the boundary layer to each neighbour (pos, temperature, orientation)",
+                "l2": "slab state larger than L2"}
     if args.workload == "cube":
         return {"workload": f"BASELINE configs[2]: single {args.cube}^3-voxel soft body under gravity with floor contact, no self-collision",
                 "worlds_per_gpu": 1, "sim_steps_per_step": args.sim_steps, "parallelism": "replicas", "l2": "state larger than L2 + explicit L2 flush between steps"}
@@ -55,7 +61,7 @@ def workload_config(args):
 def build_worlds(args, rank):
     import gpuvoxels_b200 as gv
     from gpuvoxels_b200 import worlds as W
-    if args.workload == "cube":
+    if args.workload in ("cube", "slab"):
         return [gv.Model.from_vxa(W.cube_vxa(args.cube))], [(W.cube_vxa(args.cube), None)]
     base = W.xenobot_base_vxa()
     texts = [(base, W.xenobot_vxd(rank * args.worlds + i)) for i in range(args.worlds)]
@@ -353,6 +359,107 @@ def main_ours(args):
     return 0
 
 
+def main_slab(args):
+    """One body over N GPUs (strong scaling: the body is fixed, N slabs).  A bench step = --sim-steps time steps, each followed by
+    the halo exchange; device time from CUDA events on the slab's stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import gpuvoxels_b200 as gv
+    from gpuvoxels_b200 import slab as S
+    from gpuvoxels_b200 import worlds as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t_host = time.perf_counter()
+    model = gv.Model.from_vxa(W.cube_vxa(args.cube))
+    part = S.split_body(model, world)[rank]
+    dt = S.body_time_step(model)
+    t_split = time.perf_counter() - t_host
+    run = S.SlabRunner(part, local, args.precision, dt)
+    b = run.buf
+
+    def exchange():
+        if world == 1:
+            return
+        ops = []
+        if rank > 0:
+            ops += [dist.P2POp(dist.isend, b[S.SEND_LO], rank - 1), dist.P2POp(dist.irecv, b[S.GHOST_LO], rank - 1)]
+        if rank < world - 1:
+            ops += [dist.P2POp(dist.isend, b[S.SEND_HI], rank + 1), dist.P2POp(dist.irecv, b[S.GHOST_HI], rank + 1)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()  # stream-ordered: the slab's stream waits for the transfer, the host does not
+
+    def steps(n):
+        with torch.cuda.stream(run.stream):
+            for _ in range(n):
+                run.step_begin()
+                exchange()
+                run.step_end()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        steps(args.sim_steps)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    t0 = time.perf_counter()
+    with torch.cuda.stream(run.stream):
+        ev[0].record()
+    for _ in range(args.steps):
+        steps(args.sim_steps)
+    with torch.cuda.stream(run.stream):
+        ev[1].record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop() if sampler else None
+    res = run.ctx.results()[0]
+    own = part.num_own
+    nl_own = int(part.model.num_links)
+    stats = torch.tensor([dev_ms, wall], dtype=torch.float64, device="cuda")
+    work = torch.tensor([float(own) * args.sim_steps * args.steps, float(res.diverged), float(run.halo_bytes_per_step)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_max = stats.tolist()
+    vs_all, diverged_all, halo_all = work.tolist()
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md)"
+        nsteps = args.sim_steps * args.steps
+        alg = (112 * model.num_voxels + 88 * model.num_links) if args.precision == 32 else (216 * model.num_voxels + 160 * model.num_links)
+        achieved = alg * nsteps / (dev_ms_max * 1e-3) / 1e9 / world  # per GPU
+        out = {"metric": METRIC, "value": vs_all / (dev_ms_max * 1e-3), "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32 arithmetic, f64 positions" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args),
+               "voxels_total": model.num_voxels, "links_total": model.num_links, "voxels_rank0_incl_ghosts": part.model.num_voxels, "links_rank0": nl_own,
+               "us_per_time_step": 1e3 * dev_ms_max / nsteps, "halo_bytes_per_time_step_all_ranks": int(halo_all), "wall_s_timed_region": wall_max,
+               "host_split_s_rank0": t_split, "diverged_worlds": int(diverged_all),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s per GPU", "frac": achieved / peak, "traffic": None, "kernel": "k_brick",
+                            "peak_source": peak_src, "note": "algorithmic bytes of the WHOLE body (112*Nv + 88*Nl per time step) / N GPUs / device time"},
+               "e2e": {"value": vs_all / wall_max, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "what": "same timed region by host wall clock (per-step launches + NCCL calls included); the body is uploaded once before it"},
+               "gpu_launches": int(nsteps * (1 + (2 if world > 1 else 0) * 2)), "clocks": clocks}
+        print(json.dumps(out))
+    run.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 if __name__ == "__main__":
     a = parse_args()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
+    sys.exit(main_reference(a) if a.impl == "reference" else main_slab(a) if a.workload == "slab" else main_ours(a))

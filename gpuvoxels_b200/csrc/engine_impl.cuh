@@ -4,13 +4,16 @@
 // VX3_SimulationManager::startKernel / collectResults (VX3/VX3_SimulationManager.cu:384-458) and, through the
 // kernels it launches, CUDA_Simulation + doTimeStep.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.cuh"
@@ -51,8 +54,43 @@ struct DeviceBuf { // owns one cudaMalloc allocation
     }
 };
 
+// Device memory of one context: a few large cudaMalloc chunks handed out in 256-byte aligned pieces and REUSED by the next upload
+// (a generation after a generation has the same shape: steady-state uploads allocate nothing; cudaMalloc of ~40 arrays per
+// upload cost 24 ms of a 100 ms upload - scripts/gpu_upload_probe.py).
+struct DeviceArena {
+    std::vector<std::unique_ptr<DeviceBuf>> chunks;
+    size_t cur = 0, off = 0;
+    void reset() { cur = off = 0; }
+    void release() {
+        chunks.clear();
+        reset();
+    }
+    cudaError_t alloc(size_t bytes, void **out) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (;;) {
+            if (cur < chunks.size() && off + bytes <= chunks[cur]->bytes) {
+                *out = (char *)chunks[cur]->p + off;
+                off += bytes;
+                return cudaSuccess;
+            }
+            if (cur + 1 < chunks.size()) {
+                cur++;
+                off = 0;
+                continue;
+            }
+            auto c = std::make_unique<DeviceBuf>();
+            cudaError_t e = c->alloc(std::max<size_t>(bytes, (size_t)64 << 20));
+            if (e != cudaSuccess)
+                return e;
+            chunks.push_back(std::move(c));
+            cur = chunks.size() - 1;
+            off = 0;
+        }
+    }
+};
+
 struct WorldHost {
-    int nv, nl, ns, voff, loff, soff;
+    int nv, nl, ns, voff, loff, soff, numMeasured;
     double recommendedDt;
     float dt;
 };
@@ -66,7 +104,20 @@ template <class R> class Engine : public EngineBase {
   public:
     Arrays<R> A;
     std::vector<WorldHost> H;
-    std::vector<std::unique_ptr<DeviceBuf>> bufs;
+    DeviceArena arena;
+    struct Staging { // host staging arrays of upload(), kept between uploads
+        std::vector<D2> pxy, pzt, ipxy;
+        std::vector<double> ipz, phase;
+        std::vector<T4> orient, lm, lpos2;
+        std::vector<T2> am;
+        std::vector<int32_t> vmat, vworld, vlinks, vsurf, vext, surf, lworld;
+        std::vector<short4> lat;
+        std::vector<uint8_t> vghost;
+        std::vector<D4> baseCilia;
+        std::vector<DExt> ext;
+        std::vector<int2> lends;
+        std::vector<uint32_t> lmeta;
+    } staging;
     std::vector<ContactTile> hTiles;
     ContactTile *dTiles = nullptr;
     int *dActive = nullptr;
@@ -122,7 +173,9 @@ template <class R> class Engine : public EngineBase {
         if (evBegin)
             cudaEventDestroy(evBegin);
         release_classes();
-        bufs.clear();
+        if (stream)
+            cudaStreamSynchronize(stream);
+        arena.release();
         if (ownStream && stream)
             cudaStreamDestroy(stream);
     }
@@ -138,14 +191,13 @@ template <class R> class Engine : public EngineBase {
     }
 
     template <class T> int dalloc(T **out, size_t count, const T *src = nullptr) {
-        auto b = std::make_unique<DeviceBuf>();
-        CUDA_TRY(b->alloc(std::max<size_t>(count, 1) * sizeof(T)));
-        *out = (T *)b->p;
+        void *p = nullptr;
+        CUDA_TRY(arena.alloc(std::max<size_t>(count, 1) * sizeof(T), &p));
+        *out = (T *)p;
         if (src && count)
-            CUDA_TRY(cudaMemcpyAsync(b->p, src, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, stream));
         else
-            CUDA_TRY(cudaMemsetAsync(b->p, 0, std::max<size_t>(count, 1) * sizeof(T), stream));
-        bufs.push_back(std::move(b));
+            CUDA_TRY(cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), stream));
         return VX3B_OK;
     }
 
@@ -155,7 +207,9 @@ template <class R> class Engine : public EngineBase {
         brickResident = false;
         for (auto &hl : halo)
             hl = HaloList{};
-        bufs.clear();
+        if (stream)
+            CUDA_TRY(cudaStreamSynchronize(stream)); // nothing of the previous batch is still in flight when its memory is reused
+        arena.reset();
         H.clear();
         hTiles.clear();
         release_classes();
@@ -182,9 +236,18 @@ template <class R> class Engine : public EngineBase {
             set_error("vx3b_batch_upload: batch too large for 32-bit indices");
             return VX3B_ERR_ARG;
         }
+        const bool dbgT = getenv("VX3B_DEBUG") != nullptr;
+        auto tPrev = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (!dbgT)
+                return;
+            auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[vx3b] upload %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tPrev).count());
+            tPrev = now;
+        };
         // ---- per-world summary: surface count, feature flags, shared-memory need -> k_resident size class ------------------
         struct Pre {
-            int ns = 0, cls = 0;
+            int ns = 0, cls = 0, next = 0; // surface voxels, k_resident size class, voxels with boundary conditions
             uint32_t flags = 0;
             size_t bytes = 0;
             double invCell = 0, listR2 = 0;
@@ -212,8 +275,13 @@ template <class R> class Engine : public EngineBase {
                     deg[a]++;
                     deg[b]++;
                 }
-                for (int v = 0; v < d.num_voxels; v++)
+                for (int v = 0; v < d.num_voxels; v++) {
                     p.ns += deg[v] < 6;
+                    bool bc = d.dof_fixed && d.dof_fixed[v];
+                    for (int k = 0; k < 3 && !bc; k++)
+                        bc = (d.ext_force && d.ext_force[v * 3 + k] != 0) || (d.ext_moment && d.ext_moment[v * 3 + k] != 0);
+                    p.next += bc;
+                }
                 const bool vx3 = !d.vx2_compat;
                 const bool hasFF = !formula_empty(d.force_field[0]) || !formula_empty(d.force_field[1]) || !formula_empty(d.force_field[2]);
                 double maxAlpha = 0, maxSize = d.vox_size;
@@ -265,46 +333,83 @@ template <class R> class Engine : public EngineBase {
         numResident = 0;
         vStream0 = lStream0 = tileStream0 = -1;
         H.resize(n);
+        lap("pre-pass");
         // ---- host staging
+        // The staging arrays persist in the context: a fresh 150 MB of std::vector per upload costs more in page faults than the
+        // staging itself (scripts/gpu_upload_probe.py).  Every element is (re)written below, world by world.
+        Staging &G = staging;
         std::vector<WorldD> hW(n);
-        std::vector<D2> pxy(nvTot), pzt(nvTot), ipxy(nvTot);
-        std::vector<double> ipz(nvTot), phase(nvTot, 0.0);
-        std::vector<T4> orient(nvTot), lm(nvTot);
-        std::vector<T2> am(nvTot);
-        std::vector<int32_t> vmat(nvTot), vworld(nvTot), vlinks(6 * nvTot, -1), vsurf(nvTot, -1), vext(nvTot, -1), surf;
-        std::vector<short4> lat(nvTot);
-        std::vector<uint8_t> vghost(nvTot, 0);
+        auto &pxy = G.pxy, &pzt = G.pzt, &ipxy = G.ipxy;
+        auto &ipz = G.ipz, &phase = G.phase;
+        auto &orient = G.orient, &lm = G.lm;
+        auto &am = G.am;
+        auto &vmat = G.vmat, &vworld = G.vworld, &vlinks = G.vlinks, &vsurf = G.vsurf, &vext = G.vext, &surf = G.surf;
+        auto &lat = G.lat;
+        auto &vghost = G.vghost;
+        auto &baseCilia = G.baseCilia;
+        auto &ext = G.ext;
+        auto &lpos2 = G.lpos2;
+        auto &lends = G.lends;
+        auto &lmeta = G.lmeta;
+        auto &lworld = G.lworld;
+        pxy.resize(nvTot), pzt.resize(nvTot), ipxy.resize(nvTot), ipz.resize(nvTot), phase.resize(nvTot), orient.resize(nvTot), lm.resize(nvTot);
+        am.resize(nvTot), vmat.resize(nvTot), vworld.resize(nvTot), vlinks.resize(6 * nvTot), vsurf.resize(nvTot), vext.resize(nvTot);
+        lat.resize(nvTot), vghost.resize(nvTot), baseCilia.resize(nvTot), lpos2.resize(nlTot), lends.resize(nlTot), lmeta.resize(nlTot), lworld.resize(nlTot);
         bool anyGhost = false;
-        std::vector<D4> baseCilia(nvTot);
-        std::vector<DExt> ext;
-        std::vector<T4> lpos2(nlTot), lzero(nlTot);
-        std::vector<int2> lends(nlTot);
-        std::vector<uint32_t> lmeta(nlTot);
-        std::vector<int32_t> lworld(nlTot);
         std::vector<DVoxMat> vmats(nvm);
         std::vector<DLinkMat> lmats(nlm);
-        bool anyPhase = false, anyCilia = false;
+        std::atomic<bool> anyPhaseA{false}, anyCiliaA{false}, anyGhostA{false};
         anyCollision = false;
-        size_t voff = 0, loff = 0, vmo = 0, lmo = 0;
-        memset(lzero.data(), 0, lzero.size() * sizeof(T4));
-        for (int oi = 0; oi < n; oi++) {
-            const int w = perm[oi];
+        // offsets of every world in the concatenated arrays (layout order), then the worlds are staged in parallel
+        struct Off {
+            size_t v, l, vm, lm, s, e;
+        };
+        std::vector<Off> off(n);
+        {
+            size_t voff = 0, loff = 0, vmo = 0, lmo = 0, so = 0, eo = 0;
+            for (int oi = 0; oi < n; oi++) {
+                const int w = perm[oi];
+                const VX3B_WorldDesc &d = worlds[w];
+                if (pre[w].cls > 0)
+                    numResident++;
+                else if (vStream0 < 0) {
+                    vStream0 = (int)voff;
+                    lStream0 = (int)loff;
+                    tileStream0 = (int)hTiles.size();
+                }
+                off[w] = Off{voff, loff, vmo, lmo, so, eo};
+                if (d.enable_collision) {
+                    anyCollision = true;
+                    for (int f = 0; f < pre[w].ns; f += 128)
+                        hTiles.push_back(ContactTile{w, f});
+                }
+                voff += d.num_voxels;
+                loff += d.num_links;
+                vmo += d.num_voxel_mats;
+                lmo += d.num_link_mats;
+                so += pre[w].ns;
+                eo += pre[w].next;
+            }
+            surf.resize(so);
+            ext.resize(eo);
+        }
+        auto stage_world = [&](int w) {
             const VX3B_WorldDesc &d = worlds[w];
             WorldD &W = hW[w];
             memset(&W, 0, sizeof(W));
-            if (pre[w].cls > 0)
-                numResident++;
-            else if (vStream0 < 0) {
-                vStream0 = (int)voff;
-                lStream0 = (int)loff;
-                tileStream0 = (int)hTiles.size();
-            }
+            const size_t voff = off[w].v, loff = off[w].l, vmo = off[w].vm, lmo = off[w].lm;
+            size_t surfAt = off[w].s, extAt = off[w].e;
+            for (int k = 0; k < 6; k++)
+                std::fill_n(vlinks.begin() + (size_t)k * nvTot + voff, d.num_voxels, -1);
+            std::fill_n(vsurf.begin() + voff, d.num_voxels, -1);
+            std::fill_n(vext.begin() + voff, d.num_voxels, -1);
+            std::fill_n(vghost.begin() + voff, d.num_voxels, (uint8_t)0);
             WorldHost h;
             h.nv = d.num_voxels;
             h.nl = d.num_links;
             h.voff = (int)voff;
             h.loff = (int)loff;
-            h.soff = (int)surf.size();
+            h.soff = (int)surfAt;
             const bool vx3 = !d.vx2_compat;
             // dt: VX3_VoxelyzeKernel.cu:244-254 / caller-side DtFrac*recommendedTimeStep for Voxelyze2
             double opt = recommended_dt(d);
@@ -339,8 +444,6 @@ template <class R> class Engine : public EngineBase {
             memcpy(W.stop, d.stop_condition, sizeof(W.stop));
             memcpy(W.fitnessF, d.fitness, sizeof(W.fitnessF));
             memcpy(W.ff, d.force_field, sizeof(W.ff));
-            if (d.enable_collision)
-                anyCollision = true;
             // materials
             for (int k = 0; k < d.num_voxel_mats; k++) {
                 const VX3B_VoxelMaterial &m = d.voxel_mats[k];
@@ -407,7 +510,7 @@ template <class R> class Engine : public EngineBase {
                 float temp = d.initial_temp;
                 double ph = d.phase_offset ? d.phase_offset[v] : 0.0;
                 if (ph != 0)
-                    anyPhase = true;
+                    anyPhaseA = true;
                 if (vary && !(vx3 && m.fixed)) { // first step's gpu_update_temperature at t = 0
                     double T = d.temp_amplitude * sin(2 * 3.1415926f * (0.0 / d.temp_period + ph));
                     if (!d.enable_expansion && T > 0)
@@ -433,7 +536,7 @@ template <class R> class Engine : public EngineBase {
                 lat[g] = make_short4(ix, iy, iz, 0);
                 if (d.ghost && d.ghost[v]) {
                     vghost[g] = 1;
-                    anyGhost = true;
+                    anyGhostA = true;
                 }
                 D4 bc{0, 0, 0, 0};
                 if (d.base_cilia) {
@@ -441,7 +544,7 @@ template <class R> class Engine : public EngineBase {
                     bc.y = d.base_cilia[v * 3 + 1];
                     bc.z = d.base_cilia[v * 3 + 2];
                     if (d.enable_cilia && (bc.x != 0 || bc.y != 0 || bc.z != 0))
-                        anyCilia = true;
+                        anyCiliaA = true;
                 }
                 baseCilia[g] = bc;
                 uint8_t dof = d.dof_fixed ? d.dof_fixed[v] : 0;
@@ -475,8 +578,8 @@ template <class R> class Engine : public EngineBase {
                         e.rotQ[2] = hy * s;
                         e.rotQ[3] = hz * s;
                     }
-                    vext[g] = (int)ext.size();
-                    ext.push_back(e);
+                    vext[g] = (int)extAt;
+                    ext[extAt++] = e;
                 }
             }
             // links
@@ -510,22 +613,34 @@ template <class R> class Engine : public EngineBase {
                     if (vlinks[(size_t)k * nvTot + voff + v] < 0)
                         interior = false;
                 if (!interior) {
-                    vsurf[voff + v] = (int)surf.size();
-                    surf.push_back((int)(voff + v));
+                    vsurf[voff + v] = (int)surfAt;
+                    surf[surfAt++] = (int)(voff + v);
                 }
             }
-            h.ns = (int)surf.size() - h.soff;
+            h.ns = (int)surfAt - h.soff;
             W.ns = h.ns;
-            if (d.enable_collision)
-                for (int f = 0; f < h.ns; f += 128)
-                    hTiles.push_back(ContactTile{w, f});
+            h.numMeasured = 0;
+            for (int v = 0; v < d.num_voxels; v++)
+                h.numMeasured += d.voxel_mats[d.voxel_mat[v]].isMeasured != 0;
             H[w] = h;
-            voff += d.num_voxels;
-            loff += d.num_links;
-            vmo += d.num_voxel_mats;
-            lmo += d.num_link_mats;
+        };
+        {
+            const int nThreads = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, n}));
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nThreads; t++)
+                pool.emplace_back([&, t] {
+                    for (int oi = t; oi < n; oi += nThreads) // layout order is by size: interleaving balances the threads
+                        stage_world(perm[oi]);
+                });
+            for (int oi = 0; oi < n; oi += nThreads)
+                stage_world(perm[oi]);
+            for (auto &th : pool)
+                th.join();
         }
+        const bool anyPhase = anyPhaseA, anyCilia = anyCiliaA;
+        anyGhost = anyGhostA;
 
+        lap("host staging");
         // ---- brick path plan (host only; kernels_brick.cuh): which worlds, brick tables, shared-memory fit -----------------------
         BrickHost bh;
         BA = BrickArrays<R>{};
@@ -736,6 +851,7 @@ template <class R> class Engine : public EngineBase {
                         brickLean = false;
             }
         }
+        lap("brick plan");
         // ---- device
         if (!stream) {
             CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -773,15 +889,21 @@ template <class R> class Engine : public EngineBase {
         UP(ext, ext);
         UP(surf, surf);
         UP(lpos2, lpos2);
-        UP(la1, lzero);
-        UP(la2, lzero);
+        if ((rc = dalloc(&A.la1, nlTot)) != VX3B_OK) // zero-filled on the device
+            return rc;
+        if ((rc = dalloc(&A.la2, nlTot)) != VX3B_OK) // zero-filled on the device
+            return rc;
         UP(lends, lends);
         UP(lmeta, lmeta);
         UP(lworld, lworld);
-        UP(lfN, lzero);
-        UP(lfP, lzero);
-        UP(lmN, lzero);
-        UP(lmP, lzero);
+        if ((rc = dalloc(&A.lfN, nlTot)) != VX3B_OK) // zero-filled on the device
+            return rc;
+        if ((rc = dalloc(&A.lfP, nlTot)) != VX3B_OK) // zero-filled on the device
+            return rc;
+        if ((rc = dalloc(&A.lmN, nlTot)) != VX3B_OK) // zero-filled on the device
+            return rc;
+        if ((rc = dalloc(&A.lmP, nlTot)) != VX3B_OK) // zero-filled on the device
+            return rc;
         UP(vmats, vmats);
         UP(lmats, lmats);
         if (anyPhase) {
@@ -804,6 +926,7 @@ template <class R> class Engine : public EngineBase {
             return rc;
         if (!hActive)
             CUDA_TRY(cudaMallocHost(&hActive, sizeof(int)));
+        lap("device alloc + H2D enqueue");
         // initial centre of mass (CUDA_Simulation: updateCurrentCenterOfMass + InitializeCenterOfMass)
         if (nvTot) {
             k_reduce_com<R><<<(unsigned)((nvTot + 255) / 256), 256, 0, stream>>>(A, 0);
@@ -944,6 +1067,7 @@ template <class R> class Engine : public EngineBase {
                             bricks.size(), BX, BY, BZ, fusedCapTab, fusedCapOwn, blinks.size(), 100.0 * (blinks.size() - (double)nlTot) / std::max<size_t>(nlTot, 1), fusedSmem);
             }
         }
+        lap("fused tables");
         // ---- brick path: tables and the two brick-ordered buffer sets
         if (!bh.bricks.empty()) {
             BrickB *dB = nullptr;
@@ -992,6 +1116,7 @@ template <class R> class Engine : public EngineBase {
                         bh.bricks.size(), brickDimsUsed[0], brickDimsUsed[1], brickDimsUsed[2], brickCaps.own, brickCaps.halo, brickCaps.owned, brickCaps.haloL,
                         100.0 * (double)bh.recomputed / std::max<size_t>(bh.lorig.size(), 1), brickSmem, brickGrid, brickThreads, BA.chunk, brickLean ? "lean" : "full");
         }
+        lap("brick tables");
         // ---- k_resident size classes: one launch + stream per class
         if (vStream0 < 0) {
             vStream0 = (int)nvTot;
@@ -1026,7 +1151,9 @@ template <class R> class Engine : public EngineBase {
             fprintf(stderr, "[vx3b] %d worlds, %d resident, %d streaming-only\n", n, numResident, n - numResident);
         if (!evBegin)
             CUDA_TRY(cudaEventCreateWithFlags(&evBegin, cudaEventDisableTiming));
+        lap("classes");
         CUDA_TRY(cudaStreamSynchronize(stream)); // host staging vectors die here
+        lap("final sync");
         return VX3B_OK;
     }
 
@@ -1334,10 +1461,6 @@ template <class R> class Engine : public EngineBase {
         std::vector<WorldD> hW(H.size());
         CUDA_TRY(cudaMemcpyAsync(hW.data(), A.worlds, hW.size() * sizeof(WorldD), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        std::vector<int32_t> vmat(A.nvTot);
-        std::vector<DVoxMat> vm(bufsize_of(A.vmats) / sizeof(DVoxMat));
-        CUDA_TRY(cudaMemcpy(vmat.data(), A.vmat, vmat.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(vm.data(), A.vmats, vm.size() * sizeof(DVoxMat), cudaMemcpyDeviceToHost));
         for (size_t w = 0; w < H.size(); w++) {
             const WorldD &W = hW[w];
             VX3B_WorldResult &r = out[w];
@@ -1361,20 +1484,9 @@ template <class R> class Engine : public EngineBase {
             r.stopped = W.stopped;
             r.contact_rebuilds = W.contactRebuilds;
             r.contact_overflows = W.contactOverflows;
-            int measured = 0;
-            for (int v = 0; v < W.nv; v++)
-                if (vm[vmat[W.voff + v]].isMeasured)
-                    measured++;
-            r.num_measured_voxel = measured;
+            r.num_measured_voxel = H[w].numMeasured;
         }
         return VX3B_OK;
-    }
-
-    size_t bufsize_of(const void *p) const {
-        for (auto &b : bufs)
-            if (b->p == p)
-                return b->bytes;
-        return 0;
     }
 
     bool check_world(int world) {
