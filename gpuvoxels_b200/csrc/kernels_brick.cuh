@@ -79,7 +79,8 @@ struct BrickCaps {
 template <class R> struct BrickLayout { // byte offsets into the CTA's dynamic shared memory; computed once on the host
     using T4 = typename Store<R>::T4;
     using T2 = typename Store<R>::T2;
-    uint32_t bar, hdr, glist[2], F, vmat, lmat, damp, len, stage[2];
+    uint32_t bar, hdr, glist0, glistBytes, F, vmat, lmat, damp, len, stage0, stageBytes; // stage s / list slot k at base + s * bytes
+                                                                                           // (no arrays: a dynamically indexed kernel parameter lives in local memory)
     uint32_t pxy, pzt, ori, lm, am, h0, h1, h2, desc; // relative to a stage
     uint32_t total;
     static uint32_t up(size_t x) { return (uint32_t)((x + 127) & ~(size_t)127); }
@@ -93,8 +94,8 @@ template <class R> struct BrickLayout { // byte offsets into the CTA's dynamic s
         };
         bar = take(16);
         hdr = take(sizeof(BrickB) * BRICK_CHUNK);
-        glist[0] = take(sizeof(int32_t) * c.glist());
-        glist[1] = take(sizeof(int32_t) * c.glist());
+        glist0 = take(sizeof(int32_t) * c.glist());
+        glistBytes = take(sizeof(int32_t) * c.glist()) - glist0;
         F = take(sizeof(R) * BRICK_FSTRIDE * c.own);
         vmat = take(sizeof(DVoxMat) * c.nvm);
         lmat = take(sizeof(DLinkMat) * c.nlm);
@@ -111,9 +112,8 @@ template <class R> struct BrickLayout { // byte offsets into the CTA's dynamic s
         h1 = take(sizeof(T4) * (c.owned + c.haloL));
         h2 = take(sizeof(T4) * (c.owned + c.haloL));
         desc = take(sizeof(LinkDesc) * c.links());
-        const uint32_t stageBytes = o;
-        stage[0] = base;
-        stage[1] = base + stageBytes;
+        stageBytes = o;
+        stage0 = base;
         total = base + 2 * stageBytes;
     }
 };
@@ -233,7 +233,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             }
             return __ldg(idx + i);
         };
-        unsigned char *st = smem + L.stage[s];
+        unsigned char *st = smem + L.stage0 + (uint32_t)s * L.stageBytes;
         const int nOwnPad = (B.nOwn + 1) & ~1;
         if (ft == 0) {
             const uint32_t bar = bar0 + 8 * s;
@@ -257,7 +257,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             if (bD)
                 bulk_g2s(smem_u32(st + L.desc), BA.ldesc + B.descBeg, bD, bar);
             if (bG)
-                bulk_g2s(smem_u32(smem + L.glist[nextSlot]), BA.glist + next->gBeg, bG, bar);
+                bulk_g2s(smem_u32(smem + L.glist0 + (uint32_t)nextSlot * L.glistBytes), BA.glist + next->gBeg, bG, bar);
         }
         const uint32_t dPxy = smem_u32(st + L.pxy) + (uint32_t)nOwnPad * 16u, dPzt = smem_u32(st + L.pzt) + (uint32_t)nOwnPad * 16u;
         const uint32_t dOri = smem_u32(st + L.ori) + (uint32_t)nOwnPad * (uint32_t)sizeof(T4);
@@ -304,9 +304,14 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                 dt = W.dt;
                 voxSize = W.voxSize;
                 sampling = vx3 && W.cycle > 0 && ((W.step + 1) % W.cycle == 0);
-                const int par = W.parity;
-                src = BA.set[par];
-                dst = BA.set[par ^ 1];
+                const bool par = W.parity != 0; // field-wise selects: indexing BA.set[] dynamically would put it in local memory
+                const BrickSet<R> &s0 = BA.set[0], &s1 = BA.set[1];
+                src.pxy = par ? s1.pxy : s0.pxy, src.pzt = par ? s1.pzt : s0.pzt, src.orient = par ? s1.orient : s0.orient;
+                src.lm = par ? s1.lm : s0.lm, src.am = par ? s1.am : s0.am;
+                src.lpos2 = par ? s1.lpos2 : s0.lpos2, src.la1 = par ? s1.la1 : s0.la1, src.la2 = par ? s1.la2 : s0.la2;
+                dst.pxy = par ? s0.pxy : s1.pxy, dst.pzt = par ? s0.pzt : s1.pzt, dst.orient = par ? s0.orient : s1.orient;
+                dst.lm = par ? s0.lm : s1.lm, dst.am = par ? s0.am : s1.am;
+                dst.lpos2 = par ? s0.lpos2 : s1.lpos2, dst.la1 = par ? s0.la1 : s1.la1, dst.la2 = par ? s0.la2 : s1.la2;
                 if (active) {
                     __syncthreads(); // nobody still reads the previous world's tables
                     const uint32_t *gv = (const uint32_t *)(A.vmats + W.vmatOff), *gl = (const uint32_t *)(A.lmats + W.lmatOff);
@@ -343,7 +348,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             phaseBits ^= 1u << s;
             filled = haveNext; // brick k+1 is prefetched at the end of phase 1
 
-            unsigned char *st = smem + L.stage[s];
+            unsigned char *st = smem + L.stage0 + (uint32_t)s * L.stageBytes;
             const D2 *sPxy = (const D2 *)(st + L.pxy), *sPzt = (const D2 *)(st + L.pzt);
             const T4 *sOri = (const T4 *)(st + L.ori), *sLm = (const T4 *)(st + L.lm);
             const T4 *sAm = (const T4 *)(st + L.am);
@@ -421,7 +426,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             // still have link work.)
             if (haveNext && tid >= nt - 128) {
                 const bool haveNext2 = k + 2 < cnt && sHdr[k + 2].world == curWorld;
-                fill(sHdr[k + 1], s ^ 1, (const int32_t *)(smem + L.glist[(k + 1) & 1]), true, haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, tid - (nt - 128), 128);
+                fill(sHdr[k + 1], s ^ 1, (const int32_t *)(smem + L.glist0 + (uint32_t)((k + 1) & 1) * L.glistBytes), true, haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, tid - (nt - 128), 128);
             }
             __syncthreads();
 

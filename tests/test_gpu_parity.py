@@ -264,6 +264,25 @@ def test_brick_path_equals_fused_path_bit_for_bit_in_fp64(brick):
     b.close()
 
 
+def test_brick_path_rounds_world_switches_and_empty_worlds():
+    """The persistent loop of k_brick beyond its comfortable case: more bricks than one round of chunks holds (1x1x1 bricks on a
+    27^3 body: 19,683 bricks > 296 CTAs x 64), worlds changing inside a CTA's chunk, a world that stops early (inactive bricks in
+    the middle of a chunk) and worlds with a single voxel.  fp64, bit for bit against k_fused."""
+    models = [gv.Model.from_vxa(W.cube_vxa(1)), gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=0.004, enable_collision=False), W.xenobot_vxd(3)),
+              gv.Model.from_vxa(W.cube_vxa(27)), gv.Model.from_vxa(W.cube_vxa(1)), gv.Model.from_vxa(W.small_block_vxa())]
+    opts = dict(brick_x=1, brick_y=1, brick_z=1)
+    a, b = gpu_run(models, 40, gv.FP64, FUSED, use_stop=True, **opts), gpu_run(models, 40, gv.FP64, BRICK, use_stop=True, **opts)
+    for i in range(len(models)):
+        sa, sb = a.read_state(i), b.read_state(i)
+        for k in ("pos", "orient", "linMom", "angMom"):
+            assert np.array_equal(sa[k], sb[k]), (i, k)
+        ra, rb = a.results()[i], b.results()[i]
+        assert ra.steps == rb.steps and ra.stopped == rb.stopped
+    assert a.results()[1].stopped == 1 and a.results()[1].steps < 40 and a.results()[2].steps == 40
+    a.close()
+    b.close()
+
+
 def test_job_run_writes_the_reference_report_layout():
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "base.vxa"), "w").write(W.xenobot_base_vxa(stop_seconds=0.1).replace("<Simulator>", "<Simulator><SavePositionOfAllVoxels>1</SavePositionOfAllVoxels>", 1))
