@@ -24,7 +24,7 @@ class VoxelMaterial(C.Structure):
         "epsilonFail", "gravMult", "mass", "massInverse", "sqrtMass", "momentInertia", "momentInertiaInverse",
         "_2xSqMxExS", "_2xSqIxExSxSxS")] + [
         ("nomSize", C.c_double), ("Cilia", C.c_double)] + [(n, C.c_int32) for n in (
-            "matid", "fixed", "isTarget", "isMeasured", "sticky", "linear", "pad")]
+            "matid", "fixed", "isTarget", "isMeasured", "sticky", "linear")] + [("rgba", C.c_uint32)]
 
 
 class LinkMaterial(C.Structure):
@@ -51,6 +51,7 @@ class WorldDesc(C.Structure):
         ("save_position_of_all_voxels", C.c_int32), ("initial_temp", C.c_float),
         ("stop_condition", Token * MAX_TOKENS), ("fitness", Token * MAX_TOKENS), ("force_field", (Token * MAX_TOKENS) * 3),
         ("ghost", C.POINTER(C.c_uint8)),
+        ("record_step_size", C.c_int32), ("record_voxel", C.c_int32), ("record_link", C.c_int32),
     ]
 
 
@@ -89,6 +90,8 @@ SYMBOLS = {
     "vx3b_batch_upload": (C.c_int, [_P, C.POINTER(WorldDesc), C.c_int]),
     "vx3b_batch_run": (C.c_int, [_P, C.c_int64, C.c_int]),
     "vx3b_world_time_step": (C.c_int, [C.POINTER(WorldDesc), C.POINTER(C.c_double)]),
+    "vx3b_batch_read_aux": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "vx3b_job_history": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
     "vx3b_batch_run_async": (C.c_int, [_P, C.c_int64]),
     "vx3b_batch_halo_set": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int]),
     "vx3b_batch_halo_record_bytes": (C.c_int, [_P]),

@@ -104,6 +104,7 @@ int vx3b_world_time_step(const VX3B_WorldDesc *world, double *dt) {
     *dt = (double)vx3b::world_time_step(*world);
     return VX3B_OK;
 }
+int vx3b_batch_read_aux(vx3b_ctx *ctx, int world, float *t, float *s) { return ctx ? ctx->e->read_aux(world, t, s) : VX3B_ERR_ARG; }
 int vx3b_batch_run_async(vx3b_ctx *ctx, int64_t steps) { return ctx ? ctx->e->run_async(steps) : VX3B_ERR_ARG; }
 int vx3b_batch_halo_set(vx3b_ctx *ctx, int world, int list_id, const int32_t *voxels, int n) {
     return ctx ? ctx->e->halo_set(world, list_id, voxels, n) : VX3B_ERR_ARG;

@@ -19,6 +19,7 @@ class EngineBase {
     virtual int read_initial_pos(int world, double *pos) = 0;
     virtual int read_links(int world, double *pos2, double *a1, double *a2, int32_t *flags) = 0;
     virtual int collision_pairs(int world, int32_t *pairs, int32_t *n) = 0;
+    virtual int read_aux(int world, float *voxelTemp, float *linkStrain) = 0;
     virtual int run_async(int64_t steps) = 0;
     virtual int halo_set(int world, int listId, const int32_t *voxels, int n) = 0;
     virtual int halo_record_bytes() = 0;

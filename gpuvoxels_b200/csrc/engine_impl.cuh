@@ -1542,6 +1542,37 @@ template <class R> class Engine : public EngineBase {
         return VX3B_OK;
     }
 
+    int read_aux(int world, float *voxelTemp, float *linkStrain) override {
+        CUDA_TRY(cudaSetDevice(device));
+        {
+            int rcs = ensure_api_state();
+            if (rcs != VX3B_OK)
+                return rcs;
+        }
+        if (!check_world(world))
+            return VX3B_ERR_ARG;
+        const WorldHost &h = H[world];
+        if (voxelTemp && h.nv) { // temperature = low word of pzt's second double
+            std::vector<D2> b(h.nv);
+            CUDA_TRY(cudaMemcpyAsync(b.data(), A.pzt + h.voff, sizeof(D2) * h.nv, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            for (int v = 0; v < h.nv; v++) {
+                unsigned long long bits;
+                memcpy(&bits, &b[v].y, 8);
+                const uint32_t lo = (uint32_t)(bits & 0xffffffffu);
+                memcpy(&voxelTemp[v], &lo, 4);
+            }
+        }
+        if (linkStrain && h.nl) { // strain of the last step = la2.w
+            std::vector<T4> a(h.nl);
+            CUDA_TRY(cudaMemcpyAsync(a.data(), A.la2 + h.loff, sizeof(T4) * h.nl, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            for (int l = 0; l < h.nl; l++)
+                linkStrain[l] = (float)a[l].w;
+        }
+        return VX3B_OK;
+    }
+
     int read_initial_pos(int world, double *pos) override {
         CUDA_TRY(cudaSetDevice(device));
         if (!check_world(world) || !pos)

@@ -94,6 +94,7 @@ static VX3B_VoxelMaterial derive_voxel_material(const MatInput &in, float nu, do
     o.nomSize = nomSize;
     o.Cilia = in.Cilia;
     o.matid = in.matid;
+    o.rgba = in.rgba;
     o.fixed = in.fixed;
     o.isTarget = in.isTarget;
     o.isMeasured = in.isMeasured;
@@ -231,6 +232,9 @@ void HostModel::fillDesc(VX3B_WorldDesc *d) const {
     d->vx2_compat = vx2Compat;
     d->max_dist_in_voxel_lengths_to_count_as_pair = maxDistPair;
     d->save_position_of_all_voxels = savePositions;
+    d->record_step_size = recordStepSize;
+    d->record_voxel = recordVoxel;
+    d->record_link = recordLink;
     memcpy(d->stop_condition, stopCondition.data(), sizeof(d->stop_condition));
     memcpy(d->fitness, fitness.data(), sizeof(d->fitness));
     for (int k = 0; k < 3; k++)
@@ -505,6 +509,9 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
     M->enableCilia = ptree_int(*vxa, "Simulator.EnableCilia", 0) != 0;
     M->enableExpansion = ptree_int(*vxa, "Simulator.EnableExpansion", 0) != 0;
     M->savePositions = ptree_int(*vxa, "Simulator.SavePositionOfAllVoxels", 0) != 0;
+    M->recordStepSize = ptree_int(*vxa, "Simulator.RecordHistory.RecordStepSize", 0);
+    M->recordLink = ptree_int(*vxa, "Simulator.RecordHistory.RecordLink", 0);
+    M->recordVoxel = ptree_int(*vxa, "Simulator.RecordHistory.RecordVoxel", 1);
     M->maxDistPair = ptree_double(*vxa, "Simulator.MaxDistInVoxelLengthsToCountAsPair", 0.0);
     if (!parse_math_tree(vxa->find("Simulator.StopCondition.StopConditionFormula"), M->stopCondition, err) ||
         !parse_math_tree(vxa->find("Simulator.FitnessFunction"), M->fitness, err) ||
@@ -625,6 +632,14 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
             m.isTarget = get_int(mech, "isTarget", 0) != 0;
             m.isMeasured = get_int(mech, "isMeasured", 1);
             m.sticky = get_int(mech, "Sticky", 0) != 0;
+            {
+                const XmlNode *disp = pm->child("Display"); // CVXC_Material::ReadXML: Red/Green/Blue/Alpha in 0..1
+                auto chan = [&](const char *name, double dflt) {
+                    int v = (int)((float)get_double(disp, name, dflt) * 255);
+                    return (uint32_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+                };
+                m.rgba = chan("Red", 0.5) | (chan("Green", 0.5) << 8) | (chan("Blue", 0.5) << 16) | (chan("Alpha", 1.0) << 24);
+            }
             paletteToMat.push_back(M->addMaterial(m));
         }
     }

@@ -21,6 +21,7 @@ struct MatInput { // CVX_Material state before derivation (floats, as the refere
     float E = 1.0f, nu = 0.0f, rho = 1.0f, alphaCTE = 0.0f, muStatic = 0.0f, muKinetic = 0.0f;
     float zetaInternal = 1.0f, zetaGlobal = 0.0f, zetaCollision = 0.0f;
     float sigmaFail = -1.0f, epsilonFail = -1.0f;
+    uint32_t rgba = 0xffffffffu; // display colour, (int)(value*255) per channel (VX_Object.h:419-425)
     float nuMemory = 0.0f; // Poisson's ratio as given (muMemory, VX_Sim.cpp:85)
     double Cilia = 0;
     int matid = 0, fixed = 0, isTarget = 0, isMeasured = 1, sticky = 0;
@@ -48,6 +49,7 @@ struct HostModel {
     bool volumeEffects = false;
     bool enableCollision = true, enableCilia = false, enableExpansion = false, vx2Compat = false;
     bool savePositions = false;
+    int recordStepSize = 0, recordVoxel = 1, recordLink = 0; // VXA.Simulator.RecordHistory (VX3_SimulationManager.cu:344-346)
     double maxDistPair = 0;
     std::vector<VX3B_Token> stopCondition, fitness, forceField[3];
 

@@ -260,3 +260,190 @@ extern "C" int vx3b_job_run(const char *input_dir, const char *report_path, int 
             vx3b_model_free(w.model);
     return rcAll;
 }
+
+// ---- .history stream -----------------------------------------------------------------------------------------
+// Replaces the history printf()s of CUDA_Simulation (VX3/VX3_SimulationManager.cu:40-114): same text, produced on the host from
+// read-backs every real_stepsize steps instead of from device-side printf, one world at a time (the reference interleaves the
+// output of concurrently running worlds at random).
+namespace vx3b {
+
+struct HistoryWorld {
+    const VX3B_WorldDesc *d;
+    std::vector<int> surface;            // voxels with a free face, creation order (VX3_VoxelyzeKernel.cu:495-513)
+    std::vector<int> vlinks;             // [nv][6] link per direction or -1
+    std::vector<double> pos, orient;
+    std::vector<float> temp, strain;
+};
+
+// VX3_Voxel::cornerOffset (VX3/VX3_Voxel.cu:147-159) for the all-negative / all-positive corner, returned as float like the reference
+static void corner_offset(const HistoryWorld &H, int v, bool positive, float out[3]) {
+    const VX3B_WorldDesc &d = *H.d;
+    const VX3B_VoxelMaterial &m = d.voxel_mats[d.voxel_mat[v]];
+    const double base = m.nomSize * (double)(1 + H.temp[v] * m.alphaCTE); // baseSize(), VX3_Voxel.h:90-92
+    for (int i = 0; i < 3; i++) {
+        const int l = H.vlinks[(size_t)v * 6 + 2 * i + (positive ? 0 : 1)];
+        double s = positive ? 1.0 : -1.0;
+        if (l >= 0) {
+            const VX3B_LinkMaterial &lm = d.link_mats[d.link_mat[l]];
+            const bool failed = lm.epsilonFail != -1.0f && H.strain[l] > lm.epsilonFail;
+            if (!failed) {
+                // VX3_Link::axialStrain(positiveEnd), strainRatio = E(pos end) / E(neg end) (VX3_Link.cu:72-74)
+                const float ratio = d.voxel_mats[d.voxel_mat[d.link_pos[l]]].E / d.voxel_mats[d.voxel_mat[d.link_neg[l]]].E;
+                const float ax = positive ? 2.0f * H.strain[l] * ratio / (1.0f + ratio) : 2.0f * H.strain[l] / (1.0f + ratio);
+                s = (1 + ax) * (positive ? 1 : -1);
+            }
+        }
+        out[i] = (float)(0.5 * base * s);
+    }
+}
+
+static void write_frame(FILE *f, const HistoryWorld &H, long long j, double t) {
+    const VX3B_WorldDesc &d = *H.d;
+    const double vs = 1 / 0.001;
+    if (d.record_voxel) {
+        fprintf(f, "<<<Step%lld Time:%f>>>", j, t);
+        for (int v : H.surface) {
+            const double *p = &H.pos[3 * (size_t)v], *q = &H.orient[4 * (size_t)v];
+            fprintf(f, "%.1f,%.1f,%.1f,", p[0] * vs, p[1] * vs, p[2] * vs);
+            const double angle = 2.0 * acos(q[0] > 1 ? 1 : q[0]) * 57.29577951308232; // Quat3D::AngleDegrees
+            fprintf(f, "%.1f,%.2f,%.2f,%.2f,", angle, q[1], q[2], q[3]);
+            float nnn[3], ppp[3];
+            corner_offset(H, v, false, nnn);
+            corner_offset(H, v, true, ppp);
+            fprintf(f, "%.1f,%.1f,%.1f,%.1f,%.1f,%.1f,", nnn[0] * vs, nnn[1] * vs, nnn[2] * vs, ppp[0] * vs, ppp[1] * vs, ppp[2] * vs);
+            fprintf(f, "%d,", d.voxel_mats[d.voxel_mat[v]].matid);
+            fprintf(f, "%.1f,", 0.0); // localSignal: signals are not simulated (EnableSignals = 0)
+            fprintf(f, ";");
+        }
+        fprintf(f, "<<<>>>");
+    }
+    if (d.record_link) {
+        fprintf(f, "|[[[%lld]]]", j);
+        for (int l = 0; l < d.num_links; l++) {
+            const double *a = &H.pos[3 * (size_t)d.link_pos[l]], *b = &H.pos[3 * (size_t)d.link_neg[l]];
+            fprintf(f, "%.4f,%.4f,%.4f,", a[0], a[1], a[2]);
+            fprintf(f, "%.4f,%.4f,%.4f,", b[0], b[1], b[2]);
+            fprintf(f, ";");
+        }
+        fprintf(f, "[[[]]]");
+    }
+    fprintf(f, "\n");
+}
+
+} // namespace vx3b
+
+extern "C" int vx3b_job_history(const char *input_dir, const char *out_path, int precision) {
+    using namespace vx3b;
+    if (!input_dir) {
+        set_error("vx3b_job_history: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    std::string dir = input_dir, base;
+    if (!read_file(dir + "/base.vxa", &base)) {
+        set_error("vx3b_job_history: no base.vxa in " + dir);
+        return VX3B_ERR_IO;
+    }
+    std::vector<std::string> files;
+    if (DIR *dd = opendir(dir.c_str())) {
+        while (dirent *e = readdir(dd))
+            if (ends_with_ci(e->d_name, ".vxd"))
+                files.push_back(e->d_name);
+        closedir(dd);
+    }
+    std::sort(files.begin(), files.end());
+    FILE *f = out_path ? fopen(out_path, "w") : stdout;
+    if (!f) {
+        set_error(std::string("vx3b_job_history: cannot write ") + out_path);
+        return VX3B_ERR_IO;
+    }
+    int rc = VX3B_OK;
+    vx3b_ctx *ctx = nullptr;
+    bool any = false; // does any world record? (no GPU work, no context otherwise)
+    for (size_t i = 0; i < files.size() && !any; i++) {
+        std::string vxd;
+        vx3b_model *model = nullptr;
+        if (read_file(dir + "/" + files[i], &vxd) && vx3b_model_from_vxa(base.c_str(), vxd.c_str(), &model) == VX3B_OK) {
+            VX3B_WorldDesc d;
+            vx3b_model_desc(model, &d);
+            any = d.record_step_size != 0;
+            vx3b_model_free(model);
+        }
+    }
+    if (!any) {
+        if (out_path)
+            fclose(f);
+        return VX3B_OK;
+    }
+    if ((rc = vx3b_ctx_create(0, precision, &ctx)) != VX3B_OK) {
+        if (out_path)
+            fclose(f);
+        return rc;
+    }
+    vx3b_ctx_set_option(ctx, "path", 1); // the generic link + voxel kernels: the only ones that keep every link's last strain
+    for (size_t i = 0; i < files.size() && rc == VX3B_OK; i++) {
+        std::string vxd;
+        vx3b_model *model = nullptr;
+        if (!read_file(dir + "/" + files[i], &vxd) || vx3b_model_from_vxa(base.c_str(), vxd.c_str(), &model) != VX3B_OK) {
+            fprintf(stderr, "%s: %s\n", files[i].c_str(), vx3b_last_error()); // the reference prints and carries on
+            continue;
+        }
+        VX3B_WorldDesc d;
+        vx3b_model_desc(model, &d);
+        double dt = 0;
+        vx3b_world_time_step(&d, &dt);
+        if (d.record_step_size && d.num_voxels > 0 && (rc = vx3b_batch_upload(ctx, &d, 1)) == VX3B_OK) {
+            HistoryWorld H;
+            H.d = &d;
+            H.vlinks.assign((size_t)d.num_voxels * 6, -1);
+            for (int l = 0; l < d.num_links; l++) {
+                H.vlinks[(size_t)d.link_neg[l] * 6 + 2 * d.link_axis[l]] = l;
+                H.vlinks[(size_t)d.link_pos[l] * 6 + 2 * d.link_axis[l] + 1] = l;
+            }
+            for (int v = 0; v < d.num_voxels; v++)
+                for (int k = 0; k < 6; k++)
+                    if (H.vlinks[(size_t)v * 6 + k] < 0) {
+                        H.surface.push_back(v);
+                        break;
+                    }
+            H.pos.resize(3 * (size_t)d.num_voxels);
+            H.orient.resize(4 * (size_t)d.num_voxels);
+            H.temp.resize(d.num_voxels);
+            H.strain.resize(std::max(d.num_links, 1));
+            // header (VX3_SimulationManager.cu:40-58)
+            fprintf(f, "\n{{{setting}}}<rescale>0.001</rescale>\n");
+            for (int k = 0; k < d.num_voxel_mats; k++) {
+                const uint32_t c = d.voxel_mats[k].rgba;
+                fprintf(f, "{{{setting}}}<matcolor><id>%d</id><r>%.2f</r><g>%.2f</g><b>%.2f</b><a>%.2f</a></matcolor>\n", d.voxel_mats[k].matid,
+                        (c & 255) / 255., ((c >> 8) & 255) / 255., ((c >> 16) & 255) / 255., ((c >> 24) & 255) / 255.);
+            }
+            fprintf(f, "\n{{{setting}}}<voxel_size>%f</voxel_size>\n", d.vox_size);
+            const double recommended = d.dt_frac != 0 ? dt / d.dt_frac : 0; // dt = float(DtFrac * recommendedTimeStep)
+            const int real_stepsize = (int)(d.record_step_size / (10000 * recommended * d.dt_frac)) + 1;
+            fprintf(f, "real_stepsize: %d ; recommendedTimeStep %f; d_v3->DtFrac %f . \n", real_stepsize, recommended, d.dt_frac);
+            // frames after step j+1 for j = 0, real_stepsize, 2*real_stepsize, ... while the stop condition allows (cap 1e6 steps)
+            long long done = 0;
+            for (long long j = 0; j < 1000000 && rc == VX3B_OK; j += real_stepsize) {
+                const long long target = j + 1;
+                if ((rc = vx3b_batch_run(ctx, target - done, 1)) != VX3B_OK)
+                    break;
+                VX3B_WorldResult r;
+                if ((rc = vx3b_batch_results(ctx, &r)) != VX3B_OK)
+                    break;
+                if (r.steps < target || r.diverged) // stopped by its formula (or diverged) before reaching this frame
+                    break;
+                done = r.steps;
+                if ((rc = vx3b_batch_read_state(ctx, 0, H.pos.data(), H.orient.data(), nullptr, nullptr)) != VX3B_OK ||
+                    (rc = vx3b_batch_read_aux(ctx, 0, H.temp.data(), H.strain.data())) != VX3B_OK)
+                    break;
+                write_frame(f, H, j, r.current_time);
+            }
+        }
+        vx3b_model_free(model);
+    }
+    vx3b_ctx_destroy(ctx);
+    if (out_path)
+        fclose(f);
+    else
+        fflush(f);
+    return rc;
+}

@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     const bool ciliaOn = (wflags & WF_CILIA) && A.baseCilia, varyTemp = (wflags & WF_THERMAL) && W.tempPeriod > 0;
     const bool canFail = wflags & WF_CAN_FAIL, thermal = wflags & WF_THERMAL;
     const float dt = W.dt;
+    const float invDt = 1.0f / dt;
     const double voxSize = W.voxSize, tempAmp = W.tempAmp, tempPeriod = W.tempPeriod, invCell = W.invCell, listR2 = W.listR2;
     const float skinHalf2 = W.skinHalf2;
     const double watchR2 = W.watchR2; // > 0: upper bound of every pair's squared watch distance (uniform constant sizes)
@@ -489,8 +490,16 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
             h.a2v = {sA2[3 * l], sA2[3 * l + 1], sA2[3 * l + 2]};
             h.flags = sLflags[l];
             h.maxStrain = canFail ? sLmax[l] : -1e30f;
-            float dmN = mn.sqrtMassZetaInt2 / ((vx3 && mn.fixed) ? 0.0f : dt);
-            float dmP = mp.sqrtMassZetaInt2 / ((vx3 && mp.fixed) ? 0.0f : dt);
+            // dampingMultiplier 2*sqrt(m)*zeta / previousDt (VX3_Voxel.h:206-208; Fixed voxels never set previousDt): the validation
+            // build divides as the reference does, the float build multiplies by 1/dt (an IEEE float division is ~10 instructions)
+            float dmN, dmP;
+            if constexpr (sizeof(R) == 8) {
+                dmN = mn.sqrtMassZetaInt2 / ((vx3 && mn.fixed) ? 0.0f : dt);
+                dmP = mp.sqrtMassZetaInt2 / ((vx3 && mp.fixed) ? 0.0f : dt);
+            } else {
+                dmN = mn.sqrtMassZetaInt2 * ((vx3 && mn.fixed) ? __int_as_float(0x7f800000) : invDt);
+                dmP = mp.sqrtMassZetaInt2 * ((vx3 && mp.fixed) ? __int_as_float(0x7f800000) : invDt);
+            }
             LinkForces<R> f;
             link_update<R>(lmat, axis, dpos, voxSize, qn, qp, restLen, dmN, dmP, h, f);
             sP2[3 * l] = h.pos2.x;

@@ -93,6 +93,9 @@ int main(int argc, char **argv) {
             return 1;
         }
     }
+    // worlds that ask for it (VXA.Simulator.RecordHistory.RecordStepSize) stream their .history to stdout, as the reference's
+    // device-side printf does (VX3_SimulationManager.cu:40-114); `Voxelyze3 -i <dir> > a.history` captures it
+    vx3b_job_history(dir.c_str(), nullptr, precision);
     int rc = vx3b_job_run(dir.c_str(), output.c_str(), devices, precision);
     if (rc != VX3B_OK) {
         printf("ERROR: %s\n", vx3b_last_error());

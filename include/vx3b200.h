@@ -78,7 +78,7 @@ typedef struct VX3B_VoxelMaterial {
     double Cilia;                /* scale of the cilia force */
     int32_t matid;               /* palette ID reported in <mats> */
     int32_t fixed, isTarget, isMeasured, sticky, linear;
-    int32_t pad;
+    uint32_t rgba;               /* display colour r | g << 8 | b << 16 | a << 24, each (int)(VXA value * 255) (VX_Object.h:419-425): .history only */
 } VX3B_VoxelMaterial;
 
 /* Combined material of a voxel pair: CVX_MaterialLink::updateAll/updateDerived
@@ -136,6 +136,9 @@ typedef struct VX3B_WorldDesc {
     /* One body over several GPUs (section 2b): [nv] or NULL; 1 = ghost, a copy of a voxel another GPU's slab owns.  Ghosts are
      * never integrated; their state arrives through vx3b_batch_halo_import.  Links between two ghosts must not be listed. */
     const uint8_t *ghost;
+
+    /* VXA.Simulator.RecordHistory (VX3_SimulationManager.cu:344-346): 0 = no .history stream */
+    int32_t record_step_size, record_voxel, record_link;
 } VX3B_WorldDesc;
 
 /* Numeric fields of VX3_SimulationResult (VX3_SimulationResult.h:4-24). */
@@ -199,6 +202,8 @@ int vx3b_batch_read_links(vx3b_ctx *ctx, int world, double *pos2_3, double *angl
 /* collision pair set found in the LAST executed step of `world`: pairs (i,j), i>j, voxel indices in
  * creation order, sorted ascending by (i,j).  *n in: capacity (pairs), out: count. */
 int vx3b_batch_collision_pairs(vx3b_ctx *ctx, int world, int32_t *pairs2, int32_t *n);
+/* what the .history writer needs beyond read_state: voxel temperatures [nv] and link strains [nl]; either may be NULL */
+int vx3b_batch_read_aux(vx3b_ctx *ctx, int world, float *voxel_temp, float *link_strain);
 /* device time (CUDA events) of the last vx3b_batch_run, and how many kernels it launched */
 int vx3b_ctx_timing(vx3b_ctx *ctx, float *device_ms, int64_t *kernel_launches);
 int64_t vx3b_ctx_total_voxel_steps(vx3b_ctx *ctx); /* sum over worlds of nv*steps in the last run */
@@ -228,6 +233,10 @@ int vx3b_batch_halo_import(vx3b_ctx *ctx, int world, int list_id, const void *de
  * VX3_SimulationManager.cu:138-155): every *.vxd in input_dir over base.vxa, worlds sharded over
  * `num_devices` GPUs, report XML in the reference's layout written to report_path. */
 int vx3b_job_run(const char *input_dir, const char *report_path, int num_devices, int precision);
+/* The .history stream of `Voxelyze3 -i <dir>` without -o (README.md:84-100, VX3_SimulationManager.cu:40-114): for every *.vxd
+ * over base.vxa whose RecordStepSize is non-zero, the settings header, then every real_stepsize steps one frame of surface-voxel
+ * records (and link records if RecordLink), in the reference's text format, to out_path (NULL = stdout).  One world at a time. */
+int vx3b_job_history(const char *input_dir, const char *out_path, int precision);
 /* Host-only: assign n worlds of the given cost to num_shards devices / ranks, longest-processing-time-first (the reference
  * deals files round-robin, vx3_node_worker.cu:88-93).  Deterministic, so every rank of a multi-process job agrees. */
 int vx3b_shard_worlds(const int64_t *cost, int n, int num_shards, int32_t *shard_of);

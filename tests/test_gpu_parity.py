@@ -309,3 +309,56 @@ def test_job_run_writes_the_reference_report_layout():
             assert int(d.find("num_voxel").text) == m.num_voxels
             assert len(d.find("pos").text.strip(";").split(";")) == m.num_voxels
             assert abs(float(d.find("currentCenterOfMass/x").text) - rr.current_com[0]) < 1e-9
+
+
+def test_history_stream_has_the_reference_format_and_the_oracles_positions():
+    """`.history` (VX3_SimulationManager.cu:40-114): settings header, one frame every real_stepsize steps with one
+    record per surface voxel (and per link), positions in mm with one decimal.  The reference ships no expected stream (and its
+    GPU path cannot run here), so the numbers are checked against the oracle stepped to the same frames."""
+    import re
+    rec = "<Simulator><RecordHistory><RecordStepSize>100</RecordStepSize><RecordVoxel>1</RecordVoxel><RecordLink>1</RecordLink></RecordHistory>"
+    base = W.xenobot_base_vxa(stop_seconds=0.02, enable_collision=False).replace("<Simulator>", rec, 1)
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "base.vxa"), "w").write(base)
+        open(os.path.join(td, "bot_0004.vxd"), "w").write(W.xenobot_vxd(4))
+        out = os.path.join(td, "a.history")
+        rc = gv.lib().vx3b_job_history(td.encode(), out.encode(), gv.FP64)
+        assert rc == 0, gv.lib().vx3b_last_error()
+        text = open(out).read()
+    model = gv.Model.from_vxa(base, W.xenobot_vxd(4))
+    d = model.desc
+    assert d.record_step_size == 100 and d.record_link == 1
+    assert "{{{setting}}}<rescale>0.001</rescale>" in text and "{{{setting}}}<voxel_size>0.010000</voxel_size>" in text
+    assert len(re.findall(r"\{\{\{setting\}\}\}<matcolor><id>\d+</id><r>[\d.]+</r><g>[\d.]+</g><b>[\d.]+</b><a>[\d.]+</a></matcolor>", text)) == d.num_voxel_mats
+    m = re.search(r"real_stepsize: (\d+) ; recommendedTimeStep ([\d.]+); d_v3->DtFrac ([\d.]+) \.", text)
+    real = int(m.group(1))
+    from gpuvoxels_b200 import slab
+    dt = slab.body_time_step(model)  # vx3b_world_time_step: float(DtFrac * recommendedTimeStep)
+    assert real == int(100 / (10000 * (dt / d.dt_frac) * d.dt_frac)) + 1
+    frames = re.findall(r"<<<Step(\d+) Time:([\d.]+)>>>(.*?)<<<>>>\|\[\[\[(\d+)\]\]\](.*?)\[\[\[\]\]\]\n", text)
+    want = O.OracleWorld(model)
+    want.run(1000000, use_stop_formula=True)
+    total = want.result().steps
+    assert [int(f[0]) for f in frames] == list(range(0, total, real))  # a frame after step j+1 for j = 0, real, 2*real, ... while running
+    deg = np.bincount(np.concatenate([model.array("link_neg"), model.array("link_pos")]), minlength=model.num_voxels)
+    surface = np.nonzero(deg < 6)[0]
+    mats = model.voxel_materials()
+    stepper = O.OracleWorld(model)
+    done = 0
+    for j, t, voxels, jl, links in frames[:4] + frames[-1:]:
+        stepper.run(int(j) + 1 - done)
+        done = int(j) + 1
+        st = stepper.state()
+        recs = [r.split(",") for r in voxels.split(";") if r]
+        assert len(recs) == len(surface) and int(jl) == int(j)
+        got = np.array([[float(x) for x in r[:14]] for r in recs])
+        assert np.abs(got[:, :3] - st["pos"][surface] * 1000).max() <= 0.051  # %.1f of millimetres
+        ang = 2 * np.degrees(np.arccos(np.minimum(st["orient"][surface, 0], 1)))
+        assert np.abs(got[:, 3] - ang).max() <= 0.051 and np.abs(got[:, 4:7] - st["orient"][surface, 1:]).max() <= 0.0051
+        assert np.all(got[:, 7:10] < 0) and np.all(got[:, 10:13] > 0) and np.abs(np.abs(got[:, 7:13]) - 5.0).max() < 1.0  # half a 10 mm voxel, strained
+        assert [int(r[13]) for r in recs] == [mats[k].matid for k in model.array("voxel_mat")[surface]]
+        assert abs(float(t) - stepper.result().current_time) < 1e-6
+        lrecs = [r.split(",") for r in links.split(";") if r]
+        assert len(lrecs) == model.num_links
+        lp = np.array([[float(x) for x in r[:6]] for r in lrecs])
+        assert np.abs(lp[:, :3] - st["pos"][model.array("link_pos")]).max() <= 0.000051 and np.abs(lp[:, 3:] - st["pos"][model.array("link_neg")]).max() <= 0.000051
