@@ -91,7 +91,7 @@ template <class R> struct ResidentLayout {
 };
 
 struct ResidentShared { // block-wide scalars
-    int32_t diverged, hits, running, rebuild, overflow, pad[3];
+    int32_t diverged, hits, running, rebuild, overflow, hits1, pad[2]; // hits / hits1: target-hit counter of even / odd steps
     int32_t warpSums[32];
     double com[4];
 };
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     }
     if (tid == 0) {
         sh.diverged = 0;
-        sh.hits = 0;
+        sh.hits = sh.hits1 = 0;
         sh.running = 1;
         sh.rebuild = 1;
         sh.overflow = 0;
@@ -346,11 +346,14 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
         if (collide && rebuild) {
             for (int h = tid; h < H; h += nt)
                 sCnt[h] = 0;
-            if (tid == 0) {
-                sh.rebuild = 0; // everyone has read it (barrier at the end of the previous step); the voxel pass may set it again
+            if (tid == 0)
                 sh.overflow = 0;
-            }
             __syncthreads();
+            // Only now has every thread read sh.rebuild (at the end of the previous step, with no barrier after that read): clearing
+            // it before this barrier let a slow warp see 0 where the others saw 1 and skip the barriers of this block
+            // (compute-sanitizer racecheck; it showed up as an illegal access once the link pass got faster).
+            if (tid == 0)
+                sh.rebuild = 0; // the voxel pass may set it again
             for (int i = tid; i < ns; i += nt) {
                 const int v = sSurf[i];
                 const int cx = (int)floor(sPos[3 * v] * invCell), cy = (int)floor(sPos[3 * v + 1] * invCell), cz = (int)floor(sPos[3 * v + 2] * invCell);
@@ -501,6 +504,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                 dmP = mp.sqrtMassZetaInt2 * ((vx3 && mp.fixed) ? __int_as_float(0x7f800000) : invDt);
             }
             LinkForces<R> f;
+            // (no per-axis dispatch here: links are in creation order, the three axes mix inside every warp, and a switch would run
+            // all three bodies - measured 20 % slower; k_brick sorts its links by axis and does dispatch)
             link_update<R>(lmat, axis, dpos, voxSize, qn, qp, restLen, dmN, dmP, h, f);
             sP2[3 * l] = h.pos2.x;
             sP2[3 * l + 1] = h.pos2.y;
@@ -538,11 +543,16 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
             driftZ = (float)sPos[3 * v0 + 2] - sRef[3 * s0 + 2];
             narrow(false);
         }
+        // the hit counter alternates between two slots by step parity: the slot of this step is read after the barrier below and
+        // cleared during the NEXT step (after that step's barrier), so no clear can overtake a read or an add
+        int32_t *hitSlot = (step & 1) ? &sh.hits1 : &sh.hits, *otherSlot = (step & 1) ? &sh.hits : &sh.hits1;
         if (hits)
-            atomicAdd(&sh.hits, hits);
+            atomicAdd(hitSlot, hits);
         __syncthreads();
         const bool divergedNow = sh.diverged != 0;
-        collisionCount += sh.hits;
+        collisionCount += *hitSlot;
+        if (tid == 0)
+            *otherSlot = 0;
         const bool sampling = vx3 && cycle > 0 && ((step + 1) % cycle == 0);
         // ---- phase F: voxel pass (+ reset of the grid counters and, on ordinary steps, the world bookkeeping) ---------------
         if (!divergedNow) {
@@ -653,7 +663,6 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
             W.divergedNow = 0;
             world_end_of_step(A, W, useStop);
             sh.running = W.active;
-            sh.hits = 0;
         }
         __syncthreads();
         if (late) {
@@ -674,7 +683,6 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                 }
                 world_end_of_step(A, W, useStop);
                 sh.running = W.active;
-                sh.hits = 0;
             }
             __syncthreads();
         }
