@@ -71,18 +71,19 @@ struct WorldD {
     double watchR2;         // (largest watch distance)^2 * (1 + 1e-12) when voxel sizes cannot change, else 0
     float skinHalf2;        // (skin/2)^2: a surface voxel that moved further (relative to the common drift) since the last rebuild forces a new one
     int32_t listCap;        // entries per surface voxel's candidate list
+    int32_t gridOff, gridLog2; // global-memory contact grid (kernels_contact.cuh): first bucket and log2(buckets); gridLog2 == 0: none
     // dynamic
     double t;
     int64_t step;     // CurStepCount
     int64_t runSteps; // steps left in the current vx3b_batch_run
     int32_t active, diverged, stopped, divergedNow;
-    int32_t angleSamples, numClosePairs, collisionCount, pad1;
+    int32_t angleSamples, numClosePairs, collisionCount, gRebuild; // gRebuild: the global contact lists are stale (set by k_cgrid_check)
     int32_t contactRebuilds, contactOverflows; // k_resident diagnostics: candidate-list rebuilds / rebuilds whose lists overflowed
     double recentAngle, closeness, fitness, totalDistance;
     double comAcc[4]; // Σ m·x, Σ m·y, Σ m·z, Σ m  (measured voxels)
     double distAcc;
     double com[3], initialCom[3], comHist[2][3];
-    int32_t numMeasured, pad2;
+    int32_t numMeasured, gOverflow; // gOverflow: a global contact list overflowed at the last rebuild: all-pairs this step
     VX3B_Token stop[VX3B_MAX_TOKENS], fitnessF[VX3B_MAX_TOKENS], ff[3 * VX3B_MAX_TOKENS];
 };
 

@@ -77,6 +77,8 @@ int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value) {
         ctx->e->brickDim[n[6] - 'x'] = std::max(1, std::min(64, (int)value));
     else if (n == "contact_list_cap")
         ctx->e->contactListCap = std::max(0, std::min(255, (int)value));
+    else if (n == "contact_grid")
+        ctx->e->contactGrid = value != 0;
     else if (n == "contact_skin")
         ctx->e->contactSkin = value < 0 ? 0 : value;
     else {

@@ -40,6 +40,7 @@ class EngineBase {
     int residentThreads = 0;    // threads per k_resident CTA; 0 = by size class (512 / CTAs per SM)
     double contactSkin = 0.15;  // skin of the contact candidate lists, in voxel sizes
     int contactListCap = 0;     // entries per candidate list; 0 = from the skin
+    int contactGrid = 1;        // big worlds: uniform-grid broad phase + candidate lists (1) or the all-pairs scan (0)
 };
 
 

@@ -20,6 +20,7 @@
 #include "engine_base.hpp"
 #include "host_dt.hpp"
 #include "kernels_brick.cuh"
+#include "kernels_contact.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_resident.cuh"
 #include "kernels_stream.cuh"
@@ -129,7 +130,7 @@ template <class R> class Engine : public EngineBase {
     std::vector<ResidentClass> classes; // k_resident size classes (kernels_resident.cuh)
     int numResident = 0;                // worlds that fit in shared memory (laid out first; streaming-only worlds follow)
     int vStream0 = 0, lStream0 = 0, tileStream0 = 0; // first voxel / link / contact tile of the streaming-only worlds
-    int graphMixed = -1, graphFused = -1;
+    int graphMixed = -1, graphFused = -1, graphGrid = -1;
     // fused tile path (kernels_fused.cuh): bricks of the streaming-only worlds (of every world when path 3 was chosen before upload)
     FusedArrays FA{};
     int fusedCapTab = 0, fusedCapOwn = 0, fusedBrick0 = 0; // fusedBrick0: first brick of the streaming-only worlds
@@ -144,6 +145,9 @@ template <class R> class Engine : public EngineBase {
     int brickDimsUsed[3] = {0, 0, 0};
     int brickGrid = 0, brickThreads = 256, nBrickWorlds = 0;
     bool brickDoesWorldStep = false;
+    ContactGrid CG{};           // global-memory contact broad phase of the big worlds (kernels_contact.cuh)
+    int sStream0 = 0;           // first surface slot of the streaming-only worlds
+    size_t gridBuckets = 0;
     bool brickResident = false; // the truth lives in the brick-ordered sets (after vx3b_batch_run_async); API-order arrays are stale
     std::vector<int32_t> hVoxSlot; // global voxel -> brick-order slot (-1: not a brick world's voxel)
     struct HaloList {
@@ -367,6 +371,7 @@ template <class R> class Engine : public EngineBase {
         std::vector<Off> off(n);
         {
             size_t voff = 0, loff = 0, vmo = 0, lmo = 0, so = 0, eo = 0;
+            int sStreamFirst = -1;
             for (int oi = 0; oi < n; oi++) {
                 const int w = perm[oi];
                 const VX3B_WorldDesc &d = worlds[w];
@@ -378,6 +383,8 @@ template <class R> class Engine : public EngineBase {
                     tileStream0 = (int)hTiles.size();
                 }
                 off[w] = Off{voff, loff, vmo, lmo, so, eo};
+                if (pre[w].cls == 0 && sStreamFirst < 0)
+                    sStreamFirst = (int)so;
                 if (d.enable_collision) {
                     anyCollision = true;
                     for (int f = 0; f < pre[w].ns; f += 128)
@@ -392,6 +399,7 @@ template <class R> class Engine : public EngineBase {
             }
             surf.resize(so);
             ext.resize(eo);
+            sStream0 = sStreamFirst < 0 ? (int)so : sStreamFirst;
         }
         auto stage_world = [&](int w) {
             const VX3B_WorldDesc &d = worlds[w];
@@ -441,6 +449,7 @@ template <class R> class Engine : public EngineBase {
             W.listCap = listCaps[w];
             W.watchR2 = 0; // set below once the materials' constant sizes are known
             W.residentClass = pre[w].cls;
+            W.gRebuild = 1;
             memcpy(W.stop, d.stop_condition, sizeof(W.stop));
             memcpy(W.fitnessF, d.fitness, sizeof(W.fitnessF));
             memcpy(W.ff, d.force_field, sizeof(W.ff));
@@ -639,6 +648,28 @@ template <class R> class Engine : public EngineBase {
         }
         const bool anyPhase = anyPhaseA, anyCilia = anyCiliaA;
         anyGhost = anyGhostA;
+        // global-memory contact grid (kernels_contact.cuh) for the collision worlds the streaming kernels may step: the worlds too
+        // big for k_resident, or every world when a streaming path was chosen for all of them
+        std::vector<int2> bucketTiles;
+        const bool gridAll = path == 1 || path == 3 || path == 5;
+        const int sCover0 = gridAll ? 0 : sStream0;
+        {
+            size_t buckets = 0;
+            for (int oi = 0; oi < n; oi++) {
+                const int w = perm[oi];
+                if (!contactGrid || !worlds[w].enable_collision || H[w].ns < 2 || !(gridAll || pre[w].cls == 0))
+                    continue;
+                int lg = 6;
+                while ((1 << lg) < 2 * H[w].ns && lg < 22)
+                    lg++;
+                hW[w].gridOff = (int)buckets;
+                hW[w].gridLog2 = lg;
+                for (int b = 0; b < (1 << lg); b += 1024)
+                    bucketTiles.push_back(make_int2(w, b));
+                buckets += (size_t)1 << lg;
+            }
+            gridBuckets = buckets;
+        }
 
         lap("host staging");
         // ---- brick path plan (host only; kernels_brick.cuh): which worlds, brick tables, shared-memory fit -----------------------
@@ -917,6 +948,27 @@ template <class R> class Engine : public EngineBase {
             return rc;
         if ((rc = dalloc(&dTiles, hTiles.size(), hTiles.data())) != VX3B_OK)
             return rc;
+        CG = ContactGrid{};
+        if (gridBuckets > 0) {
+            const size_t cover = surf.size() - (size_t)sCover0; // arrays are indexed by absolute surface slot: pointers are pre-offset
+            int32_t *dHead = nullptr, *dNext = nullptr, *dList = nullptr, *dCount = nullptr;
+            uint32_t *dKey = nullptr;
+            float4 *dRef = nullptr;
+            int2 *dBT = nullptr;
+            if ((rc = dalloc(&dHead, gridBuckets)) != VX3B_OK || (rc = dalloc(&dNext, cover)) != VX3B_OK || (rc = dalloc(&dKey, cover)) != VX3B_OK ||
+                (rc = dalloc(&dRef, cover)) != VX3B_OK || (rc = dalloc(&dList, cover * CGRID_CAP)) != VX3B_OK || (rc = dalloc(&dCount, cover)) != VX3B_OK ||
+                (rc = dalloc(&dBT, bucketTiles.size(), bucketTiles.data())) != VX3B_OK)
+                return rc;
+            CG.s0 = sCover0;
+            CG.head = dHead;
+            CG.next = dNext - sCover0;
+            CG.key = dKey - sCover0;
+            CG.ref = dRef - sCover0;
+            CG.list = dList - (size_t)sCover0 * CGRID_CAP;
+            CG.count = dCount - sCover0;
+            CG.buckets = dBT;
+            CG.nBucketTiles = (int)bucketTiles.size();
+        }
         if ((rc = dalloc(&dActive, 1)) != VX3B_OK)
             return rc;
         A.pairCap = 1 << 20;
@@ -1158,7 +1210,7 @@ template <class R> class Engine : public EngineBase {
     }
 
     // ---- streaming path: CUDA graph of `chunk` steps -----------------------------------------------------
-    int launches_per_step() const { return 3 + (anyCollision ? 1 : 0); }
+    int launches_per_step() const { return 3 + (anyCollision ? 1 + (contactGrid && CG.nBucketTiles > 0 ? 5 : 0) : 0); }
     // mixed: only the streaming-only worlds (a suffix of every array) are stepped here; the others run in k_resident
     // fused: one k_fused launch per step instead of k_links + k_voxels
     void enqueue_step(int useStop, bool mixed, bool fused) {
@@ -1167,7 +1219,20 @@ template <class R> class Engine : public EngineBase {
         if (!fused && A.nlTot > l0)
             k_links<R><<<lb, 256, 0, stream>>>(A, l0);
         if (anyCollision && (int)hTiles.size() > t0) {
-            k_contact<R><<<(unsigned)hTiles.size() - t0, 128, 0, stream>>>(A, dTiles + t0, recordPairs);
+            const bool grid = contactGrid && CG.nBucketTiles > 0;
+            if (grid) { // broad phase (rebuilt only when stale) + narrow phase over candidate lists; overflowed worlds fall through
+                ContactGrid G = CG;
+                G.s0 = std::max(CG.s0, mixed ? sStream0 : 0);
+                const int nsCover = A.nsTot - G.s0;
+                if (nsCover > 0) {
+                    k_cgrid_check<R><<<(unsigned)((nsCover + 255) / 256), 256, 0, stream>>>(A, G);
+                    k_cgrid_clear<R><<<(unsigned)G.nBucketTiles, 256, 0, stream>>>(A, G);
+                    k_cgrid_insert<R><<<(unsigned)((nsCover + 255) / 256), 256, 0, stream>>>(A, G);
+                    k_cgrid_lists<R><<<(unsigned)((nsCover + 127) / 128), 128, 0, stream>>>(A, G);
+                    k_cgrid_narrow<R><<<(unsigned)((nsCover + 127) / 128), 128, 0, stream>>>(A, G, recordPairs);
+                }
+            }
+            k_contact<R><<<(unsigned)hTiles.size() - t0, 128, 0, stream>>>(A, dTiles + t0, recordPairs, grid ? 1 : 0);
         }
         if (fused) {
             const int b0 = mixed ? fusedBrick0 : 0;
@@ -1193,7 +1258,7 @@ template <class R> class Engine : public EngineBase {
     // one instantiated graph per chunk length (a run of 200 steps replays the 64-step graph three times and an 8-step one once;
     // re-capturing on every change of length costs milliseconds)
     int build_graph(int steps, int useStop, bool mixed, bool fused) {
-        if (graphUseStop != useStop || graphRecord != recordPairs || graphMixed != (int)mixed || graphFused != (int)fused)
+        if (graphUseStop != useStop || graphRecord != recordPairs || graphMixed != (int)mixed || graphFused != (int)fused || graphGrid != contactGrid)
             release_graphs();
         auto it = graphs.find(steps);
         if (it != graphs.end()) {
@@ -1215,6 +1280,7 @@ template <class R> class Engine : public EngineBase {
         graphRecord = recordPairs;
         graphMixed = (int)mixed;
         graphFused = (int)fused;
+        graphGrid = contactGrid;
         return VX3B_OK;
     }
     void release_graphs() {

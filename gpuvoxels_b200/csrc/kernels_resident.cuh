@@ -91,7 +91,11 @@ template <class R> struct ResidentLayout {
 };
 
 struct ResidentShared { // block-wide scalars
-    int32_t diverged, hits, running, rebuild, overflow, hits1, pad[2]; // hits / hits1: target-hit counter of even / odd steps
+    int32_t diverged, running, rebuild, overflow;
+    // target-hit counter of even / odd steps, each in its own 16-byte granule: the compiler fetches neighbouring scalars with one
+    // vector load, and the clear of one slot must not overlap the (vector) read of anything else
+    int32_t hits, padA[3];
+    int32_t hits1, padB[3];
     int32_t warpSums[32];
     double com[4];
 };

@@ -117,11 +117,15 @@ template <class R> struct SurfRec {
     int32_t mat, v;
     short4 lat;
 };
-template <class R> __global__ void __launch_bounds__(128) k_contact(Arrays<R> A, const ContactTile *tiles, int recordPairs) {
+// gridMode: the grid broad phase (kernels_contact.cuh) runs before this kernel; only worlds it does not cover (no grid, or a
+// candidate list overflowed at this step's rebuild) are left to the all-pairs scan
+template <class R> __global__ void __launch_bounds__(128) k_contact(Arrays<R> A, const ContactTile *tiles, int recordPairs, int gridMode) {
     __shared__ SurfRec<R> tile[128];
     const ContactTile ct = tiles[blockIdx.x];
     WorldD &W = A.worlds[ct.world];
     if (!W.active || !(W.flags & WF_COLLISION) || (W.flags & WF_RESIDENT))
+        return;
+    if (gridMode && W.gridLog2 > 0 && !W.gOverflow)
         return;
     const int ns = W.ns, soff = W.soff;
     recordPairs = recordPairs && W.runSteps == 1; // parity tests read the pair set of the run's last step

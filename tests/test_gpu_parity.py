@@ -283,6 +283,35 @@ def test_brick_path_rounds_world_switches_and_empty_worlds():
     b.close()
 
 
+@pytest.mark.parametrize("precision", [gv.FP64, gv.FP32])
+@pytest.mark.parametrize("path", [STREAM, FUSED])
+def test_grid_broad_phase_equals_the_all_pairs_scan_bit_for_bit(path, precision):
+    """Big worlds find their contacts through the global-memory uniform grid + candidate lists (kernels_contact.cuh) instead of
+    the reference's all-pairs scan.  Candidates are visited in the all-pairs order and the predicate is the same, so forces -
+    and with them the whole state - must be identical to the last bit, the watched pair set and the hit count too; also when
+    a fat skin overflows the lists (fallback to the all-pairs kernel) and over several runs (lists carried across runs)."""
+    models = [gv.Model.from_vxa(W.contact_pile_vxa(k=3, cube=4)), gv.Model.from_vxa(W.xenobot_base_vxa(), W.xenobot_vxd(7)),
+              gv.Model.from_vxa(W.contact_pile_vxa(k=2, cube=3, seed=3))]
+    for skin in (0.15, 2.5):
+        a = gpu_run(models, 260, precision, path, contact_grid=0, record_pairs=1, contact_skin=skin)
+        b = gpu_run(models, 260, precision, path, contact_grid=1, record_pairs=1, contact_skin=skin)
+        for rounds in range(2):
+            for i in range(len(models)):
+                sa, sb = a.read_state(i), b.read_state(i)
+                for k in ("pos", "orient", "linMom", "angMom"):
+                    assert np.array_equal(sa[k], sb[k]), (skin, i, k, rounds)
+                assert np.array_equal(a.collision_pairs(i), b.collision_pairs(i))
+                ra, rb = a.results()[i], b.results()[i]
+                assert ra.collision_count == rb.collision_count
+                if rounds == 0:
+                    assert rb.contact_rebuilds >= 1 and (rb.contact_overflows > 0) == (skin > 1)
+            a.run(45)
+            b.run(45)
+        assert len(a.collision_pairs(0)) > 0  # the piles do touch
+        a.close()
+        b.close()
+
+
 def test_job_run_writes_the_reference_report_layout():
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "base.vxa"), "w").write(W.xenobot_base_vxa(stop_seconds=0.1).replace("<Simulator>", "<Simulator><SavePositionOfAllVoxels>1</SavePositionOfAllVoxels>", 1))
