@@ -36,8 +36,9 @@ def parse_args():
     ap.add_argument("--sim-steps", type=int, default=1000, help="time steps every world advances per bench step")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--path", type=int, default=0, help="0 auto (resident + brick/fused), 1 two-kernel streaming, 2 resident, 3 fused, 5 brick")
-    ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube", "slab"],
-                    help="xenobot: BASELINE configs[1] (worlds sharded over the GPUs); cube: configs[2] on one GPU; slab: one --cube^3 body cut into --gpus slabs with NCCL halo exchange (configs[4], second part)")
+    ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube", "slab", "pile"],
+                    help="xenobot: BASELINE configs[1] (worlds sharded over the GPUs); cube: configs[2] on one GPU; slab: one --cube^3 body cut into --gpus slabs with NCCL halo exchange (configs[4], second part); pile: configs[3], --pile x --pile bodies of 8^3 voxels (plus a second layer) dropped on each other, voxel-voxel contact on")
+    ap.add_argument("--pile", type=int, default=12)
     ap.add_argument("--cube", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-worlds", type=int, default=8)
@@ -50,6 +51,9 @@ def workload_config(args):
                 "worlds_per_gpu": 1, "sim_steps_per_step": args.sim_steps,
                 "parallelism": f"{args.gpus} slab(s), one per GPU; per time step one NCCL send/recv of the boundary layer to each neighbour (pos, temperature, orientation)",
                 "l2": "slab state larger than L2"}
+    if args.workload == "pile":
+        return {"workload": f"BASELINE configs[3]: multi-body scene, {args.pile}x{args.pile} + {args.pile - 1}x{args.pile - 1} bodies of 8^3 voxels piling up, voxel-voxel self-collision enabled (grid broad phase + candidate lists)",
+                "worlds_per_gpu": 1, "sim_steps_per_step": args.sim_steps, "parallelism": "replicas", "l2": "explicit L2 flush between steps"}
     if args.workload == "cube":
         return {"workload": f"BASELINE configs[2]: single {args.cube}^3-voxel soft body under gravity with floor contact, no self-collision",
                 "worlds_per_gpu": 1, "sim_steps_per_step": args.sim_steps, "parallelism": "replicas", "l2": "state larger than L2 + explicit L2 flush between steps"}
@@ -63,6 +67,8 @@ def build_worlds(args, rank):
     from gpuvoxels_b200 import worlds as W
     if args.workload in ("cube", "slab"):
         return [gv.Model.from_vxa(W.cube_vxa(args.cube))], [(W.cube_vxa(args.cube), None)]
+    if args.workload == "pile":
+        return [gv.Model.from_vxa(W.contact_pile_vxa(k=args.pile, cube=8))], [(W.contact_pile_vxa(k=args.pile, cube=8), None)]
     base = W.xenobot_base_vxa()
     texts = [(base, W.xenobot_vxd(rank * args.worlds + i)) for i in range(args.worlds)]
     return [gv.Model.from_vxa(a, d) for a, d in texts], texts
@@ -168,10 +174,10 @@ def oracle_port_sample(models, sim_steps):
 def cpu_baseline(args, models, texts):
     n = min(args.cpu_sample_worlds, len(texts))
     cores = os.cpu_count() or 1
-    steps = min(args.sim_steps, 500 if args.workload == "xenobot" else 5)
+    steps = min(args.sim_steps, 500 if args.workload == "xenobot" else 20 if args.workload == "pile" else 5)
     if reference_binary():
         procs = min(cores, n)
-        v, vs, wall = run_reference_sample(texts[:n], steps, procs, collisions=args.workload == "xenobot")
+        v, vs, wall = run_reference_sample(texts[:n], steps, procs, collisions=args.workload in ("xenobot", "pile"))
         return {"value": v, "unit": METRIC, "cores": procs, "kind": "reference",
                 "sample": f"{n} of the {len(texts)} worlds x {steps} time steps, oracle/_ref/vx2_ref (unmodified CVoxelyze + VX3 stepping deltas, its own "
                           f"collision system), {procs} single-threaded processes in parallel; {vs} voxel-steps in {wall:.1f} s"}
@@ -193,7 +199,7 @@ def main_reference(args):
     kind = "reference" if reference_binary() else "port"
     for it in range(args.warmup + args.steps):
         if kind == "reference":
-            v, vs, wall = run_reference_sample(texts[:n], steps, min(cores, n), collisions=args.workload == "xenobot")
+            v, vs, wall = run_reference_sample(texts[:n], steps, min(cores, n), collisions=args.workload in ("xenobot", "pile"))
         else:
             v, vs, wall = oracle_port_sample(models[:n], steps)
         if it >= args.warmup:
@@ -319,6 +325,8 @@ def main_ours(args):
         achieved = bytes_per_sim_step * args.sim_steps / ((dev_ms / args.steps) * 1e-3) / 1e9
         if args.path == 2 or (args.path == 0 and args.workload == "xenobot"):
             kernel = "k_resident"  # one launch per size class steps every world through all sim_steps
+        elif args.workload == "pile":
+            kernel = "k_fused"     # + k_cgrid_* (contact) + k_world_step: eight launches per time step
         elif args.path in (0, 5):
             kernel = "k_brick"     # one launch per time step
         else:
