@@ -119,6 +119,36 @@ template <class R> class Engine : public EngineBase {
         std::vector<int2> lends;
         std::vector<uint32_t> lmeta;
     } staging;
+    // the persistent staging arrays are registered as pinned memory (H2D at link speed instead of through the driver's bounce
+    // buffers: 7.5 -> ~25 GB/s); re-registered only when a vector had to grow
+    struct Pinned {
+        void *p = nullptr;
+        size_t bytes = 0;
+    };
+    std::vector<Pinned> pinned;
+    template <class V> void pin(size_t slot, V &v) {
+        if (pinned.size() <= slot)
+            pinned.resize(slot + 1);
+        Pinned &r = pinned[slot];
+        const size_t bytes = v.capacity() * sizeof(typename V::value_type);
+        if (r.p == (void *)v.data() && r.bytes >= v.size() * sizeof(typename V::value_type))
+            return;
+        if (r.p)
+            cudaHostUnregister(r.p);
+        r = Pinned{};
+        if (bytes >= (1u << 16) && cudaHostRegister((void *)v.data(), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+            r.p = (void *)v.data();
+            r.bytes = bytes;
+        }
+        cudaGetLastError(); // registration is an optimisation: a failure is not an error
+    }
+    void unpin_all() {
+        for (auto &r : pinned)
+            if (r.p)
+                cudaHostUnregister(r.p);
+        pinned.clear();
+        cudaGetLastError();
+    }
     std::vector<ContactTile> hTiles;
     ContactTile *dTiles = nullptr;
     int *dActive = nullptr;
@@ -179,6 +209,7 @@ template <class R> class Engine : public EngineBase {
         release_classes();
         if (stream)
             cudaStreamSynchronize(stream);
+        unpin_all();
         arena.release();
         if (ownStream && stream)
             cudaStreamDestroy(stream);
@@ -265,16 +296,16 @@ template <class R> class Engine : public EngineBase {
         CUDA_TRY(cudaDeviceGetAttribute(&smemPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
         CUDA_TRY(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         {
-            std::vector<uint8_t> deg;
-            for (int w = 0; w < n; w++) {
+            std::atomic<int> badWorld{-1};
+            auto pre_pass = [&](int w, std::vector<uint8_t> &deg) {
                 const VX3B_WorldDesc &d = worlds[w];
                 Pre &p = pre[w];
                 deg.assign(d.num_voxels, 0);
                 for (int l = 0; l < d.num_links; l++) {
                     int a = d.link_neg[l], b = d.link_pos[l];
                     if (a < 0 || a >= d.num_voxels || b < 0 || b >= d.num_voxels || d.link_axis[l] > 2) {
-                        set_error("vx3b_batch_upload: link " + std::to_string(l) + " of world " + std::to_string(w) + " is malformed");
-                        return VX3B_ERR_ARG;
+                        badWorld = w;
+                        return;
                     }
                     deg[a]++;
                     deg[b]++;
@@ -319,6 +350,22 @@ template <class R> class Engine : public EngineBase {
                     if (p.spill)
                         p.cls += 16;
                 }
+            };
+            const int nThreads = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 16, n}));
+            std::vector<std::thread> pool;
+            auto work = [&](int t) {
+                std::vector<uint8_t> deg;
+                for (int w = t; w < n; w += nThreads)
+                    pre_pass(w, deg);
+            };
+            for (int t = 1; t < nThreads; t++)
+                pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool)
+                th.join();
+            if (badWorld >= 0) {
+                set_error("vx3b_batch_upload: a link of world " + std::to_string((int)badWorld) + " is malformed");
+                return VX3B_ERR_ARG;
             }
         }
         // internal layout order: resident-capable worlds first (largest class = smallest worlds first does not matter; inside a
@@ -359,6 +406,12 @@ template <class R> class Engine : public EngineBase {
         pxy.resize(nvTot), pzt.resize(nvTot), ipxy.resize(nvTot), ipz.resize(nvTot), phase.resize(nvTot), orient.resize(nvTot), lm.resize(nvTot);
         am.resize(nvTot), vmat.resize(nvTot), vworld.resize(nvTot), vlinks.resize(6 * nvTot), vsurf.resize(nvTot), vext.resize(nvTot);
         lat.resize(nvTot), vghost.resize(nvTot), baseCilia.resize(nvTot), lpos2.resize(nlTot), lends.resize(nlTot), lmeta.resize(nlTot), lworld.resize(nlTot);
+        {
+            size_t k = 0;
+            pin(k++, pxy), pin(k++, pzt), pin(k++, ipxy), pin(k++, ipz), pin(k++, phase), pin(k++, orient), pin(k++, lm), pin(k++, am), pin(k++, vmat);
+            pin(k++, vworld), pin(k++, vlinks), pin(k++, vsurf), pin(k++, vext), pin(k++, lat), pin(k++, baseCilia), pin(k++, lpos2), pin(k++, lends);
+            pin(k++, lmeta), pin(k++, lworld);
+        }
         bool anyGhost = false;
         std::vector<DVoxMat> vmats(nvm);
         std::vector<DLinkMat> lmats(nlm);
