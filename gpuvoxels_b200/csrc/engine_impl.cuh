@@ -778,8 +778,8 @@ template <class R> class Engine : public EngineBase {
                         size_t b = a;
                         while (b < keyed.size() && keyed[b].first == keyed[a].first)
                             b++;
-                        if (bh.borig.size() & 1) { // own runs start on an even slot (16-byte alignment of the 8-byte arrays)
-                            bh.borig.push_back(-1);
+                        while (bh.borig.size() & 3) { // own runs start on a multiple of four slots: every array, down to the 4-byte
+                            bh.borig.push_back(-1);   // static words, is then 16-byte aligned for the bulk copies
                             bh.bstat.push_back(0);
                         }
                         BrickB B;
@@ -887,7 +887,7 @@ template <class R> class Engine : public EngineBase {
                             ok = false;
                     }
                 }
-                if (bh.borig.size() & 1) {
+                while (bh.borig.size() & 3) {
                     bh.borig.push_back(-1);
                     bh.bstat.push_back(0);
                 }

@@ -33,7 +33,7 @@ namespace vx3b {
 
 struct BrickB {
     int32_t world;
-    int32_t v0, nOwn, nHalo;    // own voxels: brick-order slots [v0, v0+nOwn), v0 even
+    int32_t v0, nOwn, nHalo;    // own voxels: brick-order slots [v0, v0+nOwn), v0 a multiple of 4
     int32_t l0, nOwned, nHaloL; // owned links: brick-order slots [l0, l0+nOwned); nHaloL recomputed links
     int32_t descBeg;            // even: descriptors of the recomputed links, then of the owned links
     int32_t gBeg;               // multiple of 4: gather list = nHalo voxel slots, then nHaloL link slots (padded to a multiple of 4)
@@ -81,7 +81,7 @@ template <class R> struct BrickLayout { // byte offsets into the CTA's dynamic s
     using T2 = typename Store<R>::T2;
     uint32_t bar, hdr, glist0, glistBytes, F, vmat, lmat, damp, len, stage0, stageBytes; // stage s / list slot k at base + s * bytes
                                                                                            // (no arrays: a dynamically indexed kernel parameter lives in local memory)
-    uint32_t pxy, pzt, ori, lm, am, h0, h1, h2, desc; // relative to a stage
+    uint32_t pxy, pzt, ori, lm, am, h0, h1, h2, desc, stat; // relative to a stage
     uint32_t total;
     static uint32_t up(size_t x) { return (uint32_t)((x + 127) & ~(size_t)127); }
     BrickLayout() {}
@@ -112,6 +112,7 @@ template <class R> struct BrickLayout { // byte offsets into the CTA's dynamic s
         h1 = take(sizeof(T4) * (c.owned + c.haloL));
         h2 = take(sizeof(T4) * (c.owned + c.haloL));
         desc = take(sizeof(LinkDesc) * c.links());
+        stat = take(sizeof(uint32_t) * ((c.own + 3) & ~3));
         stageBytes = o;
         stage0 = base;
         total = base + 2 * stageBytes;
@@ -240,13 +241,15 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             const uint32_t bV16 = (uint32_t)nOwnPad * 16u, bV4 = (uint32_t)nOwnPad * (uint32_t)sizeof(T4);
             const uint32_t bL = (uint32_t)B.nOwned * (uint32_t)sizeof(T4), bD = (uint32_t)((B.nHaloL + B.nOwned + 1) & ~1) * (uint32_t)sizeof(LinkDesc);
             const uint32_t bG = next ? (uint32_t)((next->nHalo + next->nHaloL + 3) & ~3) * 4u : 0u;
-            mbar_expect_tx(bar, 2 * bV16 + 3 * bV4 + 3 * bL + bD + bG);
+            const uint32_t bS = (uint32_t)((B.nOwn + 3) & ~3) * 4u; // per-voxel static words (material, link mask, flags)
+            mbar_expect_tx(bar, 2 * bV16 + 3 * bV4 + 3 * bL + bD + bG + bS);
             if (nOwnPad) {
                 bulk_g2s(smem_u32(st + L.pxy), src.pxy + B.v0, bV16, bar);
                 bulk_g2s(smem_u32(st + L.pzt), src.pzt + B.v0, bV16, bar);
                 bulk_g2s(smem_u32(st + L.ori), src.orient + B.v0, bV4, bar);
                 bulk_g2s(smem_u32(st + L.lm), src.lm + B.v0, bV4, bar);
                 bulk_g2s(smem_u32(st + L.am), src.am + B.v0, bV4, bar);
+                bulk_g2s(smem_u32(st + L.stat), BA.bstat + B.v0, bS, bar);
             }
             if (B.nOwned) { // owned history lands behind the recomputed links' (gathered) history: one array indexed by link number
                 const uint32_t off = (uint32_t)B.nHaloL * (uint32_t)sizeof(T4);
@@ -361,7 +364,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             const bool split = LEAN && nOwn <= half;
             const bool rotRole = split && tid >= half;
             const int myVox = rotRole ? tid - half : tid;
-            const uint32_t stat0 = myVox < nOwn ? BA.bstat[B.v0 + myVox] : 0u; // consumed in phase 2: in flight during phase 1
+            const uint32_t *sStat = (const uint32_t *)(st + L.stat);
 
             // ---- phase 1: links (recomputed ones first, then the owned run) ---------------------------------------------------
             bool diverged = false;
@@ -438,7 +441,7 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
             wp.forceField = nullptr;
 #pragma unroll 1
             for (int i = myVox; i < nOwn; i += (split ? nOwn : nt)) {
-                const uint32_t stw = (i == myVox) ? stat0 : BA.bstat[B.v0 + i];
+                const uint32_t stw = sStat[i];
                 const DVoxMat &m = sVm[stw & 255];
                 const D2 pzt = sPzt[i];
                 const T4 ori = sOri[i];
