@@ -180,6 +180,7 @@ template <class R> class Engine : public EngineBase {
     size_t gridBuckets = 0;
     bool brickResident = false; // the truth lives in the brick-ordered sets (after vx3b_batch_run_async); API-order arrays are stale
     std::vector<int32_t> hVoxSlot; // global voxel -> brick-order slot (-1: not a brick world's voxel)
+    std::vector<int32_t> linkSlot; // [world's loff + creation index] -> internal (axis-sorted) slot within the world
     struct HaloList {
         int world = -1, n = 0;
         int32_t *dVox = nullptr, *dSlots = nullptr;
@@ -403,6 +404,7 @@ template <class R> class Engine : public EngineBase {
         auto &lends = G.lends;
         auto &lmeta = G.lmeta;
         auto &lworld = G.lworld;
+        linkSlot.resize(nlTot);
         pxy.resize(nvTot), pzt.resize(nvTot), ipxy.resize(nvTot), ipz.resize(nvTot), phase.resize(nvTot), orient.resize(nvTot), lm.resize(nvTot);
         am.resize(nvTot), vmat.resize(nvTot), vworld.resize(nvTot), vlinks.resize(6 * nvTot), vsurf.resize(nvTot), vext.resize(nvTot);
         lat.resize(nvTot), vghost.resize(nvTot), baseCilia.resize(nvTot), lpos2.resize(nlTot), lends.resize(nlTot), lmeta.resize(nlTot), lworld.resize(nlTot);
@@ -644,10 +646,19 @@ template <class R> class Engine : public EngineBase {
                     ext[extAt++] = e;
                 }
             }
-            // links
+            // links.  Internal order = by axis (x-links, y-links, z-links, each in creation order): a warp of the link pass then
+            // works on one axis, and the axis-dependent swizzles stop diverging.  linkSlot maps creation order -> internal slot for
+            // the read-backs; nothing else depends on link order (force sums go by direction slot).
+            int axisAt[3] = {0, 0, 0};
+            for (int l = 0; l < d.num_links; l++)
+                axisAt[d.link_axis[l]]++;
+            axisAt[2] = axisAt[0] + axisAt[1];
+            axisAt[1] = axisAt[0];
+            axisAt[0] = 0;
             for (int l = 0; l < d.num_links; l++) {
-                size_t g = loff + l;
                 int a = d.link_neg[l], b = d.link_pos[l], ax = d.link_axis[l];
+                const size_t g = loff + (size_t)axisAt[ax]++;
+                linkSlot[loff + l] = (int32_t)(g - loff);
                 lends[g] = make_int2((int)voff + a, (int)voff + b);
                 lmeta[g] = (uint32_t)ax | ((uint32_t)(lmo + d.link_mat[l]) << 2);
                 lworld[g] = w;
@@ -1687,7 +1698,7 @@ template <class R> class Engine : public EngineBase {
             CUDA_TRY(cudaMemcpyAsync(a.data(), A.la2 + h.loff, sizeof(T4) * h.nl, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
             for (int l = 0; l < h.nl; l++)
-                linkStrain[l] = (float)a[l].w;
+                linkStrain[l] = (float)a[linkSlot[h.loff + l]].w;
         }
         return VX3B_OK;
     }
@@ -1725,28 +1736,29 @@ template <class R> class Engine : public EngineBase {
         CUDA_TRY(cudaMemcpy(x1.data(), A.la1 + h.loff, h.nl * sizeof(T4), cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(x2.data(), A.la2 + h.loff, h.nl * sizeof(T4), cudaMemcpyDeviceToHost));
         for (int l = 0; l < h.nl; l++) {
+            const int i = linkSlot[h.loff + l]; // creation order out, internal (axis-sorted) order in
             if (pos2) {
-                pos2[l * 3] = p[l].x;
-                pos2[l * 3 + 1] = p[l].y;
-                pos2[l * 3 + 2] = p[l].z;
+                pos2[l * 3] = p[i].x;
+                pos2[l * 3 + 1] = p[i].y;
+                pos2[l * 3 + 2] = p[i].z;
             }
             if (a1) {
-                a1[l * 3] = x1[l].x;
-                a1[l * 3 + 1] = x1[l].y;
-                a1[l * 3 + 2] = x1[l].z;
+                a1[l * 3] = x1[i].x;
+                a1[l * 3 + 1] = x1[i].y;
+                a1[l * 3 + 2] = x1[i].z;
             }
             if (a2) {
-                a2[l * 3] = x2[l].x;
-                a2[l * 3 + 1] = x2[l].y;
-                a2[l * 3 + 2] = x2[l].z;
+                a2[l * 3] = x2[i].x;
+                a2[l * 3 + 1] = x2[i].y;
+                a2[l * 3 + 2] = x2[i].z;
             }
             if (flags) {
                 uint32_t f;
                 if constexpr (sizeof(R) == 4)
-                    memcpy(&f, &p[l].w, 4);
+                    memcpy(&f, &p[i].w, 4);
                 else {
                     long long b;
-                    memcpy(&b, &p[l].w, 8);
+                    memcpy(&b, &p[i].w, 8);
                     f = (uint32_t)b;
                 }
                 flags[l] = (int32_t)f;

@@ -508,9 +508,15 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                 dmP = mp.sqrtMassZetaInt2 * ((vx3 && mp.fixed) ? __int_as_float(0x7f800000) : invDt);
             }
             LinkForces<R> f;
-            // (no per-axis dispatch here: links are in creation order, the three axes mix inside every warp, and a switch would run
-            // all three bodies - measured 20 % slower; k_brick sorts its links by axis and does dispatch)
-            link_update<R>(lmat, axis, dpos, voxSize, qn, qp, restLen, dmN, dmP, h, f);
+            // links are stored by axis (engine upload), so a warp is on one axis except at the two boundaries: the axis can be a
+            // template parameter (one switch instead of seven swizzle selects per link)
+            const LinkLen<R> len = link_len<R>(voxSize, restLen);
+            if (axis == 0)
+                link_update<R, 0>(lmat, 0, dpos, len, qn, qp, dmN, dmP, h, f);
+            else if (axis == 1)
+                link_update<R, 1>(lmat, 1, dpos, len, qn, qp, dmN, dmP, h, f);
+            else
+                link_update<R, 2>(lmat, 2, dpos, len, qn, qp, dmN, dmP, h, f);
             sP2[3 * l] = h.pos2.x;
             sP2[3 * l + 1] = h.pos2.y;
             sP2[3 * l + 2] = h.pos2.z;
