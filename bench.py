@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube", "slab", "pile"],
                     help="xenobot: BASELINE configs[1] (worlds sharded over the GPUs); cube: configs[2] on one GPU; slab: one --cube^3 body cut into --gpus slabs with NCCL halo exchange (configs[4], second part); pile: configs[3], --pile x --pile bodies of 8^3 voxels (plus a second layer) dropped on each other, voxel-voxel contact on")
     ap.add_argument("--pile", type=int, default=12)
+    ap.add_argument("--verify", action="store_true", help="slab workload: gather the slabs' final state on rank 0 and compare it, bit for bit, with the same body stepped whole on one GPU")
     ap.add_argument("--cube", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-worlds", type=int, default=8)
@@ -432,6 +433,23 @@ def main_slab(args):
     dev_ms = ev[0].elapsed_time(ev[1])
     clocks = sampler.stop() if sampler else None
     res = run.ctx.results()[0]
+    verified = None
+    if args.verify:  # parity of the sliced run over real NCCL: every voxel of every slab against the whole body on rank 0's GPU
+        state, gidx = run.own_state()
+        parts_state = [None] * world
+        if world > 1:
+            dist.all_gather_object(parts_state, (gidx, state))
+        else:
+            parts_state = [(gidx, state)]
+        if rank == 0:
+            total = args.sim_steps * (args.warmup + args.steps)
+            whole = gv.Context(local, args.precision)
+            whole.set_option("path", 5)
+            whole.upload([model])
+            whole.run(total)
+            ref = whole.read_state(0)
+            whole.close()
+            verified = all(np.array_equal(st[k], ref[k][g]) for g, st in parts_state for k in ("pos", "orient", "linMom", "angMom"))
     own = part.num_own
     nl_own = int(part.model.num_links)
     stats = torch.tensor([dev_ms, wall], dtype=torch.float64, device="cuda")
@@ -455,7 +473,7 @@ def main_slab(args):
                "dtype": "f32 arithmetic, f64 positions" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args),
                "voxels_total": model.num_voxels, "links_total": model.num_links, "voxels_rank0_incl_ghosts": part.model.num_voxels, "links_rank0": nl_own,
                "us_per_time_step": 1e3 * dev_ms_max / nsteps, "halo_bytes_per_time_step_all_ranks": int(halo_all), "wall_s_timed_region": wall_max,
-               "host_split_s_rank0": t_split, "diverged_worlds": int(diverged_all),
+               "host_split_s_rank0": t_split, "diverged_worlds": int(diverged_all), "verified_bit_exact_against_whole_body": verified,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s per GPU", "frac": achieved / peak, "traffic": None, "kernel": "k_brick",
                             "peak_source": peak_src, "note": "algorithmic bytes of the WHOLE body (112*Nv + 88*Nl per time step) / N GPUs / device time"},
                "e2e": {"value": vs_all / wall_max, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
