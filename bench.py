@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube", "slab", "pile"],
                     help="xenobot: BASELINE configs[1] (worlds sharded over the GPUs); cube: configs[2] on one GPU; slab: one --cube^3 body cut into --gpus slabs with NCCL halo exchange (configs[4], second part); pile: configs[3], --pile x --pile bodies of 8^3 voxels (plus a second layer) dropped on each other, voxel-voxel contact on")
     ap.add_argument("--pile", type=int, default=12)
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="engine option (vx3b_ctx_set_option), e.g. contact_skin=0.3")
     ap.add_argument("--verify", action="store_true", help="slab workload: gather the slabs' final state on rank 0 and compare it, bit for bit, with the same body stepped whole on one GPU")
     ap.add_argument("--cube", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -173,8 +174,8 @@ def oracle_port_sample(models, sim_steps):
 
 
 def cpu_baseline(args, models, texts):
-    n = min(args.cpu_sample_worlds, len(texts))
     cores = os.cpu_count() or 1
+    n = min(len(texts), max(args.cpu_sample_worlds, cores))  # at least one world per host core: the baseline uses the whole box
     steps = min(args.sim_steps, 500 if args.workload == "xenobot" else 20 if args.workload == "pile" else 5)
     if reference_binary():
         procs = min(cores, n)
@@ -256,6 +257,8 @@ def main_ours(args):
     models, texts = build_worlds(args, rank)
     ctx = gv.Context(local, args.precision)
     ctx.set_option("path", args.path)
+    for o in args.opt:
+        ctx.set_option(o.split("=")[0], float(o.split("=")[1]))
     ctx.upload(models)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     bytes_per_sim_step = algorithmic_bytes_per_sim_step(models, args.precision)
@@ -286,6 +289,8 @@ def main_ours(args):
     d2h = len(models) * C.sizeof(_abi.WorldResult)
     ctx2 = gv.Context(local, args.precision)
     ctx2.set_option("path", args.path)
+    for o in args.opt:
+        ctx2.set_option(o.split("=")[0], float(o.split("=")[1]))
     e2e_steps = max(1, min(args.steps, 3))
     ctx2.upload(models)
     ctx2.run(args.sim_steps)
@@ -351,6 +356,8 @@ def main_ours(args):
             "dtype": "f32 arithmetic, f64 positions" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args),
             "voxels_per_gpu": sum(m.num_voxels for m in models), "links_per_gpu": sum(m.num_links for m in models),
             "wall_s_timed_region": wall_max, "diverged_worlds": int(diverged_all),
+            "contact_rebuilds_per_world_rank0": float(np.mean([r.contact_rebuilds for r in results])), "contact_overflows_rank0": int(sum(r.contact_overflows for r in results)),
+            "steps_per_world_rank0": float(np.mean([r.steps for r in results])), "engine_options": args.opt,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": kernel, "peak_source": peak_src, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_per_sim_step * args.sim_steps,
