@@ -175,8 +175,9 @@ def oracle_port_sample(models, sim_steps):
 
 def cpu_baseline(args, models, texts):
     cores = os.cpu_count() or 1
-    n = min(len(texts), max(args.cpu_sample_worlds, cores))  # at least one world per host core: the baseline uses the whole box
-    steps = min(args.sim_steps, 500 if args.workload == "xenobot" else 20 if args.workload == "pile" else 5)
+    # xenobot: enough worlds for several seconds on every host core (32 per core); the big single-body workloads have one world
+    n = min(len(texts), max(args.cpu_sample_worlds, 32 * cores))
+    steps = min(args.sim_steps, 1000 if args.workload == "xenobot" else 20 if args.workload == "pile" else 5)
     if reference_binary():
         procs = min(cores, n)
         v, vs, wall = run_reference_sample(texts[:n], steps, procs, collisions=args.workload in ("xenobot", "pile"))
@@ -195,8 +196,8 @@ def main_reference(args):
     import gpuvoxels_b200 as gv  # host model only (parsing); no CUDA needed for this arm
     models, texts = build_worlds(args, 0)
     cores = os.cpu_count() or 1
-    n = min(len(texts), max(cores, args.cpu_sample_worlds))
-    steps = min(args.sim_steps, 300 if args.workload == "xenobot" else 3)
+    n = min(len(texts), max(8 * cores, args.cpu_sample_worlds))
+    steps = min(args.sim_steps, 500 if args.workload == "xenobot" else 3)
     times, vs_total, rates = [], 0, []
     kind = "reference" if reference_binary() else "port"
     for it in range(args.warmup + args.steps):
