@@ -343,6 +343,18 @@ template <class R> class Engine : public EngineBase {
                 p.listR2 = cell * cell;
                 p.skinHalf2 = (float)(0.25 * skin * skin * (1.0 - 1e-2)); // a little early rather than late (float compare)
                 p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags, false, listCap);
+                if (d.enable_collision && d.lattice && d.num_voxels > 0) {
+                    // k_resident's list build recognises lattice neighbours on an index packed 10:10:10 (kernels_resident.cuh, B4)
+                    int16_t lo[3] = {32767, 32767, 32767}, hi[3] = {-32768, -32768, -32768};
+                    for (int v = 0; v < d.num_voxels; v++)
+                        for (int k = 0; k < 3; k++) {
+                            lo[k] = std::min(lo[k], d.lattice[3 * v + k]);
+                            hi[k] = std::max(hi[k], d.lattice[3 * v + k]);
+                        }
+                    for (int k = 0; k < 3; k++)
+                        if (lo[k] < 0 || hi[k] > 1023) // (the VXA lattice starts at 0; other worlds take the streaming path)
+                            p.bytes = (size_t)-1;
+                }
                 p.cls = p.bytes == (size_t)-1 ? 0 : resident_class_of(p.bytes, (size_t)smemPerSm, (size_t)smemOptin);
                 if (p.cls == 0 && p.bytes != (size_t)-1) { // too big: keep the per-link force arrays in global memory instead
                     p.bytes = resident_bytes<R>(d.num_voxels, d.num_links, p.ns, d.num_voxel_mats, d.num_link_mats, p.flags, true, listCap);

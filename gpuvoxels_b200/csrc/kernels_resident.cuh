@@ -26,7 +26,7 @@ template <class R> struct ResidentLayout {
     size_t world, vmats, lmats;
     size_t pos, orient, linMom, angMom, temp, vflags, vmat, vlinks, lat, phase, cilia, vext, vsurfslot;
     size_t lpos2, la1, la2, lflags, lmaxs, lends, lmeta, lfN, lfP, lmN, lmP;
-    size_t surf, contactF, skey, sorted, cnt, nbr, nbrCnt, ref;
+    size_t surf, contactF, skey, sorted, cnt, rec4, rec2, nbr, nbrCnt, ref;
     size_t total;
     int H; // hash buckets (power of two)
     __host__ __device__ static size_t up(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -70,7 +70,11 @@ template <class R> struct ResidentLayout {
         // the four per-link force arrays and the grid scratch of the contact rebuild share one region: the scratch is only
         // alive between the start of a step and its link pass, when the forces of the previous step are dead
         const size_t forceBytes = spill ? 0 : 4 * up(sizeof(R) * 3 * capL);
-        const size_t scratchBytes = collide ? up(sizeof(uint32_t) * capS) + up(sizeof(uint16_t) * capS) + up(sizeof(int32_t) * H) : 0;
+        // scratch = cell keys, sorted order, bucket counters, and the cell-sorted records the list build streams through
+        // (float4 position relative to the world's reference voxel | packed lattice index, and {cell key, surface index})
+        const size_t scratchBytes = collide ? up(sizeof(uint32_t) * capS) + up(sizeof(uint16_t) * capS) + up(sizeof(int32_t) * H) +
+                                                  up(sizeof(float4) * capS) + up(sizeof(uint2) * capS)
+                                            : 0;
         const size_t shared = take(forceBytes > scratchBytes ? forceBytes : scratchBytes);
         lfN = shared;
         lfP = lfN + up(sizeof(R) * 3 * capL);
@@ -79,6 +83,8 @@ template <class R> struct ResidentLayout {
         skey = shared;
         sorted = skey + up(sizeof(uint32_t) * capS);
         cnt = sorted + up(sizeof(uint16_t) * capS);
+        rec4 = cnt + up(sizeof(int32_t) * H);
+        rec2 = rec4 + up(sizeof(float4) * capS);
         if (collide) {
             contactF = take(sizeof(R) * 3 * capS);
             nbr = take(sizeof(uint16_t) * listCap * capS);
@@ -147,6 +153,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
     uint32_t *sKey = (uint32_t *)(smem + L.skey);
     uint16_t *sSorted = (uint16_t *)(smem + L.sorted);
     int32_t *sCnt = (int32_t *)(smem + L.cnt);
+    float4 *sRec4 = (float4 *)(smem + L.rec4);
+    uint2 *sRec2 = (uint2 *)(smem + L.rec2);
     uint16_t *sNbr = (uint16_t *)(smem + L.nbr);
     uint8_t *sNbrCnt = smem + L.nbrCnt;
     float *sRef = (float *)(smem + L.ref);
@@ -417,34 +425,57 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                 }
             }
             __syncthreads();
+            // ---- B3b: cell-sorted records.  The list build below tests ~100 voxels per surface voxel; chasing sorted -> key ->
+            // surface -> lattice -> 3 doubles for each of them was a chain of five dependent loads.  One record per sorted slot:
+            // {cell key, surface index} (8 B) and {position relative to the world's first surface voxel as float3, lattice index
+            // packed 10:10:10 | fixed-material bit} (16 B).  The float distance test below is CONSERVATIVE (radius padded by far
+            // more than the rounding of a relative position), so a list is a superset of the exact one; every listed candidate
+            // still goes through the reference's exact double-precision predicate in the narrow phase.
+            const int vOrg = sSurf[0];
+            const double ox = sPos[3 * vOrg], oy = sPos[3 * vOrg + 1], oz = sPos[3 * vOrg + 2];
+            for (int p = tid; p < ns; p += nt) {
+                const int j = sSorted[p];
+                const int v = sSurf[j];
+                const short4 c = sLat[v];
+                const uint32_t pk = (uint32_t)(c.x & 1023) | ((uint32_t)(c.y & 1023) << 10) | ((uint32_t)(c.z & 1023) << 20) |
+                                    (vmats[sVmat[v]].fixed != 0 ? 0x40000000u : 0u);
+                sRec4[p] = make_float4((float)(sPos[3 * v] - ox), (float)(sPos[3 * v + 1] - oy), (float)(sPos[3 * v + 2] - oz), __uint_as_float(pk));
+                sRec2[p] = make_uint2(sKey[j], (uint32_t)j);
+            }
+            __syncthreads();
             // ---- B4: candidate lists, one thread per surface voxel.  A flat loop that either tests the next voxel of the current
             // cell or moves on to the next of the 27 cells, so the lanes of a warp stay busy although their cells hold different
             // numbers of voxels (a nested cell/voxel loop costs the warp the SUM over cells of the longest bucket).
+            const float listR2f = (float)(listR2 * 1.002); // padded: relative float positions are good to ~1e-7 of the world's extent
             for (int i = tid; i < ns; i += nt) {
                 const int v1 = sSurf[i];
-                const double x1 = sPos[3 * v1], y1 = sPos[3 * v1 + 1], z1 = sPos[3 * v1 + 2];
+                const double x1d = sPos[3 * v1], y1d = sPos[3 * v1 + 1], z1d = sPos[3 * v1 + 2];
+                const float x1 = (float)(x1d - ox), y1 = (float)(y1d - oy), z1 = (float)(z1d - oz);
                 const short4 c1 = sLat[v1];
-                const bool fixed1 = vmats[sVmat[v1]].fixed != 0;
+                const int pk1 = (int)((uint32_t)(c1.x & 1023) | ((uint32_t)(c1.y & 1023) << 10) | ((uint32_t)(c1.z & 1023) << 20));
+                const uint32_t fixed1 = vmats[sVmat[v1]].fixed != 0 ? 0x40000000u : 0u;
                 const uint32_t key = sKey[i];
                 const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
                 int n = -1, p = 0, end = 0, count = 0;
                 uint32_t k2 = 0;
                 while (true) {
                     if (p < end) {
-                        const int j = sSorted[p++];
-                        if (j != i && sKey[j] == k2) {
-                            const int v2 = sSurf[j];
-                            const short4 c2 = sLat[v2];
-                            const double dx = sPos[3 * v2] - x1, dy = sPos[3 * v2 + 1] - y1, dz = sPos[3 * v2 + 2] - z1;
-                            // directly linked voxels (lattice neighbours; static topology) never collide: is_neighbor(depth 1);
-                            // nor do two voxels of `fixed` materials
-                            if (dx * dx + dy * dy + dz * dz <= listR2 && abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) != 1 &&
-                                !(fixed1 && vmats[sVmat[v2]].fixed != 0)) {
+                        const uint2 kj = sRec2[p];
+                        if (kj.x == k2 && (int)kj.y != i) {
+                            const float4 r = sRec4[p];
+                            const float dx = r.x - x1, dy = r.y - y1, dz = r.z - z1;
+                            const uint32_t pk2 = __float_as_uint(r.w);
+                            // directly linked voxels (lattice neighbours; static topology) never collide: is_neighbor(depth 1).
+                            // The packed difference is +-1, +-2^10 or +-2^20 exactly for lattice neighbours (lattice indices
+                            // in 0..1023: the upload pre-pass keeps other worlds off this kernel); nor do two `fixed` voxels collide
+                            const int dl = abs(pk1 - (int)(pk2 & 0x3fffffffu));
+                            if (dx * dx + dy * dy + dz * dz <= listR2f && dl != 1 && dl != 1024 && dl != 1048576 && !(fixed1 & pk2)) {
                                 if (count < RES_K)
-                                    sNbr[i * RES_K + count] = (uint16_t)j;
+                                    sNbr[i * RES_K + count] = (uint16_t)kj.y;
                                 count++;
                             }
                         }
+                        p++;
                     } else {
                         if (++n == 27)
                             break;
@@ -458,9 +489,9 @@ __global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t 
                 sNbrCnt[i] = (uint8_t)min(count, RES_K);
                 if (count > RES_K)
                     sh.overflow = 1;
-                sRef[3 * i] = (float)x1;
-                sRef[3 * i + 1] = (float)y1;
-                sRef[3 * i + 2] = (float)z1;
+                sRef[3 * i] = (float)x1d;
+                sRef[3 * i + 1] = (float)y1d;
+                sRef[3 * i + 2] = (float)z1d;
             }
             __syncthreads();
             overflow = sh.overflow != 0;
