@@ -106,12 +106,15 @@ struct ResidentShared { // block-wide scalars
     double com[4];
 };
 
+#ifndef RES_MAXT
+#define RES_MAXT 512 // threads of one SM's k_resident CTAs together (register budget: 65536 / RES_MAXT per thread)
+#endif
 VXD uint32_t cell_hash(uint32_t key, int log2H) { return (key * 2654435761u) >> (32 - log2H); }
 
 // worldList: the worlds of one size class (every CTA lays its shared memory out for its own world's counts; the class only
 // fixes the dynamic shared-memory size, i.e. how many CTAs share an SM).
 template <class R, bool SPILL>
-__global__ void __launch_bounds__(512, 1) k_resident(Arrays<R> A, const int32_t *worldList, long long maxSteps, int useStop, int recordPairs) {
+__global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int32_t *worldList, long long maxSteps, int useStop, int recordPairs) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ ResidentShared sh;
     const int w = worldList[blockIdx.x];
