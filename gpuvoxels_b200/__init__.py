@@ -277,6 +277,13 @@ class Context:
                "vx3b_batch_read_links")
         return {"pos2": p2, "angle1v": a1, "angle2v": a2, "flags": fl}
 
+    def set_force(self, world, voxel, force=None, moment=None):
+        """CVX_External::setForce / setMoment between runs; needs a boundary-condition slot (option ext_all=1 before upload)."""
+        f = None if force is None else np.ascontiguousarray(force, dtype=np.float64)
+        m = None if moment is None else np.ascontiguousarray(moment, dtype=np.float64)
+        _check(lib().vx3b_batch_set_force(self._h, world, int(voxel), None if f is None else _dp(f), None if m is None else _dp(m)),
+               "vx3b_batch_set_force")
+
     def collision_pairs(self, world=0, capacity=1 << 20):
         buf = np.empty((capacity, 2), dtype=np.int32)
         n = C.c_int32(capacity)

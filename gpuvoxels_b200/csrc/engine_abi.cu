@@ -79,6 +79,8 @@ int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value) {
         ctx->e->contactListCap = std::max(0, std::min(255, (int)value));
     else if (n == "contact_grid")
         ctx->e->contactGrid = value != 0;
+    else if (n == "ext_all")
+        ctx->e->extAll = value != 0;
     else if (n == "contact_skin")
         ctx->e->contactSkin = value < 0 ? 0 : value;
     else {
@@ -106,6 +108,7 @@ int vx3b_world_time_step(const VX3B_WorldDesc *world, double *dt) {
     *dt = (double)vx3b::world_time_step(*world);
     return VX3B_OK;
 }
+int vx3b_batch_set_force(vx3b_ctx *ctx, int world, int voxel, const double *f, const double *m) { return ctx ? ctx->e->set_force(world, voxel, f, m) : VX3B_ERR_ARG; }
 int vx3b_batch_read_aux(vx3b_ctx *ctx, int world, float *t, float *s) { return ctx ? ctx->e->read_aux(world, t, s) : VX3B_ERR_ARG; }
 int vx3b_batch_run_async(vx3b_ctx *ctx, int64_t steps) { return ctx ? ctx->e->run_async(steps) : VX3B_ERR_ARG; }
 int vx3b_batch_halo_set(vx3b_ctx *ctx, int world, int list_id, const int32_t *voxels, int n) {

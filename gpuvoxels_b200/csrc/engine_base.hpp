@@ -20,6 +20,7 @@ class EngineBase {
     virtual int read_links(int world, double *pos2, double *a1, double *a2, int32_t *flags) = 0;
     virtual int collision_pairs(int world, int32_t *pairs, int32_t *n) = 0;
     virtual int read_aux(int world, float *voxelTemp, float *linkStrain) = 0;
+    virtual int set_force(int world, int voxel, const double *force, const double *moment) = 0;
     virtual int run_async(int64_t steps) = 0;
     virtual int halo_set(int world, int listId, const int32_t *voxels, int n) = 0;
     virtual int halo_record_bytes() = 0;
@@ -40,6 +41,7 @@ class EngineBase {
     int residentThreads = 0;    // threads per k_resident CTA; 0 = by size class (512 / CTAs per SM)
     double contactSkin = 0.15;  // skin of the contact candidate lists, in voxel sizes
     int contactListCap = 0;     // entries per candidate list; 0 = from the skin
+    int extAll = 0;             // every voxel gets a boundary-condition slot at upload, so set_force() can load any voxel later
     int contactGrid = 1;        // big worlds: uniform-grid broad phase + candidate lists (1) or the all-pairs scan (0)
 };
 

@@ -313,7 +313,7 @@ template <class R> class Engine : public EngineBase {
                 }
                 for (int v = 0; v < d.num_voxels; v++) {
                     p.ns += deg[v] < 6;
-                    bool bc = d.dof_fixed && d.dof_fixed[v];
+                    bool bc = extAll || (d.dof_fixed && d.dof_fixed[v]);
                     for (int k = 0; k < 3 && !bc; k++)
                         bc = (d.ext_force && d.ext_force[v * 3 + k] != 0) || (d.ext_moment && d.ext_moment[v * 3 + k] != 0);
                     p.next += bc;
@@ -627,7 +627,7 @@ template <class R> class Engine : public EngineBase {
                 bool hasF = false;
                 for (int k = 0; k < 3; k++)
                     hasF = hasF || (d.ext_force && d.ext_force[v * 3 + k] != 0) || (d.ext_moment && d.ext_moment[v * 3 + k] != 0);
-                if (dof || hasF) {
+                if (dof || hasF || extAll) {
                     DExt e;
                     memset(&e, 0, sizeof(e));
                     e.dof = dof;
@@ -1681,6 +1681,35 @@ template <class R> class Engine : public EngineBase {
                 ang[v * 3 + 2] = am[v].y;
             }
         }
+        return VX3B_OK;
+    }
+
+    // CVX_External::setForce / setMoment on a live world (the reference's friction, impulse and large-deformation tests change
+    // the load between steps, VoxCAD/src/VX2/test/tVoxelyze.h:471-605,1033-1160).  The voxel needs a boundary-condition slot:
+    // it has one if it was fixed or loaded at upload, or if option ext_all was set before the upload.
+    int set_force(int world, int voxel, const double *force, const double *moment) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (!check_world(world))
+            return VX3B_ERR_ARG;
+        const WorldHost &h = H[world];
+        if (voxel < 0 || voxel >= h.nv) {
+            set_error("vx3b_batch_set_force: no such voxel");
+            return VX3B_ERR_ARG;
+        }
+        const int ei = staging.vext[h.voff + voxel];
+        if (ei < 0) {
+            set_error("vx3b_batch_set_force: the voxel has no boundary-condition slot (set option ext_all = 1 before vx3b_batch_upload)");
+            return VX3B_ERR_STATE;
+        }
+        DExt &e = staging.ext[ei];
+        for (int k = 0; k < 3; k++) {
+            if (force)
+                e.force[k] = (float)force[k];
+            if (moment)
+                e.moment[k] = (float)moment[k];
+        }
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemcpy(A.ext + ei, &e, sizeof(DExt), cudaMemcpyHostToDevice));
         return VX3B_OK;
     }
 

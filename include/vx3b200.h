@@ -204,6 +204,11 @@ int vx3b_batch_read_links(vx3b_ctx *ctx, int world, double *pos2_3, double *angl
 int vx3b_batch_collision_pairs(vx3b_ctx *ctx, int world, int32_t *pairs2, int32_t *n);
 /* what the .history writer needs beyond read_state: voxel temperatures [nv] and link strains [nl]; either may be NULL */
 int vx3b_batch_read_aux(vx3b_ctx *ctx, int world, float *voxel_temp, float *link_strain);
+/* Change the external force / moment of one voxel of an uploaded world between runs (CVX_External::setForce / setMoment,
+ * VoxCAD/src/VX2/include/VX_External.h; the reference's own tests do this between doTimeStep calls, tVoxelyze.h:471-605,
+ * 1033-1160).  Either pointer may be NULL (unchanged).  The voxel must have had a boundary condition at upload, or the
+ * context option "ext_all" = 1 must have been set before vx3b_batch_upload. */
+int vx3b_batch_set_force(vx3b_ctx *ctx, int world, int voxel, const double *force3, const double *moment3);
 /* device time (CUDA events) of the last vx3b_batch_run, and how many kernels it launched */
 int vx3b_ctx_timing(vx3b_ctx *ctx, float *device_ms, int64_t *kernel_launches);
 int64_t vx3b_ctx_total_voxel_steps(vx3b_ctx *ctx); /* sum over worlds of nv*steps in the last run */

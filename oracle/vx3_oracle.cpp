@@ -857,6 +857,19 @@ int vx3o_set_dt(vx3o_world *o, double dt) { // test hook: fixed step instead of 
     return VX3B_OK;
 }
 
+// CVX_External::setForce / setMoment between steps (VoxCAD/src/VX2/test/tVoxelyze.h:471-605, 1033-1160 change the load mid-run)
+int vx3o_set_force(vx3o_world *o, int voxel, const double *force3, const double *moment3) {
+    if (!o || voxel < 0 || voxel >= o->w.nv)
+        return VX3B_ERR_ARG;
+    for (int k = 0; k < 3; k++) {
+        if (force3)
+            o->w.extF[voxel * 3 + k] = (float)force3[k];
+        if (moment3)
+            o->w.extM[voxel * 3 + k] = (float)moment3[k];
+    }
+    return VX3B_OK;
+}
+
 int vx3o_num_surface(vx3o_world *o) { return o ? (int)o->w.surface.size() : -1; }
 
 } // extern "C"

@@ -209,4 +209,179 @@ def all_kats():
     for axis in range(3):
         for sign in (1.0, -1.0):
             k.append((f"doubleBondCantilever-{axis}{'+' if sign > 0 else '-'}", double_bond_cantilever(axis, sign)))
+    return k + more_kats()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# More of the reference's suite.  Plain cases first (same (model, steps, check) form as above) ...
+def scale(i):
+    """TEST(CVoxelyze, scale), tVoxelyze.h:380-407: force 10^-i on every axis -> y = 4*10^-(i+3) within 0.1 % after 240 steps
+    (the reference carries the state from one force level to the next; the equilibrium it checks does not depend on that)."""
+    m, mat = _base(internal=1.0, glob=0.2)
+    m.set_voxel(mat, 0, 0, 0)
+    m.set_fixed(0, 0, 0, 63)
+    m.set_voxel(mat, 1, 0, 0)
+    force = float(np.float32(1.0) / np.float32(10.0) ** np.float32(i))
+    result = float(np.float32(4.0) / np.float32(10.0) ** np.float32(i + 3))
+    m.set_force(1, 0, 0, force=(force, force, force))
+    m.finalize()
+
+    def check(state, tol=0):
+        assert abs(state["pos"][1][1] - result) < result * (1e-3 + tol), (state["pos"][1], result)
+    return m, 240, check
+
+
+def multi_simple():
+    """TEST(CVoxelyze, multiSimple), tVoxelyze.h:607-640: x(3) - 0.003 == 1.5015e-6 (EXPECT_FLOAT_EQ) after 800 steps"""
+    m = gv.Model.new(0.001)
+    m1 = m.add_material(1e6, 1e3, internal_damping=0.01, global_damping=0.03)
+    m2 = m.add_material(1e9, 1e3, internal_damping=0.01, global_damping=0.03)
+    m.set_world_param("dt_frac", 1.0)
+    for i in range(2):
+        m.set_voxel(m1, 2 * i, 0, 0)
+        m.set_voxel(m2, 2 * i + 1, 0, 0)
+    m.set_fixed(0, 0, 0, 63)
+    m.set_force(3, 0, 0, force=(1e-3, 0, 0))
+    m.finalize()
+
+    def check(state, tol=4e-7):
+        data = state["pos"][3][0] - 0.003
+        assert abs(data - 1.5015e-6) < 1.5015e-6 * max(tol, 4e-7), data
+    return m, 800, check
+
+
+def more_kats():
+    return [(f"scale-1e-{i}", scale(i)) for i in range(3, 8)] + [("multiSimple", multi_simple())]
+
+
+# ... then the scripted ones: the reference test reads the state every step or changes the load between steps.
+# A script is (build() -> model, drive(world, tol)); `world` offers run(n), state(), links(), set_force(voxel, force, moment).
+def calc_period(timestep, data):
+    """calcPeriod, tVoxelyze.h:42-61: period from the zero crossings of a trace"""
+    zc = []
+    for i in range(1, len(data)):
+        if (data[i - 1] <= 0 and data[i] > 0) or (data[i - 1] >= 0 and data[i] < 0):
+            zc.append(timestep * ((i - 1) + data[i - 1] / (data[i - 1] - data[i])))
+    if len(zc) < 2:
+        return -1.0
+    return float(np.float32(np.mean(np.diff(zc)) * 2))
+
+
+def frequency():
+    """TEST(CVoxelyze, freqency), tVoxelyze.h:409-443: undamped axial oscillation, period 2*pi/sqrt(1e9) within 0.1 %"""
+    def build():
+        m = gv.Model.new(0.001)
+        mat = m.add_material(1e6, 1e3, internal_damping=0.0)
+        m.set_world_param("dt_frac", 0.1)  # ts = recommendedTimeStep()/10
+        m.set_voxel(mat, 0, 0, 0)
+        m.set_fixed(0, 0, 0, 63)
+        m.set_voxel(mat, 1, 0, 0)
+        m.set_fixed(1, 0, 0, 63 & ~TX)
+        m.set_force(1, 0, 0, force=(1e-3, 0, 0))
+        m.finalize()
+        return m
+
+    def drive(world, tol=0):
+        data = []
+        for _ in range(1000):
+            world.run(1)
+            data.append(world.state()["pos"][1][0] - 0.001001)
+        ts = world.time() / 1000
+        expected = 2 * 3.1415926 / np.sqrt(1e9)
+        assert abs(calc_period(ts, data) - expected) < expected * (1e-3 + tol), (calc_period(ts, data), expected)
+    return build, drive
+
+
+def large_deformation():
+    """TEST(CVoxelyze, largeDeformation), tVoxelyze.h:474-518: 100 rising loads of 100 steps each; the link is in the small-angle
+    regime at load 0 and out of it at load 20; the second difference of the tip height stays below 5000 (no jump at the switch)"""
+    def build():
+        m, mat = _base(internal=1.0, glob=0.2)
+        m.set_voxel(mat, 0, 0, 0)
+        m.set_fixed(0, 0, 0, 63)
+        m.set_voxel(mat, 1, 0, 0)
+        m.finalize()
+        return m
+
+    def drive(world, tol=0):
+        last = last_d = max_d2 = 0.0
+        ts = None
+        for i in range(100):
+            world.set_force(1, force=(0.0, 0.0, float(np.float32(i) * np.float32(2e-3))))
+            world.run(100)
+            if ts is None:
+                ts = float(np.float32(world.time() / 100))
+            small = bool(world.links()["flags"][0] & 1)
+            if i == 0:
+                assert small
+            if i == 20:
+                assert not small
+            val = float(np.float32(world.state()["pos"][1][2]))
+            if i > 0:
+                d = (val - last) / ts
+                if i > 1:
+                    max_d2 = max(max_d2, abs((d - last_d) / ts))
+                last_d = d
+            last = val
+            assert max_d2 < 5000, (i, max_d2)
+    return build, drive
+
+
+def impulse():
+    """TEST(CVoxelyze, impulse), tVoxelyze.h:568-605: a 100 N one-step kick on a 4x2 strip must die out: |z| < 1e-5 after 1000 steps"""
+    idx = {}
+
+    def build():
+        m, mat = _base(internal=1.0, glob=0.05)
+        for i in range(4):
+            for j in range(2):
+                v = m.set_voxel(mat, i, j, 0)
+                if i == 0:
+                    m.set_fixed(i, j, 0, 63)
+                if (i, j) == (3, 0):
+                    idx["v"] = v
+        m.finalize()
+        return m
+
+    def drive(world, tol=0):
+        v = idx["v"]
+        world.run(10)
+        world.set_force(v, force=(0, 0, 100))
+        world.run(1)
+        world.set_force(v, force=(0, 0, 0))
+        world.run(989)
+        z = world.state()["pos"][v][2]
+        assert abs(float(np.float32(z))) < 1e-5, z
+    return build, drive
+
+
+def static_friction(gravity, mu_s, load, slides):
+    """TEST(CVoxelyze, staticFriction), tVoxelyze.h:1033-1109: a voxel resting on the floor does not move AT ALL (x == 0.0) under a
+    horizontal force below mu_s * N and does move above it; repeated at 2 g and with mu_s = 2.  (resetTime() between the
+    reference's phases restores the initial state, so every phase is a fresh world here.)"""
+    def build():
+        m = gv.Model.new(0.001)
+        mat = m.add_material(1e6, 1e3, static_friction=mu_s, kinetic_friction=0.1, global_damping=1.0)
+        m.set_world_param("dt_frac", 1.0)
+        m.set_world_param("floor", 1)
+        m.set_world_param("gravity", gravity)
+        m.set_voxel(mat, 0, 0, 0)
+        m.finalize()
+        return m
+
+    def drive(world, tol=0):
+        normal = float(np.float32(1e3 * 0.001 * 0.001 * 0.001 * 9.80665))
+        world.run(50)  # let it settle down
+        world.set_force(0, force=(float(np.float32(load) * np.float32(normal)), 0.0, 0.0))
+        world.run(10)
+        x = world.state()["pos"][0][0]
+        assert (x != 0.0) if slides else (x == 0.0), x
+    return build, drive
+
+
+def scripted_kats():
+    k = [("freqency", frequency()), ("largeDeformation", large_deformation()), ("impulse", impulse())]
+    for g, mu, load, slides in ((1.0, 1.0, 0.9, False), (1.0, 1.0, 1.1, True), (2.0, 1.0, 1.9, False), (2.0, 1.0, 2.1, True),
+                                (1.0, 2.0, 1.9, False), (1.0, 2.0, 2.1, True)):
+        k.append((f"staticFriction-g{g:g}-mu{mu:g}-{load:g}N", static_friction(g, mu, load, slides)))
     return k

@@ -36,6 +36,7 @@ def oracle():
         lib.vx3o_collision_pairs.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         lib.vx3o_set_dt.argtypes = [C.c_void_p, C.c_double]
         lib.vx3o_num_surface.argtypes = [C.c_void_p]
+        lib.vx3o_set_force.argtypes = [C.c_void_p, C.c_int, _DP, _DP]
         _lib = lib
     return _lib
 
@@ -55,6 +56,11 @@ class OracleWorld:
     def set_dt(self, dt):
         oracle().vx3o_set_dt(self._h, float(dt))
 
+    def set_force(self, voxel, force=None, moment=None):
+        f = None if force is None else np.ascontiguousarray(force, dtype=np.float64)
+        m = None if moment is None else np.ascontiguousarray(moment, dtype=np.float64)
+        assert oracle().vx3o_set_force(self._h, int(voxel), None if f is None else _dp(f), None if m is None else _dp(m)) == 0
+
     def run(self, steps, use_stop_formula=False):
         return oracle().vx3o_run(self._h, int(steps), 1 if use_stop_formula else 0)
 
@@ -69,6 +75,9 @@ class OracleWorld:
         fl = np.empty((self.nl,), dtype=np.int32)
         oracle().vx3o_read_links(self._h, _dp(p2), _dp(a1), _dp(a2), fl.ctypes.data_as(C.POINTER(C.c_int32)))
         return {"pos2": p2, "angle1v": a1, "angle2v": a2, "flags": fl}
+
+    def time(self):
+        return self.result().current_time
 
     def result(self):
         r = WorldResult()

@@ -53,6 +53,55 @@ def test_reference_kats_through_the_c_abi(name, case, precision, tol, path):
     ctx.close()
 
 
+class _GpuWorld:
+    """world 0 of a context with the interface the scripted KATs drive (kats.scripted_kats)"""
+
+    def __init__(self, model, precision, path):
+        self.ctx = gv.Context(0, precision)
+        self.ctx.set_option("path", path)
+        self.ctx.set_option("ext_all", 1)  # the scripts load voxels that carry no boundary condition at upload
+        self.ctx.upload([model])
+
+    def run(self, n):
+        self.ctx.run(n)
+
+    def state(self):
+        return self.ctx.read_state(0)
+
+    def links(self):
+        return self.ctx.read_links(0)
+
+    def time(self):
+        return self.ctx.results()[0].current_time
+
+    def set_force(self, voxel, force=None, moment=None):
+        self.ctx.set_force(0, voxel, force, moment)
+
+
+SCRIPTED = kats.scripted_kats()
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
+@pytest.mark.parametrize("precision,tol", [(gv.FP64, 0.0), (gv.FP32, 2e-3)])
+@pytest.mark.parametrize("name,script", SCRIPTED, ids=[n for n, _ in SCRIPTED])
+def test_scripted_reference_kats_through_the_c_abi(name, script, precision, tol, path):
+    """freqency, largeDeformation, impulse, staticFriction (tVoxelyze.h): per-step read-back and vx3b_batch_set_force between runs"""
+    build, drive = script
+    world = _GpuWorld(build(), precision, path)
+    drive(world, tol)
+    world.ctx.close()
+
+
+def test_set_force_needs_a_boundary_condition_slot():
+    model = kats.scripted_kats()[2][1][0]()  # the impulse strip: voxel (3,0,0) carries no boundary condition
+    ctx = gv.Context(0, gv.FP32)
+    ctx.upload([model])
+    with pytest.raises(Exception):
+        ctx.set_force(0, model.num_voxels - 1, force=(0, 0, 1))
+    ctx.set_force(0, 0, force=(0, 0, 0))  # a fixed voxel has a slot
+    ctx.close()
+
+
 @pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 def test_fp64_matches_oracle_over_1000_steps(example_vxa, path):
     model = gv.Model.from_vxa(example_vxa)  # verbatim: VX3 semantics, collisions on (no pairs form in 1000 steps), actuation on

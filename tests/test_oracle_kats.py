@@ -11,3 +11,14 @@ def test_oracle_reproduces_reference_kat(name, case):
     w = O.OracleWorld(model)
     assert w.run(steps) == steps
     check(w.state())
+
+
+SCRIPTED = kats.scripted_kats()
+
+
+@pytest.mark.parametrize("name,script", SCRIPTED, ids=[n for n, _ in SCRIPTED])
+def test_oracle_reproduces_scripted_reference_kat(name, script):
+    """KATs whose reference test reads the state every step or changes the load between steps (tVoxelyze.h freqency,
+    largeDeformation, impulse, staticFriction)."""
+    build, drive = script
+    drive(O.OracleWorld(build()))
