@@ -98,6 +98,7 @@ template <class R> struct ResidentLayout {
 
 struct ResidentShared { // block-wide scalars
     int32_t diverged, running, rebuild, overflow;
+    int32_t narrowNext, padN[3]; // next unclaimed surface voxel of the narrow phase (reset during the voxel pass)
     // target-hit counter of even / odd steps, each in its own 16-byte granule: the compiler fetches neighbouring scalars with one
     // vector load, and the clear of one slot must not overlap the (vector) read of anything else
     int32_t hits, padA[3];
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
         sh.running = 1;
         sh.rebuild = 1;
         sh.overflow = 0;
+        sh.narrowNext = 0;
         sh.com[0] = sh.com[1] = sh.com[2] = sh.com[3] = 0;
     }
     __syncthreads();
@@ -295,7 +297,20 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
         // the same orientation, voxel1 = the later surface voxel, so the two forces are bit-identical and no atomics are needed)
         auto narrow = [&](bool direct) {
             const bool rec = recordPairs && left == 1; // parity tests read the pair set of the run's last step
-            for (int i = tid; i < ns; i += nt) {
+            // Surface voxels are handed out 32 at a time from a block-wide counter: in the link pass the warps past nl % nt have
+            // one link fewer than the others, and a list walk costs about as much as a link, so whoever is free first takes
+            // more of them (a static i = tid + k*nt split made the slowest warp do 2 links AND a walk).  The result of a
+            // surface voxel does not depend on which thread computes it.
+            while (true) {
+                int base = 0;
+                if (lane == 0)
+                    base = atomicAdd(&sh.narrowNext, 32);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= ns)
+                    break;
+                const int i = base + lane;
+                if (i >= ns)
+                    continue;
                 const int v1 = sSurf[i];
                 const DVoxMat &m1 = vmats[sVmat[v1]];
                 const V3<double> p1{sPos[3 * v1], sPos[3 * v1 + 1], sPos[3 * v1 + 2]};
@@ -595,8 +610,10 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
         __syncthreads();
         const bool divergedNow = sh.diverged != 0;
         collisionCount += *hitSlot;
-        if (tid == 0)
+        if (tid == 0) {
             *otherSlot = 0;
+            sh.narrowNext = 0; // every warp has left the narrow phase (barrier above); the next one starts after this step's last barrier
+        }
         const bool sampling = vx3 && cycle > 0 && ((step + 1) % cycle == 0);
         // ---- phase F: voxel pass (+ reset of the grid counters and, on ordinary steps, the world bookkeeping) ---------------
         if (!divergedNow) {

@@ -250,8 +250,27 @@ def multi_simple():
     return m, 800, check
 
 
+def collisions():
+    """TEST(CVoxelyze, collisions), tVoxelyze.h:1167-1197: a voxel dropped from two cells up onto a fixed voxel is held above it by
+    the contact force: z > 0.001 after 150 steps (an inequality, so it also holds for VX3's all-pairs contact, which is what runs)"""
+    m = gv.Model.new(0.001)
+    mat = m.add_material(1e6, 1e6, global_damping=0.0)
+    m.set_world_param("dt_frac", 1.0)
+    m.set_world_param("floor", 1)
+    m.set_world_param("gravity", 1.0)
+    m.set_world_param("enable_collision", 1)
+    m.set_voxel(mat, 0, 0, 0)
+    m.set_fixed(0, 0, 0, 63)
+    top = m.set_voxel(mat, 0, 0, 2)
+    m.finalize()
+
+    def check(state, tol=0):
+        assert state["pos"][top][2] > 0.001, state["pos"][top]
+    return m, 150, check
+
+
 def more_kats():
-    return [(f"scale-1e-{i}", scale(i)) for i in range(3, 8)] + [("multiSimple", multi_simple())]
+    return [(f"scale-1e-{i}", scale(i)) for i in range(3, 8)] + [("multiSimple", multi_simple()), ("collisions", collisions())]
 
 
 # ... then the scripted ones: the reference test reads the state every step or changes the load between steps.
