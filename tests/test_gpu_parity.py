@@ -288,6 +288,37 @@ def test_million_voxel_body_properties():
     assert abs((r.current_com[2] - r.initial_com[2]) - dz64.mean()) < 1e-9
 
 
+def test_full_generation_is_batch_invariant():
+    """BASELINE config 1 at full size (1,024 xenobot worlds, cilia + floor + contact): too many for the oracle, so check the
+    size-independent property a generation has - worlds are independent.  A world stepped inside the 1,024-world launch must
+    end bit-identical to the same world stepped alone (whatever size class, SM and neighbours it had), the launch must be
+    deterministic run to run, and a few of the worlds must agree with the oracle."""
+    base = W.xenobot_base_vxa()
+    models = [gv.Model.from_vxa(base, W.xenobot_vxd(i)) for i in range(1024)]
+    steps = 300
+    runs = []
+    for _ in range(2):
+        ctx = gpu_run(models, steps, gv.FP32, 0)
+        res = ctx.results()
+        assert all(r.steps == steps and r.diverged == 0 for r in res)
+        sizes = np.array([m.num_voxels for m in models])
+        picks = sorted({0, 17, 511, 1023, int(sizes.argmax()), int(sizes.argmin())})
+        runs.append({i: ctx.read_state(i) for i in picks})
+        ctx.close()
+    for i in picks:
+        for k in ("pos", "orient", "linMom", "angMom"):
+            assert np.array_equal(runs[0][i][k], runs[1][i][k]), (i, k)  # deterministic
+        alone = gpu_run([models[i]], steps, gv.FP32, 0)
+        got = alone.read_state(0)
+        for k in ("pos", "orient", "linMom", "angMom"):
+            assert np.array_equal(got[k], runs[0][i][k]), (i, k)  # independent of the batch around it
+        alone.close()
+    for i in picks[:2]:  # and right: fp32 against the CPU oracle (contact makes long runs chaotic; 300 steps are not yet)
+        want = O.OracleWorld(models[i])
+        want.run(steps)
+        assert pos_err(models[i], runs[0][i], want.state()) < 2e-2
+
+
 @pytest.mark.parametrize("brick", [(8, 8, 4), (3, 2, 5), (16, 1, 1)])
 def test_brick_path_equals_fused_path_bit_for_bit_in_fp64(brick):
     """Same arithmetic, different data layout (brick-ordered state + bulk copies vs gathered tables): the fp64 build is
