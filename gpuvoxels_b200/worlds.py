@@ -185,6 +185,15 @@ def xenobot_vxd(index, pebbles=True):
     return "<VXD>" + structure_xml(data, base_cilia=cilia, replace="VXA.VXC.Structure") + "</VXD>"
 
 
+def two_body_drop_vxa():
+    """One voxel resting on the floor and a second one dropped onto it from two cells up: the smallest scene with a watched
+    contact pair (the reference's TEST(CVoxelyze, collisions), VoxCAD/src/VX2/test/tVoxelyze.h:1167-1197, as a VXA)."""
+    data = np.zeros((3, 1, 1), dtype=int)
+    data[0, 0, 0], data[2, 0, 0] = 1, 2
+    mats = [material(name="lower", E=1e6, density=1e6), material(name="upper", E=1e6, density=1e6)]
+    return vxa_document(mats, structure_xml(data), dt_frac=0.9, grav_acc=-9.81, floor=True, enable_collision=True)
+
+
 def contact_pile_vxa(k=3, cube=4, seed=7):
     """C4 synthetic: k x k grid of cube^3 bodies dropped from staggered heights so they pile up and collide."""
     rng = np.random.default_rng(seed)

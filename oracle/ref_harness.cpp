@@ -282,8 +282,10 @@ int main(int argc, char **argv) {
         Sim.ReadVXA(&XML, &msg);
         Sim.Import(NULL, NULL, &msg);
         CVoxelyze &Vx = Sim.Vx;
-        if (a.vx2_collisions) // Voxelyze2's own watch-list contact (Voxelyze.cpp:670-750); Import() switched it off (Voxelyze.cpp:347)
-            Vx.enableCollisions(true);
+        if (a.vx2_collisions) { // Voxelyze2's own watch-list contact (Voxelyze.cpp:670-750).  Off and on again: enableCollisions
+            Vx.enableCollisions(false); // returns early when the world-level flag already has the requested value
+            Vx.enableCollisions(true);  // (Voxelyze.cpp:612-622), which would leave the per-voxel flags of Import()'s voxels unset
+        }
         nv = (int)Vx.voxelsList.size();
         nl = (int)Vx.linksList.size();
 
@@ -339,6 +341,9 @@ int main(int argc, char **argv) {
             }
             t += dt;
         }
+        if (getenv("VX2_REF_DEBUG"))
+            fprintf(stderr, "collisions world=%d list=%zu voxel0=%d watchlist0=%zu\n", (int)Vx.isCollisionsEnabled(), Vx.collisionList()->size(),
+                    (int)Vx.voxelsList[0]->isCollisionsEnabled(), Vx.voxelsList[0]->colWatch ? Vx.voxelsList[0]->colWatch->size() : (size_t)999);
         auto t1 = std::chrono::steady_clock::now();
         total_loop_s += std::chrono::duration<double>(t1 - t0).count();
         total_voxel_steps += (long long)nv * a.steps;

@@ -9,8 +9,11 @@
 // CPU library (oracle/_ref/vx2_ref, built from /root/reference) on VXA inputs — Voxelyze2
 // semantics directly and the VX3 stepping deltas (temperature phase offsets, cilia, angMom
 // zeroing, double dt) through the harness — and against golden vectors in tests/golden/.
-// The VX3-only voxel-voxel contact (A.4 below) has no executable reference here (the VX3 CUDA
-// code cannot be built: boost + device-side cudaDeviceSynchronize): that part is PARITY UNPINNED.
+// VX3 voxel-voxel contact (A.4 below): the per-pair FORCE is pinned against the reference's own
+// collision system (same formula, VX_Collision.cpp:42-56) on a two-body drop
+// (tests/golden/two_body_drop_vx2col.vxbin); the pair SELECTION (all surface pairs, depth-1
+// exclusion) has no executable reference here (the VX3 CUDA code cannot be built: boost +
+// device-side cudaDeviceSynchronize; Voxelyze2 selects pairs differently): that part is PARITY UNPINNED.
 //
 // Reference map (all under /root/reference/Voxelyze3/src unless noted):
 //   step sequencing          VX3/VX3_VoxelyzeKernel.cu:237-359 (doTimeStep)

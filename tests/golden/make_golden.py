@@ -44,5 +44,32 @@ def main():
         print(name, "voxels", len(state["pos"]), "links", len(state["link_pos2"]), "dt", state["scalars"][0, 1])
 
 
+TWO_BODY_STEPS = (40, 60, 100, 300, 1000)
+
+
+def two_body_model():
+    m = gv.Model.from_vxa(W.two_body_drop_vxa())
+    m.set_world_param("vx2_compat", 1)
+    m.set_world_param("vary_temp", 0)
+    return m
+
+
+def two_body_drop():
+    """The reference's OWN collision system (--vx2-collisions 1: CVoxelyze::enableCollisions, Voxelyze.cpp:612-750) on the
+    two-voxel drop: pins the per-pair contact force the VX3 step shares with it (VX_Collision.cpp:42-56)."""
+    m = two_body_model()
+    out = {}
+    for steps in TWO_BODY_STEPS:
+        state, _, _ = O.run_reference(m.merged_vxa(), steps, vx2_collisions=True)
+        out[f"pos_{steps}"] = state["pos"]
+        out[f"linMom_{steps}"] = state["linMom"]
+    O.write_vxbin(os.path.join(HERE, "two_body_drop_vx2col.vxbin"), out)
+    print("two_body_drop_vx2col", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "two_body":
+        two_body_drop()  # (the other fixtures are left as they are)
+    else:
+        main()
+        two_body_drop()

@@ -137,7 +137,7 @@ def have_reference():
 
 
 def run_reference(vxa_text, steps, vx3=False, enable_cilia=False, enable_expansion=False, no_temp=False, dt=None, threads=1,
-                  want_model=False, timing=False, repeat=1):
+                  want_model=False, timing=False, repeat=1, vx2_collisions=False):
     """Run the reference CPU path on `vxa_text`; returns (state dict, model dict or None, timing dict or None)."""
     with tempfile.TemporaryDirectory() as td:
         vxa = os.path.join(td, "in.vxa")
@@ -153,6 +153,8 @@ def run_reference(vxa_text, steps, vx3=False, enable_cilia=False, enable_expansi
             cmd += ["--enable-expansion", "1"]
         if no_temp:
             cmd.append("--no-temp")
+        if vx2_collisions:
+            cmd += ["--vx2-collisions", "1"]
         if dt is not None:
             cmd += ["--dt", repr(float(dt))]
         if want_model:

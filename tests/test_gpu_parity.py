@@ -288,6 +288,21 @@ def test_million_voxel_body_properties():
     assert abs((r.current_com[2] - r.initial_com[2]) - dz64.mean()) < 1e-9
 
 
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+def test_contact_force_matches_the_frozen_reference_run(path):
+    """The engine's contact force against the UNMODIFIED reference's own collision system on the two-voxel drop
+    (tests/golden/two_body_drop_vx2col.vxbin, tests/golden/make_golden.py two_body): impact, bounce and rest."""
+    from golden.make_golden import TWO_BODY_STEPS, two_body_model
+    g = O.read_vxbin(os.path.join(GOLD, "two_body_drop_vx2col.vxbin"))
+    m = two_body_model()
+    for precision, tol in ((gv.FP64, 1e-9), (gv.FP32, 2e-6)):
+        for steps in TWO_BODY_STEPS:
+            ctx = gpu_run([m], steps, precision, path)
+            got = ctx.read_state(0)
+            assert np.abs(got["pos"] - g[f"pos_{steps}"]).max() < tol, (precision, steps)
+            ctx.close()
+
+
 def test_full_generation_is_batch_invariant():
     """BASELINE config 1 at full size (1,024 xenobot worlds, cilia + floor + contact): too many for the oracle, so check the
     size-independent property a generation has - worlds are independent.  A world stepped inside the 1,024-world launch must

@@ -74,6 +74,45 @@ def test_oracle_matches_reference_live(mode):
     compare(w, ref, 1e-8, 1e-5)
 
 
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built (needs /root/reference)")
+def test_contact_force_matches_the_reference_collision_system_on_a_two_body_drop():
+    """Pins the per-pair contact force (VX3_Collision.cu:3-31 = VX_Collision.cpp:42-56: envelope 0.625, series stiffness, mean
+    damping, signs) against the UNMODIFIED reference: a voxel dropped from two cells up onto a voxel resting on the floor -
+    one watched pair in VX3's all-pairs scheme and in Voxelyze2's watch lists alike - through impact, bounce and rest.
+    Voxelyze2 forms the pair offset in float (VX_Collision.cpp:44), so agreement is at float, not double, precision.  What this
+    does NOT pin is VX3's pair selection (all surface pairs, depth-1 exclusion), which Voxelyze2 does differently."""
+    from golden.make_golden import two_body_model
+    m = two_body_model()
+    free_fall, _, _ = O.run_reference(m.merged_vxa(), 60)
+    for steps in (40, 60, 100, 300, 1000):
+        ref, _, _ = O.run_reference(m.merged_vxa(), steps, vx2_collisions=True)
+        w = O.OracleWorld(m)
+        w.run(steps)
+        s = w.state()
+        assert len(w.collision_pairs()) == 1
+        assert np.abs(s["pos"] - ref["pos"]).max() < 1e-9, steps  # metres; the drop is 0.01 m, the contact overlap ~5e-4 m
+        assert O.rel_err(s["pos"], ref["pos"]) < 1e-7
+        if steps <= 100:
+            assert O.rel_err(s["linMom"], ref["linMom"]) < 1e-5
+    w = O.OracleWorld(m)
+    w.run(60)
+    assert np.abs(w.state()["pos"] - free_fall["pos"]).max() > 5e-3  # the contact is what holds the upper voxel: without it it falls through
+
+
+def test_contact_force_matches_the_frozen_reference_run():
+    """the same pin from the committed fixture (tests/golden/two_body_drop_vx2col.vxbin), for boxes without the reference binary"""
+    from golden.make_golden import TWO_BODY_STEPS, two_body_model
+    g = O.read_vxbin(os.path.join(GOLD, "two_body_drop_vx2col.vxbin"))
+    m = two_body_model()
+    for steps in TWO_BODY_STEPS:
+        w = O.OracleWorld(m)
+        w.run(steps)
+        s = w.state()
+        assert np.abs(s["pos"] - g[f"pos_{steps}"]).max() < 1e-9, steps
+        if steps <= 100:
+            assert O.rel_err(s["linMom"], g[f"linMom_{steps}"]) < 1e-5
+
+
 def test_oracle_stop_condition_and_fitness():
     m = gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=0.05), W.xenobot_vxd(2))
     w = O.OracleWorld(m)
