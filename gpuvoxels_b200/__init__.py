@@ -225,8 +225,14 @@ class Context:
 
     def upload(self, models):
         models = list(models)
-        arr = (WorldDesc * len(models))(*[m.desc for m in models])
-        _check(lib().vx3b_batch_upload(self._h, arr, len(models)), "vx3b_batch_upload")
+        if all(isinstance(m, Model) for m in models):  # model handles straight through: no marshalling of n descriptors here
+            for m in models:
+                m.desc  # (finalizes a model that was not yet)
+            handles = (C.c_void_p * len(models))(*[m._h for m in models])
+            _check(lib().vx3b_batch_upload_models(self._h, handles, len(models)), "vx3b_batch_upload_models")
+        else:  # views of models (slabs): descriptors assembled on this side
+            arr = (WorldDesc * len(models))(*[m.desc for m in models])
+            _check(lib().vx3b_batch_upload(self._h, arr, len(models)), "vx3b_batch_upload")
         self._n = len(models)
         self._models = models  # keep host arrays alive (the library copies, but descs point into them)
         self._nv = [m.num_voxels for m in models]

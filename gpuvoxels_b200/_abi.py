@@ -88,6 +88,7 @@ SYMBOLS = {
     "vx3b_ctx_destroy": (None, [_P]),
     "vx3b_ctx_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "vx3b_batch_upload": (C.c_int, [_P, C.POINTER(WorldDesc), C.c_int]),
+    "vx3b_batch_upload_models": (C.c_int, [_P, C.POINTER(_P), C.c_int]),
     "vx3b_batch_run": (C.c_int, [_P, C.c_int64, C.c_int]),
     "vx3b_world_time_step": (C.c_int, [C.POINTER(WorldDesc), C.POINTER(C.c_double)]),
     "vx3b_batch_read_aux": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),

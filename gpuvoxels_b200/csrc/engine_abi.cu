@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "engine_base.hpp"
 #include "host_dt.hpp"
@@ -101,6 +102,17 @@ int vx3b_ctx_set_stream(vx3b_ctx *ctx, uint64_t s) {
 }
 
 int vx3b_batch_upload(vx3b_ctx *ctx, const VX3B_WorldDesc *worlds, int n) { return ctx ? ctx->e->upload(worlds, n) : VX3B_ERR_ARG; }
+int vx3b_batch_upload_models(vx3b_ctx *ctx, const vx3b_model *const *models, int n) {
+    if (!ctx || n < 0 || (n > 0 && !models))
+        return VX3B_ERR_ARG;
+    std::vector<VX3B_WorldDesc> descs((size_t)n);
+    for (int i = 0; i < n; i++) {
+        int rc = models[i] ? vx3b_model_desc(models[i], &descs[i]) : VX3B_ERR_ARG;
+        if (rc != VX3B_OK)
+            return rc;
+    }
+    return ctx->e->upload(descs.data(), n);
+}
 int vx3b_batch_run(vx3b_ctx *ctx, int64_t max_steps, int use_stop) { return ctx ? ctx->e->run(max_steps, use_stop) : VX3B_ERR_ARG; }
 int vx3b_world_time_step(const VX3B_WorldDesc *world, double *dt) {
     if (!world || !dt)

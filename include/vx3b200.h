@@ -190,6 +190,9 @@ void vx3b_ctx_destroy(vx3b_ctx *ctx);
  * (one CTA per world, state in shared memory); 3 = fused tile kernel (big bodies). */
 int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value);
 int vx3b_batch_upload(vx3b_ctx *ctx, const VX3B_WorldDesc *worlds, int n);
+/* The same for n finalized models (saves a caller in another language from marshalling n 5-KB descriptors; this is what
+ * VX3_SimulationManager::readVXD + startKernel do with their per-file CVX_Sim objects, VX3_SimulationManager.cu:277-414). */
+int vx3b_batch_upload_models(vx3b_ctx *ctx, const vx3b_model *const *models, int n);
 /* Advance every world by up to max_steps more steps.  use_stop_formula: test the world's stop
  * condition before every step as CUDA_Simulation does (VX3_SimulationManager.cu:62-69).
  * Worlds that diverge (any link strain > 100) stop, as VX3_VoxelyzeKernel.cu:271-280. */
