@@ -578,7 +578,45 @@ template <class R> class Engine : public EngineBase {
             }
             // voxels
             const bool vary = (W.flags & WF_VARY_TEMP) != 0;
-            for (int v = 0; v < d.num_voxels; v++) {
+            // A world big enough to matter on its own (one 100^3 body = 1e6 voxels, 3e6 links) is staged by several host threads:
+            // every loop below runs over chunks, and the three running cursors (boundary-condition slots, per-axis link slots,
+            // surface slots) start each chunk at the prefix sum of the chunks before it, so the layout is the serial one.
+            const int nChunks = d.num_voxels >= 200000 ? std::max(1, std::min((int)std::thread::hardware_concurrency(), 16)) : 1;
+            auto chunked = [&](int count, auto &&fn) { // fn(chunk, begin, end)
+                if (nChunks == 1) {
+                    fn(0, 0, count);
+                    return;
+                }
+                std::vector<std::thread> pool;
+                for (int c = 1; c < nChunks; c++)
+                    pool.emplace_back([&, c] { fn(c, (int)((int64_t)count * c / nChunks), (int)((int64_t)count * (c + 1) / nChunks)); });
+                fn(0, 0, (int)((int64_t)count / nChunks));
+                for (auto &th : pool)
+                    th.join();
+            };
+            auto has_ext = [&](int v) {
+                if (extAll || (d.dof_fixed && d.dof_fixed[v]))
+                    return true;
+                for (int k = 0; k < 3; k++)
+                    if ((d.ext_force && d.ext_force[v * 3 + k] != 0) || (d.ext_moment && d.ext_moment[v * 3 + k] != 0))
+                        return true;
+                return false;
+            };
+            std::vector<size_t> extStart(nChunks + 1, extAt);
+            if (nChunks > 1) {
+                std::vector<size_t> cnt(nChunks, 0);
+                chunked(d.num_voxels, [&](int c, int v0, int v1) {
+                    size_t k = 0;
+                    for (int v = v0; v < v1; v++)
+                        k += has_ext(v);
+                    cnt[c] = k;
+                });
+                for (int c = 0; c < nChunks; c++)
+                    extStart[c + 1] = extStart[c] + cnt[c];
+            }
+            chunked(d.num_voxels, [&](int chunk, int vBeg, int vEnd) {
+            size_t extAt = extStart[chunk];
+            for (int v = vBeg; v < vEnd; v++) {
                 size_t g = voff + v;
                 const VX3B_VoxelMaterial &m = d.voxel_mats[d.voxel_mat[v]];
                 short ix = d.lattice[v * 3], iy = d.lattice[v * 3 + 1], iz = d.lattice[v * 3 + 2];
@@ -658,16 +696,29 @@ template <class R> class Engine : public EngineBase {
                     ext[extAt++] = e;
                 }
             }
+            });
             // links.  Internal order = by axis (x-links, y-links, z-links, each in creation order): a warp of the link pass then
             // works on one axis, and the axis-dependent swizzles stop diverging.  linkSlot maps creation order -> internal slot for
             // the read-backs; nothing else depends on link order (force sums go by direction slot).
-            int axisAt[3] = {0, 0, 0};
-            for (int l = 0; l < d.num_links; l++)
-                axisAt[d.link_axis[l]]++;
-            axisAt[2] = axisAt[0] + axisAt[1];
-            axisAt[1] = axisAt[0];
-            axisAt[0] = 0;
-            for (int l = 0; l < d.num_links; l++) {
+            std::vector<int> axisCnt((size_t)nChunks * 3, 0), axisStart((size_t)nChunks * 3, 0);
+            chunked(d.num_links, [&](int c, int l0, int l1) {
+                int k[3] = {0, 0, 0};
+                for (int l = l0; l < l1; l++)
+                    k[d.link_axis[l]]++;
+                for (int ax = 0; ax < 3; ax++)
+                    axisCnt[(size_t)c * 3 + ax] = k[ax];
+            });
+            {
+                int at = 0;
+                for (int ax = 0; ax < 3; ax++)
+                    for (int c = 0; c < nChunks; c++) {
+                        axisStart[(size_t)c * 3 + ax] = at;
+                        at += axisCnt[(size_t)c * 3 + ax];
+                    }
+            }
+            chunked(d.num_links, [&](int chunk, int lBeg, int lEnd) {
+            int axisAt[3] = {axisStart[(size_t)chunk * 3], axisStart[(size_t)chunk * 3 + 1], axisStart[(size_t)chunk * 3 + 2]};
+            for (int l = lBeg; l < lEnd; l++) {
                 int a = d.link_neg[l], b = d.link_pos[l], ax = d.link_axis[l];
                 const size_t g = loff + (size_t)axisAt[ax]++;
                 linkSlot[loff + l] = (int32_t)(g - loff);
@@ -691,17 +742,36 @@ template <class R> class Engine : public EngineBase {
                 }
                 lpos2[g] = p2;
             }
+            });
             // surface list: voxels with an empty link slot, creation order (VX3_VoxelyzeKernel.cu:495-513)
-            for (int v = 0; v < d.num_voxels; v++) {
-                bool interior = true;
+            auto is_surface = [&](int v) {
                 for (int k = 0; k < 6; k++)
                     if (vlinks[(size_t)k * nvTot + voff + v] < 0)
-                        interior = false;
-                if (!interior) {
-                    vsurf[voff + v] = (int)surfAt;
-                    surf[surfAt++] = (int)(voff + v);
-                }
+                        return true;
+                return false;
+            };
+            std::vector<size_t> surfStart(nChunks + 1, surfAt);
+            if (nChunks > 1) {
+                std::vector<size_t> cnt(nChunks, 0);
+                chunked(d.num_voxels, [&](int c, int v0, int v1) {
+                    size_t k = 0;
+                    for (int v = v0; v < v1; v++)
+                        k += is_surface(v);
+                    cnt[c] = k;
+                });
+                for (int c = 0; c < nChunks; c++)
+                    surfStart[c + 1] = surfStart[c] + cnt[c];
             }
+            chunked(d.num_voxels, [&](int chunk, int v0, int v1) {
+                size_t at = surfStart[chunk];
+                for (int v = v0; v < v1; v++)
+                    if (is_surface(v)) {
+                        vsurf[voff + v] = (int)at;
+                        surf[at++] = (int)(voff + v);
+                    }
+                if (chunk == nChunks - 1)
+                    surfAt = at;
+            });
             h.ns = (int)surfAt - h.soff;
             W.ns = h.ns;
             h.numMeasured = 0;
