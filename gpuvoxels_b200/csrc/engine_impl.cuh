@@ -890,46 +890,91 @@ template <class R> class Engine : public EngineBase {
                     bh.bstat.reserve(bh.bstat.size() + (size_t)h.nv + (size_t)h.nv / 16 + 64);
                     bh.lorig.reserve(bh.lorig.size() + (size_t)h.nl);
                     bh.ldesc.reserve(bh.ldesc.size() + (size_t)h.nl + (size_t)h.nl / 4 + 64);
-                    // pass 1: brick-order slots of voxels and owned links
+                    // pass 1: brick-order slots of voxels and owned links.  Brick extents in `keyed` first, then (host threads side by
+                    // side over bricks) the number of links every brick owns, a serial prefix sum for the slot offsets, and the fill.
+                    std::vector<size_t> bBeg; // index into keyed of every brick's first voxel (+ end sentinel)
                     for (size_t a = 0; a < keyed.size();) {
-                        size_t b = a;
-                        while (b < keyed.size() && keyed[b].first == keyed[a].first)
-                            b++;
-                        while (bh.borig.size() & 3) { // own runs start on a multiple of four slots: every array, down to the 4-byte
-                            bh.borig.push_back(-1);   // static words, is then 16-byte aligned for the bulk copies
-                            bh.bstat.push_back(0);
-                        }
-                        BrickB B;
-                        memset(&B, 0, sizeof(B));
-                        B.world = w;
-                        B.v0 = (int)bh.borig.size();
-                        B.nOwn = (int)(b - a);
-                        for (size_t q = a; q < b; q++) {
-                            const int v = keyed[q].second, g = h.voff + v;
-                            slotOf[v] = (int)bh.borig.size();
-                            brickOf[v] = (int)bh.bricks.size();
-                            uint32_t mk = 0;
-                            for (int dir = 0; dir < 6; dir++)
-                                if (vlinks[(size_t)dir * nvTot + g] >= 0)
-                                    mk |= 1u << dir;
-                            bh.borig.push_back(g);
-                            bh.bstat.push_back((uint32_t)(vmat[g] - W.vmatOff) | (mk << 8) | (vext[g] >= 0 ? 1u << 14 : 0u) | (vghost[g] ? 1u << 15 : 0u));
-                            if (vext[g] >= 0)
-                                brickLean = false;
-                        }
-                        B.l0 = (int)bh.lorig.size();
-                        for (int axis = 0; axis < 3; axis++)
-                            for (size_t q = a; q < b; q++) {
-                                const int l = vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + keyed[q].second];
-                                if (l >= 0) {
-                                    lslotOf[l - h.loff] = (int)bh.lorig.size();
-                                    bh.lorig.push_back(l);
-                                }
-                            }
-                        B.nOwned = (int)bh.lorig.size() - B.l0;
-                        bh.bricks.push_back(B);
-                        a = b;
+                        bBeg.push_back(a);
+                        const int64_t key = keyed[a].first;
+                        while (a < keyed.size() && keyed[a].first == key)
+                            a++;
                     }
+                    bBeg.push_back(keyed.size());
+                    const size_t nNew = bBeg.size() - 1;
+                    const int nT1 = nNew >= 256 ? std::max(1, std::min((int)std::thread::hardware_concurrency(), 16)) : 1;
+                    auto over_bricks = [&](auto &&fn) { // fn(first brick, last brick) on nT1 threads
+                        if (nT1 == 1) {
+                            fn((size_t)0, nNew);
+                            return;
+                        }
+                        std::vector<std::thread> pool;
+                        for (int t = 1; t < nT1; t++)
+                            pool.emplace_back([&, t] { fn(nNew * (size_t)t / nT1, nNew * (size_t)(t + 1) / nT1); });
+                        fn((size_t)0, nNew / nT1);
+                        for (auto &th : pool)
+                            th.join();
+                    };
+                    std::vector<int32_t> nOwnedOf(nNew, 0);
+                    over_bricks([&](size_t k0, size_t k1) {
+                        for (size_t k = k0; k < k1; k++) {
+                            int cnt = 0;
+                            for (size_t q = bBeg[k]; q < bBeg[k + 1]; q++)
+                                for (int axis = 0; axis < 3; axis++)
+                                    cnt += vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + keyed[q].second] >= 0;
+                            nOwnedOf[k] = cnt;
+                        }
+                    });
+                    {
+                        size_t vAt = bh.borig.size(), lAt = bh.lorig.size();
+                        for (size_t k = 0; k < nNew; k++) {
+                            vAt = (vAt + 3) & ~(size_t)3; // own runs start on a multiple of four slots: every array, down to the 4-byte
+                            BrickB B;                     // static words, is then 16-byte aligned for the bulk copies
+                            memset(&B, 0, sizeof(B));
+                            B.world = w;
+                            B.v0 = (int)vAt;
+                            B.nOwn = (int)(bBeg[k + 1] - bBeg[k]);
+                            B.l0 = (int)lAt;
+                            B.nOwned = nOwnedOf[k];
+                            bh.bricks.push_back(B);
+                            vAt += (size_t)B.nOwn;
+                            lAt += (size_t)B.nOwned;
+                        }
+                        bh.borig.resize(vAt, -1); // (padding slots keep -1 / 0)
+                        bh.bstat.resize(vAt, 0);
+                        bh.lorig.resize(lAt);
+                    }
+                    std::atomic<bool> anyExtVoxel{false};
+                    over_bricks([&](size_t k0, size_t k1) {
+                        for (size_t k = k0; k < k1; k++) {
+                            const BrickB &B = bh.bricks[firstBrick + k];
+                            const size_t a = bBeg[k], b = bBeg[k + 1];
+                            size_t slot = (size_t)B.v0;
+                            for (size_t q = a; q < b; q++, slot++) {
+                                const int v = keyed[q].second, g = h.voff + v;
+                                slotOf[v] = (int)slot;
+                                brickOf[v] = (int)(firstBrick + k);
+                                uint32_t mk = 0;
+                                for (int dir = 0; dir < 6; dir++)
+                                    if (vlinks[(size_t)dir * nvTot + g] >= 0)
+                                        mk |= 1u << dir;
+                                bh.borig[slot] = g;
+                                bh.bstat[slot] = (uint32_t)(vmat[g] - W.vmatOff) | (mk << 8) | (vext[g] >= 0 ? 1u << 14 : 0u) | (vghost[g] ? 1u << 15 : 0u);
+                                if (vext[g] >= 0)
+                                    anyExtVoxel = true;
+                            }
+                            size_t ls = (size_t)B.l0;
+                            for (int axis = 0; axis < 3; axis++)
+                                for (size_t q = a; q < b; q++) {
+                                    const int l = vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + keyed[q].second];
+                                    if (l >= 0) {
+                                        lslotOf[l - h.loff] = (int)ls;
+                                        bh.lorig[ls++] = l;
+                                    }
+                                }
+                        }
+                    });
+                    if (anyExtVoxel)
+                        brickLean = false;
                     // pass 2: link descriptors (recomputed links first, then the owned run in slot order) and halo tables.  Bricks are
                     // independent here, so host threads build them side by side into per-brick pieces (each thread with its own
                     // voxel -> brick-local index scratch); the pieces are appended in brick order afterwards.
