@@ -616,6 +616,8 @@ template <class R> class Engine : public EngineBase {
             }
             chunked(d.num_voxels, [&](int chunk, int vBeg, int vEnd) {
             size_t extAt = extStart[chunk];
+            // (flags collected locally: a seq_cst store per voxel to one shared cache line from 16 threads was most of this loop's time)
+            bool anyPhaseL = false, anyCiliaL = false, anyGhostL = false;
             for (int v = vBeg; v < vEnd; v++) {
                 size_t g = voff + v;
                 const VX3B_VoxelMaterial &m = d.voxel_mats[d.voxel_mat[v]];
@@ -624,7 +626,7 @@ template <class R> class Engine : public EngineBase {
                 float temp = d.initial_temp;
                 double ph = d.phase_offset ? d.phase_offset[v] : 0.0;
                 if (ph != 0)
-                    anyPhaseA = true;
+                    anyPhaseL = true;
                 if (vary && !(vx3 && m.fixed)) { // first step's gpu_update_temperature at t = 0
                     double T = d.temp_amplitude * sin(2 * 3.1415926f * (0.0 / d.temp_period + ph));
                     if (!d.enable_expansion && T > 0)
@@ -650,7 +652,7 @@ template <class R> class Engine : public EngineBase {
                 lat[g] = make_short4(ix, iy, iz, 0);
                 if (d.ghost && d.ghost[v]) {
                     vghost[g] = 1;
-                    anyGhostA = true;
+                    anyGhostL = true;
                 }
                 D4 bc{0, 0, 0, 0};
                 if (d.base_cilia) {
@@ -658,7 +660,7 @@ template <class R> class Engine : public EngineBase {
                     bc.y = d.base_cilia[v * 3 + 1];
                     bc.z = d.base_cilia[v * 3 + 2];
                     if (d.enable_cilia && (bc.x != 0 || bc.y != 0 || bc.z != 0))
-                        anyCiliaA = true;
+                        anyCiliaL = true;
                 }
                 baseCilia[g] = bc;
                 uint8_t dof = d.dof_fixed ? d.dof_fixed[v] : 0;
@@ -696,6 +698,12 @@ template <class R> class Engine : public EngineBase {
                     ext[extAt++] = e;
                 }
             }
+            if (anyPhaseL)
+                anyPhaseA = true;
+            if (anyCiliaL)
+                anyCiliaA = true;
+            if (anyGhostL)
+                anyGhostA = true;
             });
             // links.  Internal order = by axis (x-links, y-links, z-links, each in creation order): a warp of the link pass then
             // works on one axis, and the axis-dependent swizzles stop diverging.  linkSlot maps creation order -> internal slot for
