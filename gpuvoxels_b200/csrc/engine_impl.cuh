@@ -1768,12 +1768,11 @@ template <class R> class Engine : public EngineBase {
     int halo_export(int world, int listId, void *buf) override { return halo_transfer(world, listId, buf, true); }
     int halo_import(int world, int listId, const void *buf) override { return halo_transfer(world, listId, const_cast<void *>(buf), false); }
 
-    int read_steps(std::vector<int64_t> &out) {
-        std::vector<WorldD> hW(H.size());
-        CUDA_TRY(cudaMemcpyAsync(hW.data(), A.worlds, hW.size() * sizeof(WorldD), cudaMemcpyDeviceToHost, stream));
+    std::vector<WorldD> resultScratch;
+    int read_steps(std::vector<int64_t> &out) { // only the step counters: a strided copy of 8 bytes per world, not 5.5 KB
+        CUDA_TRY(cudaMemcpy2DAsync(out.data(), sizeof(int64_t), (const char *)A.worlds + offsetof(WorldD, step), sizeof(WorldD), sizeof(int64_t),
+                                   H.size(), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        for (size_t w = 0; w < H.size(); w++)
-            out[w] = hW[w].step;
         return VX3B_OK;
     }
 
@@ -1788,7 +1787,8 @@ template <class R> class Engine : public EngineBase {
             set_error("vx3b_batch_results: nothing uploaded");
             return VX3B_ERR_STATE;
         }
-        std::vector<WorldD> hW(H.size());
+        std::vector<WorldD> &hW = resultScratch; // kept between calls: a fresh 5.6 MB vector per generation is 1,400 page faults
+        hW.resize(H.size());
         CUDA_TRY(cudaMemcpyAsync(hW.data(), A.worlds, hW.size() * sizeof(WorldD), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         for (size_t w = 0; w < H.size(); w++) {
