@@ -290,6 +290,10 @@ class Context:
         _check(lib().vx3b_batch_set_force(self._h, world, int(voxel), None if f is None else _dp(f), None if m is None else _dp(m)),
                "vx3b_batch_set_force")
 
+    def set_global_damping(self, world, mat, zeta):
+        """CVX_Material::setGlobalDamping of voxel material `mat` of world `world` between runs."""
+        _check(lib().vx3b_batch_set_global_damping(self._h, int(world), int(mat), float(zeta)), "vx3b_batch_set_global_damping")
+
     def collision_pairs(self, world=0, capacity=1 << 20):
         buf = np.empty((capacity, 2), dtype=np.int32)
         n = C.c_int32(capacity)

@@ -93,6 +93,7 @@ SYMBOLS = {
     "vx3b_world_time_step": (C.c_int, [C.POINTER(WorldDesc), C.POINTER(C.c_double)]),
     "vx3b_batch_read_aux": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vx3b_batch_set_force": (C.c_int, [_P, C.c_int, C.c_int, _DP, _DP]),
+    "vx3b_batch_set_global_damping": (C.c_int, [_P, C.c_int, C.c_int, C.c_double]),
     "vx3b_job_history": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
     "vx3b_batch_run_async": (C.c_int, [_P, C.c_int64]),
     "vx3b_batch_halo_set": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int]),

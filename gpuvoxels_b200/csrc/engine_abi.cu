@@ -121,6 +121,7 @@ int vx3b_world_time_step(const VX3B_WorldDesc *world, double *dt) {
     return VX3B_OK;
 }
 int vx3b_batch_set_force(vx3b_ctx *ctx, int world, int voxel, const double *f, const double *m) { return ctx ? ctx->e->set_force(world, voxel, f, m) : VX3B_ERR_ARG; }
+int vx3b_batch_set_global_damping(vx3b_ctx *ctx, int world, int mat, double zeta) { return ctx ? ctx->e->set_global_damping(world, mat, zeta) : VX3B_ERR_ARG; }
 int vx3b_batch_read_aux(vx3b_ctx *ctx, int world, float *t, float *s) { return ctx ? ctx->e->read_aux(world, t, s) : VX3B_ERR_ARG; }
 int vx3b_batch_run_async(vx3b_ctx *ctx, int64_t steps) { return ctx ? ctx->e->run_async(steps) : VX3B_ERR_ARG; }
 int vx3b_batch_halo_set(vx3b_ctx *ctx, int world, int list_id, const int32_t *voxels, int n) {

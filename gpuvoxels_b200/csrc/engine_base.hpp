@@ -21,6 +21,7 @@ class EngineBase {
     virtual int collision_pairs(int world, int32_t *pairs, int32_t *n) = 0;
     virtual int read_aux(int world, float *voxelTemp, float *linkStrain) = 0;
     virtual int set_force(int world, int voxel, const double *force, const double *moment) = 0;
+    virtual int set_global_damping(int world, int mat, double zeta) = 0;
     virtual int run_async(int64_t steps) = 0;
     virtual int halo_set(int world, int listId, const int32_t *voxels, int n) = 0;
     virtual int halo_record_bytes() = 0;

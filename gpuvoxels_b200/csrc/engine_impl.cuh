@@ -427,7 +427,10 @@ template <class R> class Engine : public EngineBase {
             pin(k++, lmeta), pin(k++, lworld);
         }
         bool anyGhost = false;
-        std::vector<DVoxMat> vmats(nvm);
+        std::vector<DVoxMat> &vmats = hVmats; // kept: set_global_damping() edits one entry and copies it to the device again
+        vmats.assign(nvm, DVoxMat{});
+        hDampT.assign(nvm, 0.0f);
+        hDampR.assign(nvm, 0.0f);
         std::vector<DLinkMat> lmats(nlm);
         std::atomic<bool> anyPhaseA{false}, anyCiliaA{false}, anyGhostA{false};
         anyCollision = false;
@@ -535,6 +538,8 @@ template <class R> class Engine : public EngineBase {
                 o.sqrtMassZetaInt2 = 2 * m.sqrtMass * m.zetaInternal;
                 o.globalDampTranslateC = m.zetaGlobal * m._2xSqMxExS;
                 o.globalDampRotateC = m.zetaGlobal * m._2xSqIxExSxSxS;
+                hDampT[vmo + k] = m._2xSqMxExS;
+                hDampR[vmo + k] = m._2xSqIxExSxSxS;
                 o.collisionDampTranslateC = m.zetaCollision * m._2xSqMxExS;
                 o.penetrationStiffness = (float)(2 * m.E * m.nomSize);
                 o.gravityForce = -m.mass * 9.80665f * m.gravMult;
@@ -1869,6 +1874,29 @@ template <class R> class Engine : public EngineBase {
                 ang[v * 3 + 2] = am[v].y;
             }
         }
+        return VX3B_OK;
+    }
+
+    // CVX_Material::setGlobalDamping on a live world (the reference's kineticFriction test lowers it after the voxel has settled,
+    // VoxCAD/src/VX2/test/tVoxelyze.h:1111-1158): globalDampingTranslateC / RotateC = zeta * 2*sqrt(m*E*s) / 2*sqrt(I*E*s^3)
+    // (VX_MaterialVoxel.h).  Every kernel reads the material table from global memory at launch, so the next run sees it.
+    std::vector<DVoxMat> hVmats;
+    std::vector<float> hDampT, hDampR;
+    int set_global_damping(int world, int mat, double zeta) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (!check_world(world))
+            return VX3B_ERR_ARG;
+        std::vector<WorldD> one(1);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemcpy(one.data(), A.worlds + world, sizeof(WorldD), cudaMemcpyDeviceToHost));
+        if (mat < 0 || mat >= one[0].nvm) {
+            set_error("vx3b_batch_set_global_damping: no such material");
+            return VX3B_ERR_ARG;
+        }
+        const size_t k = (size_t)one[0].vmatOff + (size_t)mat;
+        hVmats[k].globalDampTranslateC = (float)zeta * hDampT[k];
+        hVmats[k].globalDampRotateC = (float)zeta * hDampR[k];
+        CUDA_TRY(cudaMemcpy(A.vmats + k, &hVmats[k], sizeof(DVoxMat), cudaMemcpyHostToDevice));
         return VX3B_OK;
     }
 

@@ -212,6 +212,9 @@ int vx3b_batch_read_aux(vx3b_ctx *ctx, int world, float *voxel_temp, float *link
  * 1033-1160).  Either pointer may be NULL (unchanged).  The voxel must have had a boundary condition at upload, or the
  * context option "ext_all" = 1 must have been set before vx3b_batch_upload. */
 int vx3b_batch_set_force(vx3b_ctx *ctx, int world, int voxel, const double *force3, const double *moment3);
+/* CVX_Material::setGlobalDamping of one voxel material of an uploaded world between runs (the reference's kineticFriction test,
+ * tVoxelyze.h:1111-1158, lowers it once the voxel has settled). */
+int vx3b_batch_set_global_damping(vx3b_ctx *ctx, int world, int mat, double zeta);
 /* device time (CUDA events) of the last vx3b_batch_run, and how many kernels it launched */
 int vx3b_ctx_timing(vx3b_ctx *ctx, float *device_ms, int64_t *kernel_launches);
 int64_t vx3b_ctx_total_voxel_steps(vx3b_ctx *ctx); /* sum over worlds of nv*steps in the last run */

@@ -873,6 +873,14 @@ int vx3o_set_force(vx3o_world *o, int voxel, const double *force3, const double 
     return VX3B_OK;
 }
 
+// CVX_Material::setGlobalDamping between steps (tVoxelyze.h:1111-1158, kineticFriction)
+int vx3o_set_global_damping(vx3o_world *o, int mat, double zeta) {
+    if (!o || mat < 0 || mat >= (int)o->w.vm.size())
+        return VX3B_ERR_ARG;
+    o->w.vm[mat].zetaGlobal = (float)zeta;
+    return VX3B_OK;
+}
+
 int vx3o_num_surface(vx3o_world *o) { return o ? (int)o->w.surface.size() : -1; }
 
 } // extern "C"

@@ -274,7 +274,8 @@ def more_kats():
 
 
 # ... then the scripted ones: the reference test reads the state every step or changes the load between steps.
-# A script is (build() -> model, drive(world, tol)); `world` offers run(n), state(), links(), set_force(voxel, force, moment).
+# A script is (build() -> model, drive(world, tol)); `world` offers run(n), state(), links(), time(), set_force(voxel, force, moment),
+# set_global_damping(mat, zeta).
 def calc_period(timestep, data):
     """calcPeriod, tVoxelyze.h:42-61: period from the zero crossings of a trace"""
     zc = []
@@ -398,8 +399,44 @@ def static_friction(gravity, mu_s, load, slides):
     return build, drive
 
 
+def kinetic_friction():
+    """TEST(CVoxelyze, kineticFriction), tVoxelyze.h:1111-1158: a voxel settled on the floor, global damping then lowered to 1e-4,
+    pushed with 2 N (mu_k = 0.1): after 10 steps the work of (F - mu_k N) equals the kinetic energy, ASSERT_NEAR(..., 2e-16)"""
+    def build():
+        m = gv.Model.new(0.001)
+        mat = m.add_material(1e6, 1e3, static_friction=1.0, kinetic_friction=0.1, global_damping=1.0)
+        m.set_world_param("dt_frac", 1.0)
+        m.set_world_param("floor", 1)
+        m.set_world_param("gravity", 1.0)
+        m.set_voxel(mat, 0, 0, 0)
+        m.finalize()
+        return m
+
+    def drive(world, tol=0):
+        mass = 1e3 * 0.001 * 0.001 * 0.001
+        normal = float(np.float32(mass * 9.80665))
+        world.run(50)
+        ts = float(np.float32(world.time() / 50))
+        world.set_global_damping(0, 1e-4)
+        h_force = float(np.float32(2.0) * np.float32(normal))
+        world.set_force(0, force=(h_force, 0.0, 0.0))
+        last = vel = energy = 0.0
+        for step in range(10):
+            world.run(1)
+            cur = world.state()["pos"][0][0]
+            vel = (cur - last) / ts
+            factor = 0.5 if step == 9 else 1.0  # only half the energy of the last step: the discrete energy sum
+            energy += float(np.float32(factor)) * (h_force - float(np.float32(0.1)) * normal) * (cur - last)
+            last = cur
+        assert abs(energy - 0.5 * mass * vel * vel) < 2e-16 + tol * abs(energy), (energy, 0.5 * mass * vel * vel)
+        world.set_force(0, force=(0.0, 0.0, 0.0))
+        world.run(200)  # (the reference only logs the slide to a stop)
+        assert np.isfinite(world.state()["pos"]).all()
+    return build, drive
+
+
 def scripted_kats():
-    k = [("freqency", frequency()), ("largeDeformation", large_deformation()), ("impulse", impulse())]
+    k = [("freqency", frequency()), ("largeDeformation", large_deformation()), ("impulse", impulse()), ("kineticFriction", kinetic_friction())]
     for g, mu, load, slides in ((1.0, 1.0, 0.9, False), (1.0, 1.0, 1.1, True), (2.0, 1.0, 1.9, False), (2.0, 1.0, 2.1, True),
                                 (1.0, 2.0, 1.9, False), (1.0, 2.0, 2.1, True)):
         k.append((f"staticFriction-g{g:g}-mu{mu:g}-{load:g}N", static_friction(g, mu, load, slides)))

@@ -37,6 +37,7 @@ def oracle():
         lib.vx3o_set_dt.argtypes = [C.c_void_p, C.c_double]
         lib.vx3o_num_surface.argtypes = [C.c_void_p]
         lib.vx3o_set_force.argtypes = [C.c_void_p, C.c_int, _DP, _DP]
+        lib.vx3o_set_global_damping.argtypes = [C.c_void_p, C.c_int, C.c_double]
         _lib = lib
     return _lib
 
@@ -60,6 +61,9 @@ class OracleWorld:
         f = None if force is None else np.ascontiguousarray(force, dtype=np.float64)
         m = None if moment is None else np.ascontiguousarray(moment, dtype=np.float64)
         assert oracle().vx3o_set_force(self._h, int(voxel), None if f is None else _dp(f), None if m is None else _dp(m)) == 0
+
+    def set_global_damping(self, mat, zeta):
+        assert oracle().vx3o_set_global_damping(self._h, int(mat), float(zeta)) == 0
 
     def run(self, steps, use_stop_formula=False):
         return oracle().vx3o_run(self._h, int(steps), 1 if use_stop_formula else 0)

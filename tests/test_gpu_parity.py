@@ -77,6 +77,9 @@ class _GpuWorld:
     def set_force(self, voxel, force=None, moment=None):
         self.ctx.set_force(0, voxel, force, moment)
 
+    def set_global_damping(self, mat, zeta):
+        self.ctx.set_global_damping(0, mat, zeta)
+
 
 SCRIPTED = kats.scripted_kats()
 
