@@ -1288,12 +1288,26 @@ template <class R> class Engine : public EngineBase {
                     }
                 const int64_t nbx = (mx[0] - mn[0]) / BX + 1, nby = (mx[1] - mn[1]) / BY + 1;
                 std::vector<std::pair<int64_t, int>> keyed(h.nv);
-                for (int v = 0; v < h.nv; v++) {
+                auto key_of = [&](int v) {
                     const short4 c = lat[h.voff + v];
-                    int64_t key = (((int64_t)(c.z - mn[2]) / BZ) * nby + (c.y - mn[1]) / BY) * nbx + (c.x - mn[0]) / BX;
-                    keyed[v] = {key, v};
+                    return (((int64_t)(c.z - mn[2]) / BZ) * nby + (c.y - mn[1]) / BY) * nbx + (c.x - mn[0]) / BX;
+                };
+                const int64_t nCells = nbx * nby * ((int64_t)(mx[2] - mn[2]) / BZ + 1);
+                if (nCells <= (int64_t)4 * h.nv + 4096) { // stable counting sort by brick (= sorting the (key, index) pairs, much cheaper)
+                    std::vector<int32_t> start((size_t)nCells + 1, 0);
+                    for (int v = 0; v < h.nv; v++)
+                        start[(size_t)key_of(v) + 1]++;
+                    for (int64_t c = 0; c < nCells; c++)
+                        start[(size_t)c + 1] += start[(size_t)c];
+                    for (int v = 0; v < h.nv; v++) {
+                        const int64_t k = key_of(v);
+                        keyed[(size_t)start[(size_t)k]++] = {k, v};
+                    }
+                } else {
+                    for (int v = 0; v < h.nv; v++)
+                        keyed[v] = {key_of(v), v};
+                    std::sort(keyed.begin(), keyed.end());
                 }
-                std::sort(keyed.begin(), keyed.end());
                 std::vector<int64_t> brickOf(h.nv);
                 for (auto &kv : keyed)
                     brickOf[kv.second] = kv.first;
