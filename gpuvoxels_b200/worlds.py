@@ -194,6 +194,18 @@ def two_body_drop_vxa():
     return vxa_document(mats, structure_xml(data), dt_frac=0.9, grav_acc=-9.81, floor=True, enable_collision=True)
 
 
+def block_on_pebbles_vxa():
+    """A stiff 3x3x2 block dropped from two cells up onto two single-voxel pebbles lying on the floor: it lands on them, tips,
+    pushes them aside and ends on the floor.  Every contact is between different bodies, so VX3's all-pairs scheme and
+    Voxelyze2's watch lists (which differ only in which pairs INSIDE a body they exclude) watch the same pairs."""
+    data = np.zeros((5, 3, 3), dtype=int)
+    data[0, 0, 0] = 2
+    data[0, 2, 1] = 2
+    data[2:4, :, :] = 1
+    mats = [material(name="block", E=3e7, density=1e6), material(name="pebble", E=3e7, density=1e6)]
+    return vxa_document(mats, structure_xml(data), dt_frac=0.9, grav_acc=-9.81, floor=True, enable_collision=True)
+
+
 def contact_pile_vxa(k=3, cube=4, seed=7):
     """C4 synthetic: k x k grid of cube^3 bodies dropped from staggered heights so they pile up and collide."""
     rng = np.random.default_rng(seed)

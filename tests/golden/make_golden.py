@@ -67,9 +67,35 @@ def two_body_drop():
     print("two_body_drop_vx2col", {k: v.shape for k, v in out.items()})
 
 
+PEBBLE_STEPS = (200, 400, 1000, 2000)
+
+
+def pebbles_model():
+    m = gv.Model.from_vxa(W.block_on_pebbles_vxa())
+    m.set_world_param("vx2_compat", 1)
+    m.set_world_param("vary_temp", 0)
+    return m
+
+
+def block_on_pebbles():
+    """The reference's own collision system on a multi-voxel body landing on two pebbles (several watched pairs per voxel,
+    friction, tipping): every contact is inter-body, where VX3 and Voxelyze2 select the same pairs."""
+    m = pebbles_model()
+    out = {}
+    for steps in PEBBLE_STEPS:
+        state, _, _ = O.run_reference(m.merged_vxa(), steps, vx2_collisions=True)
+        out[f"pos_{steps}"] = state["pos"]
+        out[f"orient_{steps}"] = state["orient"]
+    O.write_vxbin(os.path.join(HERE, "block_on_pebbles_vx2col.vxbin"), out)
+    print("block_on_pebbles_vx2col", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "two_body":
         two_body_drop()  # (the other fixtures are left as they are)
+    elif len(sys.argv) > 1 and sys.argv[1] == "pebbles":
+        block_on_pebbles()
     else:
         main()
         two_body_drop()
+        block_on_pebbles()

@@ -306,6 +306,20 @@ def test_contact_force_matches_the_frozen_reference_run(path):
             ctx.close()
 
 
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+def test_multi_pair_contact_matches_the_frozen_reference_run(path):
+    """A block landing on two pebbles (tests/golden/block_on_pebbles_vx2col.vxbin = the unmodified reference with its own
+    collision system): the engine in fp64 against it, several watched pairs at once, contact + floor friction, 2,000 steps."""
+    from golden.make_golden import PEBBLE_STEPS, pebbles_model
+    g = O.read_vxbin(os.path.join(GOLD, "block_on_pebbles_vx2col.vxbin"))
+    m = pebbles_model()
+    for steps in PEBBLE_STEPS:
+        ctx = gpu_run([m], steps, gv.FP64, path)
+        got = ctx.read_state(0)
+        assert np.abs(got["pos"] - g[f"pos_{steps}"]).max() < 5e-8, steps
+        ctx.close()
+
+
 def test_full_generation_is_batch_invariant():
     """BASELINE config 1 at full size (1,024 xenobot worlds, cilia + floor + contact): too many for the oracle, so check the
     size-independent property a generation has - worlds are independent.  A world stepped inside the 1,024-world launch must

@@ -113,6 +113,33 @@ def test_contact_force_matches_the_frozen_reference_run():
             assert O.rel_err(s["linMom"], g[f"linMom_{steps}"]) < 1e-5
 
 
+def test_multi_pair_contact_matches_the_frozen_reference_run():
+    """A 3x3x2 block landing on two pebbles, tipping and pushing them aside (tests/golden/block_on_pebbles_vx2col.vxbin: the
+    unmodified reference with ITS collision system): several watched pairs at once, contact + floor friction, 2,000 steps."""
+    from golden.make_golden import PEBBLE_STEPS, pebbles_model
+    g = O.read_vxbin(os.path.join(GOLD, "block_on_pebbles_vx2col.vxbin"))
+    m = pebbles_model()
+    touched = 0
+    for steps in PEBBLE_STEPS:
+        w = O.OracleWorld(m)
+        w.run(steps)
+        s = w.state()
+        touched += len(w.collision_pairs())
+        assert np.abs(s["pos"] - g[f"pos_{steps}"]).max() < 5e-8, steps  # metres (voxel 0.01 m; Voxelyze2 forms pair offsets in float)
+        assert np.abs(s["orient"] - g[f"orient_{steps}"]).max() < 1e-5, steps
+    assert touched >= 4
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built (needs /root/reference)")
+def test_multi_pair_contact_matches_the_reference_live():
+    from golden.make_golden import pebbles_model
+    m = pebbles_model()
+    ref, _, _ = O.run_reference(m.merged_vxa(), 700, vx2_collisions=True)
+    w = O.OracleWorld(m)
+    w.run(700)
+    assert np.abs(w.state()["pos"] - ref["pos"]).max() < 5e-8
+
+
 def test_oracle_stop_condition_and_fitness():
     m = gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=0.05), W.xenobot_vxd(2))
     w = O.OracleWorld(m)
