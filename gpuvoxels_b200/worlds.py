@@ -206,6 +206,20 @@ def block_on_pebbles_vxa():
     return vxa_document(mats, structure_xml(data), dt_frac=0.9, grav_acc=-9.81, floor=True, enable_collision=True)
 
 
+def cilia_pusher_vxd():
+    """VXD for xenobot_base_vxa(): a solid 3x3x2 cilia body (BaseCiliaForce +x) with one target pebble two cells ahead of it.
+    The body walks into the pebble and pushes it along the floor: cilia, contact with a target (hit counter), floor friction -
+    the ingredients of a xenobot run - while every contact stays inter-body (a solid block has no unlinked pair near 1.25 cells)."""
+    Z, Y, X = 3, 5, 9
+    data = np.zeros((Z, Y, X), dtype=int)
+    data[0:2, 1:4, 0:3] = 1
+    data[0, 2, 5] = 2
+    cilia = np.zeros((Z, Y, X, 3))
+    cilia[..., 0] = 1.0
+    cilia[data != 1] = 0
+    return "<VXD>" + structure_xml(data, base_cilia=cilia, replace="VXA.VXC.Structure") + "</VXD>"
+
+
 def contact_pile_vxa(k=3, cube=4, seed=7):
     """C4 synthetic: k x k grid of cube^3 bodies dropped from staggered heights so they pile up and collide."""
     rng = np.random.default_rng(seed)

@@ -10,9 +10,10 @@
 // semantics directly and the VX3 stepping deltas (temperature phase offsets, cilia, angMom
 // zeroing, double dt) through the harness — and against golden vectors in tests/golden/.
 // VX3 voxel-voxel contact (A.4 below): the per-pair FORCE is pinned against the reference's own
-// collision system (same formula, VX_Collision.cpp:42-56) on a two-body drop
-// (tests/golden/two_body_drop_vx2col.vxbin); the pair SELECTION (all surface pairs, depth-1
-// exclusion) has no executable reference here (the VX3 CUDA code cannot be built: boost +
+// collision system (same formula, VX_Collision.cpp:42-56) on a two-body drop, a block landing on
+// two pebbles and a cilia body pushing a target (tests/golden/*_vx2col.vxbin: contacts BETWEEN
+// bodies, where both schemes watch the same pairs); the pair SELECTION inside one body (all
+// surface pairs, depth-1 exclusion) has no executable reference here (the VX3 CUDA code cannot be built: boost +
 // device-side cudaDeviceSynchronize; Voxelyze2 selects pairs differently): that part is PARITY UNPINNED.
 //
 // Reference map (all under /root/reference/Voxelyze3/src unless noted):

@@ -90,12 +90,37 @@ def block_on_pebbles():
     print("block_on_pebbles_vx2col", {k: v.shape for k, v in out.items()})
 
 
+PUSHER_STEPS = (200, 1000, 2000, 4000)
+
+
+def pusher_model():
+    m = gv.Model.from_vxa(W.xenobot_base_vxa(), W.cilia_pusher_vxd())
+    m.set_world_param("enable_cilia", 1)
+    return m
+
+
+def cilia_pusher():
+    """VX3 semantics end to end against the reference: harness --vx3 (double dt, cilia, angMom zeroing) + the reference's own
+    collision system, on a cilia body pushing a target pebble 1.4 m along the floor."""
+    m = pusher_model()
+    out = {}
+    for steps in PUSHER_STEPS:
+        state, _, _ = O.run_reference(m.merged_vxa(), steps, vx3=True, enable_cilia=True, vx2_collisions=True)
+        out[f"pos_{steps}"] = state["pos"]
+        out[f"orient_{steps}"] = state["orient"]
+    O.write_vxbin(os.path.join(HERE, "cilia_pusher_vx3_vx2col.vxbin"), out)
+    print("cilia_pusher_vx3_vx2col", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "two_body":
         two_body_drop()  # (the other fixtures are left as they are)
     elif len(sys.argv) > 1 and sys.argv[1] == "pebbles":
         block_on_pebbles()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pusher":
+        cilia_pusher()
     else:
         main()
         two_body_drop()
         block_on_pebbles()
+        cilia_pusher()

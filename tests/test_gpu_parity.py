@@ -320,6 +320,21 @@ def test_multi_pair_contact_matches_the_frozen_reference_run(path):
         ctx.close()
 
 
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+def test_vx3_cilia_body_pushing_a_target_matches_the_frozen_reference_run(path):
+    """VX3 semantics with cilia, a target hit counter, contact and floor friction against the reference (harness --vx3 + its own
+    collision system, tests/golden/cilia_pusher_vx3_vx2col.vxbin): the engine in fp64, 4,000 steps, 1.4 m of travel."""
+    from golden.make_golden import PUSHER_STEPS, pusher_model
+    g = O.read_vxbin(os.path.join(GOLD, "cilia_pusher_vx3_vx2col.vxbin"))
+    m = pusher_model()
+    for steps in PUSHER_STEPS:
+        ctx = gpu_run([m], steps, gv.FP64, path)
+        got = ctx.read_state(0)
+        assert np.abs(got["pos"] - g[f"pos_{steps}"]).max() < 5e-7, steps
+        assert ctx.results()[0].collision_count > (1000 if steps >= 2000 else 0)
+        ctx.close()
+
+
 def test_full_generation_is_batch_invariant():
     """BASELINE config 1 at full size (1,024 xenobot worlds, cilia + floor + contact): too many for the oracle, so check the
     size-independent property a generation has - worlds are independent.  A world stepped inside the 1,024-world launch must

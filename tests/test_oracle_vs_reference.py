@@ -140,6 +140,23 @@ def test_multi_pair_contact_matches_the_reference_live():
     assert np.abs(w.state()["pos"] - ref["pos"]).max() < 5e-8
 
 
+def test_vx3_cilia_body_pushing_a_target_matches_the_frozen_reference_run():
+    """VX3 semantics (double dt, cilia, angMom zeroing) WITH contact against the reference (harness --vx3 + its own collision
+    system; tests/golden/cilia_pusher_vx3_vx2col.vxbin): a cilia body walks into a target pebble and pushes it 1.4 m along the
+    floor in 4,000 steps.  The harness injects cilia through CVX_External's float force, hence float-level agreement."""
+    from golden.make_golden import PUSHER_STEPS, pusher_model
+    g = O.read_vxbin(os.path.join(GOLD, "cilia_pusher_vx3_vx2col.vxbin"))
+    m = pusher_model()
+    for steps in PUSHER_STEPS:
+        w = O.OracleWorld(m)
+        w.run(steps)
+        s = w.state()
+        assert np.abs(s["pos"] - g[f"pos_{steps}"]).max() < 5e-7, steps  # metres, after up to 1.4 m of travel
+        assert np.abs(s["orient"] - g[f"orient_{steps}"]).max() < 1e-4, steps
+    assert w.result().collision_count > 1000  # the target was being pushed (hit counter, VX3_VoxelyzeKernel.cu:706-708)
+    assert np.abs(g["pos_2000"][:, 0]).max() > 1.0
+
+
 def test_oracle_stop_condition_and_fitness():
     m = gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=0.05), W.xenobot_vxd(2))
     w = O.OracleWorld(m)
