@@ -333,6 +333,12 @@ def test_vx3_cilia_body_pushing_a_target_matches_the_frozen_reference_run(path):
         assert np.abs(got["pos"] - g[f"pos_{steps}"]).max() < 5e-7, steps
         assert ctx.results()[0].collision_count > (1000 if steps >= 2000 else 0)
         ctx.close()
+    # production precision (north star: fp32 within 1e-3 relative): within 1e-4 of the distance travelled after 2,000 steps of pushing
+    ctx = gpu_run([m], 2000, gv.FP32, path)
+    got, ref = ctx.read_state(0)["pos"], g["pos_2000"]
+    travel = np.abs(ref[:, 0]).max()
+    assert np.abs(got - ref).max() < 1e-4 * travel  # measured 1.2e-5 ... 2.4e-5 m on 1.41 m
+    ctx.close()
 
 
 def test_full_generation_is_batch_invariant():
