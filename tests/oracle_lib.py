@@ -172,6 +172,33 @@ def run_reference(vxa_text, steps, vx3=False, enable_cilia=False, enable_expansi
     return state, model, tim
 
 
+REF3_BIN = os.path.join(ROOT, "oracle", "_ref", "vx3_ref")
+
+
+def have_reference_vx3():
+    return os.path.exists(REF3_BIN) and os.access(REF3_BIN, os.X_OK)
+
+
+def run_reference_vx3(merged_vxa_text, steps, use_stop=False, dump_at=(), timing=False, repeat=1):
+    """Run the reference's own Voxelyze3 step code (host build, oracle/_ref/vx3_ref: serial thread schedule) on a MERGED VXA text
+    (base VXA with the VXD applied).  Returns (dict of arrays; checkpoints carry the suffix _N, the final state none), timing."""
+    with tempfile.TemporaryDirectory() as td:
+        vxa = os.path.join(td, "in.vxa")
+        with open(vxa, "w") as f:
+            f.write(merged_vxa_text)
+        cmd = [REF3_BIN, "--vxa", vxa, "--steps", str(steps), "--dump", os.path.join(td, "s.vxbin"), "--repeat", str(repeat)]
+        if use_stop:
+            cmd.append("--use-stop")
+        if dump_at:
+            cmd += ["--dump-at", ",".join(str(int(x)) for x in dump_at)]
+        if timing:
+            cmd.append("--time")
+        out = subprocess.run(cmd, check=True, capture_output=True, text=True)
+        state = read_vxbin(os.path.join(td, "s.vxbin"))
+        tim = json.loads(out.stdout.strip().splitlines()[-1]) if timing else None
+    return state, tim
+
+
 def rel_err(a, b):
     """max |a-b| / max(|b|) over the array — the 'relative' of the north-star tolerances."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
