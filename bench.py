@@ -44,6 +44,10 @@ def parse_args():
     ap.add_argument("--cube", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-worlds", type=int, default=8)
+    ap.add_argument("--workloads", default="all", help="N = 1, default workload only: also measure these other BASELINE configs into a \"workloads\" block "
+                    "(all | none | comma list of cube100,pile,xenobot_fp64)")
+    ap.add_argument("--slab-cube", type=int, default=160, help="N > 1: edge of the ONE body also stepped as N slabs into a \"slab\" block (0 = skip)")
+    ap.add_argument("--slab-sim-steps", type=int, default=200)
     return ap.parse_args()
 
 
@@ -66,13 +70,7 @@ def workload_config(args):
 
 def build_worlds(args, rank):
     import gpuvoxels_b200 as gv
-    from gpuvoxels_b200 import worlds as W
-    if args.workload in ("cube", "slab"):
-        return [gv.Model.from_vxa(W.cube_vxa(args.cube))], [(W.cube_vxa(args.cube), None)]
-    if args.workload == "pile":
-        return [gv.Model.from_vxa(W.contact_pile_vxa(k=args.pile, cube=8))], [(W.contact_pile_vxa(k=args.pile, cube=8), None)]
-    base = W.xenobot_base_vxa()
-    texts = [(base, W.xenobot_vxd(rank * args.worlds + i)) for i in range(args.worlds)]
+    texts = world_texts(args, rank)
     return [gv.Model.from_vxa(a, d) for a, d in texts], texts
 
 
@@ -121,19 +119,19 @@ def reference_binary():
     return p if os.path.exists(p) and os.access(p, os.X_OK) else None
 
 
-def run_reference_sample(texts, sim_steps, procs, collisions=True):
+def run_reference_sample(texts, sim_steps, procs, collisions=True, threads=1):
     """Runs the UNMODIFIED reference CPU library on a sample of the same worlds, `procs` single-threaded processes at a time
     (the reference has no CPU batch mode; one process per core is how a generation uses a whole host).  Returns
     (voxel_steps_per_sec, total_voxel_steps, wall_seconds)."""
-    import gpuvoxels_b200 as gv
+    from gpuvoxels_b200.worlds import merge_vxd  # pure Python (xml.etree): this arm never loads libvx3b200.so
     ref = reference_binary()
     with tempfile.TemporaryDirectory() as td:
         jobs = []
         for i, (vxa, vxd) in enumerate(texts):
             p = os.path.join(td, f"w{i}.vxa")
             with open(p, "w") as f:
-                f.write(gv.Model.from_vxa(vxa, vxd).merged_vxa())
-            cmd = [ref, "--vxa", p, "--steps", str(sim_steps), "--vx3", "--enable-cilia", "1", "--threads", "1", "--time"]
+                f.write(merge_vxd(vxa, vxd))
+            cmd = [ref, "--vxa", p, "--steps", str(sim_steps), "--vx3", "--enable-cilia", "1", "--threads", str(threads), "--time"]
             if collisions:
                 cmd += ["--vx2-collisions", "1"]
             jobs.append(cmd)
@@ -160,6 +158,17 @@ def run_reference_sample(texts, sim_steps, procs, collisions=True):
     return min(procs, len(jobs)) * float(np.mean(rates)), vs, wall
 
 
+def world_texts(args, rank):
+    """(base VXA, VXD) text of every world of this rank - no host model, no library"""
+    from gpuvoxels_b200 import worlds as W
+    if args.workload in ("cube", "slab"):
+        return [(W.cube_vxa(args.cube), None)]
+    if args.workload == "pile":
+        return [(W.contact_pile_vxa(k=args.pile, cube=8), None)]
+    base = W.xenobot_base_vxa()
+    return [(base, W.xenobot_vxd(rank * args.worlds + i)) for i in range(args.worlds)]
+
+
 def oracle_port_sample(models, sim_steps):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
@@ -177,10 +186,20 @@ def cpu_baseline(args, models, texts):
     cores = os.cpu_count() or 1
     # xenobot: enough worlds for several seconds on every host core (32 per core); the big single-body workloads have one world
     n = min(len(texts), max(args.cpu_sample_worlds, 32 * cores))
-    steps = min(args.sim_steps, 1000 if args.workload == "xenobot" else 20 if args.workload == "pile" else 5)
+    steps = min(args.sim_steps, 1000 if args.workload == "xenobot" else 10 if args.workload == "pile" else 5)
     if reference_binary():
+        col = args.workload in ("xenobot", "pile")
+        if len(texts) == 1:
+            # one body: the reference's OpenMP loops over links / voxels (USE_OMP), timed at 1 thread and at every host core
+            v1, vs, wall1 = run_reference_sample(texts, steps, 1, collisions=col, threads=1)
+            vn, _, walln = run_reference_sample(texts, steps, 1, collisions=col, threads=cores)
+            best, used = (vn, cores) if vn > v1 else (v1, 1)
+            return {"value": best, "unit": METRIC, "cores": used, "kind": "reference", "value_1_thread": v1, f"value_{cores}_threads": vn,
+                    "sample": f"the same body x {steps} time steps, oracle/_ref/vx2_ref (unmodified CVoxelyze, OpenMP over links and voxels"
+                              f"{', its own collision system' if col else ''}) at OMP threads = 1 and = {cores}; step loop only; {vs} voxel-steps, "
+                              f"{wall1:.1f} s + {walln:.1f} s of wall clock including parse"}
         procs = min(cores, n)
-        v, vs, wall = run_reference_sample(texts[:n], steps, procs, collisions=args.workload in ("xenobot", "pile"))
+        v, vs, wall = run_reference_sample(texts[:n], steps, procs, collisions=col)
         return {"value": v, "unit": METRIC, "cores": procs, "kind": "reference",
                 "sample": f"{n} of the {len(texts)} worlds x {steps} time steps, oracle/_ref/vx2_ref (unmodified CVoxelyze + VX3 stepping deltas, its own "
                           f"collision system), {procs} single-threaded processes in parallel; {vs} voxel-steps in {wall:.1f} s"}
@@ -193,8 +212,8 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    import gpuvoxels_b200 as gv  # host model only (parsing); no CUDA needed for this arm
-    models, texts = build_worlds(args, 0)
+    texts = world_texts(args, 0)  # text only: this arm does not load the product library
+    models = None
     cores = os.cpu_count() or 1
     n = min(len(texts), max(8 * cores, args.cpu_sample_worlds))
     steps = min(args.sim_steps, 500 if args.workload == "xenobot" else 3)
@@ -202,15 +221,18 @@ def main_reference(args):
     kind = "reference" if reference_binary() else "port"
     for it in range(args.warmup + args.steps):
         if kind == "reference":
-            v, vs, wall = run_reference_sample(texts[:n], steps, min(cores, n), collisions=args.workload in ("xenobot", "pile"))
+            one = len(texts) == 1  # a single body uses the reference's OpenMP threads, a generation one process per core
+            v, vs, wall = run_reference_sample(texts[:n], steps, min(cores, n), collisions=args.workload in ("xenobot", "pile"), threads=cores if one else 1)
         else:
+            if models is None:
+                models = build_worlds(args, 0)[0]
             v, vs, wall = oracle_port_sample(models[:n], steps)
         if it >= args.warmup:
             times.append(wall)
             vs_total += vs
             rates.append(v)
     value = float(np.mean(rates))
-    used = min(cores, n) if kind == "reference" else 1
+    used = (cores if len(texts) == 1 else min(cores, n)) if kind == "reference" else 1
     sample = (f"each step = {n} of the {len(texts)} worlds x {steps} time steps on the host CPU "
               f"({'oracle/_ref/vx2_ref, unmodified reference CPU library' if kind == 'reference' else 'oracle port'}, {used} core(s))")
     cfg = workload_config(args)
@@ -234,21 +256,14 @@ def upload_bytes(models):
     return total
 
 
-def main_ours(args):
+def measure(args, rank, world, local):
+    """One workload on this rank's GPU: device-timed throughput with the worlds resident in HBM, the end-to-end number through the
+    C ABI with host buffers, roofline of the dominant kernel, CPU baseline (rank 0, N = 1).  Returns the JSON object on rank 0."""
     import torch
     import torch.distributed as dist
     import ctypes as C
     import gpuvoxels_b200 as gv
     from gpuvoxels_b200 import _abi
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
         if world > 1:
@@ -321,6 +336,7 @@ def main_ours(args):
     dev_ms_max, wall_max, e2e_wall_max = stats.tolist()
     vs_all, e2e_vs_all, launches_all, diverged_all = work.tolist()
 
+    out = None
     if rank == 0:
         value = vs_all / (dev_ms_max * 1e-3)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -369,22 +385,69 @@ def main_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, models, texts)
-        print(json.dumps(out))
     ctx.close()
+    return out if rank == 0 else None
+
+
+# the other single-GPU configurations of BASELINE.json, measured in the same run so the driver's record carries them:
+# name -> (argument overrides, bench steps, warm-up steps)
+EXTRA_WORKLOADS = {
+    "cube100": (dict(workload="cube", cube=100, sim_steps=200, precision=32), 3, 3),
+    "pile": (dict(workload="pile", pile=12, sim_steps=200, precision=32), 3, 3),
+    "xenobot_fp64": (dict(workload="xenobot", sim_steps=200, precision=64), 2, 3),
+}
+
+
+def main_ours(args):
+    import copy
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = measure(args, rank, world, local)
+    names = [] if args.workloads == "none" else list(EXTRA_WORKLOADS) if args.workloads == "all" else args.workloads.split(",")
+    if world == 1 and args.workload == "xenobot" and args.precision == 32 and names:
+        out["workloads"] = {}
+        for name in names:
+            over, k, w = EXTRA_WORKLOADS[name]
+            a2 = copy.copy(args)
+            for key, v in over.items():
+                setattr(a2, key, v)
+            a2.steps, a2.warmup = k, w
+            try:
+                r = measure(a2, rank, world, local)
+                keep = ("value", "unit", "steps", "warmup", "ms_per_step", "dtype", "config", "voxels_per_gpu", "links_per_gpu", "diverged_worlds", "roofline", "e2e",
+                        "gpu_launches", "clocks", "cpu_baseline", "contact_rebuilds_per_world_rank0")
+                out["workloads"][name] = {key: r[key] for key in keep if key in r}
+            except Exception as e:  # noqa: BLE001 - the headline line must still be printed
+                out["workloads"][name] = {"error": f"{type(e).__name__}: {e}"}
+    if world > 1 and args.slab_cube > 0:
+        # BASELINE configs[4], second part, in the same multi-GPU run: ONE body cut into N slabs (strong scaling)
+        a2 = copy.copy(args)
+        a2.cube, a2.sim_steps, a2.steps, a2.warmup, a2.verify = args.slab_cube, args.slab_sim_steps, 3, 3, False
+        try:
+            slab = measure_slab(a2, rank, world, local)
+        except Exception as e:  # noqa: BLE001
+            slab = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            out["slab"] = slab
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
 def main_slab(args):
-    """One body over N GPUs (strong scaling: the body is fixed, N slabs).  A bench step = --sim-steps time steps, each followed by
-    the halo exchange; device time from CUDA events on the slab's stream, max over ranks."""
     import torch
     import torch.distributed as dist
-    import gpuvoxels_b200 as gv
-    from gpuvoxels_b200 import slab as S
-    from gpuvoxels_b200 import worlds as W
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -393,6 +456,23 @@ def main_slab(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    out = measure_slab(args, rank, world, local)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_slab(args, rank, world, local):
+    """One body over N GPUs (strong scaling: the body is fixed, N slabs).  A bench step = --sim-steps time steps, each followed by
+    the halo exchange; device time from CUDA events on the slab's stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import gpuvoxels_b200 as gv
+    from gpuvoxels_b200 import slab as S
+    from gpuvoxels_b200 import worlds as W
+
     t_host = time.perf_counter()
     model = gv.Model.from_vxa(W.cube_vxa(args.cube))
     part = S.split_body(model, world)[rank]
@@ -467,6 +547,7 @@ def main_slab(args):
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     dev_ms_max, wall_max = stats.tolist()
     vs_all, diverged_all, halo_all = work.tolist()
+    out = None
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -487,11 +568,8 @@ def main_slab(args):
                "e2e": {"value": vs_all / wall_max, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "what": "same timed region by host wall clock (per-step launches + NCCL calls included); the body is uploaded once before it"},
                "gpu_launches": int(nsteps * (1 + (2 if world > 1 else 0) * 2)), "clocks": clocks}
-        print(json.dumps(out))
     run.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return out if rank == 0 else None
 
 
 if __name__ == "__main__":

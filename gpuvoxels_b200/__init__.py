@@ -337,18 +337,31 @@ class SimulationManager:
 
     def start(self):
         import math
-        self.h_results = []
-        for device_index, files in enumerate(self.sub_batches):
-            if not files:
-                continue
-            models = [Model.from_files(self.base, os.path.join(self.input_dir, f)) for f in files]
-            ctx = Context(device_index, self.precision)
-            ctx.upload(models)
-            ctx.run(1000000, use_stop_formula=True)
-            for f, m, r in zip(files, models, ctx.results()):
-                self.h_results.append({"vxa_filename": os.path.basename(f), "result": r, "model": m,
-                                       "pos": ctx.read_state(len(self.h_results) % len(models))["pos"] if m.desc.save_position_of_all_voxels else None})
-            ctx.close()
+        import threading
+        per_device = [[] for _ in self.sub_batches]
+        errors = []
+
+        def run_device(device_index, files):  # one host thread + one context per device, like csrc/job.cpp
+            try:
+                models = [Model.from_files(self.base, os.path.join(self.input_dir, f)) for f in files]
+                ctx = Context(device_index, self.precision)
+                ctx.upload(models)
+                ctx.run(1000000, use_stop_formula=True)
+                for k, (f, m, r) in enumerate(zip(files, models, ctx.results())):
+                    pos = ctx.read_state(k)["pos"] if m.desc.save_position_of_all_voxels else None
+                    per_device[device_index].append({"vxa_filename": os.path.basename(f), "result": r, "model": m, "pos": pos})
+                ctx.close()
+            except Exception as e:  # noqa: BLE001 - re-raised on the caller's thread below
+                errors.append(e)
+
+        threads = [threading.Thread(target=run_device, args=(d, files)) for d, files in enumerate(self.sub_batches) if files]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        self.h_results = [e for dev in per_device for e in dev]
         self.h_results.sort(key=lambda e: (math.isnan(e["result"].fitness_score), -e["result"].fitness_score
                                            if not math.isnan(e["result"].fitness_score) else 0.0))
         return self.h_results

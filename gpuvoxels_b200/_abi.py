@@ -109,6 +109,9 @@ SYMBOLS = {
     "vx3b_ctx_total_voxel_steps": (C.c_int64, [_P]),
     "vx3b_ctx_set_stream": (C.c_int, [_P, C.c_uint64]),
     "vx3b_job_run": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
+    "vx3b_job_run_files": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int, C.c_int]),
+    "vx3b_job_run_task": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "vx3b_job_history_files": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int]),
     "vx3b_shard_worlds": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int32)]),
 }
 

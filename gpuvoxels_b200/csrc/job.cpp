@@ -89,17 +89,9 @@ extern "C" int vx3b_shard_worlds(const int64_t *cost, int n, int num_shards, int
     return VX3B_OK;
 }
 
-extern "C" int vx3b_job_run(const char *input_dir, const char *report_path, int num_devices, int precision) {
-    using namespace vx3b;
-    if (!input_dir || !report_path || num_devices < 1) {
-        set_error("vx3b_job_run: bad argument");
-        return VX3B_ERR_ARG;
-    }
-    std::string dir = input_dir, base;
-    if (!read_file(dir + "/base.vxa", &base)) {
-        set_error("vx3b_job_run: no base.vxa in " + dir);
-        return VX3B_ERR_IO;
-    }
+namespace vx3b {
+// every *.vxd of a directory, sorted by name (what Voxelyze3.cpp:101-105 lists into the task file)
+static std::vector<std::string> list_vxd(const std::string &dir) {
     std::vector<std::string> files;
     if (DIR *d = opendir(dir.c_str())) {
         while (dirent *e = readdir(d))
@@ -108,28 +100,48 @@ extern "C" int vx3b_job_run(const char *input_dir, const char *report_path, int 
         closedir(d);
     }
     std::sort(files.begin(), files.end());
-    if (files.empty()) {
-        set_error("vx3b_job_run: no .vxd files in " + dir);
+    return files;
+}
+static std::vector<std::string> to_list(const char *const *files, int n) {
+    std::vector<std::string> v;
+    for (int i = 0; i < n; i++)
+        v.push_back(files[i] ? files[i] : "");
+    return v;
+}
+
+static int job_run(const std::string &basePath, const std::string &dir, const std::vector<std::string> &files, const char *report_path, int num_devices,
+                   int precision) {
+    std::string base;
+    if (!read_file(basePath, &base)) {
+        set_error("vx3b_job_run: cannot read " + basePath);
         return VX3B_ERR_IO;
     }
-    std::vector<JobWorld> worlds(files.size());
+    if (files.empty()) {
+        set_error("vx3b_job_run: no .vxd files for " + dir);
+        return VX3B_ERR_IO;
+    }
+    // A file that cannot be read or parsed is reported and left out, like the reference, which prints the reader's message
+    // and carries on with the next file (VX3_SimulationManager.cu:305-309); the job only fails when nothing is left.
+    std::vector<JobWorld> worlds;
+    std::string firstError;
     for (size_t i = 0; i < files.size(); i++) {
         std::string vxd;
-        if (!read_file(dir + "/" + files[i], &vxd)) {
-            set_error("vx3b_job_run: cannot read " + files[i]);
-            return VX3B_ERR_IO;
-        }
-        worlds[i].file = files[i];
-        int rc = vx3b_model_from_vxa(base.c_str(), vxd.c_str(), &worlds[i].model);
+        JobWorld w;
+        w.file = files[i];
+        int rc = read_file(dir + "/" + files[i], &vxd) ? vx3b_model_from_vxa(base.c_str(), vxd.c_str(), &w.model) : VX3B_ERR_IO;
         if (rc != VX3B_OK) {
-            std::string msg = std::string(files[i]) + ": " + vx3b_last_error();
-            for (auto &w : worlds)
-                if (w.model)
-                    vx3b_model_free(w.model);
-            set_error(msg);
-            return rc;
+            const std::string msg = files[i] + ": " + (rc == VX3B_ERR_IO ? std::string("cannot read file") : std::string(vx3b_last_error()));
+            fprintf(stderr, "ERROR: %s (skipped)\n", msg.c_str());
+            if (firstError.empty())
+                firstError = msg;
+            continue;
         }
-        vx3b_model_desc(worlds[i].model, &worlds[i].desc);
+        vx3b_model_desc(w.model, &w.desc);
+        worlds.push_back(std::move(w));
+    }
+    if (worlds.empty()) {
+        set_error("vx3b_job_run: no usable .vxd (" + firstError + ")");
+        return VX3B_ERR_PARSE;
     }
     // split over devices, one host thread and one context per device.  The reference deals files round-robin
     // (vx3_node_worker.cu:88-93); worlds differ 10x in cost, so we deal them longest-processing-time-first instead.
@@ -260,6 +272,26 @@ extern "C" int vx3b_job_run(const char *input_dir, const char *report_path, int 
             vx3b_model_free(w.model);
     return rcAll;
 }
+} // namespace vx3b
+
+extern "C" int vx3b_job_run(const char *input_dir, const char *report_path, int num_devices, int precision) {
+    using namespace vx3b;
+    if (!input_dir || !report_path || num_devices < 1) {
+        set_error("vx3b_job_run: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    const std::string dir = input_dir;
+    return job_run(dir + "/base.vxa", dir, list_vxd(dir), report_path, num_devices, precision);
+}
+extern "C" int vx3b_job_run_files(const char *base_vxa_path, const char *input_dir, const char *const *vxd_files, int num_files, const char *report_path,
+                                  int num_devices, int precision) {
+    using namespace vx3b;
+    if (!base_vxa_path || !input_dir || !report_path || num_devices < 1 || num_files < 0 || (num_files > 0 && !vxd_files)) {
+        set_error("vx3b_job_run_files: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    return job_run(base_vxa_path, input_dir, to_list(vxd_files, num_files), report_path, num_devices, precision);
+}
 
 // ---- .history stream -----------------------------------------------------------------------------------------
 // Replaces the history printf()s of CUDA_Simulation (VX3/VX3_SimulationManager.cu:40-114): same text, produced on the host from
@@ -332,25 +364,13 @@ static void write_frame(FILE *f, const HistoryWorld &H, long long j, double t) {
 
 } // namespace vx3b
 
-extern "C" int vx3b_job_history(const char *input_dir, const char *out_path, int precision) {
-    using namespace vx3b;
-    if (!input_dir) {
-        set_error("vx3b_job_history: bad argument");
-        return VX3B_ERR_ARG;
-    }
-    std::string dir = input_dir, base;
-    if (!read_file(dir + "/base.vxa", &base)) {
-        set_error("vx3b_job_history: no base.vxa in " + dir);
+namespace vx3b {
+static int job_history(const std::string &basePath, const std::string &dir, const std::vector<std::string> &files, const char *out_path, int precision) {
+    std::string base;
+    if (!read_file(basePath, &base)) {
+        set_error("vx3b_job_history: cannot read " + basePath);
         return VX3B_ERR_IO;
     }
-    std::vector<std::string> files;
-    if (DIR *dd = opendir(dir.c_str())) {
-        while (dirent *e = readdir(dd))
-            if (ends_with_ci(e->d_name, ".vxd"))
-                files.push_back(e->d_name);
-        closedir(dd);
-    }
-    std::sort(files.begin(), files.end());
     FILE *f = out_path ? fopen(out_path, "w") : stdout;
     if (!f) {
         set_error(std::string("vx3b_job_history: cannot write ") + out_path);
@@ -446,4 +466,61 @@ extern "C" int vx3b_job_history(const char *input_dir, const char *out_path, int
     else
         fflush(f);
     return rc;
+}
+} // namespace vx3b
+
+extern "C" int vx3b_job_history(const char *input_dir, const char *out_path, int precision) {
+    using namespace vx3b;
+    if (!input_dir) {
+        set_error("vx3b_job_history: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    const std::string dir = input_dir;
+    return job_history(dir + "/base.vxa", dir, list_vxd(dir), out_path, precision);
+}
+extern "C" int vx3b_job_history_files(const char *base_vxa_path, const char *input_dir, const char *const *vxd_files, int num_files, const char *out_path,
+                                      int precision) {
+    using namespace vx3b;
+    if (!base_vxa_path || !input_dir || num_files < 0 || (num_files > 0 && !vxd_files)) {
+        set_error("vx3b_job_history_files: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    return job_history(base_vxa_path, input_dir, to_list(vxd_files, num_files), out_path, precision);
+}
+
+// The task file the front-end hands to the worker (Voxelyze3.cpp:101-111; read back at vx3_node_worker.cu:64-75):
+// <vxa>path of the base VXA</vxa> <input_dir>directory of the VXD files</input_dir> <vxd><f>file</f>...</vxd>
+extern "C" int vx3b_job_run_task(const char *vxt_path, const char *report_path, int num_devices, int precision, int stream_history) {
+    using namespace vx3b;
+    if (!vxt_path || !report_path || num_devices < 1) {
+        set_error("vx3b_job_run_task: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    std::string text, err;
+    if (!read_file(vxt_path, &text)) {
+        set_error(std::string("vx3b_job_run_task: cannot read ") + vxt_path);
+        return VX3B_ERR_IO;
+    }
+    auto root = xml_parse(text, &err); // decodes the predefined entities boost's write_xml escapes paths with
+    if (!root) {
+        set_error(std::string("vx3b_job_run_task: ") + vxt_path + ": " + err);
+        return VX3B_ERR_PARSE;
+    }
+    const XmlNode *vxa = root->child("vxa"), *dirNode = root->child("input_dir"), *vxd = root->child("vxd");
+    if (!dirNode || xml_trim(dirNode->text).empty()) {
+        set_error(std::string("vx3b_job_run_task: no input_dir in ") + vxt_path);
+        return VX3B_ERR_PARSE;
+    }
+    const std::string dir = xml_trim(dirNode->text);
+    const std::string base = vxa && !xml_trim(vxa->text).empty() ? xml_trim(vxa->text) : dir + "/base.vxa";
+    std::vector<std::string> files;
+    if (vxd)
+        for (auto &c : vxd->children)
+            files.push_back(xml_trim(c->text));
+    if (stream_history) {
+        int rc = job_history(base, dir, files, nullptr, precision);
+        if (rc != VX3B_OK)
+            return rc;
+    }
+    return job_run(base, dir, files, report_path, num_devices, precision);
 }

@@ -1,14 +1,12 @@
 // vx3_node_worker — same command line and report as the reference's worker (Voxelyze3/src/Executables/vx3_node_worker.cu:32-142):
 //   vx3_node_worker -i <task.vxt> -o <result.vxr> [-f]
-// <task.vxt> is the XML the front-end writes ({vxa, input_dir, vxd.f*}, Voxelyze3.cpp:101-111).  Every *.vxd of input_dir is
-// simulated over base.vxa on all visible GPUs and the report XML is written to <result.vxr>.
+// <task.vxt> is the XML the front-end writes ({vxa, input_dir, vxd.f*}, Voxelyze3.cpp:101-111).  The VXD files it lists are
+// simulated over its base VXA on all visible GPUs (vx3b_job_run_task) and the report XML is written to <result.vxr>.
 #include <sys/stat.h>
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <fstream>
-#include <sstream>
 #include <string>
 
 #include "vx3b200.h"
@@ -16,14 +14,6 @@
 static bool is_file(const std::string &p) {
     struct stat st;
     return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
-}
-static std::string tag_text(const std::string &xml, const std::string &tag) {
-    size_t a = xml.find("<" + tag + ">");
-    if (a == std::string::npos)
-        return "";
-    a += tag.size() + 2;
-    size_t b = xml.find("</" + tag + ">", a);
-    return b == std::string::npos ? "" : xml.substr(a, b - a);
 }
 static void usage() {
     printf("This application is called by Voxelyze3, and it can utilize all GPUs on single node to run simulations.\n"
@@ -67,14 +57,6 @@ int main(int argc, char **argv) {
         usage();
         return 1;
     }
-    std::ifstream f(input);
-    std::stringstream ss;
-    ss << f.rdbuf();
-    std::string dir = tag_text(ss.str(), "input_dir");
-    if (dir.empty()) {
-        printf("ERROR: no input_dir in %s\n", input.c_str());
-        return 1;
-    }
     if (devices <= 0) {
         const char *e = getenv("VX3B_DEVICES");
         devices = e ? atoi(e) : 0;
@@ -93,10 +75,9 @@ int main(int argc, char **argv) {
             return 1;
         }
     }
-    // worlds that ask for it (VXA.Simulator.RecordHistory.RecordStepSize) stream their .history to stdout, as the reference's
+    // worlds that ask for it (VXA.Simulator.RecordHistory.RecordStepSize) stream their .history to stdout first, as the reference's
     // device-side printf does (VX3_SimulationManager.cu:40-114); `Voxelyze3 -i <dir> > a.history` captures it
-    vx3b_job_history(dir.c_str(), nullptr, precision);
-    int rc = vx3b_job_run(dir.c_str(), output.c_str(), devices, precision);
+    int rc = vx3b_job_run_task(input.c_str(), output.c_str(), devices, precision, 1);
     if (rc != VX3B_OK) {
         printf("ERROR: %s\n", vx3b_last_error());
         return 1;

@@ -238,3 +238,78 @@ def contact_pile_vxa(k=3, cube=4, seed=7):
             data[z0:z0 + cube, a * gap + cube // 2 + 1:a * gap + cube // 2 + 1 + cube, b * gap + cube // 2 + 1:b * gap + cube // 2 + 1 + cube] = 2
     mats = [material(name="lower", E=5e6, density=1e6), material(name="upper", E=1e7, density=1e6)]
     return vxa_document(mats, structure_xml(data), dt_frac=0.9, grav_acc=-9.81, floor=True, enable_collision=True)
+
+
+# ---- formula XML helpers (Utils/VX3_MathTree.h operators) --------------------------------------------------------------
+def mt_const(v):
+    return f"<mtCONST>{float(v)!r}</mtCONST>"
+
+
+def mt_var(name):
+    return f"<mtVAR>{name}</mtVAR>"
+
+
+def mt(op, *args):
+    """mt("ADD", a, b) -> <mtADD>a b</mtADD>; mt("E") / mt("PI") are leaves"""
+    return f"<mt{op}>" + "".join(args) + f"</mt{op}>"
+
+
+def force_field_formulas():
+    """Three force-field formulas (N per voxel) that between them use EVERY operator of the reference's formula machine
+    (Utils/VX3_MathTree.h:50-193) on position- and time-dependent arguments."""
+    x, y, z, t = mt_var("x"), mt_var("y"), mt_var("z"), mt_var("t")
+    fx = mt("MUL", mt("MUL", mt("POW", mt("ADD", mt("ABS", mt("SUB", x, mt_const(0.01))), mt_const(1)), mt_const(0.5)), mt("GREATERTHAN", z, mt_const(0.004))),
+            mt_const(14.0))
+    fy = mt("SUB", mt("MUL", mt("NORMALCDF", mt("SUB", mt("MUL", t, mt_const(20)), mt_const(1))), mt_const(9.0)),
+            mt("MUL", mt("LESSTHAN", y, mt_const(0.01)), mt_const(2.0)))
+    wave = mt("ADD", mt("SIN", mt("MUL", t, mt_const(50))), mt("COS", mt("DIV", x, mt_const(0.01))))
+    logic = mt("OR", mt("AND", mt("GREATERTHAN", x, mt_const(0.005)), mt("NOT", mt("LESSTHAN", y, mt_const(0.005)))), mt("INT", mt("MUL", t, mt_const(3))))
+    misc = mt("ADD", mt("ATAN", mt("TAN", mt("MUL", z, mt_const(10)))), mt("MUL", mt("SQRT", mt("ADD", mt("LOG", mt("ADD", mt("E"), t)), mt("PI"))), mt_const(0.1)))
+    fz = mt("ADD", mt("MUL", mt_const(0.2), wave), mt("ADD", mt("MUL", mt_const(0.4), logic), misc))
+    return fx, fy, fz
+
+
+def force_field_vxa(enable_collision=False):
+    """A 3x3x2 two-material block under gravity on the floor, thermally actuated, inside a force field (VX3_Voxel.cu:179-184)."""
+    rng = np.random.default_rng(11)
+    data = np.ones((2, 3, 3), dtype=int)
+    data[:, 1, 1] = 2
+    phase = rng.uniform(0, 1, size=data.shape)
+    mats = [material(name="soft", E=5e6, cte=0.0), material(name="active", E=1e7, cte=0.01)]
+    return vxa_document(mats, structure_xml(data, phase=phase), dt_frac=0.5, temp_amplitude=14.4714, vary_temp=True, temp_period=0.2,
+                        enable_collision=enable_collision, force_field=force_field_formulas(),
+                        fitness_formula=mt("ADD", mt("MUL", mt_var("x"), mt_const(100)), mt("POW", mt_const(2), mt_var("z"))))
+
+
+def merge_vxd(vxa_text, vxd_text):
+    """VXD applied to the base VXA the way Utils/ctool.h:49-57 (ptree_merge / put_child) does it: every child of <VXD> carrying a
+    `replace="VXA.a.b.c"` attribute replaces the first node on that path (missing levels are created).  Pure Python (xml.etree):
+    the reference arm of bench.py prepares its input with this, without loading the CUDA library."""
+    import xml.etree.ElementTree as ET
+    if not vxd_text:
+        return vxa_text
+    root = ET.fromstring(vxa_text.encode("latin-1", "replace") if isinstance(vxa_text, str) else vxa_text)
+    vxd = ET.fromstring(vxd_text.encode("latin-1", "replace") if isinstance(vxd_text, str) else vxd_text)
+    for child in list(vxd):
+        path = child.attrib.get("replace", "")
+        if not path:
+            continue
+        parts = path.split(".")
+        assert parts[0] == root.tag, path
+        node = root
+        for name in parts[1:-1]:
+            nxt = node.find(name)
+            if nxt is None:
+                nxt = ET.SubElement(node, name)
+            node = nxt
+        new = ET.fromstring(ET.tostring(child))
+        new.tag = parts[-1]
+        new.tail = None
+        old = node.find(parts[-1])
+        if old is None:
+            node.append(new)
+        else:
+            i = list(node).index(old)
+            node.remove(old)
+            node.insert(i, new)
+    return '<?xml version="1.0" encoding="ISO-8859-1"?>\n' + ET.tostring(root, encoding="unicode")

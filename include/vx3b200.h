@@ -244,10 +244,20 @@ int vx3b_batch_halo_import(vx3b_ctx *ctx, int world, int list_id, const void *de
  * VX3_SimulationManager.cu:138-155): every *.vxd in input_dir over base.vxa, worlds sharded over
  * `num_devices` GPUs, report XML in the reference's layout written to report_path. */
 int vx3b_job_run(const char *input_dir, const char *report_path, int num_devices, int precision);
+/* The same with the base VXA and the VXD file names (relative to input_dir) given explicitly: what the worker reads from its
+ * task file (vx3_node_worker.cu:64-75) and hands to VX3_SimulationManager(sub_batches, base, input_dir, nDevices).  A VXD that
+ * cannot be read or parsed is reported on stderr and left out of the report; the call fails only if none is usable. */
+int vx3b_job_run_files(const char *base_vxa_path, const char *input_dir, const char *const *vxd_files, int num_files, const char *report_path,
+                       int num_devices, int precision);
+/* The worker's whole job: read the task file <vxa>, <input_dir>, <vxd><f>...</f></vxd> the front-end wrote (Voxelyze3.cpp:101-111),
+ * stream the .history of recording worlds to stdout first when stream_history != 0, then run and write the report. */
+int vx3b_job_run_task(const char *vxt_path, const char *report_path, int num_devices, int precision, int stream_history);
 /* The .history stream of `Voxelyze3 -i <dir>` without -o (README.md:84-100, VX3_SimulationManager.cu:40-114): for every *.vxd
  * over base.vxa whose RecordStepSize is non-zero, the settings header, then every real_stepsize steps one frame of surface-voxel
  * records (and link records if RecordLink), in the reference's text format, to out_path (NULL = stdout).  One world at a time. */
 int vx3b_job_history(const char *input_dir, const char *out_path, int precision);
+int vx3b_job_history_files(const char *base_vxa_path, const char *input_dir, const char *const *vxd_files, int num_files, const char *out_path,
+                           int precision);
 /* Host-only: assign n worlds of the given cost to num_shards devices / ranks, longest-processing-time-first (the reference
  * deals files round-robin, vx3_node_worker.cu:88-93).  Deterministic, so every rank of a multi-process job agrees. */
 int vx3b_shard_worlds(const int64_t *cost, int n, int num_shards, int32_t *shard_of);

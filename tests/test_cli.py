@@ -64,3 +64,35 @@ def test_generation_through_the_front_end():
         assert root.find("bestfit/fitness_score").text == detail[0].find("fitness_score").text
         for x in detail:
             assert float(x.find("currentTime").text) > 0.05
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _have_bins(), reason="bin/ not built (python __graft_entry__.py)")
+def test_worker_honours_the_task_file():
+    """vx3_node_worker reads <vxa>, <input_dir> and the <vxd><f> list from the .vxt (vx3_node_worker.cu:64-75): a task that lists
+    a subset simulates only that subset, over the base VXA it names; XML entities in paths are decoded (the front-end escapes
+    them); a VXD that cannot be parsed is reported and left out instead of failing the generation."""
+    with tempfile.TemporaryDirectory() as td:
+        d = os.path.join(td, "gen & <1>")
+        os.makedirs(d)
+        base = os.path.join(td, "elsewhere.vxa")  # NOT <input_dir>/base.vxa
+        open(base, "w").write(W.xenobot_base_vxa(stop_seconds=0.03))
+        for i in range(4):
+            open(os.path.join(d, f"bot_{i:04d}.vxd"), "w").write(W.xenobot_vxd(50 + i))
+        open(os.path.join(d, "broken.vxd"), "w").write("<VXD><Structure replace=")
+        esc = lambda s: s.replace("&", "&amp;").replace("<", "&lt;").replace(">", "&gt;")  # noqa: E731
+        vxt = os.path.join(td, "task.vxt")
+        open(vxt, "w").write(f'<?xml version="1.0" encoding="utf-8"?>\n<vxa>{esc(base)}</vxa><input_dir>{esc(d)}</input_dir>'
+                             "<vxd><f>bot_0001.vxd</f><f>broken.vxd</f><f>bot_0003.vxd</f></vxd>")
+        vxr = os.path.join(td, "out.vxr")
+        r = subprocess.run([WORKER, "-i", vxt, "-o", vxr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "broken.vxd" in r.stderr
+        root = ET.parse(vxr).getroot()
+        assert root.find("inputdir").text == "gen & <1>"
+        assert sorted(x.tag for x in root.find("detail")) == ["bot_0001", "bot_0003"]
+        # and through the front-end: the whole directory, the broken file skipped
+        open(os.path.join(d, "base.vxa"), "w").write(W.xenobot_base_vxa(stop_seconds=0.03))
+        r = subprocess.run([FRONT, "-i", d, "-o", "report.xml", "-l", "-f"], cwd=td, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert sorted(x.tag for x in ET.parse(os.path.join(td, "report.xml")).getroot().find("detail")) == [f"bot_{i:04d}" for i in range(4)]

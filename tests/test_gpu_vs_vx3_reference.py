@@ -1,0 +1,216 @@
+"""The CUDA engine, through the C ABI, against frozen outputs of the reference's OWN Voxelyze3 step code
+(tests/golden/vx3ref_*.vxbin = oracle/_ref/vx3_ref, tests/golden/make_golden_vx3.py): VX3 semantics end to end, including what
+Voxelyze2's library cannot pin - contact inside a body, target hits, force field, formulas, fitness - on synthetic worlds and
+on the reference's own checked-in experiment inputs (tests/data/ref_inputs).  Tolerances are the north star's (BASELINE.json):
+fp64 validation build 1e-5 relative; fp32 1e-3 relative on collision-free cases; chaotic contact-heavy runs by fitness / world
+results within 1 %; watched pair sets bit-exact at a fixed step."""
+import os
+import tempfile
+import xml.etree.ElementTree as ET
+
+import numpy as np
+import pytest
+
+import gpuvoxels_b200 as gv
+import oracle_lib as O
+from gpuvoxels_b200 import worlds as W
+from golden.make_golden_vx3 import CASES, CIRCLE_PUSH_BOTS, CUBE100_STEPS
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF_INPUTS = os.path.join(ROOT, "tests", "data", "ref_inputs")
+STREAM, RESIDENT, FUSED, BRICK = 1, 2, 3, 5
+STEPS, HITS, FIT, COM, COM0, ANGLE = 3, 4, 5, slice(6, 9), slice(9, 12), 12
+
+
+def gpu_run(models, steps, precision, path, use_stop=False, **opts):
+    ctx = gv.Context(0, precision)
+    ctx.set_option("path", path)
+    for k, v in opts.items():
+        ctx.set_option(k, v)
+    ctx.upload(models)
+    ctx.run(steps, use_stop)
+    return ctx
+
+
+def disp_scale(model, pos):
+    return max(np.abs(pos - model.array("lattice") * model.desc.vox_size).max(), 1e-30)
+
+
+def sorted_pairs(p):
+    return np.array(sorted(map(tuple, np.asarray(p).reshape(-1, 2))), dtype=np.int32).reshape(-1, 2)
+
+
+def gold(name):
+    return O.read_vxbin(os.path.join(GOLD, name + ".vxbin"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
+@pytest.mark.parametrize("precision,tol", [(gv.FP64, 1e-5), (gv.FP32, 1e-3)])
+def test_force_field_and_every_formula_operator(path, precision, tol):
+    """x/y/z_forcefield formulas that between them use every operator of the formula machine (POW, NORMALCDF, GREATERTHAN,
+    LESSTHAN, AND, OR, NOT, INT, TAN, ATAN, SQRT, LOG, E, PI ...) push a thermally actuated block 5.7 cm across the floor
+    (VX3_Voxel.cu:179-184, Utils/VX3_ForceField.h, Utils/VX3_MathTree.h:50-193): against the reference's own code, frozen."""
+    vxa, _, steps, checkpoints, _ = CASES["vx3ref_forcefield_800"]
+    g = gold("vx3ref_forcefield_800")
+    m = gv.Model.from_vxa(vxa)
+    assert m.desc.force_field[0][0].op != 0 and m.desc.force_field[2][0].op != 0
+    for c, sfx in [(c, f"_{c}") for c in checkpoints] + [(steps, "")]:
+        ctx = gpu_run([m], c, precision, path)
+        got = ctx.read_state(0)
+        scale = disp_scale(m, g["pos" + sfx])
+        assert np.abs(got["pos"] - g["pos" + sfx]).max() / scale < tol, (c, scale)
+        assert np.abs(got["orient"] - g["orient" + sfx]).max() < max(tol, 1e-5) * max(np.abs(g["orient" + sfx][:, 1:]).max(), 1e-3)
+        if c == steps:
+            r = ctx.results()[0]
+            assert scale > 0.05  # it did travel
+            assert abs(r.fitness_score - g["scalars"][0, FIT]) < tol * abs(g["scalars"][0, FIT])  # 100 x + 2^z of the COM offset
+        ctx.close()
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
+def test_example_vxa_fp64_against_the_vx3_reference(path, example_vxa):
+    g = gold("vx3ref_example_1000")
+    m = gv.Model.from_vxa(example_vxa)
+    ctx = gpu_run([m], 1000, gv.FP64, path)
+    got = ctx.read_state(0)
+    assert np.abs(got["pos"] - g["pos"]).max() / disp_scale(m, g["pos"]) < 1e-5
+    assert ctx.results()[0].dt == g["scalars"][0, 1]
+    gl = ctx.read_links(0)
+    assert O.rel_err(gl["pos2"], g["link_state"][:, 0:3]) < 1e-4 and O.rel_err(gl["angle2v"], g["link_state"][:, 6:9]) < 1e-4
+    ctx.close()
+
+
+CONTACT_CASES = [("vx3ref_xeno7_contact_500", (100, 300, 500)), ("vx3ref_pile_k3c4_600", (260, 600)), ("vx3ref_memleaking_bot0000_1000", (300, 1000))] + \
+                [(f"vx3ref_circle_push_{b}_1000", (300, 1000)) for b in CIRCLE_PUSH_BOTS]
+
+
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("name,checkpoints", CONTACT_CASES, ids=[c[0][7:] for c in CONTACT_CASES])
+def test_contact_worlds_fp64_against_the_vx3_reference(name, checkpoints, path):
+    """Worlds WITH contact inside the body (thermally contracted xenobots bring their own diagonal neighbours inside the watch
+    radius), between bodies and with target pebbles - synthetic ones and the reference's own e.circle_push / d.memleaking
+    inputs - against the reference's VX3 code: positions to 1e-5 of the largest displacement, the watched pair SET and the
+    target-hit counter exactly."""
+    vxa, vxd, steps, _, _ = CASES[name]
+    g = gold(name)
+    m = gv.Model.from_vxa(vxa, vxd)
+    ctx = gv.Context(0, gv.FP64)
+    ctx.set_option("path", path)
+    ctx.set_option("record_pairs", 1)
+    ctx.upload([m])
+    done = 0
+    for c in checkpoints:
+        ctx.run(c - done)
+        done = c
+        sfx = "" if c == steps else f"_{c}"
+        got = ctx.read_state(0)
+        assert np.abs(got["pos"] - g["pos" + sfx]).max() / disp_scale(m, g["pos" + sfx]) < 1e-5, c
+        assert np.array_equal(sorted_pairs(ctx.collision_pairs(0)), g["pairs" + sfx]), c
+        assert ctx.results()[0].collision_count == g["scalars" + sfx][0, HITS], c
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["vx3ref_xeno7_contact_500", "vx3ref_circle_push_bot_0009_1000", "vx3ref_circle_push_bot_0003_1000"])
+def test_contact_worlds_fp32_against_the_vx3_reference(name):
+    """production precision on the same worlds, 300 steps (contact makes longer runs chaotic in float): 1e-3 of the displacement"""
+    vxa, vxd, _, _, _ = CASES[name]
+    g = gold(name)
+    m = gv.Model.from_vxa(vxa, vxd)
+    for path in (STREAM, RESIDENT, FUSED):
+        ctx = gpu_run([m], 300, gv.FP32, path, record_pairs=1)
+        got = ctx.read_state(0)
+        assert np.abs(got["pos"] - g["pos_300"]).max() / disp_scale(m, g["pos_300"]) < 1e-3, path
+        assert np.array_equal(sorted_pairs(ctx.collision_pairs(0)), g["pairs_300"]), path
+        ctx.close()
+
+
+def test_report_of_the_reference_generation_matches_the_vx3_reference():
+    """Experiments/xenobot/e.circle_push/data901 (base.vxa + 11 bots) through vx3b_job_run, the drop-in for `Voxelyze3 -i dir -o
+    report.xml`, in production precision: every world stops at the step the reference's code stops at (t = 5 s, 9,935 steps);
+    fitness = |angle| + ln(hit + 1) + ln(x^2 + y^2) within 1 % of the size of its terms (they nearly cancel, so a plain relative
+    error would be ill-defined), centre-of-mass travel within 1 % of the distance travelled for the worlds that go somewhere,
+    and the ranking of the worlds by fitness - what the evolution uses the report for - the same up to near-ties."""
+    d = os.path.join(REF_INPUTS, "e.circle_push_data901")
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "report.xml")
+        rc = gv.lib().vx3b_job_run(d.encode(), out.encode(), 1, gv.FP32)
+        assert rc == 0, gv.lib().vx3b_last_error()
+        detail = {x.tag: x for x in ET.parse(out).getroot().find("detail")}
+    assert sorted(detail) == sorted(CIRCLE_PUSH_BOTS)
+    fit, ref_fit = {}, {}
+    for b in CIRCLE_PUSH_BOTS:
+        sc = gold(f"vx3ref_circle_push_{b}_full")["scalars"][0]
+        x = detail[b]
+        assert abs(float(x.find("currentTime").text) - sc[0]) < 1e-9, b
+        com = np.array([float(x.find(f"currentCenterOfMass/{a}").text) for a in "xyz"])
+        com0 = np.array([float(x.find(f"initialCenterOfMass/{a}").text) for a in "xyz"])
+        assert np.abs(com0 - sc[COM0]).max() < 1e-12, b
+        travel, ref_travel = com - com0, sc[COM] - sc[COM0]
+        terms = abs(sc[ANGLE]) + abs(np.log(sc[HITS] + 1)) + abs(np.log(ref_travel[0] ** 2 + ref_travel[1] ** 2))
+        fit[b], ref_fit[b] = float(x.find("fitness_score").text), sc[FIT]
+        assert abs(fit[b] - ref_fit[b]) < 0.01 * terms, (b, fit[b], ref_fit[b])
+        if np.linalg.norm(ref_travel[:2]) > 0.02:  # two voxel lengths: below that the heading of a body that barely moves is noise
+            assert np.linalg.norm(travel - ref_travel) < 0.01 * np.linalg.norm(ref_travel) + 1e-4, (b, travel, ref_travel)
+    order, ref_order = sorted(fit, key=fit.get), sorted(ref_fit, key=ref_fit.get)
+    for a, b in zip(order, ref_order):
+        assert a == b or abs(ref_fit[a] - ref_fit[b]) < 0.05, (order, ref_order)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_million_voxel_body_against_the_vx3_reference_and_the_oracle():
+    """BASELINE configs[2] at FULL size (100^3 voxels, 2.97 M links), 20 steps: k_brick against (a) a frozen voxel subsample of
+    the reference's VX3 code on the same body (corner column, centre column, bottom-layer diagonal; per-layer mean sag) and
+    (b) the whole state of the CPU oracle run here - fp64 1e-5, fp32 1e-3 of the largest displacement."""
+    from golden.make_golden_vx3 import cube100_sample_indices
+    n = 100
+    g = gold("vx3ref_cube100_20")
+    pick = cube100_sample_indices(n)
+    assert np.array_equal(pick, g["sample"][:, 0])
+    m = gv.Model.from_vxa(W.cube_vxa(n))
+    want = O.OracleWorld(m)
+    want.run(CUBE100_STEPS)
+    ref = want.state()
+    nominal = m.array("lattice") * m.desc.vox_size
+    scale = np.abs(ref["pos"] - nominal).max()
+    assert abs(scale - g["disp_max_abs"].max()) < 1e-12 and scale > 5e-4
+    assert np.abs(ref["pos"][pick] - g["pos"]).max() < 1e-10 * scale  # the oracle itself against the frozen reference subsample
+    for precision, tol in ((gv.FP64, 1e-5), (gv.FP32, 1e-3)):
+        ctx = gpu_run([m], CUBE100_STEPS, precision, 0)  # automatic: a body this size goes to the brick path
+        got = ctx.read_state(0)
+        assert ctx.results()[0].dt == g["scalars"][0, 1]
+        assert np.abs(got["pos"][pick] - g["pos"]).max() < tol * scale, precision
+        assert np.abs(got["pos"] - ref["pos"]).max() < tol * scale, precision
+        assert np.abs(got["linMom"] - ref["linMom"]).max() < tol * np.abs(ref["linMom"]).max(), precision
+        sag = (got["pos"][:, 2] - nominal[:, 2]).reshape(n, -1).mean(axis=1)
+        assert np.abs(sag - g["disp_z_layer_mean"][:, 0]).max() < tol * scale
+        ctx.close()
+
+
+def test_full_generation_32_worlds_against_the_oracle():
+    """BASELINE configs[1] at full size: 32 of the 1,024 worlds of one launch (every 32nd: all size classes) against the CPU
+    oracle, which is bit-identical to the reference's VX3 code on such worlds (tests/test_oracle_vs_reference_vx3.py).
+    Production precision, 300 steps, cilia + floor + intra-body contact.  Tolerances per component, of the largest displacement:
+    z (gravity-driven, friction-free) 1e-3; x / y (cilia push against floor friction, whose static <-> kinetic switch amplifies
+    float rounding) 1e-2; the watched-pair count of the last step may differ by borderline pairs only."""
+    base = W.xenobot_base_vxa()
+    models = [gv.Model.from_vxa(base, W.xenobot_vxd(i)) for i in range(1024)]
+    steps = 300
+    ctx = gpu_run(models, steps, gv.FP32, 0, record_pairs=1)
+    res = ctx.results()
+    assert all(r.steps == steps and r.diverged == 0 for r in res)
+    worst = np.zeros(3)
+    for i in range(7, 1024, 32):
+        want = O.OracleWorld(models[i])
+        want.run(steps)
+        got, ref = ctx.read_state(i), want.state()
+        scale = disp_scale(models[i], ref["pos"])
+        e = np.abs(got["pos"] - ref["pos"]).max(axis=0) / scale
+        worst = np.maximum(worst, e)
+        assert e[2] < 1e-3 and e[0] < 1e-2 and e[1] < 1e-2, (i, e, scale)
+        assert res[i].collision_count == want.result().collision_count, i
+        assert abs(len(ctx.collision_pairs(i)) - len(want.collision_pairs())) <= 2, i
+    print("worst relative position error over 32 worlds (x, y, z):", worst)
+    ctx.close()

@@ -72,6 +72,22 @@ def test_model_matches_reference_live(maker):
     assert_model_matches(m, md)
 
 
+REF_INPUTS = os.path.join(ROOT, "tests", "data", "ref_inputs")
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("case", [("e.circle_push_data901", f"bot_{i:04d}.vxd") for i in range(11)] + [("d.memleaking_data1", "bot_0000.vxd")],
+                         ids=lambda c: c[0][0] + "_" + c[1][:8])
+def test_model_of_the_reference_experiment_inputs_matches_the_reference_parser(case):
+    """the reference's own checked-in experiment inputs (Experiments/xenobot/e.circle_push/data901, d.memleaking/data1): every
+    voxel, link, per-voxel phase / cilia vector and every float material constant is the one the reference's reader builds"""
+    d, f = case
+    m = gv.Model.from_files(os.path.join(REF_INPUTS, d, "base.vxa"), os.path.join(REF_INPUTS, d, f))
+    _, md, _ = O.run_reference(m.merged_vxa(), 0, want_model=True)
+    assert_model_matches(m, md)
+    assert m.num_voxels >= 34
+
+
 def test_vxd_replaces_subtree_and_keeps_the_rest():
     base = W.xenobot_base_vxa()
     m0 = gv.Model.from_vxa(base)
