@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvx3b200.so")
+LIB_PATH = os.environ.get("VX3B_LIB") or os.path.join(_HERE, "libvx3b200.so")  # VX3B_LIB: an experimental build (__graft_entry__.py VX3B_VARIANT)
 
 MAX_TOKENS = 64
 FP32, FP64 = 32, 64

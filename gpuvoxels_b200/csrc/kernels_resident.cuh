@@ -110,6 +110,22 @@ struct ResidentShared { // block-wide scalars
 #ifndef RES_MAXT
 #define RES_MAXT 512 // threads of one SM's k_resident CTAs together (register budget: 65536 / RES_MAXT per thread)
 #endif
+// -DRES_PROFILE: per-phase clock64() accounting of k_resident (warp-cycles, summed over all warps and steps; scripts/gpu_resident_phases.py).
+// 0 rebuild (with its barriers), 1 link pass, 2 narrow phase, 3 wait at the barrier after them, 4 voxel pass, 5 bookkeeping + barrier(s)
+// at the end of the step, 8 warp-steps counted, 9 rebuilds (warp-rebuilds)
+#ifdef RES_PROFILE
+static __device__ unsigned long long g_resProf[16];
+#define RP_DECL long long rp[6] = {0, 0, 0, 0, 0, 0}, rpT = clock64(), rpSteps = 0, rpRebuilds = 0;
+#define RP(i)                                                                                                                   \
+    {                                                                                                                           \
+        const long long rpN = clock64();                                                                                        \
+        rp[i] += rpN - rpT;                                                                                                     \
+        rpT = rpN;                                                                                                              \
+    }
+#else
+#define RP_DECL
+#define RP(i)
+#endif
 VXD uint32_t cell_hash(uint32_t key, int log2H) { return (key * 2654435761u) >> (32 - log2H); }
 
 // worldList: the worlds of one size class (every CTA lays its shared memory out for its own world's counts; the class only
@@ -286,6 +302,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
     bool running = true;
     bool rebuild = true; // contact candidate lists must be rebuilt this step (uniform over the block)
     const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    RP_DECL
 
     while (running) {
         // ---- contact step 1 (only when the candidate lists are stale): grid + lists from the positions of the step start.
@@ -523,7 +540,11 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 narrow(true);
                 __syncthreads();
             }
+#ifdef RES_PROFILE
+            rpRebuilds++;
+#endif
         }
+        RP(0)
         // ---- phase A: link pass, and the contact narrow phase over the candidate lists (independent of each other) ------------
         for (int l = tid; l < nl; l += nt) {
             const int a = sLends[2 * l], b = sLends[2 * l + 1];
@@ -593,6 +614,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
             if (f.strain > 100.0f)
                 sh.diverged = 1;
         }
+        RP(1)
         if (collide && !overflow) {
             // common displacement since the rebuild (that of one reference voxel): the rebuild test in the voxel pass removes it,
             // because only RELATIVE motion of two voxels can bring an unlisted pair inside the watch distance
@@ -607,7 +629,9 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
         int32_t *hitSlot = (step & 1) ? &sh.hits1 : &sh.hits, *otherSlot = (step & 1) ? &sh.hits : &sh.hits1;
         if (hits)
             atomicAdd(hitSlot, hits);
+        RP(2)
         __syncthreads();
+        RP(3)
         const bool divergedNow = sh.diverged != 0;
         collisionCount += *hitSlot;
         if (tid == 0) {
@@ -715,6 +739,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 }
             }
         }
+        RP(4)
         // ---- end-of-step bookkeeping on the shared-memory copy of the world record.  On ordinary steps the last thread does
         // it right after its own voxels (nothing it needs depends on the other threads); on COM-sampling steps and on
         // divergence it waits for the voxel pass.
@@ -749,12 +774,26 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
         }
         running = sh.running != 0;
         rebuild = sh.rebuild != 0;
+        RP(5)
+#ifdef RES_PROFILE
+        rpSteps++;
+#endif
         step++;
         left--;
         if (!divergedNow)
             t += dt;
     }
 
+#ifdef RES_PROFILE
+    if (lane == 0) {
+        for (int i = 0; i < 6; i++)
+            atomicAdd(&g_resProf[i], (unsigned long long)rp[i]);
+        atomicAdd(&g_resProf[8], (unsigned long long)rpSteps);
+        atomicAdd(&g_resProf[9], (unsigned long long)rpRebuilds);
+        atomicAdd(&g_resProf[10], (unsigned long long)(rpSteps * ((nl + nt - 1) / nt)));  // link rounds
+        atomicAdd(&g_resProf[11], (unsigned long long)(rpSteps * ((nv + nt - 1) / nt)));  // voxel rounds
+    }
+#endif
     // ---- write the world back ------------------------------------------------------------------------------------
     __syncthreads();
     {
