@@ -68,10 +68,14 @@ struct WorldD {
     double tempAmp, tempPeriod, voxSize, maxDistPair;
     // contact broad phase (k_resident): cell edge = largest watch distance of this world + skin
     double invCell, listR2; // 1/edge; edge^2 (a voxel's candidate list holds everything within the edge)
-    double watchR2;         // (largest watch distance)^2 * (1 + 1e-12) when voxel sizes cannot change, else 0
+    double watchR2;         // (1 + 1e-12) * square of an UPPER BOUND of every pair's watch distance (exact when voxel sizes cannot change): quick reject
     float skinHalf2;        // (skin/2)^2: a surface voxel that moved further (relative to the common drift) since the last rebuild forces a new one
     int32_t listCap;        // entries per surface voxel's candidate list
     int32_t gridOff, gridLog2; // global-memory contact grid (kernels_contact.cuh): first bucket and log2(buckets); gridLog2 == 0: none
+    // stop formula of the common shape `t - C` (every shipped experiment): compared directly instead of run through the formula machine
+    int32_t stopIsTimeMinusC, padStop;
+    double stopC;
+    double tempK; // thermal worlds: 2 * 3.1415926f as the reference evaluates it (VX3_VoxelyzeKernel.cu:640), in double
     // dynamic
     double t;
     int64_t step;     // CurStepCount

@@ -97,6 +97,24 @@ struct WorldHost {
 };
 
 static bool formula_empty(const VX3B_Token *t) { return t[0].op == VX3B_MT_END; }
+// Upper bound of 0.625 * (size1 + size2) over every pair of voxels and every temperature the world can reach
+// (VX3_VoxelyzeKernel.cu:660: watchDistance = (baseSizeAverage1 + baseSizeAverage2) * COLLISION_ENVELOPE_RADIUS).  The temperature is
+// TempAmplitude * sin(...) in [-|A|, |A|], clamped to <= 0 unless EnableExpansion (VX3_VoxelyzeKernel.cu:638-647), or the initial one.
+static double max_watch_distance(const VX3B_WorldDesc &d) {
+    double maxSize = 0;
+    const double amp = fabs(d.temp_amplitude), t0 = (double)d.initial_temp;
+    const bool vary = d.vary_temp_enabled && d.temp_period > 0;
+    for (int k = 0; k < d.num_voxel_mats; k++) {
+        const double a = (double)d.voxel_mats[k].alphaCTE;
+        double grow = std::max(0.0, t0 * a);
+        if (vary)
+            grow = std::max(grow, d.enable_expansion ? amp * fabs(a) : std::max(0.0, -amp * a));
+        maxSize = std::max(maxSize, d.voxel_mats[k].nomSize * (1.0 + grow));
+    }
+    if (maxSize == 0)
+        maxSize = d.vox_size;
+    return 1.25 * maxSize * (1.0 + 1e-6);
+}
 
 template <class R> class Engine : public EngineBase {
     using T4 = typename Store<R>::T4;
@@ -284,6 +302,7 @@ template <class R> class Engine : public EngineBase {
         // ---- per-world summary: surface count, feature flags, shared-memory need -> k_resident size class ------------------
         struct Pre {
             int ns = 0, cls = 0, next = 0; // surface voxels, k_resident size class, voxels with boundary conditions
+            bool full = false;             // needs k_resident's FULL instantiation (boundary conditions, force field, failure strain)
             uint32_t flags = 0;
             size_t bytes = 0;
             double invCell = 0, listR2 = 0;
@@ -333,12 +352,13 @@ template <class R> class Engine : public EngineBase {
                           (d.enable_cilia ? WF_CILIA : 0) | (d.enable_expansion ? WF_EXPANSION : 0) | (vx3 ? WF_VX3 : 0) |
                           (hasFF ? WF_FORCE_FIELD : 0) | (!formula_empty(d.stop_condition) ? WF_STOP_FORMULA : 0) |
                           ((vary && maxAlpha != 0) ? WF_THERMAL : 0) | (canFail ? WF_CAN_FAIL : 0);
+                p.full = p.next > 0 || hasFF || canFail;
                 // contact broad-phase cell: >= the largest watch distance 0.625*(size1+size2), sizes at their largest temperature
                 const double skin = contactSkin * d.vox_size;
                 // list capacity: at rest the 12 face diagonals (1.414) enter once skin > 0.16, the 8 body diagonals (1.732) once skin > 0.48
-                const int listCap = contactListCap > 0 ? contactListCap : contactSkin < 0.16 ? 16 : contactSkin < 0.48 ? 24 : 36;
+                const int listCap = contactListCap > 0 ? ((contactListCap + 3) & ~3) : contactSkin < 0.16 ? 16 : contactSkin < 0.48 ? 24 : 36; // multiple of 4
                 listCaps[w] = listCap;
-                double cell = 1.25 * maxSize * (1.0 + (fabs(d.temp_amplitude) + fabs((double)d.initial_temp)) * maxAlpha) * (1.0 + 1e-6) + skin;
+                double cell = max_watch_distance(d) + skin;
                 p.invCell = cell > 0 ? 1.0 / cell : 0.0;
                 p.listR2 = cell * cell;
                 p.skinHalf2 = (float)(0.25 * skin * skin * (1.0 - 1e-2)); // a little early rather than late (float compare)
@@ -556,12 +576,23 @@ template <class R> class Engine : public EngineBase {
                 o.isTarget = m.isTarget;
                 o.isMeasured = m.isMeasured;
             }
-            if (!(pre[w].flags & WF_THERMAL)) { // quick reject of contact candidates: nothing beyond the largest watch distance matters
-                double maxAvg = 0;
-                for (int k = 0; k < d.num_voxel_mats; k++)
-                    maxAvg = std::max(maxAvg, vmats[vmo + k].avgSize0);
-                const double Rw = (maxAvg + maxAvg) * 0.625;
+            { // quick reject of contact candidates: nothing beyond the largest watch distance matters
+                double Rw = max_watch_distance(d);
+                if (!(pre[w].flags & WF_THERMAL)) { // sizes cannot change: the exact largest value
+                    double maxAvg = 0;
+                    for (int k = 0; k < d.num_voxel_mats; k++)
+                        maxAvg = std::max(maxAvg, vmats[vmo + k].avgSize0);
+                    Rw = (maxAvg + maxAvg) * 0.625;
+                }
                 W.watchR2 = Rw * Rw * (1.0 + 1e-12);
+            }
+            {
+                const VX3B_Token *t = d.stop_condition; // <mtSUB><mtVAR>t</mtVAR><mtCONST>C</mtCONST></mtSUB> = CONST C, VAR t, SUB, END
+                const bool tMinusC = t[0].op == VX3B_MT_CONST && t[1].op == VX3B_MT_VAR && t[1].value > 3.5 && t[1].value < 4.5 && t[2].op == VX3B_MT_SUB &&
+                                     t[3].op == VX3B_MT_END;
+                W.stopIsTimeMinusC = tMinusC ? 1 : 0;
+                W.stopC = tMinusC ? t[0].value : 0.0;
+                W.tempK = (double)(2 * 3.1415926f);
             }
             for (int k = 0; k < d.num_link_mats; k++) {
                 const VX3B_LinkMaterial &m = d.link_mats[k];
@@ -1459,13 +1490,15 @@ template <class R> class Engine : public EngineBase {
             tileStream0 = (int)hTiles.size();
         }
         static const int ks[] = {1 + 16, 2 + 16, 3 + 16, 1, 2, 3, 4, 6}; // most expensive worlds are launched first
-        for (int kc : ks) {
+        for (int kcf = 0; kcf < 2 * (int)(sizeof(ks) / sizeof(ks[0])); kcf++) {
+            const int kc = ks[kcf >> 1];
             ResidentClass c;
             const int k = kc & 15;
             c.ctasPerSm = k;
             c.spill = kc >= 16;
+            c.full = (kcf & 1) != 0;
             for (int oi = 0; oi < n; oi++)
-                if (pre[perm[oi]].cls == kc) {
+                if (pre[perm[oi]].cls == kc && pre[perm[oi]].full == c.full) {
                     c.worlds.push_back(perm[oi]);
                     c.smem = std::max(c.smem, pre[perm[oi]].bytes);
                 }
@@ -1478,8 +1511,8 @@ template <class R> class Engine : public EngineBase {
             CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
             if (getenv("VX3B_DEBUG"))
-                fprintf(stderr, "[vx3b] resident class: %d CTA/SM%s, %zu worlds, %d threads, %zu B shared memory\n", k, c.spill ? " (spill)" : "",
-                        c.worlds.size(), c.threads, c.smem);
+                fprintf(stderr, "[vx3b] resident class: %d CTA/SM%s%s, %zu worlds, %d threads, %zu B shared memory\n", k, c.spill ? " (spill)" : "",
+                        c.full ? " (full)" : "", c.worlds.size(), c.threads, c.smem);
             classes.push_back(std::move(c));
         }
         if (getenv("VX3B_DEBUG"))

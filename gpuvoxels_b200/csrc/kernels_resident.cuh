@@ -24,7 +24,7 @@ namespace vx3b {
 // shared-memory layout for capacities (capV, capL, capS); every array is 16-byte aligned
 template <class R> struct ResidentLayout {
     size_t world, vmats, lmats;
-    size_t pos, orient, linMom, angMom, temp, vflags, vmat, vlinks, lat, phase, cilia, vext, vsurfslot;
+    size_t pos, orient, linMom, angMom, temp, vflags, vmat, vlinks, lat, phase, bsa, cilia, vext, vsurfslot;
     size_t lpos2, la1, la2, lflags, lmaxs, lends, lmeta, lfN, lfP, lmN, lmP;
     size_t surf, contactF, skey, sorted, cnt, rec4, rec2, nbr, nbrCnt, ref;
     size_t total;
@@ -52,7 +52,10 @@ template <class R> struct ResidentLayout {
         vmat = take(capV);
         vlinks = take(sizeof(uint16_t) * 6 * capV);
         lat = take(sizeof(short4) * capV);
-        phase = take((wflags & WF_THERMAL) ? sizeof(double) * capV : 0);
+        // thermal worlds: per voxel the phase offset (validation build) or sin / cos of K * phase (float build: voxel_temperature_split),
+        // and the cached baseSizeAverage at the voxel's current temperature
+        phase = take((wflags & WF_THERMAL) ? sizeof(double) * (sizeof(R) == 4 ? 2 : 1) * capV : 0);
+        bsa = take((wflags & WF_THERMAL) ? sizeof(double) * capV : 0);
         cilia = take((wflags & WF_CILIA) ? sizeof(float) * 3 * capV : 0);
         vext = take(sizeof(int32_t) * capV);
         vsurfslot = take(sizeof(uint16_t) * capV);
@@ -97,6 +100,7 @@ template <class R> struct ResidentLayout {
 };
 
 struct ResidentShared { // block-wide scalars
+    double sinA, cosA; // float build, thermal worlds: sin / cos of K * (t + dt) / period of the current step (thread 0, before the link pass)
     int32_t diverged, running, rebuild, overflow;
     int32_t narrowNext, padN[3]; // next unclaimed surface voxel of the narrow phase (reset during the voxel pass)
     // target-hit counter of even / odd steps, each in its own 16-byte granule: the compiler fetches neighbouring scalars with one
@@ -113,9 +117,24 @@ struct ResidentShared { // block-wide scalars
 // -DRES_PROFILE: per-phase clock64() accounting of k_resident (warp-cycles, summed over all warps and steps; scripts/gpu_resident_phases.py).
 // 0 rebuild (with its barriers), 1 link pass, 2 narrow phase, 3 wait at the barrier after them, 4 voxel pass, 5 bookkeeping + barrier(s)
 // at the end of the step, 8 warp-steps counted, 9 rebuilds (warp-rebuilds)
+// -DRES_MARKERS: pmevent instructions (PMTRIG in SASS, free at run time) at the phase boundaries, so that the per-instruction
+// counters of an `ncu --import-source` capture can be summed per phase by address range (scripts/ncu_phases.py)
+#ifdef RES_MARKERS
+#define RM(n) asm volatile("pmevent " #n ";");
+#else
+#define RM(n)
+#endif
 #ifdef RES_PROFILE
 static __device__ unsigned long long g_resProf[16];
-#define RP_DECL long long rp[6] = {0, 0, 0, 0, 0, 0}, rpT = clock64(), rpSteps = 0, rpRebuilds = 0;
+#define RP_DECL long long rp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, rpT = clock64(), rpT2 = 0, rpSteps = 0, rpRebuilds = 0;
+// sub-phases of the rebuild (slots 6, 7, 12, 13, 14: keys + counts, scan, scatter + bucket sort, records, lists), timed separately
+#define RP2_START rpT2 = clock64();
+#define RP2(i)                                                                                                                  \
+    {                                                                                                                           \
+        const long long rpN = clock64();                                                                                        \
+        rp[i] += rpN - rpT2;                                                                                                    \
+        rpT2 = rpN;                                                                                                             \
+    }
 #define RP(i)                                                                                                                   \
     {                                                                                                                           \
         const long long rpN = clock64();                                                                                        \
@@ -125,12 +144,17 @@ static __device__ unsigned long long g_resProf[16];
 #else
 #define RP_DECL
 #define RP(i)
+#define RP2_START
+#define RP2(i)
 #endif
 VXD uint32_t cell_hash(uint32_t key, int log2H) { return (key * 2654435761u) >> (32 - log2H); }
 
 // worldList: the worlds of one size class (every CTA lays its shared memory out for its own world's counts; the class only
 // fixes the dynamic shared-memory size, i.e. how many CTAs share an SM).
-template <class R, bool SPILL>
+// FULL = false: no world of the launch has boundary conditions, a force field or a failure strain - their code (the boundary-condition
+// branches of the voxel update, three formula evaluations per voxel, the failure tests of the link) is compiled away, which keeps
+// the generation kernel's hot loops small (instruction cache) and its register budget for the arithmetic.
+template <class R, bool SPILL, bool FULL>
 __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int32_t *worldList, long long maxSteps, int useStop, int recordPairs) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ ResidentShared sh;
@@ -152,6 +176,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
     uint16_t *sVlinks = (uint16_t *)(smem + L.vlinks);
     short4 *sLat = (short4 *)(smem + L.lat);
     double *sPhase = (double *)(smem + L.phase);
+    double *sBsa = (double *)(smem + L.bsa);
     float *sCilia = (float *)(smem + L.cilia);
     int32_t *sVext = (int32_t *)(smem + L.vext);
     uint16_t *sVsurf = (uint16_t *)(smem + L.vsurfslot);
@@ -192,7 +217,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
     const uint32_t wflags = W.flags;
     const bool vx3 = wflags & WF_VX3, floorOn = wflags & WF_FLOOR, collide = (wflags & WF_COLLISION) && ns > 1;
     const bool ciliaOn = (wflags & WF_CILIA) && A.baseCilia, varyTemp = (wflags & WF_THERMAL) && W.tempPeriod > 0;
-    const bool canFail = wflags & WF_CAN_FAIL, thermal = wflags & WF_THERMAL;
+    const bool canFail = FULL && (wflags & WF_CAN_FAIL), thermal = wflags & WF_THERMAL;
     const float dt = W.dt;
     const float invDt = 1.0f / dt;
     const double voxSize = W.voxSize, tempAmp = W.tempAmp, tempPeriod = W.tempPeriod, invCell = W.invCell, listR2 = W.listR2;
@@ -235,8 +260,17 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
             sVlinks[6 * v + k] = l < 0 ? (uint16_t)0xffff : (uint16_t)(l - loff);
         }
         sLat[v] = A.lat[g];
-        if (varyTemp)
-            sPhase[v] = A.phase ? A.phase[g] : 0.0;
+        if (thermal) {
+            const double ph = (varyTemp && A.phase) ? A.phase[g] : 0.0;
+            if constexpr (sizeof(R) == 4) {
+                double sn, cs;
+                sincos(W.tempK * ph, &sn, &cs);
+                sPhase[2 * v] = sn;
+                sPhase[2 * v + 1] = cs;
+            } else
+                sPhase[v] = ph;
+            sBsa[v] = base_size_average(A.vmats[A.vmat[g]], temp);
+        }
         if (ciliaOn) {
             D4 b = A.baseCilia[g];
             sCilia[3 * v] = (float)b.x;
@@ -332,22 +366,22 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 const DVoxMat &m1 = vmats[sVmat[v1]];
                 const V3<double> p1{sPos[3 * v1], sPos[3 * v1 + 1], sPos[3 * v1 + 2]};
                 const V3<R> l1{sLin[3 * v1], sLin[3 * v1 + 1], sLin[3 * v1 + 2]};
-                const float t1 = thermal ? sTemp[v1] : 0.0f;
+                const double avg1 = thermal ? sBsa[v1] : m1.avgSize0;
                 V3<R> acc{R(0), R(0), R(0)};
-                auto pair = [&](int j) {
-                    const int v2 = sSurf[j];
+                // candidate = VOXEL index (the surface list ascends in voxel index, so "the later surface voxel" = the larger index)
+                auto pair = [&](int v2) {
                     const V3<double> p2{sPos[3 * v2], sPos[3 * v2 + 1], sPos[3 * v2 + 2]};
-                    if (watchR2 > 0) { // all voxel sizes of this world are constant: reject on the squared distance alone
+                    { // nothing beyond the world's largest possible watch distance matters: reject on the squared distance alone
                         const double ex = p1.x - p2.x, ey = p1.y - p2.y, ez = p1.z - p2.z;
                         if (ex * ex + ey * ey + ez * ez > watchR2)
                             return;
                     }
                     const DVoxMat &m2 = vmats[sVmat[v2]];
                     const V3<R> l2{sLin[3 * v2], sLin[3 * v2 + 1], sLin[3 * v2 + 2]};
-                    const float t2 = thermal ? sTemp[v2] : 0.0f;
+                    const double avg2 = thermal ? sBsa[v2] : m2.avgSize0;
                     V3<R> f;
-                    if (i > j) {
-                        if (contact_pair<R>(m1, t1, p1, l1, m2, t2, p2, l2, f)) {
+                    if (v1 > v2) {
+                        if (contact_pair_sized<R>(m1, avg1, p1, l1, m2, avg2, p2, l2, f)) {
                             acc = acc + f;
                             if ((m1.isTarget != 0) != (m2.isTarget != 0))
                                 hits++;
@@ -357,7 +391,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                                     A.pairBuf[slot] = make_int4(w, v1, v2, 0);
                             }
                         }
-                    } else if (contact_pair<R>(m2, t2, p2, l2, m1, t1, p1, l1, f))
+                    } else if (contact_pair_sized<R>(m2, avg2, p2, l2, m1, avg1, p1, l1, f))
                         acc = acc - f;
                 };
                 if (!direct) {
@@ -381,7 +415,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                             const short4 c2 = sLat[v2];
                             if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1 || (m1.fixed && vmats[sVmat[v2]].fixed))
                                 continue;
-                            pair(j);
+                            pair(v2);
                         }
                     }
                 }
@@ -390,7 +424,9 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 sCF[3 * i + 2] = acc.z;
             }
         };
+        RM(1)
         if (collide && rebuild) {
+            RP2_START
             for (int h = tid; h < H; h += nt)
                 sCnt[h] = 0;
             if (tid == 0)
@@ -409,6 +445,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 atomicAdd(&sCnt[cell_hash(key, log2H)], 1);
             }
             __syncthreads();
+            RP2(6)
             // ---- B1: exclusive scan of the bucket counts -------------------------------------------------------------
             const int per = (H + nt - 1) / nt, b0 = tid * per;
             int sum = 0;
@@ -442,6 +479,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                     offset += c;
                 }
             __syncthreads();
+            RP2(7)
             // ---- B2: scatter (after it sCnt[h] = END of bucket h; its start is sCnt[h-1]) --------------------------------
             for (int i = tid; i < ns; i += nt)
                 sSorted[atomicAdd(&sCnt[cell_hash(sKey[i], log2H)], 1)] = (uint16_t)i;
@@ -460,6 +498,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 }
             }
             __syncthreads();
+            RP2(12)
             // ---- B3b: cell-sorted records.  The list build below tests ~100 voxels per surface voxel; chasing sorted -> key ->
             // surface -> lattice -> 3 doubles for each of them was a chain of five dependent loads.  One record per sorted slot:
             // {cell key, surface index} (8 B) and {position relative to the world's first surface voxel as float3, lattice index
@@ -475,9 +514,10 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 const uint32_t pk = (uint32_t)(c.x & 1023) | ((uint32_t)(c.y & 1023) << 10) | ((uint32_t)(c.z & 1023) << 20) |
                                     (vmats[sVmat[v]].fixed != 0 ? 0x40000000u : 0u);
                 sRec4[p] = make_float4((float)(sPos[3 * v] - ox), (float)(sPos[3 * v + 1] - oy), (float)(sPos[3 * v + 2] - oz), __uint_as_float(pk));
-                sRec2[p] = make_uint2(sKey[j], (uint32_t)j);
+                sRec2[p] = make_uint2(sKey[j], (uint32_t)j | ((uint32_t)v << 16)); // surface index | voxel index << 16
             }
             __syncthreads();
+            RP2(13)
             // ---- B4: candidate lists, one thread per surface voxel.  A flat loop that either tests the next voxel of the current
             // cell or moves on to the next of the 27 cells, so the lanes of a warp stay busy although their cells hold different
             // numbers of voxels (a nested cell/voxel loop costs the warp the SUM over cells of the longest bucket).
@@ -496,7 +536,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 while (true) {
                     if (p < end) {
                         const uint2 kj = sRec2[p];
-                        if (kj.x == k2 && (int)kj.y != i) {
+                        if (kj.x == k2 && (int)(kj.y & 0xffffu) != i) {
                             const float4 r = sRec4[p];
                             const float dx = r.x - x1, dy = r.y - y1, dz = r.z - z1;
                             const uint32_t pk2 = __float_as_uint(r.w);
@@ -506,7 +546,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                             const int dl = abs(pk1 - (int)(pk2 & 0x3fffffffu));
                             if (dx * dx + dy * dy + dz * dz <= listR2f && dl != 1 && dl != 1024 && dl != 1048576 && !(fixed1 & pk2)) {
                                 if (count < RES_K)
-                                    sNbr[i * RES_K + count] = (uint16_t)kj.y;
+                                    sNbr[i * RES_K + count] = (uint16_t)(kj.y >> 16); // the candidate's voxel index
                                 count++;
                             }
                         }
@@ -529,6 +569,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 sRef[3 * i + 2] = (float)z1d;
             }
             __syncthreads();
+            RP2(14)
             overflow = sh.overflow != 0;
             if (tid == 0) {
                 W.contactRebuilds++;
@@ -545,6 +586,16 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
 #endif
         }
         RP(0)
+        RM(2)
+        if constexpr (sizeof(R) == 4) {
+            // the sine of this step's temperature update (t + dt), taken once: read by the voxel pass, after the barrier below
+            if (varyTemp && tid == 0) {
+                double sn, cs;
+                sincos(W.tempK * ((t + (double)dt) / tempPeriod), &sn, &cs);
+                sh.sinA = sn;
+                sh.cosA = cs;
+            }
+        }
         // ---- phase A: link pass, and the contact narrow phase over the candidate lists (independent of each other) ------------
         for (int l = tid; l < nl; l += nt) {
             const int a = sLends[2 * l], b = sLends[2 * l + 1];
@@ -615,6 +666,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                 sh.diverged = 1;
         }
         RP(1)
+        RM(3)
         if (collide && !overflow) {
             // common displacement since the rebuild (that of one reference voxel): the rebuild test in the voxel pass removes it,
             // because only RELATIVE motion of two voxels can bring an unlisted pair inside the watch distance
@@ -630,6 +682,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
         if (hits)
             atomicAdd(hitSlot, hits);
         RP(2)
+        RM(4)
         __syncthreads();
         RP(3)
         const bool divergedNow = sh.diverged != 0;
@@ -640,6 +693,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
         }
         const bool sampling = vx3 && cycle > 0 && ((step + 1) % cycle == 0);
         // ---- phase F: voxel pass (+ reset of the grid counters and, on ordinary steps, the world bookkeeping) ---------------
+        RM(5)
         if (!divergedNow) {
             double cx = 0, cy = 0, cz = 0, cm = 0;
             for (int v = tid; v < nv; v += nt) {
@@ -651,6 +705,10 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                     s.linMom = {sLin[3 * v], sLin[3 * v + 1], sLin[3 * v + 2]};
                     s.angMom = {sAng[3 * v], sAng[3 * v + 1], sAng[3 * v + 2]};
                     s.temp = thermal ? sTemp[v] : 0.0f;
+                    if (thermal) { // floor offset from the cached average size (valid for s.temp): no double division per floor test
+                        s.haveFloorOffset = true;
+                        s.floorOffset = sBsa[v] / 2 - m.nomSize / 2;
+                    }
                     s.flags = sVflags[v];
                     V3<R> F{R(0), R(0), R(0)}, M{R(0), R(0), R(0)};
 #pragma unroll
@@ -674,25 +732,33 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
                     wp.dt = dt;
                     wp.floorEnabled = floorOn;
                     wp.vx3 = vx3;
-                    wp.forceField = (wflags & WF_FORCE_FIELD) ? Wg.ff : nullptr; // (not part of the shared-memory copy)
+                    wp.forceField = (FULL && (wflags & WF_FORCE_FIELD)) ? Wg.ff : nullptr; // (not part of the shared-memory copy)
                     wp.fv = FormulaVars{0, 0, 0, (double)collisionCount, t, W.recentAngle, W.closeness, W.numClosePairs, nv};
-                    VoxExt ext;
-                    const VoxExt *pe = nullptr;
-                    const int ei = sVext[v];
-                    const short4 lat = sLat[v];
-                    V3<double> nominal{lat.x * m.nomSize, lat.y * m.nomSize, lat.z * m.nomSize};
-                    if (ei >= 0) {
-                        const DExt &x = A.ext[ei];
-                        ext.dof = x.dof;
-                        ext.force = {x.force[0], x.force[1], x.force[2]};
-                        ext.moment = {x.moment[0], x.moment[1], x.moment[2]};
-                        ext.translation = {x.translation[0], x.translation[1], x.translation[2]};
-                        ext.rotationQ = {x.rotQ[0], x.rotQ[1], x.rotQ[2], x.rotQ[3]};
-                        pe = &ext;
+                    if constexpr (FULL) {
+                        VoxExt ext;
+                        const VoxExt *pe = nullptr;
+                        const int ei = sVext[v];
+                        const short4 lat = sLat[v];
+                        V3<double> nominal{lat.x * m.nomSize, lat.y * m.nomSize, lat.z * m.nomSize};
+                        if (ei >= 0) {
+                            const DExt &x = A.ext[ei];
+                            ext.dof = x.dof;
+                            ext.force = {x.force[0], x.force[1], x.force[2]};
+                            ext.moment = {x.moment[0], x.moment[1], x.moment[2]};
+                            ext.translation = {x.translation[0], x.translation[1], x.translation[2]};
+                            ext.rotationQ = {x.rotQ[0], x.rotQ[1], x.rotQ[2], x.rotQ[3]};
+                            pe = &ext;
+                        }
+                        voxel_update<R>(m, wp, pe, nominal, s, F, M, contact, cilia);
+                    } else
+                        voxel_update<R>(m, wp, nullptr, V3<double>{0, 0, 0}, s, F, M, contact, cilia);
+                    if (varyTemp && m.alphaCTE != 0.0f) { // temperature is only observable through alphaCTE
+                        if constexpr (sizeof(R) == 4)
+                            s.temp = voxel_temperature_split(tempAmp, sh.sinA, sh.cosA, sPhase[2 * v], sPhase[2 * v + 1], (wflags & WF_EXPANSION) != 0);
+                        else
+                            s.temp = voxel_temperature(tempAmp, tempPeriod, sPhase[v], t + (double)dt, (wflags & WF_EXPANSION) != 0);
+                        sBsa[v] = base_size_average_expr(base_size_expr(m.nomSize, m.alphaCTE, s.temp)); // for the next step's floor and contact tests
                     }
-                    voxel_update<R>(m, wp, pe, nominal, s, F, M, contact, cilia);
-                    if (varyTemp && m.alphaCTE != 0.0f) // temperature is only observable through alphaCTE
-                        s.temp = voxel_temperature(tempAmp, tempPeriod, sPhase[v], t + (double)dt, (wflags & WF_EXPANSION) != 0);
                     sPos[3 * v] = s.pos.x;
                     sPos[3 * v + 1] = s.pos.y;
                     sPos[3 * v + 2] = s.pos.z;
@@ -740,6 +806,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
             }
         }
         RP(4)
+        RM(6)
         // ---- end-of-step bookkeeping on the shared-memory copy of the world record.  On ordinary steps the last thread does
         // it right after its own voxels (nothing it needs depends on the other threads); on COM-sampling steps and on
         // divergence it waits for the voxel pass.
@@ -775,6 +842,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
         running = sh.running != 0;
         rebuild = sh.rebuild != 0;
         RP(5)
+        RM(7)
 #ifdef RES_PROFILE
         rpSteps++;
 #endif
@@ -786,8 +854,9 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
 
 #ifdef RES_PROFILE
     if (lane == 0) {
-        for (int i = 0; i < 6; i++)
-            atomicAdd(&g_resProf[i], (unsigned long long)rp[i]);
+        for (int i = 0; i < 16; i++)
+            if (i < 8 || i > 11)
+                atomicAdd(&g_resProf[i], (unsigned long long)rp[i]);
         atomicAdd(&g_resProf[8], (unsigned long long)rpSteps);
         atomicAdd(&g_resProf[9], (unsigned long long)rpRebuilds);
         atomicAdd(&g_resProf[10], (unsigned long long)(rpSteps * ((nl + nt - 1) / nt)));  // link rounds
@@ -839,6 +908,7 @@ __global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int
 struct ResidentClass {
     int ctasPerSm = 1, threads = 512;
     bool spill = false; // per-link force arrays in global memory (worlds too big for shared memory otherwise)
+    bool full = true;   // some world has boundary conditions, a force field or a failure strain (k_resident<.., FULL>)
     size_t smem = 0; // dynamic shared memory of the launch = largest member
     std::vector<int32_t> worlds;
     int32_t *dList = nullptr;
@@ -869,7 +939,7 @@ template <class R>
 int resident_launch(const Arrays<R> &A, const ResidentClass &c, int64_t maxSteps, int useStop, int recordPairs) {
     if (c.worlds.empty())
         return VX3B_OK;
-    auto kernel = c.spill ? k_resident<R, true> : k_resident<R, false>;
+    auto kernel = c.spill ? (c.full ? k_resident<R, true, true> : k_resident<R, true, false>) : (c.full ? k_resident<R, false, true> : k_resident<R, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e == cudaSuccess) {
         kernel<<<(unsigned)c.worlds.size(), c.threads, c.smem, c.stream>>>(A, c.dList, (long long)maxSteps, useStop, recordPairs);

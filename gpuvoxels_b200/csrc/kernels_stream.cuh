@@ -357,6 +357,13 @@ VXD void finish_com(WorldD &W) {
 VXD FormulaVars world_vars(const WorldD &W, double x, double y, double z) {
     return FormulaVars{x, y, z, (double)W.collisionCount, W.t, W.recentAngle, W.closeness, W.numClosePairs, W.nv};
 }
+// StopConditionMet (VX3_VoxelyzeKernel.cu:160-166): formula > 0.  `t - C` is evaluated directly (the same subtraction the formula
+// machine would do, Utils/VX3_MathTree.h:123-126) - every world evaluates this every step.
+VXD bool stop_condition_met(const WorldD &W) {
+    if (W.stopIsTimeMinusC)
+        return W.t - W.stopC > 0;
+    return eval_formula(W.stop, world_vars(W, W.com[0], W.com[1], W.com[2])) > 0;
+}
 
 // mode 0: after upload (initial COM).  mode 1: end of a run (final COM, fitness, total distance).
 template <class R> __global__ void k_world_finish(Arrays<R> A, int mode) {
@@ -391,7 +398,7 @@ template <class R> __global__ void k_world_begin(Arrays<R> A, long long maxSteps
     W.flags = fl;
     W.runSteps = maxSteps;
     W.active = (!W.diverged && !W.stopped && maxSteps > 0 && W.nv > 0) ? 1 : 0;
-    if (W.active && useStop && (W.flags & WF_STOP_FORMULA) && eval_formula(W.stop, world_vars(W, W.com[0], W.com[1], W.com[2])) > 0) {
+    if (W.active && useStop && (W.flags & WF_STOP_FORMULA) && stop_condition_met(W)) {
         W.stopped = 1;
         W.active = 0;
     }
@@ -460,7 +467,7 @@ template <class R, bool TARGETS = true> __device__ void world_end_of_step(const 
     W.runSteps--;
     if (W.runSteps <= 0)
         W.active = 0;
-    else if (useStop && (W.flags & WF_STOP_FORMULA) && eval_formula(W.stop, world_vars(W, W.com[0], W.com[1], W.com[2])) > 0) {
+    else if (useStop && (W.flags & WF_STOP_FORMULA) && stop_condition_met(W)) {
         W.stopped = 1;
         W.active = 0;
     }

@@ -461,6 +461,10 @@ template <class R> struct VoxState {
     V3<R> linMom, angMom;
     uint32_t flags;
     float temp;
+    // baseSizeAverage()/2 - nominalSize()/2 at `temp` when the caller keeps it per voxel (k_resident caches baseSizeAverage of
+    // thermally actuated voxels: it costs a double division, and the floor and every contact candidate need it)
+    bool haveFloorOffset = false;
+    double floorOffset;
 };
 struct VoxExt { // boundary conditions of one voxel (CVX_External)
     uint32_t dof;
@@ -473,6 +477,11 @@ VXD float floor_penetration(const DVoxMat &m, float temp, double z) { // VX3/VX3
     if (m.sizeIsConst)
         return (float)(m.floorOffset0 - z);
     return (float)(base_size_average(m, temp) / 2 - m.nomSize / 2 - z);
+}
+template <class R> VXD float floor_penetration(const DVoxMat &m, const VoxState<R> &s, double z) {
+    if (s.haveFloorOffset) // given by the caller (same expression, evaluated once per temperature change)
+        return (float)(s.floorOffset - z);
+    return floor_penetration(m, s.temp, z);
 }
 
 // Fsum/Msum: sums of the ≤6 link forces/moments in the voxel's local frame; contact/cilia in the global frame.
@@ -510,7 +519,7 @@ VXD bool voxel_translate(const DVoxMat &m, const WorldStepParams &wp, const VoxE
     bool staticFric = s.flags & VF_STATIC_FRICTION;
     bool onFloor = false; // floor enabled and penetrating at the start of the step
     if (wp.floorEnabled) {
-        float pen = floor_penetration(m, s.temp, s.pos.z);
+        float pen = floor_penetration(m, s, s.pos.z);
         onFloor = pen >= 0;
         if (pen >= 0) {
             V3<R> vel = s.linMom * (R)m.massInverse;
@@ -569,6 +578,9 @@ template <class R, bool PLAIN = false> VXD void voxel_rotate(const DVoxMat &m, c
 VXD bool voxel_zero_angmom(const DVoxMat &m, const WorldStepParams &wp, bool staticFric, float temp, double newZ) {
     return wp.vx3 && wp.floorEnabled && staticFric && floor_penetration(m, temp, newZ) >= 0;
 }
+template <class R> VXD bool voxel_zero_angmom(const DVoxMat &m, const WorldStepParams &wp, bool staticFric, const VoxState<R> &s) {
+    return wp.vx3 && wp.floorEnabled && staticFric && floor_penetration(m, s, s.pos.z) >= 0;
+}
 template <class R, bool PLAIN = false>
 VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt *ext, V3<double> nominalPos, VoxState<R> &s, V3<R> Fsum, V3<R> Msum,
                       V3<R> contact, V3<R> cilia) {
@@ -619,7 +631,7 @@ VXD void voxel_update(const DVoxMat &m, const WorldStepParams &wp, const VoxExt 
             }
         }
     }
-    if (voxel_zero_angmom(m, wp, staticFric, s.temp, s.pos.z))
+    if (voxel_zero_angmom(m, wp, staticFric, s))
         s.angMom = V3<R>{R(0), R(0), R(0)};
     s.flags = staticFric ? VF_STATIC_FRICTION : 0;
 }
@@ -632,14 +644,25 @@ VXD float voxel_temperature(double amplitude, double period, double phase, doubl
     return (float)T;
 }
 
+// The same temperature from per-voxel sin / cos of K*phase and per-step sin / cos of K*t/period (K = 2 * 3.1415926f): the float
+// build's form in k_resident, where one thread takes the sine of the step and every voxel pays four multiply-adds instead of a
+// double-precision sin() of its own.  Agrees with the expression above to ~1e-14 of the amplitude before the cast to float.
+VXD float voxel_temperature_split(double amplitude, double sinA, double cosA, double sinB, double cosB, int enableExpansion) {
+    double T = amplitude * (sinA * cosB + cosA * sinB);
+    if (!enableExpansion && T > 0)
+        T = 0;
+    return (float)T;
+}
+
 // Contact between two surface voxels (VX3/VX3_VoxelyzeKernel.cu:682-727, VX3/VX3_Collision.cu:3-31).
 // Returns true when (1,2) is a watched pair (inside the envelope on every axis and in distance); `force` is the force
 // the reference adds to voxel 1's contactForce (voxel 2 gets the negative).  The caller has already excluded linked
 // voxels and pairs whose materials are both `fixed`.
+// avg1 / avg2: baseSizeAverage() of the two voxels at their current temperatures
 template <class R>
-VXD bool contact_pair(const DVoxMat &m1, float temp1, V3<double> p1, V3<R> linMom1, const DVoxMat &m2, float temp2, V3<double> p2,
-                      V3<R> linMom2, V3<R> &force) {
-    double Rw = (base_size_average(m1, temp1) + base_size_average(m2, temp2)) * 0.625;
+VXD bool contact_pair_sized(const DVoxMat &m1, double avg1, V3<double> p1, V3<R> linMom1, const DVoxMat &m2, double avg2, V3<double> p2, V3<R> linMom2,
+                            V3<R> &force) {
+    double Rw = (avg1 + avg2) * 0.625;
     double dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
     force = V3<R>{R(0), R(0), R(0)};
     double d2 = dx * dx + dy * dy + dz * dz;
@@ -660,6 +683,11 @@ VXD bool contact_pair(const DVoxMat &m1, float temp1, V3<double> p1, V3<R> linMo
         force = unit * ((R)stiff * (R)relDist + (R)damp * relVel);
     }
     return true;
+}
+template <class R>
+VXD bool contact_pair(const DVoxMat &m1, float temp1, V3<double> p1, V3<R> linMom1, const DVoxMat &m2, float temp2, V3<double> p2,
+                      V3<R> linMom2, V3<R> &force) {
+    return contact_pair_sized<R>(m1, base_size_average(m1, temp1), p1, linMom1, m2, base_size_average(m2, temp2), p2, linMom2, force);
 }
 
 } // namespace vx3b

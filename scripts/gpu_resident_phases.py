@@ -33,3 +33,6 @@ print(f"link rounds per step {v[10] / max(v[8], 1):.2f}, voxel rounds per step {
 for i, nm in enumerate(names):
     print(f"  {nm:28s} {100 * v[i] / tot:5.1f} %   {v[i] / max(v[8], 1):8.0f} cycles per warp-step")
 print(f"  total {tot / max(v[8], 1):.0f} cycles per warp-step")
+sub = {6: "keys + bucket counts", 7: "scan", 12: "scatter + bucket sort", 13: "cell-sorted records", 14: "candidate lists"}
+for i, nm in sub.items():
+    print(f"  rebuild / {nm:24s} {100 * v[i] / max(v[0], 1):5.1f} % of the rebuild   {v[i] / max(v[9], 1):8.0f} cycles per warp-rebuild")
