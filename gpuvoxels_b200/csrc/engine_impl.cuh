@@ -1505,7 +1505,8 @@ template <class R> class Engine : public EngineBase {
             if (c.worlds.empty())
                 continue;
             // registers cap the SM at 512 threads of this kernel (__launch_bounds__(512, 1) -> 128 registers/thread)
-            c.threads = residentThreads > 0 ? std::max(32, std::min(RES_MAXT, (residentThreads + 31) / 32 * 32)) : std::max(128, (RES_MAXT / k) / 32 * 32);
+            const int maxT = c.full ? res_maxt<R, true>() : res_maxt<R, false>();
+            c.threads = residentThreads > 0 ? std::max(32, std::min(maxT, (residentThreads + 31) / 32 * 32)) : std::max(128, (maxT / k) / 32 * 32);
             if ((rc = dalloc(&c.dList, c.worlds.size(), c.worlds.data())) != VX3B_OK)
                 return rc;
             CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));

@@ -111,9 +111,17 @@ struct ResidentShared { // block-wide scalars
     double com[4];
 };
 
+// Threads of one SM's k_resident CTAs together (register budget: 65536 / threads per thread).  The lean float instantiation needs 104
+// registers when left alone; measured on the 1,024-world generation (profiles/r02i): 512 threads 5.59e9 voxel-steps/s, 608 5.75e9,
+// 768 (80 registers, 88 bytes of spills) 6.08e9, 896 5.95e9, 1,024 (64 registers) 5.66e9.  The full and the fp64 instantiations
+// want 128 and more and stay at 512.
 #ifndef RES_MAXT
-#define RES_MAXT 512 // threads of one SM's k_resident CTAs together (register budget: 65536 / RES_MAXT per thread)
+#define RES_MAXT 512
 #endif
+#ifndef RES_MAXT_LEAN
+#define RES_MAXT_LEAN 768
+#endif
+template <class R, bool FULL> constexpr int res_maxt() { return (sizeof(R) == 4 && !FULL) ? RES_MAXT_LEAN : RES_MAXT; }
 // -DRES_PROFILE: per-phase clock64() accounting of k_resident (warp-cycles, summed over all warps and steps; scripts/gpu_resident_phases.py).
 // 0 rebuild (with its barriers), 1 link pass, 2 narrow phase, 3 wait at the barrier after them, 4 voxel pass, 5 bookkeeping + barrier(s)
 // at the end of the step, 8 warp-steps counted, 9 rebuilds (warp-rebuilds)
@@ -155,7 +163,7 @@ VXD uint32_t cell_hash(uint32_t key, int log2H) { return (key * 2654435761u) >> 
 // branches of the voxel update, three formula evaluations per voxel, the failure tests of the link) is compiled away, which keeps
 // the generation kernel's hot loops small (instruction cache) and its register budget for the arithmetic.
 template <class R, bool SPILL, bool FULL>
-__global__ void __launch_bounds__(RES_MAXT, 1) k_resident(Arrays<R> A, const int32_t *worldList, long long maxSteps, int useStop, int recordPairs) {
+__global__ void __launch_bounds__((res_maxt<R, FULL>()), 1) k_resident(Arrays<R> A, const int32_t *worldList, long long maxSteps, int useStop, int recordPairs) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ ResidentShared sh;
     const int w = worldList[blockIdx.x];
