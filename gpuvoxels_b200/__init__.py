@@ -76,6 +76,18 @@ class Model:
         self._desc = None
         _check(lib().vx3b_model_set_material_param(self._h, mat, name.encode(), float(value)), "vx3b_model_set_material_param")
 
+    def set_material_bilinear(self, mat, youngs_modulus, plastic_modulus, yield_stress, failure_stress=-1.0):
+        """CVX_Material::setModelBilinear"""
+        self._desc = None
+        _check(lib().vx3b_model_set_material_bilinear(self._h, mat, float(youngs_modulus), float(plastic_modulus), float(yield_stress), float(failure_stress)),
+               "vx3b_model_set_material_bilinear")
+
+    def set_material_data(self, mat, strain, stress):
+        """CVX_Material::setModel: stress/strain points, ascending, from or after (0, 0)"""
+        self._desc = None
+        a, b = np.ascontiguousarray(strain, dtype=np.float64), np.ascontiguousarray(stress, dtype=np.float64)
+        _check(lib().vx3b_model_set_material_data(self._h, mat, len(a), _dp(a), _dp(b)), "vx3b_model_set_material_data")
+
     def set_voxel(self, mat, ix, iy, iz):
         self._desc = None
         return _check(lib().vx3b_model_set_voxel(self._h, mat, ix, iy, iz), "vx3b_model_set_voxel")

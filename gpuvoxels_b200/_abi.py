@@ -27,10 +27,14 @@ class VoxelMaterial(C.Structure):
             "matid", "fixed", "isTarget", "isMeasured", "sticky", "linear")] + [("rgba", C.c_uint32)]
 
 
+MAX_SS_POINTS = 16
+
+
 class LinkMaterial(C.Structure):
     _fields_ = [(n, C.c_float) for n in (
         "E", "nu", "eHat", "a1", "a2", "b1", "b2", "b3", "sqA1", "sqA2xIp", "sqB1", "sqB2xFMp", "sqB3xIp",
-        "epsilonFail")] + [("mat1", C.c_int32), ("mat2", C.c_int32)]
+        "epsilonFail")] + [("mat1", C.c_int32), ("mat2", C.c_int32), ("linear", C.c_int32), ("num_points", C.c_int32),
+                           ("strain_data", C.c_float * MAX_SS_POINTS), ("stress_data", C.c_float * MAX_SS_POINTS)]
 
 
 class WorldDesc(C.Structure):
@@ -108,6 +112,8 @@ SYMBOLS = {
     "vx3b_ctx_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "vx3b_ctx_total_voxel_steps": (C.c_int64, [_P]),
     "vx3b_ctx_set_stream": (C.c_int, [_P, C.c_uint64]),
+    "vx3b_model_set_material_bilinear": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "vx3b_model_set_material_data": (C.c_int, [_P, C.c_int, C.c_int, _DP, _DP]),
     "vx3b_job_run": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int]),
     "vx3b_job_run_files": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int, C.c_int]),
     "vx3b_job_run_task": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]),

@@ -53,7 +53,8 @@ enum {
     WF_THERMAL = 512,  // temperature varies AND some material has alphaCTE != 0 (otherwise temperature is unobservable)
     WF_CAN_FAIL = 1024, // some link material has a failure strain
     WF_FUSED = 2048,    // stepped by k_fused in this run (state ping-pongs between the main and the alternate buffers)
-    WF_BRICK = 4096     // stepped by k_brick in this run (state lives in the brick-ordered buffer sets, kernels_brick.cuh)
+    WF_BRICK = 4096,    // stepped by k_brick in this run (state lives in the brick-ordered buffer sets, kernels_brick.cuh)
+    WF_NONLIN = 8192    // some link material is bilinear / data based or has a non-zero Poisson's ratio: links use DLinkModel (k_links)
 };
 struct WorldD {
     // static
@@ -148,6 +149,8 @@ template <class R> struct Arrays {
     // materials
     DVoxMat *vmats;
     DLinkMat *lmats;
+    DLinkModel *lmodels; // per link material, or nullptr when no world of the batch is WF_NONLIN
+    float *lso;          // per link: strainOffset (VX3_Link.cu:232-268), or nullptr
     // pair recording (parity tests)
     int4 *pairBuf;
     int32_t *pairCount;

@@ -35,6 +35,7 @@ class EngineBase {
     // options
     int path = 0;         // 0 auto (resident + brick/fused), 1 two-kernel streaming, 2 resident, 3 fused for all, 4 resident + two-kernel streaming,
                           // 5 brick for every eligible world, fused for the rest (3 and 5 must be set before upload)
+    int requestedPath = -1; // the caller's `path` while a batch with non-linear / Poisson worlds forces it to 1 (restored at the next upload)
     int brickDim[3] = {8, 8, 4}; // lattice cells per brick of the fused and brick paths (the brick path halves them until a brick fits)
     int recordPairs = 0;  // keep the collision pair list of the last step (parity tests)
     int chunk = 64;       // steps per CUDA-graph replay on the streaming path

@@ -452,6 +452,20 @@ template <class R> class Engine : public EngineBase {
         hDampT.assign(nvm, 0.0f);
         hDampR.assign(nvm, 0.0f);
         std::vector<DLinkMat> lmats(nlm);
+        // worlds with bilinear / data materials or a Poisson's ratio need the stress/strain model per link material and a strain offset
+        // per link; they are stepped by the two-kernel streaming path, and so is the whole batch they are part of
+        bool anyNonlin = false;
+        for (int w = 0; w < n && !anyNonlin; w++)
+            for (int k = 0; k < worlds[w].num_link_mats && !anyNonlin; k++)
+                anyNonlin = !worlds[w].link_mats[k].linear || worlds[w].link_mats[k].nu != 0.0f;
+        if (requestedPath >= 0)
+            path = requestedPath; // (undo the override of an earlier batch)
+        requestedPath = -1;
+        if (anyNonlin && path != 1) {
+            requestedPath = path;
+            path = 1;
+        }
+        std::vector<DLinkModel> lmodels(anyNonlin ? nlm : 0);
         std::atomic<bool> anyPhaseA{false}, anyCiliaA{false}, anyGhostA{false};
         anyCollision = false;
         // offsets of every world in the concatenated arrays (layout order), then the worlds are staged in parallel
@@ -611,6 +625,22 @@ template <class R> class Engine : public EngineBase {
                 float s1 = (float)d.voxel_mats[m.mat1].nomSize, s2 = (float)d.voxel_mats[m.mat2].nomSize;
                 o.area = 0.5f * (s1 * s1 + s2 * s2); // currentTransverseArea for nu == 0 (VX3_Link.cu:85-88, VX3_Voxel.cu:496-499)
                 o.matPair = (uint32_t)m.mat1 | ((uint32_t)m.mat2 << 16);
+                if (anyNonlin) {
+                    DLinkModel &q = lmodels[lmo + k];
+                    memset(&q, 0, sizeof(q));
+                    q.linear = m.linear;
+                    q.npts = std::max(2, std::min(m.num_points, VX3B_MAX_SS_POINTS));
+                    q.E = m.E;
+                    q.nu = m.nu;
+                    q.eHat = m.eHat;
+                    q.epsilonFail = m.epsilonFail;
+                    for (int i = 0; i < VX3B_MAX_SS_POINTS; i++) {
+                        q.strain[i] = m.strain_data[i];
+                        q.stress[i] = m.stress_data[i];
+                    }
+                    if (!m.linear || m.nu != 0.0f)
+                        W.flags |= WF_NONLIN;
+                }
             }
             // voxels
             const bool vary = (W.flags & WF_VARY_TEMP) != 0;
@@ -1237,6 +1267,11 @@ template <class R> class Engine : public EngineBase {
             return rc;
         UP(vmats, vmats);
         UP(lmats, lmats);
+        if (anyNonlin) {
+            UP(lmodels, lmodels);
+            if ((rc = dalloc(&A.lso, nlTot)) != VX3B_OK) // zero-filled on the device
+                return rc;
+        }
         if (anyPhase) {
             UP(phase, phase);
         }

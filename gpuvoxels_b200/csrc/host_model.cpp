@@ -116,13 +116,131 @@ static VX3B_VoxelMaterial derive_voxel_material(const MatInput &in, float nu, do
     return o;
 }
 
-static VX3B_LinkMaterial derive_link_material(const VX3B_VoxelMaterial &m1, const MatInput &i1, const VX3B_VoxelMaterial &m2,
-                                              const MatInput &i2, int a, int b) {
+// ---- stress/strain models: CVX_Material::setModelLinear / setModelBilinear / setModel (old/VX_Material.cpp:300-449) ----------
+bool mat_set_model_linear(MatInput &m, float youngsModulus, float failureStress, std::string *err) {
+    if (youngsModulus <= 0) {
+        if (err)
+            *err = "Young's modulus must be positive";
+        return false;
+    }
+    if (failureStress != -1.0f && failureStress <= 0) {
+        if (err)
+            *err = "Failure stress must be positive";
+        return false;
+    }
+    float tmpFailureStress = failureStress; // a dummy failure stress if none was provided
+    if (tmpFailureStress == -1)
+        tmpFailureStress = 1000000;
+    const float tmpFailStrain = tmpFailureStress / youngsModulus;
+    m.strainData = {0.0f, tmpFailStrain};
+    m.stressData = {0.0f, tmpFailureStress};
+    m.linear = true;
+    m.E = youngsModulus;
+    m.sigmaFail = failureStress;
+    m.epsilonFail = (failureStress == -1) ? -1 : tmpFailStrain;
+    return true;
+}
+bool mat_set_model_bilinear(MatInput &m, float youngsModulus, float plasticModulus, float yieldStress, float failureStress, std::string *err) {
+    const char *why = nullptr;
+    if (youngsModulus <= 0)
+        why = "Young's modulus must be positive";
+    else if (plasticModulus <= 0 || plasticModulus >= youngsModulus)
+        why = "Plastic modulus must be positive but less than Young's modulus";
+    else if (yieldStress <= 0)
+        why = "Yield stress must be positive";
+    else if (failureStress != -1.0f && failureStress <= yieldStress)
+        why = "Failure stress must be positive and greater than the yield stress";
+    if (why) {
+        if (err)
+            *err = why;
+        return false;
+    }
+    const float yieldStrain = yieldStress / youngsModulus;
+    float tmpFailureStress = failureStress;
+    if (tmpFailureStress == -1)
+        tmpFailureStress = 3 * yieldStress;
+    const float tM = plasticModulus;
+    const float tB = yieldStress - tM * yieldStrain; // y - m x = b
+    const float tmpFailStrain = (tmpFailureStress - tB) / tM;
+    m.strainData = {0.0f, yieldStrain, tmpFailStrain};
+    m.stressData = {0.0f, yieldStress, tmpFailureStress};
+    m.linear = false;
+    m.E = youngsModulus;
+    m.sigmaFail = failureStress;
+    m.epsilonFail = failureStress == -1.0f ? -1.0f : tmpFailStrain;
+    return true;
+}
+bool mat_set_model_data(MatInput &m, int n, const float *strain, const float *stress, std::string *err) {
+    if (n > 0 && *strain == 0 && *stress == 0) { // a leading (0, 0) is implied
+        strain++;
+        stress++;
+        n--;
+    }
+    const char *why = nullptr;
+    if (n <= 0)
+        why = "Not enough data points";
+    else if (*strain <= 0 || *stress <= 0)
+        why = "First stress and strain data points negative or zero";
+    std::vector<float> sd{0.0f}, td{0.0f};
+    float sweepStrain = 0.0f, sweepStress = 0.0f;
+    for (int i = 0; i < n && !why; i++) {
+        const float thisStrain = strain[i], thisStress = stress[i];
+        if (thisStrain <= sweepStrain)
+            why = "Out of order strain data";
+        // (the reference compares with element 0 of both arrays, i.e. 0/0 = NaN: the slope test never fires - kept)
+        else if (i > 0 && (thisStress - sweepStress) / (thisStrain - sweepStrain) > td[0] / sd[0])
+            why = "Slope of stress/strain curve should never exceed that of the first line segment (youngs modulus)";
+        sweepStrain = thisStrain;
+        sweepStress = thisStress;
+        sd.push_back(thisStrain);
+        td.push_back(thisStress);
+    }
+    if (!why && (int)sd.size() > VX3B_MAX_SS_POINTS)
+        why = "too many stress/strain data points (VX3B_MAX_SS_POINTS)";
+    if (why) {
+        if (err)
+            *err = why;
+        return false;
+    }
+    m.strainData = sd;
+    m.stressData = td;
+    m.E = td[1] / sd[1];
+    m.sigmaFail = td.back();
+    m.epsilonFail = sd.back();
+    m.linear = (n == 1);
+    return true;
+}
+// CVX_Material::modulus / strain (old/VX_Material.cpp:186-220)
+static float model_modulus(const MatInput &m, float strain) {
+    if (m.epsilonFail != -1.0f && strain > m.epsilonFail)
+        return 0.0f;
+    if (strain <= m.strainData[1] || m.linear)
+        return m.E;
+    const int n = (int)m.strainData.size();
+    for (int i = 2; i < n; i++)
+        if (strain <= m.strainData[i] || i == n - 1)
+            return (m.stressData[i] - m.stressData[i - 1]) / (m.strainData[i] - m.strainData[i - 1]);
+    return 0.0f;
+}
+static float model_strain_at(const MatInput &m, float stress) {
+    if (stress <= m.stressData[1] || m.linear)
+        return stress / m.E;
+    const int n = (int)m.strainData.size();
+    for (int i = 2; i < n; i++)
+        if (stress <= m.stressData[i] || i == n - 1) {
+            const float perc = (stress - m.stressData[i - 1]) / (m.stressData[i] - m.stressData[i - 1]);
+            return m.strainData[i - 1] + perc * (m.strainData[i] - m.strainData[i - 1]);
+        }
+    return 0.0f;
+}
+
+// CVX_MaterialLink::updateAll + updateDerived (old/VX_MaterialLink.cpp:53-139 = VX3/VX3_MaterialLink.cu:53-148)
+static bool derive_link_material(const VX3B_VoxelMaterial &m1, const MatInput &i1, const VX3B_VoxelMaterial &m2, const MatInput &i2, int a, int b,
+                                 VX3B_LinkMaterial *out, std::string *err) {
     VX3B_LinkMaterial o;
     memset(&o, 0, sizeof(o));
     o.mat1 = a;
     o.mat2 = b;
-    // CVX_MaterialLink::updateAll (old/VX_MaterialLink.cpp:53-117), linear ∘ linear branch
     double nomSize = 0.5 * (m1.nomSize + m2.nomSize);
     float f1 = i1.sigmaFail, f2 = i2.sigmaFail, stressFail;
     if (f1 == -1.0f)
@@ -131,11 +249,54 @@ static VX3B_LinkMaterial derive_link_material(const VX3B_VoxelMaterial &m1, cons
         stressFail = f1;
     else
         stressFail = f1 < f2 ? f1 : f2;
-    o.E = 2.0f * m1.E * m2.E / (m1.E + m2.E);
-    o.epsilonFail = (stressFail == -1.0f) ? -1.0f : stressFail / o.E; // setModelLinear, old/VX_Material.cpp:373-401
-    o.nu = 0.0f;                                                     // both ends have nu == 0 (checked in finalize)
+    MatInput lm; // the link's own model
+    if (i1.linear && i2.linear) {
+        if (!mat_set_model_linear(lm, 2.0f * m1.E * m2.E / (m1.E + m2.E), stressFail, err))
+            return false;
+    } else { // at least one bilinear or data-based end: step up through the ascending strain points of both, springs in series
+        std::vector<float> newStress{0.0f}, newStrain{0.0f};
+        int it1 = 1, it2 = 1;
+        while (it1 < (int)i1.strainData.size() && it2 < (int)i2.strainData.size()) {
+            float strain = FLT_MAX;
+            if (it1 < (int)i1.strainData.size())
+                strain = i1.strainData[it1];
+            if (it2 < (int)i2.strainData.size() && i2.strainData[it2] < strain)
+                strain = i2.strainData[it2];
+            if (strain == i1.strainData[it1])
+                it1++;
+            if (strain == i2.strainData[it2])
+                it2++;
+            const float modulus1 = model_modulus(i1, strain - FLT_EPSILON), modulus2 = model_modulus(i2, strain - FLT_EPSILON);
+            const float thisModulus = 2.0f * modulus1 * modulus2 / (modulus1 + modulus2);
+            const int last = (int)newStrain.size() - 1;
+            const float s0 = newStrain[last], t0 = newStress[last];
+            newStrain.push_back(strain);
+            newStress.push_back(t0 + thisModulus * (strain - s0));
+        }
+        if (!mat_set_model_data(lm, (int)newStrain.size(), newStrain.data(), newStress.data(), err))
+            return false;
+        lm.sigmaFail = stressFail; // no failure specified before: possible in combinations of linear and bilinear materials
+        lm.epsilonFail = stressFail == -1.0f ? -1.0f : model_strain_at(lm, stressFail);
+    }
+    o.E = lm.E;
+    o.epsilonFail = lm.epsilonFail;
+    o.linear = lm.linear ? 1 : 0;
+    o.num_points = (int)lm.strainData.size();
+    for (int k = 0; k < o.num_points; k++) {
+        o.strain_data[k] = lm.strainData[k];
+        o.stress_data[k] = lm.stressData[k];
+    }
+    // Poisson's ratio: chosen so that eHat ends up as the series spring of the two ends' eHat
+    if (m1.nu == 0 && m2.nu == 0)
+        o.nu = 0;
+    else {
+        const float eHat1 = m1.E / ((1 - 2 * m1.nu) * (1 + m1.nu)), eHat2 = m2.E / ((1 - 2 * m2.nu) * (1 + m2.nu));
+        const float tmpEHat = 2 * eHat1 * eHat2 / (eHat1 + eHat2);
+        const float tmpE = o.E;
+        const float c2 = (tmpEHat - tmpE) / (2 * tmpEHat) + 0.0625; // (nu + 0.25)^2 = c2
+        o.nu = (float)(sqrtf(c2) - 0.25); // float root (std::sqrt(float) in the reference), then the double subtraction
+    }
     o.eHat = o.E / ((1 - 2 * o.nu) * (1 + o.nu));
-    // CVX_MaterialLink::updateDerived (old/VX_MaterialLink.cpp:119-139)
     float L = (float)nomSize;
     o.a1 = o.E * L;
     o.a2 = o.E * L * L * L / (12.0f * (1 + o.nu));
@@ -147,19 +308,24 @@ static VX3B_LinkMaterial derive_link_material(const VX3B_VoxelMaterial &m1, cons
     o.sqB1 = sqrtf(o.b1);
     o.sqB2xFMp = sqrtf(o.b2 * L / 2.0f);
     o.sqB3xIp = sqrtf(o.b3 * L * L / 6.0f);
-    return o;
+    *out = o;
+    return true;
 }
 
 bool HostModel::finalize(std::string *err) {
     voxelMats.clear();
     for (auto &m : mats) {
         float nu = volumeEffects ? m.nuMemory : 0.0f; // CVX_Sim::EnableVolumeEffects, VX_Sim.cpp:445-458
-        if (nu != 0.0f) {
+        if (nu != 0.0f && vx2Compat) {
+            // Voxelyze2 re-derives every link's transverse area and strain sum each step from neighbour strains the same sweep is
+            // updating (CVX_Link::updateTransverseInfo under `omp parallel for`): order dependent, not restated.  Voxelyze3 compiles
+            // that update out (VX3_Link.cu:147-150) and keeps the initial values; that form is supported.
             if (err)
-                *err = "Poisson/volume effects (VolumeEffectsEnabled with nu != 0) are not on the fused path yet (SURVEY.md §8f-4)";
+                *err = "Poisson/volume effects with Voxelyze2 semantics (vx2_compat with nu != 0) are not supported (SURVEY.md §8f-4)";
             return false;
         }
         voxelMats.push_back(derive_voxel_material(m, nu, voxSize, gravMult));
+        voxelMats.back().linear = m.linear ? 1 : 0;
     }
     linkMatPairs.clear();
     linkMats.clear();
@@ -175,7 +341,10 @@ bool HostModel::finalize(std::string *err) {
         if (found < 0) {
             found = (int)linkMatPairs.size();
             linkMatPairs.emplace_back(a, b);
-            linkMats.push_back(derive_link_material(voxelMats[a], mats[a], voxelMats[b], mats[b], a, b));
+            VX3B_LinkMaterial lm;
+            if (!derive_link_material(voxelMats[a], mats[a], voxelMats[b], mats[b], a, b, &lm, err))
+                return false;
+            linkMats.push_back(lm);
         }
         linkMat[l] = found;
     }
@@ -592,21 +761,44 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
             }
             int matModel = get_int(mech, "MatModel", 0);
             double E = get_double(mech, "Elastic_Mod", 0), failStress = get_double(mech, "Fail_Stress", 0);
-            if (matModel >= 2) {
-                if (err)
-                    *err = "bilinear / data material models are not on the fused path yet (SURVEY.md §8f-4)";
-                return nullptr;
+            // CVX_Sim::CopyMat (VX_Sim.cpp:368-420) -> CVX_Material::setModel* (old/VX_Material.cpp:300-449)
+            std::string merr;
+            bool ok = true;
+            if (matModel == 0)
+                ok = mat_set_model_linear(m, (float)E, -1.0f, &merr);
+            else if (matModel == 1) // (a LINEAR_FAIL material without a positive Fail_Stress never fails)
+                ok = mat_set_model_linear(m, (float)E, (float)failStress > 0 ? (float)failStress : -1.0f, &merr);
+            else if (matModel == 2)
+                ok = mat_set_model_bilinear(m, (float)E, (float)get_double(mech, "Plastic_Mod", 0), (float)get_double(mech, "Yield_Stress", 0), (float)failStress, &merr);
+            else if (matModel == 3) { // <SSData><NumDataPts>n</NumDataPts><StrainData><Strain>..</Strain>..</StrainData><StressData><Stress>..
+                std::vector<float> strain, stress;
+                const XmlNode *ss = mech ? mech->child("SSData") : nullptr;
+                const int npts = ss ? get_int(ss, "NumDataPts", 0) : 0;
+                if (ss) {
+                    if (const XmlNode *sd = ss->child("StrainData"))
+                        for (auto &c : sd->children)
+                            if (c->name == "Strain" && (int)strain.size() < npts)
+                                strain.push_back((float)atof(c->text.c_str()));
+                    if (const XmlNode *td = ss->child("StressData"))
+                        for (auto &c : td->children)
+                            if (c->name == "Stress" && (int)stress.size() < npts)
+                                stress.push_back((float)atof(c->text.c_str()));
+                }
+                if ((int)strain.size() != npts || (int)stress.size() != npts || npts == 0) {
+                    ok = false;
+                    merr = "SSData needs NumDataPts Strain and Stress values";
+                } else
+                    ok = mat_set_model_data(m, npts, strain.data(), stress.data(), &merr);
+            } else {
+                ok = false;
+                merr = "unknown MatModel " + std::to_string(matModel);
             }
-            // CVX_Sim::CopyMat (VX_Sim.cpp:368-420) -> CVX_Material::setModelLinear (old/VX_Material.cpp:373-401)
-            m.E = (float)E;
-            if (!(m.E > 0)) {
+            if (!ok) {
+                // the reference keeps the material's previous (default) model when a setModel* call refuses its arguments
+                // (CVX_Material::setModelLinear returns false); a world with such a material would run on E = 1 Pa - refuse instead
                 if (err)
-                    *err = "material " + std::to_string(m.matid) + ": Young's modulus must be positive";
+                    *err = "material " + std::to_string(m.matid) + ": " + merr;
                 return nullptr;
-            }
-            if (matModel == 1 && (float)failStress > 0) {
-                m.sigmaFail = (float)failStress;
-                m.epsilonFail = m.sigmaFail / m.E;
             }
             float nu = (float)get_double(mech, "Poissons_Ratio", 0);
             if (nu < 0)
@@ -834,14 +1026,12 @@ int vx3b_model_set_material_param(vx3b_model *m, int mat, const char *name, doub
     vx3b::MatInput &M = m->m->mats[mat];
     std::string n = name;
     float f = (float)value;
-    if (n == "youngs_modulus") {
-        if (!(f > 0)) {
-            vx3b::set_error("Young's modulus must be positive");
+    if (n == "youngs_modulus") { // CVX_Material::setModelLinear(E, current failure stress)
+        std::string e;
+        if (!vx3b::mat_set_model_linear(M, f, M.sigmaFail, &e)) {
+            vx3b::set_error(e);
             return VX3B_ERR_ARG;
         }
-        M.E = f;
-        if (M.sigmaFail != -1.0f)
-            M.epsilonFail = M.sigmaFail / M.E;
     } else if (n == "density")
         M.rho = f <= 0 ? FLT_MIN : f;
     else if (n == "poissons_ratio") {
@@ -864,11 +1054,10 @@ int vx3b_model_set_material_param(vx3b_model *m, int mat, const char *name, doub
     else if (n == "collision_damping")
         M.zetaCollision = f <= 0 ? 0 : f;
     else if (n == "fail_stress") {
-        if (f > 0) {
-            M.sigmaFail = f;
-            M.epsilonFail = f / M.E;
-        } else {
-            M.sigmaFail = M.epsilonFail = -1.0f;
+        std::string e;
+        if (!vx3b::mat_set_model_linear(M, M.E, f > 0 ? f : -1.0f, &e)) {
+            vx3b::set_error(e);
+            return VX3B_ERR_ARG;
         }
     } else if (n == "cilia")
         M.Cilia = value;
@@ -882,6 +1071,35 @@ int vx3b_model_set_material_param(vx3b_model *m, int mat, const char *name, doub
         M.matid = (int)value;
     else {
         vx3b::set_error("unknown material parameter: " + n);
+        return VX3B_ERR_ARG;
+    }
+    m->m->finalized = false;
+    return VX3B_OK;
+}
+
+// CVX_Material::setModelBilinear / setModel on a builder material (old/VX_Material.cpp:300-449)
+int vx3b_model_set_material_bilinear(vx3b_model *m, int mat, double youngs_modulus, double plastic_modulus, double yield_stress, double failure_stress) {
+    if (!m || mat < 0 || mat >= (int)m->m->mats.size()) {
+        vx3b::set_error("vx3b_model_set_material_bilinear: bad material index");
+        return VX3B_ERR_ARG;
+    }
+    std::string e;
+    if (!vx3b::mat_set_model_bilinear(m->m->mats[mat], (float)youngs_modulus, (float)plastic_modulus, (float)yield_stress, (float)failure_stress, &e)) {
+        vx3b::set_error(e);
+        return VX3B_ERR_ARG;
+    }
+    m->m->finalized = false;
+    return VX3B_OK;
+}
+int vx3b_model_set_material_data(vx3b_model *m, int mat, int num_points, const double *strain, const double *stress) {
+    if (!m || mat < 0 || mat >= (int)m->m->mats.size() || num_points < 1 || !strain || !stress) {
+        vx3b::set_error("vx3b_model_set_material_data: bad argument");
+        return VX3B_ERR_ARG;
+    }
+    std::vector<float> sd(strain, strain + num_points), td(stress, stress + num_points);
+    std::string e;
+    if (!vx3b::mat_set_model_data(m->m->mats[mat], num_points, sd.data(), td.data(), &e)) {
+        vx3b::set_error(e);
         return VX3B_ERR_ARG;
     }
     m->m->finalized = false;

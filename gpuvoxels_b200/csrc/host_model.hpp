@@ -21,11 +21,19 @@ struct MatInput { // CVX_Material state before derivation (floats, as the refere
     float E = 1.0f, nu = 0.0f, rho = 1.0f, alphaCTE = 0.0f, muStatic = 0.0f, muKinetic = 0.0f;
     float zetaInternal = 1.0f, zetaGlobal = 0.0f, zetaCollision = 0.0f;
     float sigmaFail = -1.0f, epsilonFail = -1.0f;
+    // stress/strain model (CVX_Material::setModelLinear / setModelBilinear / setModel, old/VX_Material.cpp:300-449): the points
+    // from (0, 0); linear materials carry the two points the reference gives them
+    bool linear = true;
+    std::vector<float> strainData{0.0f, 1000000.0f}, stressData{0.0f, 1000000.0f};
     uint32_t rgba = 0xffffffffu; // display colour, (int)(value*255) per channel (VX_Object.h:419-425)
     float nuMemory = 0.0f; // Poisson's ratio as given (muMemory, VX_Sim.cpp:85)
     double Cilia = 0;
     int matid = 0, fixed = 0, isTarget = 0, isMeasured = 1, sticky = 0;
 };
+
+bool mat_set_model_linear(MatInput &m, float youngsModulus, float failureStress, std::string *err);
+bool mat_set_model_bilinear(MatInput &m, float youngsModulus, float plasticModulus, float yieldStress, float failureStress, std::string *err);
+bool mat_set_model_data(MatInput &m, int n, const float *strain, const float *stress, std::string *err);
 
 struct HostModel {
     // --- inputs -------------------------------------------------------------------------

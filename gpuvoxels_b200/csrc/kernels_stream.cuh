@@ -89,7 +89,12 @@ template <class R> __global__ void __launch_bounds__(256) k_links(Arrays<R> A, i
     float dmN = mn.sqrtMassZetaInt2 / ((vx3 && mn.fixed) ? 0.0f : W.dt);
     float dmP = mp.sqrtMassZetaInt2 / ((vx3 && mp.fixed) ? 0.0f : W.dt);
     LinkForces<R> f;
-    link_update<R>(lm, axis, V3<double>{pp.x - pn.x, pp.y - pn.y, pp.z - pn.z}, W.voxSize, qn, qp, restLen, dmN, dmP, h, f);
+    if (W.flags & WF_NONLIN) { // bilinear / data materials, Poisson's ratio: the material's stress/strain model + the link's strain offset
+        float so = A.lso[l];
+        link_update<R>(lm, axis, V3<double>{pp.x - pn.x, pp.y - pn.y, pp.z - pn.z}, W.voxSize, qn, qp, restLen, dmN, dmP, h, f, &A.lmodels[meta >> 2], &so);
+        A.lso[l] = so;
+    } else
+        link_update<R>(lm, axis, V3<double>{pp.x - pn.x, pp.y - pn.y, pp.z - pn.z}, W.voxSize, qn, qp, restLen, dmN, dmP, h, f);
     R fl;
     if constexpr (sizeof(R) == 4)
         fl = u2f(h.flags);

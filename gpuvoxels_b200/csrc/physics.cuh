@@ -238,6 +238,62 @@ struct DLinkMat {
     uint32_t matPair; // world-local voxel materials the link material combines: mat1 | mat2 << 16
 };
 
+// Stress/strain model of a link material for worlds with bilinear / data materials or a non-zero Poisson's ratio (the streaming
+// kernels; every other world's links are the single line E of DLinkMat): CVX_Material::strainData / stressData, nu, eHat.
+struct DLinkModel {
+    int32_t linear, npts;
+    float E, nu, eHat, epsilonFail;
+    float strain[VX3B_MAX_SS_POINTS], stress[VX3B_MAX_SS_POINTS];
+};
+// VX3_Material::stress (VX3/VX3_Material.cu:90-124).  transverseStrainSum is the link's currentTransverseStrainSum, which Voxelyze3
+// never refreshes after construction (updateTransverseInfo() is commented out, VX3/VX3_Link.cu:147-150): 0.
+VXD float material_stress(const DLinkModel &m, float strain, float transverseStrainSum, bool forceLinear) {
+    if (m.epsilonFail != -1.0f && strain > m.epsilonFail)
+        return 0.0f;
+    if (strain <= m.strain[1] || m.linear || forceLinear) {
+        if (m.nu == 0.0f)
+            return m.E * strain;
+        return m.eHat * ((1 - m.nu) * strain + m.nu * transverseStrainSum);
+    }
+    const int n = m.npts;
+    for (int i = 2; i < n; i++) {
+        if (strain <= m.strain[i] || i == n - 1) {
+            const float Perc = (strain - m.strain[i - 1]) / (m.strain[i] - m.strain[i - 1]);
+            const float basicStress = m.stress[i - 1] + Perc * (m.stress[i] - m.stress[i - 1]);
+            if (m.nu == 0.0f)
+                return basicStress;
+            const float modulus = (m.stress[i] - m.stress[i - 1]) / (m.strain[i] - m.strain[i - 1]);
+            const float modulusHat = modulus / ((1 - 2 * m.nu) * (1 + m.nu));
+            const float effectiveStrain = basicStress / modulus;
+            const float effectiveTransverseStrainSum = transverseStrainSum * (effectiveStrain / strain);
+            return modulusHat * ((1 - m.nu) * effectiveStrain + m.nu * effectiveTransverseStrainSum);
+        }
+    }
+    return 0.0f;
+}
+// VX3_Link::updateStrain (VX3/VX3_Link.cu:232-268): a non-linear material remembers its largest strain and backs off along E
+VXD float update_strain(const DLinkModel &m, float axialStrain, float &maxStrain, float &strainOffset) {
+    const float tss = 0.0f;
+    if (m.linear) {
+        if (axialStrain > maxStrain)
+            maxStrain = axialStrain;
+        return material_stress(m, axialStrain, tss, false);
+    }
+    float returnStress;
+    if (axialStrain > maxStrain) { // new territory on the stress/strain curve
+        maxStrain = axialStrain;
+        returnStress = material_stress(m, axialStrain, tss, false);
+        if (m.nu != 0.0f)
+            strainOffset = maxStrain - material_stress(m, axialStrain, 0.0f, false) / (m.eHat * (1 - m.nu));
+        else
+            strainOffset = maxStrain - returnStress / m.E;
+    } else { // backed off a non-linear material: linear with a strain offset according to the maximum plastic deformation
+        const float relativeStrain = axialStrain - strainOffset;
+        returnStress = m.nu != 0.0f ? material_stress(m, relativeStrain, tss, true) : m.E * relativeStrain;
+    }
+    return returnStress;
+}
+
 // link history flags
 enum { LF_SMALL_ANGLE = 1, LF_VEL_VALID = 2 };
 // voxel flags
@@ -280,9 +336,11 @@ template <class R> VXD LinkLen<R> link_len(double nomLen, double restLen) {
 }
 // AXIS >= 0: the link axis is a compile-time constant (the caller dispatches once per link; the seven swizzles fold away);
 // AXIS == -1: run-time axis
+// model / strainOffset: the link material's stress/strain model and the link's strain offset, for worlds that need them (nullptr
+// otherwise: the single line E of `m`)
 template <class R, int AXIS = -1>
 VXD void link_update(const DLinkMat &m, int axisRt, V3<double> dpos, const LinkLen<R> len, Qt<R> qn, Qt<R> qp, float dmN, float dmP, LinkHist<R> &h,
-                     LinkForces<R> &out) {
+                     LinkForces<R> &out, const DLinkModel *model = nullptr, float *strainOffset = nullptr) {
     const int axis = AXIS >= 0 ? AXIS : axisRt;
     const double nomLen = len.nomLen;
     const V3<R> oldPos2 = h.pos2, oldA1 = h.a1v, oldA2 = h.a2v;
@@ -346,10 +404,15 @@ VXD void link_update(const DLinkMat &m, int axisRt, V3<double> dpos, const LinkL
     else
         eps = d.x * len.invRest;
     out.strain = eps;
-    if (eps > h.maxStrain)
-        h.maxStrain = eps;
     const bool canFail = m.epsilonFail != -1.0f;
-    float stress = (canFail && eps > m.epsilonFail) ? 0.0f : m.E * eps;
+    float stress;
+    if (model)
+        stress = update_strain(*model, eps, h.maxStrain, *strainOffset);
+    else {
+        if (eps > h.maxStrain)
+            h.maxStrain = eps;
+        stress = (canFail && eps > m.epsilonFail) ? 0.0f : m.E * eps;
+    }
     if (canFail && h.maxStrain > m.epsilonFail) { // isFailed(): outputs zero, flags keep their pre-damping value
         out.fNeg = out.fPos = out.mNeg = out.mPos = V3<R>{R(0), R(0), R(0)};
         h.flags = (small ? LF_SMALL_ANGLE : 0) | (valid ? LF_VEL_VALID : 0);
@@ -385,8 +448,8 @@ VXD void link_update(const DLinkMat &m, int axisRt, V3<double> dpos, const LinkL
 }
 template <class R>
 VXD void link_update(const DLinkMat &m, int axis, V3<double> dpos, double nomLen, Qt<R> qn, Qt<R> qp, double restLen, float dmN, float dmP,
-                     LinkHist<R> &h, LinkForces<R> &out) {
-    link_update<R, -1>(m, axis, dpos, link_len<R>(nomLen, restLen), qn, qp, dmN, dmP, h, out);
+                     LinkHist<R> &h, LinkForces<R> &out, const DLinkModel *model = nullptr, float *strainOffset = nullptr) {
+    link_update<R, -1>(m, axis, dpos, link_len<R>(nomLen, restLen), qn, qp, dmN, dmP, h, out, model, strainOffset);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@ parser (oracle/_ref).  Fixed seeds; numpy only.
 import numpy as np
 
 _MAT_DEFAULTS = dict(name="mat", E=5e6, density=1e6, nu=0.35, cte=0.0, u_static=1.0, u_dynamic=0.5, cilia=0.0,
-                     is_target=0, fixed=0, is_measured=1, mat_model=0, fail_stress=0.0)
+                     is_target=0, fixed=0, is_measured=1, mat_model=0, fail_stress=0.0, plastic_mod=0.0, yield_stress=0.0, ss_data=None)
 
 
 def material(**kw):
@@ -25,10 +25,15 @@ def _mat_xml(i, m):
         extra += "<Fixed>1</Fixed>"
     if not m["is_measured"]:
         extra += "<isMeasured>0</isMeasured>"
+    ss = ""
+    if m["ss_data"]:  # MatModel 3: stress/strain points (CVXC_Material::ReadXML, VXA/VX_Object.cpp:1395-1417)
+        pts = list(m["ss_data"])
+        ss = (f"<SSData><NumDataPts>{len(pts)}</NumDataPts><StrainData>" + "".join(f"<Strain>{float(a)!r}</Strain>" for a, _ in pts) +
+              "</StrainData><StressData>" + "".join(f"<Stress>{float(b)!r}</Stress>" for _, b in pts) + "</StressData></SSData>")
     return (f'<Material ID="{i}"><MatType>0</MatType><Name>{m["name"]}</Name>'
             f"<Display><Red>0.5</Red><Green>0.5</Green><Blue>0.5</Blue><Alpha>1</Alpha></Display>"
-            f"<Mechanical>{extra}<MatModel>{m['mat_model']}</MatModel><Elastic_Mod>{m['E']!r}</Elastic_Mod>"
-            f"<Plastic_Mod>0</Plastic_Mod><Yield_Stress>0</Yield_Stress><FailModel>0</FailModel>"
+            f"<Mechanical>{extra}<MatModel>{m['mat_model']}</MatModel>{ss}<Elastic_Mod>{m['E']!r}</Elastic_Mod>"
+            f"<Plastic_Mod>{m['plastic_mod']!r}</Plastic_Mod><Yield_Stress>{m['yield_stress']!r}</Yield_Stress><FailModel>0</FailModel>"
             f"<Fail_Stress>{m['fail_stress']!r}</Fail_Stress><Fail_Strain>0</Fail_Strain><Density>{m['density']!r}</Density>"
             f"<Poissons_Ratio>{m['nu']!r}</Poissons_Ratio><CTE>{m['cte']!r}</CTE><MaterialTempPhase>0</MaterialTempPhase>"
             f"<uStatic>{m['u_static']!r}</uStatic><uDynamic>{m['u_dynamic']!r}</uDynamic></Mechanical></Material>")
@@ -313,3 +318,23 @@ def merge_vxd(vxa_text, vxd_text):
             node.remove(old)
             node.insert(i, new)
     return '<?xml version="1.0" encoding="ISO-8859-1"?>\n' + ET.tostring(root, encoding="unicode")
+
+
+
+def plastic_beam_vxa(volume_effects=False, nu=0.0, DENS=2e4):
+    """A cantilever of three materials - bilinear (yields at strain 0.004), data model (three segments) and a linear tip weight -
+    held by a block of `Fixed` material and bent by gravity hard enough to take the bilinear and data links to strains of 0.05,
+    past their yield points but short of failure; it then swings back along E (the strain-offset path of VX3_Link.cu:232-268).
+    volume_effects + nu: Poisson's ratio as Voxelyze3 applies it (eHat, frozen transverse terms)."""
+    data = np.zeros((4, 2, 6), dtype=int)  # [z][y][x]
+    data[3, :, 0] = 4          # the fixed anchor block (top layer, x = 0)
+    data[3, :, 1:3] = 1        # bilinear
+    data[3, :, 3:5] = 2        # data model
+    data[3, :, 5] = 3          # linear tip weight
+    data[2, :, 5] = 3
+    mats = [material(name="bilinear", E=1e6, density=DENS, nu=nu, mat_model=2, plastic_mod=2.5e5, yield_stress=4e3, fail_stress=5e4),
+            material(name="data", E=1e6, density=DENS, nu=nu, mat_model=3, ss_data=[(0.004, 4e3), (0.02, 1.2e4), (0.08, 2.0e4)]),
+            material(name="tip", E=5e6, density=2 * DENS, nu=nu),
+            material(name="anchor", E=5e7, density=1e6, nu=nu, fixed=1)]
+    return vxa_document(mats, structure_xml(data), lattice_dim=0.01, dt_frac=0.5, bond_damping=0.3, slow_damping=0.002, grav_acc=-9.81, floor=False,
+                        enable_collision=False, volume_effects=volume_effects)

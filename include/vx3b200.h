@@ -77,18 +77,24 @@ typedef struct VX3B_VoxelMaterial {
     double nomSize;
     double Cilia;                /* scale of the cilia force */
     int32_t matid;               /* palette ID reported in <mats> */
-    int32_t fixed, isTarget, isMeasured, sticky, linear;
+    int32_t fixed, isTarget, isMeasured, sticky, linear; /* linear = 0: bilinear or data model (the link materials carry the curves) */
     uint32_t rgba;               /* display colour r | g << 8 | b << 16 | a << 24, each (int)(VXA value * 255) (VX_Object.h:419-425): .history only */
 } VX3B_VoxelMaterial;
 
 /* Combined material of a voxel pair: CVX_MaterialLink::updateAll/updateDerived
  * (VX3_MaterialLink.cu:53-148). */
+#define VX3B_MAX_SS_POINTS 16 /* points of a stress/strain model, the leading (0, 0) included */
 typedef struct VX3B_LinkMaterial {
     float E, nu, eHat;
     float a1, a2, b1, b2, b3;
     float sqA1, sqA2xIp, sqB1, sqB2xFMp, sqB3xIp;
     float epsilonFail;           /* -1 = never fails */
     int32_t mat1, mat2;          /* indices into voxel_mats */
+    /* stress/strain model (CVX_Material::strainData / stressData, VX3_Material.cu:90-156): linear = 1: the single line E;
+     * else num_points points from (0, 0), piecewise linear, extrapolated along the last segment; a link backs off along E from
+     * its largest strain (VX3_Link.cu:232-268) */
+    int32_t linear, num_points;
+    float strain_data[VX3B_MAX_SS_POINTS], stress_data[VX3B_MAX_SS_POINTS];
 } VX3B_LinkMaterial;
 
 /* One world (= one VXA⊕VXD), flattened.  Voxels are in the reference's creation order
@@ -172,6 +178,10 @@ int vx3b_model_from_files(const char *vxa_path, const char *vxd_path /* may be N
 int vx3b_model_new(double vox_size, vx3b_model **out);
 int vx3b_model_add_material(vx3b_model *m, double youngs_modulus, double density); /* returns material index >= 0 */
 int vx3b_model_set_material_param(vx3b_model *m, int mat, const char *name, double value);
+/* CVX_Material::setModelBilinear (failure_stress -1 = none) and setModel (points from or after (0, 0), ascending) on a builder
+ * material (old/VX_Material.cpp:300-449); links of such voxels step with the non-linear stress model (VX3_Link.cu:232-268). */
+int vx3b_model_set_material_bilinear(vx3b_model *m, int mat, double youngs_modulus, double plastic_modulus, double yield_stress, double failure_stress);
+int vx3b_model_set_material_data(vx3b_model *m, int mat, int num_points, const double *strain, const double *stress);
 int vx3b_model_set_voxel(vx3b_model *m, int mat, int ix, int iy, int iz);
 int vx3b_model_set_fixed(vx3b_model *m, int ix, int iy, int iz, int dof_mask, const double *translation3, const double *rotation3);
 int vx3b_model_set_force(vx3b_model *m, int ix, int iy, int iz, const double *force3, const double *moment3);

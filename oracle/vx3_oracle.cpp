@@ -210,7 +210,7 @@ struct World {
     // link state
     std::vector<V3> pos2, a1v, a2v, fNeg, fPos, mNeg, mPos;
     std::vector<uint8_t> smallAngle, velValid;
-    std::vector<float> strain, maxStrain;
+    std::vector<float> strain, maxStrain, strainOffset;
     std::vector<double> restLen;
 
     double t = 0, optimalDt = 0;
@@ -311,6 +311,7 @@ struct World {
         velValid.assign(nl, 0);
         strain.assign(nl, 0.0f);
         maxStrain.assign(nl, 0.0f);
+        strainOffset.assign(nl, 0.0f);
         restLen.resize(nl);
         for (int l = 0; l < nl; l++)
             update_rest_length(l);
@@ -320,12 +321,22 @@ struct World {
 
     void update_rest_length(int l) { restLen[l] = 0.5 * (base_size(lneg[l]) + base_size(lpos[l])); } // VX3_Link.cu:80-83
 
+    // VX3_Link::axialStiffness (VX3_Link.cu:277-286): a1 for nu == 0, else eHat * area / ((strain + 1) * restLength) with the link's
+    // current values - at the first step, where the time step is fixed: strain 0, area size^2, rest length at the first temperature
+    float axial_stiffness(int l) const {
+        const VX3B_LinkMaterial &m = lm[lmat[l]];
+        if (m.nu == 0.0f)
+            return m.a1;
+        float sz1 = (float)M(lneg[l]).nomSize, sz2 = (float)M(lpos[l]).nomSize;
+        float area = 0.5f * (sz1 * sz1 + sz2 * sz2);
+        return (float)(m.eHat * area / ((strain[l] + 1) * restLen[l]));
+    }
     double recommended_dt() const {
         if (vx3()) { // VX3_VoxelyzeKernel.cu:184-217: double accumulation
             double maxF2 = 0.0f;
             for (int l = 0; l < nl; l++) {
                 double m1 = M(lneg[l]).mass, m2 = M(lpos[l]).mass;
-                double f2 = lm[lmat[l]].a1 / (m1 < m2 ? m1 : m2);
+                double f2 = axial_stiffness(l) / (m1 < m2 ? m1 : m2);
                 if (f2 > maxF2)
                     maxF2 = f2;
             }
@@ -372,6 +383,59 @@ struct World {
             update_rest_length(l);
     }
 
+    // VX3_Material::stress (VX3_Material.cu:90-124).  transverseStrainSum: the link's currentTransverseStrainSum, which Voxelyze3
+    // never refreshes after construction (updateTransverseInfo is commented out, VX3_Link.cu:147-150), i.e. 0.
+    static float material_stress(const VX3B_LinkMaterial &m, float strain, float transverseStrainSum, bool forceLinear) {
+        if (m.epsilonFail != -1.0f && strain > m.epsilonFail)
+            return 0.0f; // isFailed(strain)
+        if (strain <= m.strain_data[1] || m.linear || forceLinear) {
+            if (m.nu == 0.0f)
+                return m.E * strain;
+            return m.eHat * ((1 - m.nu) * strain + m.nu * transverseStrainSum);
+        }
+        const int n = m.num_points;
+        for (int i = 2; i < n; i++) {
+            if (strain <= m.strain_data[i] || i == n - 1) {
+                float Perc = (strain - m.strain_data[i - 1]) / (m.strain_data[i] - m.strain_data[i - 1]);
+                float basicStress = m.stress_data[i - 1] + Perc * (m.stress_data[i] - m.stress_data[i - 1]);
+                if (m.nu == 0.0f)
+                    return basicStress;
+                float modulus = (m.stress_data[i] - m.stress_data[i - 1]) / (m.strain_data[i] - m.strain_data[i - 1]);
+                float modulusHat = modulus / ((1 - 2 * m.nu) * (1 + m.nu));
+                float effectiveStrain = basicStress / modulus;
+                float effectiveTransverseStrainSum = transverseStrainSum * (effectiveStrain / strain);
+                return modulusHat * ((1 - m.nu) * effectiveStrain + m.nu * effectiveTransverseStrainSum);
+            }
+        }
+        return 0.0f;
+    }
+    // VX3_Link::updateStrain (VX3_Link.cu:232-268): a non-linear material remembers its largest strain and backs off along E
+    float update_strain(int l, const VX3B_LinkMaterial &m, float axialStrain) {
+        const float tss = 0.0f;
+        strain[l] = axialStrain;
+        if (m.linear) {
+            if (axialStrain > maxStrain[l])
+                maxStrain[l] = axialStrain;
+            return material_stress(m, axialStrain, tss, false);
+        }
+        float returnStress;
+        if (axialStrain > maxStrain[l]) { // new territory on the stress/strain curve
+            maxStrain[l] = axialStrain;
+            returnStress = material_stress(m, axialStrain, tss, false);
+            if (m.nu != 0.0f)
+                strainOffset[l] = maxStrain[l] - material_stress(m, axialStrain, 0.0f, false) / (m.eHat * (1 - m.nu));
+            else
+                strainOffset[l] = maxStrain[l] - returnStress / m.E;
+        } else { // backed off: linear with a strain offset according to the maximum plastic deformation
+            float relativeStrain = axialStrain - strainOffset[l];
+            if (m.nu != 0.0f)
+                returnStress = material_stress(m, relativeStrain, tss, true);
+            else
+                returnStress = m.E * relativeStrain;
+        }
+        return returnStress;
+    }
+
     void update_link(int l) { // VX3_Link.cu:135-218
         const VX3B_LinkMaterial &m = lm[lmat[l]];
         int vn = lneg[l], vp = lpos[l], axis = laxis[l];
@@ -407,12 +471,8 @@ struct World {
         a2v[l] = th2;
         V3 dPos2 = 0.5 * (d2 - oldPos2), dA1 = 0.5 * (th1 - oldA1), dA2 = 0.5 * (th2 - oldA2);
 
-        // updateStrain, linear material with nu == 0 (VX3_Link.cu:220-231, VX3_Material.cu:90-99)
         float eps = (float)(d2.x / restLen[l]);
-        strain[l] = eps;
-        if (eps > maxStrain[l])
-            maxStrain[l] = eps;
-        float stress = (m.epsilonFail != -1.0f && eps > m.epsilonFail) ? 0.0f : m.E * eps;
+        float stress = update_strain(l, m, eps);
         if (m.epsilonFail != -1.0f && maxStrain[l] > m.epsilonFail) { // isFailed(): all four outputs zero
             fNeg[l] = fPos[l] = mNeg[l] = mPos[l] = V3{};
             return;

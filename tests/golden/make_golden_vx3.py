@@ -39,6 +39,9 @@ CASES = {
     "vx3ref_pile_k3c4_600": (W.contact_pile_vxa(k=3, cube=4), None, 600, (260,), False),
     "vx3ref_forcefield_800": (W.force_field_vxa(), None, 800, (1, 100), False),
     "vx3ref_example_1000": (open(os.path.join(ROOT, "tests", "data", "example.vxa")).read(), None, 1000, (), False),
+    # bilinear + data-model materials bent past their yield points and swinging back; the same with Poisson's ratio 0.3
+    "vx3ref_plastic_beam_6000": (W.plastic_beam_vxa(), None, 6000, (1000, 3000), False),
+    "vx3ref_plastic_beam_poisson_6000": (W.plastic_beam_vxa(volume_effects=True, nu=0.3), None, 6000, (1000, 3000), False),
     "vx3ref_memleaking_bot0000_1000": (_read("d.memleaking_data1", "base.vxa"), _read("d.memleaking_data1", "bot_0000.vxd"), 1000, (300,), False),
 }
 for _b in CIRCLE_PUSH_BOTS:
@@ -46,7 +49,7 @@ for _b in CIRCLE_PUSH_BOTS:
     CASES[f"vx3ref_circle_push_{_b}_1000"] = (_read("e.circle_push_data901", "base.vxa"), _read("e.circle_push_data901", _b + ".vxd"), 1000, (300,), False)
     CASES[f"vx3ref_circle_push_{_b}_full"] = (_read("e.circle_push_data901", "base.vxa"), _read("e.circle_push_data901", _b + ".vxd"), 1000000, (), True)
 
-LINK_STATE_CASES = ("vx3ref_xeno7_contact_500", "vx3ref_example_1000", "vx3ref_forcefield_800")  # link history kept for these only (size)
+LINK_STATE_CASES = ("vx3ref_xeno7_contact_500", "vx3ref_example_1000", "vx3ref_forcefield_800", "vx3ref_plastic_beam_6000", "vx3ref_plastic_beam_poisson_6000")  # link history kept for these only (size)
 KEEP = ("scalars", "pos", "orient", "linMom", "angMom", "pairs")
 SCALARS = ("currentTime", "dt", "OptimalDt", "steps", "collisionCount", "fitness_score", "com_x", "com_y", "com_z", "initial_com_x", "initial_com_y",
            "initial_com_z", "recentAngle", "targetCloseness", "numClosePairs", "angleSampleTimes", "diverged", "CurStepCount")

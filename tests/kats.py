@@ -435,8 +435,43 @@ def kinetic_friction():
     return build, drive
 
 
+def deformable_material():
+    """TEST(CVoxelyze, deformableMaterial), tVoxelyze.h:845-886: a 5x3x3 bar of a BILINEAR material (E 1e6, plastic modulus 5e5, yield
+    stress 1e5), clamped at x = 0, pulled with 0.2 N per voxel at x = 4 for 400 steps - past the yield point - then released for
+    250 steps: the permanent set of voxel (4,1,1) is 4e-4 +- 1e-7 m (strain offset of VX_Link.cpp updateStrain)."""
+    def build():
+        m = gv.Model.new(0.001)
+        mat = m.add_material(1e6, 1e3, internal_damping=1.0, global_damping=0.2)
+        m.set_material_bilinear(mat, 1e6, 5e5, 1e5)
+        m.set_world_param("dt_frac", 1.0)
+        for i in range(5):
+            for j in range(3):
+                for k in range(3):
+                    m.set_voxel(mat, i, j, k)
+                    if i == 0:
+                        m.set_fixed(i, j, k, 63)
+                    if i == 4:
+                        m.set_force(i, j, k, force=(0.2, 0.0, 0.0))
+        m.finalize()
+        return m
+
+    def drive(world, tol=0):
+        idx = lambda i, j, k: (i * 3 + j) * 3 + k  # noqa: E731
+        world.run(400)
+        stretched = world.state()["pos"][idx(4, 1, 1)][0] - 0.004
+        assert stretched > 6e-4  # beyond the elastic limit: yield strain 0.1 over four links = 4e-4
+        for j in range(3):
+            for k in range(3):
+                world.set_force(idx(4, j, k), force=(0.0, 0.0, 0.0))
+        world.run(250)
+        x = float(np.float32(world.state()["pos"][idx(4, 1, 1)][0] - 0.004))
+        assert abs(x - 4e-4) < 1e-7 + tol * 4e-4, x
+    return build, drive
+
+
 def scripted_kats():
-    k = [("freqency", frequency()), ("largeDeformation", large_deformation()), ("impulse", impulse()), ("kineticFriction", kinetic_friction())]
+    k = [("freqency", frequency()), ("largeDeformation", large_deformation()), ("impulse", impulse()), ("kineticFriction", kinetic_friction()),
+         ("deformableMaterial", deformable_material())]
     for g, mu, load, slides in ((1.0, 1.0, 0.9, False), (1.0, 1.0, 1.1, True), (2.0, 1.0, 1.9, False), (2.0, 1.0, 2.1, True),
                                 (1.0, 2.0, 1.9, False), (1.0, 2.0, 2.1, True)):
         k.append((f"staticFriction-g{g:g}-mu{mu:g}-{load:g}N", static_friction(g, mu, load, slides)))

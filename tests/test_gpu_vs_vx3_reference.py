@@ -225,3 +225,47 @@ def test_full_generation_32_worlds_against_the_oracle():
         assert abs(len(ctx.collision_pairs(i)) - len(want.collision_pairs())) <= 2, i
     print("worst relative position error over 32 worlds (x, y, z):", worst)
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", [0, STREAM, RESIDENT, BRICK])  # every request is served by the streaming kernels (non-linear worlds)
+@pytest.mark.parametrize("name", ["vx3ref_plastic_beam_6000", "vx3ref_plastic_beam_poisson_6000"])
+def test_nonlinear_materials_and_poissons_ratio_against_the_vx3_reference(name, path):
+    """bilinear + data-model materials bent past their yield points and swinging back (strain offset), and the same
+    with Poisson's ratio 0.3 as Voxelyze3 applies it (eHat, the time step from eHat): fp64 1e-5 / fp32 1e-3 of the displacement."""
+    vxa, _, steps, checkpoints, _ = CASES[name]
+    g = gold(name)
+    m = gv.Model.from_vxa(vxa)
+    for precision, tol in ((gv.FP64, 1e-5), (gv.FP32, 1e-3)):
+        ctx = gv.Context(0, precision)
+        ctx.set_option("path", path)
+        ctx.upload([m])
+        done = 0
+        for c in list(checkpoints) + [steps]:
+            ctx.run(c - done)
+            done = c
+            sfx = "" if c == steps else f"_{c}"
+            got = ctx.read_state(0)
+            assert np.abs(got["pos"] - g["pos" + sfx]).max() / disp_scale(m, g["pos" + sfx]) < tol, (precision, c)
+        assert ctx.results()[0].dt == g["scalars"][0, 1]
+        gl = ctx.read_links(0)
+        assert O.rel_err(gl["pos2"], g["link_state"][:, 0:3]) < 10 * tol
+        ctx.close()
+
+
+def test_nonlinear_world_in_a_batch_of_ordinary_worlds():
+    """a batch with one non-linear world is stepped by the streaming kernels as a whole; every world still equals its oracle run"""
+    models = [gv.Model.from_vxa(W.small_block_vxa()), gv.Model.from_vxa(W.plastic_beam_vxa()), gv.Model.from_vxa(W.xenobot_base_vxa(), W.xenobot_vxd(3))]
+    ctx = gpu_run(models, 400, gv.FP64, 0)
+    for i, m in enumerate(models):
+        want = O.OracleWorld(m)
+        want.run(400)
+        ref = want.state()
+        assert np.abs(ctx.read_state(i)["pos"] - ref["pos"]).max() / disp_scale(m, ref["pos"]) < 1e-5, i
+    ctx.close()
+    # and the context goes back to the requested path with the next, ordinary batch
+    ctx = gpu_run(models[:1], 10, gv.FP32, RESIDENT)
+    ctx.upload([models[0], models[2]])
+    ctx.run(10)
+    assert ctx.timing()[1] <= 6  # resident: a handful of launches, not 3 per step
+    ctx.close()
