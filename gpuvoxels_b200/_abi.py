@@ -24,7 +24,9 @@ class VoxelMaterial(C.Structure):
         "epsilonFail", "gravMult", "mass", "massInverse", "sqrtMass", "momentInertia", "momentInertiaInverse",
         "_2xSqMxExS", "_2xSqIxExSxSxS")] + [
         ("nomSize", C.c_double), ("Cilia", C.c_double)] + [(n, C.c_int32) for n in (
-            "matid", "fixed", "isTarget", "isMeasured", "sticky", "linear")] + [("rgba", C.c_uint32)]
+            "matid", "fixed", "isTarget", "isMeasured", "sticky", "linear")] + [("rgba", C.c_uint32), ("isPaceMaker", C.c_int32), ("padSignal", C.c_int32)] + [
+        (n, C.c_double) for n in ("PaceMakerPeriod", "signalValueDecay", "signalTimeDelay", "inactivePeriod", "RemoveFromSimulationAfterThisManySeconds",
+                                  "TurnOnThermalExpansionAfterThisManySeconds", "TurnOnCiliaAfterThisManySeconds")]
 
 
 MAX_SS_POINTS = 16
@@ -56,6 +58,9 @@ class WorldDesc(C.Structure):
         ("stop_condition", Token * MAX_TOKENS), ("fitness", Token * MAX_TOKENS), ("force_field", (Token * MAX_TOKENS) * 3),
         ("ghost", C.POINTER(C.c_uint8)),
         ("record_step_size", C.c_int32), ("record_voxel", C.c_int32), ("record_link", C.c_int32),
+        ("enable_signals", C.c_int32), ("enable_attach", C.c_int32), ("enable_detach", C.c_int32), ("safety_guard", C.c_int32),
+        ("secondary_experiment", C.c_int32), ("pad_dyn", C.c_int32), ("reinitialize_initial_position_after", C.c_double),
+        ("attach_condition", (Token * MAX_TOKENS) * 5),
     ]
 
 

@@ -99,6 +99,14 @@ static VX3B_VoxelMaterial derive_voxel_material(const MatInput &in, float nu, do
     o.isTarget = in.isTarget;
     o.isMeasured = in.isMeasured;
     o.sticky = in.sticky;
+    o.isPaceMaker = in.isPaceMaker;
+    o.PaceMakerPeriod = in.PaceMakerPeriod;
+    o.signalValueDecay = in.signalValueDecay;
+    o.signalTimeDelay = in.signalTimeDelay;
+    o.inactivePeriod = in.inactivePeriod;
+    o.RemoveFromSimulationAfterThisManySeconds = in.removeAfter;
+    o.TurnOnThermalExpansionAfterThisManySeconds = in.thermalAfter;
+    o.TurnOnCiliaAfterThisManySeconds = in.ciliaAfter;
     o.linear = 1;
     // CVX_MaterialVoxel::updateDerived (old/VX_MaterialVoxel.cpp:58-80)
     double volume = nomSize * nomSize * nomSize;
@@ -348,6 +356,24 @@ bool HostModel::finalize(std::string *err) {
         }
         linkMat[l] = found;
     }
+    if (enableAttach) {
+        // Attachment links two voxels of one sticky material (VX3_VoxelyzeKernel.cu:734-741) with the material
+        // VX3_VoxelyzeKernel::combinedMaterial finds or makes on the device (:515-528); list those up front, after the used ones
+        for (int a = 0; a < (int)voxelMats.size(); a++) {
+            if (!voxelMats[a].sticky || voxelMats[a].fixed)
+                continue;
+            bool have = false;
+            for (auto &pr : linkMatPairs)
+                have = have || (pr.first == a && pr.second == a);
+            if (have)
+                continue;
+            linkMatPairs.emplace_back(a, a);
+            VX3B_LinkMaterial lm;
+            if (!derive_link_material(voxelMats[a], mats[a], voxelMats[a], mats[a], a, a, &lm, err))
+                return false;
+            linkMats.push_back(lm);
+        }
+    }
     auto pad = [](std::vector<VX3B_Token> &t) {
         if (t.size() > VX3B_MAX_TOKENS)
             return false;
@@ -356,7 +382,8 @@ bool HostModel::finalize(std::string *err) {
         t.resize(VX3B_MAX_TOKENS, e);
         return true;
     };
-    if (!pad(stopCondition) || !pad(fitness) || !pad(forceField[0]) || !pad(forceField[1]) || !pad(forceField[2])) {
+    if (!pad(stopCondition) || !pad(fitness) || !pad(forceField[0]) || !pad(forceField[1]) || !pad(forceField[2]) || !pad(attachCondition[0]) ||
+        !pad(attachCondition[1]) || !pad(attachCondition[2]) || !pad(attachCondition[3]) || !pad(attachCondition[4])) {
         if (err)
             *err = "formula longer than VX3B_MAX_TOKENS";
         return false;
@@ -408,6 +435,14 @@ void HostModel::fillDesc(VX3B_WorldDesc *d) const {
     memcpy(d->fitness, fitness.data(), sizeof(d->fitness));
     for (int k = 0; k < 3; k++)
         memcpy(d->force_field[k], forceField[k].data(), sizeof(d->force_field[k]));
+    for (int k = 0; k < 5; k++)
+        memcpy(d->attach_condition[k], attachCondition[k].data(), sizeof(d->attach_condition[k]));
+    d->enable_signals = enableSignals;
+    d->enable_attach = enableAttach;
+    d->enable_detach = enableDetach;
+    d->safety_guard = safetyGuard;
+    d->secondary_experiment = secondaryExperiment;
+    d->reinitialize_initial_position_after = reinitializeAfter;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -668,13 +703,16 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
             M->volumeEffects = get_bool(feat, "VolumeEffectsEnabled", false);
     }
     M->enableCollision = ptree_int(*vxa, "Simulator.AttachDetach.EnableCollision", 1) != 0;
-    if (ptree_int(*vxa, "Simulator.AttachDetach.EnableAttach", 0) || ptree_int(*vxa, "Simulator.AttachDetach.EnableDetach", 0) ||
-        ptree_int(*vxa, "Simulator.EnableSignals", 0) || ptree_int(*vxa, "Simulator.SecondaryExperiment", 0)) {
-        if (err)
-            *err = "EnableAttach / EnableDetach / EnableSignals / SecondaryExperiment change topology during the run; "
-                   "the static-topology fused path does not run them (SURVEY.md §8f-3)";
-        return nullptr;
-    }
+    // signals and topology changes (VX3_SimulationManager.cu:325-371): stepped by the dynamic-topology kernel
+    M->enableAttach = ptree_int(*vxa, "Simulator.AttachDetach.EnableAttach", 0) != 0;
+    M->enableDetach = ptree_int(*vxa, "Simulator.AttachDetach.EnableDetach", 0) != 0;
+    M->safetyGuard = ptree_int(*vxa, "Simulator.AttachDetach.SafetyGuard", 500);
+    M->enableSignals = ptree_int(*vxa, "Simulator.EnableSignals", 0) != 0;
+    M->secondaryExperiment = ptree_int(*vxa, "Simulator.SecondaryExperiment", 0) != 0;
+    M->reinitializeAfter = ptree_double(*vxa, "Simulator.ReinitializeInitialPositionAfterThisManySeconds", 0.0);
+    for (int c = 0; c < 5; c++)
+        if (!parse_math_tree(vxa->find("Simulator.AttachDetach.AttachCondition.Condition_" + std::to_string(c)), M->attachCondition[c], err))
+            return nullptr;
     M->enableCilia = ptree_int(*vxa, "Simulator.EnableCilia", 0) != 0;
     M->enableExpansion = ptree_int(*vxa, "Simulator.EnableExpansion", 0) != 0;
     M->savePositions = ptree_int(*vxa, "Simulator.SavePositionOfAllVoxels", 0) != 0;
@@ -824,6 +862,14 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
             m.isTarget = get_int(mech, "isTarget", 0) != 0;
             m.isMeasured = get_int(mech, "isMeasured", 1);
             m.sticky = get_int(mech, "Sticky", 0) != 0;
+            m.isPaceMaker = get_int(mech, "isPaceMaker", 0) != 0;
+            m.PaceMakerPeriod = get_double(mech, "PaceMakerPeriod", 0);
+            m.signalValueDecay = get_double(mech, "signalValueDecay", 0.9);
+            m.signalTimeDelay = get_double(mech, "signalTimeDelay", 0.03);
+            m.inactivePeriod = get_double(mech, "inactivePeriod", 0.03);
+            m.removeAfter = get_double(mech, "RemoveFromSimulationAfterThisManySeconds", 0.0);
+            m.thermalAfter = get_double(mech, "TurnOnThermalExpansionAfterThisManySeconds", 0.0);
+            m.ciliaAfter = get_double(mech, "TurnOnCiliaAfterThisManySeconds", 0.0);
             {
                 const XmlNode *disp = pm->child("Display"); // CVXC_Material::ReadXML: Red/Green/Blue/Alpha in 0..1
                 auto chan = [&](const char *name, double dflt) {

@@ -29,6 +29,10 @@ struct MatInput { // CVX_Material state before derivation (floats, as the refere
     float nuMemory = 0.0f; // Poisson's ratio as given (muMemory, VX_Sim.cpp:85)
     double Cilia = 0;
     int matid = 0, fixed = 0, isTarget = 0, isMeasured = 1, sticky = 0;
+    // signals and secondary-experiment switches (defaults of CVXC_Material::ReadXML, VXA/VX_Object.cpp:1420-1430)
+    int isPaceMaker = 0;
+    double PaceMakerPeriod = 0, signalValueDecay = 0.9, signalTimeDelay = 0.03, inactivePeriod = 0.03;
+    double removeAfter = 0, thermalAfter = 0, ciliaAfter = 0;
 };
 
 bool mat_set_model_linear(MatInput &m, float youngsModulus, float failureStress, std::string *err);
@@ -59,7 +63,10 @@ struct HostModel {
     bool savePositions = false;
     int recordStepSize = 0, recordVoxel = 1, recordLink = 0; // VXA.Simulator.RecordHistory (VX3_SimulationManager.cu:344-346)
     double maxDistPair = 0;
-    std::vector<VX3B_Token> stopCondition, fitness, forceField[3];
+    std::vector<VX3B_Token> stopCondition, fitness, forceField[3], attachCondition[5];
+    bool enableSignals = false, enableAttach = false, enableDetach = false, secondaryExperiment = false;
+    int safetyGuard = 500;
+    double reinitializeAfter = 0;
 
     // --- derived (finalize) ---------------------------------------------------------------
     std::vector<int32_t> linkNeg, linkPos, linkMat;

@@ -23,6 +23,10 @@ def _mat_xml(i, m):
         extra += "<isTarget>1</isTarget>"
     if m["fixed"]:
         extra += "<Fixed>1</Fixed>"
+    for tag in ("Sticky", "isPaceMaker", "PaceMakerPeriod", "signalValueDecay", "signalTimeDelay", "inactivePeriod", "RemoveFromSimulationAfterThisManySeconds",
+                "TurnOnThermalExpansionAfterThisManySeconds", "TurnOnCiliaAfterThisManySeconds"):
+        if tag in m and m[tag]:
+            extra += f"<{tag}>{m[tag]!r}</{tag}>"
     if not m["is_measured"]:
         extra += "<isMeasured>0</isMeasured>"
     ss = ""
@@ -75,16 +79,29 @@ FITNESS_XY_DISTANCE = ("<mtSQRT><mtADD><mtMUL><mtVAR>x</mtVAR><mtVAR>x</mtVAR></
 def vxa_document(materials, structure, lattice_dim=0.01, dt_frac=0.9, bond_damping=1.0, col_damping=0.8, slow_damping=0.01,
                  grav_acc=-9.81, floor=True, temp_enabled=True, temp_amplitude=0.0, temp_base=25.0, vary_temp=False,
                  temp_period=0.1, enable_collision=None, enable_cilia=False, enable_expansion=False, stop_formula=None,
-                 fitness_formula=None, force_field=None, save_positions=False, volume_effects=False):
+                 fitness_formula=None, force_field=None, save_positions=False, volume_effects=False, enable_signals=False, enable_attach=False,
+                 enable_detach=False, attach_conditions=None, safety_guard=None, secondary_experiment=False, reinitialize_after=None):
     sim = []
+    if enable_signals:
+        sim.append("<EnableSignals>1</EnableSignals>")
+    if secondary_experiment:
+        sim.append("<SecondaryExperiment>1</SecondaryExperiment>")
+    if reinitialize_after is not None:
+        sim.append(f"<ReinitializeInitialPositionAfterThisManySeconds>{reinitialize_after!r}</ReinitializeInitialPositionAfterThisManySeconds>")
     if enable_cilia:
         sim.append("<EnableCilia>1</EnableCilia>")
     if enable_expansion:
         sim.append("<EnableExpansion>1</EnableExpansion>")
     if save_positions:
         sim.append("<SavePositionOfAllVoxels>1</SavePositionOfAllVoxels>")
-    if enable_collision is not None:
-        sim.append(f"<AttachDetach><EnableCollision>{int(enable_collision)}</EnableCollision></AttachDetach>")
+    if enable_collision is not None or enable_attach or enable_detach:
+        ad = f"<EnableCollision>{int(enable_collision if enable_collision is not None else 1)}</EnableCollision>"
+        ad += f"<EnableAttach>{int(enable_attach)}</EnableAttach><EnableDetach>{int(enable_detach)}</EnableDetach>"
+        if safety_guard is not None:
+            ad += f"<SafetyGuard>{int(safety_guard)}</SafetyGuard>"
+        if attach_conditions:
+            ad += "<AttachCondition>" + "".join(f"<Condition_{i}>{c}</Condition_{i}>" for i, c in enumerate(attach_conditions)) + "</AttachCondition>"
+        sim.append(f"<AttachDetach>{ad}</AttachDetach>")
     if fitness_formula:
         sim.append(formula_xml("FitnessFunction", fitness_formula))
     if force_field:
@@ -338,3 +355,43 @@ def plastic_beam_vxa(volume_effects=False, nu=0.0, DENS=2e4):
             material(name="anchor", E=5e7, density=1e6, nu=nu, fixed=1)]
     return vxa_document(mats, structure_xml(data), lattice_dim=0.01, dt_frac=0.5, bond_damping=0.3, slow_damping=0.002, grav_acc=-9.81, floor=False,
                         enable_collision=False, volume_effects=volume_effects)
+
+
+
+def sticky_pebbles_vxa(safety_guard=50):
+    """Attachment (VX3_VoxelyzeKernel.cu:718-831): a 2x2x1 raft of sticky voxels resting on the floor and two sticky pebbles of the same
+    material dropped onto it from two cells up, one of them off-centre.  On contact they grow links to the raft (and, once they lean
+    together, possibly to each other); a new link eases in over SafetyGuard steps.  A pace-maker voxel in the raft fires signals that
+    travel along the links, old and new, and modulate the cilia push of the pebbles (ShiftCiliaForce)."""
+    data = np.zeros((4, 3, 3), dtype=int)
+    data[0, 0:2, 0:2] = 1
+    data[0, 0, 0] = 2      # pace maker (different material: its links to the raft use the 1-2 link material)
+    data[3, 0, 0] = 1      # pebble A above the pace maker
+    data[3, 1, 1] = 1      # pebble B above the opposite corner
+    mats = [material(name="sticky", E=2e6, density=1e6, Sticky=1, cilia=0.2, signalValueDecay=0.8, signalTimeDelay=0.004, inactivePeriod=0.01),
+            material(name="pacer", E=2e6, density=1e6, isPaceMaker=1, PaceMakerPeriod=0.05, signalValueDecay=0.8, signalTimeDelay=0.004, inactivePeriod=0.01)]
+    Z, Y, X = data.shape
+    cilia = np.zeros((Z, Y, X, 3))
+    cilia[3, 0, 0] = (0.3, 0.1, 0.0)
+    shift = np.zeros((Z, Y, X, 3))
+    shift[..., 0] = 0.002
+    shift[data == 0] = 0
+    st = structure_xml(data, base_cilia=cilia).replace("</Structure>", "<ShiftCiliaForce>" + "".join(
+        "<Layer><![CDATA[" + ", ".join(repr(float(p)) for p in shift[z].reshape(-1)) + "]]></Layer>" for z in range(Z)) + "</ShiftCiliaForce></Structure>")
+    return vxa_document(mats, st, dt_frac=0.5, grav_acc=-9.81, floor=True, enable_collision=True, enable_cilia=True, enable_signals=True, enable_attach=True,
+                        attach_conditions=[mt_const(1)], safety_guard=safety_guard)
+
+
+def breaking_chain_vxa():
+    """Detachment (VX3_VoxelyzeKernel.cu:946-967) and removal (:365-399): a vertical chain hanging from a `Fixed` voxel whose middle
+    material fails at 2 % strain under the weight below it - the failed link lets go, the lower part drops to the floor - and whose
+    bottom material is taken out of the simulation after 0.03 s (SecondaryExperiment); the initial position is re-initialised at 0.02 s."""
+    data = np.zeros((8, 1, 1), dtype=int)
+    data[7, 0, 0] = 4
+    data[5:7, 0, 0] = 1
+    data[3:5, 0, 0] = 2
+    data[1:3, 0, 0] = 3
+    mats = [material(name="strong", E=1e7, density=1e6), material(name="weak", E=2e5, density=1e6, mat_model=1, fail_stress=3.5e3),
+            material(name="vanishing", E=1e7, density=1.5e6, RemoveFromSimulationAfterThisManySeconds=0.03), material(name="anchor", E=1e7, density=1e6, fixed=1)]
+    return vxa_document(mats, structure_xml(data), dt_frac=0.5, bond_damping=0.5, grav_acc=-9.81, floor=True, enable_collision=True, enable_detach=True,
+                        secondary_experiment=True, reinitialize_after=0.02, fitness_formula=mt_var("z"))

@@ -79,6 +79,11 @@ typedef struct VX3B_VoxelMaterial {
     int32_t matid;               /* palette ID reported in <mats> */
     int32_t fixed, isTarget, isMeasured, sticky, linear; /* linear = 0: bilinear or data model (the link materials carry the curves) */
     uint32_t rgba;               /* display colour r | g << 8 | b << 16 | a << 24, each (int)(VXA value * 255) (VX_Object.h:419-425): .history only */
+    /* signals (VX3_Voxel.cu:279-348; defaults of VXA/VX_Object.cpp:1420-1424) and the "secondary experiment" switches
+     * (VX3_VoxelyzeKernel.cu:365-399, 632-634, 852-854); times in seconds, 0 = off */
+    int32_t isPaceMaker, padSignal;
+    double PaceMakerPeriod, signalValueDecay, signalTimeDelay, inactivePeriod;
+    double RemoveFromSimulationAfterThisManySeconds, TurnOnThermalExpansionAfterThisManySeconds, TurnOnCiliaAfterThisManySeconds;
 } VX3B_VoxelMaterial;
 
 /* Combined material of a voxel pair: CVX_MaterialLink::updateAll/updateDerived
@@ -145,6 +150,17 @@ typedef struct VX3B_WorldDesc {
 
     /* VXA.Simulator.RecordHistory (VX3_SimulationManager.cu:344-346): 0 = no .history stream */
     int32_t record_step_size, record_voxel, record_link;
+
+    /* Topology-changing features and signals (VX3_SimulationManager.cu:325-371).  Worlds that use any of them are
+     * stepped by the engine's dynamic-topology kernel, in the serial thread order of oracle/_ref/vx3_ref. */
+    int32_t enable_signals;      /* VXA.Simulator.EnableSignals: target hits and pace makers raise signals that travel along links */
+    int32_t enable_attach;       /* AttachDetach.EnableAttach: sticky voxels of one material that touch grow a link */
+    int32_t enable_detach;       /* AttachDetach.EnableDetach: failed links let go */
+    int32_t safety_guard;        /* AttachDetach.SafetyGuard: steps a new link's forces are scaled by 0.01 (VX3_Link.cu:206-213) */
+    int32_t secondary_experiment; /* VXA.Simulator.SecondaryExperiment: removal of materials / re-initialised initial position */
+    int32_t pad_dyn;
+    double reinitialize_initial_position_after; /* seconds; with secondary_experiment */
+    VX3B_Token attach_condition[5][VX3B_MAX_TOKENS]; /* all five must be > 0 at a voxel's position for it to attach; empty = CONST 0... see host */
 } VX3B_WorldDesc;
 
 /* Numeric fields of VX3_SimulationResult (VX3_SimulationResult.h:4-24). */

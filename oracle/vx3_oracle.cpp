@@ -194,7 +194,7 @@ struct World {
     std::vector<int16_t> lattice;
     std::vector<int32_t> vmat, lneg, lpos, lmat;
     std::vector<uint8_t> laxis, dof;
-    std::vector<double> phase, baseCilia, extT, extR;
+    std::vector<double> phase, baseCilia, shiftCilia, extT, extR;
     std::vector<float> extF, extM;
     std::vector<VX3B_VoxelMaterial> vm;
     std::vector<VX3B_LinkMaterial> lm;
@@ -207,6 +207,15 @@ struct World {
     std::vector<uint8_t> staticFriction;
     std::vector<int32_t> vlinks; // [nv][6]
     std::vector<int32_t> surface;
+    // signals and topology changes.  The reference's kernels race here; this restatement runs every "thread" of a
+    // launch to completion in index order - the schedule of oracle/_ref/vx3_ref, ONE valid execution of the reference's code.
+    std::vector<uint8_t> vremoved, vEnableAttach, lremoved, ldetached, matRemoved;
+    std::vector<int32_t> lNewLink;
+    std::vector<double> localSignal, localSignalDt, inactiveUntil, sigValue, sigActiveTime, paceMakerNext;
+    bool surfaceChanged = true; // CUDA_Simulation sets it before the first step (VX3_SimulationManager.cu:22)
+    bool initialPositionReinitialized = false;
+    std::vector<int32_t> targets; // registerTargets (VX3_VoxelyzeKernel.cu:536-543)
+    bool dynamic() const { return d.enable_signals || d.enable_attach || d.enable_detach || d.secondary_experiment; }
     // link state
     std::vector<V3> pos2, a1v, a2v, fNeg, fPos, mNeg, mPos;
     std::vector<uint8_t> smallAngle, velValid;
@@ -254,6 +263,7 @@ struct World {
         };
         cp(in->phase_offset, nv, phase);
         cp(in->base_cilia, 3 * nv, baseCilia);
+        cp(in->shift_cilia, 3 * nv, shiftCilia);
         cp(in->ext_translation, 3 * nv, extT);
         cp(in->ext_rotation, 3 * nv, extR);
         if (in->dof_fixed)
@@ -312,6 +322,17 @@ struct World {
         strain.assign(nl, 0.0f);
         maxStrain.assign(nl, 0.0f);
         strainOffset.assign(nl, 0.0f);
+        vremoved.assign(nv, 0);
+        vEnableAttach.assign(nv, 1); // VX3_Voxel.h: enableAttach = true
+        lremoved.assign(nl, 0);
+        ldetached.assign(nl, 0);
+        lNewLink.assign(nl, 0);
+        matRemoved.assign(in->num_voxel_mats, 0);
+        for (auto *a : {&localSignal, &localSignalDt, &inactiveUntil, &sigValue, &sigActiveTime, &paceMakerNext})
+            a->assign(nv, 0.0);
+        for (int v = 0; v < nv; v++)
+            if (M(v).isTarget)
+                targets.push_back(v);
         restLen.resize(nl);
         for (int l = 0; l < nl; l++)
             update_rest_length(l);
@@ -372,6 +393,8 @@ struct World {
         if (!d.vary_temp_enabled || !(d.temp_period > 0))
             return;
         for (int v = 0; v < nv; v++) {
+            if (vremoved[v] || (vx3() && M(v).TurnOnThermalExpansionAfterThisManySeconds > t))
+                continue;
             if (vx3() && M(v).fixed)
                 continue;
             double T = d.temp_amplitude * sin(2 * 3.1415926f * (t / d.temp_period + phase[v]));
@@ -507,14 +530,23 @@ struct World {
         fPos[l] = to_axis_original(FP, axis);
         mNeg[l] = to_axis_original(MN, axis);
         mPos[l] = to_axis_original(MP, axis);
+        if (lNewLink[l]) { // a link made by attachment eases in: 1 % of its forces for SafetyGuard steps (VX3_Link.cu:206-213)
+            fNeg[l] = fNeg[l] * 0.01;
+            fPos[l] = fPos[l] * 0.01;
+            mNeg[l] = mNeg[l] * 0.01;
+            mPos[l] = mPos[l] * 0.01;
+            lNewLink[l] -= 1;
+        }
     }
 
-    void update_contacts() { // VX3_VoxelyzeKernel.cu:682-727, 833-843; VX3_Collision.cu:3-31
+    void update_contacts() { // VX3_VoxelyzeKernel.cu:682-831, 833-843; VX3_Collision.cu:3-31
         lastPairs.clear();
         int ns = (int)surface.size();
         for (int a = 0; a < ns; a++)
             for (int b = 0; b < a; b++) {
                 int v1 = surface[a], v2 = surface[b];
+                if (vremoved[v1] || vremoved[v2])
+                    continue;
                 const VX3B_VoxelMaterial &m1 = M(v1), &m2 = M(v2);
                 if (m1.fixed && m2.fixed)
                     continue;
@@ -532,31 +564,41 @@ struct World {
                 }
                 if (linked)
                     continue;
-                lastPairs.emplace_back(v1, v2);
-                float k1 = (float)(2 * m1.E * m1.nomSize), k2 = (float)(2 * m2.E * m2.nomSize); // penetrationStiffness
-                double stiff = 2.0f / (1.0f / k1 + 1.0f / k2);
-                double damp = 0.5f * (m1.zetaCollision * m1._2xSqMxExS + m2.zetaCollision * m2._2xSqMxExS);
-                V3 offset = pos[v2] - pos[v1];
-                double relDist = R - len(offset);
                 V3 force{};
-                if (relDist > 0) {
-                    V3 unit = normalized(offset);
-                    double relVel = dot(linMom[v1] * m1.massInverse, unit) - dot(linMom[v2] * m2.massInverse, unit);
-                    force = unit * (stiff * relDist + damp * relVel);
+                if (d.enable_collision) {
+                    lastPairs.emplace_back(v1, v2);
+                    float k1 = (float)(2 * m1.E * m1.nomSize), k2 = (float)(2 * m2.E * m2.nomSize); // penetrationStiffness
+                    double stiff = 2.0f / (1.0f / k1 + 1.0f / k2);
+                    double damp = 0.5f * (m1.zetaCollision * m1._2xSqMxExS + m2.zetaCollision * m2._2xSqMxExS);
+                    V3 offset = pos[v2] - pos[v1];
+                    double relDist = R - len(offset);
+                    if (relDist > 0) {
+                        V3 unit = normalized(offset);
+                        double relVel = dot(linMom[v1] * m1.massInverse, unit) - dot(linMom[v2] * m2.massInverse, unit);
+                        force = unit * (stiff * relDist + damp * relVel);
+                    }
+                    contactForce[v1] = contactForce[v1] + force;
+                    contactForce[v2] = contactForce[v2] - force;
+                    if ((m1.isTarget && !m2.isTarget) || (m2.isTarget && !m1.isTarget)) {
+                        collisionCount++;
+                        if (d.enable_signals) // the voxel that touched a target fires (VX3_VoxelyzeKernel.cu:706-716)
+                            receive_signal(m1.isTarget ? v2 : v1, 100, t, true);
+                    }
                 }
-                contactForce[v1] = contactForce[v1] + force;
-                contactForce[v2] = contactForce[v2] - force;
-                if ((m1.isTarget && !m2.isTarget) || (m2.isTarget && !m1.isTarget))
-                    collisionCount++;
+                if (d.enable_attach && try_attach(v1, v2)) { // a pair that has just been linked does not push apart this step
+                    contactForce[v1] = contactForce[v1] - force;
+                    contactForce[v2] = contactForce[v2] + force;
+                }
             }
         std::sort(lastPairs.begin(), lastPairs.end());
     }
 
-    void update_cilia() { // VX3_VoxelyzeKernel.cu:846-859 (localSignal == 0 while EnableSignals == 0)
+    void update_cilia() { // VX3_VoxelyzeKernel.cu:846-859
         for (int v : surface) {
-            if (M(v).Cilia == 0)
+            if (vremoved[v] || M(v).Cilia == 0 || M(v).TurnOnCiliaAfterThisManySeconds > t)
                 continue;
-            ciliaForce[v] = rotate(orient[v], V3{baseCilia[v * 3], baseCilia[v * 3 + 1], baseCilia[v * 3 + 2]});
+            V3 base{baseCilia[v * 3], baseCilia[v * 3 + 1], baseCilia[v * 3 + 2]}, shift{shiftCilia[v * 3], shiftCilia[v * 3 + 1], shiftCilia[v * 3 + 2]};
+            ciliaForce[v] = rotate(orient[v], base + localSignal[v] * shift);
         }
     }
 
@@ -680,6 +722,8 @@ struct World {
         }
         if (vx3() && floorOn && floor_penetration(v) >= 0 && staticFriction[v]) // VX3_Voxel.cu:258-264
             angMom[v] = V3{};
+        if (d.enable_signals)
+            step_signals(v);
     }
 
     void update_com() { // VX3_VoxelyzeKernel.cu:477-493
@@ -700,10 +744,6 @@ struct World {
             return;
         double R = d.max_dist_in_voxel_lengths_to_count_as_pair * d.vox_size, ret = 0;
         numClosePairs = 0;
-        std::vector<int> targets;
-        for (int v = 0; v < nv; v++)
-            if (M(v).isTarget)
-                targets.push_back(v);
         for (size_t i = 0; i < targets.size(); i++)
             for (size_t j = i + 1; j < targets.size(); j++) {
                 double dist = len(pos[targets[i]] - pos[targets[j]]);
@@ -732,7 +772,9 @@ struct World {
         if (dt == 0)
             return true;
         bool div = false;
-        for (int l = 0; l < nl; l++) {
+        for (int l = 0; l < nl; l++) { // gpu_update_links (VX3_VoxelyzeKernel.cu:566-581)
+            if (lremoved[l] || ldetached[l])
+                continue;
             if (vx3() && M(lneg[l]).fixed && M(lpos[l]).fixed)
                 continue;
             update_link(l);
@@ -741,15 +783,35 @@ struct World {
         }
         if (div)
             return false;
-        if (d.enable_collision)
+        if (dynamic() && surfaceChanged) { // VX3_VoxelyzeKernel.cu:282-286
+            surfaceChanged = false;
+            regenerate_surface();
+        }
+        if (d.enable_collision || d.enable_attach)
             update_contacts();
+        if (d.enable_detach)
+            update_detach();
         if (d.enable_cilia)
             update_cilia();
         double dtD = dt;
-        for (int v = 0; v < nv; v++) {
+        for (int v = 0; v < nv; v++) { // gpu_update_voxels (VX3_VoxelyzeKernel.cu:582-624)
+            if (vremoved[v])
+                continue;
             if (vx3() && M(v).fixed)
                 continue;
             step_voxel(v, dtD);
+            if (dynamic()) { // "sticky status": every AttachCondition formula > 0 at the voxel's position
+                vEnableAttach[v] = 0;
+                bool any = false, all = true;
+                for (int c = 0; c < 5 && all; c++) {
+                    if (d.attach_condition[c][0].op == VX3B_MT_END)
+                        continue; // (the reference evaluates an empty program to whatever its value stack last held: DESIGN.md section 8)
+                    any = true;
+                    all = eval_formula(d.attach_condition[c], pos[v].x, pos[v].y, pos[v].z, collisionCount, t, recentAngle, targetCloseness, numClosePairs,
+                                       nv) > 0;
+                }
+                vEnableAttach[v] = any && all;
+            }
         }
         if (vx3()) { // heading angle + closeness sampling (VX3_VoxelyzeKernel.cu:314-334)
             int cycle = (int)(d.temp_period / dt);
@@ -767,7 +829,203 @@ struct World {
                 compute_target_closeness();
             }
         }
+        if (d.secondary_experiment) { // VX3_VoxelyzeKernel.cu:336-350
+            remove_voxels();
+            if (!initialPositionReinitialized && d.reinitialize_initial_position_after < t) {
+                initialPositionReinitialized = true;
+                initialCom = com;
+                initialPos = pos;
+            }
+        }
         t += dt;
+        return true;
+    }
+
+    // regenerateSurfaceVoxels (VX3_VoxelyzeKernel.cu:495-513): a voxel is interior when all six link slots hold a link that is not
+    // detached (VX3_Voxel.cu:515-524); removed voxels are not listed
+    void regenerate_surface() {
+        surface.clear();
+        for (int v = 0; v < nv; v++) {
+            bool interior = true;
+            for (int k = 0; k < 6; k++) {
+                int l = vlinks[(size_t)v * 6 + k];
+                if (l < 0 || ldetached[l])
+                    interior = false;
+            }
+            if (!interior && !vremoved[v])
+                surface.push_back(v);
+        }
+    }
+    // gpu_update_detach (VX3_VoxelyzeKernel.cu:946-967): a failed link lets go of both voxels
+    void update_detach() {
+        for (int l = 0; l < nl; l++) {
+            if (lremoved[l] || ldetached[l])
+                continue;
+            const VX3B_LinkMaterial &m = lm[lmat[l]];
+            if (m.epsilonFail != -1.0f && maxStrain[l] > m.epsilonFail) {
+                ldetached[l] = 1;
+                for (int k = 0; k < 6; k++) {
+                    if (vlinks[(size_t)lneg[l] * 6 + k] == l)
+                        vlinks[(size_t)lneg[l] * 6 + k] = -1;
+                    if (vlinks[(size_t)lpos[l] * 6 + k] == l)
+                        vlinks[(size_t)lpos[l] * 6 + k] = -1;
+                }
+                surfaceChanged = true;
+            }
+        }
+    }
+    // removeVoxels (VX3_VoxelyzeKernel.cu:365-399): a material whose time has come takes its voxels and their links out of the run
+    void remove_voxels() {
+        for (int i = 0; i < (int)vm.size(); i++) {
+            const double after = vm[i].RemoveFromSimulationAfterThisManySeconds;
+            if (matRemoved[i] || !(after > 0) || !(after < t))
+                continue;
+            for (int v = 0; v < nv; v++) {
+                if (vmat[v] != i || vremoved[v])
+                    continue;
+                vremoved[v] = 1;
+                for (int k = 0; k < 6; k++) {
+                    const int l = vlinks[(size_t)v * 6 + k];
+                    if (l < 0)
+                        continue;
+                    lremoved[l] = 1;
+                    const int other = lneg[l] == v ? lpos[l] : lneg[l];
+                    for (int q = 0; q < 6; q++)
+                        if (vlinks[(size_t)other * 6 + q] == l) {
+                            vlinks[(size_t)other * 6 + q] = -1;
+                            break;
+                        }
+                    vlinks[(size_t)v * 6 + k] = -1;
+                }
+            }
+            matRemoved[i] = 1;
+            surfaceChanged = true;
+        }
+    }
+    // is_neighbor (VX3_VoxelyzeKernel.cu:651-680): v2 reachable from v1 over at most `depth` links
+    bool is_neighbor(int v1, int v2, int incoming, int depth) const {
+        if (v1 == v2)
+            return true;
+        if (depth <= 0)
+            return false;
+        for (int k = 0; k < 6; k++) {
+            const int l = vlinks[(size_t)v1 * 6 + k];
+            if (l < 0 || l == incoming)
+                continue;
+            if (is_neighbor(lneg[l] == v1 ? lpos[l] : lneg[l], v2, l, depth - 1))
+                return true;
+        }
+        return false;
+    }
+    // VX3_Voxel::receiveSignal (VX3_Voxel.cu:306-326)
+    void receive_signal(int v, double value, double activeTime, bool force) {
+        if (!force && inactiveUntil[v] > activeTime)
+            return;
+        if (value < 0.1)
+            return;
+        const VX3B_VoxelMaterial &m = M(v);
+        inactiveUntil[v] = activeTime + m.inactivePeriod;
+        localSignal[v] = value;
+        sigValue[v] = value * m.signalValueDecay;
+        if (sigValue[v] < 0.1)
+            sigValue[v] = 0;
+        sigActiveTime[v] = activeTime;
+    }
+    // propagateSignal, packMaker, localSignalDecay at the end of VX3_Voxel::timeStep (VX3_Voxel.cu:268-348)
+    void step_signals(int v) {
+        const VX3B_VoxelMaterial &m = M(v);
+        if (!(sigActiveTime[v] > t) && !(sigValue[v] < 0.1)) {
+            for (int k = 0; k < 6; k++) {
+                const int l = vlinks[(size_t)v * 6 + k];
+                if (l >= 0)
+                    receive_signal(lneg[l] == v ? lpos[l] : lneg[l], sigValue[v], t + m.signalTimeDelay, false);
+            }
+            sigValue[v] = 0;
+            sigActiveTime[v] = 0;
+            inactiveUntil[v] = t + 2 * m.signalTimeDelay + m.inactivePeriod;
+        }
+        if (m.isPaceMaker && !(paceMakerNext[v] > t)) {
+            receive_signal(v, 100, t, true);
+            paceMakerNext[v] = t + m.PaceMakerPeriod;
+        }
+        if (!(localSignalDt[v] > t)) {
+            if (localSignal[v] < 0.1)
+                localSignal[v] = 0;
+            else {
+                localSignal[v] = localSignal[v] * 0.9;
+                localSignalDt[v] = t + 0.01;
+            }
+        }
+    }
+    int find_link_material(int a, int b) const { // VX3_VoxelyzeKernel::combinedMaterial (VX3_VoxelyzeKernel.cu:515-528): either order
+        for (int k = 0; k < (int)lm.size(); k++)
+            if ((lm[k].mat1 == a && lm[k].mat2 == b) || (lm[k].mat1 == b && lm[k].mat2 == a))
+                return k;
+        return -1;
+    }
+    // the attachment half of handle_collision_attachment (VX3_VoxelyzeKernel.cu:718-831); returns true when a link was made
+    bool try_attach(int v1, int v2) {
+        if (!vEnableAttach[v1] || !vEnableAttach[v2])
+            return false;
+        const VX3B_VoxelMaterial &m1 = M(v1), &m2 = M(v2);
+        if (m1.fixed || m2.fixed || vmat[v1] != vmat[v2] || !m1.sticky)
+            return false;
+        if (is_neighbor(v1, v2, -1, 5))
+            return false;
+        V3 e = pos[v1] - pos[v2];
+        V3 ea = rotate_inv(orient[v1], V3{-e.x, -e.y, -e.z});
+        V3 f{fabs(ea.x), fabs(ea.y), fabs(ea.z)};
+        int axis, dir1, dir2;
+        bool reverse = false;
+        auto pick = [&](int a, double comp) {
+            axis = a;
+            if (comp < 0) {
+                dir1 = 2 * a + 1; // *_NEG
+                dir2 = 2 * a;
+                reverse = true;
+            } else {
+                dir1 = 2 * a;
+                dir2 = 2 * a + 1;
+            }
+        };
+        if (f.x >= f.y && f.x >= f.z)
+            pick(0, ea.x);
+        else if (f.y >= f.x && f.y >= f.z)
+            pick(1, ea.y);
+        else
+            pick(2, ea.z);
+        if (vlinks[(size_t)v1 * 6 + dir1] >= 0 || vlinks[(size_t)v2 * 6 + dir2] >= 0)
+            return false;
+        const int mat = find_link_material(vmat[v1], vmat[v2]);
+        if (mat < 0)
+            return false; // (the host model lists the same-material link material of every sticky material)
+        // VX3_Link(voxel1, dir1, voxel2, dir2): pVNeg = its second voxel, pVPos = its first (VX3_Link.cu:31-58)
+        const int neg = reverse ? v2 : v1, posv = reverse ? v1 : v2;
+        const int l = nl++;
+        lneg.push_back(neg);
+        lpos.push_back(posv);
+        laxis.push_back((uint8_t)axis);
+        lmat.push_back(mat);
+        vlinks[(size_t)v1 * 6 + dir1] = l;
+        vlinks[(size_t)v2 * 6 + dir2] = l;
+        pos2.push_back(V3{});
+        a1v.push_back(V3{});
+        a2v.push_back(V3{});
+        fNeg.push_back(V3{});
+        fPos.push_back(V3{});
+        mNeg.push_back(V3{});
+        mPos.push_back(V3{});
+        smallAngle.push_back(1);
+        velValid.push_back(0);
+        strain.push_back(0.0f);
+        maxStrain.push_back(0.0f);
+        strainOffset.push_back(0.0f);
+        lremoved.push_back(0);
+        ldetached.push_back(0);
+        lNewLink.push_back(d.safety_guard);
+        restLen.push_back(0.0);
+        update_rest_length(l);
+        surfaceChanged = true;
         return true;
     }
 
@@ -865,6 +1123,40 @@ int vx3o_read_links(vx3o_world *o, double *pos2_3, double *a1v3, double *a2v3, i
         if (flags)
             flags[l] = (w.smallAngle[l] ? 1 : 0) | (w.velValid[l] ? 2 : 0);
     }
+    return VX3B_OK;
+}
+
+// signals: [nv][6] = localSignal, localSignaldt, inactiveUntil, d_signal.value, d_signal.activeTime, packmakerNextPulse;
+// vflags: [nv][2] = removed, enableAttach
+int vx3o_read_signals(vx3o_world *o, double *sig6, int32_t *vflags2) {
+    if (!o)
+        return VX3B_ERR_ARG;
+    World &w = o->w;
+    for (int v = 0; v < w.nv; v++) {
+        if (sig6) {
+            double *q = sig6 + 6 * (size_t)v;
+            q[0] = w.localSignal[v], q[1] = w.localSignalDt[v], q[2] = w.inactiveUntil[v], q[3] = w.sigValue[v], q[4] = w.sigActiveTime[v], q[5] = w.paceMakerNext[v];
+        }
+        if (vflags2) {
+            vflags2[2 * v] = w.vremoved[v];
+            vflags2[2 * v + 1] = w.vEnableAttach[v];
+        }
+    }
+    return VX3B_OK;
+}
+// current link list (it grows by attachment): *n in = capacity in links, out = number of links; links6 = neg, pos, axis, removed,
+// detached, isNewLink per link
+int vx3o_read_topology(vx3o_world *o, int32_t *links6, int32_t *n) {
+    if (!o || !n)
+        return VX3B_ERR_ARG;
+    World &w = o->w;
+    const int cap = *n;
+    *n = w.nl;
+    if (links6)
+        for (int l = 0; l < w.nl && l < cap; l++) {
+            int32_t *q = links6 + 6 * (size_t)l;
+            q[0] = w.lneg[l], q[1] = w.lpos[l], q[2] = w.laxis[l], q[3] = w.lremoved[l], q[4] = w.ldetached[l], q[5] = w.lNewLink[l];
+        }
     return VX3B_OK;
 }
 

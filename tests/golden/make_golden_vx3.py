@@ -42,6 +42,12 @@ CASES = {
     # bilinear + data-model materials bent past their yield points and swinging back; the same with Poisson's ratio 0.3
     "vx3ref_plastic_beam_6000": (W.plastic_beam_vxa(), None, 6000, (1000, 3000), False),
     "vx3ref_plastic_beam_poisson_6000": (W.plastic_beam_vxa(volume_effects=True, nu=0.3), None, 6000, (1000, 3000), False),
+    # signals, attachment, detachment, removal: the reference's own c.signaling / h.target_only inputs and two synthetic worlds
+    "vx3ref_signaling_data1_3000": (_read("c.signaling_data1", "base.vxa"), _read("c.signaling_data1", "rob.vxd"), 3000, (1000, 2000), False),
+    "vx3ref_signaling_data2_3000": (_read("c.signaling_data2", "base.vxa"), _read("c.signaling_data2", "rob.vxd"), 3000, (1000, 2000), False),
+    "vx3ref_target_only_300": (_read("h.target_only_data1", "base.vxa"), _read("h.target_only_data1", "bot_0000.vxd"), 300, (), False),
+    "vx3ref_sticky_pebbles_3000": (W.sticky_pebbles_vxa(), None, 3000, (200, 600, 1500), False),
+    "vx3ref_breaking_chain_3000": (W.breaking_chain_vxa(), None, 3000, (300, 1000), False),
     "vx3ref_memleaking_bot0000_1000": (_read("d.memleaking_data1", "base.vxa"), _read("d.memleaking_data1", "bot_0000.vxd"), 1000, (300,), False),
 }
 for _b in CIRCLE_PUSH_BOTS:
@@ -51,6 +57,8 @@ for _b in CIRCLE_PUSH_BOTS:
 
 LINK_STATE_CASES = ("vx3ref_xeno7_contact_500", "vx3ref_example_1000", "vx3ref_forcefield_800", "vx3ref_plastic_beam_6000", "vx3ref_plastic_beam_poisson_6000")  # link history kept for these only (size)
 KEEP = ("scalars", "pos", "orient", "linMom", "angMom", "pairs")
+DYNAMIC_CASES = ("vx3ref_signaling_data1_3000", "vx3ref_signaling_data2_3000", "vx3ref_target_only_300", "vx3ref_sticky_pebbles_3000", "vx3ref_breaking_chain_3000")
+KEEP_DYNAMIC = ("signals", "links", "vflags", "surface")  # signal state per voxel, the (grown) link list, removed / enableAttach flags
 SCALARS = ("currentTime", "dt", "OptimalDt", "steps", "collisionCount", "fitness_score", "com_x", "com_y", "com_z", "initial_com_x", "initial_com_y",
            "initial_com_z", "recentAngle", "targetCloseness", "numClosePairs", "angleSampleTimes", "diverged", "CurStepCount")
 
@@ -69,7 +77,9 @@ def generate(name):
         if full:  # whole runs are chaotic: only the world-level results are a fixture
             if k == "scalars":
                 out[k] = v
-        elif base in KEEP or (k.startswith("link_state") and name in LINK_STATE_CASES):
+        elif base in KEEP or (k.startswith("link_state") and name in LINK_STATE_CASES) or (name in DYNAMIC_CASES and base in KEEP_DYNAMIC):
+            if name == "vx3ref_target_only_300" and base in ("linMom", "angMom", "pairs", "links"):
+                continue  # 2,964 voxels: keep the fixture small (positions, orientations, signals, flags)
             out[k] = v
     O.write_vxbin(os.path.join(HERE, name + ".vxbin"), out)
     sc = state["scalars"][0]

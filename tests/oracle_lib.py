@@ -38,6 +38,8 @@ def oracle():
         lib.vx3o_num_surface.argtypes = [C.c_void_p]
         lib.vx3o_set_force.argtypes = [C.c_void_p, C.c_int, _DP, _DP]
         lib.vx3o_set_global_damping.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        lib.vx3o_read_signals.argtypes = [C.c_void_p, _DP, C.POINTER(C.c_int32)]
+        lib.vx3o_read_topology.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = lib
     return _lib
 
@@ -79,6 +81,22 @@ class OracleWorld:
         fl = np.empty((self.nl,), dtype=np.int32)
         oracle().vx3o_read_links(self._h, _dp(p2), _dp(a1), _dp(a2), fl.ctypes.data_as(C.POINTER(C.c_int32)))
         return {"pos2": p2, "angle1v": a1, "angle2v": a2, "flags": fl}
+
+    def signals(self):
+        """(signals [nv][6]: localSignal, localSignaldt, inactiveUntil, d_signal.value, d_signal.activeTime, packmakerNextPulse;
+        flags [nv][2]: removed, enableAttach)"""
+        sig, fl = np.empty((self.nv, 6)), np.empty((self.nv, 2), dtype=np.int32)
+        oracle().vx3o_read_signals(self._h, _dp(sig), fl.ctypes.data_as(C.POINTER(C.c_int32)))
+        return sig, fl
+
+    def topology(self):
+        """current links [nl][6]: neg, pos, axis, removed, detached, isNewLink (attachment appends links)"""
+        n = C.c_int32(0)
+        oracle().vx3o_read_topology(self._h, None, C.byref(n))
+        buf = np.empty((max(n.value, 1), 6), dtype=np.int32)
+        n2 = C.c_int32(n.value)
+        oracle().vx3o_read_topology(self._h, buf.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n2))
+        return buf[: n.value].copy()
 
     def time(self):
         return self.result().current_time
