@@ -88,6 +88,9 @@ struct WorldD {
     double comAcc[4]; // Σ m·x, Σ m·y, Σ m·z, Σ m  (measured voxels)
     double distAcc;
     double com[3], initialCom[3], comHist[2][3];
+    // centre of mass at the end of the last run (results, fitness).  Kept apart from `com`, which the reference refreshes only on the
+    // sampling steps of a run (VX3_VoxelyzeKernel.cu:314-334): a run continued by another call must see what one long run sees
+    double finalCom[3];
     int32_t numMeasured, gOverflow; // gOverflow: a global contact list overflowed at the last rebuild: all-pairs this step
     VX3B_Token stop[VX3B_MAX_TOKENS], fitnessF[VX3B_MAX_TOKENS], ff[3 * VX3B_MAX_TOKENS];
 };

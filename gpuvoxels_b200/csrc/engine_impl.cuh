@@ -1887,7 +1887,7 @@ template <class R> class Engine : public EngineBase {
             r.fitness_score = W.fitness;
             for (int k = 0; k < 3; k++) {
                 r.initial_com[k] = W.initialCom[k];
-                r.current_com[k] = W.com[k];
+                r.current_com[k] = W.finalCom[k];
             }
             r.total_distance_of_all_voxels = W.totalDistance;
             r.vox_size = W.voxSize;

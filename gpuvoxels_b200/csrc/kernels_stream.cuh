@@ -376,14 +376,18 @@ template <class R> __global__ void k_world_finish(Arrays<R> A, int mode) {
     if (w >= A.nWorlds)
         return;
     WorldD &W = A.worlds[w];
-    finish_com(W);
     if (mode == 0) {
+        finish_com(W);
         for (int k = 0; k < 3; k++)
-            W.initialCom[k] = W.com[k];
+            W.initialCom[k] = W.finalCom[k] = W.com[k];
     } else {
+        const double inv = W.comAcc[3] == 0 ? 0.0 : 1.0 / W.comAcc[3];
+        for (int k = 0; k < 3; k++)
+            W.finalCom[k] = inv * W.comAcc[k];
+        W.comAcc[0] = W.comAcc[1] = W.comAcc[2] = W.comAcc[3] = 0;
         W.totalDistance = W.distAcc;
         W.distAcc = 0;
-        W.fitness = eval_formula(W.fitnessF, world_vars(W, W.com[0] - W.initialCom[0], W.com[1] - W.initialCom[1], W.com[2] - W.initialCom[2]));
+        W.fitness = eval_formula(W.fitnessF, world_vars(W, W.finalCom[0] - W.initialCom[0], W.finalCom[1] - W.initialCom[1], W.finalCom[2] - W.initialCom[2]));
     }
 }
 

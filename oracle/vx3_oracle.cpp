@@ -225,7 +225,7 @@ struct World {
     double t = 0, optimalDt = 0;
     float dt = 0;
     int64_t stepCount = 0;
-    V3 com, initialCom, comHist[2];
+    V3 com, finalCom, initialCom, comHist[2];
     int angleSampleTimes = 0, collisionCount = 0, numClosePairs = 0;
     double recentAngle = 0, targetCloseness = 0, fitness = 0;
     bool diverged = false, stopped = false;
@@ -337,7 +337,7 @@ struct World {
         for (int l = 0; l < nl; l++)
             update_rest_length(l);
         update_com();
-        initialCom = com;
+        initialCom = finalCom = com;
     }
 
     void update_rest_length(int l) { restLen[l] = 0.5 * (base_size(lneg[l]) + base_size(lpos[l])); } // VX3_Link.cu:80-83
@@ -1043,8 +1043,13 @@ struct World {
                 break;
             }
         }
+        // (into finalCom: `com` is what the stop formula and the heading angle see, refreshed only on sampling steps - a run continued
+        // by another call must see what one long run sees)
+        const V3 sampled = com;
         update_com();
-        V3 off = com - initialCom;
+        finalCom = com;
+        com = sampled;
+        V3 off = finalCom - initialCom;
         fitness = eval_formula(d.fitness, off.x, off.y, off.z, collisionCount, t, recentAngle, targetCloseness, numClosePairs, nv);
         return done;
     }
@@ -1170,9 +1175,9 @@ int vx3o_result(vx3o_world *o, VX3B_WorldResult *r) {
     r->initial_com[0] = w.initialCom.x;
     r->initial_com[1] = w.initialCom.y;
     r->initial_com[2] = w.initialCom.z;
-    r->current_com[0] = w.com.x;
-    r->current_com[1] = w.com.y;
-    r->current_com[2] = w.com.z;
+    r->current_com[0] = w.finalCom.x;
+    r->current_com[1] = w.finalCom.y;
+    r->current_com[2] = w.finalCom.z;
     r->vox_size = w.d.vox_size;
     r->recent_angle = w.recentAngle;
     r->target_closeness = w.targetCloseness;
