@@ -800,7 +800,7 @@ struct World {
             if (vx3() && M(v).fixed)
                 continue;
             step_voxel(v, dtD);
-            if (dynamic()) { // "sticky status": every AttachCondition formula > 0 at the voxel's position
+            { // "sticky status": every AttachCondition formula > 0 at the voxel's position
                 vEnableAttach[v] = 0;
                 bool any = false, all = true;
                 for (int c = 0; c < 5 && all; c++) {
