@@ -287,8 +287,28 @@ class Context:
         _check(lib().vx3b_batch_read_initial_pos(self._h, world, _dp(pos)), "vx3b_batch_read_initial_pos")
         return pos
 
+    def num_links(self, world=0):
+        """links in use (a world with attachment grows new ones)"""
+        n = C.c_int32()
+        _check(lib().vx3b_batch_num_links(self._h, world, C.byref(n)), "vx3b_batch_num_links")
+        return n.value
+
+    def read_signals(self, world=0):
+        """(signals [nv][6], flags [nv][2] = removed, enableAttach): include/vx3b200.h vx3b_batch_read_signals"""
+        nv = self._nv[world]
+        sig, fl = np.empty((nv, 6)), np.empty((nv, 2), dtype=np.int32)
+        _check(lib().vx3b_batch_read_signals(self._h, world, _dp(sig), fl.ctypes.data_as(C.POINTER(C.c_int32))), "vx3b_batch_read_signals")
+        return sig, fl
+
+    def read_topology(self, world=0):
+        """current link list [nl][6] = neg, pos, axis, removed, detached, isNewLink"""
+        n = C.c_int32(self.num_links(world))
+        out = np.empty((n.value, 6), dtype=np.int32)
+        _check(lib().vx3b_batch_read_topology(self._h, world, out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)), "vx3b_batch_read_topology")
+        return out[: n.value]
+
     def read_links(self, world=0):
-        nl = self._nl[world]
+        nl = self.num_links(world)
         p2, a1, a2 = np.empty((nl, 3)), np.empty((nl, 3)), np.empty((nl, 3))
         fl = np.empty((nl,), dtype=np.int32)
         _check(lib().vx3b_batch_read_links(self._h, world, _dp(p2), _dp(a1), _dp(a2), fl.ctypes.data_as(C.POINTER(C.c_int32))),

@@ -114,6 +114,9 @@ SYMBOLS = {
     "vx3b_batch_read_initial_pos": (C.c_int, [_P, C.c_int, _DP]),
     "vx3b_batch_read_links": (C.c_int, [_P, C.c_int, _DP, _DP, _DP, C.POINTER(C.c_int32)]),
     "vx3b_batch_collision_pairs": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "vx3b_batch_num_links": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32)]),
+    "vx3b_batch_read_signals": (C.c_int, [_P, C.c_int, _DP, C.POINTER(C.c_int32)]),
+    "vx3b_batch_read_topology": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "vx3b_ctx_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
     "vx3b_ctx_total_voxel_steps": (C.c_int64, [_P]),
     "vx3b_ctx_set_stream": (C.c_int, [_P, C.c_uint64]),

@@ -141,6 +141,9 @@ int vx3b_batch_read_links(vx3b_ctx *ctx, int world, double *p2, double *a1, doub
 int vx3b_batch_collision_pairs(vx3b_ctx *ctx, int world, int32_t *pairs, int32_t *n) {
     return ctx ? ctx->e->collision_pairs(world, pairs, n) : VX3B_ERR_ARG;
 }
+int vx3b_batch_num_links(vx3b_ctx *ctx, int world, int32_t *n) { return ctx ? ctx->e->num_links(world, n) : VX3B_ERR_ARG; }
+int vx3b_batch_read_signals(vx3b_ctx *ctx, int world, double *sig6, int32_t *vflags2) { return ctx ? ctx->e->read_signals(world, sig6, vflags2) : VX3B_ERR_ARG; }
+int vx3b_batch_read_topology(vx3b_ctx *ctx, int world, int32_t *links6, int32_t *n) { return ctx ? ctx->e->read_topology(world, links6, n) : VX3B_ERR_ARG; }
 int vx3b_ctx_timing(vx3b_ctx *ctx, float *ms, int64_t *launches) {
     if (!ctx)
         return VX3B_ERR_ARG;

@@ -27,6 +27,10 @@ class EngineBase {
     virtual int halo_record_bytes() = 0;
     virtual int halo_export(int world, int listId, void *deviceBuffer) = 0;
     virtual int halo_import(int world, int listId, const void *deviceBuffer) = 0;
+    // dynamic topology: links in use, signal scalars + removed / attach flags per voxel, current link list
+    virtual int num_links(int world, int32_t *n) = 0;
+    virtual int read_signals(int world, double *sig6, int32_t *vflags2) = 0;
+    virtual int read_topology(int world, int32_t *links6, int32_t *n) = 0;
     int device = 0, precision = 32;
     cudaStream_t stream = nullptr;
     bool ownStream = false;

@@ -1,7 +1,7 @@
 // Engine<float>: production arithmetic (FMA contraction on).
-#include "engine_impl.cuh"
+#include "engine_dynamic.cuh"
 namespace vx3b {
-EngineBase *make_engine_f32() { return new Engine<float>(); }
+EngineBase *make_engine_f32() { return new EngineMux<float>(); }
 } // namespace vx3b
 
 #ifdef RES_PROFILE

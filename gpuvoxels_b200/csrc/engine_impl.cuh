@@ -19,6 +19,7 @@
 #include "engine.cuh"
 #include "engine_base.hpp"
 #include "host_dt.hpp"
+#include "materials_dev.cuh"
 #include "kernels_brick.cuh"
 #include "kernels_contact.cuh"
 #include "kernels_fused.cuh"
@@ -560,35 +561,9 @@ template <class R> class Engine : public EngineBase {
             // materials
             for (int k = 0; k < d.num_voxel_mats; k++) {
                 const VX3B_VoxelMaterial &m = d.voxel_mats[k];
-                DVoxMat &o = vmats[vmo + k];
-                memset(&o, 0, sizeof(o));
-                o.E = m.E;
-                o.alphaCTE = m.alphaCTE;
-                o.muStatic = m.muStatic;
-                o.muKinetic = m.muKinetic;
-                o.mass = m.mass;
-                o.massInverse = m.massInverse;
-                o.momentInertiaInverse = m.momentInertiaInverse;
-                o.sqrtMassZetaInt2 = 2 * m.sqrtMass * m.zetaInternal;
-                o.globalDampTranslateC = m.zetaGlobal * m._2xSqMxExS;
-                o.globalDampRotateC = m.zetaGlobal * m._2xSqIxExSxSxS;
+                vmats[vmo + k] = make_dvoxmat(m, (pre[w].flags & WF_THERMAL) != 0, (pre[w].flags & WF_VARY_TEMP) != 0, d.initial_temp);
                 hDampT[vmo + k] = m._2xSqMxExS;
                 hDampR[vmo + k] = m._2xSqIxExSxSxS;
-                o.collisionDampTranslateC = m.zetaCollision * m._2xSqMxExS;
-                o.penetrationStiffness = (float)(2 * m.E * m.nomSize);
-                o.gravityForce = -m.mass * 9.80665f * m.gravMult;
-                o.nomSizeF = (float)m.nomSize;
-                o.nomSize = m.nomSize;
-                o.cilia = m.Cilia;
-                // sizes are constant unless the world is thermally actuated (then the kernels evaluate the expressions every step)
-                o.sizeIsConst = (pre[w].flags & WF_THERMAL) ? 0 : 1;
-                const float T0 = (pre[w].flags & WF_VARY_TEMP) ? 0.0f : d.initial_temp; // varying but not thermal => every alphaCTE == 0
-                o.baseSize0 = base_size_expr(m.nomSize, m.alphaCTE, T0);
-                o.avgSize0 = base_size_average_expr(o.baseSize0);
-                o.floorOffset0 = o.avgSize0 / 2 - m.nomSize / 2;
-                o.fixed = m.fixed;
-                o.isTarget = m.isTarget;
-                o.isMeasured = m.isMeasured;
             }
             { // quick reject of contact candidates: nothing beyond the largest watch distance matters
                 double Rw = max_watch_distance(d);
@@ -610,35 +585,10 @@ template <class R> class Engine : public EngineBase {
             }
             for (int k = 0; k < d.num_link_mats; k++) {
                 const VX3B_LinkMaterial &m = d.link_mats[k];
-                DLinkMat &o = lmats[lmo + k];
-                o.E = m.E;
-                o.a2 = m.a2;
-                o.b1 = m.b1;
-                o.b2 = m.b2;
-                o.b3 = m.b3;
-                o.sqA1 = m.sqA1;
-                o.sqA2xIp = m.sqA2xIp;
-                o.sqB1 = m.sqB1;
-                o.sqB2xFMp = m.sqB2xFMp;
-                o.sqB3xIp = m.sqB3xIp;
-                o.epsilonFail = m.epsilonFail;
-                float s1 = (float)d.voxel_mats[m.mat1].nomSize, s2 = (float)d.voxel_mats[m.mat2].nomSize;
-                o.area = 0.5f * (s1 * s1 + s2 * s2); // currentTransverseArea for nu == 0 (VX3_Link.cu:85-88, VX3_Voxel.cu:496-499)
-                o.matPair = (uint32_t)m.mat1 | ((uint32_t)m.mat2 << 16);
+                lmats[lmo + k] = make_dlinkmat(m, d.voxel_mats);
                 if (anyNonlin) {
-                    DLinkModel &q = lmodels[lmo + k];
-                    memset(&q, 0, sizeof(q));
-                    q.linear = m.linear;
-                    q.npts = std::max(2, std::min(m.num_points, VX3B_MAX_SS_POINTS));
-                    q.E = m.E;
-                    q.nu = m.nu;
-                    q.eHat = m.eHat;
-                    q.epsilonFail = m.epsilonFail;
-                    for (int i = 0; i < VX3B_MAX_SS_POINTS; i++) {
-                        q.strain[i] = m.strain_data[i];
-                        q.stress[i] = m.stress_data[i];
-                    }
-                    if (!m.linear || m.nu != 0.0f)
+                    lmodels[lmo + k] = make_dlinkmodel(m);
+                    if (link_material_is_nonlinear(m))
                         W.flags |= WF_NONLIN;
                 }
             }
@@ -2104,6 +2054,39 @@ template <class R> class Engine : public EngineBase {
                 flags[l] = (int32_t)f;
             }
         }
+        return VX3B_OK;
+    }
+
+    // the static engine's share of the dynamic-topology read-backs: nothing changes, so they report the uploaded topology and the
+    // reference's initial signal state
+    int num_links(int world, int32_t *n) override {
+        if (!check_world(world) || !n)
+            return VX3B_ERR_ARG;
+        *n = H[world].nl;
+        return VX3B_OK;
+    }
+    int read_signals(int world, double *sig6, int32_t *vflags2) override {
+        if (!check_world(world))
+            return VX3B_ERR_ARG;
+        if (sig6)
+            std::fill_n(sig6, (size_t)H[world].nv * 6, 0.0);
+        if (vflags2)
+            for (int v = 0; v < H[world].nv; v++)
+                vflags2[2 * v] = 0, vflags2[2 * v + 1] = 1;
+        return VX3B_OK;
+    }
+    int read_topology(int world, int32_t *links6, int32_t *n) override {
+        if (!check_world(world) || !n)
+            return VX3B_ERR_ARG;
+        const WorldHost &h = H[world];
+        const int cap = *n;
+        *n = h.nl;
+        if (links6)
+            for (int l = 0; l < h.nl && l < cap; l++) {
+                const size_t g = (size_t)h.loff + linkSlot[(size_t)h.loff + l];
+                int32_t *q = links6 + 6 * (size_t)l;
+                q[0] = staging.lends[g].x - h.voff, q[1] = staging.lends[g].y - h.voff, q[2] = (int32_t)(staging.lmeta[g] & 3u), q[3] = q[4] = q[5] = 0;
+            }
         return VX3B_OK;
     }
 

@@ -231,6 +231,14 @@ int vx3b_batch_read_links(vx3b_ctx *ctx, int world, double *pos2_3, double *angl
 /* collision pair set found in the LAST executed step of `world`: pairs (i,j), i>j, voxel indices in
  * creation order, sorted ascending by (i,j).  *n in: capacity (pairs), out: count. */
 int vx3b_batch_collision_pairs(vx3b_ctx *ctx, int world, int32_t *pairs2, int32_t *n);
+/* Dynamic topology.  Links in use in `world` (it grows by attachment; vx3b_batch_read_links and the link_strain of
+ * vx3b_batch_read_aux write that many entries).  Signal state per voxel: sig6 [nv][6] = localSignal, localSignaldt, inactiveUntil,
+ * d_signal.value, d_signal.activeTime, packmakerNextPulse (VX3_Voxel.h); vflags2 [nv][2] = removed, enableAttach; either may be NULL.
+ * Current link list: *n in = capacity in links, out = links in use; links6 [n][6] = negative end, positive end, axis, removed,
+ * detached, isNewLink (steps left of the SafetyGuard easing); links6 may be NULL to ask for the count. */
+int vx3b_batch_num_links(vx3b_ctx *ctx, int world, int32_t *n);
+int vx3b_batch_read_signals(vx3b_ctx *ctx, int world, double *sig6, int32_t *vflags2);
+int vx3b_batch_read_topology(vx3b_ctx *ctx, int world, int32_t *links6, int32_t *n);
 /* what the .history writer needs beyond read_state: voxel temperatures [nv] and link strains [nl]; either may be NULL */
 int vx3b_batch_read_aux(vx3b_ctx *ctx, int world, float *voxel_temp, float *link_strain);
 /* Change the external force / moment of one voxel of an uploaded world between runs (CVX_External::setForce / setMoment,
