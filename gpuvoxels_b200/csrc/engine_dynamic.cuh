@@ -168,6 +168,11 @@ template <class R> class DynEngine {
             DW.safetyGuard = d.safety_guard;
             DW.enableSignals = d.enable_signals, DW.enableAttach = d.enable_attach, DW.enableDetach = d.enable_detach, DW.secondary = d.secondary_experiment;
             DW.reinitAfter = d.reinitialize_initial_position_after;
+            { // contact candidate lists: everything within the largest watch distance + a skin of 0.4 voxels
+                const double skin = 0.4 * d.vox_size, cell = max_watch_distance(d) + skin;
+                W.listR2 = cell * cell;
+                W.skinHalf2 = (float)(0.25 * skin * skin * (1.0 - 1e-2)); // a little early rather than late (float compare)
+            }
             DW.candOff = (int)candOff;
             DW.candCap = d.enable_attach ? std::max(1024, d.num_voxels) : 1;
             DW.toff = (int)targets.size();
@@ -314,6 +319,9 @@ template <class R> class DynEngine {
         ZEROS(vhit, nvTot);
         ZEROS(vsurfFlag, nvTot);
         ZEROS(surf, nvTot);
+        ZEROS(clist, nvTot * DYN_LIST_CAP);
+        ZEROS(ccount, nvTot);
+        ZEROS(cref, nvTot);
         PUT(targets, targets);
         ZEROS(rowScratch, nvTot);
         PUT(lends, lends);

@@ -37,6 +37,7 @@ struct DynWorld {
     WorldD W; // voff / loff / soff: offsets into DynArrays (loff counts link CAPACITY); nl = links in use; ns = listed surface voxels
     int32_t lcap, surfaceChanged, safetyGuard, enableSignals, enableAttach, enableDetach, secondary, reinitDone;
     int32_t nCand, candOff, candCap, error, nTargets, toff, attachLinks, detachedLinks;
+    int32_t listsValid, listOverflow, listRebuilds, padList; // contact candidate lists (Verlet lists) of the world
     double reinitAfter;
     VX3B_Token attach[5 * VX3B_MAX_TOKENS];
 };
@@ -66,6 +67,8 @@ template <class R> struct DynArrays {
     double *sigT; // [v][4] scratch: inactiveUntil, localSignal, signal value, signal activeTime of the voxel at its turn
     uint8_t *vremoved, *vattach, *vhit, *vsurfFlag;
     int32_t *surf;      // surface list per world (capacity nv)
+    int32_t *clist, *ccount; // per surface slot: candidate list (DYN_LIST_CAP surface slots, ascending) and its length
+    P3 *cref;           // per surface slot: position when the lists were built
     int32_t *targets;   // voxels of target materials per world
     double *rowScratch; // [v] per-row partial sums of the target closeness
     // links (capacity lcap per world)
@@ -150,7 +153,7 @@ VXD double dyn_block_sum(double x, double *sh) {
     return s;
 }
 
-enum { DYN_THREADS = 512, DYN_TILE = 128 };
+enum { DYN_THREADS = 512, DYN_TILE = 128, DYN_LIST_CAP = 40 };
 
 template <class R> struct DynSurfRec {
     double x, y, z, avg;
@@ -331,10 +334,16 @@ template <class R> __global__ void __launch_bounds__(DYN_THREADS, 1) k_dynamic(D
             if (tid == 0) {
                 W.ns = sBase;
                 DW.surfaceChanged = 0;
+                DW.listsValid = 0; // the candidate lists index the surface list
             }
             __syncthreads();
         }
         // ---- contact, target hits, attachment candidates (VX3_VoxelyzeKernel.cu:682-843, VX3_Collision.cu:3-31) -------------------
+        // The reference tests all ns^2/2 surface pairs every step.  Here every surface voxel keeps a candidate list (Verlet list):
+        // the surface voxels within the world's largest watch distance + a skin at the last all-pairs scan, in ascending order.  The
+        // lists stay valid until some surface voxel has moved more than skin / 2 (or the surface list itself changed); every step
+        // each voxel applies the reference's exact predicate to its candidates only, in the all-pairs order - the same pair set, the
+        // same sums.  A list that overflows sends the world back to the all-pairs scan for that step.
         const int ns = W.ns;
         if ((collision || doAttach) && ns > 0) {
             auto load = [&](int slot) {
@@ -352,112 +361,203 @@ template <class R> __global__ void __launch_bounds__(DYN_THREADS, 1) k_dynamic(D
                 r.attachOk = (vattach[v] && !m.fixed && D.matx[mi].sticky) ? 1 : 0;
                 return r;
             };
-            for (int i0 = 0; i0 < ns; i0 += nt) {
-                const int i = i0 + tid;
-                const bool have = i < ns;
-                DynSurfRec<R> me;
-                int nb[6];
-                if (have) {
-                    me = load(i);
-                    for (int k = 0; k < 6; k++) {
-                        const int l = me.v >= 0 ? vlinks[(size_t)me.v * 6 + k] : -1;
-                        nb[k] = l >= 0 ? other_end(l, me.v) : -1;
-                    }
-                }
-                V3<R> acc{R(0), R(0), R(0)};
-                int hits = 0;
-                for (int base = 0; base < ns; base += DYN_TILE) {
-                    __syncthreads();
-                    if (tid < DYN_TILE && base + tid < ns)
-                        tile[tid] = load(base + tid);
-                    __syncthreads();
-                    if (!have || me.v < 0)
-                        continue;
-                    const int lim = min((int)DYN_TILE, ns - base);
-                    const DVoxMat &m1 = D.vmats[me.mat];
-                    for (int k = 0; k < lim; k++) {
-                        const int j = base + k;
-                        if (j == i)
-                            continue;
-                        const DynSurfRec<R> &o = tile[k];
-                        if (o.v < 0)
-                            continue;
-                        const DVoxMat &m2 = D.vmats[o.mat];
-                        if (m1.fixed && m2.fixed)
-                            continue;
-                        // the reference evaluates a pair once, voxel1 = the later surface voxel, and gives voxel2 the negative;
-                        // both members evaluate it in that orientation, so the two forces are the same bits
-                        const bool hi = i > j;
-                        V3<R> f;
-                        bool watched;
-                        if (hi)
-                            watched = contact_pair_sized<R>(m1, me.avg, {me.x, me.y, me.z}, {me.lx, me.ly, me.lz}, m2, o.avg, {o.x, o.y, o.z}, {o.lx, o.ly, o.lz}, f);
-                        else
-                            watched = contact_pair_sized<R>(m2, o.avg, {o.x, o.y, o.z}, {o.lx, o.ly, o.lz}, m1, me.avg, {me.x, me.y, me.z}, {me.lx, me.ly, me.lz}, f);
-                        if (!watched)
-                            continue;
-                        if (o.v == nb[0] || o.v == nb[1] || o.v == nb[2] || o.v == nb[3] || o.v == nb[4] || o.v == nb[5])
-                            continue; // is_neighbor(depth 1): directly linked voxels never collide
-                        if (collision) {
-                            acc = hi ? acc + f : acc - f;
-                            if (hi) {
-                                if ((m1.isTarget != 0) != (m2.isTarget != 0)) {
-                                    hits++;
-                                    if (doSignals) // the voxel that touched a target fires (VX3_VoxelyzeKernel.cu:706-716): forced, the same values from every hit
-                                        vhit[m1.isTarget ? o.v : me.v] = 1;
-                                }
-                                if (recordPairs) {
-                                    const int slot = atomicAdd(D.pairCount, 1);
-                                    if (slot < D.pairCap)
-                                        D.pairBuf[slot] = make_int4(blockIdx.x, me.v, o.v, 0);
-                                }
-                            }
-                        } else
-                            f = V3<R>{R(0), R(0), R(0)};
-                        if (doAttach && hi && me.attachOk && o.attachOk && me.mat == o.mat) {
-                            // the attachment half of handle_collision_attachment (VX3_VoxelyzeKernel.cu:718-831) on the topology at the start
-                            // of this phase; a link made earlier in the phase can only turn these tests from pass to fail
-                            const int v1 = me.v, v2 = o.v;
-                            const auto q = orient[v1];
-                            const Qt<double> qd{(double)q.x, (double)q.y, (double)q.z, (double)q.w};
-                            const V3<double> ea = qrot_inv(qd, V3<double>{-(me.x - o.x), -(me.y - o.y), -(me.z - o.z)});
-                            const double fx = fabs(ea.x), fy = fabs(ea.y), fz = fabs(ea.z);
-                            int axis;
-                            double comp;
-                            if (fx >= fy && fx >= fz)
-                                axis = 0, comp = ea.x;
-                            else if (fy >= fx && fy >= fz)
-                                axis = 1, comp = ea.y;
-                            else
-                                axis = 2, comp = ea.z;
-                            const int reverse = comp < 0 ? 1 : 0;
-                            const int dir1 = reverse ? 2 * axis + 1 : 2 * axis, dir2 = reverse ? 2 * axis : 2 * axis + 1;
-                            if (vlinks[(size_t)v1 * 6 + dir1] >= 0 || vlinks[(size_t)v2 * 6 + dir2] >= 0)
-                                continue;
-                            const int ml = D.matx[me.mat].localIndex;
-                            int mat = -1;
-                            for (int q2 = 0; q2 < W.nlm && mat < 0; q2++) { // combinedMaterial (VX3_VoxelyzeKernel.cu:515-528)
-                                const uint32_t mp2 = D.lmats[W.lmatOff + q2].matPair;
-                                if ((int)(mp2 & 0xffff) == ml && (int)(mp2 >> 16) == ml)
-                                    mat = W.lmatOff + q2;
-                            }
-                            if (mat < 0)
-                                continue;
-                            if (dyn_is_neighbor5(vlinks, lends, v1, v2)) // (last: the walk over up to five links is the expensive test)
-                                continue;
-                            const int at = atomicAdd(&DW.nCand, 1);
-                            if (at < DW.candCap)
-                                cand[at] = DynCand<R>{i, j, v1, v2, dir1, dir2, axis, reverse, mat, 0, f.x, f.y, f.z};
+            // one pair, seen from surface voxel i (record `me`, linked voxels nb[6]) towards surface voxel j (record `o`)
+            auto pair = [&](int i, const DynSurfRec<R> &me, const int *nb, int j, const DynSurfRec<R> &o, V3<R> &acc, int &hits) {
+                if (o.v < 0)
+                    return;
+                const DVoxMat &m1 = D.vmats[me.mat];
+                const DVoxMat &m2 = D.vmats[o.mat];
+                if (m1.fixed && m2.fixed)
+                    return;
+                // the reference evaluates a pair once, voxel1 = the later surface voxel, and gives voxel2 the negative; both members
+                // evaluate it in that orientation, so the two forces are the same bits
+                const bool hi = i > j;
+                V3<R> f;
+                bool watched;
+                if (hi)
+                    watched = contact_pair_sized<R>(m1, me.avg, {me.x, me.y, me.z}, {me.lx, me.ly, me.lz}, m2, o.avg, {o.x, o.y, o.z}, {o.lx, o.ly, o.lz}, f);
+                else
+                    watched = contact_pair_sized<R>(m2, o.avg, {o.x, o.y, o.z}, {o.lx, o.ly, o.lz}, m1, me.avg, {me.x, me.y, me.z}, {me.lx, me.ly, me.lz}, f);
+                if (!watched)
+                    return;
+                if (o.v == nb[0] || o.v == nb[1] || o.v == nb[2] || o.v == nb[3] || o.v == nb[4] || o.v == nb[5])
+                    return; // is_neighbor(depth 1): directly linked voxels never collide
+                if (collision) {
+                    acc = hi ? acc + f : acc - f;
+                    if (hi) {
+                        if ((m1.isTarget != 0) != (m2.isTarget != 0)) {
+                            hits++;
+                            if (doSignals) // the voxel that touched a target fires (VX3_VoxelyzeKernel.cu:706-716): forced, the same values from every hit
+                                vhit[m1.isTarget ? o.v : me.v] = 1;
+                        }
+                        if (recordPairs) {
+                            const int slot = atomicAdd(D.pairCount, 1);
+                            if (slot < D.pairCap)
+                                D.pairBuf[slot] = make_int4(blockIdx.x, me.v, o.v, 0);
                         }
                     }
+                } else
+                    f = V3<R>{R(0), R(0), R(0)};
+                if (doAttach && hi && me.attachOk && o.attachOk && me.mat == o.mat) {
+                    // the attachment half of handle_collision_attachment (VX3_VoxelyzeKernel.cu:718-831) on the topology at the start of
+                    // this phase; a link made earlier in the phase can only turn these tests from pass to fail
+                    const int v1 = me.v, v2 = o.v;
+                    const auto q = orient[v1];
+                    const Qt<double> qd{(double)q.x, (double)q.y, (double)q.z, (double)q.w};
+                    const V3<double> ea = qrot_inv(qd, V3<double>{-(me.x - o.x), -(me.y - o.y), -(me.z - o.z)});
+                    const double fx = fabs(ea.x), fy = fabs(ea.y), fz = fabs(ea.z);
+                    int axis;
+                    double comp;
+                    if (fx >= fy && fx >= fz)
+                        axis = 0, comp = ea.x;
+                    else if (fy >= fx && fy >= fz)
+                        axis = 1, comp = ea.y;
+                    else
+                        axis = 2, comp = ea.z;
+                    const int reverse = comp < 0 ? 1 : 0;
+                    const int dir1 = reverse ? 2 * axis + 1 : 2 * axis, dir2 = reverse ? 2 * axis : 2 * axis + 1;
+                    if (vlinks[(size_t)v1 * 6 + dir1] >= 0 || vlinks[(size_t)v2 * 6 + dir2] >= 0)
+                        return;
+                    const int ml = D.matx[me.mat].localIndex;
+                    int mat = -1;
+                    for (int q2 = 0; q2 < W.nlm && mat < 0; q2++) { // combinedMaterial (VX3_VoxelyzeKernel.cu:515-528)
+                        const uint32_t mp2 = D.lmats[W.lmatOff + q2].matPair;
+                        if ((int)(mp2 & 0xffff) == ml && (int)(mp2 >> 16) == ml)
+                            mat = W.lmatOff + q2;
+                    }
+                    if (mat < 0)
+                        return;
+                    if (dyn_is_neighbor5(vlinks, lends, v1, v2)) // (last: the walk over up to five links is the expensive test)
+                        return;
+                    const int at = atomicAdd(&DW.nCand, 1);
+                    if (at < DW.candCap)
+                        cand[at] = DynCand<R>{i, j, v1, v2, dir1, dir2, axis, reverse, mat, 0, f.x, f.y, f.z};
                 }
-                if (have && me.v >= 0)
+            };
+            auto neighbours = [&](const DynSurfRec<R> &me, int *nb) {
+                for (int k = 0; k < 6; k++) {
+                    const int l = me.v >= 0 ? vlinks[(size_t)me.v * 6 + k] : -1;
+                    nb[k] = l >= 0 ? other_end(l, me.v) : -1;
+                }
+            };
+            int32_t *clist = D.clist + voff * DYN_LIST_CAP;
+            int32_t *ccount = D.ccount + voff;
+            P3 *cref = D.cref + voff;
+            // are the lists still good?  (a voxel that moved more than skin / 2 since they were built may have met one it does not list)
+            const int validBefore = DW.listsValid; // (read by every thread before anyone may clear it)
+            __syncthreads();
+            if (validBefore) {
+                bool moved = false;
+                for (int i = tid; i < ns; i += nt) {
+                    const P3 p = pos[surf[i]], q = cref[i];
+                    const double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+                    moved = moved || (float)(dx * dx + dy * dy + dz * dz) > W.skinHalf2;
+                }
+                if (moved)
+                    DW.listsValid = 0;
+            }
+            __syncthreads();
+            if (!DW.listsValid) { // all-pairs scan through shared-memory tiles: lists of everything within watch distance + skin
+                __syncthreads();
+                if (tid == 0)
+                    DW.listOverflow = 0;
+                for (int i0 = 0; i0 < ns; i0 += nt) {
+                    const int i = i0 + tid;
+                    const bool have = i < ns;
+                    P3 me{0, 0, 0};
+                    bool meOk = false;
+                    if (have) {
+                        const int v = surf[i];
+                        me = pos[v];
+                        meOk = !vremoved[v];
+                        cref[i] = me;
+                    }
+                    int cnt = 0;
+                    for (int base = 0; base < ns; base += DYN_TILE) {
+                        __syncthreads();
+                        if (tid < DYN_TILE && base + tid < ns) {
+                            const int v = surf[base + tid];
+                            const P3 p = pos[v];
+                            tile[tid].x = p.x, tile[tid].y = p.y, tile[tid].z = p.z;
+                            tile[tid].v = vremoved[v] ? -1 : v;
+                        }
+                        __syncthreads();
+                        if (!have || !meOk)
+                            continue;
+                        const int lim = min((int)DYN_TILE, ns - base);
+                        for (int k = 0; k < lim; k++) {
+                            const double dx = me.x - tile[k].x, dy = me.y - tile[k].y, dz = me.z - tile[k].z;
+                            if (dx * dx + dy * dy + dz * dz > W.listR2 || base + k == i || tile[k].v < 0)
+                                continue;
+                            if (cnt < DYN_LIST_CAP)
+                                clist[(size_t)i * DYN_LIST_CAP + cnt] = base + k;
+                            cnt++;
+                        }
+                    }
+                    if (have) {
+                        ccount[i] = cnt;
+                        if (cnt > DYN_LIST_CAP)
+                            DW.listOverflow = 1;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    DW.listsValid = DW.listOverflow ? 0 : 1;
+                    DW.listRebuilds++;
+                }
+                __syncthreads();
+            }
+            if (DW.listsValid) { // narrow phase over the candidate lists
+                int hits = 0;
+                for (int i = tid; i < ns; i += nt) {
+                    const DynSurfRec<R> me = load(i);
+                    if (me.v < 0)
+                        continue;
+                    int nb[6];
+                    neighbours(me, nb);
+                    V3<R> acc{R(0), R(0), R(0)};
+                    const int cnt = ccount[i];
+                    for (int c = 0; c < cnt; c++) {
+                        const int j = clist[(size_t)i * DYN_LIST_CAP + c];
+                        pair(i, me, nb, j, load(j), acc, hits);
+                    }
                     contactF[me.v] = acc;
+                }
                 for (int o = 16; o > 0; o >>= 1)
                     hits += __shfl_xor_sync(0xffffffffu, hits, o);
                 if (lane == 0 && hits)
                     atomicAdd(&W.collisionCount, hits);
-            }
+            } else // a list overflowed: the reference's all-pairs scan for this step
+                for (int i0 = 0; i0 < ns; i0 += nt) {
+                    const int i = i0 + tid;
+                    const bool have = i < ns;
+                    DynSurfRec<R> me;
+                    int nb[6];
+                    if (have) {
+                        me = load(i);
+                        neighbours(me, nb);
+                    }
+                    V3<R> acc{R(0), R(0), R(0)};
+                    int hits = 0;
+                    for (int base = 0; base < ns; base += DYN_TILE) {
+                        __syncthreads();
+                        if (tid < DYN_TILE && base + tid < ns)
+                            tile[tid] = load(base + tid);
+                        __syncthreads();
+                        if (!have || me.v < 0)
+                            continue;
+                        const int lim = min((int)DYN_TILE, ns - base);
+                        for (int k = 0; k < lim; k++)
+                            if (base + k != i)
+                                pair(i, me, nb, base + k, tile[k], acc, hits);
+                    }
+                    if (have && me.v >= 0)
+                        contactF[me.v] = acc;
+                    for (int o = 16; o > 0; o >>= 1)
+                        hits += __shfl_xor_sync(0xffffffffu, hits, o);
+                    if (lane == 0 && hits)
+                        atomicAdd(&W.collisionCount, hits);
+                }
             __syncthreads();
             // ---- the survivors are linked by one thread, in pair order (a ascending, then b) -----------------------------------
             if (tid == 0 && DW.nCand > 0) {

@@ -29,3 +29,19 @@ print("pos err", np.abs(s["pos"] - ref["pos"]).max(), "oracle links", len(w.topo
 sig, fl = ctx.read_signals(0)
 osig, ofl = w.signals()
 print("sig equal", np.array_equal(sig, osig), np.abs(sig - osig).max(), "topo equal", np.array_equal(ctx.read_topology(0), w.topology()), flush=True)
+if len(sys.argv) > 4:  # timing variants: which feature costs what
+    import re
+    for what, sub in (("all", None), ("no attach", ("<EnableAttach>1", "<EnableAttach>0")), ("no signals", ("<EnableSignals>1", "<EnableSignals>0")),
+                      ("no collision, no attach", ("<EnableCollision>1", "<EnableCollision>0"))):
+        v = vxa
+        if sub:
+            v = v.replace(*sub)
+            if what.startswith("no collision"):
+                v = v.replace("<EnableAttach>1", "<EnableAttach>0")
+        mm = gv.Model.from_vxa(v, vxd)
+        c = gv.Context(0, prec)
+        c.upload([mm])
+        c.run(20)
+        c.run(steps)
+        print(f"{what:28s} {c.timing()[0] / steps * 1e3:9.1f} us per step  (attach {mm.desc.enable_attach} signals {mm.desc.enable_signals} collision {mm.desc.enable_collision})", flush=True)
+        c.close()

@@ -34,9 +34,12 @@ def check_against(ctx, world, model, g, sfx, tol, exact_signals=True):
     err = np.abs(s["pos"] - g["pos" + sfx]).max() / scale
     assert err < tol, ("pos", sfx, err)
     assert np.abs(s["orient"] - g["orient" + sfx]).max() < max(tol * 10, 1e-9), ("orient", sfx)
-    topo = ctx.read_topology(world)
-    assert np.array_equal(topo[:, :5], g["links" + sfx][:, :5]), ("links", sfx)
-    assert np.array_equal(topo[:, 5], g["links" + sfx][:, 5]), ("isNewLink", sfx)
+    if "links" + sfx in g:  # (not kept for the 2,964-voxel world: size)
+        topo = ctx.read_topology(world)
+        assert np.array_equal(topo[:, :5], g["links" + sfx][:, :5]), ("links", sfx)
+        assert np.array_equal(topo[:, 5], g["links" + sfx][:, 5]), ("isNewLink", sfx)
+    else:
+        assert ctx.num_links(world) == model.num_links  # nothing has attached in the oracle either (tests/test_dynamic_topology.py)
     sig, fl = ctx.read_signals(world)
     assert np.array_equal(fl[:, 0], g["vflags" + sfx][:, 1]), ("removed", sfx)
     if model.desc.enable_attach:
@@ -84,16 +87,11 @@ def test_fp32_follows_the_reference_step_code(name, steps):
     s = ctx.read_state(0)
     err = np.abs(s["pos"] - g["pos" + sfx]).max() / disp_scale(m, g["pos" + sfx])
     print(f"{name} fp32 step {steps}: displacement rel err {err:.2e}")
-    assert err < 1e-3 or name.startswith("vx3ref_signaling"), err  # (the signaling worlds are contact-heavy: fitness rule below)
+    assert err < 1e-3, err
     topo = ctx.read_topology(0)
     assert np.array_equal(topo[:, :5], g["links" + sfx][:, :5])
     _, fl = ctx.read_signals(0)
     assert np.array_equal(fl[:, 0], g["vflags" + sfx][:, 1])
-    if name.startswith("vx3ref_signaling"):  # chaotic contact-heavy: world results within 1 % (centre of mass against the body's travel)
-        com = np.array(ctx.results()[0].current_com)
-        ref = g["scalars" + sfx][0, 6:9]
-        travel = max(np.abs(ref - g["scalars" + sfx][0, 9:12]).max(), m.desc.vox_size)
-        assert np.abs(com - ref).max() / travel < 1e-2
     ctx.close()
 
 
@@ -124,7 +122,10 @@ def test_dynamic_and_static_worlds_share_a_context():
         for k in ("pos", "orient", "linMom", "angMom"):
             assert np.array_equal(got[k], s[k]), (w, k)
         assert res[w].steps == steps and res[w].num_voxel == m.num_voxels
-        assert res[w].fitness_score == r.fitness_score and list(res[w].current_com) == list(r.current_com)
+        # (the static engine's end-of-run centre of mass is an atomic sum: last-bit differences between batch layouts)
+        assert np.allclose(res[w].current_com, r.current_com, rtol=1e-12, atol=0) and abs(res[w].fitness_score - r.fitness_score) <= 1e-12 * abs(r.fitness_score)
+        if m in (dyn1, dyn2):
+            assert list(res[w].current_com) == list(r.current_com) and res[w].fitness_score == r.fitness_score
         assert np.array_equal(ctx.read_topology(w), topo)
         assert np.array_equal(ctx.read_signals(w)[0], sig) and np.array_equal(ctx.read_signals(w)[1], fl)
         assert len(ctx.read_links(w)["flags"]) == ctx.num_links(w)
@@ -160,13 +161,13 @@ def test_dynamic_world_is_deterministic_and_matches_the_oracle_pair_set():
     vxa, vxd = CASES["vx3ref_signaling_data1_3000"][:2]
     m = gv.Model.from_vxa(vxa, vxd)
     w = O.OracleWorld(m)
-    w.run(250)
+    w.run(1800)
     states = []
     for _ in range(2):
         ctx = gv.Context(0, gv.FP64)
         ctx.set_option("record_pairs", 1)
         ctx.upload([m])
-        ctx.run(250)
+        ctx.run(1800)
         states.append(ctx.read_state(0))
         pairs = ctx.collision_pairs(0)
         ctx.close()
