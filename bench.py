@@ -48,6 +48,9 @@ def parse_args():
                     "(all | none | comma list of cube100,pile,xenobot_fp64)")
     ap.add_argument("--slab-cube", type=int, default=160, help="N > 1: edge of the ONE body also stepped as N slabs into a \"slab\" block (0 = skip)")
     ap.add_argument("--slab-sim-steps", type=int, default=200)
+    ap.add_argument("--slab-exchange", default="device", choices=["device", "nccl"],
+                    help="slab halo exchange: device = stores into the neighbour's IPC-mapped memory + flags, no host in the loop; nccl = round 1's per-step ncclSend/Recv")
+    ap.add_argument("--slab-big", type=int, default=400, help="N = 8: edge of the big body (BASELINE configs[4]: 400^3) also stepped as 8 slabs into a \"slab_big\" block (0 = skip)")
     return ap.parse_args()
 
 
@@ -55,7 +58,8 @@ def workload_config(args):
     if args.workload == "slab":
         return {"workload": f"BASELINE configs[4] (second part): ONE {args.cube}^3-voxel soft body under gravity with floor contact, split into {args.gpus} z-slab(s)",
                 "worlds_per_gpu": 1, "sim_steps_per_step": args.sim_steps,
-                "parallelism": f"{args.gpus} slab(s), one per GPU; per time step one NCCL send/recv of the boundary layer to each neighbour (pos, temperature, orientation)",
+                "parallelism": f"{args.gpus} slab(s), one per GPU; per time step the boundary layer (pos, temperature, orientation) goes to each neighbour "
+                               + ("by device-side stores into its IPC-mapped receive area over NVLink" if getattr(args, "slab_exchange", "device") == "device" else "by one NCCL send/recv"),
                 "l2": "slab state larger than L2"}
     if args.workload == "pile":
         return {"workload": f"BASELINE configs[3]: multi-body scene, {args.pile}x{args.pile} + {args.pile - 1}x{args.pile - 1} bodies of 8^3 voxels piling up, voxel-voxel self-collision enabled (grid broad phase + candidate lists)",
@@ -428,16 +432,20 @@ def main_ours(args):
                 out["workloads"][name] = {key: r[key] for key in keep if key in r}
             except Exception as e:  # noqa: BLE001 - the headline line must still be printed
                 out["workloads"][name] = {"error": f"{type(e).__name__}: {e}"}
-    if world > 1 and args.slab_cube > 0:
-        # BASELINE configs[4], second part, in the same multi-GPU run: ONE body cut into N slabs (strong scaling)
-        a2 = copy.copy(args)
-        a2.cube, a2.sim_steps, a2.steps, a2.warmup, a2.verify = args.slab_cube, args.slab_sim_steps, 3, 3, False
-        try:
-            slab = measure_slab(a2, rank, world, local)
-        except Exception as e:  # noqa: BLE001
-            slab = {"error": f"{type(e).__name__}: {e}"}
-        if rank == 0:
-            out["slab"] = slab
+    if world > 1:
+        # BASELINE configs[4], second part, in the same multi-GPU run: ONE body cut into N slabs (strong scaling); at N = 8 also the
+        # 400^3 body the config names
+        for key, cube, sim_steps in (("slab", args.slab_cube, args.slab_sim_steps), ("slab_big", args.slab_big if world >= 8 else 0, 100)):
+            if cube <= 0:
+                continue
+            a2 = copy.copy(args)
+            a2.workload, a2.cube, a2.sim_steps, a2.steps, a2.warmup, a2.verify = "slab", cube, sim_steps, 3, 3, False
+            try:
+                slab = measure_slab(a2, rank, world, local)
+            except Exception as e:  # noqa: BLE001
+                slab = {"error": f"{type(e).__name__}: {e}"}
+            if rank == 0:
+                out[key] = slab
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -474,12 +482,24 @@ def measure_slab(args, rank, world, local):
     from gpuvoxels_b200 import worlds as W
 
     t_host = time.perf_counter()
-    model = gv.Model.from_vxa(W.cube_vxa(args.cube))
-    part = S.split_body(model, world)[rank]
-    dt = S.body_time_step(model)
-    t_split = time.perf_counter() - t_host
+    vxa = W.cube_vxa(args.cube)
+    t_text = time.perf_counter() - t_host
+    device_exchange = args.slab_exchange == "device"
+    # every rank builds ONLY its own slab, in C++ (vx3b_model_from_vxa_slab); the whole body never exists on any rank
+    part = S.native_part(vxa, None, rank, world)
+    dt = part.body_dt
+    t_split = time.perf_counter() - t_host - t_text
+    body_voxels, body_links = int(part.body_voxels), int(part.body_links)
     run = S.SlabRunner(part, local, args.precision, dt)
+    t_upload = time.perf_counter() - t_host - t_text - t_split
     b = run.buf
+    if device_exchange and world > 1:
+        # receive areas are mapped into the neighbours' processes (CUDA IPC, stores over NVLink): the handles travel once, here
+        mine = run.open_endpoints()
+        eps = [None] * world
+        dist.all_gather_object(eps, mine)
+        run.connect(eps[rank - 1]["hi"] if rank > 0 else None, eps[rank + 1]["lo"] if rank < world - 1 else None)
+        dist.barrier()
 
     def exchange():
         if world == 1:
@@ -493,6 +513,9 @@ def measure_slab(args, rank, world, local):
             w.wait()  # stream-ordered: the slab's stream waits for the transfer, the host does not
 
     def steps(n):
+        if device_exchange:
+            run.run(n)  # step kernel + push + pull per time step, 64 time steps per CUDA graph, nothing on the host in between
+            return
         with torch.cuda.stream(run.stream):
             for _ in range(n):
                 run.step_begin()
@@ -521,6 +544,13 @@ def measure_slab(args, rank, world, local):
     dev_ms = ev[0].elapsed_time(ev[1])
     clocks = sampler.stop() if sampler else None
     res = run.ctx.results()[0]
+    timeouts = run.ctx.halo_timeouts()
+    # whole-body centre of mass across the slabs (one all-reduce of <= 8 doubles): every slab reports the centre of
+    # mass of its own voxels (ghosts excluded); the body here is of one material, so the weights are the own-voxel counts
+    com = torch.tensor([c * part.num_own for c in res.current_com] + [float(part.num_own)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(com, op=dist.ReduceOp.SUM)
+    body_com = (com[:3] / com[3]).tolist()
     verified = None
     if args.verify:  # parity of the sliced run over real NCCL: every voxel of every slab against the whole body on rank 0's GPU
         state, gidx = run.own_state()
@@ -531,6 +561,7 @@ def measure_slab(args, rank, world, local):
             parts_state = [(gidx, state)]
         if rank == 0:
             total = args.sim_steps * (args.warmup + args.steps)
+            model = gv.Model.from_vxa(vxa)
             whole = gv.Context(local, args.precision)
             whole.set_option("path", 5)
             whole.upload([model])
@@ -541,12 +572,12 @@ def measure_slab(args, rank, world, local):
     own = part.num_own
     nl_own = int(part.model.num_links)
     stats = torch.tensor([dev_ms, wall], dtype=torch.float64, device="cuda")
-    work = torch.tensor([float(own) * args.sim_steps * args.steps, float(res.diverged), float(run.halo_bytes_per_step)], dtype=torch.float64, device="cuda")
+    work = torch.tensor([float(own) * args.sim_steps * args.steps, float(res.diverged), float(run.halo_bytes_per_step), float(timeouts)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     dev_ms_max, wall_max = stats.tolist()
-    vs_all, diverged_all, halo_all = work.tolist()
+    vs_all, diverged_all, halo_all, timeouts_all = work.tolist()
     out = None
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -555,19 +586,25 @@ def measure_slab(args, rank, world, local):
         else:
             peak, peak_src = 6650.0, "of fallback (B200_PROFILING.md)"
         nsteps = args.sim_steps * args.steps
-        alg = (112 * model.num_voxels + 88 * model.num_links) if args.precision == 32 else (216 * model.num_voxels + 160 * model.num_links)
+        alg = (112 * body_voxels + 88 * body_links) if args.precision == 32 else (216 * body_voxels + 160 * body_links)
         achieved = alg * nsteps / (dev_ms_max * 1e-3) / 1e9 / world  # per GPU
         out = {"metric": METRIC, "value": vs_all / (dev_ms_max * 1e-3), "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32 arithmetic, f64 positions" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args),
-               "voxels_total": model.num_voxels, "links_total": model.num_links, "voxels_rank0_incl_ghosts": part.model.num_voxels, "links_rank0": nl_own,
+               "voxels_total": body_voxels, "links_total": body_links, "voxels_rank0_incl_ghosts": part.model.num_voxels, "links_rank0": nl_own,
+               "exchange": "device-side: k_halo_push into the neighbour's IPC-mapped receive area + flag, k_halo_pull; 64 time steps per CUDA graph" if device_exchange
+               else "host-driven: k_halo_export, ncclSend/ncclRecv (torch.distributed.batch_isend_irecv), k_halo_import per time step",
+               "halo_pull_timeouts": int(timeouts_all), "body_center_of_mass_allreduced": body_com,
+               "host_s_rank0": {"vxa_text": t_text, "slab_model_cpp": t_split, "upload": t_upload},
                "us_per_time_step": 1e3 * dev_ms_max / nsteps, "halo_bytes_per_time_step_all_ranks": int(halo_all), "wall_s_timed_region": wall_max,
-               "host_split_s_rank0": t_split, "diverged_worlds": int(diverged_all), "verified_bit_exact_against_whole_body": verified,
+               "diverged_worlds": int(diverged_all), "verified_bit_exact_against_whole_body": verified,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s per GPU", "frac": achieved / peak, "traffic": None, "kernel": "k_brick",
                             "peak_source": peak_src, "note": "algorithmic bytes of the WHOLE body (112*Nv + 88*Nl per time step) / N GPUs / device time"},
                "e2e": {"value": vs_all / wall_max, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                       "what": "same timed region by host wall clock (per-step launches + NCCL calls included); the body is uploaded once before it"},
+                       "what": "same timed region by host wall clock (graph launches, or per-step launches + NCCL calls, included); the body is uploaded once before it"},
                "gpu_launches": int(nsteps * (1 + (2 if world > 1 else 0) * 2)), "clocks": clocks}
+        if timeouts_all:
+            out["error"] = "a halo pull timed out: the run is invalid"
     run.close()
     return out if rank == 0 else None
 

@@ -60,6 +60,27 @@ class Model:
         return cls(h)
 
     @classmethod
+    def from_vxa_slab(cls, vxa_text, vxd_text=None, axis=2, part=0, n_parts=1):
+        """ONE SLAB of the body (vx3b_model_from_vxa_slab): own voxels of range `part` of `n_parts` along `axis` + ghosts"""
+        h = C.c_void_p()
+        _check(lib().vx3b_model_from_vxa_slab(vxa_text.encode() if isinstance(vxa_text, str) else vxa_text,
+                                              None if vxd_text is None else vxd_text.encode() if isinstance(vxd_text, str) else vxd_text,
+                                              int(axis), int(part), int(n_parts), C.byref(h)), "vx3b_model_from_vxa_slab")
+        return cls(h)
+
+    def slab_info(self):
+        """exchange lists and whole-body figures of a slab model, as numpy arrays (copies)"""
+        si = _abi.SlabInfo()
+        _check(lib().vx3b_model_slab_info(self._h, C.byref(si)), "vx3b_model_slab_info")
+        out = {k: getattr(si, k) for k in ("part", "n_parts", "axis", "layer_lo", "layer_hi", "num_own", "body_voxels", "body_links", "body_dt")}
+        for name in ("send_lo", "send_hi", "ghost_lo", "ghost_hi"):
+            n = getattr(si, "n_" + name)
+            out[name] = np.ctypeslib.as_array(getattr(si, name), shape=(n,)).copy() if n else np.zeros(0, dtype=np.int32)
+        nv = self.num_voxels
+        out["global_index"] = np.ctypeslib.as_array(si.global_index, shape=(nv,)).copy() if nv else np.zeros(0, dtype=np.int64)
+        return out
+
+    @classmethod
     def new(cls, vox_size):
         h = C.c_void_p()
         _check(lib().vx3b_model_new(float(vox_size), C.byref(h)), "vx3b_model_new")
@@ -141,7 +162,7 @@ class Model:
         shapes = {
             "lattice": (nv, 3), "voxel_mat": (nv,), "phase_offset": (nv,), "base_cilia": (nv, 3), "shift_cilia": (nv, 3),
             "dof_fixed": (nv,), "ext_force": (nv, 3), "ext_moment": (nv, 3), "ext_translation": (nv, 3), "ext_rotation": (nv, 3),
-            "link_neg": (nl,), "link_pos": (nl,), "link_axis": (nl,), "link_mat": (nl,),
+            "link_neg": (nl,), "link_pos": (nl,), "link_axis": (nl,), "link_mat": (nl,), "ghost": (nv,),
         }
         ptr = getattr(d, name)
         shape = shapes[name]
@@ -269,6 +290,25 @@ class Context:
 
     def halo_import(self, world, list_id, device_ptr):
         _check(lib().vx3b_batch_halo_import(self._h, int(world), int(list_id), C.c_void_p(int(device_ptr))), "vx3b_batch_halo_import")
+
+    def halo_open(self, world, list_id):
+        """receive area of a ghost list (device-side exchange); returns the endpoint to hand to the neighbour"""
+        ep = _abi.HaloEndpoint()
+        _check(lib().vx3b_batch_halo_open(self._h, world, list_id, C.byref(ep)), "vx3b_batch_halo_open")
+        return ep
+
+    def halo_connect(self, world, list_id, endpoint, same_process=False):
+        if isinstance(endpoint, (bytes, bytearray)):
+            endpoint = _abi.HaloEndpoint.from_buffer_copy(endpoint)
+        _check(lib().vx3b_batch_halo_connect(self._h, world, list_id, C.byref(endpoint), 1 if same_process else 0), "vx3b_batch_halo_connect")
+
+    def run_slab(self, steps):
+        _check(lib().vx3b_batch_run_slab(self._h, int(steps)), "vx3b_batch_run_slab")
+
+    def halo_timeouts(self):
+        n = C.c_int64()
+        _check(lib().vx3b_batch_halo_timeouts(self._h, C.byref(n)), "vx3b_batch_halo_timeouts")
+        return n.value
 
     def results(self):
         out = (WorldResult * self._n)()

@@ -64,6 +64,18 @@ class WorldDesc(C.Structure):
     ]
 
 
+class SlabInfo(C.Structure):
+    _fields_ = [("part", C.c_int32), ("n_parts", C.c_int32), ("axis", C.c_int32), ("layer_lo", C.c_int32), ("layer_hi", C.c_int32), ("num_own", C.c_int32),
+                ("n_send_lo", C.c_int32), ("n_send_hi", C.c_int32), ("n_ghost_lo", C.c_int32), ("n_ghost_hi", C.c_int32),
+                ("body_voxels", C.c_int64), ("body_links", C.c_int64), ("body_dt", C.c_double),
+                ("send_lo", C.POINTER(C.c_int32)), ("send_hi", C.POINTER(C.c_int32)), ("ghost_lo", C.POINTER(C.c_int32)), ("ghost_hi", C.POINTER(C.c_int32)),
+                ("global_index", C.POINTER(C.c_int64))]
+
+
+class HaloEndpoint(C.Structure):
+    _fields_ = [("ipc_handle", C.c_uint8 * 64), ("device_ptr", C.c_uint64), ("device", C.c_int32), ("n", C.c_int32), ("record_bytes", C.c_int32), ("pad", C.c_int32)]
+
+
 class WorldResult(C.Structure):
     _fields_ = [
         ("current_time", C.c_double), ("fitness_score", C.c_double), ("initial_com", C.c_double * 3), ("current_com", C.c_double * 3),
@@ -109,6 +121,12 @@ SYMBOLS = {
     "vx3b_batch_halo_record_bytes": (C.c_int, [_P]),
     "vx3b_batch_halo_export": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
     "vx3b_batch_halo_import": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
+    "vx3b_batch_halo_open": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(HaloEndpoint)]),
+    "vx3b_batch_halo_connect": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(HaloEndpoint), C.c_int]),
+    "vx3b_batch_run_slab": (C.c_int, [_P, C.c_int64]),
+    "vx3b_batch_halo_timeouts": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "vx3b_model_from_vxa_slab": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vx3b_model_slab_info": (C.c_int, [_P, C.POINTER(SlabInfo)]),
     "vx3b_batch_results": (C.c_int, [_P, C.POINTER(WorldResult)]),
     "vx3b_batch_read_state": (C.c_int, [_P, C.c_int, _DP, _DP, _DP, _DP]),
     "vx3b_batch_read_initial_pos": (C.c_int, [_P, C.c_int, _DP]),

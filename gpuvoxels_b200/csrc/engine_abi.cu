@@ -130,6 +130,12 @@ int vx3b_batch_halo_set(vx3b_ctx *ctx, int world, int list_id, const int32_t *vo
 int vx3b_batch_halo_record_bytes(vx3b_ctx *ctx) { return ctx ? ctx->e->halo_record_bytes() : VX3B_ERR_ARG; }
 int vx3b_batch_halo_export(vx3b_ctx *ctx, int world, int list_id, void *buf) { return ctx ? ctx->e->halo_export(world, list_id, buf) : VX3B_ERR_ARG; }
 int vx3b_batch_halo_import(vx3b_ctx *ctx, int world, int list_id, const void *buf) { return ctx ? ctx->e->halo_import(world, list_id, buf) : VX3B_ERR_ARG; }
+int vx3b_batch_halo_open(vx3b_ctx *ctx, int world, int list_id, VX3B_HaloEndpoint *out) { return ctx && out ? ctx->e->halo_open(world, list_id, out) : VX3B_ERR_ARG; }
+int vx3b_batch_halo_connect(vx3b_ctx *ctx, int world, int list_id, const VX3B_HaloEndpoint *peer, int same_process) {
+    return ctx && peer ? ctx->e->halo_connect(world, list_id, peer, same_process) : VX3B_ERR_ARG;
+}
+int vx3b_batch_run_slab(vx3b_ctx *ctx, int64_t steps) { return ctx ? ctx->e->run_slab(steps) : VX3B_ERR_ARG; }
+int vx3b_batch_halo_timeouts(vx3b_ctx *ctx, int64_t *n) { return ctx && n ? ctx->e->halo_timeouts(n) : VX3B_ERR_ARG; }
 int vx3b_batch_results(vx3b_ctx *ctx, VX3B_WorldResult *out) { return ctx ? ctx->e->results(out) : VX3B_ERR_ARG; }
 int vx3b_batch_read_state(vx3b_ctx *ctx, int world, double *p, double *o, double *l, double *a) {
     return ctx ? ctx->e->read_state(world, p, o, l, a) : VX3B_ERR_ARG;

@@ -27,6 +27,10 @@ class EngineBase {
     virtual int halo_record_bytes() = 0;
     virtual int halo_export(int world, int listId, void *deviceBuffer) = 0;
     virtual int halo_import(int world, int listId, const void *deviceBuffer) = 0;
+    virtual int halo_open(int world, int listId, VX3B_HaloEndpoint *out) = 0;
+    virtual int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess) = 0;
+    virtual int run_slab(int64_t steps) = 0;
+    virtual int halo_timeouts(int64_t *n) = 0;
     // dynamic topology: links in use, signal scalars + removed / attach flags per voxel, current link list
     virtual int num_links(int world, int32_t *n) = 0;
     virtual int read_signals(int world, double *sig6, int32_t *vflags2) = 0;

@@ -772,6 +772,25 @@ template <class R> class EngineMux : public EngineBase {
             return VX3B_ERR_ARG;
         return w.dyn ? no_dynamic("vx3b_batch_halo_import") : S.halo_import(w.idx, listId, deviceBuffer);
     }
+    int halo_open(int world, int listId, VX3B_HaloEndpoint *out) override {
+        Where w;
+        if (!locate(world, w))
+            return VX3B_ERR_ARG;
+        return w.dyn ? no_dynamic("vx3b_batch_halo_open") : S.halo_open(w.idx, listId, out);
+    }
+    int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess) override {
+        Where w;
+        if (!locate(world, w))
+            return VX3B_ERR_ARG;
+        return w.dyn ? no_dynamic("vx3b_batch_halo_connect") : S.halo_connect(w.idx, listId, peer, sameProcess);
+    }
+    int run_slab(int64_t steps) override {
+        if (nDyn)
+            return no_dynamic("vx3b_batch_run_slab");
+        push_options();
+        return S.run_slab(steps);
+    }
+    int halo_timeouts(int64_t *n) override { return S.halo_timeouts(n); }
 };
 
 } // namespace vx3b

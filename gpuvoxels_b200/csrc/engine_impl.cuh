@@ -205,6 +205,14 @@ template <class R> class Engine : public EngineBase {
         int32_t *dVox = nullptr, *dSlots = nullptr;
     };
     HaloList halo[8];
+    struct HaloLink { // device-side exchange: a ghost list owns `area`, a send list maps the neighbour's as `peer`
+        void *area = nullptr, *peer = nullptr;
+        bool peerIpc = false;
+        HaloSync *sync = nullptr;
+    };
+    HaloLink haloLink[8];
+    std::map<int, cudaGraphExec_t> slabGraphs; // chunk length -> step + exchange graph
+    bool slabGraphsStale = false;
     std::vector<int> brickWorldList;
     struct BrickHost {
         std::vector<BrickB> bricks;
@@ -229,6 +237,7 @@ template <class R> class Engine : public EngineBase {
         release_classes();
         if (stream)
             cudaStreamSynchronize(stream);
+        release_halo_links();
         unpin_all();
         arena.release();
         if (ownStream && stream)
@@ -264,6 +273,7 @@ template <class R> class Engine : public EngineBase {
             hl = HaloList{};
         if (stream)
             CUDA_TRY(cudaStreamSynchronize(stream)); // nothing of the previous batch is still in flight when its memory is reused
+        release_halo_links();
         arena.reset();
         H.clear();
         hTiles.clear();
@@ -1805,6 +1815,176 @@ template <class R> class Engine : public EngineBase {
     }
     int halo_export(int world, int listId, void *buf) override { return halo_transfer(world, listId, buf, true); }
     int halo_import(int world, int listId, const void *buf) override { return halo_transfer(world, listId, const_cast<void *>(buf), false); }
+
+    // ---- device-side exchange (include/vx3b200.h section 2b; kernels: k_halo_push / k_halo_pull) -----------------------------------
+    // Receive area of a ghost list, in this device's memory: [flag, padded to 128 B][buffer 0: n records][buffer 1: n records].
+    // Plain cudaMalloc (not the arena): cudaIpcGetMemHandle needs an allocation of its own.
+    static size_t halo_area_bytes(int n) { return 128 + 2 * (size_t)n * sizeof(HaloRec<R>); }
+    void release_halo_links() {
+        for (auto &k : haloLink) {
+            if (k.peer && k.peerIpc)
+                cudaIpcCloseMemHandle(k.peer);
+            if (k.area)
+                cudaFree(k.area);
+            if (k.sync)
+                cudaFree(k.sync);
+            k = HaloLink{};
+        }
+        for (auto &kv : slabGraphs)
+            cudaGraphExecDestroy(kv.second);
+        slabGraphs.clear();
+    }
+    int halo_sync_alloc(HaloLink &K) {
+        if (!K.sync) {
+            CUDA_TRY(cudaMalloc(&K.sync, sizeof(HaloSync)));
+            CUDA_TRY(cudaMemset(K.sync, 0, sizeof(HaloSync)));
+        }
+        return VX3B_OK;
+    }
+    int halo_open(int world, int listId, VX3B_HaloEndpoint *out) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (listId < 0 || listId >= 8 || halo[listId].world != world || halo[listId].n <= 0) {
+            set_error("vx3b_batch_halo_open: list not registered for this world (vx3b_batch_halo_set), or empty");
+            return VX3B_ERR_ARG;
+        }
+        HaloLink &K = haloLink[listId];
+        if (K.peer) {
+            set_error("vx3b_batch_halo_open: this list is already connected as a send list");
+            return VX3B_ERR_STATE;
+        }
+        int rc = halo_sync_alloc(K);
+        if (rc != VX3B_OK)
+            return rc;
+        if (!K.area) {
+            CUDA_TRY(cudaMalloc(&K.area, halo_area_bytes(halo[listId].n)));
+            CUDA_TRY(cudaMemset(K.area, 0, halo_area_bytes(halo[listId].n)));
+        }
+        memset(out, 0, sizeof(*out));
+        cudaIpcMemHandle_t h;
+        if (cudaIpcGetMemHandle(&h, K.area) == cudaSuccess) // (fails e.g. under a profiler's restrictions: same-process use still works)
+            memcpy(out->ipc_handle, &h, sizeof(h) < sizeof(out->ipc_handle) ? sizeof(h) : sizeof(out->ipc_handle));
+        else
+            cudaGetLastError();
+        out->device_ptr = (uint64_t)(uintptr_t)K.area;
+        out->device = device;
+        out->n = halo[listId].n;
+        out->record_bytes = (int32_t)sizeof(HaloRec<R>);
+        slabGraphsStale = true;
+        return VX3B_OK;
+    }
+    int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (listId < 0 || listId >= 8 || halo[listId].world != world || halo[listId].n <= 0) {
+            set_error("vx3b_batch_halo_connect: list not registered for this world (vx3b_batch_halo_set), or empty");
+            return VX3B_ERR_ARG;
+        }
+        if (peer->n != halo[listId].n || peer->record_bytes != (int32_t)sizeof(HaloRec<R>)) {
+            set_error("vx3b_batch_halo_connect: the neighbour's ghost list has " + std::to_string(peer->n) + " records of " + std::to_string(peer->record_bytes) +
+                      " bytes, this send list " + std::to_string(halo[listId].n) + " of " + std::to_string(sizeof(HaloRec<R>)));
+            return VX3B_ERR_ARG;
+        }
+        HaloLink &K = haloLink[listId];
+        if (K.area) {
+            set_error("vx3b_batch_halo_connect: this list is already open as a ghost list");
+            return VX3B_ERR_STATE;
+        }
+        int rc = halo_sync_alloc(K);
+        if (rc != VX3B_OK)
+            return rc;
+        if (K.peer && K.peerIpc)
+            cudaIpcCloseMemHandle(K.peer);
+        K.peer = nullptr;
+        if (sameProcess) {
+            K.peer = (void *)(uintptr_t)peer->device_ptr;
+            K.peerIpc = false;
+            if (peer->device != device) { // another device of this process: needs peer access (NVLink)
+                cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    set_error(std::string("vx3b_batch_halo_connect: cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                    return VX3B_ERR_CUDA;
+                }
+                cudaGetLastError();
+            }
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, peer->ipc_handle, sizeof(h) < sizeof(peer->ipc_handle) ? sizeof(h) : sizeof(peer->ipc_handle));
+            CUDA_TRY(cudaIpcOpenMemHandle(&K.peer, h, cudaIpcMemLazyEnablePeerAccess));
+            K.peerIpc = true;
+        }
+        slabGraphsStale = true;
+        return VX3B_OK;
+    }
+    void enqueue_exchange() {
+        for (int id = 0; id < 8; id++) { // pushes first: the neighbours wait for them
+            const HaloLink &K = haloLink[id];
+            const HaloList &L = halo[id];
+            if (!K.peer || L.n <= 0)
+                continue;
+            char *base = (char *)K.peer;
+            k_halo_push<R><<<(unsigned)((L.n + 127) / 128), 128, 0, stream>>>(A, BA, L.world, L.dVox, L.dSlots, L.n, 1, (HaloRec<R> *)(base + 128),
+                                                                            (HaloRec<R> *)(base + 128) + L.n, (unsigned long long *)base, K.sync);
+        }
+        for (int id = 0; id < 8; id++) {
+            const HaloLink &K = haloLink[id];
+            const HaloList &L = halo[id];
+            if (!K.area || L.n <= 0)
+                continue;
+            const char *base = (const char *)K.area;
+            k_halo_pull<R><<<(unsigned)((L.n + 127) / 128), 128, 0, stream>>>(A, BA, L.world, L.dVox, L.dSlots, L.n, 1, (const HaloRec<R> *)(base + 128),
+                                                                            (const HaloRec<R> *)(base + 128) + L.n, (const unsigned long long *)base, K.sync);
+        }
+    }
+    int run_slab(int64_t steps) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (H.empty() || BA.nBricks == 0 || nBrickWorlds != (int)H.size() || !fusedAllWorlds || FA.nBricks > 0) {
+            set_error("vx3b_batch_run_slab: every world must be on the brick path (option path = 5 before upload; no collision, force field or targets)");
+            return VX3B_ERR_STATE;
+        }
+        const unsigned wb = (A.nWorlds + 127) / 128, nbb = (unsigned)((std::max(BA.nvSlots, BA.nlSlots) + 255) / 256);
+        k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)steps, 0, 0, 1);
+        if (!brickResident) {
+            k_brick_pack<R><<<nbb, 256, 0, stream>>>(A, BA);
+            brickResident = true;
+        }
+        if (slabGraphsStale) {
+            for (auto &kv : slabGraphs)
+                cudaGraphExecDestroy(kv.second);
+            slabGraphs.clear();
+            slabGraphsStale = false;
+        }
+        int64_t done = 0;
+        while (done < steps) {
+            const int c = (int)std::min<int64_t>(chunk, steps - done);
+            auto it = slabGraphs.find(c);
+            if (it == slabGraphs.end()) {
+                cudaGraph_t g;
+                cudaGraphExec_t ge;
+                CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                for (int k = 0; k < c; k++) {
+                    enqueue_step(0, false, true);
+                    enqueue_exchange();
+                }
+                CUDA_TRY(cudaStreamEndCapture(stream, &g));
+                CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
+                cudaGraphDestroy(g);
+                it = slabGraphs.emplace(c, ge).first;
+            }
+            CUDA_TRY(cudaGraphLaunch(it->second, stream));
+            done += c;
+        }
+        return VX3B_OK;
+    }
+    int halo_timeouts(int64_t *n) override {
+        CUDA_TRY(cudaSetDevice(device));
+        *n = 0;
+        for (auto &K : haloLink)
+            if (K.sync) {
+                HaloSync hs;
+                CUDA_TRY(cudaMemcpy(&hs, K.sync, sizeof(hs), cudaMemcpyDeviceToHost));
+                *n += hs.timeouts;
+            }
+        return VX3B_OK;
+    }
 
     std::vector<WorldD> resultScratch;
     int read_steps(std::vector<int64_t> &out) { // only the step counters: a strided copy of 8 bytes per world, not 5.5 KB

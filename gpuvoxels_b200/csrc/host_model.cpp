@@ -25,7 +25,7 @@ void HostModel::ensureExt() {
     extRotation.resize(nv * 3, 0.0);
 }
 
-int HostModel::setVoxel(int mat, int ix, int iy, int iz, std::string *err) {
+int HostModel::setVoxel(int mat, int ix, int iy, int iz, std::string *err, bool isGhost) {
     if (mat < 0 || mat >= (int)mats.size()) {
         if (err)
             *err = "set_voxel: no such material index " + std::to_string(mat);
@@ -48,7 +48,11 @@ int HostModel::setVoxel(int mat, int ix, int iy, int iz, std::string *err) {
     phaseOffset.push_back(0.0);
     baseCilia.insert(baseCilia.end(), 3, 0.0);
     shiftCilia.insert(shiftCilia.end(), 3, 0.0);
-    occupied[std::make_tuple(ix, iy, iz)] = v;
+    occupied.set(ix, iy, iz, v);
+    if (isGhost || !ghost.empty())
+        ghost.resize((size_t)v + 1, 0);
+    if (isGhost)
+        ghost[v] = 1;
     ensureExt();
     // links to already-present neighbours, directions X_POS,X_NEG,Y_POS,Y_NEG,Z_POS,Z_NEG
     // (CVoxelyze::addVoxel, old/Voxelyze.cpp:439-461; end ordering CVX_Link ctor old/VX_Link.cpp:20-49)
@@ -58,13 +62,12 @@ int HostModel::setVoxel(int mat, int ix, int iy, int iz, std::string *err) {
         int o = voxelAt(nx, ny, nz);
         if (o < 0)
             continue;
+        if (isGhost && ghost[o])
+            continue; // a link between two ghosts belongs to the neighbouring slab alone
         int axis = dir / 2;
         bool positive = (dir % 2) == 0; // neighbour lies on our positive side -> we are the negative end
         int neg = positive ? v : o, pos = positive ? o : v;
-        auto key = std::make_tuple(axis, (int)lattice[neg * 3], (int)lattice[neg * 3 + 1], (int)lattice[neg * 3 + 2]);
-        if (linkAt.count(key))
-            continue;
-        linkAt[key] = (int)linkNeg.size();
+        // (v is new, so no link between the two exists yet)
         linkNeg.push_back(neg);
         linkPos.push_back(pos);
         linkAxis.push_back((uint8_t)axis);
@@ -337,6 +340,13 @@ bool HostModel::finalize(std::string *err) {
     }
     linkMatPairs.clear();
     linkMats.clear();
+    for (auto &pr : presetLinkMatPairs) { // a slab: the whole body's combined materials, in the whole body's order
+        linkMatPairs.push_back(pr);
+        VX3B_LinkMaterial lm;
+        if (!derive_link_material(voxelMats[pr.first], mats[pr.first], voxelMats[pr.second], mats[pr.second], pr.first, pr.second, &lm, err))
+            return false;
+        linkMats.push_back(lm);
+    }
     for (size_t l = 0; l < linkNeg.size(); l++) {
         // CVoxelyze::combinedMaterial (old/Voxelyze.cpp:614-628): first use creates, later uses find (either order)
         int a = voxelMat[linkNeg[l]], b = voxelMat[linkPos[l]];
@@ -414,6 +424,7 @@ void HostModel::fillDesc(VX3B_WorldDesc *d) const {
     d->link_pos = linkPos.data();
     d->link_axis = linkAxis.data();
     d->link_mat = linkMat.data();
+    d->ghost = ghost.empty() ? nullptr : ghost.data();
     d->voxel_mats = voxelMats.data();
     d->link_mats = linkMats.data();
     d->dt_frac = dtFrac;
@@ -662,7 +673,7 @@ std::vector<const XmlNode *> layers_of(const XmlNode *parent) {
 
 } // namespace
 
-std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char *vxdText, std::string *err) {
+std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char *vxdText, std::string *err, const SlabCut *cut) {
     std::string perr;
     auto doc = xml_parse(vxaText, &perr);
     if (!doc) {
@@ -901,7 +912,7 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
             *err = "Structure/Data has fewer <Layer> elements than Z_Voxels";
         return nullptr;
     }
-    std::vector<int> cell((size_t)X * Y * Z, 0);
+    std::vector<signed char> cell((size_t)X * Y * Z, 0); // (a byte per cell: a 400^3 body is 64 M cells)
     for (int z = 0; z < Z; z++) {
         const std::string &raw = dataLayers[z]->text; // CDATA content, untrimmed like tinyxml's CDATA text
         std::string t = raw.size() == (size_t)X * Y ? raw : xml_trim(raw);
@@ -911,7 +922,7 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
             return nullptr;
         }
         for (int k = 0; k < X * Y; k++)
-            cell[(size_t)X * Y * z + k] = (int)(signed char)(t[k] - 48);
+            cell[(size_t)X * Y * z + k] = (signed char)(t[k] - 48);
     }
     // per-voxel CSV layers, indexed over present voxels only (VX_Object.cpp:1851-1959)
     std::vector<double> phase, baseC, shiftC;
@@ -948,8 +959,60 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
     read_vec3_layers("BaseCiliaForce", baseC);
     read_vec3_layers("ShiftCiliaForce", shiftC);
 
+    // one slab of the body (include/vx3b200.h section 2b): cut the layers along the axis into nParts ranges holding (nearly) equal
+    // numbers of voxels; this model gets range `part` and, as ghosts, the cells of the layer below / above it that a cut link joins
+    // to one of its own.  The same rule on every rank, so neighbouring slabs agree on the cut and on the order of the exchange lists.
+    const int dims[3] = {X, Y, Z};
+    auto cell_at = [&](int x, int y, int z) -> int { return (x < 0 || y < 0 || z < 0 || x >= X || y >= Y || z >= Z) ? 0 : (int)cell[(size_t)X * Y * z + (size_t)X * y + x]; };
+    int lo = 0, hi = 0;
+    if (cut) {
+        if (cut->axis < 0 || cut->axis > 2 || cut->nParts < 1 || cut->part < 0 || cut->part >= cut->nParts) {
+            if (err)
+                *err = "slab: axis must be 0..2 and 0 <= part < n_parts";
+            return nullptr;
+        }
+        const int n = dims[cut->axis];
+        std::vector<int64_t> perLayer((size_t)n, 0);
+        int first = n, last = -1;
+        for (int z = 0; z < Z; z++)
+            for (int y = 0; y < Y; y++)
+                for (int x = 0; x < X; x++)
+                    if (cell[(size_t)X * Y * z + (size_t)X * y + x] > 0) {
+                        const int c = cut->axis == 0 ? x : cut->axis == 1 ? y : z;
+                        perLayer[c]++;
+                        first = std::min(first, c), last = std::max(last, c);
+                    }
+        if (last < first || last - first + 1 < cut->nParts) {
+            if (err)
+                *err = "slab: cannot cut " + std::to_string(std::max(0, last - first + 1)) + " lattice layers into " + std::to_string(cut->nParts) + " slabs";
+            return nullptr;
+        }
+        std::vector<int64_t> cum;
+        int64_t run = 0;
+        for (int c = first; c <= last; c++)
+            cum.push_back(run += perLayer[c]);
+        std::vector<int> bounds{first};
+        for (int k = 1; k < cut->nParts; k++) { // first layer whose cumulative count reaches k/nParts of the body, then one past it
+            const double want = (double)run * k / cut->nParts;
+            int idx = (int)(std::lower_bound(cum.begin(), cum.end(), want, [](int64_t a, double b) { return (double)a < b; }) - cum.begin());
+            int layer = idx + 1 + first;
+            bounds.push_back(std::min(std::max(layer, bounds.back() + 1), last + 1));
+        }
+        bounds.push_back(last + 1);
+        for (size_t k = 1; k < bounds.size(); k++)
+            if (bounds[k] <= bounds[k - 1]) {
+                if (err)
+                    *err = "slab: a slab would be empty";
+                return nullptr;
+            }
+        lo = bounds[cut->part], hi = bounds[cut->part + 1];
+        M->slab.part = cut->part, M->slab.nParts = cut->nParts, M->slab.axis = cut->axis, M->slab.layerLo = lo, M->slab.layerHi = hi;
+    }
+    const int ax = cut ? cut->axis : 2;
+    const int step[3] = {ax == 0 ? 1 : 0, ax == 1 ? 1 : 0, ax == 2 ? 1 : 0};
+
     // voxels in x-fastest, y, z order (VX_Sim.cpp:92-107)
-    int counter = 0;
+    int64_t counter = 0; // occupied cells of the whole body so far = the voxel's index in the whole body
     for (int z = 0; z < Z; z++)
         for (int y = 0; y < Y; y++)
             for (int x = 0; x < X; x++) {
@@ -961,21 +1024,109 @@ std::unique_ptr<HostModel> model_from_vxa(const std::string &vxaText, const char
                         *err = "Structure refers to material " + std::to_string(c) + " which is not in the palette";
                     return nullptr;
                 }
-                int v = M->setVoxel(paletteToMat[c - 1], x, y, z, err);
+                bool isGhost = false;
+                if (cut) {
+                    const int co = ax == 0 ? x : ax == 1 ? y : z;
+                    const bool own = co >= lo && co < hi;
+                    if (!own) {
+                        isGhost = (co == lo - 1 && cell_at(x + step[0], y + step[1], z + step[2]) > 0) ||
+                                  (co == hi && cell_at(x - step[0], y - step[1], z - step[2]) > 0);
+                        if (!isGhost) {
+                            counter++;
+                            continue;
+                        }
+                    }
+                }
+                int v = M->setVoxel(paletteToMat[c - 1], x, y, z, err, isGhost);
                 if (v < 0)
                     return nullptr;
-                if ((int)phase.size() > counter)
+                if ((int64_t)phase.size() > counter)
                     M->phaseOffset[v] = phase[counter];
-                if ((int)baseC.size() > counter * 3 + 2)
+                if ((int64_t)baseC.size() > counter * 3 + 2)
                     for (int k = 0; k < 3; k++)
                         M->baseCilia[v * 3 + k] = baseC[counter * 3 + k];
-                if ((int)shiftC.size() > counter * 3 + 2)
+                if ((int64_t)shiftC.size() > counter * 3 + 2)
                     for (int k = 0; k < 3; k++)
                         M->shiftCilia[v * 3 + k] = shiftC[counter * 3 + k];
+                if (cut) {
+                    const int co = ax == 0 ? x : ax == 1 ? y : z;
+                    HostModel::Slab &S = M->slab;
+                    S.globalIndex.push_back(counter);
+                    if (isGhost)
+                        (co < lo ? S.ghostLo : S.ghostHi).push_back(v);
+                    else {
+                        S.numOwn++;
+                        // my boundary voxels that the lower / upper neighbour holds as ghosts = own ends of the cut links towards it
+                        if (co == lo && cut->part > 0 && cell_at(x - step[0], y - step[1], z - step[2]) > 0)
+                            S.sendLo.push_back(v);
+                        if (co == hi - 1 && cut->part < cut->nParts - 1 && cell_at(x + step[0], y + step[1], z + step[2]) > 0)
+                            S.sendHi.push_back(v);
+                    }
+                }
                 counter++;
             }
+    if (cut && M->ghost.size() < (size_t)M->numVoxels())
+        M->ghost.resize((size_t)M->numVoxels(), 0);
+    if (cut) {
+        // whole-body figures every slab needs: voxel / link counts, and the material pairs the body's links join IN THE ORDER the whole
+        // body first uses them (CVoxelyze::combinedMaterial, old/Voxelyze.cpp:614-628: a voxel links to its already-present -x, -y, -z
+        // neighbours, which are the negative ends), so that link-material numbers and orientations equal the whole body's
+        HostModel::Slab &S = M->slab;
+        S.bodyVoxels = counter;
+        for (int z = 0; z < Z; z++)
+            for (int y = 0; y < Y; y++)
+                for (int x = 0; x < X; x++) {
+                    const int c = cell[(size_t)X * Y * z + (size_t)X * y + x];
+                    if (c <= 0)
+                        continue;
+                    const int nb[3] = {cell_at(x - 1, y, z), cell_at(x, y - 1, z), cell_at(x, y, z - 1)};
+                    for (int k = 0; k < 3; k++) {
+                        if (nb[k] <= 0)
+                            continue;
+                        S.bodyLinks++;
+                        const int a = paletteToMat[nb[k] - 1], b = paletteToMat[c - 1];
+                        bool have = false;
+                        for (auto &pr : M->presetLinkMatPairs)
+                            have = have || (pr.first == a && pr.second == b) || (pr.first == b && pr.second == a);
+                        if (!have)
+                            M->presetLinkMatPairs.emplace_back(a, b);
+                    }
+                }
+        if (M->presetLinkMatPairs.empty()) {
+            if (err)
+                *err = "slab: the body has no links";
+            return nullptr;
+        }
+    }
     if (!M->finalize(err))
         return nullptr;
+    if (cut) {
+        // recommended time step as host_dt.hpp computes it on a whole-body description (VX3_VoxelyzeKernel.cu:184-217; old/Voxelyze.cpp:286-311)
+        HostModel::Slab &S = M->slab;
+        const bool vx3 = !M->vx2Compat;
+        double maxF2d = 0.0f;
+        float maxF2f = 0.0f;
+        for (size_t k = 0; k < M->presetLinkMatPairs.size(); k++) {
+            const VX3B_LinkMaterial &lm = M->linkMats[k];
+            const int a = M->presetLinkMatPairs[k].first, b = M->presetLinkMatPairs[k].second;
+            if (lm.nu != 0.0f) {
+                if (err)
+                    *err = "slab: a body with Poisson's ratio != 0 cannot be cut (its time step depends on every link's rest length)";
+                return nullptr;
+            }
+            if (vx3) {
+                const double m1 = M->voxelMats[a].mass, m2 = M->voxelMats[b].mass;
+                maxF2d = std::max(maxF2d, (double)(lm.a1 / (m1 < m2 ? m1 : m2)));
+            } else {
+                const float m1 = M->voxelMats[a].mass, m2 = M->voxelMats[b].mass;
+                maxF2f = std::max(maxF2f, lm.a1 / (m1 < m2 ? m1 : m2));
+            }
+        }
+        double opt = vx3 ? 1.0f / (6.283185f * sqrt(maxF2d)) : (double)(float)(1.0f / (6.283185f * sqrtf(maxF2f)));
+        if (vx3 && opt < 1e-10)
+            opt = 1e-10;
+        S.bodyDt = (double)(float)(M->dtFrac * opt);
+    }
     return M;
 }
 
@@ -1021,6 +1172,38 @@ static bool slurp(const char *path, std::string *out) {
     ss << f.rdbuf();
     *out = ss.str();
     return true;
+}
+
+int vx3b_model_from_vxa_slab(const char *vxa_xml, const char *vxd_xml, int axis, int part, int n_parts, vx3b_model **out) {
+    if (!vxa_xml || !out) {
+        vx3b::set_error("vx3b_model_from_vxa_slab: null argument");
+        return VX3B_ERR_ARG;
+    }
+    std::string err;
+    const vx3b::SlabCut cut{axis, part, n_parts};
+    auto m = vx3b::model_from_vxa(vxa_xml, vxd_xml, &err, &cut);
+    if (!m) {
+        vx3b::set_error(err);
+        return VX3B_ERR_PARSE;
+    }
+    *out = new vx3b_model{std::move(m)};
+    return VX3B_OK;
+}
+
+int vx3b_model_slab_info(const vx3b_model *m, VX3B_SlabInfo *out) {
+    if (!m || !out || m->m->slab.nParts == 0) {
+        vx3b::set_error("vx3b_model_slab_info: not a slab model (vx3b_model_from_vxa_slab)");
+        return VX3B_ERR_ARG;
+    }
+    const vx3b::HostModel::Slab &S = m->m->slab;
+    memset(out, 0, sizeof(*out));
+    out->part = S.part, out->n_parts = S.nParts, out->axis = S.axis, out->layer_lo = S.layerLo, out->layer_hi = S.layerHi, out->num_own = S.numOwn;
+    out->n_send_lo = (int32_t)S.sendLo.size(), out->n_send_hi = (int32_t)S.sendHi.size();
+    out->n_ghost_lo = (int32_t)S.ghostLo.size(), out->n_ghost_hi = (int32_t)S.ghostHi.size();
+    out->body_voxels = S.bodyVoxels, out->body_links = S.bodyLinks, out->body_dt = S.bodyDt;
+    out->send_lo = S.sendLo.data(), out->send_hi = S.sendHi.data(), out->ghost_lo = S.ghostLo.data(), out->ghost_hi = S.ghostHi.data();
+    out->global_index = S.globalIndex.data();
+    return VX3B_OK;
 }
 
 int vx3b_model_from_files(const char *vxa_path, const char *vxd_path, vx3b_model **out) {

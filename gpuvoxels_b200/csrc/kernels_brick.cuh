@@ -682,4 +682,94 @@ template <class R> __global__ void k_halo_import(Arrays<R> A, BrickArrays<R> BA,
         A.pxy[vox[i]] = a, A.pzt[vox[i]] = b, A.orient[vox[i]] = r.orient;
 }
 
+// ---- device-side exchange: no host in the loop ----------------------------------------------------------------------------
+// The neighbouring slab's receive area (two record buffers + a sequence flag, in ITS memory) is mapped into this process (CUDA IPC
+// over NVLink, or a plain pointer when both slabs live in one process).  k_halo_push writes this step's records straight into the
+// buffer of the step's parity and then raises the flag to the step's sequence number; k_halo_pull on the other side waits for that
+// number and unpacks.  Two buffers suffice: a sender can be at most one step ahead of the slab it feeds (its step s + 2 needs that
+// slab's step s + 1, which is enqueued after that slab's pull of step s).
+struct HaloSync {
+    unsigned long long seq;    // exchanges completed on this side of the link
+    unsigned int ticket;       // CTAs of the running kernel that have finished
+    unsigned int timeouts;     // pulls that gave up waiting (the run is invalid; reported by the host)
+};
+VXD unsigned long long halo_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+template <class R>
+__global__ void k_halo_push(Arrays<R> A, BrickArrays<R> BA, int world, const int32_t *vox, const int32_t *slots, int n, int resident, HaloRec<R> *peer0,
+                            HaloRec<R> *peer1, unsigned long long *peerFlag, HaloSync *sync) {
+    const unsigned long long next = sync->seq + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        D2 a, b;
+        typename Store<R>::T4 o;
+        if (resident) {
+            const BrickSet<R> &s = BA.set[A.worlds[world].parity];
+            a = s.pxy[slots[i]], b = s.pzt[slots[i]], o = s.orient[slots[i]];
+        } else
+            a = A.pxy[vox[i]], b = A.pzt[vox[i]], o = A.orient[vox[i]];
+        HaloRec<R> r;
+        r.x = a.x, r.y = a.y, r.z = b.x;
+        r.packed = (unsigned long long)__double_as_longlong(b.y);
+        r.orient = o;
+        ((next & 1) ? peer1 : peer0)[i] = r;
+    }
+    __threadfence_system(); // the records are visible to the peer before the flag can be
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&sync->ticket, 1u) == gridDim.x - 1) { // the last CTA to finish
+        sync->ticket = 0;
+        sync->seq = next;
+        __threadfence_system();
+        *(volatile unsigned long long *)peerFlag = next;
+    }
+}
+template <class R>
+__global__ void k_halo_pull(Arrays<R> A, BrickArrays<R> BA, int world, const int32_t *vox, const int32_t *slots, int n, int resident, const HaloRec<R> *buf0,
+                            const HaloRec<R> *buf1, const unsigned long long *flag, HaloSync *sync) {
+    __shared__ int ok;
+    const unsigned long long want = sync->seq + 1;
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = halo_now_ns();
+        ok = 1;
+        while (*(const volatile unsigned long long *)flag < want) {
+            __nanosleep(200);
+            if (halo_now_ns() - t0 > 10000000000ull) { // 10 s: the neighbour is gone; never hang the device
+                ok = 0;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ok && i < n) {
+        const HaloRec<R> *src = ((want & 1) ? buf1 : buf0) + i;
+        HaloRec<R> r; // (cache-volatile loads: the lines were written by another device)
+        static_assert(sizeof(HaloRec<R>) % 16 == 0, "halo record is copied in 16-byte pieces");
+        const uint4 *s4 = (const uint4 *)src;
+        uint4 *d4 = (uint4 *)&r;
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(HaloRec<R>) / 16); k++)
+            d4[k] = __ldcv(s4 + k);
+        const D2 a{r.x, r.y}, b{r.z, __longlong_as_double((long long)r.packed)};
+        if (resident) {
+            const BrickSet<R> &s = BA.set[A.worlds[world].parity];
+            s.pxy[slots[i]] = a, s.pzt[slots[i]] = b, s.orient[slots[i]] = r.orient;
+        } else
+            A.pxy[vox[i]] = a, A.pzt[vox[i]] = b, A.orient[vox[i]] = r.orient;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!ok)
+            atomicAdd(&sync->timeouts, 1u);
+        if (atomicAdd(&sync->ticket, 1u) == gridDim.x - 1) {
+            sync->ticket = 0;
+            sync->seq = want;
+        }
+    }
+}
+
 } // namespace vx3b

@@ -10,9 +10,15 @@ The lattice is regular and links only join 6-neighbours, so a cut perpendicular 
   * after every time step each rank sends the new position / temperature / orientation of its boundary voxels to the neighbour
     that holds them as ghosts (28-48 bytes per voxel and face) - the only data-path exchange, neighbour to neighbour.
 
-`split_body` is pure numpy on the host model; `SlabRunner` drives one slab through the C ABI (vx3b_batch_run_async +
-vx3b_batch_halo_export / _import) with the exchange done by a caller-supplied function: NCCL send/recv over torch.distributed
-in bench.py, plain device copies when several slabs share one GPU (tests).
+`native_part` asks the C++ host model for ONE slab (vx3b_model_from_vxa_slab: every rank parses the text and builds only its own
+voxels, ghosts and exchange lists - what a 400^3 body needs); `split_body` is the same cut in numpy on a whole-body model and
+stays as its cross-check (tests/test_slab.py).  `SlabRunner` drives one slab through the C ABI, with either of two exchanges:
+
+  * device-side (`connect` + `run`): the neighbour's receive area is mapped into this process (CUDA IPC over NVLink; a plain
+    pointer inside one process), k_halo_push stores the boundary records straight into it and raises a flag, k_halo_pull waits
+    for the flag - no host, no NCCL call in the loop, 64 time steps per CUDA graph (vx3b_batch_run_slab);
+  * host-driven (`step_begin` / `step_end` around a caller-supplied exchange of packed buffers: NCCL send/recv in bench.py
+    --slab-exchange nccl, plain device copies in the tests) - the round-1 path, kept as the reference point.
 """
 import numpy as np
 
@@ -35,6 +41,17 @@ class SlabPart:
     @property
     def num_own(self):
         return int(self.own.sum())
+
+
+def native_part(vxa_text, vxd_text, rank, n_parts, axis=2):
+    """Rank `rank`'s slab straight from the VXA (+ VXD) text, built by the C++ host model; .body_dt is the whole body's time step"""
+    from . import Model
+    m = Model.from_vxa_slab(vxa_text, vxd_text, axis, rank, n_parts)
+    si = m.slab_info()
+    own = m.array("ghost") == 0
+    p = SlabPart(rank, n_parts, m, si["global_index"], own, si["send_lo"], si["send_hi"], si["ghost_lo"], si["ghost_hi"])
+    p.body_dt, p.body_voxels, p.body_links = si["body_dt"], si["body_voxels"], si["body_links"]
+    return p
 
 
 def slab_bounds(coords, n_parts):
@@ -141,6 +158,25 @@ class SlabRunner:
         for lid in (GHOST_LO, GHOST_HI):
             if self.buf[lid] is not None:
                 self.ctx.halo_import(0, lid, self.buf[lid].data_ptr())
+
+    # -- device-side exchange -----------------------------------------------------------------------------------------------
+    def open_endpoints(self):
+        """receive areas of my two ghost lists -> {"lo": bytes | None, "hi": bytes | None} to hand to the neighbours"""
+        out = {}
+        for name, lid, idx in (("lo", GHOST_LO, self.part.ghost_lo), ("hi", GHOST_HI, self.part.ghost_hi)):
+            out[name] = bytes(self.ctx.halo_open(0, lid)) if len(idx) else None
+        return out
+
+    def connect(self, lower_hi_endpoint, upper_lo_endpoint, same_process=False):
+        """my send lists write into the lower neighbour's "hi" area and the upper neighbour's "lo" area"""
+        if len(self.part.send_lo):
+            self.ctx.halo_connect(0, SEND_LO, lower_hi_endpoint, same_process)
+        if len(self.part.send_hi):
+            self.ctx.halo_connect(0, SEND_HI, upper_lo_endpoint, same_process)
+
+    def run(self, steps):
+        """`steps` time steps with the device-side exchange after each (asynchronous; every slab must be given the same count)"""
+        self.ctx.run_slab(steps)
 
     def own_state(self):
         s = self.ctx.read_state(0)

@@ -207,6 +207,26 @@ int vx3b_model_desc(const vx3b_model *m, VX3B_WorldDesc *out); /* pointers stay 
 int vx3b_model_merged_vxa(const vx3b_model *m, char *buf, int64_t cap, int64_t *needed); /* merged VXA text (for the reference harness) */
 void vx3b_model_free(vx3b_model *m);
 
+/* ONE SLAB of a body (section 2b; no reference counterpart - a reference world never spans devices).  Parses the same VXA (+ VXD)
+ * but keeps only the voxels whose lattice coordinate along `axis` (0 x, 1 y, 2 z) falls into range `part` of `n_parts` ranges
+ * holding (nearly) equal numbers of voxels, plus - flagged in VX3B_WorldDesc.ghost - the voxels of the two neighbouring slabs that
+ * a cut link joins to one of its own.  Every process builds only its own slab: nothing of the size of the whole body but one
+ * byte per lattice cell.  Voxels keep the creation order of the whole body (VX_Sim.cpp:92-107). */
+typedef struct VX3B_SlabInfo {
+    int32_t part, n_parts, axis;
+    int32_t layer_lo, layer_hi;   /* own lattice layers [layer_lo, layer_hi) along axis */
+    int32_t num_own;              /* voxels of this model that are not ghosts */
+    int32_t n_send_lo, n_send_hi, n_ghost_lo, n_ghost_hi;
+    int64_t body_voxels, body_links; /* of the whole body */
+    double body_dt;               /* the time step the WHOLE body takes (context option "dt_override" of every slab) */
+    /* exchange lists, voxel indices of THIS model, ascending = in the whole body's creation order, so a sender's list and the
+     * receiver's ghost list name the same voxels in the same order; owned by the model */
+    const int32_t *send_lo, *send_hi, *ghost_lo, *ghost_hi;
+    const int64_t *global_index;  /* [num_voxels] voxel of this model -> voxel of the whole body */
+} VX3B_SlabInfo;
+int vx3b_model_from_vxa_slab(const char *vxa_xml, const char *vxd_xml /* may be NULL */, int axis, int part, int n_parts, vx3b_model **out);
+int vx3b_model_slab_info(const vx3b_model *m, VX3B_SlabInfo *out);
+
 /* ---------------------------------------------------------------- 2. step engine -----
  * Replaces VX3_VoxelyzeKernel (host ctor, VX3_VoxelyzeKernel.cu:27-105) + CUDA_Simulation
  * + doTimeStep and all gpu_update_* kernels (VX3_VoxelyzeKernel.cu:237-359, 566-650, 833-859). */
@@ -272,6 +292,26 @@ int vx3b_batch_halo_record_bytes(vx3b_ctx *ctx); /* bytes per voxel record: pos 
 /* pack / unpack the current records of a registered list into / from a DEVICE buffer of n * record_bytes, on the context's stream */
 int vx3b_batch_halo_export(vx3b_ctx *ctx, int world, int list_id, void *device_buffer);
 int vx3b_batch_halo_import(vx3b_ctx *ctx, int world, int list_id, const void *device_buffer);
+/* Device-side exchange: no host, no NCCL call in the time-step loop.  A slab's ghost list gets a RECEIVE AREA in its own device
+ * memory (two record buffers + a sequence flag); the neighbour that owns those voxels maps the area (CUDA IPC across processes, a
+ * plain pointer inside one process; stores travel over NVLink) and its k_halo_push writes each step's records straight into it and
+ * raises the flag; k_halo_pull on the receiving side waits for the flag and refreshes the ghosts.  vx3b_batch_run_slab enqueues,
+ * per time step, the step kernel, the pushes and the pulls (captured in one CUDA graph per 64 steps). */
+typedef struct VX3B_HaloEndpoint {
+    uint8_t ipc_handle[64];  /* cudaIpcMemHandle_t of the receive area */
+    uint64_t device_ptr;     /* its address in the creating process (used when same_process != 0) */
+    int32_t device, n;       /* CUDA device of the area; records per buffer */
+    int32_t record_bytes, pad;
+} VX3B_HaloEndpoint;
+/* create (or return) the receive area of ghost list `ghost_list_id` */
+int vx3b_batch_halo_open(vx3b_ctx *ctx, int world, int ghost_list_id, VX3B_HaloEndpoint *out);
+/* connect send list `send_list_id` to the neighbour's receive area (its record count and record size must match) */
+int vx3b_batch_halo_connect(vx3b_ctx *ctx, int world, int send_list_id, const VX3B_HaloEndpoint *peer, int same_process);
+/* `steps` time steps, each followed by the push of every connected send list and the pull of every opened ghost list; asynchronous
+ * like vx3b_batch_run_async.  Every slab of the body must be given the same number of steps. */
+int vx3b_batch_run_slab(vx3b_ctx *ctx, int64_t steps);
+/* after a synchronisation: how many pulls gave up waiting for their neighbour (10 s each); non-zero = the run is invalid */
+int vx3b_batch_halo_timeouts(vx3b_ctx *ctx, int64_t *n);
 
 /* ---------------------------------------------------------------- 3. job -------------
  * Replaces vx3_node_worker main + VX3_SimulationManager::start (vx3_node_worker.cu:32-142,

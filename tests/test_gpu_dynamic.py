@@ -200,3 +200,26 @@ def test_material_timers_route_a_world_to_the_dynamic_kernel():
     c0.run(600)
     assert np.abs(c0.read_state(0)["pos"] - got).max() > 1e-6
     ctx.close(), c0.close()
+
+
+@pytest.mark.parametrize("case", ["c.signaling_data1", "c.signaling_data2"])
+def test_job_run_on_the_reference_signaling_experiments(case):
+    """Experiments/xenobot/c.signaling/data1|data2 through vx3b_job_run (the drop-in for `Voxelyze3 -i dir -o report.xml`), which
+    refused them in round 1: the report's fitness, stop time and centre of mass equal the oracle's run to the stop condition"""
+    import tempfile
+    import xml.etree.ElementTree as ET
+    d = os.path.join(ROOT, "tests", "data", "ref_inputs", case)
+    m = gv.Model.from_files(os.path.join(d, "base.vxa"), os.path.join(d, "rob.vxd"))
+    w = O.OracleWorld(m)
+    w.run(1000000, True)
+    want = w.result()
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "report.xml")
+        rc = gv.lib().vx3b_job_run(d.encode(), out.encode(), 1, gv.FP64)
+        assert rc == 0, gv.lib().vx3b_last_error()
+        x = ET.parse(out).getroot().find("detail/rob")
+    assert abs(float(x.find("currentTime").text) - want.current_time) < 1e-12
+    com = np.array([float(x.find(f"currentCenterOfMass/{a}").text) for a in "xyz"])
+    travel = max(np.abs(np.array(want.current_com) - np.array(want.initial_com)).max(), m.desc.vox_size)
+    assert np.abs(com - np.array(want.current_com)).max() / travel < 1e-5
+    assert abs(float(x.find("fitness_score").text) - want.fitness_score) <= 1e-5 * max(abs(want.fitness_score), 1.0)

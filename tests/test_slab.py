@@ -55,6 +55,44 @@ def test_split_body_invariants(name, n_parts, axis):
     assert dt > 0 and dt == np.float32(dt)
 
 
+def _body_texts():
+    return {"cube7": (W.cube_vxa(7), None), "xenobot": (W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(9)), "block": (W.small_block_vxa(), None)}
+
+
+@pytest.mark.parametrize("name", ["cube7", "xenobot", "block"])
+@pytest.mark.parametrize("n_parts,axis", [(2, 2), (3, 2), (2, 0), (2, 1)])
+def test_native_slab_model_equals_the_numpy_split(name, n_parts, axis):
+    """vx3b_model_from_vxa_slab (C++: every rank parses the text and builds ONLY its own slab) against split_body (numpy, on the
+    whole body's model): same voxels in the same order, same ghosts, links, exchange lists, materials and the whole body's time step"""
+    vxa, vxd = _body_texts()[name]
+    model = gv.Model.from_vxa(vxa, vxd)
+    lat = model.array("lattice")
+    if lat[:, axis].max() - lat[:, axis].min() + 1 < n_parts:
+        with pytest.raises(gv.VX3Error):
+            gv.Model.from_vxa_slab(vxa, vxd, axis, 0, n_parts)
+        return
+    parts = slab.split_body(model, n_parts, axis)
+    vm_whole, lm_whole = model.voxel_materials(), model.link_materials()
+    for p in parts:
+        m = gv.Model.from_vxa_slab(vxa, vxd, axis, p.rank, n_parts)
+        si = m.slab_info()
+        assert (si["part"], si["n_parts"], si["axis"], si["num_own"]) == (p.rank, n_parts, axis, p.num_own)
+        assert si["body_voxels"] == model.num_voxels and si["body_links"] == model.num_links
+        assert si["body_dt"] == slab.body_time_step(model)
+        assert np.array_equal(si["global_index"], p.global_index)
+        for k in ("send_lo", "send_hi", "ghost_lo", "ghost_hi"):
+            assert np.array_equal(si[k], getattr(p, k)), k
+        assert m.num_voxels == p.model.num_voxels and m.num_links == p.model.num_links
+        for k in ("lattice", "ghost", "link_neg", "link_pos", "link_axis", "phase_offset", "base_cilia", "shift_cilia"):
+            assert np.array_equal(m.array(k), p.model.array(k)), k
+        # the combined (link) materials are the WHOLE body's, numbered and oriented as the whole body first uses them
+        assert np.array_equal(m.array("voxel_mat"), p.model.array("voxel_mat")) and np.array_equal(m.array("link_mat"), p.model.array("link_mat"))
+        assert [bytes(x) for x in m.voxel_materials()] == [bytes(x) for x in vm_whole]
+        assert [bytes(x) for x in m.link_materials()] == [bytes(x) for x in lm_whole]
+        for f in ("dt_frac", "vox_size", "floor_enabled", "vary_temp_enabled", "temp_amplitude", "temp_period", "vx2_compat", "enable_cilia"):
+            assert getattr(m.desc, f) == getattr(model.desc, f), f
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -147,6 +185,52 @@ def test_slabs_with_halo_exchange_equal_the_whole_body_bit_for_bit(precision, n_
         ref = whole.read_state(0)
         whole.close()
         got = run_slabs(model, n_parts, steps, precision, opts)
+        for k in ("pos", "orient", "linMom", "angMom"):
+            assert np.array_equal(got[k], ref[k]), (k, np.abs(got[k] - ref[k]).max())
+
+
+def run_slabs_device_exchange(vxa, vxd, n_parts, steps, precision, options=None, calls=(None,)):
+    """slabs built by the C++ host model, one context + one stream each on device 0, exchanging through mapped receive areas"""
+    import torch
+    parts = [slab.native_part(vxa, vxd, r, n_parts) for r in range(n_parts)]
+    runners = [slab.SlabRunner(p, 0, precision, p.body_dt, options, stream=torch.cuda.Stream(0)) for p in parts]
+    eps = [r.open_endpoints() for r in runners]
+    for k, r in enumerate(runners):
+        r.connect(eps[k - 1]["hi"] if k > 0 else None, eps[k + 1]["lo"] if k < n_parts - 1 else None, same_process=True)
+    for n in calls:  # several calls: the sequence numbers carry on from one to the next
+        for r in runners:
+            r.run(steps if n is None else n)
+    torch.cuda.synchronize()
+    nv = parts[0].body_voxels
+    out = {"pos": np.zeros((nv, 3)), "orient": np.zeros((nv, 4)), "linMom": np.zeros((nv, 3)), "angMom": np.zeros((nv, 3))}
+    for r in runners:
+        assert r.ctx.halo_timeouts() == 0
+        st, g = r.own_state()
+        for k in out:
+            out[k][g] = st[k]
+        assert r.ctx.results()[0].steps == (steps if calls == (None,) else sum(calls))
+        r.close()
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [gv.FP64, gv.FP32])
+@pytest.mark.parametrize("n_parts", [2, 3])
+def test_device_side_exchange_equals_the_whole_body_bit_for_bit(precision, n_parts):
+    """vx3b_batch_run_slab: push into the neighbour's mapped receive area + flag, pull on the other side, 64 steps per graph, no
+    host in the loop - against the same body stepped whole; slabs from vx3b_model_from_vxa_slab"""
+    for (vxa, vxd), opts, calls in (((W.cube_vxa(9), None), dict(brick_x=4, brick_y=3, brick_z=2), (150,)),
+                                   ((W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(9)), None, (70, 1, 79))):
+        model = gv.Model.from_vxa(vxa, vxd)
+        whole = gv.Context(0, precision)
+        whole.set_option("path", 5)
+        for k, v in (opts or {}).items():
+            whole.set_option(k, v)
+        whole.upload([model])
+        whole.run(150)
+        ref = whole.read_state(0)
+        whole.close()
+        got = run_slabs_device_exchange(vxa, vxd, n_parts, 150, precision, opts, calls)
         for k in ("pos", "orient", "linMom", "angMom"):
             assert np.array_equal(got[k], ref[k]), (k, np.abs(got[k] - ref[k]).max())
 
