@@ -48,8 +48,9 @@ def parse_args():
                     "(all | none | comma list of cube100,pile,xenobot_fp64)")
     ap.add_argument("--slab-cube", type=int, default=160, help="N > 1: edge of the ONE body also stepped as N slabs into a \"slab\" block (0 = skip)")
     ap.add_argument("--slab-sim-steps", type=int, default=200)
-    ap.add_argument("--slab-exchange", default="device", choices=["device", "nccl"],
-                    help="slab halo exchange: device = stores into the neighbour's IPC-mapped memory + flags, no host in the loop; nccl = round 1's per-step ncclSend/Recv")
+    ap.add_argument("--slab-exchange", default="fused", choices=["fused", "device", "nccl"],
+                    help="slab halo exchange: fused = the step kernel stores boundary voxels straight into the neighbour's IPC-mapped state arrays and raises its flag "
+                         "(one launch per time step); device = separate push / pull kernels through a mapped receive area; nccl = round 1's per-step ncclSend/Recv")
     ap.add_argument("--slab-big", type=int, default=400, help="N = 8: edge of the big body (BASELINE configs[4]: 400^3) also stepped as 8 slabs into a \"slab_big\" block (0 = skip)")
     return ap.parse_args()
 
@@ -59,7 +60,8 @@ def workload_config(args):
         return {"workload": f"BASELINE configs[4] (second part): ONE {args.cube}^3-voxel soft body under gravity with floor contact, split into {args.gpus} z-slab(s)",
                 "worlds_per_gpu": 1, "sim_steps_per_step": args.sim_steps,
                 "parallelism": f"{args.gpus} slab(s), one per GPU; per time step the boundary layer (pos, temperature, orientation) goes to each neighbour "
-                               + ("by device-side stores into its IPC-mapped receive area over NVLink" if getattr(args, "slab_exchange", "device") == "device" else "by one NCCL send/recv"),
+                               + {"fused": "by stores of the step kernel itself into its IPC-mapped state arrays over NVLink", "device": "by a push kernel's stores into its IPC-mapped receive area over NVLink",
+                                  "nccl": "by one NCCL send/recv"}[getattr(args, "slab_exchange", "fused")],
                 "l2": "slab state larger than L2"}
     if args.workload == "pile":
         return {"workload": f"BASELINE configs[3]: multi-body scene, {args.pile}x{args.pile} + {args.pile - 1}x{args.pile - 1} bodies of 8^3 voxels piling up, voxel-voxel self-collision enabled (grid broad phase + candidate lists)",
@@ -484,7 +486,7 @@ def measure_slab(args, rank, world, local):
     t_host = time.perf_counter()
     vxa = W.cube_vxa(args.cube)
     t_text = time.perf_counter() - t_host
-    device_exchange = args.slab_exchange == "device"
+    device_exchange = args.slab_exchange in ("fused", "device")
     # every rank builds ONLY its own slab, in C++ (vx3b_model_from_vxa_slab); the whole body never exists on any rank
     part = S.native_part(vxa, None, rank, world)
     dt = part.body_dt
@@ -498,7 +500,7 @@ def measure_slab(args, rank, world, local):
         mine = run.open_endpoints()
         eps = [None] * world
         dist.all_gather_object(eps, mine)
-        run.connect(eps[rank - 1]["hi"] if rank > 0 else None, eps[rank + 1]["lo"] if rank < world - 1 else None)
+        run.connect(eps[rank - 1]["hi"] if rank > 0 else None, eps[rank + 1]["lo"] if rank < world - 1 else None, fused=args.slab_exchange == "fused")
         dist.barrier()
 
     def exchange():
@@ -545,6 +547,10 @@ def measure_slab(args, rank, world, local):
     clocks = sampler.stop() if sampler else None
     res = run.ctx.results()[0]
     timeouts = run.ctx.halo_timeouts()
+    wait_us_per_step = run.ctx.halo_wait_ns() / 1e3 / max(1, args.sim_steps * (args.warmup + args.steps)) / (2 if 0 < rank < world - 1 else 1)
+    waits = [None] * world
+    if world > 1:
+        dist.all_gather_object(waits, round(wait_us_per_step, 1))
     # whole-body centre of mass across the slabs (one all-reduce of <= 8 doubles): every slab reports the centre of
     # mass of its own voxels (ghosts excluded); the body here is of one material, so the weights are the own-voxel counts
     com = torch.tensor([c * part.num_own for c in res.current_com] + [float(part.num_own)], dtype=torch.float64, device="cuda")
@@ -592,9 +598,10 @@ def measure_slab(args, rank, world, local):
                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32 arithmetic, f64 positions" if args.precision == 32 else "f64", "data": "synthetic", "config": workload_config(args),
                "voxels_total": body_voxels, "links_total": body_links, "voxels_rank0_incl_ghosts": part.model.num_voxels, "links_rank0": nl_own,
-               "exchange": "device-side: k_halo_push into the neighbour's IPC-mapped receive area + flag, k_halo_pull; 64 time steps per CUDA graph" if device_exchange
+               "exchange": "fused into k_brick: boundary voxels stored straight into the neighbour's IPC-mapped state arrays over NVLink, flag raised by the last CTA, next launch waits for it; 64 time steps per CUDA graph" if args.slab_exchange == "fused"
+               else "device-side: k_halo_push into the neighbour's IPC-mapped receive area + flag, k_halo_pull; 64 time steps per CUDA graph" if device_exchange
                else "host-driven: k_halo_export, ncclSend/ncclRecv (torch.distributed.batch_isend_irecv), k_halo_import per time step",
-               "halo_pull_timeouts": int(timeouts_all), "body_center_of_mass_allreduced": body_com,
+               "halo_pull_timeouts": int(timeouts_all), "halo_wait_us_per_time_step_by_rank": waits, "body_center_of_mass_allreduced": body_com,
                "host_s_rank0": {"vxa_text": t_text, "slab_model_cpp": t_split, "upload": t_upload},
                "us_per_time_step": 1e3 * dev_ms_max / nsteps, "halo_bytes_per_time_step_all_ranks": int(halo_all), "wall_s_timed_region": wall_max,
                "diverged_worlds": int(diverged_all), "verified_bit_exact_against_whole_body": verified,
@@ -602,7 +609,7 @@ def measure_slab(args, rank, world, local):
                             "peak_source": peak_src, "note": "algorithmic bytes of the WHOLE body (112*Nv + 88*Nl per time step) / N GPUs / device time"},
                "e2e": {"value": vs_all / wall_max, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "what": "same timed region by host wall clock (graph launches, or per-step launches + NCCL calls, included); the body is uploaded once before it"},
-               "gpu_launches": int(nsteps * (1 + (2 if world > 1 else 0) * 2)), "clocks": clocks}
+               "gpu_launches": int(nsteps * (1 if args.slab_exchange == "fused" or world == 1 else 3 if device_exchange else 5)), "clocks": clocks}
         if timeouts_all:
             out["error"] = "a halo pull timed out: the run is invalid"
     run.close()

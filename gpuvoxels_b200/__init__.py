@@ -297,10 +297,21 @@ class Context:
         _check(lib().vx3b_batch_halo_open(self._h, world, list_id, C.byref(ep)), "vx3b_batch_halo_open")
         return ep
 
-    def halo_connect(self, world, list_id, endpoint, same_process=False):
+    def halo_connect(self, world, list_id, endpoint, same_process=False, peer_slots=None):
+        """peer_slots (the neighbour's halo_slots of its ghost list): the exchange fused into the step kernel; None: staged push / pull kernels"""
         if isinstance(endpoint, (bytes, bytearray)):
             endpoint = _abi.HaloEndpoint.from_buffer_copy(endpoint)
-        _check(lib().vx3b_batch_halo_connect(self._h, world, list_id, C.byref(endpoint), 1 if same_process else 0), "vx3b_batch_halo_connect")
+        if peer_slots is None:
+            _check(lib().vx3b_batch_halo_connect(self._h, world, list_id, C.byref(endpoint), 1 if same_process else 0), "vx3b_batch_halo_connect")
+        else:
+            ps = np.ascontiguousarray(peer_slots, dtype=np.int32)
+            _check(lib().vx3b_batch_halo_connect_fused(self._h, world, list_id, C.byref(endpoint), ps.ctypes.data_as(C.POINTER(C.c_int32)), 1 if same_process else 0),
+                   "vx3b_batch_halo_connect_fused")
+
+    def halo_slots(self, world, list_id, n):
+        out = np.empty(n, dtype=np.int32)
+        _check(lib().vx3b_batch_halo_slots(self._h, world, list_id, out.ctypes.data_as(C.POINTER(C.c_int32))), "vx3b_batch_halo_slots")
+        return out
 
     def run_slab(self, steps):
         _check(lib().vx3b_batch_run_slab(self._h, int(steps)), "vx3b_batch_run_slab")
@@ -308,6 +319,11 @@ class Context:
     def halo_timeouts(self):
         n = C.c_int64()
         _check(lib().vx3b_batch_halo_timeouts(self._h, C.byref(n)), "vx3b_batch_halo_timeouts")
+        return n.value
+
+    def halo_wait_ns(self):
+        n = C.c_int64()
+        _check(lib().vx3b_batch_halo_wait_ns(self._h, C.byref(n)), "vx3b_batch_halo_wait_ns")
         return n.value
 
     def results(self):

@@ -73,7 +73,8 @@ class SlabInfo(C.Structure):
 
 
 class HaloEndpoint(C.Structure):
-    _fields_ = [("ipc_handle", C.c_uint8 * 64), ("device_ptr", C.c_uint64), ("device", C.c_int32), ("n", C.c_int32), ("record_bytes", C.c_int32), ("pad", C.c_int32)]
+    _fields_ = [("ipc_handle", C.c_uint8 * 64), ("device_ptr", C.c_uint64), ("device", C.c_int32), ("n", C.c_int32), ("record_bytes", C.c_int32), ("pad", C.c_int32),
+                ("state_ipc_handle", (C.c_uint8 * 64) * 6), ("state_ptr", C.c_uint64 * 6)]
 
 
 class WorldResult(C.Structure):
@@ -124,7 +125,10 @@ SYMBOLS = {
     "vx3b_batch_halo_open": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(HaloEndpoint)]),
     "vx3b_batch_halo_connect": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(HaloEndpoint), C.c_int]),
     "vx3b_batch_run_slab": (C.c_int, [_P, C.c_int64]),
+    "vx3b_batch_halo_slots": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
+    "vx3b_batch_halo_connect_fused": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(HaloEndpoint), C.POINTER(C.c_int32), C.c_int]),
     "vx3b_batch_halo_timeouts": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "vx3b_batch_halo_wait_ns": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "vx3b_model_from_vxa_slab": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "vx3b_model_slab_info": (C.c_int, [_P, C.POINTER(SlabInfo)]),
     "vx3b_batch_results": (C.c_int, [_P, C.POINTER(WorldResult)]),

@@ -80,6 +80,8 @@ int vx3b_ctx_set_option(vx3b_ctx *ctx, const char *name, double value) {
         ctx->e->contactListCap = std::max(0, std::min(255, (int)value));
     else if (n == "contact_grid")
         ctx->e->contactGrid = value != 0;
+    else if (n == "slab_fused")
+        ctx->e->slabFused = value != 0;
     else if (n == "ext_all")
         ctx->e->extAll = value != 0;
     else if (n == "contact_skin")
@@ -134,8 +136,16 @@ int vx3b_batch_halo_open(vx3b_ctx *ctx, int world, int list_id, VX3B_HaloEndpoin
 int vx3b_batch_halo_connect(vx3b_ctx *ctx, int world, int list_id, const VX3B_HaloEndpoint *peer, int same_process) {
     return ctx && peer ? ctx->e->halo_connect(world, list_id, peer, same_process) : VX3B_ERR_ARG;
 }
+int vx3b_batch_halo_slots(vx3b_ctx *ctx, int world, int list_id, int32_t *slots) { return ctx && slots ? ctx->e->halo_slots(world, list_id, slots) : VX3B_ERR_ARG; }
+int vx3b_batch_halo_connect_fused(vx3b_ctx *ctx, int world, int list_id, const VX3B_HaloEndpoint *peer, const int32_t *peer_slots, int same_process) {
+    return ctx && peer && peer_slots ? ctx->e->halo_connect(world, list_id, peer, same_process, peer_slots) : VX3B_ERR_ARG;
+}
 int vx3b_batch_run_slab(vx3b_ctx *ctx, int64_t steps) { return ctx ? ctx->e->run_slab(steps) : VX3B_ERR_ARG; }
-int vx3b_batch_halo_timeouts(vx3b_ctx *ctx, int64_t *n) { return ctx && n ? ctx->e->halo_timeouts(n) : VX3B_ERR_ARG; }
+int vx3b_batch_halo_timeouts(vx3b_ctx *ctx, int64_t *n) { return ctx && n ? ctx->e->halo_timeouts(n, nullptr) : VX3B_ERR_ARG; }
+int vx3b_batch_halo_wait_ns(vx3b_ctx *ctx, int64_t *ns) {
+    int64_t n;
+    return ctx && ns ? ctx->e->halo_timeouts(&n, ns) : VX3B_ERR_ARG;
+}
 int vx3b_batch_results(vx3b_ctx *ctx, VX3B_WorldResult *out) { return ctx ? ctx->e->results(out) : VX3B_ERR_ARG; }
 int vx3b_batch_read_state(vx3b_ctx *ctx, int world, double *p, double *o, double *l, double *a) {
     return ctx ? ctx->e->read_state(world, p, o, l, a) : VX3B_ERR_ARG;

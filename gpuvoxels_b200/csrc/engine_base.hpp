@@ -28,9 +28,10 @@ class EngineBase {
     virtual int halo_export(int world, int listId, void *deviceBuffer) = 0;
     virtual int halo_import(int world, int listId, const void *deviceBuffer) = 0;
     virtual int halo_open(int world, int listId, VX3B_HaloEndpoint *out) = 0;
-    virtual int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess) = 0;
+    virtual int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess, const int32_t *peerSlots = nullptr) = 0;
+    virtual int halo_slots(int world, int listId, int32_t *slots) = 0;
     virtual int run_slab(int64_t steps) = 0;
-    virtual int halo_timeouts(int64_t *n) = 0;
+    virtual int halo_timeouts(int64_t *n, int64_t *waitNs) = 0;
     // dynamic topology: links in use, signal scalars + removed / attach flags per voxel, current link list
     virtual int num_links(int world, int32_t *n) = 0;
     virtual int read_signals(int world, double *sig6, int32_t *vflags2) = 0;
@@ -52,6 +53,7 @@ class EngineBase {
     double contactSkin = 0.15;  // skin of the contact candidate lists, in voxel sizes
     int contactListCap = 0;     // entries per candidate list; 0 = from the skin
     int extAll = 0;             // every voxel gets a boundary-condition slot at upload, so set_force() can load any voxel later
+    int slabFused = 1;          // one body over several GPUs: exchange fused into the step kernel (1) or staged push / pull kernels (0)
     int contactGrid = 1;        // big worlds: uniform-grid broad phase + candidate lists (1) or the all-pairs scan (0)
 };
 

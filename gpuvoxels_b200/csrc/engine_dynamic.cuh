@@ -588,7 +588,7 @@ template <class R> class EngineMux : public EngineBase {
         for (int k = 0; k < 3; k++)
             S.brickDim[k] = brickDim[k];
         S.recordPairs = recordPairs, S.chunk = chunk, S.dtOverride = dtOverride, S.residentThreads = residentThreads, S.contactSkin = contactSkin;
-        S.contactListCap = contactListCap, S.extAll = extAll, S.contactGrid = contactGrid;
+        S.contactListCap = contactListCap, S.extAll = extAll, S.contactGrid = contactGrid, S.slabFused = slabFused;
         Dy.device = device;
     }
     bool locate(int world, Where &w) {
@@ -778,11 +778,17 @@ template <class R> class EngineMux : public EngineBase {
             return VX3B_ERR_ARG;
         return w.dyn ? no_dynamic("vx3b_batch_halo_open") : S.halo_open(w.idx, listId, out);
     }
-    int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess) override {
+    int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess, const int32_t *peerSlots) override {
         Where w;
         if (!locate(world, w))
             return VX3B_ERR_ARG;
-        return w.dyn ? no_dynamic("vx3b_batch_halo_connect") : S.halo_connect(w.idx, listId, peer, sameProcess);
+        return w.dyn ? no_dynamic("vx3b_batch_halo_connect") : S.halo_connect(w.idx, listId, peer, sameProcess, peerSlots);
+    }
+    int halo_slots(int world, int listId, int32_t *slots) override {
+        Where w;
+        if (!locate(world, w))
+            return VX3B_ERR_ARG;
+        return w.dyn ? no_dynamic("vx3b_batch_halo_slots") : S.halo_slots(w.idx, listId, slots);
     }
     int run_slab(int64_t steps) override {
         if (nDyn)
@@ -790,7 +796,7 @@ template <class R> class EngineMux : public EngineBase {
         push_options();
         return S.run_slab(steps);
     }
-    int halo_timeouts(int64_t *n) override { return S.halo_timeouts(n); }
+    int halo_timeouts(int64_t *n, int64_t *waitNs) override { return S.halo_timeouts(n, waitNs); }
 };
 
 } // namespace vx3b

@@ -211,6 +211,12 @@ template <class R> class Engine : public EngineBase {
         HaloSync *sync = nullptr;
     };
     HaloLink haloLink[8];
+    // exchange fused into k_brick: arrays of this slab the neighbours write into, the neighbours' arrays mapped here, flags
+    std::vector<void *> peerExported;   // cudaMalloc'ed brick-set arrays (freed at the next upload)
+    std::vector<void *> peerOpened;     // cudaIpcOpenMemHandle results
+    BrickPeer<R> peer{};                // kernel parameter
+    bool peerOn = false;                // every connected list is connected in fused form
+    int peerLists = 0, stagedLists = 0; // connected / opened lists by kind
     std::map<int, cudaGraphExec_t> slabGraphs; // chunk length -> step + exchange graph
     bool slabGraphsStale = false;
     std::vector<int> brickWorldList;
@@ -1456,15 +1462,30 @@ template <class R> class Engine : public EngineBase {
             BA.ticket = dTicket;
             BA.nvSlots = (int)bh.borig.size();
             BA.nlSlots = (int)bh.lorig.size();
+            // a slab (ghost voxels): the arrays a neighbouring slab's kernel writes into get allocations of their own, which CUDA IPC can export
+            const bool exportable = std::any_of(vghost.begin(), vghost.end(), [](uint8_t g) { return g != 0; });
+            auto own_alloc = [&](auto **out, size_t count) -> int {
+                if (!exportable)
+                    return dalloc(out, count);
+                void *q = nullptr;
+                const size_t bytes = std::max<size_t>(count, 1) * sizeof(**out);
+                CUDA_TRY(cudaMalloc(&q, bytes));
+                peerExported.push_back(q);
+                CUDA_TRY(cudaMemsetAsync(q, 0, bytes, stream));
+                *out = (std::remove_reference_t<decltype(**out)> *)q;
+                return VX3B_OK;
+            };
             for (int k = 0; k < 2; k++) {
                 BrickSet<R> &S = BA.set[k];
-                if ((rc = dalloc(&S.pxy, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.pzt, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.orient, BA.nvSlots)) != VX3B_OK ||
+                if ((rc = own_alloc(&S.pxy, BA.nvSlots)) != VX3B_OK || (rc = own_alloc(&S.pzt, BA.nvSlots)) != VX3B_OK || (rc = own_alloc(&S.orient, BA.nvSlots)) != VX3B_OK ||
                     (rc = dalloc(&S.lm, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.am, BA.nvSlots)) != VX3B_OK || (rc = dalloc(&S.lpos2, BA.nlSlots)) != VX3B_OK ||
                     (rc = dalloc(&S.la1, BA.nlSlots)) != VX3B_OK || (rc = dalloc(&S.la2, BA.nlSlots)) != VX3B_OK)
                     return rc;
             }
             CUDA_TRY(cudaFuncSetAttribute(k_brick<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin)); // per function, shared by every context
             CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
             // persistent grid: as many CTAs as fit at once, each stepping consecutive bricks in chunks
             int numSm = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev));
@@ -1556,7 +1577,12 @@ template <class R> class Engine : public EngineBase {
             brickDoesWorldStep = BA.nBricks > 0 && FA.nBricks <= b0 && !anyCollision && nBrickWorlds == (mixed ? (int)H.size() - numResident : (int)H.size());
             if (BA.nBricks > 0) {
                 const int ws = brickDoesWorldStep ? 1 : 0;
-                if (brickLean)
+                if (peerOn && ws) { // one body over several GPUs: the exchange with the neighbouring slabs is part of the kernel
+                    if (brickLean)
+                        k_brick<R, true, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive, peer);
+                    else
+                        k_brick<R, false, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive, peer);
+                } else if (brickLean)
                     k_brick<R, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive);
                 else
                     k_brick<R, false><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive);
@@ -1821,6 +1847,21 @@ template <class R> class Engine : public EngineBase {
     // Plain cudaMalloc (not the arena): cudaIpcGetMemHandle needs an allocation of its own.
     static size_t halo_area_bytes(int n) { return 128 + 2 * (size_t)n * sizeof(HaloRec<R>); }
     void release_halo_links() {
+        for (void *q : peerOpened)
+            cudaIpcCloseMemHandle(q);
+        peerOpened.clear();
+        if (peer.sync)
+            cudaFree(peer.sync);
+        if (peer.sendLo)
+            cudaFree((void *)peer.sendLo);
+        if (peer.sendHi)
+            cudaFree((void *)peer.sendHi);
+        peer = BrickPeer<R>{};
+        peerOn = false;
+        peerLists = stagedLists = 0;
+        for (void *q : peerExported)
+            cudaFree(q);
+        peerExported.clear();
         for (auto &k : haloLink) {
             if (k.peer && k.peerIpc)
                 cudaIpcCloseMemHandle(k.peer);
@@ -1869,10 +1910,74 @@ template <class R> class Engine : public EngineBase {
         out->device = device;
         out->n = halo[listId].n;
         out->record_bytes = (int32_t)sizeof(HaloRec<R>);
+        if (!peerExported.empty() && BA.nBricks > 0) { // for the exchange fused into the step kernel
+            void *arr[6] = {BA.set[0].pxy, BA.set[0].pzt, BA.set[0].orient, BA.set[1].pxy, BA.set[1].pzt, BA.set[1].orient};
+            for (int k = 0; k < 6; k++) {
+                out->state_ptr[k] = (uint64_t)(uintptr_t)arr[k];
+                if (cudaIpcGetMemHandle(&h, arr[k]) == cudaSuccess)
+                    memcpy(out->state_ipc_handle[k], &h, sizeof(h) < 64 ? sizeof(h) : 64);
+                else
+                    cudaGetLastError();
+            }
+        }
         slabGraphsStale = true;
         return VX3B_OK;
     }
-    int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess) override {
+    int halo_slots(int world, int listId, int32_t *slots) override {
+        CUDA_TRY(cudaSetDevice(device));
+        if (listId < 0 || listId >= 8 || halo[listId].world != world || halo[listId].n <= 0 || BA.nBricks == 0) {
+            set_error("vx3b_batch_halo_slots: list not registered for this world, empty, or not on the brick path");
+            return VX3B_ERR_ARG;
+        }
+        CUDA_TRY(cudaMemcpy(slots, halo[listId].dSlots, (size_t)halo[listId].n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        return VX3B_OK;
+    }
+    // fused form: map the neighbour's six state arrays, note where it keeps my boundary voxels, mark them in the static words
+    int connect_fused(int listId, const VX3B_HaloEndpoint *ep, int sameProcess, const int32_t *peerSlots, void *peerArea) {
+        const HaloList &L = halo[listId];
+        const bool lower = listId == 0; // list 0 feeds the lower neighbour, any other id the upper one (gpuvoxels_b200/slab.py: SEND_LO, SEND_HI)
+        void *arr[6];
+        for (int k = 0; k < 6; k++) {
+            if (!ep->state_ptr[k]) {
+                set_error("vx3b_batch_halo_connect_fused: the neighbour's endpoint does not export its state arrays (not a slab, or not on the brick path)");
+                return VX3B_ERR_ARG;
+            }
+            if (sameProcess)
+                arr[k] = (void *)(uintptr_t)ep->state_ptr[k];
+            else {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, ep->state_ipc_handle[k], sizeof(h) < 64 ? sizeof(h) : 64);
+                CUDA_TRY(cudaIpcOpenMemHandle(&arr[k], h, cudaIpcMemLazyEnablePeerAccess));
+                peerOpened.push_back(arr[k]);
+            }
+        }
+        if (!peer.sync) {
+            CUDA_TRY(cudaMalloc(&peer.sync, sizeof(BrickPeerSync)));
+            CUDA_TRY(cudaMemset(peer.sync, 0, sizeof(BrickPeerSync)));
+        }
+        int32_t *&table = const_cast<int32_t *&>(lower ? peer.sendLo : peer.sendHi);
+        if (!table)
+            CUDA_TRY(cudaMalloc(&table, (size_t)BA.nvSlots * sizeof(int32_t)));
+        int32_t *dRemote = nullptr;
+        CUDA_TRY(cudaMalloc(&dRemote, (size_t)L.n * sizeof(int32_t)));
+        CUDA_TRY(cudaMemcpy(dRemote, peerSlots, (size_t)L.n * sizeof(int32_t), cudaMemcpyHostToDevice));
+        k_brick_mark<<<(unsigned)((L.n + 255) / 256), 256, 0, stream>>>(const_cast<uint32_t *>(BA.bstat), L.dSlots, L.n, lower ? BS_SEND_LO : BS_SEND_HI, table, dRemote);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(dRemote);
+        using T4 = typename Store<R>::T4;
+        if (lower) {
+            peer.loPxy0 = (D2 *)arr[0], peer.loPzt0 = (D2 *)arr[1], peer.loOri0 = (T4 *)arr[2];
+            peer.loPxy1 = (D2 *)arr[3], peer.loPzt1 = (D2 *)arr[4], peer.loOri1 = (T4 *)arr[5];
+            peer.loFlag = (unsigned long long *)peerArea;
+        } else {
+            peer.hiPxy0 = (D2 *)arr[0], peer.hiPzt0 = (D2 *)arr[1], peer.hiOri0 = (T4 *)arr[2];
+            peer.hiPxy1 = (D2 *)arr[3], peer.hiPzt1 = (D2 *)arr[4], peer.hiOri1 = (T4 *)arr[5];
+            peer.hiFlag = (unsigned long long *)peerArea;
+        }
+        peerLists++;
+        return VX3B_OK;
+    }
+    int halo_connect(int world, int listId, const VX3B_HaloEndpoint *peer, int sameProcess, const int32_t *peerSlots) override {
         CUDA_TRY(cudaSetDevice(device));
         if (listId < 0 || listId >= 8 || halo[listId].world != world || halo[listId].n <= 0) {
             set_error("vx3b_batch_halo_connect: list not registered for this world (vx3b_batch_halo_set), or empty");
@@ -1912,26 +2017,33 @@ template <class R> class Engine : public EngineBase {
             K.peerIpc = true;
         }
         slabGraphsStale = true;
+        if (peerSlots)
+            return connect_fused(listId, peer, sameProcess, peerSlots, K.peer);
+        stagedLists++;
         return VX3B_OK;
     }
+    // one launch for every connected send list, then one for every opened ghost list (two sides per launch: blockIdx.y)
     void enqueue_exchange() {
-        for (int id = 0; id < 8; id++) { // pushes first: the neighbours wait for them
-            const HaloLink &K = haloLink[id];
-            const HaloList &L = halo[id];
-            if (!K.peer || L.n <= 0)
-                continue;
-            char *base = (char *)K.peer;
-            k_halo_push<R><<<(unsigned)((L.n + 127) / 128), 128, 0, stream>>>(A, BA, L.world, L.dVox, L.dSlots, L.n, 1, (HaloRec<R> *)(base + 128),
-                                                                            (HaloRec<R> *)(base + 128) + L.n, (unsigned long long *)base, K.sync);
-        }
-        for (int id = 0; id < 8; id++) {
-            const HaloLink &K = haloLink[id];
-            const HaloList &L = halo[id];
-            if (!K.area || L.n <= 0)
-                continue;
-            const char *base = (const char *)K.area;
-            k_halo_pull<R><<<(unsigned)((L.n + 127) / 128), 128, 0, stream>>>(A, BA, L.world, L.dVox, L.dSlots, L.n, 1, (const HaloRec<R> *)(base + 128),
-                                                                            (const HaloRec<R> *)(base + 128) + L.n, (const unsigned long long *)base, K.sync);
+        for (int pull = 0; pull < 2; pull++) {
+            HaloSide<R> side[8];
+            int world = -1, ns = 0, nmax = 0;
+            for (int id = 0; id < 8; id++) {
+                const HaloLink &K = haloLink[id];
+                const HaloList &L = halo[id];
+                char *base = (char *)(pull ? K.area : K.peer);
+                if (!base || L.n <= 0)
+                    continue;
+                side[ns++] = HaloSide<R>{L.dSlots, L.n, (HaloRec<R> *)(base + 128), (HaloRec<R> *)(base + 128) + L.n, (unsigned long long *)base, K.sync};
+                world = L.world;
+                nmax = std::max(nmax, L.n);
+            }
+            for (int k = 0; k < ns; k += 2) {
+                const dim3 grid((unsigned)((nmax + HALO_THREADS - 1) / HALO_THREADS), k + 1 < ns ? 2 : 1);
+                if (pull)
+                    k_halo_pull<R><<<grid, HALO_THREADS, 0, stream>>>(A, BA, world, side[k], side[k + 1 < ns ? k + 1 : k]);
+                else
+                    k_halo_push<R><<<grid, HALO_THREADS, 0, stream>>>(A, BA, world, side[k], side[k + 1 < ns ? k + 1 : k]);
+            }
         }
     }
     int run_slab(int64_t steps) override {
@@ -1940,6 +2052,14 @@ template <class R> class Engine : public EngineBase {
             set_error("vx3b_batch_run_slab: every world must be on the brick path (option path = 5 before upload; no collision, force field or targets)");
             return VX3B_ERR_STATE;
         }
+        for (int id = 0, w = -1; id < 8; id++)
+            if ((haloLink[id].area || haloLink[id].peer) && halo[id].n > 0) {
+                if (w >= 0 && halo[id].world != w) {
+                    set_error("vx3b_batch_run_slab: the connected halo lists must belong to one world");
+                    return VX3B_ERR_STATE;
+                }
+                w = halo[id].world;
+            }
         const unsigned wb = (A.nWorlds + 127) / 128, nbb = (unsigned)((std::max(BA.nvSlots, BA.nlSlots) + 255) / 256);
         k_world_begin<R><<<wb, 128, 0, stream>>>(A, (long long)steps, 0, 0, 1);
         if (!brickResident) {
@@ -1951,6 +2071,25 @@ template <class R> class Engine : public EngineBase {
                 cudaGraphExecDestroy(kv.second);
             slabGraphs.clear();
             slabGraphsStale = false;
+            // fused form when every connected send list is: the opened ghost lists are then fed by the neighbours' kernels
+            if (peerLists > 0 && stagedLists > 0) {
+                set_error("vx3b_batch_run_slab: connect every send list the same way (vx3b_batch_halo_connect or vx3b_batch_halo_connect_fused)");
+                return VX3B_ERR_STATE;
+            }
+            const bool fused = peerLists > 0 && slabFused;
+            if (fused && !peerOn) {
+                for (int id = 0; id < 8; id++) {
+                    const HaloLink &K = haloLink[id];
+                    const HaloList &L = halo[id];
+                    if (!K.area || L.n <= 0)
+                        continue;
+                    // the ghost list that sits below my own voxels is fed by the lower neighbour (gpuvoxels_b200/slab.py: GHOST_LO = 2, GHOST_HI = 3)
+                    (id == 2 ? peer.myLo : peer.myHi) = (const unsigned long long *)K.area;
+                    k_brick_mark<<<(unsigned)((L.n + 255) / 256), 256, 0, stream>>>(const_cast<uint32_t *>(BA.bstat), L.dSlots, L.n, BS_REMOTE_FED, nullptr, nullptr);
+                }
+                CUDA_TRY(cudaGetLastError());
+            }
+            peerOn = fused;
         }
         int64_t done = 0;
         while (done < steps) {
@@ -1962,7 +2101,8 @@ template <class R> class Engine : public EngineBase {
                 CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
                 for (int k = 0; k < c; k++) {
                     enqueue_step(0, false, true);
-                    enqueue_exchange();
+                    if (!peerOn)
+                        enqueue_exchange();
                 }
                 CUDA_TRY(cudaStreamEndCapture(stream, &g));
                 CUDA_TRY(cudaGraphInstantiate(&ge, g, 0));
@@ -1974,14 +2114,25 @@ template <class R> class Engine : public EngineBase {
         }
         return VX3B_OK;
     }
-    int halo_timeouts(int64_t *n) override {
+    int halo_timeouts(int64_t *n, int64_t *waitNs) override {
         CUDA_TRY(cudaSetDevice(device));
         *n = 0;
+        if (waitNs)
+            *waitNs = 0;
+        if (peer.sync) {
+            BrickPeerSync ps;
+            CUDA_TRY(cudaMemcpy(&ps, peer.sync, sizeof(ps), cudaMemcpyDeviceToHost));
+            *n += ps.timeouts;
+            if (waitNs)
+                *waitNs += (int64_t)ps.waitNs;
+        }
         for (auto &K : haloLink)
             if (K.sync) {
                 HaloSync hs;
                 CUDA_TRY(cudaMemcpy(&hs, K.sync, sizeof(hs), cudaMemcpyDeviceToHost));
                 *n += hs.timeouts;
+                if (waitNs)
+                    *waitNs += (int64_t)hs.waitNs;
             }
         return VX3B_OK;
     }

@@ -69,6 +69,31 @@ template <class R> struct BrickArrays {
     int nWorlds;
     int *ticket;              // CTAs that have finished the current launch
 };
+// One body over several GPUs, exchange FUSED into the step kernel (include/vx3b200.h section 2b): the voxel pass stores the new
+// position / temperature / orientation of a boundary voxel not only into this slab's arrays but also - over NVLink, into the
+// neighbouring slab's IPC-mapped arrays - into the slot that slab keeps for it as a ghost; the last CTA of the launch raises a
+// sequence flag in the neighbour's memory, and the neighbour's next launch starts by waiting for it.  No pack / unpack kernels,
+// no staging buffers: one launch per time step, as on one GPU.  Safe with two buffer sets: a slab can start step s + 1 (which
+// overwrites, in the neighbour, the set that neighbour READ in step s) only after it has seen the neighbour's flag of step s.
+enum { BS_SEND_LO = 1u << 16, BS_SEND_HI = 1u << 17, BS_REMOTE_FED = 1u << 18 }; // bits of the per-slot static word (BrickArrays::bstat)
+struct BrickPeerSync {
+    unsigned long long seq;    // launches completed = the sequence number the neighbours' flags must have reached before the next one
+    unsigned long long waitNs; // time CTA 0 spent waiting for the neighbours (diagnostic)
+    unsigned int timeouts;     // launches that gave up waiting (10 s): the run is invalid
+    unsigned int pad;
+};
+template <class R> struct BrickPeer { // (no arrays: a dynamically indexed kernel parameter lives in local memory)
+    using T4 = typename Store<R>::T4;
+    D2 *loPxy0, *loPxy1, *loPzt0, *loPzt1; // the lower neighbour's buffer sets 0 / 1 (mapped), NULL without such a neighbour
+    T4 *loOri0, *loOri1;
+    D2 *hiPxy0, *hiPxy1, *hiPzt0, *hiPzt1;
+    T4 *hiOri0, *hiOri1;
+    const int32_t *sendLo, *sendHi;        // [my brick-order slot] -> the neighbour's slot of its ghost copy (read where BS_SEND_* is set)
+    unsigned long long *loFlag, *hiFlag;   // in the neighbours' memory: raised to seq + 1 when this launch's stores are visible
+    const unsigned long long *myLo, *myHi; // in my memory: raised by the lower / upper neighbour
+    BrickPeerSync *sync;
+};
+
 struct BrickCaps {
     int own, halo, owned, haloL, nvm, nlm; // own even
     int tab() const { return own + halo; }
@@ -143,6 +168,11 @@ VXD void mbar_wait(uint32_t bar, uint32_t phase) {
                      : "memory");
     } while (!done);
 }
+VXD unsigned long long halo_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 template <int BYTES> VXD void gather16(uint32_t dst, const void *src) { // BYTES = 16 or 32
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     if constexpr (BYTES == 32)
@@ -193,7 +223,8 @@ template <class R> __device__ __noinline__ void brick_world_step(WorldD *worlds,
     }
 }
 
-template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L, int worldStep, int useStop, int *activeCount) {
+template <class R, bool LEAN, bool PEER = false>
+__global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L, int worldStep, int useStop, int *activeCount, const BrickPeer<R> P = BrickPeer<R>{}) {
     using T4 = typename Store<R>::T4;
     using T2 = typename Store<R>::T2;
     extern __shared__ __align__(128) unsigned char smem_brick[];
@@ -210,6 +241,27 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
         mbar_fence_init();
+    }
+    if constexpr (PEER) { // the neighbours' stores of the previous step into my ghost slots must have landed
+        if (tid == 0) {
+            const unsigned long long want = P.sync->seq, t0 = halo_now_ns();
+            bool ok = true;
+            while ((P.myLo && *(const volatile unsigned long long *)P.myLo < want) || (P.myHi && *(const volatile unsigned long long *)P.myHi < want)) {
+                __nanosleep(64);
+                if (halo_now_ns() - t0 > 10000000000ull) { // 10 s: a neighbour is gone; never hang the device
+                    ok = false;
+                    break;
+                }
+            }
+            __threadfence_system();
+            if (blockIdx.x == 0) {
+                P.sync->waitNs += halo_now_ns() - t0;
+                if (!ok)
+                    P.sync->timeouts++;
+            }
+        }
+        __syncthreads();
+        asm volatile("fence.proxy.async;" ::: "memory"); // the bulk copies below read what another device's ordinary stores wrote
     }
     uint32_t phaseBits = 0; // bit s: parity the next wait on stage s's mbarrier expects
     int curWorld = -1;
@@ -470,6 +522,11 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                     return a;
                 };
                 const bool ghost = stw & (1u << 15); // a voxel another GPU's slab owns: carried through, refreshed by the halo import
+                if constexpr (PEER)
+                    if (stw & BS_REMOTE_FED)
+                        continue; // a ghost the owning slab's kernel writes straight into my other buffer set
+                // PEER: where the neighbours keep this voxel as a ghost, in the buffer set they write this step (the same parity as mine)
+                [[maybe_unused]] const bool dpar1 = PEER && dst.pxy == BA.set[1].pxy;
                 if (split) { // LEAN only
                     if (ghost) {
                         if (!rotRole) {
@@ -494,6 +551,18 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                         const unsigned long long b2 = ((unsigned long long)fl << 32) | (unsigned long long)f2u(v.temp);
                         dst.pzt[vs] = D2{v.pos.z, __longlong_as_double((long long)b2)};
                         dst.lm[vs] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
+                        if constexpr (PEER) {
+                            if (stw & BS_SEND_LO) {
+                                const int rs = P.sendLo[vs];
+                                (dpar1 ? P.loPxy1 : P.loPxy0)[rs] = D2{v.pos.x, v.pos.y};
+                                (dpar1 ? P.loPzt1 : P.loPzt0)[rs] = D2{v.pos.z, __longlong_as_double((long long)b2)};
+                            }
+                            if (stw & BS_SEND_HI) {
+                                const int rs = P.sendHi[vs];
+                                (dpar1 ? P.hiPxy1 : P.hiPxy0)[rs] = D2{v.pos.x, v.pos.y};
+                                (dpar1 ? P.hiPzt1 : P.hiPzt0)[rs] = D2{v.pos.z, __longlong_as_double((long long)b2)};
+                            }
+                        }
                         if (sampling) {
                             const double mass = m.mass;
                             world_accumulate(Wp->comAcc, B.world, m.isMeasured != 0 && !ghost, v.pos.x * mass, v.pos.y * mass, v.pos.z * mass, mass);
@@ -504,6 +573,12 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                         voxel_rotate<R, true>(m, wp, nullptr, v, sum_slots(3));
                         dst.orient[vs] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
                         dst.am[vs] = mk4<R>(v.angMom.x, v.angMom.y, v.angMom.z, R(0));
+                        if constexpr (PEER) {
+                            if (stw & BS_SEND_LO)
+                                (dpar1 ? P.loOri1 : P.loOri0)[P.sendLo[vs]] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
+                            if (stw & BS_SEND_HI)
+                                (dpar1 ? P.hiOri1 : P.hiOri0)[P.sendHi[vs]] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
+                        }
                     }
                     continue;
                 }
@@ -555,6 +630,20 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
                 dst.orient[vs] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
                 dst.lm[vs] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
                 dst.am[vs] = mk4<R>(v.angMom.x, v.angMom.y, v.angMom.z, R(0));
+                if constexpr (PEER) {
+                    if (stw & BS_SEND_LO) {
+                        const int rs = P.sendLo[vs];
+                        (dpar1 ? P.loPxy1 : P.loPxy0)[rs] = D2{v.pos.x, v.pos.y};
+                        (dpar1 ? P.loPzt1 : P.loPzt0)[rs] = D2{v.pos.z, __longlong_as_double((long long)b2)};
+                        (dpar1 ? P.loOri1 : P.loOri0)[rs] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
+                    }
+                    if (stw & BS_SEND_HI) {
+                        const int rs = P.sendHi[vs];
+                        (dpar1 ? P.hiPxy1 : P.hiPxy0)[rs] = D2{v.pos.x, v.pos.y};
+                        (dpar1 ? P.hiPzt1 : P.hiPzt0)[rs] = D2{v.pos.z, __longlong_as_double((long long)b2)};
+                        (dpar1 ? P.hiOri1 : P.hiOri0)[rs] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
+                    }
+                }
                 if (sampling) {
                     const double mass = m.mass;
                     world_accumulate(Wp->comAcc, B.world, m.isMeasured != 0 && !ghost, v.pos.x * mass, v.pos.y * mass, v.pos.z * mass, mass);
@@ -570,11 +659,23 @@ template <class R, bool LEAN> __global__ void __launch_bounds__(512, 1) k_brick(
     if (worldStep) {
         __syncthreads();
         if (tid == 0) {
-            __threadfence();
+            if constexpr (PEER)
+                __threadfence_system(); // this CTA's stores into the neighbours' memory are visible there before the flag can be
+            else
+                __threadfence();
             if (atomicAdd(BA.ticket, 1) == (int)gridDim.x - 1) {
                 *BA.ticket = 0;
                 __threadfence();
                 brick_world_step<R>(A.worlds, BA.worldList, BA.nWorlds, useStop, activeCount);
+                if constexpr (PEER) {
+                    const unsigned long long next = P.sync->seq + 1;
+                    P.sync->seq = next;
+                    __threadfence_system();
+                    if (P.loFlag)
+                        *(volatile unsigned long long *)P.loFlag = next;
+                    if (P.hiFlag)
+                        *(volatile unsigned long long *)P.hiFlag = next;
+                }
             }
         }
     }
@@ -692,82 +793,117 @@ struct HaloSync {
     unsigned long long seq;    // exchanges completed on this side of the link
     unsigned int ticket;       // CTAs of the running kernel that have finished
     unsigned int timeouts;     // pulls that gave up waiting (the run is invalid; reported by the host)
+    unsigned long long waitNs; // time the first CTA of a pull spent waiting for the neighbour's flag, summed over the steps (diagnostic)
 };
-VXD unsigned long long halo_now_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-template <class R>
-__global__ void k_halo_push(Arrays<R> A, BrickArrays<R> BA, int world, const int32_t *vox, const int32_t *slots, int n, int resident, HaloRec<R> *peer0,
-                            HaloRec<R> *peer1, unsigned long long *peerFlag, HaloSync *sync) {
-    const unsigned long long next = sync->seq + 1;
+// set-up of the fused exchange: flag bits into the static words of the listed slots, and (send lists) my slot -> the neighbour's slot
+static __global__ void k_brick_mark(uint32_t *bstat, const int32_t *slots, int n, uint32_t bit, int32_t *sendSlot, const int32_t *remoteSlots) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        D2 a, b;
-        typename Store<R>::T4 o;
-        if (resident) {
-            const BrickSet<R> &s = BA.set[A.worlds[world].parity];
-            a = s.pxy[slots[i]], b = s.pzt[slots[i]], o = s.orient[slots[i]];
-        } else
-            a = A.pxy[vox[i]], b = A.pzt[vox[i]], o = A.orient[vox[i]];
+    if (i >= n)
+        return;
+    atomicOr(&bstat[slots[i]], bit);
+    if (sendSlot)
+        sendSlot[slots[i]] = remoteSlots[i];
+}
+
+// One side (lower / upper neighbour) of an exchange kernel; blockIdx.y selects it, so a slab's two pushes are ONE launch and so are its pulls.
+template <class R> struct HaloSide {
+    const int32_t *slots;       // brick-order slot of every listed voxel
+    int n;
+    HaloRec<R> *buf0, *buf1;    // push: the neighbour's two record buffers (mapped); pull: my own
+    unsigned long long *flag;   // push: the neighbour's flag; pull: mine
+    HaloSync *sync;
+};
+constexpr int HALO_THREADS = 128;
+// Records are staged in shared memory and leave as consecutive 16-byte pieces, so a warp's store covers 512 contiguous bytes of the
+// neighbour's buffer: stores of single 48-byte records at a 48-byte stride went over NVLink as 16-byte packets and cost 270 us per
+// time step on the 160,000-voxel faces of a 400^3 body's slabs.
+template <class R> __global__ void __launch_bounds__(HALO_THREADS) k_halo_push(Arrays<R> A, BrickArrays<R> BA, int world, HaloSide<R> lo, HaloSide<R> hi) {
+    constexpr int P = (int)(sizeof(HaloRec<R>) / 16);
+    static_assert(sizeof(HaloRec<R>) % 16 == 0, "halo record is copied in 16-byte pieces");
+    __shared__ uint4 stage[HALO_THREADS * P];
+    const HaloSide<R> &S = blockIdx.y ? hi : lo;
+    const unsigned long long next = S.sync->seq + 1;
+    const int base = blockIdx.x * HALO_THREADS, i = base + threadIdx.x;
+    if (i < S.n) {
+        const BrickSet<R> &s = BA.set[A.worlds[world].parity];
+        const D2 a = s.pxy[S.slots[i]], b = s.pzt[S.slots[i]];
         HaloRec<R> r;
         r.x = a.x, r.y = a.y, r.z = b.x;
         r.packed = (unsigned long long)__double_as_longlong(b.y);
-        r.orient = o;
-        ((next & 1) ? peer1 : peer0)[i] = r;
+        r.orient = s.orient[S.slots[i]];
+        const uint4 *r4 = (const uint4 *)&r;
+#pragma unroll
+        for (int k = 0; k < P; k++)
+            stage[threadIdx.x * P + k] = r4[k];
     }
-    __threadfence_system(); // the records are visible to the peer before the flag can be
     __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(&sync->ticket, 1u) == gridDim.x - 1) { // the last CTA to finish
-        sync->ticket = 0;
-        sync->seq = next;
-        __threadfence_system();
-        *(volatile unsigned long long *)peerFlag = next;
+    const int cnt = min(HALO_THREADS, S.n - base);
+    if (cnt > 0) {
+        uint4 *dst = (uint4 *)(((next & 1) ? S.buf1 : S.buf0) + base);
+        for (int j = threadIdx.x; j < cnt * P; j += HALO_THREADS)
+            dst[j] = stage[j];
+    }
+    // ONE system-scope fence per CTA, by the thread that then takes the ticket (fences are cumulative over the barrier): a fence by
+    // each of the 128 threads made a slab's push cost tens of microseconds once the stores went over NVLink
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system(); // the records are visible to the peer before the flag can be
+        if (atomicAdd(&S.sync->ticket, 1u) == gridDim.x - 1) { // the last CTA of this side to finish
+            S.sync->ticket = 0;
+            S.sync->seq = next;
+            __threadfence_system();
+            *(volatile unsigned long long *)S.flag = next;
+        }
     }
 }
-template <class R>
-__global__ void k_halo_pull(Arrays<R> A, BrickArrays<R> BA, int world, const int32_t *vox, const int32_t *slots, int n, int resident, const HaloRec<R> *buf0,
-                            const HaloRec<R> *buf1, const unsigned long long *flag, HaloSync *sync) {
+template <class R> __global__ void __launch_bounds__(HALO_THREADS) k_halo_pull(Arrays<R> A, BrickArrays<R> BA, int world, HaloSide<R> lo, HaloSide<R> hi) {
+    constexpr int P = (int)(sizeof(HaloRec<R>) / 16);
+    __shared__ uint4 stage[HALO_THREADS * P];
     __shared__ int ok;
-    const unsigned long long want = sync->seq + 1;
+    const HaloSide<R> &S = blockIdx.y ? hi : lo;
+    const unsigned long long want = S.sync->seq + 1;
+    const int base = blockIdx.x * HALO_THREADS, i = base + threadIdx.x;
+    const int cnt = min(HALO_THREADS, S.n - base);
     if (threadIdx.x == 0) {
-        const unsigned long long t0 = halo_now_ns();
         ok = 1;
-        while (*(const volatile unsigned long long *)flag < want) {
-            __nanosleep(200);
-            if (halo_now_ns() - t0 > 10000000000ull) { // 10 s: the neighbour is gone; never hang the device
-                ok = 0;
-                break;
+        if (cnt > 0) {
+            const unsigned long long t0 = halo_now_ns();
+            while (*(const volatile unsigned long long *)S.flag < want) {
+                __nanosleep(100);
+                if (halo_now_ns() - t0 > 10000000000ull) { // 10 s: the neighbour is gone; never hang the device
+                    ok = 0;
+                    break;
+                }
             }
+            if (blockIdx.x == 0)
+                S.sync->waitNs += halo_now_ns() - t0;
+            __threadfence_system();
         }
-        __threadfence_system();
     }
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ok && i < n) {
-        const HaloRec<R> *src = ((want & 1) ? buf1 : buf0) + i;
-        HaloRec<R> r; // (cache-volatile loads: the lines were written by another device)
-        static_assert(sizeof(HaloRec<R>) % 16 == 0, "halo record is copied in 16-byte pieces");
-        const uint4 *s4 = (const uint4 *)src;
-        uint4 *d4 = (uint4 *)&r;
+    const int good = ok;
+    if (good && cnt > 0) {
+        const uint4 *src = (const uint4 *)(((want & 1) ? S.buf1 : S.buf0) + base); // (cache-volatile loads: the lines were written by another device)
+        for (int j = threadIdx.x; j < cnt * P; j += HALO_THREADS)
+            stage[j] = __ldcv(src + j);
+    }
+    __syncthreads();
+    if (good && i < S.n) {
+        HaloRec<R> r;
+        uint4 *r4 = (uint4 *)&r;
 #pragma unroll
-        for (int k = 0; k < (int)(sizeof(HaloRec<R>) / 16); k++)
-            d4[k] = __ldcv(s4 + k);
-        const D2 a{r.x, r.y}, b{r.z, __longlong_as_double((long long)r.packed)};
-        if (resident) {
-            const BrickSet<R> &s = BA.set[A.worlds[world].parity];
-            s.pxy[slots[i]] = a, s.pzt[slots[i]] = b, s.orient[slots[i]] = r.orient;
-        } else
-            A.pxy[vox[i]] = a, A.pzt[vox[i]] = b, A.orient[vox[i]] = r.orient;
+        for (int k = 0; k < P; k++)
+            r4[k] = stage[threadIdx.x * P + k];
+        const BrickSet<R> &s = BA.set[A.worlds[world].parity];
+        s.pxy[S.slots[i]] = D2{r.x, r.y}, s.pzt[S.slots[i]] = D2{r.z, __longlong_as_double((long long)r.packed)}, s.orient[S.slots[i]] = r.orient;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (!ok)
-            atomicAdd(&sync->timeouts, 1u);
-        if (atomicAdd(&sync->ticket, 1u) == gridDim.x - 1) {
-            sync->ticket = 0;
-            sync->seq = want;
+        if (!good)
+            atomicAdd(&S.sync->timeouts, 1u);
+        if (atomicAdd(&S.sync->ticket, 1u) == gridDim.x - 1) {
+            S.sync->ticket = 0;
+            S.sync->seq = want;
         }
     }
 }

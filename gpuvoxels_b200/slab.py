@@ -161,18 +161,18 @@ class SlabRunner:
 
     # -- device-side exchange -----------------------------------------------------------------------------------------------
     def open_endpoints(self):
-        """receive areas of my two ghost lists -> {"lo": bytes | None, "hi": bytes | None} to hand to the neighbours"""
+        """receive sides of my two ghost lists -> {"lo": (endpoint bytes, slots) | None, "hi": ...} to hand to the neighbours"""
         out = {}
         for name, lid, idx in (("lo", GHOST_LO, self.part.ghost_lo), ("hi", GHOST_HI, self.part.ghost_hi)):
-            out[name] = bytes(self.ctx.halo_open(0, lid)) if len(idx) else None
+            out[name] = (bytes(self.ctx.halo_open(0, lid)), self.ctx.halo_slots(0, lid, len(idx))) if len(idx) else None
         return out
 
-    def connect(self, lower_hi_endpoint, upper_lo_endpoint, same_process=False):
-        """my send lists write into the lower neighbour's "hi" area and the upper neighbour's "lo" area"""
-        if len(self.part.send_lo):
-            self.ctx.halo_connect(0, SEND_LO, lower_hi_endpoint, same_process)
-        if len(self.part.send_hi):
-            self.ctx.halo_connect(0, SEND_HI, upper_lo_endpoint, same_process)
+    def connect(self, lower_hi_endpoint, upper_lo_endpoint, same_process=False, fused=True):
+        """my send lists feed the lower neighbour's "hi" ghosts and the upper neighbour's "lo" ghosts; fused: the step kernel stores
+        straight into the neighbour's state arrays (one launch per time step), else staged push / pull kernels"""
+        for lid, idx, ep in ((SEND_LO, self.part.send_lo, lower_hi_endpoint), (SEND_HI, self.part.send_hi, upper_lo_endpoint)):
+            if len(idx):
+                self.ctx.halo_connect(0, lid, ep[0], same_process, ep[1] if fused else None)
 
     def run(self, steps):
         """`steps` time steps with the device-side exchange after each (asynchronous; every slab must be given the same count)"""

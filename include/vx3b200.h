@@ -302,16 +302,29 @@ typedef struct VX3B_HaloEndpoint {
     uint64_t device_ptr;     /* its address in the creating process (used when same_process != 0) */
     int32_t device, n;       /* CUDA device of the area; records per buffer */
     int32_t record_bytes, pad;
+    /* for the exchange FUSED into the step kernel (below): the brick-ordered position / orientation arrays of both buffer sets
+     * (set 0: pos.xy, pos.z|temperature|flags, orientation; then set 1), each an allocation of its own; 0 = not available */
+    uint8_t state_ipc_handle[6][64];
+    uint64_t state_ptr[6];
 } VX3B_HaloEndpoint;
 /* create (or return) the receive area of ghost list `ghost_list_id` */
 int vx3b_batch_halo_open(vx3b_ctx *ctx, int world, int ghost_list_id, VX3B_HaloEndpoint *out);
 /* connect send list `send_list_id` to the neighbour's receive area (its record count and record size must match) */
 int vx3b_batch_halo_connect(vx3b_ctx *ctx, int world, int send_list_id, const VX3B_HaloEndpoint *peer, int same_process);
+/* The exchange FUSED into the step kernel - the default when every connected list was connected with vx3b_batch_halo_connect_fused:
+ * the step kernel itself stores the new state of a boundary voxel into the neighbour's (mapped) brick-ordered arrays, at the slot
+ * the neighbour keeps for its ghost copy, raises the neighbour's flag when the launch is complete, and starts by waiting for its own
+ * flags.  ONE launch per time step, nothing staged.  vx3b_batch_halo_slots: the internal slots of a registered list ([n] int32), which
+ * the neighbour passes as peer_slots (same order as its send list). */
+int vx3b_batch_halo_slots(vx3b_ctx *ctx, int world, int list_id, int32_t *slots);
+int vx3b_batch_halo_connect_fused(vx3b_ctx *ctx, int world, int send_list_id, const VX3B_HaloEndpoint *peer, const int32_t *peer_slots, int same_process);
 /* `steps` time steps, each followed by the push of every connected send list and the pull of every opened ghost list; asynchronous
  * like vx3b_batch_run_async.  Every slab of the body must be given the same number of steps. */
 int vx3b_batch_run_slab(vx3b_ctx *ctx, int64_t steps);
 /* after a synchronisation: how many pulls gave up waiting for their neighbour (10 s each); non-zero = the run is invalid */
 int vx3b_batch_halo_timeouts(vx3b_ctx *ctx, int64_t *n);
+/* diagnostic: nanoseconds the pulls have spent waiting for their neighbours' flags since the lists were connected (load imbalance) */
+int vx3b_batch_halo_wait_ns(vx3b_ctx *ctx, int64_t *ns);
 
 /* ---------------------------------------------------------------- 3. job -------------
  * Replaces vx3_node_worker main + VX3_SimulationManager::start (vx3_node_worker.cu:32-142,

@@ -189,14 +189,14 @@ def test_slabs_with_halo_exchange_equal_the_whole_body_bit_for_bit(precision, n_
             assert np.array_equal(got[k], ref[k]), (k, np.abs(got[k] - ref[k]).max())
 
 
-def run_slabs_device_exchange(vxa, vxd, n_parts, steps, precision, options=None, calls=(None,)):
+def run_slabs_device_exchange(vxa, vxd, n_parts, steps, precision, options=None, calls=(None,), fused=True):
     """slabs built by the C++ host model, one context + one stream each on device 0, exchanging through mapped receive areas"""
     import torch
     parts = [slab.native_part(vxa, vxd, r, n_parts) for r in range(n_parts)]
     runners = [slab.SlabRunner(p, 0, precision, p.body_dt, options, stream=torch.cuda.Stream(0)) for p in parts]
     eps = [r.open_endpoints() for r in runners]
     for k, r in enumerate(runners):
-        r.connect(eps[k - 1]["hi"] if k > 0 else None, eps[k + 1]["lo"] if k < n_parts - 1 else None, same_process=True)
+        r.connect(eps[k - 1]["hi"] if k > 0 else None, eps[k + 1]["lo"] if k < n_parts - 1 else None, same_process=True, fused=fused)
     for n in calls:  # several calls: the sequence numbers carry on from one to the next
         for r in runners:
             r.run(steps if n is None else n)
@@ -214,11 +214,13 @@ def run_slabs_device_exchange(vxa, vxd, n_parts, steps, precision, options=None,
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("precision", [gv.FP64, gv.FP32])
 @pytest.mark.parametrize("n_parts", [2, 3])
-def test_device_side_exchange_equals_the_whole_body_bit_for_bit(precision, n_parts):
-    """vx3b_batch_run_slab: push into the neighbour's mapped receive area + flag, pull on the other side, 64 steps per graph, no
-    host in the loop - against the same body stepped whole; slabs from vx3b_model_from_vxa_slab"""
+def test_device_side_exchange_equals_the_whole_body_bit_for_bit(precision, n_parts, fused):
+    """vx3b_batch_run_slab, 64 steps per graph, no host in the loop - against the same body stepped whole; slabs from
+    vx3b_model_from_vxa_slab.  fused: k_brick itself stores the boundary voxels into the neighbour's mapped state arrays and raises
+    its flag (one launch per time step); staged: k_halo_push into the neighbour's receive area + flag, k_halo_pull on the other side"""
     for (vxa, vxd), opts, calls in (((W.cube_vxa(9), None), dict(brick_x=4, brick_y=3, brick_z=2), (150,)),
                                    ((W.xenobot_base_vxa(enable_collision=False), W.xenobot_vxd(9)), None, (70, 1, 79))):
         model = gv.Model.from_vxa(vxa, vxd)
@@ -230,7 +232,7 @@ def test_device_side_exchange_equals_the_whole_body_bit_for_bit(precision, n_par
         whole.run(150)
         ref = whole.read_state(0)
         whole.close()
-        got = run_slabs_device_exchange(vxa, vxd, n_parts, 150, precision, opts, calls)
+        got = run_slabs_device_exchange(vxa, vxd, n_parts, 150, precision, opts, calls, fused)
         for k in ("pos", "orient", "linMom", "angMom"):
             assert np.array_equal(got[k], ref[k]), (k, np.abs(got[k] - ref[k]).max())
 
