@@ -74,7 +74,7 @@ struct WorldD {
     int32_t listCap;        // entries per surface voxel's candidate list
     int32_t gridOff, gridLog2; // global-memory contact grid (kernels_contact.cuh): first bucket and log2(buckets); gridLog2 == 0: none
     // stop formula of the common shape `t - C` (every shipped experiment): compared directly instead of run through the formula machine
-    int32_t stopIsTimeMinusC, padStop;
+    int32_t stopIsTimeMinusC, gEpoch; // gEpoch (dynamic): epoch of the global contact grid's bucket heads (kernels_contact.cuh)
     double stopC;
     double tempK; // thermal worlds: 2 * 3.1415926f as the reference evaluates it (VX3_VoxelyzeKernel.cu:640), in double
     // dynamic
@@ -91,7 +91,7 @@ struct WorldD {
     // centre of mass at the end of the last run (results, fitness).  Kept apart from `com`, which the reference refreshes only on the
     // sampling steps of a run (VX3_VoxelyzeKernel.cu:314-334): a run continued by another call must see what one long run sees
     double finalCom[3];
-    int32_t numMeasured, gOverflow; // gOverflow: a global contact list overflowed at the last rebuild: all-pairs this step
+    int32_t numMeasured, gRebuildNext; // gRebuildNext: some surface voxel has moved skin/2 since the global contact lists were built: rebuild at the next step
     VX3B_Token stop[VX3B_MAX_TOKENS], fitnessF[VX3B_MAX_TOKENS], ff[3 * VX3B_MAX_TOKENS];
 };
 

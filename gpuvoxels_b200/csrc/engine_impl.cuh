@@ -195,6 +195,8 @@ template <class R> class Engine : public EngineBase {
     int brickGrid = 0, brickThreads = 256, nBrickWorlds = 0;
     bool brickDoesWorldStep = false;
     ContactGrid CG{};           // global-memory contact broad phase of the big worlds (kernels_contact.cuh)
+    bool gridCoversAll = false;
+    int stepLaunches = 0;        // kernels one enqueue_step launches (counted while enqueueing)
     int sStream0 = 0;           // first surface slot of the streaming-only worlds
     size_t gridBuckets = 0;
     bool brickResident = false; // the truth lives in the brick-ordered sets (after vx3b_batch_run_async); API-order arrays are stale
@@ -570,7 +572,9 @@ template <class R> class Engine : public EngineBase {
             W.listCap = listCaps[w];
             W.watchR2 = 0; // set below once the materials' constant sizes are known
             W.residentClass = pre[w].cls;
-            W.gRebuild = 1;
+            W.gRebuild = 1; // global contact lists (kernels_contact.cuh): built at the first step, in epoch 1
+            W.gEpoch = 1;
+            W.gRebuildNext = 0;
             memcpy(W.stop, d.stop_condition, sizeof(W.stop));
             memcpy(W.fitnessF, d.fitness, sizeof(W.fitnessF));
             memcpy(W.ff, d.force_field, sizeof(W.ff));
@@ -836,7 +840,6 @@ template <class R> class Engine : public EngineBase {
         anyGhost = anyGhostA;
         // global-memory contact grid (kernels_contact.cuh) for the collision worlds the streaming kernels may step: the worlds too
         // big for k_resident, or every world when a streaming path was chosen for all of them
-        std::vector<int2> bucketTiles;
         const bool gridAll = path == 1 || path == 3 || path == 5;
         const int sCover0 = gridAll ? 0 : sStream0;
         {
@@ -850,11 +853,15 @@ template <class R> class Engine : public EngineBase {
                     lg++;
                 hW[w].gridOff = (int)buckets;
                 hW[w].gridLog2 = lg;
-                for (int b = 0; b < (1 << lg); b += 1024)
-                    bucketTiles.push_back(make_int2(w, b));
                 buckets += (size_t)1 << lg;
             }
             gridBuckets = buckets;
+            gridCoversAll = true; // every collision world the streaming kernels may step has a grid: k_contact is not needed
+            for (int oi = 0; oi < n; oi++) {
+                const int w = perm[oi];
+                if (worlds[w].enable_collision && H[w].ns >= 2 && (gridAll || pre[w].cls == 0) && hW[w].gridLog2 == 0)
+                    gridCoversAll = false;
+            }
         }
 
         lap("host staging");
@@ -1252,13 +1259,12 @@ template <class R> class Engine : public EngineBase {
         CG = ContactGrid{};
         if (gridBuckets > 0) {
             const size_t cover = surf.size() - (size_t)sCover0; // arrays are indexed by absolute surface slot: pointers are pre-offset
-            int32_t *dHead = nullptr, *dNext = nullptr, *dList = nullptr, *dCount = nullptr;
+            unsigned long long *dHead = nullptr; // zero-filled: epoch 0, which no world ever has
+            int32_t *dNext = nullptr, *dList = nullptr, *dCount = nullptr;
             uint32_t *dKey = nullptr;
             float4 *dRef = nullptr;
-            int2 *dBT = nullptr;
             if ((rc = dalloc(&dHead, gridBuckets)) != VX3B_OK || (rc = dalloc(&dNext, cover)) != VX3B_OK || (rc = dalloc(&dKey, cover)) != VX3B_OK ||
-                (rc = dalloc(&dRef, cover)) != VX3B_OK || (rc = dalloc(&dList, cover * CGRID_CAP)) != VX3B_OK || (rc = dalloc(&dCount, cover)) != VX3B_OK ||
-                (rc = dalloc(&dBT, bucketTiles.size(), bucketTiles.data())) != VX3B_OK)
+                (rc = dalloc(&dRef, cover)) != VX3B_OK || (rc = dalloc(&dList, cover * CGRID_CAP)) != VX3B_OK || (rc = dalloc(&dCount, cover)) != VX3B_OK)
                 return rc;
             CG.s0 = sCover0;
             CG.head = dHead;
@@ -1267,8 +1273,8 @@ template <class R> class Engine : public EngineBase {
             CG.ref = dRef - sCover0;
             CG.list = dList - (size_t)sCover0 * CGRID_CAP;
             CG.count = dCount - sCover0;
-            CG.buckets = dBT;
-            CG.nBucketTiles = (int)bucketTiles.size();
+            CG.cap = contactListCap > 0 ? std::min((int)CGRID_CAP, contactListCap) : (int)CGRID_CAP;
+            CG.nBuckets = (int)std::min<size_t>(gridBuckets, 0x7fffffff);
         }
         if ((rc = dalloc(&dActive, 1)) != VX3B_OK)
             return rc;
@@ -1310,21 +1316,71 @@ template <class R> class Engine : public EngineBase {
                 const WorldHost &h = H[w];
                 if (h.nv == 0)
                     continue;
-                // brick key of every voxel; voxels of a brick stay in creation order (x runs are contiguous in memory)
-                int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+                // brick key of every voxel; voxels of a brick stay in creation order (x runs are contiguous in memory).
+                // Bricks are cut per connected body when that gives fewer of them: a scene of many bodies (BASELINE configs[3]: 8^3 cubes on
+                // a 9-cell pitch) cut on ONE world-wide grid fills its bricks to 58 %; cut from each body's own corner, every brick is full.
+                std::vector<int32_t> comp(h.nv);
                 for (int v = 0; v < h.nv; v++)
-                    for (int k = 0; k < 3; k++) {
-                        int c = (&lat[h.voff + v].x)[k];
-                        mn[k] = std::min(mn[k], c);
-                        mx[k] = std::max(mx[k], c);
+                    comp[v] = v;
+                auto find = [&](int v) {
+                    while (comp[v] != v)
+                        v = comp[v] = comp[comp[v]];
+                    return v;
+                };
+                for (int l = 0; l < h.nl; l++) {
+                    const int a = find(lends[h.loff + l].x - h.voff), b = find(lends[h.loff + l].y - h.voff);
+                    if (a != b)
+                        comp[std::max(a, b)] = std::min(a, b); // the root is the component's first voxel
+                }
+                std::vector<int32_t> rank(h.nv, -1); // component number, in order of the first voxel
+                int nComp = 0;
+                for (int v = 0; v < h.nv; v++) {
+                    const int r = find(v);
+                    if (rank[r] < 0)
+                        rank[r] = nComp++;
+                    comp[v] = r;
+                }
+                auto count_bricks = [&](bool perBody, std::vector<int> &mnOut, int ext[3]) -> int64_t {
+                    const int nc = perBody ? nComp : 1;
+                    mnOut.assign((size_t)nc * 3, 1 << 30);
+                    std::vector<int> mxs((size_t)nc * 3, -(1 << 30));
+                    for (int v = 0; v < h.nv; v++) {
+                        const int c = perBody ? rank[comp[v]] : 0;
+                        for (int k = 0; k < 3; k++) {
+                            const int x = (&lat[h.voff + v].x)[k];
+                            mnOut[(size_t)c * 3 + k] = std::min(mnOut[(size_t)c * 3 + k], x);
+                            mxs[(size_t)c * 3 + k] = std::max(mxs[(size_t)c * 3 + k], x);
+                        }
                     }
-                const int64_t nbx = (mx[0] - mn[0]) / BX + 1, nby = (mx[1] - mn[1]) / BY + 1;
+                    const int bd[3] = {BX, BY, BZ};
+                    ext[0] = ext[1] = ext[2] = 1;
+                    int64_t total = 0; // upper bound of the bricks in use: cells of every body's own box
+                    for (int c = 0; c < nc; c++) {
+                        int64_t cells = 1;
+                        for (int k = 0; k < 3; k++) {
+                            const int e = (mxs[(size_t)c * 3 + k] - mnOut[(size_t)c * 3 + k]) / bd[k] + 1;
+                            ext[k] = std::max(ext[k], e);
+                            cells *= e;
+                        }
+                        total += cells;
+                    }
+                    return total;
+                };
+                std::vector<int> mnWorld, mnBody;
+                int extWorld[3], extBody[3];
+                const int64_t cellsWorld = count_bricks(false, mnWorld, extWorld);
+                const int64_t cellsBody = nComp > 1 ? count_bricks(true, mnBody, extBody) : cellsWorld;
+                const bool perBody = nComp > 1 && cellsBody * 5 < cellsWorld * 4 && (int64_t)nComp * extBody[0] * extBody[1] * extBody[2] <= (int64_t)8 * h.nv + 4096;
+                const std::vector<int> &mnUse = perBody ? mnBody : mnWorld;
+                const int64_t nbx = perBody ? extBody[0] : extWorld[0], nby = perBody ? extBody[1] : extWorld[1], nbz = perBody ? extBody[2] : extWorld[2];
                 std::vector<std::pair<int64_t, int>> keyed(h.nv);
                 auto key_of = [&](int v) {
                     const short4 c = lat[h.voff + v];
-                    return (((int64_t)(c.z - mn[2]) / BZ) * nby + (c.y - mn[1]) / BY) * nbx + (c.x - mn[0]) / BX;
+                    const int64_t body = perBody ? rank[comp[v]] : 0;
+                    const int *mn = &mnUse[(size_t)body * 3];
+                    return ((body * nbz + (c.z - mn[2]) / BZ) * nby + (c.y - mn[1]) / BY) * nbx + (c.x - mn[0]) / BX;
                 };
-                const int64_t nCells = nbx * nby * ((int64_t)(mx[2] - mn[2]) / BZ + 1);
+                const int64_t nCells = (perBody ? (int64_t)nComp : 1) * nbx * nby * nbz;
                 if (nCells <= (int64_t)4 * h.nv + 4096) { // stable counting sort by brick (= sorting the (key, index) pairs, much cheaper)
                     std::vector<int32_t> start((size_t)nCells + 1, 0);
                     for (int v = 0; v < h.nv; v++)
@@ -1543,38 +1599,46 @@ template <class R> class Engine : public EngineBase {
     }
 
     // ---- streaming path: CUDA graph of `chunk` steps -----------------------------------------------------
-    int launches_per_step() const { return 3 + (anyCollision ? 1 + (contactGrid && CG.nBucketTiles > 0 ? 5 : 0) : 0); }
     // mixed: only the streaming-only worlds (a suffix of every array) are stepped here; the others run in k_resident
     // fused: one k_fused launch per step instead of k_links + k_voxels
     void enqueue_step(int useStop, bool mixed, bool fused) {
         const int l0 = mixed ? lStream0 : 0, v0 = mixed ? vStream0 : 0, t0 = mixed ? tileStream0 : 0;
         const unsigned lb = (A.nlTot - l0 + 255) / 256, vb = (A.nvTot - v0 + 255) / 256, wb = (A.nWorlds + 127) / 128;
-        if (!fused && A.nlTot > l0)
+        int launches = 0;
+        if (!fused && A.nlTot > l0) {
             k_links<R><<<lb, 256, 0, stream>>>(A, l0);
+            launches++;
+        }
+        ContactGrid G{};
+        int nsCover = 0;
         if (anyCollision && (int)hTiles.size() > t0) {
-            const bool grid = contactGrid && CG.nBucketTiles > 0;
-            if (grid) { // broad phase (rebuilt only when stale) + narrow phase over candidate lists; overflowed worlds fall through
-                ContactGrid G = CG;
+            const bool grid = contactGrid && CG.nBuckets > 0;
+            if (grid) { // broad phase (insert: only on the steps a world rebuilds) + lists and narrow phase in one kernel
+                G = CG;
                 G.s0 = std::max(CG.s0, mixed ? sStream0 : 0);
-                const int nsCover = A.nsTot - G.s0;
+                nsCover = A.nsTot - G.s0;
                 if (nsCover > 0) {
-                    k_cgrid_check<R><<<(unsigned)((nsCover + 255) / 256), 256, 0, stream>>>(A, G);
-                    k_cgrid_clear<R><<<(unsigned)G.nBucketTiles, 256, 0, stream>>>(A, G);
                     k_cgrid_insert<R><<<(unsigned)((nsCover + 255) / 256), 256, 0, stream>>>(A, G);
-                    k_cgrid_lists<R><<<(unsigned)((nsCover + 127) / 128), 128, 0, stream>>>(A, G);
                     k_cgrid_narrow<R><<<(unsigned)((nsCover + 127) / 128), 128, 0, stream>>>(A, G, recordPairs);
-                }
+                    launches += 2;
+                } else
+                    G = ContactGrid{};
             }
-            k_contact<R><<<(unsigned)hTiles.size() - t0, 128, 0, stream>>>(A, dTiles + t0, recordPairs, grid ? 1 : 0);
+            if (!grid || !gridCoversAll) { // the all-pairs scan for the worlds without a grid
+                k_contact<R><<<(unsigned)hTiles.size() - t0, 128, 0, stream>>>(A, dTiles + t0, recordPairs, grid ? 1 : 0);
+                launches++;
+            }
         }
         if (fused) {
             const int b0 = mixed ? fusedBrick0 : 0;
             FusedArrays F = FA;
             F.bricks += b0;
-            if (FA.nBricks > b0)
-                k_fused<R><<<(unsigned)(FA.nBricks - b0), 256, fusedSmem, stream>>>(A, F, fusedCapTab, fusedCapOwn);
             // every world this step touches is a brick world: k_brick's last CTA does the end-of-step bookkeeping itself
             brickDoesWorldStep = BA.nBricks > 0 && FA.nBricks <= b0 && !anyCollision && nBrickWorlds == (mixed ? (int)H.size() - numResident : (int)H.size());
+            if (FA.nBricks > b0) {
+                k_fused<R><<<(unsigned)(FA.nBricks - b0), 256, fusedSmem, stream>>>(A, F, fusedCapTab, fusedCapOwn, G);
+                launches++;
+            }
             if (BA.nBricks > 0) {
                 const int ws = brickDoesWorldStep ? 1 : 0;
                 if (peerOn && ws) { // one body over several GPUs: the exchange with the neighbouring slabs is part of the kernel
@@ -1586,12 +1650,22 @@ template <class R> class Engine : public EngineBase {
                     k_brick<R, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive);
                 else
                     k_brick<R, false><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive);
+                launches++;
             }
-            if (brickDoesWorldStep)
+            if (brickDoesWorldStep) {
+                stepLaunches = launches;
                 return;
-        } else if (A.nvTot > v0)
+            }
+        } else if (A.nvTot > v0) {
             k_voxels<R><<<vb, 256, 0, stream>>>(A, v0);
+            launches++;
+            if (nsCover > 0) { // stale candidate lists?  (the fused path asks inside its voxel pass)
+                k_cgrid_check<R><<<(unsigned)((nsCover + 255) / 256), 256, 0, stream>>>(A, G);
+                launches++;
+            }
+        }
         k_world_step<R><<<wb, 128, 0, stream>>>(A, useStop, dActive);
+        stepLaunches = launches + 1;
     }
     // one instantiated graph per chunk length (a run of 200 steps replays the 64-step graph three times and an 8-step one once;
     // re-capturing on every change of length costs milliseconds)
@@ -1636,8 +1710,7 @@ template <class R> class Engine : public EngineBase {
             if (rc != VX3B_OK)
                 return rc;
             CUDA_TRY(cudaGraphLaunch(graphExec, stream));
-            const int fusedLaunches = (FA.nBricks > (mixed ? fusedBrick0 : 0) ? 1 : 0) + (BA.nBricks > 0 ? 1 : 0);
-            lastLaunches += (int64_t)steps * (fused ? (brickDoesWorldStep ? 1 : launches_per_step() - 2 + fusedLaunches) : launches_per_step()) + 1;
+            lastLaunches += (int64_t)steps * stepLaunches + 1;
             done += steps;
             CUDA_TRY(cudaMemcpyAsync(hActive, dActive, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));

@@ -217,6 +217,15 @@ template <class R> __device__ __noinline__ void brick_world_step(WorldD *worlds,
         if (!W.active || !(W.flags & WF_BRICK))
             continue;
         W.parity ^= 1;
+        // fields other CTAs of the still-running kernel wrote - divergedNow with plain stores, comAcc with atomics - are fetched with
+        // atomics and stored back, so that the plain loads of the bookkeeping code cannot be served from a stale L1 line of this SM
+        // (a thread always sees its own stores)
+        if (atomicOr(&W.divergedNow, 0))
+            W.divergedNow = 1;
+        for (int k = 0; k < 4; k++) {
+            const double fresh = atomicAdd(&W.comAcc[k], 0.0);
+            W.comAcc[k] = fresh;
+        }
         world_end_of_step<R, false>(*none, W, useStop);
         if (W.active && activeCount)
             atomicAdd(activeCount, 1);

@@ -3,17 +3,21 @@
 //
 // The reference tests all Ns^2/2 surface pairs every step (gpu_update_attach, VX3/VX3_VoxelyzeKernel.cu:833-843, 682-727);
 // k_contact (kernels_stream.cuh) restates that with shared-memory tiles and stays as the fallback and cross-check.  Here:
-//   check   every step, one thread per surface voxel: has it moved more than skin/2 (relative to the world's common drift) since
-//           its lists were built?  -> the world rebuilds this step;
-//   rebuild (only then) hashed cell buckets as linked lists (atomicExch push), then each surface voxel walks the 27 cells around
-//           it and lists every surface voxel within (largest watch distance + skin) that it may collide with (not a lattice
-//           neighbour, not both Fixed), sorted ascending so that force sums keep the all-pairs order;
-//   narrow  every step: the reference's exact double-precision predicate on the listed candidates only; both members of a pair
-//           evaluate it in the same orientation (voxel1 = the later surface voxel), so the forces are equal and opposite without
-//           atomics and - candidate order being the all-pairs order - BIT-IDENTICAL to k_contact's.
+//   check   every step, inside the voxel pass (k_fused) or right after it (k_cgrid_check, two-kernel path): has a surface voxel moved
+//           more than skin/2 (relative to the world's common drift) since its lists were built?  -> the world rebuilds at the next step;
+//   insert  (rebuild steps only) hashed cell buckets as linked lists (atomicExch push); bucket heads carry the epoch of the rebuild,
+//           so a new rebuild needs no clearing pass;
+//   narrow  (k_cgrid_narrow) on rebuild steps each surface voxel first walks the 27 cells around it and lists every surface voxel
+//           within (largest watch distance + skin) that it may collide with (not a lattice neighbour, not both Fixed), sorted
+//           ascending so that force sums keep the all-pairs order; every step: the reference's exact double-precision predicate on
+//           the listed candidates only; both members of a pair evaluate it in the same orientation (voxel1 = the later surface
+//           voxel), so the forces are equal and opposite without atomics and - candidate order being the all-pairs order -
+//           BIT-IDENTICAL to k_contact's.
 // Any pair the reference would watch at the current step is within the list radius of the rebuild positions (triangle
-// inequality on the skin), so the watched-pair set is exactly the reference's.  A list that overflows sends its world back to
-// k_contact for that step.  Same scheme as k_resident's shared-memory version, sized for 1e5+ surface voxels.
+// inequality on the skin), so the watched-pair set is exactly the reference's.  A voxel whose list overflows takes its candidates
+// from the grid directly, in the same order.  Same scheme as k_resident's shared-memory version, sized for 1e5+ surface voxels.
+// Per time step: insert (exits at once when no world rebuilds), narrow, then the step kernel and k_world_step - 4 launches with
+// k_fused (8 in round 1).
 #pragma once
 #include "engine.cuh"
 #include "kernels_stream.cuh"
@@ -24,14 +28,14 @@ enum { CGRID_CAP = 32 }; // candidates per surface voxel (12 face + 8 body diago
 
 struct ContactGrid {
     int s0;              // first surface slot of the streaming-only worlds (the kernels cover [s0, nsTot))
-    int32_t *head;       // [sum of buckets] first surface slot (world-local) of every bucket or -1
+    unsigned long long *head; // [sum of buckets] epoch << 32 | first surface slot (world-local) of the bucket; another epoch than the world's = empty
     int32_t *next;       // [nsTot] chain
     uint32_t *key;       // [nsTot] packed cell of the voxel at the last rebuild
     float4 *ref;         // [nsTot] position at the last rebuild
     int32_t *list;       // [nsTot][CGRID_CAP] world-local surface slots, ascending
-    int32_t *count;      // [nsTot]
-    const int2 *buckets; // work items of the clear kernel: (world, first bucket) per 1024 buckets
-    int nBucketTiles;
+    int32_t *count;      // [nsTot]; cap + 1 = the list overflowed: the voxel walks the grid itself
+    int cap;             // entries per list in use (<= CGRID_CAP)
+    int nBuckets;        // sum over the worlds (0 = no grid)
 };
 
 VXD uint32_t cgrid_key(double x, double y, double z, double invCell) {
@@ -39,16 +43,28 @@ VXD uint32_t cgrid_key(double x, double y, double z, double invCell) {
     return (uint32_t)(cx & 1023) | ((uint32_t)(cy & 1023) << 10) | ((uint32_t)(cz & 1023) << 20);
 }
 VXD uint32_t cgrid_hash(uint32_t key, int log2H) { return (key * 2654435761u) >> (32 - log2H); }
+VXD bool cgrid_covers(const WorldD &W) { return W.active && (W.flags & WF_COLLISION) && !(W.flags & WF_RESIDENT) && W.gridLog2 > 0; }
 
 template <class R> VXD bool cgrid_world(const Arrays<R> &A, int s, int &w, int &v, int &local) {
     v = A.surf[s];
     w = A.vworld[v];
     const WorldD &W = A.worlds[w];
     local = s - W.soff;
-    return W.active && (W.flags & WF_COLLISION) && !(W.flags & WF_RESIDENT) && W.gridLog2 > 0;
+    return cgrid_covers(W);
 }
 
-// every step: stale lists?  (the first surface voxel's thread also opens the step: hit counting happens in k_cgrid_narrow)
+// Stale lists?  One surface voxel: has it moved more than skin/2, relative to the drift `c` of the world's reference voxel, since
+// the lists were built?  Any c common to the voxels of one check serves (|d_i - d_j| <= |d_i - c| + |d_j - c|); the callers take
+// the reference voxel's position from the buffer set that no thread of the running kernel writes.  The answer is for the NEXT step
+// (W.gRebuildNext; the world's end-of-step bookkeeping turns it into gRebuild and opens a new epoch of the bucket heads).
+VXD void cgrid_check_one(WorldD &W, const ContactGrid &G, int s, double x, double y, double z, double mx, double my, double mz) {
+    const int sm = W.soff + (W.ns >> 1);
+    const float4 r = G.ref[s], rm = G.ref[sm];
+    const float dx = ((float)x - r.x) - ((float)mx - rm.x), dy = ((float)y - r.y) - ((float)my - rm.y), dz = ((float)z - r.z) - ((float)mz - rm.z);
+    if (dx * dx + dy * dy + dz * dz > W.skinHalf2)
+        W.gRebuildNext = 1; // benign race: everybody writes 1
+}
+// the streaming (two-kernel) path: after k_voxels, before k_world_step
 template <class R> __global__ void __launch_bounds__(256) k_cgrid_check(Arrays<R> A, ContactGrid G) {
     const int s = G.s0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= A.nsTot)
@@ -57,25 +73,10 @@ template <class R> __global__ void __launch_bounds__(256) k_cgrid_check(Arrays<R
     if (!cgrid_world(A, s, w, v, i))
         return;
     WorldD &W = A.worlds[w];
-    if (W.gRebuild)
-        return;
     const StateSet<R> cur = cur_set(A, W.parity);
-    const int sm = W.soff + (W.ns >> 1), vm = A.surf[sm]; // common drift = that of one reference voxel
+    const int vm = A.surf[W.soff + (W.ns >> 1)];
     const D2 a = cur.pxy[v], b = cur.pzt[v], am = cur.pxy[vm], bm = cur.pzt[vm];
-    const float4 r = G.ref[s], rm = G.ref[sm];
-    const float dx = ((float)a.x - r.x) - ((float)am.x - rm.x), dy = ((float)a.y - r.y) - ((float)am.y - rm.y), dz = ((float)b.x - r.z) - ((float)bm.x - rm.z);
-    if (dx * dx + dy * dy + dz * dz > W.skinHalf2)
-        W.gRebuild = 1; // benign race: everybody writes 1
-}
-template <class R> __global__ void __launch_bounds__(256) k_cgrid_clear(Arrays<R> A, ContactGrid G) {
-    const int2 t = G.buckets[blockIdx.x];
-    const WorldD &W = A.worlds[t.x];
-    if (!W.active || !W.gRebuild || (W.flags & WF_RESIDENT) || W.gridLog2 == 0)
-        return;
-    const int H = 1 << W.gridLog2;
-    for (int k = threadIdx.x; k < 1024; k += blockDim.x)
-        if (t.y + k < H)
-            G.head[W.gridOff + t.y + k] = -1;
+    cgrid_check_one(W, G, s, a.x, a.y, b.x, am.x, am.y, bm.x);
 }
 template <class R> __global__ void __launch_bounds__(256) k_cgrid_insert(Arrays<R> A, ContactGrid G) {
     const int s = G.s0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,124 +93,139 @@ template <class R> __global__ void __launch_bounds__(256) k_cgrid_insert(Arrays<
     const uint32_t key = cgrid_key(a.x, a.y, b.x, W.invCell);
     G.key[s] = key;
     G.ref[s] = make_float4((float)a.x, (float)a.y, (float)b.x, 0.f);
-    G.next[s] = atomicExch(&G.head[W.gridOff + cgrid_hash(key, W.gridLog2)], i);
-    if (i == 0) {
+    const unsigned long long epoch = (unsigned long long)(uint32_t)W.gEpoch << 32;
+    const unsigned long long old = atomicExch(&G.head[W.gridOff + cgrid_hash(key, W.gridLog2)], epoch | (unsigned long long)(uint32_t)i);
+    G.next[s] = (old >> 32) == (epoch >> 32) ? (int)(uint32_t)old : -1;
+    if (i == 0)
         W.contactRebuilds++;
-        W.gOverflow = 0;
-    }
 }
-template <class R> __global__ void __launch_bounds__(128) k_cgrid_lists(Arrays<R> A, ContactGrid G) {
-    const int s = G.s0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= A.nsTot)
-        return;
-    int w, v, i;
-    if (!cgrid_world(A, s, w, v, i))
-        return;
-    WorldD &W = A.worlds[w];
-    if (!W.gRebuild)
-        return;
-    const StateSet<R> cur = cur_set(A, W.parity);
-    const D2 a = cur.pxy[v], b = cur.pzt[v];
-    const short4 c1 = A.lat[v];
-    const bool fixed1 = A.vmats[A.vmat[v]].fixed != 0;
-    const uint32_t key = G.key[s];
-    const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
-    const double listR2 = W.listR2;
-    int32_t *list = G.list + (size_t)s * CGRID_CAP;
-    int n = 0;
-    bool overflow = false;
-    for (int c = 0; c < 27; c++) {
-        const int dx = c % 3 - 1, dy = (c / 3) % 3 - 1, dz = c / 9 - 1;
-        const uint32_t k2 = (uint32_t)((cx + dx) & 1023) | ((uint32_t)((cy + dy) & 1023) << 10) | ((uint32_t)((cz + dz) & 1023) << 20);
-        for (int j = G.head[W.gridOff + cgrid_hash(k2, W.gridLog2)]; j >= 0; j = G.next[W.soff + j]) {
-            if (j == i || G.key[W.soff + j] != k2)
-                continue;
-            const int v2 = A.surf[W.soff + j];
-            const short4 c2 = A.lat[v2];
-            if (abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1 || (fixed1 && A.vmats[A.vmat[v2]].fixed))
-                continue; // lattice neighbours are linked and never collide (is_neighbor depth 1); two Fixed voxels are skipped
-            const D2 a2 = cur.pxy[v2], b2 = cur.pzt[v2];
-            const double ex = a.x - a2.x, ey = a.y - a2.y, ez = b.x - b2.x;
-            if (ex * ex + ey * ey + ez * ez > listR2)
-                continue;
-            if (n == CGRID_CAP) {
-                overflow = true;
-                continue;
-            }
-            int p = n++; // insertion sort: ascending surface slot = the order in which the all-pairs scan meets them
-            while (p > 0 && list[p - 1] > j) {
-                list[p] = list[p - 1];
-                p--;
-            }
-            list[p] = j;
-        }
-    }
-    G.count[s] = n;
-    if (overflow) {
-        W.gOverflow = 1; // this world takes the all-pairs kernel this step and rebuilds again at the next
-        W.contactOverflows++;
-    }
+// first slot of a bucket's chain in the world's current epoch, or -1
+VXD int cgrid_first(const WorldD &W, const ContactGrid &G, uint32_t k2) {
+    const unsigned long long h = G.head[W.gridOff + cgrid_hash(k2, W.gridLog2)];
+    return (uint32_t)(h >> 32) == (uint32_t)W.gEpoch ? (int)(uint32_t)h : -1;
 }
-// every step: forces from the listed candidates.  Worlds whose lists overflowed are left to k_contact (launched after this).
+// Every step, one thread per surface voxel: (only when the world's lists are stale) walk the 27 cells around the voxel and list,
+// ascending, every surface voxel within (largest watch distance + skin) it may collide with; then the forces from the listed
+// candidates.  A voxel whose list overflowed walks the grid itself every step, taking the candidates in ascending order too (the
+// cells are those of the last rebuild: whatever is within the watch distance now was within the list radius then).
 template <class R> __global__ void __launch_bounds__(128) k_cgrid_narrow(Arrays<R> A, ContactGrid G, int recordPairs) {
     const int s = G.s0 + blockIdx.x * blockDim.x + threadIdx.x;
     int hits = 0, w = -1, v = 0, i = 0;
-    bool mine = s < A.nsTot && cgrid_world(A, s, w, v, i);
-    if (mine && A.worlds[w].gOverflow)
-        mine = false;
-    if (mine) {
-        WorldD &W = A.worlds[w];
-        const bool rec = recordPairs && W.runSteps == 1;
-        const StateSet<R> cur = cur_set(A, W.parity);
-        auto load = [&](int vv, V3<double> &p, V3<R> &l, float &temp) {
-            const D2 pa = cur.pxy[vv], pb = cur.pzt[vv];
-            temp = u2f((uint32_t)((unsigned long long)__double_as_longlong(pb.y) & 0xffffffffu));
-            p = {pa.x, pa.y, pb.x};
-            const auto lm = cur.lm[vv];
-            l = {lm.x, lm.y, lm.z};
-        };
-        V3<double> p1;
-        V3<R> l1;
-        float t1;
-        load(v, p1, l1, t1);
-        const DVoxMat &m1 = A.vmats[A.vmat[v]];
-        const double watchR2 = W.watchR2;
-        V3<R> acc{R(0), R(0), R(0)};
-        const int n = G.count[s];
-        const int32_t *list = G.list + (size_t)s * CGRID_CAP;
-        for (int k = 0; k < n; k++) {
-            const int j = list[k], v2 = A.surf[W.soff + j];
-            V3<double> p2;
-            V3<R> l2;
-            float t2;
-            load(v2, p2, l2, t2);
-            if (watchR2 > 0) { // constant voxel sizes: reject on the squared distance alone
-                const double ex = p1.x - p2.x, ey = p1.y - p2.y, ez = p1.z - p2.z;
-                if (ex * ex + ey * ey + ez * ez > watchR2)
+    if (s >= A.nsTot || !cgrid_world(A, s, w, v, i))
+        return;
+    WorldD &W = A.worlds[w];
+    const StateSet<R> cur = cur_set(A, W.parity);
+    const D2 a = cur.pxy[v], b = cur.pzt[v];
+    const short4 c1 = A.lat[v];
+    const DVoxMat &m1 = A.vmats[A.vmat[v]];
+    const bool fixed1 = m1.fixed != 0;
+    const uint32_t key = G.key[s];
+    const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
+    int32_t *list = G.list + (size_t)s * CGRID_CAP;
+    auto cell_key = [&](int c) {
+        const int dx = c % 3 - 1, dy = (c / 3) % 3 - 1, dz = c / 9 - 1;
+        return (uint32_t)((cx + dx) & 1023) | ((uint32_t)((cy + dy) & 1023) << 10) | ((uint32_t)((cz + dz) & 1023) << 20);
+    };
+    auto may_collide = [&](int j) { // not itself, not a lattice neighbour (linked: is_neighbor depth 1), not both Fixed
+        if (j == i)
+            return false;
+        const int v2 = A.surf[W.soff + j];
+        const short4 c2 = A.lat[v2];
+        return !(abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1 || (fixed1 && A.vmats[A.vmat[v2]].fixed));
+    };
+    if (W.gRebuild) {
+        const double listR2 = W.listR2;
+        int n = 0;
+        bool overflow = false;
+        for (int c = 0; c < 27 && !overflow; c++) {
+            const uint32_t k2 = cell_key(c);
+            for (int j = cgrid_first(W, G, k2); j >= 0; j = G.next[W.soff + j]) {
+                if (G.key[W.soff + j] != k2 || !may_collide(j))
                     continue;
-            }
-            const DVoxMat &m2 = A.vmats[A.vmat[v2]];
-            V3<R> f;
-            if (i > j) {
-                if (contact_pair<R>(m1, t1, p1, l1, m2, t2, p2, l2, f)) {
-                    acc = acc + f;
-                    if ((m1.isTarget != 0) != (m2.isTarget != 0))
-                        hits++;
-                    if (rec) {
-                        int slot = atomicAdd(A.pairCount, 1);
-                        if (slot < A.pairCap)
-                            A.pairBuf[slot] = make_int4(w, v - W.voff, v2 - W.voff, 0);
-                    }
+                const int v2 = A.surf[W.soff + j];
+                const D2 a2 = cur.pxy[v2], b2 = cur.pzt[v2];
+                const double ex = a.x - a2.x, ey = a.y - a2.y, ez = b.x - b2.x;
+                if (ex * ex + ey * ey + ez * ez > listR2)
+                    continue;
+                if (n == G.cap) {
+                    overflow = true;
+                    break;
                 }
-            } else if (contact_pair<R>(m2, t2, p2, l2, m1, t1, p1, l1, f))
-                acc = acc - f;
+                int p = n++; // insertion sort: ascending surface slot = the order in which the all-pairs scan meets them
+                while (p > 0 && list[p - 1] > j) {
+                    list[p] = list[p - 1];
+                    p--;
+                }
+                list[p] = j;
+            }
         }
-        A.contactF[s] = mk4<R>(acc.x, acc.y, acc.z, R(0));
-        if (i == 0)
-            W.gRebuild = 0; // lists are fresh (or still valid); k_cgrid_check of the next step decides again
-        if (hits)
-            atomicAdd(&W.collisionCount, hits);
+        G.count[s] = overflow ? G.cap + 1 : n;
+        if (overflow)
+            atomicAdd(&W.contactOverflows, 1);
     }
+    const bool rec = recordPairs && W.runSteps == 1;
+    auto load = [&](int vv, V3<double> &p, V3<R> &l, float &temp) {
+        const D2 pa = cur.pxy[vv], pb = cur.pzt[vv];
+        temp = u2f((uint32_t)((unsigned long long)__double_as_longlong(pb.y) & 0xffffffffu));
+        p = {pa.x, pa.y, pb.x};
+        const auto lm = cur.lm[vv];
+        l = {lm.x, lm.y, lm.z};
+    };
+    V3<double> p1;
+    V3<R> l1;
+    float t1;
+    load(v, p1, l1, t1);
+    const double watchR2 = W.watchR2;
+    V3<R> acc{R(0), R(0), R(0)};
+    auto pair = [&](int j) {
+        const int v2 = A.surf[W.soff + j];
+        V3<double> p2;
+        V3<R> l2;
+        float t2;
+        load(v2, p2, l2, t2);
+        if (watchR2 > 0) { // constant voxel sizes: reject on the squared distance alone
+            const double ex = p1.x - p2.x, ey = p1.y - p2.y, ez = p1.z - p2.z;
+            if (ex * ex + ey * ey + ez * ez > watchR2)
+                return;
+        }
+        const DVoxMat &m2 = A.vmats[A.vmat[v2]];
+        V3<R> f;
+        if (i > j) {
+            if (contact_pair<R>(m1, t1, p1, l1, m2, t2, p2, l2, f)) {
+                acc = acc + f;
+                if ((m1.isTarget != 0) != (m2.isTarget != 0))
+                    hits++;
+                if (rec) {
+                    int slot = atomicAdd(A.pairCount, 1);
+                    if (slot < A.pairCap)
+                        A.pairBuf[slot] = make_int4(w, v - W.voff, v2 - W.voff, 0);
+                }
+            }
+        } else if (contact_pair<R>(m2, t2, p2, l2, m1, t1, p1, l1, f))
+            acc = acc - f;
+    };
+    const int n = G.count[s];
+    if (n <= G.cap) {
+        for (int k = 0; k < n; k++)
+            pair(list[k]);
+    } else { // overflowed list: the candidates straight from the grid, smallest slot first (selection: rare, and exact)
+        for (int last = -1;;) {
+            int best = 0x7fffffff;
+            for (int c = 0; c < 27; c++) {
+                const uint32_t k2 = cell_key(c);
+                for (int j = cgrid_first(W, G, k2); j >= 0; j = G.next[W.soff + j])
+                    if (j > last && j < best && G.key[W.soff + j] == k2 && may_collide(j))
+                        best = j;
+            }
+            if (best == 0x7fffffff)
+                break;
+            pair(best);
+            last = best;
+        }
+    }
+    A.contactF[s] = mk4<R>(acc.x, acc.y, acc.z, R(0));
+    if (hits)
+        atomicAdd(&W.collisionCount, hits);
 }
 
 } // namespace vx3b

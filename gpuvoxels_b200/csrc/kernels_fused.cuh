@@ -20,6 +20,7 @@
 // integrated by the time the world is stopped (the reference returns from doTimeStep before its voxel pass).
 #pragma once
 #include "engine.cuh"
+#include "kernels_contact.cuh"
 #include "kernels_stream.cuh"
 
 namespace vx3b {
@@ -65,12 +66,8 @@ template <class R> struct FusedLayout {
 };
 
 // src = buffer set holding the world's state at the start of the step (W.parity), dst = the other one
-template <class R> __global__ void __launch_bounds__(256, 2) k_fused(Arrays<R> A, FusedArrays FA, int capTab, int capOwn) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const BrickD B = FA.bricks[blockIdx.x];
-    WorldD &W = A.worlds[B.world];
-    if (!W.active || !(W.flags & WF_FUSED))
-        return;
+template <class R>
+__device__ __forceinline__ void fused_brick(const Arrays<R> &A, const FusedArrays &FA, int capTab, int capOwn, const ContactGrid &G, const BrickD &B, WorldD &W, unsigned char *smem) {
     const StateSet<R> src = cur_set(A, W.parity), dst = cur_set(A, W.parity ^ 1);
     const FusedLayout<R> L(capTab, capOwn);
     double *tPos = (double *)(smem + L.pos);
@@ -168,6 +165,13 @@ template <class R> __global__ void __launch_bounds__(256, 2) k_fused(Arrays<R> A
     // ---- phase 2: own voxels ---------------------------------------------------------------------------------------------------------
     const bool sampling = vx3 && W.cycle > 0 && ((W.step + 1) % W.cycle == 0);
     const uint8_t *mask = FA.linkMask + B.voxBeg;
+    const bool gridCheck = G.nBuckets > 0 && (wflags & WF_COLLISION) && W.gridLog2 > 0 && W.soff >= G.s0;
+    double refX = 0, refY = 0, refZ = 0;
+    if (gridCheck) {
+        const int vm = A.surf[W.soff + (W.ns >> 1)];
+        const D2 am = src.pxy[vm], bm = src.pzt[vm];
+        refX = am.x, refY = am.y, refZ = bm.x;
+    }
     for (int i = tid; i < B.nOwn; i += nt) {
         const int v = bvox[i];
         const DVoxMat &m = A.vmats[tMat[i]];
@@ -240,11 +244,27 @@ template <class R> __global__ void __launch_bounds__(256, 2) k_fused(Arrays<R> A
             dst.lm[v] = mk4<R>(s.linMom.x, s.linMom.y, s.linMom.z, s.angMom.x);
             dst.am[v] = mk2<R>(s.angMom.y, s.angMom.z);
         }
+        if (gridCheck) { // k_cgrid_check's job: stale candidate lists?  (reference voxel from the source set, which nobody writes)
+            const int slot = A.vsurf[v];
+            if (slot >= 0)
+                cgrid_check_one(W, G, slot, s.pos.x, s.pos.y, s.pos.z, refX, refY, refZ);
+        }
         if (sampling) {
             double mass = m.mass;
             world_accumulate(W.comAcc, B.world, m.isMeasured != 0, s.pos.x * mass, s.pos.y * mass, s.pos.z * mass, mass);
         }
     }
+}
+
+// G: the global contact grid (G.nBuckets == 0: none): the voxel pass also does k_cgrid_check's job.
+// (Folding k_world_step into the last CTA to finish, as k_brick does, was measured and dropped: with ~900 one-brick CTAs the
+// fence + ticket of every CTA and the serial tail cost 7 us per step more than the separate launch does.)
+template <class R> __global__ void __launch_bounds__(256, 2) k_fused(Arrays<R> A, FusedArrays FA, int capTab, int capOwn, ContactGrid G) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const BrickD B = FA.bricks[blockIdx.x];
+    WorldD &W = A.worlds[B.world];
+    if (W.active && (W.flags & WF_FUSED))
+        fused_brick<R>(A, FA, capTab, capOwn, G, B, W, smem);
 }
 
 // End of a run: worlds whose current state sits in the alternate buffers are copied back, so that outside vx3b_batch_run the

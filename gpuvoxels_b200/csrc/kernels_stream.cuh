@@ -122,15 +122,15 @@ template <class R> struct SurfRec {
     int32_t mat, v;
     short4 lat;
 };
-// gridMode: the grid broad phase (kernels_contact.cuh) runs before this kernel; only worlds it does not cover (no grid, or a
-// candidate list overflowed at this step's rebuild) are left to the all-pairs scan
+// gridMode: the grid broad phase (kernels_contact.cuh) runs before this kernel; only worlds it does not cover (no grid) are left to
+// the all-pairs scan
 template <class R> __global__ void __launch_bounds__(128) k_contact(Arrays<R> A, const ContactTile *tiles, int recordPairs, int gridMode) {
     __shared__ SurfRec<R> tile[128];
     const ContactTile ct = tiles[blockIdx.x];
     WorldD &W = A.worlds[ct.world];
     if (!W.active || !(W.flags & WF_COLLISION) || (W.flags & WF_RESIDENT))
         return;
-    if (gridMode && W.gridLog2 > 0 && !W.gOverflow)
+    if (gridMode && W.gridLog2 > 0)
         return;
     const int ns = W.ns, soff = W.soff;
     recordPairs = recordPairs && W.runSteps == 1; // parity tests read the pair set of the run's last step
@@ -482,18 +482,33 @@ template <class R, bool TARGETS = true> __device__ void world_end_of_step(const 
     }
 }
 
-template <class R> __global__ void k_world_step(Arrays<R> A, int useStop, int *activeCount) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= A.nWorlds)
+// Global contact grid (kernels_contact.cuh), end of a step, one thread per world (k_world_step, or the last CTA of k_fused): lists found stale are rebuilt at the next step, in a
+// new epoch - every bucket head of the old one reads as empty, so nothing has to be cleared.  The flags are read with atomics:
+// they were written by other CTAs of a kernel that may still be running on this SM's L1.
+VXD void cgrid_end_of_step(WorldD &W) {
+    if (!(W.flags & WF_COLLISION) || W.gridLog2 <= 0)
         return;
-    WorldD &W = A.worlds[w];
+    const int stale = atomicExch(&W.gRebuildNext, 0);
+    W.gRebuild = stale;
+    if (stale)
+        W.gEpoch++;
+}
+// k_world_step's work for one streaming world
+template <class R> VXD void stream_world_step(const Arrays<R> &A, WorldD &W, int useStop, int *activeCount) {
     if (!W.active || (W.flags & WF_RESIDENT))
         return;
     if (W.flags & (WF_FUSED | WF_BRICK))
         W.parity ^= 1; // k_fused / k_brick has just written the other buffer set
+    cgrid_end_of_step(W);
     world_end_of_step(A, W, useStop);
     if (W.active && activeCount)
         atomicAdd(activeCount, 1);
+}
+template <class R> __global__ void k_world_step(Arrays<R> A, int useStop, int *activeCount) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= A.nWorlds)
+        return;
+    stream_world_step<R>(A, A.worlds[w], useStop, activeCount);
 }
 
 static __global__ void k_zero_int(int *p) { *p = 0; }

@@ -422,12 +422,13 @@ def test_grid_broad_phase_equals_the_all_pairs_scan_bit_for_bit(path, precision)
     """Big worlds find their contacts through the global-memory uniform grid + candidate lists (kernels_contact.cuh) instead of
     the reference's all-pairs scan.  Candidates are visited in the all-pairs order and the predicate is the same, so forces -
     and with them the whole state - must be identical to the last bit, the watched pair set and the hit count too; also when
-    a fat skin overflows the lists (fallback to the all-pairs kernel) and over several runs (lists carried across runs)."""
+    a fat skin (or a list capacity of one) overflows the lists - such a voxel then takes its candidates straight from the grid, in
+    the same order - and over several runs (lists carried across runs)."""
     models = [gv.Model.from_vxa(W.contact_pile_vxa(k=3, cube=4)), gv.Model.from_vxa(W.xenobot_base_vxa(), W.xenobot_vxd(7)),
               gv.Model.from_vxa(W.contact_pile_vxa(k=2, cube=3, seed=3))]
-    for skin in (0.15, 2.5):
-        a = gpu_run(models, 260, precision, path, contact_grid=0, record_pairs=1, contact_skin=skin)
-        b = gpu_run(models, 260, precision, path, contact_grid=1, record_pairs=1, contact_skin=skin)
+    for skin, cap in ((0.15, 0), (2.5, 0), (0.5, 1)):
+        a = gpu_run(models, 260, precision, path, contact_grid=0, record_pairs=1, contact_skin=skin, contact_list_cap=cap)
+        b = gpu_run(models, 260, precision, path, contact_grid=1, record_pairs=1, contact_skin=skin, contact_list_cap=cap)
         for rounds in range(2):
             for i in range(len(models)):
                 sa, sb = a.read_state(i), b.read_state(i)
@@ -437,7 +438,7 @@ def test_grid_broad_phase_equals_the_all_pairs_scan_bit_for_bit(path, precision)
                 ra, rb = a.results()[i], b.results()[i]
                 assert ra.collision_count == rb.collision_count
                 if rounds == 0:
-                    assert rb.contact_rebuilds >= 1 and (rb.contact_overflows > 0) == (skin > 1)
+                    assert rb.contact_rebuilds >= 1 and (rb.contact_overflows > 0) == (skin > 0.2), (skin, cap, rb.contact_overflows)
             a.run(45)
             b.run(45)
         assert len(a.collision_pairs(0)) > 0  # the piles do touch
