@@ -340,9 +340,20 @@ template <class R> class Engine : public EngineBase {
                 const VX3B_WorldDesc &d = worlds[w];
                 Pre &p = pre[w];
                 deg.assign(d.num_voxels, 0);
+                // material indices index host vectors and device tables, and a link material's two voxel materials are packed into 16 bits
+                // each: refuse what is out of range here instead of reading past the tables
+                bool badMat = d.num_voxel_mats < 1 || d.num_voxel_mats > 65535 || d.num_link_mats < 0 || (d.num_links > 0 && d.num_link_mats < 1);
+                for (int v = 0; v < d.num_voxels && !badMat; v++)
+                    badMat = d.voxel_mat[v] < 0 || d.voxel_mat[v] >= d.num_voxel_mats;
+                for (int k = 0; k < d.num_link_mats && !badMat; k++)
+                    badMat = d.link_mats[k].mat1 < 0 || d.link_mats[k].mat1 >= d.num_voxel_mats || d.link_mats[k].mat2 < 0 || d.link_mats[k].mat2 >= d.num_voxel_mats;
+                if (badMat) {
+                    badWorld = w;
+                    return;
+                }
                 for (int l = 0; l < d.num_links; l++) {
                     int a = d.link_neg[l], b = d.link_pos[l];
-                    if (a < 0 || a >= d.num_voxels || b < 0 || b >= d.num_voxels || d.link_axis[l] > 2) {
+                    if (a < 0 || a >= d.num_voxels || b < 0 || b >= d.num_voxels || d.link_axis[l] > 2 || d.link_mat[l] < 0 || d.link_mat[l] >= d.num_link_mats) {
                         badWorld = w;
                         return;
                     }
@@ -416,7 +427,7 @@ template <class R> class Engine : public EngineBase {
             for (auto &th : pool)
                 th.join();
             if (badWorld >= 0) {
-                set_error("vx3b_batch_upload: a link of world " + std::to_string((int)badWorld) + " is malformed");
+                set_error("vx3b_batch_upload: a link of world " + std::to_string((int)badWorld) + " is malformed, or a voxel / link material index of it is out of range");
                 return VX3B_ERR_ARG;
             }
         }

@@ -446,6 +446,23 @@ def test_grid_broad_phase_equals_the_all_pairs_scan_bit_for_bit(path, precision)
         b.close()
 
 
+def test_upload_refuses_material_indices_out_of_range():
+    """the public C ABI takes raw arrays: a voxel or link material index outside the world's tables is an argument error, not a read
+    past the tables (VX3B_WorldDesc via ArrayModel)"""
+    m = gv.Model.from_vxa(W.small_block_vxa())
+    names = ("lattice", "voxel_mat", "link_neg", "link_pos", "link_axis", "link_mat")
+    good = {k: m.array(k) for k in names}
+    ctx = gv.Context(0, gv.FP64)
+    ctx.upload([gv.ArrayModel(m, good)])
+    for key, bad in (("voxel_mat", m.desc.num_voxel_mats), ("voxel_mat", -1), ("link_mat", m.desc.num_link_mats), ("link_mat", -3)):
+        arrays = dict(good)
+        arrays[key] = good[key].copy()
+        arrays[key][len(arrays[key]) // 2] = bad
+        with pytest.raises(gv.VX3Error, match="out of range"):
+            ctx.upload([gv.ArrayModel(m, arrays)])
+    ctx.close()
+
+
 def test_job_run_writes_the_reference_report_layout():
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "base.vxa"), "w").write(W.xenobot_base_vxa(stop_seconds=0.1).replace("<Simulator>", "<Simulator><SavePositionOfAllVoxels>1</SavePositionOfAllVoxels>", 1))
