@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--workloads", default="all", help="N = 1, default workload only: also measure these other BASELINE configs into a \"workloads\" block "
                     "(all | none | comma list of cube100,pile,xenobot_fp64)")
     ap.add_argument("--slab-cube", type=int, default=160, help="N > 1: edge of the ONE body also stepped as N slabs into a \"slab\" block (0 = skip)")
+    ap.add_argument("--gen-parts", type=int, default=6, help="e2e of a many-world generation: sub-batches of the pipelined runner vx3b_gen_run (1 = plain upload + run + results)")
     ap.add_argument("--slab-sim-steps", type=int, default=200)
     ap.add_argument("--slab-exchange", default="fused", choices=["fused", "device", "nccl"],
                     help="slab halo exchange: fused = the step kernel stores boundary voxels straight into the neighbour's IPC-mapped state arrays and raises its flag "
@@ -309,20 +310,28 @@ def measure(args, rank, world, local):
     # ---- end to end through the C ABI with host buffers: upload + run + results (+ report gather) ----------------------
     h2d = upload_bytes(models)
     d2h = len(models) * C.sizeof(_abi.WorldResult)
-    ctx2 = gv.Context(local, args.precision)
+    # a generation of many worlds goes through the pipelined runner (vx3b_gen_run: sub-batch k + 1 is staged and copied while sub-batch k
+    # already steps); one big world through the plain context calls
+    pipelined = len(models) >= 16 and args.gen_parts > 1
+    ctx2 = gv.Generation(local, args.precision, args.gen_parts) if pipelined else gv.Context(local, args.precision)
     ctx2.set_option("path", args.path)
     for o in args.opt:
         ctx2.set_option(o.split("=")[0], float(o.split("=")[1]))
     e2e_steps = max(1, min(args.steps, 3))
-    ctx2.upload(models)
-    ctx2.run(args.sim_steps)
+
+    def generation():
+        if pipelined:
+            return ctx2.run(models, args.sim_steps)
+        ctx2.upload(models)
+        ctx2.run(args.sim_steps)
+        return ctx2.results()
+
+    generation()
     barrier()
     t1 = time.perf_counter()
     e2e_vs = 0
     for _ in range(e2e_steps):
-        ctx2.upload(models)
-        ctx2.run(args.sim_steps)
-        res = ctx2.results()
+        res = generation()
         fit = torch.tensor([r.fitness_score for r in res], dtype=torch.float64, device="cuda")
         if world > 1:
             gathered = [torch.empty_like(fit) for _ in range(world)]
@@ -355,7 +364,7 @@ def measure(args, rank, world, local):
         if args.path == 2 or (args.path == 0 and args.workload == "xenobot"):
             kernel = "k_resident"  # one launch per size class steps every world through all sim_steps
         elif args.workload == "pile":
-            kernel = "k_fused"     # + k_cgrid_* (contact) + k_world_step: eight launches per time step
+            kernel = "k_fused"     # + k_cgrid_insert / k_cgrid_narrow (contact) + k_world_step: four launches per time step
         elif args.path in (0, 5):
             kernel = "k_brick"     # one launch per time step
         else:
@@ -386,7 +395,8 @@ def measure(args, rank, world, local):
                          "algorithmic_bytes_per_launch": bytes_per_sim_step * args.sim_steps,
                          "note": "algorithmic bytes = (112*Nv + 88*Nl) per time step (SURVEY.md 8d) x time steps per launch, rank 0's worlds"},
             "e2e": {"value": e2e_vs_all / e2e_wall_max, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "vx3b_batch_upload (host arrays -> HBM) + vx3b_batch_run + vx3b_batch_results (+ NCCL gather of fitness for N>1), wall clock"},
+                    "what": (f"vx3b_gen_run (host arrays -> HBM, run, results; {args.gen_parts} sub-batches, each stepping while the next is uploaded)" if pipelined
+                             else "vx3b_batch_upload (host arrays -> HBM) + vx3b_batch_run + vx3b_batch_results") + " (+ NCCL gather of fitness for N>1), wall clock"},
             "gpu_launches": int(launches_all), "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

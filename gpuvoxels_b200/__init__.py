@@ -411,6 +411,40 @@ class Context:
             pass
 
 
+class Generation:
+    """A generation of worlds on one device, pipelined over `parts` sub-batches (vx3b_gen_*): sub-batch k + 1 is staged and copied
+    while sub-batch k already steps.  run() returns the results in the order of `models`."""
+
+    def __init__(self, device=0, precision=FP32, parts=4):
+        self._h = C.c_void_p()
+        _check(lib().vx3b_gen_create(int(device), int(precision), int(parts), C.byref(self._h)), "vx3b_gen_create")
+
+    def set_option(self, name, value):
+        _check(lib().vx3b_gen_set_option(self._h, name.encode(), float(value)), "vx3b_gen_set_option")
+
+    def run(self, models, max_steps, use_stop_formula=False):
+        for m in models:
+            m.desc  # (finalizes a model that was not yet)
+        handles = (C.c_void_p * len(models))(*[m._h for m in models])
+        out = (WorldResult * len(models))()
+        _check(lib().vx3b_gen_run(self._h, handles, len(models), int(max_steps), 1 if use_stop_formula else 0, out), "vx3b_gen_run")
+        return list(out)
+
+    def total_voxel_steps(self):
+        return lib().vx3b_gen_total_voxel_steps(self._h)
+
+    def close(self):
+        if self._h:
+            lib().vx3b_gen_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SimulationManager:
     """Mirror of VX3_SimulationManager(sub_batches, base, input_dir, num_devices): start() is blocking and
     leaves h_results sorted by fitness descending, NaN last (VX3_SimulationResult.h:26-33)."""

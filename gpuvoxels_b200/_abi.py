@@ -148,6 +148,11 @@ SYMBOLS = {
     "vx3b_job_run_files": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int, C.c_int]),
     "vx3b_job_run_task": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]),
     "vx3b_job_history_files": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_int]),
+    "vx3b_gen_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "vx3b_gen_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
+    "vx3b_gen_run": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int64, C.c_int, C.POINTER(WorldResult)]),
+    "vx3b_gen_total_voxel_steps": (C.c_int64, [_P]),
+    "vx3b_gen_destroy": (None, [_P]),
     "vx3b_shard_worlds": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int32)]),
 }
 

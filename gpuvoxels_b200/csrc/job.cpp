@@ -169,6 +169,30 @@ static int job_run(const std::string &basePath, const std::string &dir, const st
                 if (ctx)
                     vx3b_ctx_destroy(ctx);
             };
+            // a generation of many worlds, none of which wants its voxel positions back: the pipelined runner (generation.cpp) steps the
+            // first sub-batches while the later ones are still being staged and copied
+            bool wantsPositions = false;
+            for (int i : sub[dev])
+                wantsPositions = wantsPositions || worlds[i].desc.save_position_of_all_voxels;
+            if (sub[dev].size() >= 64 && !wantsPositions) {
+                vx3b_gen *gen = nullptr;
+                int rc = vx3b_gen_create(dev, precision, 6, &gen);
+                if (rc != VX3B_OK)
+                    return fail(rc);
+                std::vector<const vx3b_model *> ms;
+                for (int i : sub[dev])
+                    ms.push_back(worlds[i].model);
+                std::vector<VX3B_WorldResult> res(ms.size());
+                rc = vx3b_gen_run(gen, ms.data(), (int)ms.size(), 1000000, 1, res.data());
+                if (rc != VX3B_OK) {
+                    status[dev] = rc;
+                    errors[dev] = vx3b_last_error();
+                } else
+                    for (size_t k = 0; k < sub[dev].size(); k++)
+                        worlds[sub[dev][k]].res = res[k];
+                vx3b_gen_destroy(gen);
+                return;
+            }
             int rc = vx3b_ctx_create(dev, precision, &ctx);
             if (rc != VX3B_OK)
                 return fail(rc);

@@ -345,6 +345,19 @@ int vx3b_job_run_task(const char *vxt_path, const char *report_path, int num_dev
 int vx3b_job_history(const char *input_dir, const char *out_path, int precision);
 int vx3b_job_history_files(const char *base_vxa_path, const char *input_dir, const char *const *vxd_files, int num_files, const char *out_path,
                            int precision);
+/* ---------------------------------------------------------------- 3b. a generation on one device, pipelined ----
+ * What VX3_SimulationManager::start does for ONE device - readVXD, startKernel, collectResults, one after the other
+ * (VX3_SimulationManager.cu:138-155, 277-458) - as a software pipeline: the worlds are dealt (by cost) to `parts` sub-batches, each with
+ * its own context, stream and host thread; the sub-batches are uploaded one after the other and each starts stepping the moment it is
+ * resident, so the GPU works while the rest of the generation is still being staged and copied.  results [n] come back in input order.
+ * Contexts (and their device memory) are kept between calls: a generation after a generation allocates nothing. */
+typedef struct vx3b_gen vx3b_gen;
+int vx3b_gen_create(int device, int precision, int parts, vx3b_gen **out);
+int vx3b_gen_set_option(vx3b_gen *gen, const char *name, double value); /* vx3b_ctx_set_option on every sub-batch */
+int vx3b_gen_run(vx3b_gen *gen, const vx3b_model *const *models, int n, int64_t max_steps, int use_stop_formula, VX3B_WorldResult *results);
+int64_t vx3b_gen_total_voxel_steps(vx3b_gen *gen); /* of the last vx3b_gen_run */
+void vx3b_gen_destroy(vx3b_gen *gen);
+
 /* Host-only: assign n worlds of the given cost to num_shards devices / ranks, longest-processing-time-first (the reference
  * deals files round-robin, vx3_node_worker.cu:88-93).  Deterministic, so every rank of a multi-process job agrees. */
 int vx3b_shard_worlds(const int64_t *cost, int n, int num_shards, int32_t *shard_of);

@@ -446,6 +446,53 @@ def test_grid_broad_phase_equals_the_all_pairs_scan_bit_for_bit(path, precision)
         b.close()
 
 
+def test_pipelined_generation_equals_the_plain_batch():
+    """vx3b_gen_run (sub-batches staged while earlier ones already step) returns, in input order, what one context returns for the
+    same worlds - worlds are independent - also on a second call (contexts are reused) and with more sub-batches than worlds"""
+    models = [gv.Model.from_vxa(W.xenobot_base_vxa(stop_seconds=0.05), W.xenobot_vxd(40 + i)) for i in range(13)]
+    ctx = gv.Context(0, gv.FP32)
+    ctx.upload(models)
+    ctx.run(1000000, True)
+    want = ctx.results()
+    for parts, subset in ((3, models), (4, models[:2]), (1, models)):
+        gen = gv.Generation(0, gv.FP32, parts)
+        for _ in range(2):
+            got = gen.run(subset, 1000000, True)
+            assert len(got) == len(subset)
+            for a, b in zip(got, want):  # (the centre-of-mass sums are atomics: their last bits depend on the batch a world is part of)
+                assert (a.steps, a.current_time, a.num_voxel, a.stopped, a.diverged, a.collision_count) == (b.steps, b.current_time, b.num_voxel, b.stopped, b.diverged, b.collision_count)
+                assert abs(a.fitness_score - b.fitness_score) <= 1e-9 * abs(b.fitness_score)
+                assert np.allclose(a.current_com, b.current_com, rtol=1e-12, atol=0)
+            assert gen.total_voxel_steps() == sum(r.steps * m.num_voxels for r, m in zip(got, subset))
+        gen.close()
+    ctx.close()
+
+
+def test_job_run_of_a_big_generation_goes_through_the_pipelined_runner():
+    """vx3b_job_run hands a directory of 64+ worlds (none asking for voxel positions) to vx3b_gen_run: the report must hold what a plain
+    context computes for the same files"""
+    n = 70
+    with tempfile.TemporaryDirectory() as td:
+        base = W.xenobot_base_vxa(stop_seconds=0.03)
+        open(os.path.join(td, "base.vxa"), "w").write(base)
+        for i in range(n):
+            open(os.path.join(td, f"bot_{i:04d}.vxd"), "w").write(W.xenobot_vxd(200 + i))
+        out = os.path.join(td, "report.xml")
+        rc = gv.lib().vx3b_job_run(td.encode(), out.encode(), 1, gv.FP32)
+        assert rc == 0, gv.lib().vx3b_last_error()
+        detail = {d.tag: d for d in ET.parse(out).getroot().find("detail")}
+    assert len(detail) == n
+    models = [gv.Model.from_vxa(base, W.xenobot_vxd(200 + i)) for i in range(n)]
+    ctx = gv.Context(0, gv.FP32)
+    ctx.upload(models)
+    ctx.run(1000000, True)
+    for i, r in enumerate(ctx.results()):
+        d = detail[f"bot_{i:04d}"]
+        assert float(d.find("currentTime").text) == r.current_time
+        assert abs(float(d.find("fitness_score").text) - r.fitness_score) <= 1e-9 * abs(r.fitness_score)
+    ctx.close()
+
+
 def test_upload_refuses_material_indices_out_of_range():
     """the public C ABI takes raw arrays: a voxel or link material index outside the world's tables is an argument error, not a read
     past the tables (VX3B_WorldDesc via ArrayModel)"""
