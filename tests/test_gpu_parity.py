@@ -493,6 +493,32 @@ def test_job_run_of_a_big_generation_goes_through_the_pipelined_runner():
     ctx.close()
 
 
+def test_job_run_over_two_devices_equals_one_device():
+    """vx3b_job_run(num_devices = 2): worlds dealt over two GPUs (one host thread + context per device, csrc/job.cpp) give the report one
+    GPU gives - what bin/vx3_node_worker does on a multi-GPU box.  Needs two devices (skipped on the single-GPU test box; run with
+    `gpurun --gpus 2`, log in profiles/r02r_two_device_job.log)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "base.vxa"), "w").write(W.xenobot_base_vxa(stop_seconds=0.05).replace("<Simulator>", "<Simulator><SavePositionOfAllVoxels>1</SavePositionOfAllVoxels>", 1))
+        for i in range(9):
+            open(os.path.join(td, f"bot_{i:04d}.vxd"), "w").write(W.xenobot_vxd(300 + i))
+        reports = []
+        for nd in (1, 2):
+            out = os.path.join(td, f"report{nd}.xml")
+            rc = gv.lib().vx3b_job_run(td.encode(), out.encode(), nd, gv.FP32)
+            assert rc == 0, gv.lib().vx3b_last_error()
+            reports.append({d.tag: d for d in ET.parse(out).getroot().find("detail")})
+    assert sorted(reports[0]) == sorted(reports[1]) and len(reports[0]) == 9
+    for name, a in reports[0].items():
+        b = reports[1][name]
+        assert a.find("currentTime").text == b.find("currentTime").text
+        fa, fb = float(a.find("fitness_score").text), float(b.find("fitness_score").text)
+        assert abs(fa - fb) <= 1e-9 * abs(fa)
+        assert a.find("voxelPositions") is None or len(a.find("voxelPositions").text or "") == len(b.find("voxelPositions").text or "")
+
+
 def test_upload_refuses_material_indices_out_of_range():
     """the public C ABI takes raw arrays: a voxel or link material index outside the world's tables is an argument error, not a read
     past the tables (VX3B_WorldDesc via ArrayModel)"""
