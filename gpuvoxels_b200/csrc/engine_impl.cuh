@@ -1559,7 +1559,7 @@ template <class R> class Engine : public EngineBase {
             const int perSm = std::max(1, std::min(2, (int)((size_t)smemPerSm / (brickSmem + 1024))));
             brickGrid = std::min(BA.nBricks, perSm * numSm);
             BA.chunk = std::max(1, std::min((int)BRICK_CHUNK, (BA.nBricks + brickGrid - 1) / brickGrid));
-            brickThreads = perSm == 1 ? 512 : 256;
+            brickThreads = perSm == 1 ? BRICK_MAXT : 256;
             if (getenv("VX3B_DEBUG"))
                 fprintf(stderr, "[vx3b] brick path: %zu bricks (%dx%dx%d), own <= %d, halo <= %d, owned links <= %d, recomputed links <= %d (%.1f%%), %zu B shared memory, grid %d x %d threads x chunk %d, %s\n",
                         bh.bricks.size(), brickDimsUsed[0], brickDimsUsed[1], brickDimsUsed[2], brickCaps.own, brickCaps.halo, brickCaps.owned, brickCaps.haloL,

@@ -44,6 +44,9 @@ struct alignas(8) LinkDesc {
     uint16_t a, b, lmat, flags; // lmat: world-local link material; flags: bits 0-1 axis, BD_NEG_OWN, BD_POS_OWN, bits 4-7 / 8-11 world-local voxel material of a / b
 };
 enum { BD_NEG_OWN = 4, BD_POS_OWN = 8 };
+#ifndef BRICK_MAXT
+#define BRICK_MAXT 512 // threads of a k_brick CTA (one CTA per SM); -DBRICK_MAXT=768 for experiments: 85 registers per thread
+#endif
 enum { BRICK_MAX_VMATS = 16, BRICK_MAX_LMATS = 48, BRICK_CHUNK = 64, BRICK_FSTRIDE = 37 };
 
 // One brick-ordered buffer set.  Unlike the API-order StateSet the angular momentum has its own 16-byte array (am = angMom.xyz, 0;
@@ -233,7 +236,7 @@ template <class R> __device__ __noinline__ void brick_world_step(WorldD *worlds,
 }
 
 template <class R, bool LEAN, bool PEER = false>
-__global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L, int worldStep, int useStop, int *activeCount, const BrickPeer<R> P = BrickPeer<R>{}) {
+__global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L, int worldStep, int useStop, int *activeCount, const BrickPeer<R> P = BrickPeer<R>{}) {
     using T4 = typename Store<R>::T4;
     using T2 = typename Store<R>::T2;
     extern __shared__ __align__(128) unsigned char smem_brick[];
@@ -285,7 +288,8 @@ __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA
     // Fill stage `s` with brick B: bulk copies of its runs (+ the gather list of the brick after it, `next`, into its list slot)
     // on the stage's mbarrier by thread 0, halo gathers by everybody.  idx: the brick's gather list (shared or global memory).
     // ft / fnt: this thread's rank among, and the number of, the threads that take part.
-    auto fill = [&](const BrickB &B, int s, const int32_t *idx, bool idxShared, const BrickB *next, int nextSlot, int ft, int fnt) {
+    // what: 3 = everything, 1 = the bulk copies only (one thread: ft == 0), 2 = the halo gathers only
+    auto fill = [&](const BrickB &B, int s, const int32_t *idx, bool idxShared, const BrickB *next, int nextSlot, int ft, int fnt, int what) {
         const uint32_t idxS = idxShared ? smem_u32(idx) : 0u;
         auto index = [&](int i) -> int {
             if (idxShared) {
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA
         };
         unsigned char *st = smem + L.stage0 + (uint32_t)s * L.stageBytes;
         const int nOwnPad = (B.nOwn + 1) & ~1;
-        if (ft == 0) {
+        if (ft == 0 && (what & 1)) {
             const uint32_t bar = bar0 + 8 * s;
             const uint32_t bV16 = (uint32_t)nOwnPad * 16u, bV4 = (uint32_t)nOwnPad * (uint32_t)sizeof(T4);
             const uint32_t bL = (uint32_t)B.nOwned * (uint32_t)sizeof(T4), bD = (uint32_t)((B.nHaloL + B.nOwned + 1) & ~1) * (uint32_t)sizeof(LinkDesc);
@@ -323,6 +327,8 @@ __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA
             if (bG)
                 bulk_g2s(smem_u32(smem + L.glist0 + (uint32_t)nextSlot * L.glistBytes), BA.glist + next->gBeg, bG, bar);
         }
+        if (!(what & 2))
+            return;
         const uint32_t dPxy = smem_u32(st + L.pxy) + (uint32_t)nOwnPad * 16u, dPzt = smem_u32(st + L.pzt) + (uint32_t)nOwnPad * 16u;
         const uint32_t dOri = smem_u32(st + L.ori) + (uint32_t)nOwnPad * (uint32_t)sizeof(T4);
 #pragma unroll 1
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA
             }
             const bool haveNext = k + 1 < cnt && sHdr[k + 1].world == curWorld;
             if (!filled) { // first brick of a round / of a world: nothing was prefetched, indices come from global memory
-                fill(B, s, BA.glist + B.gBeg, false, haveNext ? &sHdr[k + 1] : nullptr, (k + 1) & 1, tid, nt);
+                fill(B, s, BA.glist + B.gBeg, false, haveNext ? &sHdr[k + 1] : nullptr, (k + 1) & 1, tid, nt, 3);
                 gather_wait_all();
                 __syncthreads();
             }
@@ -427,6 +433,13 @@ __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA
             const int myVox = rotRole ? tid - half : tid;
             const uint32_t *sStat = (const uint32_t *)(st + L.stat);
 
+            // The bulk copies of brick k+1 (the bytes: its own runs, link history, descriptors, static words, and brick k+2's gather list)
+            // start NOW, a whole brick ahead - one thread, a dozen instructions; the other stage's last readers passed the barrier that
+            // ended brick k-1.  Its halo gathers (hundreds of instructions) still wait for the end of the link pass, below.
+            if (haveNext && tid == nt - 128) {
+                const bool haveNext2 = k + 2 < cnt && sHdr[k + 2].world == curWorld;
+                fill(sHdr[k + 1], s ^ 1, nullptr, true, haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, 0, 128, 1);
+            }
             // ---- phase 1: links (recomputed ones first, then the owned run) ---------------------------------------------------
             bool diverged = false;
 #pragma unroll 1
@@ -490,7 +503,7 @@ __global__ void __launch_bounds__(512, 1) k_brick(Arrays<R> A, BrickArrays<R> BA
             // still have link work.)
             if (haveNext && tid >= nt - 128) {
                 const bool haveNext2 = k + 2 < cnt && sHdr[k + 2].world == curWorld;
-                fill(sHdr[k + 1], s ^ 1, (const int32_t *)(smem + L.glist0 + (uint32_t)((k + 1) & 1) * L.glistBytes), true, haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, tid - (nt - 128), 128);
+                fill(sHdr[k + 1], s ^ 1, (const int32_t *)(smem + L.glist0 + (uint32_t)((k + 1) & 1) * L.glistBytes), true, haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, tid - (nt - 128), 128, 2);
             }
             __syncthreads();
 
