@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArray
             // Prefetch brick k+1 into the other stage (its last readers passed the barrier that ended brick k-1).  The last four warps
             // do it, after their links: they hold the highest link numbers, so they are the ones with an iteration to spare.
             // (Issuing it before the links instead costs 20 % - measured, profiles/r01m: it takes issue slots while all 16 warps
-            // still have link work.)
+            // still have link work.  Round 2 re-measured it with the gathers spread over ALL threads at the start of the link pass: 166 us
+            // per step against 156.)
             if (haveNext && tid >= nt - 128) {
                 const bool haveNext2 = k + 2 < cnt && sHdr[k + 2].world == curWorld;
                 fill(sHdr[k + 1], s ^ 1, (const int32_t *)(smem + L.glist0 + (uint32_t)((k + 1) & 1) * L.glistBytes), true, haveNext2 ? &sHdr[k + 2] : nullptr, k & 1, tid - (nt - 128), 128, 2);
