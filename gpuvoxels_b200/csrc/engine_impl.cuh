@@ -1314,8 +1314,10 @@ template <class R> class Engine : public EngineBase {
             std::vector<int32_t> local(nvTot, -1);
             fusedCapTab = fusedCapOwn = 0;
             fusedBrick0 = -1;
-            const int BX = brickDim[0], BY = brickDim[1], BZ = brickDim[2];
+            const int BX = brickDim[0], BY = brickDim[1], BZ0 = brickDim[2];
+            int fusedBZ = BZ0; // (for the debug line: the last world's)
             for (int oi = 0; oi < n; oi++) {
+                int BZ = BZ0;
                 const int w = perm[oi];
                 const bool streamingOnly = pre[w].cls == 0;
                 if (!streamingOnly && !fusedAllWorlds)
@@ -1351,7 +1353,7 @@ template <class R> class Engine : public EngineBase {
                         rank[r] = nComp++;
                     comp[v] = r;
                 }
-                auto count_bricks = [&](bool perBody, std::vector<int> &mnOut, int ext[3]) -> int64_t {
+                auto count_bricks = [&](bool perBody, std::vector<int> &mnOut, int ext[3], int BZ) -> int64_t {
                     const int nc = perBody ? nComp : 1;
                     mnOut.assign((size_t)nc * 3, 1 << 30);
                     std::vector<int> mxs((size_t)nc * 3, -(1 << 30));
@@ -1379,8 +1381,23 @@ template <class R> class Engine : public EngineBase {
                 };
                 std::vector<int> mnWorld, mnBody;
                 int extWorld[3], extBody[3];
-                const int64_t cellsWorld = count_bricks(false, mnWorld, extWorld);
-                const int64_t cellsBody = nComp > 1 ? count_bricks(true, mnBody, extBody) : cellsWorld;
+                const int64_t cellsWorld = count_bricks(false, mnWorld, extWorld, BZ);
+                int64_t cellsBody = nComp > 1 ? count_bricks(true, mnBody, extBody, BZ) : cellsWorld;
+                // bodies that fit ONE brick of twice the height (the pile's 8^3 cubes in 8x8x8 bricks): no link is cut by a brick face, so
+                // nothing is recomputed and nothing gathered; 2.72e9 -> 2.93e9 voxel-steps/s on the pile
+                if (nComp > 1 && BX * BY * BZ * 2 <= 512) {
+                    std::vector<int> mn2;
+                    int ext2[3];
+                    const int64_t cells2 = count_bricks(true, mn2, ext2, 2 * BZ);
+                    if (cells2 == nComp && cellsBody > nComp) {
+                        BZ = 2 * BZ;
+                        cellsBody = cells2;
+                        mnBody = mn2;
+                        for (int k = 0; k < 3; k++)
+                            extBody[k] = ext2[k];
+                    }
+                }
+                fusedBZ = BZ;
                 const bool perBody = nComp > 1 && cellsBody * 5 < cellsWorld * 4 && (int64_t)nComp * extBody[0] * extBody[1] * extBody[2] <= (int64_t)8 * h.nv + 4096;
                 const std::vector<int> &mnUse = perBody ? mnBody : mnWorld;
                 const int64_t nbx = perBody ? extBody[0] : extWorld[0], nby = perBody ? extBody[1] : extWorld[1], nbz = perBody ? extBody[2] : extWorld[2];
@@ -1498,7 +1515,7 @@ template <class R> class Engine : public EngineBase {
                 CUDA_TRY(cudaFuncSetAttribute(k_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin)); // the limit is per function, not per context: never lower it
                 if (getenv("VX3B_DEBUG"))
                     fprintf(stderr, "[vx3b] fused path: %zu bricks (%dx%dx%d), table <= %d voxels, own <= %d, %zu links incl. %.1f%% recomputed, %zu B shared memory\n",
-                            bricks.size(), BX, BY, BZ, fusedCapTab, fusedCapOwn, blinks.size(), 100.0 * (blinks.size() - (double)nlTot) / std::max<size_t>(nlTot, 1), fusedSmem);
+                            bricks.size(), BX, BY, fusedBZ, fusedCapTab, fusedCapOwn, blinks.size(), 100.0 * (blinks.size() - (double)nlTot) / std::max<size_t>(nlTot, 1), fusedSmem);
             }
         }
         lap("fused tables");
