@@ -273,6 +273,571 @@ template <class R> class Engine : public EngineBase {
         return VX3B_OK;
     }
 
+    // per-world summary of upload()'s pre-pass: surface count, feature flags, shared-memory need -> k_resident size class
+    struct Pre {
+        int ns = 0, cls = 0, next = 0; // surface voxels, k_resident size class, voxels with boundary conditions
+        bool full = false;             // needs k_resident's FULL instantiation (boundary conditions, force field, failure strain)
+        uint32_t flags = 0;
+        size_t bytes = 0;
+        double invCell = 0, listR2 = 0;
+        float skinHalf2 = 0;
+        bool spill = false;
+    };
+
+    // ---- k_brick plan (host only; kernels_brick.cuh): which worlds take the brick path, their voxels and links in brick order, the
+    // per-brick descriptor / gather tables, and the brick size that fits the shared memory.  Part of upload(); reads the staging arrays
+    // upload() has filled, marks the chosen worlds in hW[].brickOk.
+    int build_brick_plan(const VX3B_WorldDesc *worlds, int n, const std::vector<int> &perm, const std::vector<Pre> &pre, std::vector<WorldD> &hW,
+                         const std::vector<DVoxMat> &vmats, size_t nvTot, int smemOptin, bool anyGhost, BrickHost &bh) {
+        const auto &lat = staging.lat;
+        const auto &lends = staging.lends;
+        const auto &lmeta = staging.lmeta;
+        const auto &vlinks = staging.vlinks;
+        const auto &vmat = staging.vmat;
+        const auto &vext = staging.vext;
+        const auto &vghost = staging.vghost;
+        {
+            std::vector<int> bw; // brick worlds in layout order
+            for (int oi = 0; oi < n; oi++) {
+                const int w = perm[oi];
+                const VX3B_WorldDesc &d = worlds[w];
+                const bool wanted = path == 5 || (path == 0 && pre[w].cls == 0);
+                if (!wanted || d.num_voxels == 0 || (pre[w].flags & (WF_COLLISION | WF_FORCE_FIELD)) || d.max_dist_in_voxel_lengths_to_count_as_pair != 0 ||
+                    d.num_voxel_mats > BRICK_MAX_VMATS || d.num_link_mats > BRICK_MAX_LMATS)
+                    continue;
+                bw.push_back(w);
+            }
+            int dims[3] = {brickDim[0], brickDim[1], brickDim[2]};
+            // one persistent CTA (512 threads, two-stage ring) may take the whole SM; small bricks leave room for two (256 threads each)
+            const size_t limit = (size_t)smemOptin;
+            while (!bw.empty()) {
+                bh = BrickHost{};
+                BrickCaps caps{0, 0, 0, 0, 1, 1};
+                bool ok = true;
+                std::vector<int32_t> slotOf, lslotOf, brickOf, local;
+                for (int w : bw) {
+                    const WorldHost &h = H[w];
+                    const WorldD &W = hW[w];
+                    caps.nvm = std::max(caps.nvm, W.nvm);
+                    caps.nlm = std::max(caps.nlm, W.nlm);
+                    int mn[3] = {1 << 30, 1 << 30, 1 << 30};
+                    for (int v = 0; v < h.nv; v++)
+                        for (int k = 0; k < 3; k++)
+                            mn[k] = std::min(mn[k], (int)(&lat[h.voff + v].x)[k]);
+                    int mx[2] = {-(1 << 30), -(1 << 30)};
+                    for (int v = 0; v < h.nv; v++)
+                        for (int k = 0; k < 2; k++)
+                            mx[k] = std::max(mx[k], (int)(&lat[h.voff + v].x)[k]);
+                    const int64_t nbx = (mx[0] - mn[0]) / dims[0] + 1, nby = (mx[1] - mn[1]) / dims[1] + 1;
+                    std::vector<std::pair<int64_t, int>> keyed(h.nv); // (brick key, voxel): creation order inside a brick = x fastest
+                    int mxz = -(1 << 30);
+                    for (int v = 0; v < h.nv; v++)
+                        mxz = std::max(mxz, (int)lat[h.voff + v].z);
+                    const int64_t nbz = (mxz - mn[2]) / dims[2] + 1, nCells = nbx * nby * nbz;
+                    auto key_of = [&](int v) {
+                        const short4 c = lat[h.voff + v];
+                        return (((int64_t)(c.z - mn[2]) / dims[2]) * nby + (c.y - mn[1]) / dims[1]) * nbx + (c.x - mn[0]) / dims[0];
+                    };
+                    if (nCells <= (int64_t)4 * h.nv + 4096) {
+                        // counting sort by brick: stable, so voxels keep their creation order (ascending index) inside a brick, which is
+                        // what sorting the (key, index) pairs gives - at a tenth of the time on a million-voxel body
+                        std::vector<int32_t> start((size_t)nCells + 1, 0);
+                        for (int v = 0; v < h.nv; v++)
+                            start[(size_t)key_of(v) + 1]++;
+                        for (int64_t c = 0; c < nCells; c++)
+                            start[(size_t)c + 1] += start[(size_t)c];
+                        for (int v = 0; v < h.nv; v++) {
+                            const int64_t k = key_of(v);
+                            keyed[(size_t)start[(size_t)k]++] = {k, v};
+                        }
+                    } else { // a sparse world on a huge lattice: sort the pairs
+                        for (int v = 0; v < h.nv; v++)
+                            keyed[v] = {key_of(v), v};
+                        std::sort(keyed.begin(), keyed.end());
+                    }
+                    slotOf.assign(h.nv, -1);
+                    lslotOf.assign(h.nl, -1);
+                    brickOf.assign(h.nv, -1);
+                    local.assign(h.nv, -1);
+                    const size_t firstBrick = bh.bricks.size();
+                    bh.borig.reserve(bh.borig.size() + (size_t)h.nv + (size_t)h.nv / 16 + 64);
+                    bh.bstat.reserve(bh.bstat.size() + (size_t)h.nv + (size_t)h.nv / 16 + 64);
+                    bh.lorig.reserve(bh.lorig.size() + (size_t)h.nl);
+                    bh.ldesc.reserve(bh.ldesc.size() + (size_t)h.nl + (size_t)h.nl / 4 + 64);
+                    // pass 1: brick-order slots of voxels and owned links.  Brick extents in `keyed` first, then (host threads side by
+                    // side over bricks) the number of links every brick owns, a serial prefix sum for the slot offsets, and the fill.
+                    std::vector<size_t> bBeg; // index into keyed of every brick's first voxel (+ end sentinel)
+                    for (size_t a = 0; a < keyed.size();) {
+                        bBeg.push_back(a);
+                        const int64_t key = keyed[a].first;
+                        while (a < keyed.size() && keyed[a].first == key)
+                            a++;
+                    }
+                    bBeg.push_back(keyed.size());
+                    const size_t nNew = bBeg.size() - 1;
+                    const int nT1 = nNew >= 256 ? std::max(1, std::min((int)std::thread::hardware_concurrency(), 16)) : 1;
+                    auto over_bricks = [&](auto &&fn) { // fn(first brick, last brick) on nT1 threads
+                        if (nT1 == 1) {
+                            fn((size_t)0, nNew);
+                            return;
+                        }
+                        std::vector<std::thread> pool;
+                        for (int t = 1; t < nT1; t++)
+                            pool.emplace_back([&, t] { fn(nNew * (size_t)t / nT1, nNew * (size_t)(t + 1) / nT1); });
+                        fn((size_t)0, nNew / nT1);
+                        for (auto &th : pool)
+                            th.join();
+                    };
+                    std::vector<int32_t> nOwnedOf(nNew, 0);
+                    over_bricks([&](size_t k0, size_t k1) {
+                        for (size_t k = k0; k < k1; k++) {
+                            int cnt = 0;
+                            for (size_t q = bBeg[k]; q < bBeg[k + 1]; q++)
+                                for (int axis = 0; axis < 3; axis++)
+                                    cnt += vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + keyed[q].second] >= 0;
+                            nOwnedOf[k] = cnt;
+                        }
+                    });
+                    {
+                        size_t vAt = bh.borig.size(), lAt = bh.lorig.size();
+                        for (size_t k = 0; k < nNew; k++) {
+                            vAt = (vAt + 3) & ~(size_t)3; // own runs start on a multiple of four slots: every array, down to the 4-byte
+                            BrickB B;                     // static words, is then 16-byte aligned for the bulk copies
+                            memset(&B, 0, sizeof(B));
+                            B.world = w;
+                            B.v0 = (int)vAt;
+                            B.nOwn = (int)(bBeg[k + 1] - bBeg[k]);
+                            B.l0 = (int)lAt;
+                            B.nOwned = nOwnedOf[k];
+                            bh.bricks.push_back(B);
+                            vAt += (size_t)B.nOwn;
+                            lAt += (size_t)B.nOwned;
+                        }
+                        bh.borig.resize(vAt, -1); // (padding slots keep -1 / 0)
+                        bh.bstat.resize(vAt, 0);
+                        bh.lorig.resize(lAt);
+                    }
+                    std::atomic<bool> anyExtVoxel{false};
+                    over_bricks([&](size_t k0, size_t k1) {
+                        for (size_t k = k0; k < k1; k++) {
+                            const BrickB &B = bh.bricks[firstBrick + k];
+                            const size_t a = bBeg[k], b = bBeg[k + 1];
+                            size_t slot = (size_t)B.v0;
+                            for (size_t q = a; q < b; q++, slot++) {
+                                const int v = keyed[q].second, g = h.voff + v;
+                                slotOf[v] = (int)slot;
+                                brickOf[v] = (int)(firstBrick + k);
+                                uint32_t mk = 0;
+                                for (int dir = 0; dir < 6; dir++)
+                                    if (vlinks[(size_t)dir * nvTot + g] >= 0)
+                                        mk |= 1u << dir;
+                                bh.borig[slot] = g;
+                                bh.bstat[slot] = (uint32_t)(vmat[g] - W.vmatOff) | (mk << 8) | (vext[g] >= 0 ? 1u << 14 : 0u) | (vghost[g] ? 1u << 15 : 0u);
+                                if (vext[g] >= 0)
+                                    anyExtVoxel = true;
+                            }
+                            size_t ls = (size_t)B.l0;
+                            for (int axis = 0; axis < 3; axis++)
+                                for (size_t q = a; q < b; q++) {
+                                    const int l = vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + keyed[q].second];
+                                    if (l >= 0) {
+                                        lslotOf[l - h.loff] = (int)ls;
+                                        bh.lorig[ls++] = l;
+                                    }
+                                }
+                        }
+                    });
+                    if (anyExtVoxel)
+                        brickLean = false;
+                    // pass 2: link descriptors (recomputed links first, then the owned run in slot order) and halo tables.  Bricks are
+                    // independent here, so host threads build them side by side into per-brick pieces (each thread with its own
+                    // voxel -> brick-local index scratch); the pieces are appended in brick order afterwards.
+                    struct Piece {
+                        std::vector<LinkDesc> desc;
+                        std::vector<int32_t> glist; // halo voxel slots, then recomputed-link slots
+                        int nHalo = 0, nHaloL = 0;
+                    };
+                    const size_t nb = bh.bricks.size() - firstBrick;
+                    std::vector<Piece> pieces(nb);
+                    std::vector<size_t> firstVox(nb + 1, 0); // index into keyed of every brick's first own voxel
+                    for (size_t k = 0; k < nb; k++)
+                        firstVox[k + 1] = firstVox[k] + (size_t)bh.bricks[firstBrick + k].nOwn;
+                    auto build = [&](size_t k0, size_t k1, std::vector<int32_t> &loc) {
+                        std::vector<int> halo; // world-local voxel index
+                        for (size_t k = k0; k < k1; k++) {
+                            const size_t bi = firstBrick + k, a = firstVox[k];
+                            const BrickB &B = bh.bricks[bi];
+                            Piece &P = pieces[k];
+                            const int nOwnPad = (B.nOwn + 1) & ~1;
+                            halo.clear();
+                            for (int i = 0; i < B.nOwn; i++)
+                                loc[keyed[a + i].second] = i;
+                            auto local_of = [&](int v) {
+                                if (loc[v] < 0) {
+                                    loc[v] = nOwnPad + (int)halo.size();
+                                    halo.push_back(v);
+                                }
+                                return loc[v];
+                            };
+                            auto mat_of = [&](int v) { return (uint32_t)(vmat[h.voff + v] - W.vmatOff); };
+                            std::vector<int32_t> haloLinks;
+                            P.desc.reserve((size_t)B.nOwned + (size_t)B.nOwned / 4 + 8);
+                            for (int axis = 0; axis < 3; axis++)
+                                for (int i = 0; i < B.nOwn; i++) {
+                                    const int v = keyed[a + i].second;
+                                    const int l = vlinks[(size_t)(2 * axis) * nvTot + h.voff + v]; // v is the negative end
+                                    if (l < 0)
+                                        continue;
+                                    const int pos = lends[l].y - h.voff;
+                                    if (brickOf[pos] == (int)bi)
+                                        continue; // owned by this brick
+                                    LinkDesc d;
+                                    d.a = (uint16_t)i;
+                                    d.b = (uint16_t)local_of(pos);
+                                    d.lmat = (uint16_t)((lmeta[l] >> 2) - (uint32_t)W.lmatOff);
+                                    d.flags = (uint16_t)(axis | BD_NEG_OWN | (mat_of(v) << 4) | (mat_of(pos) << 8));
+                                    P.desc.push_back(d);
+                                    haloLinks.push_back(lslotOf[l - h.loff]);
+                                }
+                            P.nHaloL = (int)haloLinks.size();
+                            for (int axis = 0; axis < 3; axis++)
+                                for (int i = 0; i < B.nOwn; i++) {
+                                    const int v = keyed[a + i].second;
+                                    const int l = vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + v]; // v is the positive end: owned
+                                    if (l < 0)
+                                        continue;
+                                    const int neg = lends[l].x - h.voff;
+                                    LinkDesc d;
+                                    d.a = (uint16_t)local_of(neg);
+                                    d.b = (uint16_t)i;
+                                    d.lmat = (uint16_t)((lmeta[l] >> 2) - (uint32_t)W.lmatOff);
+                                    d.flags = (uint16_t)(axis | BD_POS_OWN | (brickOf[neg] == (int)bi ? BD_NEG_OWN : 0) | (mat_of(neg) << 4) | (mat_of(v) << 8));
+                                    P.desc.push_back(d);
+                                }
+                            P.nHalo = (int)halo.size();
+                            P.glist.reserve(halo.size() + haloLinks.size());
+                            for (int v : halo) {
+                                P.glist.push_back(slotOf[v]);
+                                loc[v] = -1;
+                            }
+                            for (int ls : haloLinks)
+                                P.glist.push_back(ls);
+                            for (int i = 0; i < B.nOwn; i++)
+                                loc[keyed[a + i].second] = -1;
+                        }
+                    };
+                    {
+                        const int nT = nb >= 256 ? std::max(1, std::min((int)std::thread::hardware_concurrency(), 16)) : 1;
+                        if (nT == 1)
+                            build(0, nb, local);
+                        else {
+                            std::vector<std::thread> pool;
+                            for (int t = 0; t < nT; t++)
+                                pool.emplace_back([&, t] {
+                                    std::vector<int32_t> loc((size_t)h.nv, -1);
+                                    build(nb * (size_t)t / nT, nb * (size_t)(t + 1) / nT, loc);
+                                });
+                            for (auto &th : pool)
+                                th.join();
+                        }
+                    }
+                    for (size_t k = 0; k < nb; k++) {
+                        BrickB &B = bh.bricks[firstBrick + k];
+                        const Piece &P = pieces[k];
+                        const int nOwnPad = (B.nOwn + 1) & ~1;
+                        if (bh.ldesc.size() & 1)
+                            bh.ldesc.push_back(LinkDesc{0, 0, 0, 0});
+                        B.descBeg = (int)bh.ldesc.size();
+                        bh.ldesc.insert(bh.ldesc.end(), P.desc.begin(), P.desc.end());
+                        B.nHaloL = P.nHaloL;
+                        bh.recomputed += (size_t)P.nHaloL;
+                        B.gBeg = (int)bh.glist.size(); // a multiple of 4 (bulk copies move 16-byte units)
+                        B.nHalo = P.nHalo;
+                        bh.glist.insert(bh.glist.end(), P.glist.begin(), P.glist.end());
+                        while (bh.glist.size() & 3)
+                            bh.glist.push_back(0);
+                        caps.own = std::max(caps.own, nOwnPad);
+                        caps.halo = std::max(caps.halo, B.nHalo);
+                        caps.owned = std::max(caps.owned, B.nOwned);
+                        caps.haloL = std::max(caps.haloL, B.nHaloL);
+                        if (nOwnPad + B.nHalo > 0xffff)
+                            ok = false;
+                    }
+                }
+                while (bh.borig.size() & 3) {
+                    bh.borig.push_back(-1);
+                    bh.bstat.push_back(0);
+                }
+                if (bh.ldesc.size() & 1)
+                    bh.ldesc.push_back(LinkDesc{0, 0, 0, 0});
+                brickLayout = BrickLayout<R>(caps);
+                brickSmem = brickLayout.total;
+                if (ok && brickSmem <= limit) {
+                    brickCaps = caps;
+                    for (int k = 0; k < 3; k++)
+                        brickDimsUsed[k] = dims[k];
+                    break;
+                }
+                int big = dims[1] >= dims[0] && dims[1] >= dims[2] ? 1 : dims[2] >= dims[0] ? 2 : 0; // ties: keep the x runs long
+                if (dims[big] <= 1) { // cannot happen for lattice worlds; leave every world to k_fused
+                    bw.clear();
+                    bh = BrickHost{};
+                    break;
+                }
+                dims[big] = (dims[big] + 1) / 2;
+                brickLean = true;
+            }
+            nBrickWorlds = (int)bw.size();
+            brickWorldList = bw;
+            hVoxSlot.assign(anyGhost ? nvTot : 0, -1);
+            if (anyGhost) {
+                for (size_t sl = 0; sl < bh.borig.size(); sl++)
+                    if (bh.borig[sl] >= 0)
+                        hVoxSlot[bh.borig[sl]] = (int32_t)sl;
+                std::vector<char> isBrick(n, 0);
+                for (int w : bw)
+                    isBrick[w] = 1;
+                for (int w = 0; w < n; w++)
+                    if (worlds[w].ghost && !isBrick[w]) {
+                        set_error("vx3b_batch_upload: world " + std::to_string(w) + " has ghost voxels but is not stepped by the brick path (select option path = 5; no collision / force field / targets)");
+                        return VX3B_ERR_ARG;
+                    }
+            }
+            for (int w : bw) {
+                hW[w].brickOk = 1;
+                if (pre[w].flags & (WF_VARY_TEMP | WF_THERMAL | WF_CILIA))
+                    brickLean = false;
+                for (int k = 0; k < hW[w].nvm; k++)
+                    if (vmats[hW[w].vmatOff + k].fixed)
+                        brickLean = false;
+            }
+        }
+        return VX3B_OK;
+    }
+
+    // ---- k_fused tables (kernels_fused.cuh): bricks of every world the fused path may step, their voxel / link tables, the second
+    // buffer set.  Part of upload(); reads the staging arrays upload() has filled.
+    int build_fused_tables(int n, const std::vector<int> &perm, const std::vector<Pre> &pre, const std::vector<WorldD> &hW, size_t nvTot, size_t nlTot, int smemOptin) {
+        int rc;
+        const auto &lat = staging.lat;
+        const auto &lends = staging.lends;
+        const auto &lmeta = staging.lmeta;
+        const auto &vlinks = staging.vlinks;
+        {
+            std::vector<BrickD> bricks;
+            std::vector<int32_t> bvox;
+            std::vector<uint8_t> mask;
+            std::vector<BrickLink> blinks;
+            std::vector<int32_t> local(nvTot, -1);
+            fusedCapTab = fusedCapOwn = 0;
+            fusedBrick0 = -1;
+            const int BX = brickDim[0], BY = brickDim[1], BZ0 = brickDim[2];
+            int fusedBZ = BZ0; // (for the debug line: the last world's)
+            for (int oi = 0; oi < n; oi++) {
+                int BZ = BZ0;
+                const int w = perm[oi];
+                const bool streamingOnly = pre[w].cls == 0;
+                if (!streamingOnly && !fusedAllWorlds)
+                    continue;
+                if (hW[w].brickOk)
+                    continue; // stepped by k_brick
+                if (streamingOnly && fusedBrick0 < 0)
+                    fusedBrick0 = (int)bricks.size();
+                const WorldHost &h = H[w];
+                if (h.nv == 0)
+                    continue;
+                // brick key of every voxel; voxels of a brick stay in creation order (x runs are contiguous in memory).
+                // Bricks are cut per connected body when that gives fewer of them: a scene of many bodies (BASELINE configs[3]: 8^3 cubes on
+                // a 9-cell pitch) cut on ONE world-wide grid fills its bricks to 58 %; cut from each body's own corner, every brick is full.
+                std::vector<int32_t> comp(h.nv);
+                for (int v = 0; v < h.nv; v++)
+                    comp[v] = v;
+                auto find = [&](int v) {
+                    while (comp[v] != v)
+                        v = comp[v] = comp[comp[v]];
+                    return v;
+                };
+                for (int l = 0; l < h.nl; l++) {
+                    const int a = find(lends[h.loff + l].x - h.voff), b = find(lends[h.loff + l].y - h.voff);
+                    if (a != b)
+                        comp[std::max(a, b)] = std::min(a, b); // the root is the component's first voxel
+                }
+                std::vector<int32_t> rank(h.nv, -1); // component number, in order of the first voxel
+                int nComp = 0;
+                for (int v = 0; v < h.nv; v++) {
+                    const int r = find(v);
+                    if (rank[r] < 0)
+                        rank[r] = nComp++;
+                    comp[v] = r;
+                }
+                auto count_bricks = [&](bool perBody, std::vector<int> &mnOut, int ext[3], int BZ) -> int64_t {
+                    const int nc = perBody ? nComp : 1;
+                    mnOut.assign((size_t)nc * 3, 1 << 30);
+                    std::vector<int> mxs((size_t)nc * 3, -(1 << 30));
+                    for (int v = 0; v < h.nv; v++) {
+                        const int c = perBody ? rank[comp[v]] : 0;
+                        for (int k = 0; k < 3; k++) {
+                            const int x = (&lat[h.voff + v].x)[k];
+                            mnOut[(size_t)c * 3 + k] = std::min(mnOut[(size_t)c * 3 + k], x);
+                            mxs[(size_t)c * 3 + k] = std::max(mxs[(size_t)c * 3 + k], x);
+                        }
+                    }
+                    const int bd[3] = {BX, BY, BZ};
+                    ext[0] = ext[1] = ext[2] = 1;
+                    int64_t total = 0; // upper bound of the bricks in use: cells of every body's own box
+                    for (int c = 0; c < nc; c++) {
+                        int64_t cells = 1;
+                        for (int k = 0; k < 3; k++) {
+                            const int e = (mxs[(size_t)c * 3 + k] - mnOut[(size_t)c * 3 + k]) / bd[k] + 1;
+                            ext[k] = std::max(ext[k], e);
+                            cells *= e;
+                        }
+                        total += cells;
+                    }
+                    return total;
+                };
+                std::vector<int> mnWorld, mnBody;
+                int extWorld[3], extBody[3];
+                const int64_t cellsWorld = count_bricks(false, mnWorld, extWorld, BZ);
+                int64_t cellsBody = nComp > 1 ? count_bricks(true, mnBody, extBody, BZ) : cellsWorld;
+                // bodies that fit ONE brick of twice the height (the pile's 8^3 cubes in 8x8x8 bricks): no link is cut by a brick face, so
+                // nothing is recomputed and nothing gathered; 2.72e9 -> 2.93e9 voxel-steps/s on the pile
+                if (nComp > 1 && BX * BY * BZ * 2 <= 512) {
+                    std::vector<int> mn2;
+                    int ext2[3];
+                    const int64_t cells2 = count_bricks(true, mn2, ext2, 2 * BZ);
+                    if (cells2 == nComp && cellsBody > nComp) {
+                        BZ = 2 * BZ;
+                        cellsBody = cells2;
+                        mnBody = mn2;
+                        for (int k = 0; k < 3; k++)
+                            extBody[k] = ext2[k];
+                    }
+                }
+                fusedBZ = BZ;
+                const bool perBody = nComp > 1 && cellsBody * 5 < cellsWorld * 4 && (int64_t)nComp * extBody[0] * extBody[1] * extBody[2] <= (int64_t)8 * h.nv + 4096;
+                const std::vector<int> &mnUse = perBody ? mnBody : mnWorld;
+                const int64_t nbx = perBody ? extBody[0] : extWorld[0], nby = perBody ? extBody[1] : extWorld[1], nbz = perBody ? extBody[2] : extWorld[2];
+                std::vector<std::pair<int64_t, int>> keyed(h.nv);
+                auto key_of = [&](int v) {
+                    const short4 c = lat[h.voff + v];
+                    const int64_t body = perBody ? rank[comp[v]] : 0;
+                    const int *mn = &mnUse[(size_t)body * 3];
+                    return ((body * nbz + (c.z - mn[2]) / BZ) * nby + (c.y - mn[1]) / BY) * nbx + (c.x - mn[0]) / BX;
+                };
+                const int64_t nCells = (perBody ? (int64_t)nComp : 1) * nbx * nby * nbz;
+                if (nCells <= (int64_t)4 * h.nv + 4096) { // stable counting sort by brick (= sorting the (key, index) pairs, much cheaper)
+                    std::vector<int32_t> start((size_t)nCells + 1, 0);
+                    for (int v = 0; v < h.nv; v++)
+                        start[(size_t)key_of(v) + 1]++;
+                    for (int64_t c = 0; c < nCells; c++)
+                        start[(size_t)c + 1] += start[(size_t)c];
+                    for (int v = 0; v < h.nv; v++) {
+                        const int64_t k = key_of(v);
+                        keyed[(size_t)start[(size_t)k]++] = {k, v};
+                    }
+                } else {
+                    for (int v = 0; v < h.nv; v++)
+                        keyed[v] = {key_of(v), v};
+                    std::sort(keyed.begin(), keyed.end());
+                }
+                std::vector<int64_t> brickOf(h.nv);
+                for (auto &kv : keyed)
+                    brickOf[kv.second] = kv.first;
+                for (size_t a = 0; a < keyed.size();) {
+                    size_t b = a;
+                    while (b < keyed.size() && keyed[b].first == keyed[a].first)
+                        b++;
+                    BrickD B;
+                    memset(&B, 0, sizeof(B));
+                    B.world = w;
+                    B.voxBeg = (int)bvox.size();
+                    B.nOwn = (int)(b - a);
+                    B.linkBeg = (int)blinks.size();
+                    for (size_t q = a; q < b; q++) {
+                        local[h.voff + keyed[q].second] = (int)(q - a);
+                        bvox.push_back(h.voff + keyed[q].second);
+                    }
+                    mask.resize(bvox.size(), 0);
+                    std::vector<int> halo;
+                    auto local_of = [&](int g) { // brick-local table index of global voxel g (own or halo)
+                        if (local[g] < 0) {
+                            local[g] = B.nOwn + (int)halo.size();
+                            halo.push_back(g);
+                        }
+                        return local[g];
+                    };
+                    for (size_t q = a; q < b; q++) {
+                        const int g = h.voff + keyed[q].second;
+                        uint8_t mk = 0;
+                        for (int dir = 0; dir < 6; dir++) {
+                            const int l = vlinks[(size_t)dir * nvTot + g];
+                            if (l < 0)
+                                continue;
+                            mk |= (uint8_t)(1u << dir);
+                            const int neg = lends[l].x, pos = lends[l].y;
+                            const bool negOwn = brickOf[neg - h.voff] == keyed[a].first, posOwn = brickOf[pos - h.voff] == keyed[a].first;
+                            // a link is listed once per brick: by its positive end when that end is here (owned), else by its negative end
+                            if ((dir & 1) == 0 && posOwn)
+                                continue;
+                            BrickLink k;
+                            memset(&k, 0, sizeof(k));
+                            k.link = l;
+                            k.a = (uint16_t)local_of(neg);
+                            k.b = (uint16_t)local_of(pos);
+                            k.flags = (uint16_t)((lmeta[l] & 3) | (posOwn ? BL_OWNED | BL_POS_OWN : 0) | (negOwn ? BL_NEG_OWN : 0));
+                            k.lmat = lmeta[l] >> 2;
+                            blinks.push_back(k);
+                        }
+                        mask[B.voxBeg + (q - a)] = mk;
+                    }
+                    for (int g : halo)
+                        bvox.push_back(g);
+                    mask.resize(bvox.size(), 0);
+                    B.nHalo = (int)halo.size();
+                    B.nLinks = (int)blinks.size() - B.linkBeg;
+                    for (int q = 0; q < B.nOwn + B.nHalo; q++)
+                        local[bvox[B.voxBeg + q]] = -1;
+                    fusedCapTab = std::max(fusedCapTab, B.nOwn + B.nHalo);
+                    fusedCapOwn = std::max(fusedCapOwn, B.nOwn);
+                    bricks.push_back(B);
+                    a = b;
+                }
+            }
+            if (fusedBrick0 < 0)
+                fusedBrick0 = (int)bricks.size();
+            if (!bricks.empty()) {
+                if (fusedCapTab > 0xffff) {
+                    set_error("vx3b_batch_upload: brick too large for 16-bit local indices");
+                    return VX3B_ERR_ARG;
+                }
+                BrickD *dB = nullptr;
+                int32_t *dV = nullptr;
+                BrickLink *dL = nullptr;
+                uint8_t *dM = nullptr;
+                if ((rc = dalloc(&dB, bricks.size(), bricks.data())) != VX3B_OK || (rc = dalloc(&dV, bvox.size(), bvox.data())) != VX3B_OK ||
+                    (rc = dalloc(&dL, blinks.size(), blinks.data())) != VX3B_OK || (rc = dalloc(&dM, mask.size(), mask.data())) != VX3B_OK)
+                    return rc;
+                FA.nBricks = (int)bricks.size();
+                FA.bricks = dB;
+                FA.bvox = dV;
+                FA.blinks = dL;
+                FA.linkMask = dM;
+                // second buffer set for the ping-pong (contents are produced by the first fused step)
+                if ((rc = dalloc(&A.alt.pxy, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.pzt, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.orient, nvTot)) != VX3B_OK ||
+                    (rc = dalloc(&A.alt.lm, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.am, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.lpos2, nlTot)) != VX3B_OK ||
+                    (rc = dalloc(&A.alt.la1, nlTot)) != VX3B_OK || (rc = dalloc(&A.alt.la2, nlTot)) != VX3B_OK)
+                    return rc;
+                fusedSmem = FusedLayout<R>(fusedCapTab, fusedCapOwn).total;
+                CUDA_TRY(cudaFuncSetAttribute(k_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin)); // the limit is per function, not per context: never lower it
+                if (getenv("VX3B_DEBUG"))
+                    fprintf(stderr, "[vx3b] fused path: %zu bricks (%dx%dx%d), table <= %d voxels, own <= %d, %zu links incl. %.1f%% recomputed, %zu B shared memory\n",
+                            bricks.size(), BX, BY, fusedBZ, fusedCapTab, fusedCapOwn, blinks.size(), 100.0 * (blinks.size() - (double)nlTot) / std::max<size_t>(nlTot, 1), fusedSmem);
+            }
+        }
+        return VX3B_OK;
+    }
+
     int upload(const VX3B_WorldDesc *worlds, int n) override {
         CUDA_TRY(cudaSetDevice(device));
         release_graphs();
@@ -319,15 +884,6 @@ template <class R> class Engine : public EngineBase {
             tPrev = now;
         };
         // ---- per-world summary: surface count, feature flags, shared-memory need -> k_resident size class ------------------
-        struct Pre {
-            int ns = 0, cls = 0, next = 0; // surface voxels, k_resident size class, voxels with boundary conditions
-            bool full = false;             // needs k_resident's FULL instantiation (boundary conditions, force field, failure strain)
-            uint32_t flags = 0;
-            size_t bytes = 0;
-            double invCell = 0, listR2 = 0;
-            float skinHalf2 = 0;
-            bool spill = false;
-        };
         std::vector<Pre> pre(n);
         std::vector<int> listCaps(n, 16);
         int dev = 0, smemPerSm = 0, smemOptin = 0;
@@ -876,326 +1432,12 @@ template <class R> class Engine : public EngineBase {
         }
 
         lap("host staging");
-        // ---- brick path plan (host only; kernels_brick.cuh): which worlds, brick tables, shared-memory fit -----------------------
+        // ---- brick path plan (host only; kernels_brick.cuh): which worlds, brick tables, shared-memory fit
         BrickHost bh;
         BA = BrickArrays<R>{};
         brickLean = true;
-        {
-            std::vector<int> bw; // brick worlds in layout order
-            for (int oi = 0; oi < n; oi++) {
-                const int w = perm[oi];
-                const VX3B_WorldDesc &d = worlds[w];
-                const bool wanted = path == 5 || (path == 0 && pre[w].cls == 0);
-                if (!wanted || d.num_voxels == 0 || (pre[w].flags & (WF_COLLISION | WF_FORCE_FIELD)) || d.max_dist_in_voxel_lengths_to_count_as_pair != 0 ||
-                    d.num_voxel_mats > BRICK_MAX_VMATS || d.num_link_mats > BRICK_MAX_LMATS)
-                    continue;
-                bw.push_back(w);
-            }
-            int dims[3] = {brickDim[0], brickDim[1], brickDim[2]};
-            // one persistent CTA (512 threads, two-stage ring) may take the whole SM; small bricks leave room for two (256 threads each)
-            const size_t limit = (size_t)smemOptin;
-            while (!bw.empty()) {
-                bh = BrickHost{};
-                BrickCaps caps{0, 0, 0, 0, 1, 1};
-                bool ok = true;
-                std::vector<int32_t> slotOf, lslotOf, brickOf, local;
-                for (int w : bw) {
-                    const WorldHost &h = H[w];
-                    const WorldD &W = hW[w];
-                    caps.nvm = std::max(caps.nvm, W.nvm);
-                    caps.nlm = std::max(caps.nlm, W.nlm);
-                    int mn[3] = {1 << 30, 1 << 30, 1 << 30};
-                    for (int v = 0; v < h.nv; v++)
-                        for (int k = 0; k < 3; k++)
-                            mn[k] = std::min(mn[k], (int)(&lat[h.voff + v].x)[k]);
-                    int mx[2] = {-(1 << 30), -(1 << 30)};
-                    for (int v = 0; v < h.nv; v++)
-                        for (int k = 0; k < 2; k++)
-                            mx[k] = std::max(mx[k], (int)(&lat[h.voff + v].x)[k]);
-                    const int64_t nbx = (mx[0] - mn[0]) / dims[0] + 1, nby = (mx[1] - mn[1]) / dims[1] + 1;
-                    std::vector<std::pair<int64_t, int>> keyed(h.nv); // (brick key, voxel): creation order inside a brick = x fastest
-                    int mxz = -(1 << 30);
-                    for (int v = 0; v < h.nv; v++)
-                        mxz = std::max(mxz, (int)lat[h.voff + v].z);
-                    const int64_t nbz = (mxz - mn[2]) / dims[2] + 1, nCells = nbx * nby * nbz;
-                    auto key_of = [&](int v) {
-                        const short4 c = lat[h.voff + v];
-                        return (((int64_t)(c.z - mn[2]) / dims[2]) * nby + (c.y - mn[1]) / dims[1]) * nbx + (c.x - mn[0]) / dims[0];
-                    };
-                    if (nCells <= (int64_t)4 * h.nv + 4096) {
-                        // counting sort by brick: stable, so voxels keep their creation order (ascending index) inside a brick, which is
-                        // what sorting the (key, index) pairs gives - at a tenth of the time on a million-voxel body
-                        std::vector<int32_t> start((size_t)nCells + 1, 0);
-                        for (int v = 0; v < h.nv; v++)
-                            start[(size_t)key_of(v) + 1]++;
-                        for (int64_t c = 0; c < nCells; c++)
-                            start[(size_t)c + 1] += start[(size_t)c];
-                        for (int v = 0; v < h.nv; v++) {
-                            const int64_t k = key_of(v);
-                            keyed[(size_t)start[(size_t)k]++] = {k, v};
-                        }
-                    } else { // a sparse world on a huge lattice: sort the pairs
-                        for (int v = 0; v < h.nv; v++)
-                            keyed[v] = {key_of(v), v};
-                        std::sort(keyed.begin(), keyed.end());
-                    }
-                    slotOf.assign(h.nv, -1);
-                    lslotOf.assign(h.nl, -1);
-                    brickOf.assign(h.nv, -1);
-                    local.assign(h.nv, -1);
-                    const size_t firstBrick = bh.bricks.size();
-                    bh.borig.reserve(bh.borig.size() + (size_t)h.nv + (size_t)h.nv / 16 + 64);
-                    bh.bstat.reserve(bh.bstat.size() + (size_t)h.nv + (size_t)h.nv / 16 + 64);
-                    bh.lorig.reserve(bh.lorig.size() + (size_t)h.nl);
-                    bh.ldesc.reserve(bh.ldesc.size() + (size_t)h.nl + (size_t)h.nl / 4 + 64);
-                    // pass 1: brick-order slots of voxels and owned links.  Brick extents in `keyed` first, then (host threads side by
-                    // side over bricks) the number of links every brick owns, a serial prefix sum for the slot offsets, and the fill.
-                    std::vector<size_t> bBeg; // index into keyed of every brick's first voxel (+ end sentinel)
-                    for (size_t a = 0; a < keyed.size();) {
-                        bBeg.push_back(a);
-                        const int64_t key = keyed[a].first;
-                        while (a < keyed.size() && keyed[a].first == key)
-                            a++;
-                    }
-                    bBeg.push_back(keyed.size());
-                    const size_t nNew = bBeg.size() - 1;
-                    const int nT1 = nNew >= 256 ? std::max(1, std::min((int)std::thread::hardware_concurrency(), 16)) : 1;
-                    auto over_bricks = [&](auto &&fn) { // fn(first brick, last brick) on nT1 threads
-                        if (nT1 == 1) {
-                            fn((size_t)0, nNew);
-                            return;
-                        }
-                        std::vector<std::thread> pool;
-                        for (int t = 1; t < nT1; t++)
-                            pool.emplace_back([&, t] { fn(nNew * (size_t)t / nT1, nNew * (size_t)(t + 1) / nT1); });
-                        fn((size_t)0, nNew / nT1);
-                        for (auto &th : pool)
-                            th.join();
-                    };
-                    std::vector<int32_t> nOwnedOf(nNew, 0);
-                    over_bricks([&](size_t k0, size_t k1) {
-                        for (size_t k = k0; k < k1; k++) {
-                            int cnt = 0;
-                            for (size_t q = bBeg[k]; q < bBeg[k + 1]; q++)
-                                for (int axis = 0; axis < 3; axis++)
-                                    cnt += vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + keyed[q].second] >= 0;
-                            nOwnedOf[k] = cnt;
-                        }
-                    });
-                    {
-                        size_t vAt = bh.borig.size(), lAt = bh.lorig.size();
-                        for (size_t k = 0; k < nNew; k++) {
-                            vAt = (vAt + 3) & ~(size_t)3; // own runs start on a multiple of four slots: every array, down to the 4-byte
-                            BrickB B;                     // static words, is then 16-byte aligned for the bulk copies
-                            memset(&B, 0, sizeof(B));
-                            B.world = w;
-                            B.v0 = (int)vAt;
-                            B.nOwn = (int)(bBeg[k + 1] - bBeg[k]);
-                            B.l0 = (int)lAt;
-                            B.nOwned = nOwnedOf[k];
-                            bh.bricks.push_back(B);
-                            vAt += (size_t)B.nOwn;
-                            lAt += (size_t)B.nOwned;
-                        }
-                        bh.borig.resize(vAt, -1); // (padding slots keep -1 / 0)
-                        bh.bstat.resize(vAt, 0);
-                        bh.lorig.resize(lAt);
-                    }
-                    std::atomic<bool> anyExtVoxel{false};
-                    over_bricks([&](size_t k0, size_t k1) {
-                        for (size_t k = k0; k < k1; k++) {
-                            const BrickB &B = bh.bricks[firstBrick + k];
-                            const size_t a = bBeg[k], b = bBeg[k + 1];
-                            size_t slot = (size_t)B.v0;
-                            for (size_t q = a; q < b; q++, slot++) {
-                                const int v = keyed[q].second, g = h.voff + v;
-                                slotOf[v] = (int)slot;
-                                brickOf[v] = (int)(firstBrick + k);
-                                uint32_t mk = 0;
-                                for (int dir = 0; dir < 6; dir++)
-                                    if (vlinks[(size_t)dir * nvTot + g] >= 0)
-                                        mk |= 1u << dir;
-                                bh.borig[slot] = g;
-                                bh.bstat[slot] = (uint32_t)(vmat[g] - W.vmatOff) | (mk << 8) | (vext[g] >= 0 ? 1u << 14 : 0u) | (vghost[g] ? 1u << 15 : 0u);
-                                if (vext[g] >= 0)
-                                    anyExtVoxel = true;
-                            }
-                            size_t ls = (size_t)B.l0;
-                            for (int axis = 0; axis < 3; axis++)
-                                for (size_t q = a; q < b; q++) {
-                                    const int l = vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + keyed[q].second];
-                                    if (l >= 0) {
-                                        lslotOf[l - h.loff] = (int)ls;
-                                        bh.lorig[ls++] = l;
-                                    }
-                                }
-                        }
-                    });
-                    if (anyExtVoxel)
-                        brickLean = false;
-                    // pass 2: link descriptors (recomputed links first, then the owned run in slot order) and halo tables.  Bricks are
-                    // independent here, so host threads build them side by side into per-brick pieces (each thread with its own
-                    // voxel -> brick-local index scratch); the pieces are appended in brick order afterwards.
-                    struct Piece {
-                        std::vector<LinkDesc> desc;
-                        std::vector<int32_t> glist; // halo voxel slots, then recomputed-link slots
-                        int nHalo = 0, nHaloL = 0;
-                    };
-                    const size_t nb = bh.bricks.size() - firstBrick;
-                    std::vector<Piece> pieces(nb);
-                    std::vector<size_t> firstVox(nb + 1, 0); // index into keyed of every brick's first own voxel
-                    for (size_t k = 0; k < nb; k++)
-                        firstVox[k + 1] = firstVox[k] + (size_t)bh.bricks[firstBrick + k].nOwn;
-                    auto build = [&](size_t k0, size_t k1, std::vector<int32_t> &loc) {
-                        std::vector<int> halo; // world-local voxel index
-                        for (size_t k = k0; k < k1; k++) {
-                            const size_t bi = firstBrick + k, a = firstVox[k];
-                            const BrickB &B = bh.bricks[bi];
-                            Piece &P = pieces[k];
-                            const int nOwnPad = (B.nOwn + 1) & ~1;
-                            halo.clear();
-                            for (int i = 0; i < B.nOwn; i++)
-                                loc[keyed[a + i].second] = i;
-                            auto local_of = [&](int v) {
-                                if (loc[v] < 0) {
-                                    loc[v] = nOwnPad + (int)halo.size();
-                                    halo.push_back(v);
-                                }
-                                return loc[v];
-                            };
-                            auto mat_of = [&](int v) { return (uint32_t)(vmat[h.voff + v] - W.vmatOff); };
-                            std::vector<int32_t> haloLinks;
-                            P.desc.reserve((size_t)B.nOwned + (size_t)B.nOwned / 4 + 8);
-                            for (int axis = 0; axis < 3; axis++)
-                                for (int i = 0; i < B.nOwn; i++) {
-                                    const int v = keyed[a + i].second;
-                                    const int l = vlinks[(size_t)(2 * axis) * nvTot + h.voff + v]; // v is the negative end
-                                    if (l < 0)
-                                        continue;
-                                    const int pos = lends[l].y - h.voff;
-                                    if (brickOf[pos] == (int)bi)
-                                        continue; // owned by this brick
-                                    LinkDesc d;
-                                    d.a = (uint16_t)i;
-                                    d.b = (uint16_t)local_of(pos);
-                                    d.lmat = (uint16_t)((lmeta[l] >> 2) - (uint32_t)W.lmatOff);
-                                    d.flags = (uint16_t)(axis | BD_NEG_OWN | (mat_of(v) << 4) | (mat_of(pos) << 8));
-                                    P.desc.push_back(d);
-                                    haloLinks.push_back(lslotOf[l - h.loff]);
-                                }
-                            P.nHaloL = (int)haloLinks.size();
-                            for (int axis = 0; axis < 3; axis++)
-                                for (int i = 0; i < B.nOwn; i++) {
-                                    const int v = keyed[a + i].second;
-                                    const int l = vlinks[(size_t)(2 * axis + 1) * nvTot + h.voff + v]; // v is the positive end: owned
-                                    if (l < 0)
-                                        continue;
-                                    const int neg = lends[l].x - h.voff;
-                                    LinkDesc d;
-                                    d.a = (uint16_t)local_of(neg);
-                                    d.b = (uint16_t)i;
-                                    d.lmat = (uint16_t)((lmeta[l] >> 2) - (uint32_t)W.lmatOff);
-                                    d.flags = (uint16_t)(axis | BD_POS_OWN | (brickOf[neg] == (int)bi ? BD_NEG_OWN : 0) | (mat_of(neg) << 4) | (mat_of(v) << 8));
-                                    P.desc.push_back(d);
-                                }
-                            P.nHalo = (int)halo.size();
-                            P.glist.reserve(halo.size() + haloLinks.size());
-                            for (int v : halo) {
-                                P.glist.push_back(slotOf[v]);
-                                loc[v] = -1;
-                            }
-                            for (int ls : haloLinks)
-                                P.glist.push_back(ls);
-                            for (int i = 0; i < B.nOwn; i++)
-                                loc[keyed[a + i].second] = -1;
-                        }
-                    };
-                    {
-                        const int nT = nb >= 256 ? std::max(1, std::min((int)std::thread::hardware_concurrency(), 16)) : 1;
-                        if (nT == 1)
-                            build(0, nb, local);
-                        else {
-                            std::vector<std::thread> pool;
-                            for (int t = 0; t < nT; t++)
-                                pool.emplace_back([&, t] {
-                                    std::vector<int32_t> loc((size_t)h.nv, -1);
-                                    build(nb * (size_t)t / nT, nb * (size_t)(t + 1) / nT, loc);
-                                });
-                            for (auto &th : pool)
-                                th.join();
-                        }
-                    }
-                    for (size_t k = 0; k < nb; k++) {
-                        BrickB &B = bh.bricks[firstBrick + k];
-                        const Piece &P = pieces[k];
-                        const int nOwnPad = (B.nOwn + 1) & ~1;
-                        if (bh.ldesc.size() & 1)
-                            bh.ldesc.push_back(LinkDesc{0, 0, 0, 0});
-                        B.descBeg = (int)bh.ldesc.size();
-                        bh.ldesc.insert(bh.ldesc.end(), P.desc.begin(), P.desc.end());
-                        B.nHaloL = P.nHaloL;
-                        bh.recomputed += (size_t)P.nHaloL;
-                        B.gBeg = (int)bh.glist.size(); // a multiple of 4 (bulk copies move 16-byte units)
-                        B.nHalo = P.nHalo;
-                        bh.glist.insert(bh.glist.end(), P.glist.begin(), P.glist.end());
-                        while (bh.glist.size() & 3)
-                            bh.glist.push_back(0);
-                        caps.own = std::max(caps.own, nOwnPad);
-                        caps.halo = std::max(caps.halo, B.nHalo);
-                        caps.owned = std::max(caps.owned, B.nOwned);
-                        caps.haloL = std::max(caps.haloL, B.nHaloL);
-                        if (nOwnPad + B.nHalo > 0xffff)
-                            ok = false;
-                    }
-                }
-                while (bh.borig.size() & 3) {
-                    bh.borig.push_back(-1);
-                    bh.bstat.push_back(0);
-                }
-                if (bh.ldesc.size() & 1)
-                    bh.ldesc.push_back(LinkDesc{0, 0, 0, 0});
-                brickLayout = BrickLayout<R>(caps);
-                brickSmem = brickLayout.total;
-                if (ok && brickSmem <= limit) {
-                    brickCaps = caps;
-                    for (int k = 0; k < 3; k++)
-                        brickDimsUsed[k] = dims[k];
-                    break;
-                }
-                int big = dims[1] >= dims[0] && dims[1] >= dims[2] ? 1 : dims[2] >= dims[0] ? 2 : 0; // ties: keep the x runs long
-                if (dims[big] <= 1) { // cannot happen for lattice worlds; leave every world to k_fused
-                    bw.clear();
-                    bh = BrickHost{};
-                    break;
-                }
-                dims[big] = (dims[big] + 1) / 2;
-                brickLean = true;
-            }
-            nBrickWorlds = (int)bw.size();
-            brickWorldList = bw;
-            hVoxSlot.assign(anyGhost ? nvTot : 0, -1);
-            if (anyGhost) {
-                for (size_t sl = 0; sl < bh.borig.size(); sl++)
-                    if (bh.borig[sl] >= 0)
-                        hVoxSlot[bh.borig[sl]] = (int32_t)sl;
-                std::vector<char> isBrick(n, 0);
-                for (int w : bw)
-                    isBrick[w] = 1;
-                for (int w = 0; w < n; w++)
-                    if (worlds[w].ghost && !isBrick[w]) {
-                        set_error("vx3b_batch_upload: world " + std::to_string(w) + " has ghost voxels but is not stepped by the brick path (select option path = 5; no collision / force field / targets)");
-                        return VX3B_ERR_ARG;
-                    }
-            }
-            for (int w : bw) {
-                hW[w].brickOk = 1;
-                if (pre[w].flags & (WF_VARY_TEMP | WF_THERMAL | WF_CILIA))
-                    brickLean = false;
-                for (int k = 0; k < hW[w].nvm; k++)
-                    if (vmats[hW[w].vmatOff + k].fixed)
-                        brickLean = false;
-            }
-        }
+        if (int rcPlan = build_brick_plan(worlds, n, perm, pre, hW, vmats, nvTot, smemOptin, anyGhost, bh))
+            return rcPlan;
         lap("brick plan");
         // ---- device
         if (!stream) {
@@ -1306,218 +1548,8 @@ template <class R> class Engine : public EngineBase {
         // ---- fused tile path: cut the streaming-only worlds (all worlds for path 3) into bricks --------------------------------
         FA = FusedArrays{};
         fusedAllWorlds = path == 3 || path == 5;
-        {
-            std::vector<BrickD> bricks;
-            std::vector<int32_t> bvox;
-            std::vector<uint8_t> mask;
-            std::vector<BrickLink> blinks;
-            std::vector<int32_t> local(nvTot, -1);
-            fusedCapTab = fusedCapOwn = 0;
-            fusedBrick0 = -1;
-            const int BX = brickDim[0], BY = brickDim[1], BZ0 = brickDim[2];
-            int fusedBZ = BZ0; // (for the debug line: the last world's)
-            for (int oi = 0; oi < n; oi++) {
-                int BZ = BZ0;
-                const int w = perm[oi];
-                const bool streamingOnly = pre[w].cls == 0;
-                if (!streamingOnly && !fusedAllWorlds)
-                    continue;
-                if (hW[w].brickOk)
-                    continue; // stepped by k_brick
-                if (streamingOnly && fusedBrick0 < 0)
-                    fusedBrick0 = (int)bricks.size();
-                const WorldHost &h = H[w];
-                if (h.nv == 0)
-                    continue;
-                // brick key of every voxel; voxels of a brick stay in creation order (x runs are contiguous in memory).
-                // Bricks are cut per connected body when that gives fewer of them: a scene of many bodies (BASELINE configs[3]: 8^3 cubes on
-                // a 9-cell pitch) cut on ONE world-wide grid fills its bricks to 58 %; cut from each body's own corner, every brick is full.
-                std::vector<int32_t> comp(h.nv);
-                for (int v = 0; v < h.nv; v++)
-                    comp[v] = v;
-                auto find = [&](int v) {
-                    while (comp[v] != v)
-                        v = comp[v] = comp[comp[v]];
-                    return v;
-                };
-                for (int l = 0; l < h.nl; l++) {
-                    const int a = find(lends[h.loff + l].x - h.voff), b = find(lends[h.loff + l].y - h.voff);
-                    if (a != b)
-                        comp[std::max(a, b)] = std::min(a, b); // the root is the component's first voxel
-                }
-                std::vector<int32_t> rank(h.nv, -1); // component number, in order of the first voxel
-                int nComp = 0;
-                for (int v = 0; v < h.nv; v++) {
-                    const int r = find(v);
-                    if (rank[r] < 0)
-                        rank[r] = nComp++;
-                    comp[v] = r;
-                }
-                auto count_bricks = [&](bool perBody, std::vector<int> &mnOut, int ext[3], int BZ) -> int64_t {
-                    const int nc = perBody ? nComp : 1;
-                    mnOut.assign((size_t)nc * 3, 1 << 30);
-                    std::vector<int> mxs((size_t)nc * 3, -(1 << 30));
-                    for (int v = 0; v < h.nv; v++) {
-                        const int c = perBody ? rank[comp[v]] : 0;
-                        for (int k = 0; k < 3; k++) {
-                            const int x = (&lat[h.voff + v].x)[k];
-                            mnOut[(size_t)c * 3 + k] = std::min(mnOut[(size_t)c * 3 + k], x);
-                            mxs[(size_t)c * 3 + k] = std::max(mxs[(size_t)c * 3 + k], x);
-                        }
-                    }
-                    const int bd[3] = {BX, BY, BZ};
-                    ext[0] = ext[1] = ext[2] = 1;
-                    int64_t total = 0; // upper bound of the bricks in use: cells of every body's own box
-                    for (int c = 0; c < nc; c++) {
-                        int64_t cells = 1;
-                        for (int k = 0; k < 3; k++) {
-                            const int e = (mxs[(size_t)c * 3 + k] - mnOut[(size_t)c * 3 + k]) / bd[k] + 1;
-                            ext[k] = std::max(ext[k], e);
-                            cells *= e;
-                        }
-                        total += cells;
-                    }
-                    return total;
-                };
-                std::vector<int> mnWorld, mnBody;
-                int extWorld[3], extBody[3];
-                const int64_t cellsWorld = count_bricks(false, mnWorld, extWorld, BZ);
-                int64_t cellsBody = nComp > 1 ? count_bricks(true, mnBody, extBody, BZ) : cellsWorld;
-                // bodies that fit ONE brick of twice the height (the pile's 8^3 cubes in 8x8x8 bricks): no link is cut by a brick face, so
-                // nothing is recomputed and nothing gathered; 2.72e9 -> 2.93e9 voxel-steps/s on the pile
-                if (nComp > 1 && BX * BY * BZ * 2 <= 512) {
-                    std::vector<int> mn2;
-                    int ext2[3];
-                    const int64_t cells2 = count_bricks(true, mn2, ext2, 2 * BZ);
-                    if (cells2 == nComp && cellsBody > nComp) {
-                        BZ = 2 * BZ;
-                        cellsBody = cells2;
-                        mnBody = mn2;
-                        for (int k = 0; k < 3; k++)
-                            extBody[k] = ext2[k];
-                    }
-                }
-                fusedBZ = BZ;
-                const bool perBody = nComp > 1 && cellsBody * 5 < cellsWorld * 4 && (int64_t)nComp * extBody[0] * extBody[1] * extBody[2] <= (int64_t)8 * h.nv + 4096;
-                const std::vector<int> &mnUse = perBody ? mnBody : mnWorld;
-                const int64_t nbx = perBody ? extBody[0] : extWorld[0], nby = perBody ? extBody[1] : extWorld[1], nbz = perBody ? extBody[2] : extWorld[2];
-                std::vector<std::pair<int64_t, int>> keyed(h.nv);
-                auto key_of = [&](int v) {
-                    const short4 c = lat[h.voff + v];
-                    const int64_t body = perBody ? rank[comp[v]] : 0;
-                    const int *mn = &mnUse[(size_t)body * 3];
-                    return ((body * nbz + (c.z - mn[2]) / BZ) * nby + (c.y - mn[1]) / BY) * nbx + (c.x - mn[0]) / BX;
-                };
-                const int64_t nCells = (perBody ? (int64_t)nComp : 1) * nbx * nby * nbz;
-                if (nCells <= (int64_t)4 * h.nv + 4096) { // stable counting sort by brick (= sorting the (key, index) pairs, much cheaper)
-                    std::vector<int32_t> start((size_t)nCells + 1, 0);
-                    for (int v = 0; v < h.nv; v++)
-                        start[(size_t)key_of(v) + 1]++;
-                    for (int64_t c = 0; c < nCells; c++)
-                        start[(size_t)c + 1] += start[(size_t)c];
-                    for (int v = 0; v < h.nv; v++) {
-                        const int64_t k = key_of(v);
-                        keyed[(size_t)start[(size_t)k]++] = {k, v};
-                    }
-                } else {
-                    for (int v = 0; v < h.nv; v++)
-                        keyed[v] = {key_of(v), v};
-                    std::sort(keyed.begin(), keyed.end());
-                }
-                std::vector<int64_t> brickOf(h.nv);
-                for (auto &kv : keyed)
-                    brickOf[kv.second] = kv.first;
-                for (size_t a = 0; a < keyed.size();) {
-                    size_t b = a;
-                    while (b < keyed.size() && keyed[b].first == keyed[a].first)
-                        b++;
-                    BrickD B;
-                    memset(&B, 0, sizeof(B));
-                    B.world = w;
-                    B.voxBeg = (int)bvox.size();
-                    B.nOwn = (int)(b - a);
-                    B.linkBeg = (int)blinks.size();
-                    for (size_t q = a; q < b; q++) {
-                        local[h.voff + keyed[q].second] = (int)(q - a);
-                        bvox.push_back(h.voff + keyed[q].second);
-                    }
-                    mask.resize(bvox.size(), 0);
-                    std::vector<int> halo;
-                    auto local_of = [&](int g) { // brick-local table index of global voxel g (own or halo)
-                        if (local[g] < 0) {
-                            local[g] = B.nOwn + (int)halo.size();
-                            halo.push_back(g);
-                        }
-                        return local[g];
-                    };
-                    for (size_t q = a; q < b; q++) {
-                        const int g = h.voff + keyed[q].second;
-                        uint8_t mk = 0;
-                        for (int dir = 0; dir < 6; dir++) {
-                            const int l = vlinks[(size_t)dir * nvTot + g];
-                            if (l < 0)
-                                continue;
-                            mk |= (uint8_t)(1u << dir);
-                            const int neg = lends[l].x, pos = lends[l].y;
-                            const bool negOwn = brickOf[neg - h.voff] == keyed[a].first, posOwn = brickOf[pos - h.voff] == keyed[a].first;
-                            // a link is listed once per brick: by its positive end when that end is here (owned), else by its negative end
-                            if ((dir & 1) == 0 && posOwn)
-                                continue;
-                            BrickLink k;
-                            memset(&k, 0, sizeof(k));
-                            k.link = l;
-                            k.a = (uint16_t)local_of(neg);
-                            k.b = (uint16_t)local_of(pos);
-                            k.flags = (uint16_t)((lmeta[l] & 3) | (posOwn ? BL_OWNED | BL_POS_OWN : 0) | (negOwn ? BL_NEG_OWN : 0));
-                            k.lmat = lmeta[l] >> 2;
-                            blinks.push_back(k);
-                        }
-                        mask[B.voxBeg + (q - a)] = mk;
-                    }
-                    for (int g : halo)
-                        bvox.push_back(g);
-                    mask.resize(bvox.size(), 0);
-                    B.nHalo = (int)halo.size();
-                    B.nLinks = (int)blinks.size() - B.linkBeg;
-                    for (int q = 0; q < B.nOwn + B.nHalo; q++)
-                        local[bvox[B.voxBeg + q]] = -1;
-                    fusedCapTab = std::max(fusedCapTab, B.nOwn + B.nHalo);
-                    fusedCapOwn = std::max(fusedCapOwn, B.nOwn);
-                    bricks.push_back(B);
-                    a = b;
-                }
-            }
-            if (fusedBrick0 < 0)
-                fusedBrick0 = (int)bricks.size();
-            if (!bricks.empty()) {
-                if (fusedCapTab > 0xffff) {
-                    set_error("vx3b_batch_upload: brick too large for 16-bit local indices");
-                    return VX3B_ERR_ARG;
-                }
-                BrickD *dB = nullptr;
-                int32_t *dV = nullptr;
-                BrickLink *dL = nullptr;
-                uint8_t *dM = nullptr;
-                if ((rc = dalloc(&dB, bricks.size(), bricks.data())) != VX3B_OK || (rc = dalloc(&dV, bvox.size(), bvox.data())) != VX3B_OK ||
-                    (rc = dalloc(&dL, blinks.size(), blinks.data())) != VX3B_OK || (rc = dalloc(&dM, mask.size(), mask.data())) != VX3B_OK)
-                    return rc;
-                FA.nBricks = (int)bricks.size();
-                FA.bricks = dB;
-                FA.bvox = dV;
-                FA.blinks = dL;
-                FA.linkMask = dM;
-                // second buffer set for the ping-pong (contents are produced by the first fused step)
-                if ((rc = dalloc(&A.alt.pxy, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.pzt, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.orient, nvTot)) != VX3B_OK ||
-                    (rc = dalloc(&A.alt.lm, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.am, nvTot)) != VX3B_OK || (rc = dalloc(&A.alt.lpos2, nlTot)) != VX3B_OK ||
-                    (rc = dalloc(&A.alt.la1, nlTot)) != VX3B_OK || (rc = dalloc(&A.alt.la2, nlTot)) != VX3B_OK)
-                    return rc;
-                fusedSmem = FusedLayout<R>(fusedCapTab, fusedCapOwn).total;
-                CUDA_TRY(cudaFuncSetAttribute(k_fused<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin)); // the limit is per function, not per context: never lower it
-                if (getenv("VX3B_DEBUG"))
-                    fprintf(stderr, "[vx3b] fused path: %zu bricks (%dx%dx%d), table <= %d voxels, own <= %d, %zu links incl. %.1f%% recomputed, %zu B shared memory\n",
-                            bricks.size(), BX, BY, fusedBZ, fusedCapTab, fusedCapOwn, blinks.size(), 100.0 * (blinks.size() - (double)nlTot) / std::max<size_t>(nlTot, 1), fusedSmem);
-            }
-        }
+        if ((rc = build_fused_tables(n, perm, pre, hW, nvTot, nlTot, smemOptin)) != VX3B_OK)
+            return rc;
         lap("fused tables");
         // ---- brick path: tables and the two brick-ordered buffer sets
         if (!bh.bricks.empty()) {
