@@ -91,6 +91,7 @@ struct WorldD {
     // centre of mass at the end of the last run (results, fitness).  Kept apart from `com`, which the reference refreshes only on the
     // sampling steps of a run (VX3_VoxelyzeKernel.cu:314-334): a run continued by another call must see what one long run sees
     double finalCom[3];
+    int32_t gRefSlot, padG; // brick worlds with contact: brick-order slot of the reference voxel of the stale-list check (kernels_contact.cuh)
     int32_t numMeasured, gRebuildNext; // gRebuildNext: some surface voxel has moved skin/2 since the global contact lists were built: rebuild at the next step
     VX3B_Token stop[VX3B_MAX_TOKENS], fitnessF[VX3B_MAX_TOKENS], ff[3 * VX3B_MAX_TOKENS];
 };
@@ -163,5 +164,8 @@ template <class R> struct Arrays {
 template <class R> VXD StateSet<R> main_set(const Arrays<R> &A) { return StateSet<R>{A.pxy, A.pzt, A.orient, A.lm, A.am, A.lpos2, A.la1, A.la2}; }
 // buffer set holding a world's current state
 template <class R> VXD StateSet<R> cur_set(const Arrays<R> &A, int parity) { return parity ? A.alt : main_set(A); }
+// what the contact kernels read (positions and linear momentum of SURFACE voxels): the world's current buffer set - except for a world
+// on the brick path, whose state lives in brick order: its step kernel mirrors the surface voxels into the main arrays every step
+template <class R> VXD StateSet<R> contact_set(const Arrays<R> &A, const WorldD &W) { return cur_set(A, (W.flags & WF_BRICK) ? 0 : W.parity); }
 
 } // namespace vx3b

@@ -194,6 +194,7 @@ template <class R> class Engine : public EngineBase {
     int brickDimsUsed[3] = {0, 0, 0};
     int brickGrid = 0, brickThreads = 256, nBrickWorlds = 0;
     bool brickDoesWorldStep = false;
+    bool brickColl = false;     // some brick world has voxel-voxel contact (k_brick's COLL instantiation)
     ContactGrid CG{};           // global-memory contact broad phase of the big worlds (kernels_contact.cuh)
     bool gridCoversAll = false;
     int stepLaunches = 0;        // kernels one enqueue_step launches (counted while enqueueing)
@@ -284,6 +285,91 @@ template <class R> class Engine : public EngineBase {
         bool spill = false;
     };
 
+    // ---- which brick a voxel belongs to (both brick builders).  Bricks are cut on one grid from the world's corner, or - when that needs
+    // fewer of them - per connected body from each body's own corner: a scene of many bodies (BASELINE configs[3]: 8^3 cubes on a 9-cell
+    // pitch) cut on ONE grid fills its bricks to 58 %; cut per body, every brick is full.
+    struct BrickCut {
+        std::vector<int32_t> body; // [nv] number of the voxel's connected body, in order of the bodies' first voxels
+        int nBodies = 0;
+        bool perBody = false;
+        std::vector<int> mn;       // per body (or one entry for the world): lattice corner
+        int64_t nb[3] = {1, 1, 1}; // bricks per axis of the largest box
+        int d[3] = {1, 1, 1};
+        int64_t cells() const { return (perBody ? (int64_t)nBodies : 1) * nb[0] * nb[1] * nb[2]; }
+        int64_t key(short4 c, int v) const {
+            const int64_t b = perBody ? body[v] : 0;
+            const int *m = &mn[(size_t)b * 3];
+            return ((b * nb[2] + (c.z - m[2]) / d[2]) * nb[1] + (c.y - m[1]) / d[1]) * nb[0] + (c.x - m[0]) / d[0];
+        }
+    };
+    void brick_cut_bodies(const WorldHost &h, BrickCut &C) const { // union-find over the links; the root is a body's first voxel
+        const auto &lends = staging.lends;
+        std::vector<int32_t> &comp = C.body;
+        comp.resize(h.nv);
+        for (int v = 0; v < h.nv; v++)
+            comp[v] = v;
+        auto find = [&](int v) {
+            while (comp[v] != v)
+                v = comp[v] = comp[comp[v]];
+            return v;
+        };
+        for (int l = 0; l < h.nl; l++) {
+            const int a = find(lends[h.loff + l].x - h.voff), b = find(lends[h.loff + l].y - h.voff);
+            if (a != b)
+                comp[std::max(a, b)] = std::min(a, b);
+        }
+        std::vector<int32_t> rank(h.nv, -1);
+        C.nBodies = 0;
+        for (int v = 0; v < h.nv; v++) { // (roots come first: a root is its body's first voxel)
+            const int r = find(v);
+            if (rank[r] < 0)
+                rank[r] = C.nBodies++;
+            comp[v] = r;
+        }
+        for (int v = 0; v < h.nv; v++)
+            comp[v] = rank[comp[v]];
+    }
+    // boxes of the bodies (or of the world) in bricks of dims[]; returns the number of brick cells of all boxes
+    int64_t brick_cut_boxes(const WorldHost &h, const BrickCut &C, bool perBody, const int dims[3], std::vector<int> &mnOut, int64_t nb[3]) const {
+        const auto &lat = staging.lat;
+        const int nc = perBody ? C.nBodies : 1;
+        mnOut.assign((size_t)nc * 3, 1 << 30);
+        std::vector<int> mxs((size_t)nc * 3, -(1 << 30));
+        for (int v = 0; v < h.nv; v++) {
+            const int c = perBody ? C.body[v] : 0;
+            for (int k = 0; k < 3; k++) {
+                const int x = (&lat[h.voff + v].x)[k];
+                mnOut[(size_t)c * 3 + k] = std::min(mnOut[(size_t)c * 3 + k], x);
+                mxs[(size_t)c * 3 + k] = std::max(mxs[(size_t)c * 3 + k], x);
+            }
+        }
+        nb[0] = nb[1] = nb[2] = 1;
+        int64_t total = 0;
+        for (int c = 0; c < nc; c++) {
+            int64_t cells = 1;
+            for (int k = 0; k < 3; k++) {
+                const int64_t e = (mxs[(size_t)c * 3 + k] - mnOut[(size_t)c * 3 + k]) / dims[k] + 1;
+                nb[k] = std::max(nb[k], e);
+                cells *= e;
+            }
+            total += cells;
+        }
+        return total;
+    }
+    // the cut of world h for bricks of dims[]: per body when that saves a fifth of the bricks (and the key space stays small)
+    void brick_cut_choose(const WorldHost &h, BrickCut &C, const int dims[3]) const {
+        std::vector<int> mnW, mnB;
+        int64_t nbW[3], nbB[3];
+        const int64_t cellsW = brick_cut_boxes(h, C, false, dims, mnW, nbW);
+        const int64_t cellsB = C.nBodies > 1 ? brick_cut_boxes(h, C, true, dims, mnB, nbB) : cellsW;
+        C.perBody = C.nBodies > 1 && cellsB * 5 < cellsW * 4 && (int64_t)C.nBodies * nbB[0] * nbB[1] * nbB[2] <= (int64_t)8 * h.nv + 4096;
+        C.mn = C.perBody ? mnB : mnW;
+        for (int k = 0; k < 3; k++) {
+            C.nb[k] = C.perBody ? nbB[k] : nbW[k];
+            C.d[k] = dims[k];
+        }
+    }
+
     // ---- k_brick plan (host only; kernels_brick.cuh): which worlds take the brick path, their voxels and links in brick order, the
     // per-brick descriptor / gather tables, and the brick size that fits the shared memory.  Part of upload(); reads the staging arrays
     // upload() has filled, marks the chosen worlds in hW[].brickOk.
@@ -301,13 +387,17 @@ template <class R> class Engine : public EngineBase {
             for (int oi = 0; oi < n; oi++) {
                 const int w = perm[oi];
                 const VX3B_WorldDesc &d = worlds[w];
-                const bool wanted = path == 5 || (path == 0 && pre[w].cls == 0);
-                if (!wanted || d.num_voxels == 0 || (pre[w].flags & (WF_COLLISION | WF_FORCE_FIELD)) || d.max_dist_in_voxel_lengths_to_count_as_pair != 0 ||
+                // (automatic path: worlds with voxel-voxel contact stay on k_fused - on the 265-body pile k_brick's COLL instantiation takes
+                // 49.8 us per step against k_fused's 46.1 with one 8x8x8 brick per body: 3.6 bricks per CTA leave the ring nothing to overlap,
+                // and every surface voxel costs three scattered stores into the API-order arrays; path = 5 asks for k_brick regardless)
+                const bool wanted = path == 5 || (path == 0 && pre[w].cls == 0 && !(pre[w].flags & WF_COLLISION));
+                if (!wanted || d.num_voxels == 0 || (pre[w].flags & WF_FORCE_FIELD) || (d.ghost && (pre[w].flags & WF_COLLISION)) || d.max_dist_in_voxel_lengths_to_count_as_pair != 0 ||
                     d.num_voxel_mats > BRICK_MAX_VMATS || d.num_link_mats > BRICK_MAX_LMATS)
                     continue;
                 bw.push_back(w);
             }
             int dims[3] = {brickDim[0], brickDim[1], brickDim[2]};
+            std::map<int, BrickCut> cuts; // per brick world: its connected bodies (found once), the cut for the current dims
             // one persistent CTA (512 threads, two-stage ring) may take the whole SM; small bricks leave room for two (256 threads each)
             const size_t limit = (size_t)smemOptin;
             while (!bw.empty()) {
@@ -320,24 +410,13 @@ template <class R> class Engine : public EngineBase {
                     const WorldD &W = hW[w];
                     caps.nvm = std::max(caps.nvm, W.nvm);
                     caps.nlm = std::max(caps.nlm, W.nlm);
-                    int mn[3] = {1 << 30, 1 << 30, 1 << 30};
-                    for (int v = 0; v < h.nv; v++)
-                        for (int k = 0; k < 3; k++)
-                            mn[k] = std::min(mn[k], (int)(&lat[h.voff + v].x)[k]);
-                    int mx[2] = {-(1 << 30), -(1 << 30)};
-                    for (int v = 0; v < h.nv; v++)
-                        for (int k = 0; k < 2; k++)
-                            mx[k] = std::max(mx[k], (int)(&lat[h.voff + v].x)[k]);
-                    const int64_t nbx = (mx[0] - mn[0]) / dims[0] + 1, nby = (mx[1] - mn[1]) / dims[1] + 1;
+                    BrickCut &cut = cuts[w];
+                    if (cut.body.empty())
+                        brick_cut_bodies(h, cut);
+                    brick_cut_choose(h, cut, dims);
                     std::vector<std::pair<int64_t, int>> keyed(h.nv); // (brick key, voxel): creation order inside a brick = x fastest
-                    int mxz = -(1 << 30);
-                    for (int v = 0; v < h.nv; v++)
-                        mxz = std::max(mxz, (int)lat[h.voff + v].z);
-                    const int64_t nbz = (mxz - mn[2]) / dims[2] + 1, nCells = nbx * nby * nbz;
-                    auto key_of = [&](int v) {
-                        const short4 c = lat[h.voff + v];
-                        return (((int64_t)(c.z - mn[2]) / dims[2]) * nby + (c.y - mn[1]) / dims[1]) * nbx + (c.x - mn[0]) / dims[0];
-                    };
+                    const int64_t nCells = cut.cells();
+                    auto key_of = [&](int v) { return cut.key(lat[h.voff + v], v); };
                     if (nCells <= (int64_t)4 * h.nv + 4096) {
                         // counting sort by brick: stable, so voxels keep their creation order (ascending index) inside a brick, which is
                         // what sorting the (key, index) pairs gives - at a tenth of the time on a million-voxel body
@@ -603,7 +682,18 @@ template <class R> class Engine : public EngineBase {
                         return VX3B_ERR_ARG;
                     }
             }
+            brickColl = false;
             for (int w : bw) {
+                if (pre[w].flags & WF_COLLISION) { // voxel-voxel contact on the brick path: where the reference voxel of the stale-list check sits
+                    brickColl = true;
+                    const int g = hW[w].ns > 0 ? staging.surf[hW[w].soff + (hW[w].ns >> 1)] : -1;
+                    hW[w].gRefSlot = 0;
+                    for (size_t sl = 0; sl < bh.borig.size(); sl++)
+                        if (bh.borig[sl] == g) {
+                            hW[w].gRefSlot = (int32_t)sl;
+                            break;
+                        }
+                }
                 hW[w].brickOk = 1;
                 if (pre[w].flags & (WF_VARY_TEMP | WF_THERMAL | WF_CILIA))
                     brickLean = false;
@@ -646,86 +736,25 @@ template <class R> class Engine : public EngineBase {
                 const WorldHost &h = H[w];
                 if (h.nv == 0)
                     continue;
-                // brick key of every voxel; voxels of a brick stay in creation order (x runs are contiguous in memory).
-                // Bricks are cut per connected body when that gives fewer of them: a scene of many bodies (BASELINE configs[3]: 8^3 cubes on
-                // a 9-cell pitch) cut on ONE world-wide grid fills its bricks to 58 %; cut from each body's own corner, every brick is full.
-                std::vector<int32_t> comp(h.nv);
-                for (int v = 0; v < h.nv; v++)
-                    comp[v] = v;
-                auto find = [&](int v) {
-                    while (comp[v] != v)
-                        v = comp[v] = comp[comp[v]];
-                    return v;
-                };
-                for (int l = 0; l < h.nl; l++) {
-                    const int a = find(lends[h.loff + l].x - h.voff), b = find(lends[h.loff + l].y - h.voff);
-                    if (a != b)
-                        comp[std::max(a, b)] = std::min(a, b); // the root is the component's first voxel
-                }
-                std::vector<int32_t> rank(h.nv, -1); // component number, in order of the first voxel
-                int nComp = 0;
-                for (int v = 0; v < h.nv; v++) {
-                    const int r = find(v);
-                    if (rank[r] < 0)
-                        rank[r] = nComp++;
-                    comp[v] = r;
-                }
-                auto count_bricks = [&](bool perBody, std::vector<int> &mnOut, int ext[3], int BZ) -> int64_t {
-                    const int nc = perBody ? nComp : 1;
-                    mnOut.assign((size_t)nc * 3, 1 << 30);
-                    std::vector<int> mxs((size_t)nc * 3, -(1 << 30));
-                    for (int v = 0; v < h.nv; v++) {
-                        const int c = perBody ? rank[comp[v]] : 0;
-                        for (int k = 0; k < 3; k++) {
-                            const int x = (&lat[h.voff + v].x)[k];
-                            mnOut[(size_t)c * 3 + k] = std::min(mnOut[(size_t)c * 3 + k], x);
-                            mxs[(size_t)c * 3 + k] = std::max(mxs[(size_t)c * 3 + k], x);
-                        }
-                    }
-                    const int bd[3] = {BX, BY, BZ};
-                    ext[0] = ext[1] = ext[2] = 1;
-                    int64_t total = 0; // upper bound of the bricks in use: cells of every body's own box
-                    for (int c = 0; c < nc; c++) {
-                        int64_t cells = 1;
-                        for (int k = 0; k < 3; k++) {
-                            const int e = (mxs[(size_t)c * 3 + k] - mnOut[(size_t)c * 3 + k]) / bd[k] + 1;
-                            ext[k] = std::max(ext[k], e);
-                            cells *= e;
-                        }
-                        total += cells;
-                    }
-                    return total;
-                };
-                std::vector<int> mnWorld, mnBody;
-                int extWorld[3], extBody[3];
-                const int64_t cellsWorld = count_bricks(false, mnWorld, extWorld, BZ);
-                int64_t cellsBody = nComp > 1 ? count_bricks(true, mnBody, extBody, BZ) : cellsWorld;
-                // bodies that fit ONE brick of twice the height (the pile's 8^3 cubes in 8x8x8 bricks): no link is cut by a brick face, so
-                // nothing is recomputed and nothing gathered; 2.72e9 -> 2.93e9 voxel-steps/s on the pile
-                if (nComp > 1 && BX * BY * BZ * 2 <= 512) {
-                    std::vector<int> mn2;
-                    int ext2[3];
-                    const int64_t cells2 = count_bricks(true, mn2, ext2, 2 * BZ);
-                    if (cells2 == nComp && cellsBody > nComp) {
-                        BZ = 2 * BZ;
-                        cellsBody = cells2;
-                        mnBody = mn2;
-                        for (int k = 0; k < 3; k++)
-                            extBody[k] = ext2[k];
-                    }
+                // brick key of every voxel (BrickCut: one grid from the world's corner, or per connected body); voxels of a brick stay in
+                // creation order (x runs are contiguous in memory)
+                BrickCut cut;
+                brick_cut_bodies(h, cut);
+                int dims[3] = {BX, BY, BZ};
+                if (cut.nBodies > 1 && BX * BY * BZ * 2 <= 512) {
+                    // bodies that fit ONE brick of twice the height (the pile's 8^3 cubes in 8x8x8 bricks): no link is cut by a brick face, so
+                    // nothing is recomputed and nothing gathered; 2.72e9 -> 2.93e9 voxel-steps/s on the pile
+                    std::vector<int> mnTmp;
+                    int64_t nbTmp[3];
+                    const int d2[3] = {BX, BY, 2 * BZ};
+                    if (brick_cut_boxes(h, cut, true, d2, mnTmp, nbTmp) == cut.nBodies && brick_cut_boxes(h, cut, true, dims, mnTmp, nbTmp) > cut.nBodies)
+                        dims[2] = BZ = 2 * BZ;
                 }
                 fusedBZ = BZ;
-                const bool perBody = nComp > 1 && cellsBody * 5 < cellsWorld * 4 && (int64_t)nComp * extBody[0] * extBody[1] * extBody[2] <= (int64_t)8 * h.nv + 4096;
-                const std::vector<int> &mnUse = perBody ? mnBody : mnWorld;
-                const int64_t nbx = perBody ? extBody[0] : extWorld[0], nby = perBody ? extBody[1] : extWorld[1], nbz = perBody ? extBody[2] : extWorld[2];
+                brick_cut_choose(h, cut, dims);
                 std::vector<std::pair<int64_t, int>> keyed(h.nv);
-                auto key_of = [&](int v) {
-                    const short4 c = lat[h.voff + v];
-                    const int64_t body = perBody ? rank[comp[v]] : 0;
-                    const int *mn = &mnUse[(size_t)body * 3];
-                    return ((body * nbz + (c.z - mn[2]) / BZ) * nby + (c.y - mn[1]) / BY) * nbx + (c.x - mn[0]) / BX;
-                };
-                const int64_t nCells = (perBody ? (int64_t)nComp : 1) * nbx * nby * nbz;
+                auto key_of = [&](int v) { return cut.key(lat[h.voff + v], v); };
+                const int64_t nCells = cut.cells();
                 if (nCells <= (int64_t)4 * h.nv + 4096) { // stable counting sort by brick (= sorting the (key, index) pairs, much cheaper)
                     std::vector<int32_t> start((size_t)nCells + 1, 0);
                     for (int v = 0; v < h.nv; v++)
@@ -1569,6 +1598,17 @@ template <class R> class Engine : public EngineBase {
             BA.lorig = dLO;
             BA.ldesc = dD;
             BA.bstat = dS;
+            if (brickColl) { // brick-order slot -> global surface slot
+                std::vector<int32_t> bsurf(bh.borig.size(), -1);
+                for (size_t sl = 0; sl < bsurf.size(); sl++)
+                    if (bh.borig[sl] >= 0)
+                        bsurf[sl] = staging.vsurf[bh.borig[sl]];
+                int32_t *dBS = nullptr;
+                if ((rc = dalloc(&dBS, bsurf.size(), bsurf.data())) != VX3B_OK)
+                    return rc;
+                CUDA_TRY(cudaStreamSynchronize(stream)); // (the staging vector dies here)
+                BA.bsurf = dBS;
+            }
             int32_t *dWL = nullptr;
             int *dTicket = nullptr;
             if ((rc = dalloc(&dWL, brickWorldList.size(), brickWorldList.data())) != VX3B_OK || (rc = dalloc(&dTicket, 1)) != VX3B_OK)
@@ -1602,6 +1642,8 @@ template <class R> class Engine : public EngineBase {
             CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
             CUDA_TRY(cudaFuncSetAttribute(k_brick<R, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
             CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+            CUDA_TRY(cudaFuncSetAttribute(k_brick<R, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
             // persistent grid: as many CTAs as fit at once, each stepping consecutive bricks in chunks
             int numSm = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&numSm, cudaDevAttrMultiProcessorCount, dev));
@@ -1694,7 +1736,7 @@ template <class R> class Engine : public EngineBase {
             FusedArrays F = FA;
             F.bricks += b0;
             // every world this step touches is a brick world: k_brick's last CTA does the end-of-step bookkeeping itself
-            brickDoesWorldStep = BA.nBricks > 0 && FA.nBricks <= b0 && !anyCollision && nBrickWorlds == (mixed ? (int)H.size() - numResident : (int)H.size());
+            brickDoesWorldStep = BA.nBricks > 0 && FA.nBricks <= b0 && nBrickWorlds == (mixed ? (int)H.size() - numResident : (int)H.size());
             if (FA.nBricks > b0) {
                 k_fused<R><<<(unsigned)(FA.nBricks - b0), 256, fusedSmem, stream>>>(A, F, fusedCapTab, fusedCapOwn, G);
                 launches++;
@@ -1706,6 +1748,11 @@ template <class R> class Engine : public EngineBase {
                         k_brick<R, true, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive, peer);
                     else
                         k_brick<R, false, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive, peer);
+                } else if (brickColl) { // voxel-voxel contact: contact force in, surface voxels mirrored out, stale-list check of the grid G
+                    if (brickLean)
+                        k_brick<R, true, false, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive, BrickPeer<R>{}, G);
+                    else
+                        k_brick<R, false, false, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive, BrickPeer<R>{}, G);
                 } else if (brickLean)
                     k_brick<R, true><<<(unsigned)brickGrid, brickThreads, brickSmem, stream>>>(A, BA, brickLayout, ws, useStop, dActive);
                 else

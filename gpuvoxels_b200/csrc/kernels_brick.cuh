@@ -27,6 +27,7 @@
 // (VX3/VX3_VoxelyzeKernel.cu:566-650, 846-859) for large worlds.  Same deliberate difference as k_fused on divergence.
 #pragma once
 #include "engine.cuh"
+#include "kernels_contact.cuh"
 #include "kernels_stream.cuh"
 
 namespace vx3b {
@@ -65,6 +66,7 @@ template <class R> struct BrickArrays {
     const int32_t *glist;    // gather lists (brick-order voxel slots, then link slots)
     const uint32_t *bstat;   // per brick-order voxel slot: world-local material | link mask << 8 | has boundary conditions << 14 | ghost << 15
     const int32_t *borig;    // brick-order voxel slot -> global (API-order) voxel index, -1 for alignment padding
+    const int32_t *bsurf;    // brick-order voxel slot -> global surface slot or -1 (allocated when a brick world has voxel-voxel contact)
     const int32_t *lorig;    // brick-order link slot -> global link index
     BrickSet<R> set[2];
     int nvSlots, nlSlots;
@@ -220,6 +222,7 @@ template <class R> __device__ __noinline__ void brick_world_step(WorldD *worlds,
         if (!W.active || !(W.flags & WF_BRICK))
             continue;
         W.parity ^= 1;
+        cgrid_end_of_step(W);
         // fields other CTAs of the still-running kernel wrote - divergedNow with plain stores, comAcc with atomics - are fetched with
         // atomics and stored back, so that the plain loads of the bookkeeping code cannot be served from a stale L1 line of this SM
         // (a thread always sees its own stores)
@@ -235,8 +238,12 @@ template <class R> __device__ __noinline__ void brick_world_step(WorldD *worlds,
     }
 }
 
-template <class R, bool LEAN, bool PEER = false>
-__global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L, int worldStep, int useStop, int *activeCount, const BrickPeer<R> P = BrickPeer<R>{}) {
+// COLL: some brick world has voxel-voxel contact.  The contact kernels (kernels_contact.cuh, k_contact) run before this one and read
+// SURFACE voxels from the main (API-order) arrays: the voxel pass takes a surface voxel's contact force from A.contactF, mirrors its new
+// position and linear momentum into the main arrays, and does the stale-list check of the global contact grid G.
+template <class R, bool LEAN, bool PEER = false, bool COLL = false>
+__global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArrays<R> BA, const BrickLayout<R> L, int worldStep, int useStop, int *activeCount, const BrickPeer<R> P = BrickPeer<R>{},
+                                                          const ContactGrid G = ContactGrid{}) {
     using T4 = typename Store<R>::T4;
     using T2 = typename Store<R>::T2;
     extern __shared__ __align__(128) unsigned char smem_brick[];
@@ -284,6 +291,8 @@ __global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArray
     double voxSize = 0;
     BrickSet<R> src = BA.set[0], dst = BA.set[1];
     WorldD *Wp = nullptr;
+    [[maybe_unused]] bool gridCheck = false; // COLL: this world's candidate lists live in the global contact grid G
+    [[maybe_unused]] double refX = 0, refY = 0, refZ = 0; // ... and the position of its reference voxel at the start of the step
 
     // Fill stage `s` with brick B: bulk copies of its runs (+ the gather list of the brick after it, `next`, into its list slot)
     // on the stage's mbarrier by thread 0, halo gathers by everybody.  idx: the brick's gather list (shared or global memory).
@@ -382,6 +391,13 @@ __global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArray
                 dst.pxy = par ? s0.pxy : s1.pxy, dst.pzt = par ? s0.pzt : s1.pzt, dst.orient = par ? s0.orient : s1.orient;
                 dst.lm = par ? s0.lm : s1.lm, dst.am = par ? s0.am : s1.am;
                 dst.lpos2 = par ? s0.lpos2 : s1.lpos2, dst.la1 = par ? s0.la1 : s1.la1, dst.la2 = par ? s0.la2 : s1.la2;
+                if constexpr (COLL) {
+                    gridCheck = G.nBuckets > 0 && (wflags & WF_COLLISION) && W.gridLog2 > 0 && W.soff >= G.s0;
+                    if (gridCheck) { // from the source set, which no thread writes during this launch
+                        const D2 ra = src.pxy[W.gRefSlot], rb = src.pzt[W.gRefSlot];
+                        refX = ra.x, refY = ra.y, refZ = rb.x;
+                    }
+                }
                 if (active) {
                     __syncthreads(); // nobody still reads the previous world's tables
                     const uint32_t *gv = (const uint32_t *)(A.vmats + W.vmatOff), *gl = (const uint32_t *)(A.lmats + W.lmatOff);
@@ -568,12 +584,31 @@ __global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArray
                         v.pos = {pxy.x, pxy.y, pzt.x};
                         v.linMom = {lm.x, lm.y, lm.z};
                         const V3<R> zero{R(0), R(0), R(0)};
-                        const bool sf = voxel_translate<R, true>(m, wp, nullptr, v, sum_slots(0), zero, zero);
+                        V3<R> contact = zero;
+                        [[maybe_unused]] int ss = -1;
+                        if constexpr (COLL)
+                            if (wflags & WF_COLLISION) {
+                                ss = BA.bsurf[vs];
+                                if (ss >= 0) {
+                                    const auto c = A.contactF[ss];
+                                    contact = {c.x, c.y, c.z};
+                                }
+                            }
+                        const bool sf = voxel_translate<R, !COLL>(m, wp, nullptr, v, sum_slots(0), contact, zero); // (PLAIN ignores the contact force)
                         const uint32_t fl = (sf ? VF_STATIC_FRICTION : 0u) | (voxel_zero_angmom(m, wp, sf, v.temp, v.pos.z) ? VF_ZERO_ANGMOM : 0u);
                         dst.pxy[vs] = D2{v.pos.x, v.pos.y};
                         const unsigned long long b2 = ((unsigned long long)fl << 32) | (unsigned long long)f2u(v.temp);
                         dst.pzt[vs] = D2{v.pos.z, __longlong_as_double((long long)b2)};
                         dst.lm[vs] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
+                        if constexpr (COLL)
+                            if (ss >= 0) { // what the contact kernels of the next step read, and: are the candidate lists stale?
+                                const int g = A.surf[ss];
+                                A.pxy[g] = D2{v.pos.x, v.pos.y};
+                                A.pzt[g] = D2{v.pos.z, __longlong_as_double((long long)b2)};
+                                A.lm[g] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
+                                if (gridCheck)
+                                    cgrid_check_one(*Wp, G, ss, v.pos.x, v.pos.y, v.pos.z, refX, refY, refZ);
+                            }
                         if constexpr (PEER) {
                             if (stw & BS_SEND_LO) {
                                 const int rs = P.sendLo[vs];
@@ -612,11 +647,20 @@ __global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArray
                 v.angMom = (v.flags & VF_ZERO_ANGMOM) ? V3<R>{R(0), R(0), R(0)} : V3<R>{am.x, am.y, am.z};
                 v.flags &= VF_STATIC_FRICTION;
                 bool fixedMat = ghost;
+                [[maybe_unused]] int ssG = -1;
                 if constexpr (!LEAN)
                     fixedMat = ghost || (vx3 && m.fixed);
                 if (!fixedMat) {
                     const V3<R> F = sum_slots(0), M = sum_slots(3);
                     V3<R> contact{R(0), R(0), R(0)}, cilia{R(0), R(0), R(0)};
+                    if constexpr (COLL)
+                        if (wflags & WF_COLLISION) {
+                            ssG = BA.bsurf[vs];
+                            if (ssG >= 0) {
+                                const auto c = A.contactF[ssG];
+                                contact = {c.x, c.y, c.z};
+                            }
+                        }
                     VoxExt ext;
                     const VoxExt *pe = nullptr;
                     V3<double> nominal{0, 0, 0};
@@ -638,7 +682,7 @@ __global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArray
                             pe = &ext;
                         }
                     }
-                    voxel_update<R, LEAN>(m, wp, pe, nominal, v, F, M, contact, cilia);
+                    voxel_update<R, LEAN && !COLL>(m, wp, pe, nominal, v, F, M, contact, cilia);
                     if constexpr (!LEAN) {
                         const WorldD &W = *Wp;
                         if ((wflags & WF_VARY_TEMP) && W.tempPeriod > 0) { // temperature the next step will see (start-of-step time t+dt)
@@ -653,6 +697,15 @@ __global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArray
                 dst.orient[vs] = mk4<R>(v.orient.w, v.orient.x, v.orient.y, v.orient.z);
                 dst.lm[vs] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
                 dst.am[vs] = mk4<R>(v.angMom.x, v.angMom.y, v.angMom.z, R(0));
+                if constexpr (COLL)
+                    if (ssG >= 0) {
+                        const int g = A.surf[ssG];
+                        A.pxy[g] = D2{v.pos.x, v.pos.y};
+                        A.pzt[g] = D2{v.pos.z, __longlong_as_double((long long)b2)};
+                        A.lm[g] = mk4<R>(v.linMom.x, v.linMom.y, v.linMom.z, R(0));
+                        if (gridCheck)
+                            cgrid_check_one(*Wp, G, ssG, v.pos.x, v.pos.y, v.pos.z, refX, refY, refZ);
+                    }
                 if constexpr (PEER) {
                     if (stw & BS_SEND_LO) {
                         const int rs = P.sendLo[vs];

@@ -88,7 +88,7 @@ template <class R> __global__ void __launch_bounds__(256) k_cgrid_insert(Arrays<
     WorldD &W = A.worlds[w];
     if (!W.gRebuild)
         return;
-    const StateSet<R> cur = cur_set(A, W.parity);
+    const StateSet<R> cur = contact_set(A, W);
     const D2 a = cur.pxy[v], b = cur.pzt[v];
     const uint32_t key = cgrid_key(a.x, a.y, b.x, W.invCell);
     G.key[s] = key;
@@ -114,7 +114,7 @@ template <class R> __global__ void __launch_bounds__(128) k_cgrid_narrow(Arrays<
     if (s >= A.nsTot || !cgrid_world(A, s, w, v, i))
         return;
     WorldD &W = A.worlds[w];
-    const StateSet<R> cur = cur_set(A, W.parity);
+    const StateSet<R> cur = contact_set(A, W);
     const D2 a = cur.pxy[v], b = cur.pzt[v];
     const short4 c1 = A.lat[v];
     const DVoxMat &m1 = A.vmats[A.vmat[v]];

@@ -137,7 +137,7 @@ template <class R> __global__ void __launch_bounds__(128) k_contact(Arrays<R> A,
     const int i = ct.first + threadIdx.x; // local surface index
     SurfRec<R> me;
     const bool have = i < ns;
-    const StateSet<R> cur = cur_set(A, W.parity);
+    const StateSet<R> cur = contact_set(A, W);
     auto load = [&](int slot) {
         SurfRec<R> r;
         int v = A.surf[soff + slot];

@@ -291,7 +291,7 @@ def test_million_voxel_body_properties():
     assert abs((r.current_com[2] - r.initial_com[2]) - dz64.mean()) < 1e-9
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 def test_contact_force_matches_the_frozen_reference_run(path):
     """The engine's contact force against the UNMODIFIED reference's own collision system on the two-voxel drop
     (tests/golden/two_body_drop_vx2col.vxbin, tests/golden/make_golden.py two_body): impact, bounce and rest."""
@@ -306,7 +306,7 @@ def test_contact_force_matches_the_frozen_reference_run(path):
             ctx.close()
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 def test_multi_pair_contact_matches_the_frozen_reference_run(path):
     """A block landing on two pebbles (tests/golden/block_on_pebbles_vx2col.vxbin = the unmodified reference with its own
     collision system): the engine in fp64 against it, several watched pairs at once, contact + floor friction, 2,000 steps."""
@@ -320,7 +320,7 @@ def test_multi_pair_contact_matches_the_frozen_reference_run(path):
         ctx.close()
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 def test_vx3_cilia_body_pushing_a_target_matches_the_frozen_reference_run(path):
     """VX3 semantics with cilia, a target hit counter, contact and floor friction against the reference (harness --vx3 + its own
     collision system, tests/golden/cilia_pusher_vx3_vx2col.vxbin): the engine in fp64, 4,000 steps, 1.4 m of travel."""
@@ -417,7 +417,7 @@ def test_brick_path_rounds_world_switches_and_empty_worlds():
 
 
 @pytest.mark.parametrize("precision", [gv.FP64, gv.FP32])
-@pytest.mark.parametrize("path", [STREAM, FUSED])
+@pytest.mark.parametrize("path", [STREAM, FUSED, BRICK])
 def test_grid_broad_phase_equals_the_all_pairs_scan_bit_for_bit(path, precision):
     """Big worlds find their contacts through the global-memory uniform grid + candidate lists (kernels_contact.cuh) instead of
     the reference's all-pairs scan.  Candidates are visited in the all-pairs order and the predicate is the same, so forces -

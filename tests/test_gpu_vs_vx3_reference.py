@@ -87,7 +87,7 @@ CONTACT_CASES = [("vx3ref_xeno7_contact_500", (100, 300, 500)), ("vx3ref_pile_k3
                 [(f"vx3ref_circle_push_{b}_1000", (300, 1000)) for b in CIRCLE_PUSH_BOTS]
 
 
-@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED])
+@pytest.mark.parametrize("path", [STREAM, RESIDENT, FUSED, BRICK])
 @pytest.mark.parametrize("name,checkpoints", CONTACT_CASES, ids=[c[0][7:] for c in CONTACT_CASES])
 def test_contact_worlds_fp64_against_the_vx3_reference(name, checkpoints, path):
     """Worlds WITH contact inside the body (thermally contracted xenobots bring their own diagonal neighbours inside the watch
@@ -122,7 +122,7 @@ def test_contact_worlds_fp32_against_the_vx3_reference(name):
     vxa, vxd, _, _, _ = CASES[name]
     g = gold(name)
     m = gv.Model.from_vxa(vxa, vxd)
-    for path in (STREAM, RESIDENT, FUSED):
+    for path in (STREAM, RESIDENT, FUSED, BRICK):
         ctx = gpu_run([m], 300, gv.FP32, path, record_pairs=1)
         got = ctx.read_state(0)
         assert np.abs(got["pos"] - g["pos_300"]).max() / disp_scale(m, g["pos_300"]) < 1e-3, path
