@@ -114,6 +114,10 @@ template <class R> __global__ void __launch_bounds__(128) k_cgrid_narrow(Arrays<
     if (s >= A.nsTot || !cgrid_world(A, s, w, v, i))
         return;
     WorldD &W = A.worlds[w];
+    if (!W.gRebuild && G.count[s] == 0) { // most surface voxels of a scene touch nothing: no candidates, no force, nothing else to load
+        A.contactF[s] = mk4<R>(R(0), R(0), R(0), R(0));
+        return;
+    }
     const StateSet<R> cur = contact_set(A, W);
     const D2 a = cur.pxy[v], b = cur.pzt[v];
     const short4 c1 = A.lat[v];
