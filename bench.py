@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--workloads", default="all", help="N = 1, default workload only: also measure these other BASELINE configs into a \"workloads\" block "
                     "(all | none | comma list of cube100,pile,xenobot_fp64)")
     ap.add_argument("--slab-cube", type=int, default=160, help="N > 1: edge of the ONE body also stepped as N slabs into a \"slab\" block (0 = skip)")
+    ap.add_argument("--first-world", type=int, default=0, help="xenobot workload: index of rank 0's first world (rank r of a multi-GPU run takes worlds first + r * worlds ...)")
     ap.add_argument("--gen-parts", type=int, default=6, help="e2e of a many-world generation: sub-batches of the pipelined runner vx3b_gen_run (1 = plain upload + run + results)")
     ap.add_argument("--slab-sim-steps", type=int, default=200)
     ap.add_argument("--slab-exchange", default="fused", choices=["fused", "device", "nccl"],
@@ -173,7 +174,20 @@ def world_texts(args, rank):
     if args.workload == "pile":
         return [(W.contact_pile_vxa(k=args.pile, cube=8), None)]
     base = W.xenobot_base_vxa()
-    return [(base, W.xenobot_vxd(rank * args.worlds + i)) for i in range(args.worlds)]
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    if world == 1:
+        return [(base, W.xenobot_vxd(args.first_world + i)) for i in range(args.worlds)]
+    # a generation over several GPUs is dealt by cost, longest-processing-time-first, as vx3b_job_run deals a directory over its devices
+    # (vx3b_shard_worlds; every rank computes the same deal): contiguous index ranges differ by 9 % in run time (worlds 1,024-2,047
+    # take 92.8 ms where worlds 0-1,023 take 85.2), which a max over ranks then reports as lost scaling
+    import ctypes as C
+    import gpuvoxels_b200 as gv
+    n = world * args.worlds
+    cost = (C.c_int64 * n)(*[W.xenobot_cost(args.first_world + i) for i in range(n)])
+    shard = (C.c_int32 * n)()
+    if gv.lib().vx3b_shard_worlds(cost, n, world, shard) != 0:
+        raise RuntimeError("vx3b_shard_worlds failed")
+    return [(base, W.xenobot_vxd(args.first_world + i)) for i in range(n) if shard[i] == rank]
 
 
 def oracle_port_sample(models, sim_steps):

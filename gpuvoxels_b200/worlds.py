@@ -207,6 +207,15 @@ def xenobot_vxd(index, pebbles=True):
     return "<VXD>" + structure_xml(data, base_cilia=cilia, replace="VXA.VXC.Structure") + "</VXD>"
 
 
+def xenobot_cost(index):
+    """Estimated cost (voxels + 2 x links) of the body xenobot_vxd(index) builds, from its fill probability alone (the first draw of
+    the world's generator): what a driver needs to deal a generation to devices by cost before any world is built.  (A job that has
+    the models in hand uses their real counts: csrc/job.cpp.)"""
+    p = np.random.default_rng(1000 + index).uniform(0.35, 0.75)
+    cells = XENOBOT_DIMS[0] * 12 * 12
+    return int(cells * p + 2 * 3 * cells * p * p)
+
+
 def two_body_drop_vxa():
     """One voxel resting on the floor and a second one dropped onto it from two cells up: the smallest scene with a watched
     contact pair (the reference's TEST(CVoxelyze, collisions), VoxCAD/src/VX2/test/tVoxelyze.h:1167-1197, as a VXA)."""
