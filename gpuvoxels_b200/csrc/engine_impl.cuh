@@ -1830,6 +1830,10 @@ template <class R> class Engine : public EngineBase {
     // every size class on its own stream, all of them ordered after k_world_begin and before the final reductions
     int run_resident(int64_t maxSteps, int useStop) {
         CUDA_TRY(cudaEventRecord(evBegin, stream));
+        // (classes are launched as built: the most expensive worlds first.  Reversed, or with the several-per-SM classes first, the run
+        // time of a 1,024-world shard moves by +-5 % either way depending on the shard - 85.1 / 92.7 / 87.8 / 90.1 ms as built, 85.6 /
+        // 88.5 / 92.4 / 88.0 reversed on four shards - : how the block scheduler packs CTAs of different shared-memory size decides
+        // the tail, not the order)
         for (auto &c : classes) {
             CUDA_TRY(cudaStreamWaitEvent(c.stream, evBegin, 0));
             int rc = resident_launch<R>(A, c, maxSteps, useStop, recordPairs);
