@@ -265,7 +265,9 @@ __global__ void __launch_bounds__(BRICK_MAXT, 1) k_brick(Arrays<R> A, BrickArray
         if (tid == 0) {
             const unsigned long long want = P.sync->seq, t0 = halo_now_ns();
             bool ok = true;
-            while ((P.myLo && *(const volatile unsigned long long *)P.myLo < want) || (P.myHi && *(const volatile unsigned long long *)P.myHi < want)) {
+            // (after one timeout the run is invalid anyway: later launches do not wait again, so a dead neighbour costs 10 s, not 10 s per step)
+            while (P.sync->timeouts == 0 &&
+                   ((P.myLo && *(const volatile unsigned long long *)P.myLo < want) || (P.myHi && *(const volatile unsigned long long *)P.myHi < want))) {
                 __nanosleep(64);
                 if (halo_now_ns() - t0 > 10000000000ull) { // 10 s: a neighbour is gone; never hang the device
                     ok = false;
@@ -944,7 +946,7 @@ template <class R> __global__ void __launch_bounds__(HALO_THREADS) k_halo_pull(A
         ok = 1;
         if (cnt > 0) {
             const unsigned long long t0 = halo_now_ns();
-            while (*(const volatile unsigned long long *)S.flag < want) {
+            while (S.sync->timeouts == 0 && *(const volatile unsigned long long *)S.flag < want) { // (one timeout ends the waiting for good)
                 __nanosleep(100);
                 if (halo_now_ns() - t0 > 10000000000ull) { // 10 s: the neighbour is gone; never hang the device
                     ok = 0;

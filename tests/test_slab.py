@@ -238,6 +238,28 @@ def test_device_side_exchange_equals_the_whole_body_bit_for_bit(precision, n_par
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [True, False])
+def test_a_neighbour_that_never_steps_is_reported_not_hung_on(fused):
+    """the wait for a neighbour's flag gives up after 10 s - once: later launches do not wait again - and the run is flagged invalid"""
+    import time
+    import torch
+    vxa = W.cube_vxa(6)
+    parts = [slab.native_part(vxa, None, r, 2) for r in range(2)]
+    runners = [slab.SlabRunner(p, 0, gv.FP32, p.body_dt, None, stream=torch.cuda.Stream(0)) for p in parts]
+    eps = [r.open_endpoints() for r in runners]
+    runners[0].connect(None, eps[1]["lo"], same_process=True, fused=fused)
+    runners[1].connect(eps[0]["hi"], None, same_process=True, fused=fused)
+    t0 = time.time()
+    runners[0].run(5)  # slab 1 never runs
+    torch.cuda.synchronize()
+    assert 8 < time.time() - t0 < 25
+    assert runners[0].ctx.halo_timeouts() >= 1
+    assert runners[0].ctx.results()[0].steps == 5
+    for r in runners:
+        r.close()
+
+
+@pytest.mark.gpu
 def test_asynchronous_runs_keep_state_in_brick_order_until_read_back():
     """vx3b_batch_run_async leaves the state in the engine's internal order; any read-back must synchronise it, and mixing
     asynchronous and synchronous runs must give what one synchronous run gives."""
