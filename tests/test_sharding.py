@@ -56,6 +56,31 @@ def _worker(rank, world, port, q):
     q.put((rank, mine, merged))
 
 
+def test_bench_deals_a_generation_to_its_ranks_by_cost(monkeypatch):
+    """bench.py --gpus N: every rank computes the same longest-processing-time-first deal (vx3b_shard_worlds on the generator's cost
+    estimate) and takes its own share - a disjoint cover of the generation with near-equal cost per rank; N = 1 keeps the plain range"""
+    import argparse
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    import bench
+    a = argparse.Namespace(workload="xenobot", worlds=24, first_world=7, cube=100, pile=12)
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    one = bench.world_texts(a, 0)
+    assert [d for _, d in one] == [W.xenobot_vxd(7 + i) for i in range(24)]
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    everything = {W.xenobot_vxd(7 + i): W.xenobot_cost(7 + i) for i in range(96)}
+    seen, costs = set(), []
+    for rank in range(4):
+        mine = [d for _, d in bench.world_texts(a, rank)]
+        assert not seen & set(mine)
+        seen |= set(mine)
+        costs.append(sum(everything[d] for d in mine))
+    assert seen == set(everything)
+    assert max(costs) - min(costs) <= max(everything.values())  # LPT: no rank is ahead of another by more than one world
+    est = [W.xenobot_cost(i) for i in range(40)]
+    real = [m.num_voxels + 2 * m.num_links for m in (gv.Model.from_vxa(W.xenobot_base_vxa(), W.xenobot_vxd(i)) for i in range(40))]
+    assert np.corrcoef(est, real)[0, 1] > 0.95  # the estimate ranks worlds like their real size does
+
+
 def test_two_ranks_shard_and_merge_a_generation():
     import torch.multiprocessing as mp
     s = socket.socket()
