@@ -1542,17 +1542,25 @@ template <class R> class Engine : public EngineBase {
         if (gridBuckets > 0) {
             const size_t cover = surf.size() - (size_t)sCover0; // arrays are indexed by absolute surface slot: pointers are pre-offset
             unsigned long long *dHead = nullptr; // zero-filled: epoch 0, which no world ever has
-            int32_t *dNext = nullptr, *dList = nullptr, *dCount = nullptr;
-            uint32_t *dKey = nullptr;
+            int32_t *dList = nullptr, *dCount = nullptr;
+            int2 *dLink = nullptr;
             float4 *dRef = nullptr;
-            if ((rc = dalloc(&dHead, gridBuckets)) != VX3B_OK || (rc = dalloc(&dNext, cover)) != VX3B_OK || (rc = dalloc(&dKey, cover)) != VX3B_OK ||
-                (rc = dalloc(&dRef, cover)) != VX3B_OK || (rc = dalloc(&dList, cover * CGRID_CAP)) != VX3B_OK || (rc = dalloc(&dCount, cover)) != VX3B_OK)
+            short4 *dSlat = nullptr;
+            std::vector<short4> slat(cover); // static: lattice index of every covered surface voxel, w = its material is Fixed
+            for (size_t k = 0; k < cover; k++) {
+                const int g = surf[(size_t)sCover0 + k];
+                slat[k] = lat[g];
+                slat[k].w = vmats[vmat[g]].fixed ? 1 : 0;
+            }
+            if ((rc = dalloc(&dHead, gridBuckets)) != VX3B_OK || (rc = dalloc(&dLink, cover)) != VX3B_OK || (rc = dalloc(&dRef, cover)) != VX3B_OK ||
+                (rc = dalloc(&dList, cover * CGRID_CAP)) != VX3B_OK || (rc = dalloc(&dCount, cover)) != VX3B_OK || (rc = dalloc(&dSlat, cover, slat.data())) != VX3B_OK)
                 return rc;
+            CUDA_TRY(cudaStreamSynchronize(stream)); // (the staging vector dies here)
             CG.s0 = sCover0;
             CG.head = dHead;
-            CG.next = dNext - sCover0;
-            CG.key = dKey - sCover0;
+            CG.link = dLink - sCover0;
             CG.ref = dRef - sCover0;
+            CG.slat = dSlat - sCover0;
             CG.list = dList - (size_t)sCover0 * CGRID_CAP;
             CG.count = dCount - sCover0;
             CG.cap = contactListCap > 0 ? std::min((int)CGRID_CAP, contactListCap) : (int)CGRID_CAP;

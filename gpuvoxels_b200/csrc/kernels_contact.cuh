@@ -29,9 +29,11 @@ enum { CGRID_CAP = 32 }; // candidates per surface voxel (12 face + 8 body diago
 struct ContactGrid {
     int s0;              // first surface slot of the streaming-only worlds (the kernels cover [s0, nsTot))
     unsigned long long *head; // [sum of buckets] epoch << 32 | first surface slot (world-local) of the bucket; another epoch than the world's = empty
-    int32_t *next;       // [nsTot] chain
-    uint32_t *key;       // [nsTot] packed cell of the voxel at the last rebuild
+    int2 *link;          // [nsTot] {next slot of the bucket's chain or -1, packed cell of the voxel at the last rebuild}
     float4 *ref;         // [nsTot] position at the last rebuild
+    const short4 *slat;  // [nsTot] static: lattice index of the surface voxel, w = its material is Fixed.  A chain element is judged from
+                         // link / ref / slat, three INDEPENDENT loads by surface slot (the list build used to chase five dependent ones
+                         // per candidate: next -> key -> surface voxel -> lattice -> position; 80 us per rebuild on the 78,440-surface-voxel pile)
     int32_t *list;       // [nsTot][CGRID_CAP] world-local surface slots, ascending
     int32_t *count;      // [nsTot]; cap + 1 = the list overflowed: the voxel walks the grid itself
     int cap;             // entries per list in use (<= CGRID_CAP)
@@ -91,11 +93,10 @@ template <class R> __global__ void __launch_bounds__(256) k_cgrid_insert(Arrays<
     const StateSet<R> cur = contact_set(A, W);
     const D2 a = cur.pxy[v], b = cur.pzt[v];
     const uint32_t key = cgrid_key(a.x, a.y, b.x, W.invCell);
-    G.key[s] = key;
     G.ref[s] = make_float4((float)a.x, (float)a.y, (float)b.x, 0.f);
     const unsigned long long epoch = (unsigned long long)(uint32_t)W.gEpoch << 32;
     const unsigned long long old = atomicExch(&G.head[W.gridOff + cgrid_hash(key, W.gridLog2)], epoch | (unsigned long long)(uint32_t)i);
-    G.next[s] = (old >> 32) == (epoch >> 32) ? (int)(uint32_t)old : -1;
+    G.link[s] = make_int2((old >> 32) == (epoch >> 32) ? (int)(uint32_t)old : -1, (int)key);
     if (i == 0)
         W.contactRebuilds++;
 }
@@ -119,11 +120,9 @@ template <class R> __global__ void __launch_bounds__(128) k_cgrid_narrow(Arrays<
         return;
     }
     const StateSet<R> cur = contact_set(A, W);
-    const D2 a = cur.pxy[v], b = cur.pzt[v];
-    const short4 c1 = A.lat[v];
+    const short4 c1 = G.slat[s];
     const DVoxMat &m1 = A.vmats[A.vmat[v]];
-    const bool fixed1 = m1.fixed != 0;
-    const uint32_t key = G.key[s];
+    const uint32_t key = (uint32_t)G.link[s].y;
     const int cx = key & 1023, cy = (key >> 10) & 1023, cz = key >> 20;
     int32_t *list = G.list + (size_t)s * CGRID_CAP;
     auto cell_key = [&](int c) {
@@ -133,22 +132,26 @@ template <class R> __global__ void __launch_bounds__(128) k_cgrid_narrow(Arrays<
     auto may_collide = [&](int j) { // not itself, not a lattice neighbour (linked: is_neighbor depth 1), not both Fixed
         if (j == i)
             return false;
-        const int v2 = A.surf[W.soff + j];
-        const short4 c2 = A.lat[v2];
-        return !(abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1 || (fixed1 && A.vmats[A.vmat[v2]].fixed));
+        const short4 c2 = G.slat[W.soff + j];
+        return !(abs(c1.x - c2.x) + abs(c1.y - c2.y) + abs(c1.z - c2.z) == 1 || (c1.w && c2.w));
     };
     if (W.gRebuild) {
-        const double listR2 = W.listR2;
+        // positions as float, as stored at this rebuild, against the list radius padded by 0.1 %: a superset of the exact list (every
+        // listed candidate still goes through the reference's double-precision predicate below, in ascending order)
+        const float listR2 = (float)W.listR2 * 1.002f;
+        const float4 r1 = G.ref[s];
         int n = 0;
         bool overflow = false;
         for (int c = 0; c < 27 && !overflow; c++) {
             const uint32_t k2 = cell_key(c);
-            for (int j = cgrid_first(W, G, k2); j >= 0; j = G.next[W.soff + j]) {
-                if (G.key[W.soff + j] != k2 || !may_collide(j))
+            for (int j = cgrid_first(W, G, k2); j >= 0;) {
+                const int2 lk = G.link[W.soff + j];
+                const float4 r2 = G.ref[W.soff + j];
+                const int jj = j;
+                j = lk.x;
+                if ((uint32_t)lk.y != k2 || !may_collide(jj))
                     continue;
-                const int v2 = A.surf[W.soff + j];
-                const D2 a2 = cur.pxy[v2], b2 = cur.pzt[v2];
-                const double ex = a.x - a2.x, ey = a.y - a2.y, ez = b.x - b2.x;
+                const float ex = r1.x - r2.x, ey = r1.y - r2.y, ez = r1.z - r2.z;
                 if (ex * ex + ey * ey + ez * ez > listR2)
                     continue;
                 if (n == G.cap) {
@@ -156,11 +159,11 @@ template <class R> __global__ void __launch_bounds__(128) k_cgrid_narrow(Arrays<
                     break;
                 }
                 int p = n++; // insertion sort: ascending surface slot = the order in which the all-pairs scan meets them
-                while (p > 0 && list[p - 1] > j) {
+                while (p > 0 && list[p - 1] > jj) {
                     list[p] = list[p - 1];
                     p--;
                 }
-                list[p] = j;
+                list[p] = jj;
             }
         }
         G.count[s] = overflow ? G.cap + 1 : n;
@@ -217,9 +220,12 @@ template <class R> __global__ void __launch_bounds__(128) k_cgrid_narrow(Arrays<
             int best = 0x7fffffff;
             for (int c = 0; c < 27; c++) {
                 const uint32_t k2 = cell_key(c);
-                for (int j = cgrid_first(W, G, k2); j >= 0; j = G.next[W.soff + j])
-                    if (j > last && j < best && G.key[W.soff + j] == k2 && may_collide(j))
+                for (int j = cgrid_first(W, G, k2); j >= 0;) {
+                    const int2 lk = G.link[W.soff + j];
+                    if (j > last && j < best && (uint32_t)lk.y == k2 && may_collide(j))
                         best = j;
+                    j = lk.x;
+                }
             }
             if (best == 0x7fffffff)
                 break;
