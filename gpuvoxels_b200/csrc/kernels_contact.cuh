@@ -142,9 +142,16 @@ template <class R> __global__ void __launch_bounds__(128) k_cgrid_narrow(Arrays<
         const float4 r1 = G.ref[s];
         int n = 0;
         bool overflow = false;
-        for (int c = 0; c < 27 && !overflow; c++) {
+        int first[27]; // the 27 bucket heads first: independent loads, instead of one more hop at the start of every cell's chain
+#pragma unroll
+        for (int c = 0; c < 27; c++)
+            first[c] = cgrid_first(W, G, cell_key(c));
+#pragma unroll
+        for (int c = 0; c < 27; c++) {
+            if (overflow)
+                break;
             const uint32_t k2 = cell_key(c);
-            for (int j = cgrid_first(W, G, k2); j >= 0;) {
+            for (int j = first[c]; j >= 0;) {
                 const int2 lk = G.link[W.soff + j];
                 const float4 r2 = G.ref[W.soff + j];
                 const int jj = j;
