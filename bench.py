@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--path", type=int, default=0, help="0 auto (resident + brick/fused), 1 two-kernel streaming, 2 resident, 3 fused, 5 brick")
     ap.add_argument("--workload", default="xenobot", choices=["xenobot", "cube", "slab", "pile"],
-                    help="xenobot: BASELINE configs[1] (worlds sharded over the GPUs); cube: configs[2] on one GPU; slab: one --cube^3 body cut into --gpus slabs with NCCL halo exchange (configs[4], second part); pile: configs[3], --pile x --pile bodies of 8^3 voxels (plus a second layer) dropped on each other, voxel-voxel contact on")
+                    help="xenobot: BASELINE configs[1] (worlds sharded over the GPUs); cube: configs[2] on one GPU; slab: one --cube^3 body cut into --gpus slabs, halo exchange fused into the step kernel over IPC-mapped peer memory (configs[4], second part; --slab-exchange); pile: configs[3], --pile x --pile bodies of 8^3 voxels (plus a second layer) dropped on each other, voxel-voxel contact on")
     ap.add_argument("--pile", type=int, default=12)
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="engine option (vx3b_ctx_set_option), e.g. contact_skin=0.3")
     ap.add_argument("--verify", action="store_true", help="slab workload: gather the slabs' final state on rank 0 and compare it, bit for bit, with the same body stepped whole on one GPU")
