@@ -252,7 +252,7 @@ def test_a_neighbour_that_never_steps_is_reported_not_hung_on(fused):
     t0 = time.time()
     runners[0].run(5)  # slab 1 never runs
     torch.cuda.synchronize()
-    assert 8 < time.time() - t0 < 25
+    assert 8 < time.time() - t0 < 45  # one 10 s wait, not one per step
     assert runners[0].ctx.halo_timeouts() >= 1
     assert runners[0].ctx.results()[0].steps == 5
     for r in runners:
